@@ -1,0 +1,13 @@
+"""B200-native (sm_100a) DDPM U-Net hot path of Victarry/Image-Generation-models.
+
+Host side: thin PyTorch mirror of the reference's class surface
+(``src/models/ddpm.py``: Unet, GaussianDiffusion, DDPM) that keeps constructor
+signatures, method names and ``state_dict`` keys, and calls the hand-written
+CUDA kernels of ``lib/libigm_b200.so`` through its C ABI (include/igm_b200.h).
+There is no CPU / eager fallback: importing the engine without the built
+library raises.
+"""
+from . import _lib  # noqa: F401
+from .ddpm import DDPM, FusedAdam, GaussianDiffusion, Unet, ValidationResult  # noqa: F401
+
+__all__ = ["Unet", "GaussianDiffusion", "DDPM", "FusedAdam", "ValidationResult"]

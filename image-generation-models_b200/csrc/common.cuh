@@ -1,0 +1,250 @@
+// Shared declarations for libigm_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/igm_b200.h"
+
+namespace igm {
+
+// ---------------------------------------------------------------------------
+// error plumbing: CUDA failures are recorded with file:line and surface as
+// IGM_ERR_CUDA through the C ABI (never abort / throw across the boundary).
+// ---------------------------------------------------------------------------
+struct Status {
+  int code = IGM_OK;
+  std::string msg;
+};
+
+void set_error(Status& st, int code, const char* file, int line, const char* what);
+
+#define IGM_CUDA(st, expr)                                                      \
+  do {                                                                          \
+    cudaError_t _e = (expr);                                                    \
+    if (_e != cudaSuccess) {                                                    \
+      ::igm::set_error((st), IGM_ERR_CUDA, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return (st).code;                                                         \
+    }                                                                           \
+  } while (0)
+
+#define IGM_FAIL(st, errc, what)                                   \
+  do {                                                             \
+    ::igm::set_error((st), (errc), __FILE__, __LINE__, (what));    \
+    return (errc);                                                 \
+  } while (0)
+
+#define IGM_TRY(expr)          \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != IGM_OK) return _r; \
+  } while (0)
+
+// Launch bookkeeping: every kernel launch goes through this so that
+// igm_launch_count() is exact and launch errors are caught where they happen.
+struct LaunchCtx {
+  cudaStream_t stream = 0;
+  Status* st = nullptr;
+  int64_t* counter = nullptr;
+};
+
+inline int post_launch(const LaunchCtx& lc, const char* file, int line) {
+  if (lc.counter) ++*lc.counter;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error(*lc.st, IGM_ERR_CUDA, file, line, cudaGetErrorString(e));
+    return lc.st->code;
+  }
+  return IGM_OK;
+}
+#define IGM_POST_LAUNCH(lc) IGM_TRY(::igm::post_launch((lc), __FILE__, __LINE__))
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+constexpr int kGroups = 8;          // reference ddpm.py:113 / :132-133
+constexpr int kHeads = 4;           // reference ddpm.py:147
+constexpr int kDimHead = 32;        // reference ddpm.py:147
+constexpr float kGnEps = 1e-5f;     // torch.nn.GroupNorm default
+constexpr float kLnEps = 1e-5f;     // reference ddpm.py:86
+constexpr int kGnChunk = 64;        // pixels per GroupNorm partial-statistics chunk
+
+// ---------------------------------------------------------------------------
+// Generic implicit-GEMM convolution (gather form) on NHWC fp32 activations.
+//   out[m, n] = bias[n] + sum_{tap, k} in[pix(m, tap), k] * w[tap][k][n] (+ add[m, n])
+// m enumerates output pixels (b, oy, ox); k runs over the (optionally
+// concatenated) input channels.  Two gather modes cover every conv of the
+// path and its data-gradient:
+//   transposed = 0:  iy = oy*stride - pad + ky*dil         (Conv2d fprop, ConvTranspose2d dgrad)
+//   transposed = 1:  iy = (oy + pad - ky*dil) / stride      (ConvTranspose2d fprop, Conv2d dgrad)
+// ---------------------------------------------------------------------------
+struct ConvArgs {
+  const float* in0 = nullptr;   // [B, IH, IW, C0]
+  const float* in1 = nullptr;   // [B, IH, IW, C1] second source of a channel concat (or null)
+  int C0 = 0, C1 = 0;
+  int B = 0, IH = 0, IW = 0, OH = 0, OW = 0;
+  int N = 0;                    // output channels
+  int KH = 1, KW = 1, stride = 1, pad = 0, dil = 1;
+  int transposed = 0;
+  const float* w = nullptr;     // packed [KH*KW][C0+C1][N]
+  const float* bias = nullptr;  // [N] or null
+  float* out0 = nullptr;        // n <  N0 -> out0[m*N0 + n]
+  float* out1 = nullptr;        // n >= N0 -> out1[m*(N-N0) + n-N0]   (null when N0 == N)
+  int N0 = 0;
+  const float* add0 = nullptr;  // optional addends with the same split
+  const float* add1 = nullptr;
+};
+int launch_conv(const LaunchCtx& lc, const ConvArgs& a);
+
+// Weight gradient of the same convolution family.
+//   g[tap][qc][pc] += sum_pix Q[gather(pix, tap), qc] * P[pix, pc]
+// P is the tensor enumerated pixel by pixel, Q the gathered one
+// (iy = py*stride - pad + ky*dil).  The result is ACCUMULATED (atomicAdd) at
+//   grad[qc*sq + pc*sp + tap]
+// which addresses PyTorch's OIHW (Conv2d) or IOHW (ConvTranspose2d) layouts directly.
+struct WgradArgs {
+  const float* P = nullptr;  int PC = 0, PH = 0, PW = 0;   // [B, PH, PW, PC]
+  const float* Q = nullptr;  int QC = 0, QH = 0, QW = 0;   // [B, QH, QW, QC]
+  int B = 0;
+  int KH = 1, KW = 1, stride = 1, pad = 0, dil = 1;
+  float* grad = nullptr;
+  int64_t sq = 0, sp = 0;
+};
+int launch_wgrad(const LaunchCtx& lc, const WgradArgs& a);
+
+// colsum: out[n] += sum_m x[m, n]   (bias gradients)
+int launch_colsum(const LaunchCtx& lc, const float* x, int64_t M, int N, float* out);
+
+// Weight packing: dst[tap][k][n] = src[k*sk + n*sn + tap]
+int launch_pack_weight(const LaunchCtx& lc, const float* src, float* dst, int taps, int K, int N,
+                       int64_t sk, int64_t sn);
+
+// ---------------------------------------------------------------------------
+// normalisation / activation kernels (norm_act.cu)
+// ---------------------------------------------------------------------------
+// GroupNorm(8) partial statistics: part[b][chunk][g] = (sum, sumsq) over a chunk of kGnChunk pixels.
+int launch_gn_partial(const LaunchCtx& lc, const float* y, int B, int HW, int C, float* part);
+// Finalise statistics (stats[b][g] = mean, rstd), then out = mish(gn(y)) [+ temb[b, c]] [+ res[m, c]].
+// temb has row stride temb_stride.
+int launch_gn_apply(const LaunchCtx& lc, const float* y, const float* part, const float* gamma,
+                    const float* beta, const float* temb, int temb_stride, const float* res,
+                    float* out, float* stats, int B, int HW, int C);
+// Backward of the above.  d_out: grad of `out`.  Produces dy (grad of conv output y),
+// accumulates dgamma/dbeta into the grad arena, and (optionally) dtemb[b, c] (+= over pixels).
+struct GnBwdArgs {
+  const float* d_out; const float* y; const float* stats; const float* gamma; const float* beta;
+  float* dy; float* dgamma; float* dbeta; float* dtemb; int dtemb_stride;
+  float* ws_group;    // [B][chunks][G][2]
+  float* ws_chan;     // [B][chunks][C][3]
+  int B, HW, C;
+};
+int launch_gn_backward(const LaunchCtx& lc, const GnBwdArgs& a);
+
+// Channel LayerNorm of reference ddpm.py:85-95 (eps added to std).  x,out: [M, C]
+int launch_ln_forward(const LaunchCtx& lc, const float* x, const float* g, const float* b, float* out,
+                      int64_t M, int C);
+// dx = d_res + LN'(d_out)  (the Residual branch add is fused); dg/db accumulated via ws partials.
+int launch_ln_backward(const LaunchCtx& lc, const float* d_out, const float* x, const float* g,
+                       const float* d_res, float* dx, float* dg, float* db, float* ws, int64_t M, int C);
+int ln_backward_parts(int64_t M);   // CTAs (= partial rows of ws [parts][2][C]) the backward kernel uses
+
+// ---------------------------------------------------------------------------
+// linear attention (attention.cu) — reference ddpm.py:154-166
+// qkv: [B, n, 384] (q | k | v, each heads*32), out: [B, n, 128]
+// ctx: [B, heads, 32, 32], kstat: [B, heads, 32, 2] (max, sum of exp)
+// ---------------------------------------------------------------------------
+int launch_linattn_forward(const LaunchCtx& lc, const float* qkv, float* out, float* ctx, float* kstat,
+                           int B, int n);
+int launch_linattn_backward(const LaunchCtx& lc, const float* qkv, const float* ctx, const float* kstat,
+                            const float* d_out, float* d_qkv, int B, int n);
+
+// ---------------------------------------------------------------------------
+// time embedding MLP (time_mlp.cu) — reference ddpm.py:47-59, :188-193, :126-130
+// ---------------------------------------------------------------------------
+struct TimeMlpParams {
+  const float* w1; const float* b1;   // [4d, d], [4d]
+  const float* w2; const float* b2;   // [d, 4d], [d]
+  float* gw1; float* gb1; float* gw2; float* gb2;
+  int dim;
+};
+struct TimeProj {                      // one per ResnetBlock: Linear(dim, cout) after Mish
+  const float* w; const float* b; float* gw; float* gb; int cout; int offset;
+};
+// emb:[B,d] h1:[B,4d] (pre-activation) temb:[B,d] act:[B,d]=mish(temb) proj:[B,total]
+int launch_time_mlp_forward(const LaunchCtx& lc, const TimeMlpParams& p, const int64_t* t, int B,
+                            float* emb, float* h1, float* temb, float* act);
+int launch_time_proj_forward(const LaunchCtx& lc, const TimeProj* d_table, int n_proj, const float* act,
+                             int dim, int B, int total, float* proj);
+int launch_time_backward(const LaunchCtx& lc, const TimeMlpParams& p, const TimeProj* d_table, int n_proj,
+                         int total, int B, const float* emb, const float* h1, const float* temb,
+                         const float* act, const float* d_proj, float* ws /* [B, d + 4d + d] */);
+
+// ---------------------------------------------------------------------------
+// boundary + diffusion elementwise (diffusion.cu)
+// ---------------------------------------------------------------------------
+// NCHW -> NHWC with optional q_sample fused: out = a[t_b]*x + s[t_b]*noise (ddpm.py:441-444)
+int launch_input_prep(const LaunchCtx& lc, const float* x_nchw, const float* noise_nchw,
+                      const int64_t* t, const float* sqrt_ac, const float* sqrt_1mac, float* out_nhwc,
+                      float* out_nchw, int B, int C, int HW);
+// final Conv1x1(dim -> C) of ddpm.py:236, writing NCHW.
+int launch_final_conv(const LaunchCtx& lc, const float* act, const float* w, const float* b,
+                      float* out_nchw, int B, int HW, int K, int C);
+// loss = mean |noise - pred| (l1) or mean (noise - pred)^2 (l2); deterministic two-stage reduce.
+int launch_loss(const LaunchCtx& lc, const float* pred, const float* noise, int64_t n, int loss_type,
+                float* ws, float* loss_out);
+// d_pred (written NHWC [B*HW, C]) = scale * dloss/dpred; pred/noise are NCHW with n elements
+int launch_loss_backward_nhwc(const LaunchCtx& lc, const float* pred, const float* noise, int64_t n, int C,
+                              int HW, int loss_type, const float* d_loss, float scale, float* d_nhwc);
+int launch_nchw_to_nhwc(const LaunchCtx& lc, const float* src, float* dst, int B, int HW, int C);
+// fused p_sample tail (ddpm.py:359-364, :385, :367-376, :394-397); t read from *t_dev (int64 [B], uniform)
+struct SamplerStepArgs {
+  float* img;            // [B,C,H,W] in/out
+  const float* eps;      // U-Net output
+  const float* noise;    // injected noise for this step or null
+  const int64_t* t_dev;  // [B] (all equal)
+  const igm_schedule* sched_dev;  // device copy of the pointer table
+  uint64_t seed;
+  const int* step_dev;   // device step counter (for Philox offset)
+  int64_t n; int per_sample; int clip;
+};
+int launch_sampler_update(const LaunchCtx& lc, const SamplerStepArgs& a);
+// t[b] = *t_scalar for all b; then (*t_scalar)--, (*step)++   (device-side loop state for graph replay)
+int launch_sampler_tick(const LaunchCtx& lc, int64_t* t_vec, int B, int* state /* [t, step] */);
+int launch_add(const LaunchCtx& lc, float* dst, const float* src, int64_t n);
+int launch_adam(const LaunchCtx& lc, float* p, const float* g, float* m, float* v, int64_t n, float lr,
+                float b1, float b2, float eps, int step, float grad_scale);
+// NHWC -> NCHW copy (debug taps, d_x)
+int launch_nhwc_to_nchw(const LaunchCtx& lc, const float* src, float* dst, int B, int HW, int C);
+
+// ---------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float softplus_f(float x) {
+  // F.softplus(beta=1, threshold=20): x > 20 -> x, else log1p(exp(x))
+  return x > 20.f ? x : log1pf(expf(x));
+}
+__device__ __forceinline__ float mish_f(float x) { return x * tanhf(softplus_f(x)); }
+__device__ __forceinline__ float mish_grad_f(float x) {
+  // d/dx [x * tanh(sp(x))] = tanh(sp) + x * (1 - tanh(sp)^2) * sp'(x);  sp' = sigmoid (1 above threshold)
+  float sp = softplus_f(x);
+  float th = tanhf(sp);
+  float sg = x > 20.f ? 1.f : 1.f / (1.f + expf(-x));
+  return th + x * (1.f - th * th) * sg;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+#endif
+
+}  // namespace igm

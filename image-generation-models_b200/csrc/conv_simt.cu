@@ -1,0 +1,477 @@
+// Generic fp32 implicit-GEMM convolution family on CUDA cores (NHWC activations).
+//
+// This is the shape-agnostic engine: it serves every convolution of the U-Net
+// that the tcgen05 engine (conv_tc.cu) does not take (C_in = 1/3 stem, stride-2
+// Downsample, 4x4 ConvTranspose2d Upsample and all their gradients), and is the
+// bit-for-bit-fp32 comparator for the tensor-core engine in the tests.
+//
+// Replaces the ATen calls behind reference src/models/ddpm.py:70 (ConvTranspose2d),
+// :79 (Conv2d s2), :116 (Conv2d 3x3), :134/:151/:152 (1x1) and their autograd.
+#include "common.cuh"
+
+namespace igm {
+
+namespace {
+
+constexpr int BM = 128;   // output pixels per CTA
+constexpr int BN = 64;    // output channels per CTA
+constexpr int BK = 16;    // input channels per K step (within one tap)
+constexpr int APAD = 4;
+constexpr int MAX_TAPS = 32;
+
+struct RowCoord {
+  int b, oy, ox;
+  bool valid;
+};
+
+// decode a K-step (tap) into an input coordinate for one output pixel
+__device__ __forceinline__ bool gather_coord(const ConvArgs& a, int oy, int ox, int ky, int kx, int& iy,
+                                             int& ix) {
+  if (!a.transposed) {
+    iy = oy * a.stride - a.pad + ky * a.dil;
+    ix = ox * a.stride - a.pad + kx * a.dil;
+    return iy >= 0 && iy < a.IH && ix >= 0 && ix < a.IW;
+  } else {
+    int ty = oy + a.pad - ky * a.dil;
+    int tx = ox + a.pad - kx * a.dil;
+    if (ty < 0 || tx < 0) return false;
+    if (a.stride > 1 && ((ty % a.stride) != 0 || (tx % a.stride) != 0)) return false;
+    iy = ty / a.stride;
+    ix = tx / a.stride;
+    return iy < a.IH && ix < a.IW;
+  }
+}
+
+// grid: x = M tiles (within a phase), y = N tiles, z = phases (stride^2 for strided transposed mode)
+template <bool VEC>
+__global__ void __launch_bounds__(256) conv_igemm_kernel(const ConvArgs a) {
+  __shared__ __align__(16) float As[2][BK][BM + APAD];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  __shared__ int s_taps[MAX_TAPS];
+  __shared__ int s_ntaps;
+
+  const int tid = threadIdx.x;
+  const int Ctot = a.C0 + a.C1;
+
+  // ---- phase decomposition (only for strided gather-transposed mode) ----
+  const int ps = (a.transposed && a.stride > 1) ? a.stride : 1;
+  const int py = blockIdx.z / ps, px = blockIdx.z % ps;
+  const int OHp = (a.OH - py + ps - 1) / ps;   // rows of this phase
+  const int OWp = (a.OW - px + ps - 1) / ps;
+  const int Mp = a.B * OHp * OWp;
+  const int m0 = blockIdx.x * BM;
+  if (m0 >= Mp) return;
+  const int n0 = blockIdx.y * BN;
+
+  if (tid == 0) {
+    int nt = 0;
+    for (int ky = 0; ky < a.KH; ++ky)
+      for (int kx = 0; kx < a.KW; ++kx) {
+        bool live = true;
+        if (ps > 1) {
+          int ry = ((py + a.pad - ky * a.dil) % ps + ps) % ps;
+          int rx = ((px + a.pad - kx * a.dil) % ps + ps) % ps;
+          live = (ry == 0) && (rx == 0);
+        }
+        if (live) s_taps[nt++] = ky * a.KW + kx;
+      }
+    s_ntaps = nt;
+  }
+  __syncthreads();
+  const int ntaps = s_ntaps;
+  const int nchunks = (Ctot + BK - 1) / BK;
+  const int KT = ntaps * nchunks;
+
+  // ---- per-thread A-load assignment: 2 x (row, 4 channels) ----
+  RowCoord rc[2];
+  int rrow[2], rc4[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int idx = tid + i * 256;
+    rrow[i] = idx >> 2;
+    rc4[i] = idx & 3;
+    int m = m0 + rrow[i];
+    rc[i].valid = m < Mp;
+    int mm = rc[i].valid ? m : 0;
+    int b = mm / (OHp * OWp);
+    int r = mm - b * (OHp * OWp);
+    int oyp = r / OWp;
+    int oxp = r - oyp * OWp;
+    rc[i].b = b;
+    rc[i].oy = oyp * ps + py;
+    rc[i].ox = oxp * ps + px;
+  }
+  // B-load assignment: row k = tid / 16, 4 columns at (tid % 16) * 4
+  const int bk = tid >> 4, bn4 = (tid & 15) * 4;
+
+  float4 ra[2];
+  float4 rb;
+
+  auto load_tile = [&](int kt) {
+    const int ti = kt / nchunks;
+    const int ch = kt - ti * nchunks;
+    const int tap = s_taps[ti];
+    const int ky = tap / a.KW, kx = tap - ky * a.KW;
+    const int c0 = ch * BK;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      int iy, ix;
+      if (rc[i].valid && gather_coord(a, rc[i].oy, rc[i].ox, ky, kx, iy, ix)) {
+        const int c = c0 + rc4[i] * 4;
+        const int64_t pix = ((int64_t)rc[i].b * a.IH + iy) * a.IW + ix;
+        if (VEC) {
+          if (c < a.C0)
+            v = __ldg(reinterpret_cast<const float4*>(a.in0 + pix * a.C0 + c));
+          else if (c < Ctot)
+            v = __ldg(reinterpret_cast<const float4*>(a.in1 + pix * a.C1 + (c - a.C0)));
+        } else {
+          float t[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            int cj = c + j;
+            t[j] = 0.f;
+            if (cj < a.C0)
+              t[j] = __ldg(a.in0 + pix * a.C0 + cj);
+            else if (cj < Ctot)
+              t[j] = __ldg(a.in1 + pix * a.C1 + (cj - a.C0));
+          }
+          v = make_float4(t[0], t[1], t[2], t[3]);
+        }
+      }
+      ra[i] = v;
+    }
+    {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int k = c0 + bk;
+      const int n = n0 + bn4;
+      if (k < Ctot) {
+        const float* wp = a.w + ((int64_t)tap * Ctot + k) * a.N + n;
+        if (VEC) {
+          if (n < a.N) v = __ldg(reinterpret_cast<const float4*>(wp));
+        } else {
+          float t[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) t[j] = (n + j < a.N) ? __ldg(wp + j) : 0.f;
+          v = make_float4(t[0], t[1], t[2], t[3]);
+        }
+      }
+      rb = v;
+    }
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int k = rc4[i] * 4;
+      As[buf][k + 0][rrow[i]] = ra[i].x;
+      As[buf][k + 1][rrow[i]] = ra[i].y;
+      As[buf][k + 2][rrow[i]] = ra[i].z;
+      As[buf][k + 3][rrow[i]] = ra[i].w;
+    }
+    *reinterpret_cast<float4*>(&Bs[buf][bk][bn4]) = rb;
+  };
+
+  const int tn = tid & 15;   // 16 x 4 columns
+  const int tm = tid >> 4;   // 16 x 8 rows
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  if (KT > 0) {
+    load_tile(0);
+    store_tile(0);
+  }
+  __syncthreads();
+  for (int kt = 0; kt < KT; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < KT) load_tile(kt + 1);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][tm * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][tm * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tn * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < KT) store_tile(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ---- epilogue: + bias, + addend, split store ----
+  const int n = n0 + tn * 4;
+  if (n >= a.N) return;
+  float bias[4] = {0.f, 0.f, 0.f, 0.f};
+  if (a.bias) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (n + j < a.N) bias[j] = __ldg(a.bias + n + j);
+  }
+  const int N1 = a.N - a.N0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + tm * 8 + i;
+    if (m >= Mp) continue;
+    // map phase-local m back to the dense output pixel index
+    int64_t opix;
+    if (ps == 1) {
+      opix = m;
+    } else {
+      int b = m / (OHp * OWp);
+      int r = m - b * (OHp * OWp);
+      int oyp = r / OWp, oxp = r - oyp * OWp;
+      opix = ((int64_t)b * a.OH + (oyp * ps + py)) * a.OW + (oxp * ps + px);
+    }
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + bias[j];
+    if (VEC) {
+      // N0 and N are multiples of 4 on this path, so a float4 never straddles the split
+      if (n < a.N0) {
+        float* o = a.out0 + opix * a.N0 + n;
+        if (a.add0) {
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(a.add0 + opix * a.N0 + n));
+          v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+        }
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+        float* o = a.out1 + opix * N1 + (n - a.N0);
+        if (a.add1) {
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(a.add1 + opix * N1 + (n - a.N0)));
+          v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+        }
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int nj = n + j;
+        if (nj >= a.N) break;
+        if (nj < a.N0) {
+          float r = a.add0 ? __ldg(a.add0 + opix * a.N0 + nj) : 0.f;
+          a.out0[opix * a.N0 + nj] = v[j] + r;
+        } else {
+          float r = a.add1 ? __ldg(a.add1 + opix * N1 + (nj - a.N0)) : 0.f;
+          a.out1[opix * N1 + (nj - a.N0)] = v[j] + r;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// wgrad: G[tap][qc][pc] = sum_pix Q[gather(pix,tap), qc] * P[pix, pc]
+// CTA tile: 64 (qc) x 64 (pc), K step = 16 pixels, split-K over pixel ranges.
+// grid: x = split, y = qc tiles * pc tiles, z = tap
+// ---------------------------------------------------------------------------
+constexpr int WB = 64;
+constexpr int WK = 16;
+
+template <bool QVEC, bool PVEC>
+__global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a, int pix_per_split, int p_tiles) {
+  __shared__ __align__(16) float Qs[2][WK][WB];
+  __shared__ __align__(16) float Ps[2][WK][WB];
+  const int tid = threadIdx.x;
+  const int tap = blockIdx.z;
+  const int ky = tap / a.KW, kx = tap - ky * a.KW;
+  const int qt = blockIdx.y / p_tiles, pt = blockIdx.y - qt * p_tiles;
+  const int q0 = qt * WB, p0 = pt * WB;
+  const int64_t npix = (int64_t)a.B * a.PH * a.PW;
+  const int64_t pix_begin = (int64_t)blockIdx.x * pix_per_split;
+  int64_t pix_end = pix_begin + pix_per_split;
+  if (pix_end > npix) pix_end = npix;
+  if (pix_begin >= pix_end) return;
+  const int KT = (int)((pix_end - pix_begin + WK - 1) / WK);
+
+  // loader: pixel row lr = tid / 16, 4 channels at lc4 = (tid % 16) * 4
+  const int lr = tid >> 4, lc4 = (tid & 15) * 4;
+  float4 rq, rp;
+  auto load_tile = [&](int kt) {
+    const int64_t pix = pix_begin + (int64_t)kt * WK + lr;
+    rq = make_float4(0.f, 0.f, 0.f, 0.f);
+    rp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pix < pix_end) {
+      const int b = (int)(pix / (a.PH * a.PW));
+      const int r = (int)(pix - (int64_t)b * a.PH * a.PW);
+      const int y = r / a.PW, x = r - y * a.PW;
+      {
+        const int c = p0 + lc4;
+        const float* src = a.P + pix * a.PC + c;
+        if (PVEC) {
+          if (c < a.PC) rp = __ldg(reinterpret_cast<const float4*>(src));
+        } else {
+          float t[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) t[j] = (c + j < a.PC) ? __ldg(src + j) : 0.f;
+          rp = make_float4(t[0], t[1], t[2], t[3]);
+        }
+      }
+      const int iy = y * a.stride - a.pad + ky * a.dil;
+      const int ix = x * a.stride - a.pad + kx * a.dil;
+      if (iy >= 0 && iy < a.QH && ix >= 0 && ix < a.QW) {
+        const int c = q0 + lc4;
+        const float* src = a.Q + (((int64_t)b * a.QH + iy) * a.QW + ix) * a.QC + c;
+        if (QVEC) {
+          if (c < a.QC) rq = __ldg(reinterpret_cast<const float4*>(src));
+        } else {
+          float t[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) t[j] = (c + j < a.QC) ? __ldg(src + j) : 0.f;
+          rq = make_float4(t[0], t[1], t[2], t[3]);
+        }
+      }
+    }
+  };
+  auto store_tile = [&](int buf) {
+    *reinterpret_cast<float4*>(&Qs[buf][lr][lc4]) = rq;
+    *reinterpret_cast<float4*>(&Ps[buf][lr][lc4]) = rp;
+  };
+
+  const int tq = tid >> 4, tp = tid & 15;   // 16 x 16 threads, 4 x 4 outputs each
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  load_tile(0);
+  store_tile(0);
+  __syncthreads();
+  for (int kt = 0; kt < KT; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < KT) load_tile(kt + 1);
+#pragma unroll
+    for (int k = 0; k < WK; ++k) {
+      const float4 q = *reinterpret_cast<const float4*>(&Qs[buf][k][tq * 4]);
+      const float4 p = *reinterpret_cast<const float4*>(&Ps[buf][k][tp * 4]);
+      const float qv[4] = {q.x, q.y, q.z, q.w};
+      const float pv[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(qv[i], pv[j], acc[i][j]);
+    }
+    if (kt + 1 < KT) store_tile(buf ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int qc = q0 + tq * 4 + i;
+    if (qc >= a.QC) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pc = p0 + tp * 4 + j;
+      if (pc >= a.PC) continue;
+      atomicAdd(a.grad + qc * a.sq + pc * a.sp + tap, acc[i][j]);
+    }
+  }
+}
+
+// out[n] += sum_m x[m, n]; grid.x = row splits; block (32 x 8): 32 columns x 8 row lanes
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int64_t M, int N,
+                                                     float* __restrict__ out, int rows_per_cta) {
+  __shared__ float red[8][33];
+  const int col = blockIdx.y * 32 + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  int64_t r1 = r0 + rows_per_cta;
+  if (r1 > M) r1 = M;
+  float s = 0.f;
+  if (col < N)
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) s += __ldg(x + r * N + col);
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    atomicAdd(out + col, t);
+  }
+}
+
+__global__ void pack_weight_kernel(const float* __restrict__ src, float* __restrict__ dst, int taps, int K,
+                                   int N, int64_t sk, int64_t sn) {
+  const int64_t total = (int64_t)taps * K * N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i % N);
+    const int64_t r = i / N;
+    const int k = (int)(r % K);
+    const int tap = (int)(r / K);
+    dst[i] = src[k * sk + n * sn + tap];
+  }
+}
+
+}  // namespace
+
+int launch_conv(const LaunchCtx& lc, const ConvArgs& a) {
+  const int Ctot = a.C0 + a.C1;
+  if (a.KH * a.KW > MAX_TAPS) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "conv: too many taps");
+  if (a.N0 <= 0 || a.N0 > a.N || (a.N0 < a.N && !a.out1))
+    IGM_FAIL(*lc.st, IGM_ERR_INVALID, "conv: bad output split");
+  const int ps = (a.transposed && a.stride > 1) ? a.stride : 1;
+  const int OHp = cdiv(a.OH, ps), OWp = cdiv(a.OW, ps);
+  const int64_t Mp = (int64_t)a.B * OHp * OWp;
+  dim3 grid((unsigned)cdiv64(Mp, BM), (unsigned)cdiv(a.N, BN), (unsigned)(ps * ps));
+  const bool vec = (a.C0 % BK == 0) && (a.C1 % BK == 0) && (a.N % 4 == 0) && (a.N0 % 4 == 0) && Ctot > 0;
+  if (vec)
+    conv_igemm_kernel<true><<<grid, 256, 0, lc.stream>>>(a);
+  else
+    conv_igemm_kernel<false><<<grid, 256, 0, lc.stream>>>(a);
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+int launch_wgrad(const LaunchCtx& lc, const WgradArgs& a) {
+  const int64_t npix = (int64_t)a.B * a.PH * a.PW;
+  const int q_tiles = cdiv(a.QC, WB), p_tiles = cdiv(a.PC, WB);
+  const int taps = a.KH * a.KW;
+  // aim for ~4 CTAs per SM in total
+  int64_t base = (int64_t)q_tiles * p_tiles * taps;
+  int split = (int)((148 * 4 + base - 1) / base);
+  int64_t max_split = cdiv64(npix, 256);
+  if (split > max_split) split = (int)max_split;
+  if (split < 1) split = 1;
+  int pix_per_split = (int)cdiv64(npix, split);
+  pix_per_split = cdiv(pix_per_split, WK) * WK;
+  split = (int)cdiv64(npix, pix_per_split);
+  dim3 grid((unsigned)split, (unsigned)(q_tiles * p_tiles), (unsigned)taps);
+  const bool qv = a.QC % 4 == 0, pv = a.PC % 4 == 0;
+  if (qv && pv)
+    wgrad_kernel<true, true><<<grid, 256, 0, lc.stream>>>(a, pix_per_split, p_tiles);
+  else if (qv)
+    wgrad_kernel<true, false><<<grid, 256, 0, lc.stream>>>(a, pix_per_split, p_tiles);
+  else if (pv)
+    wgrad_kernel<false, true><<<grid, 256, 0, lc.stream>>>(a, pix_per_split, p_tiles);
+  else
+    wgrad_kernel<false, false><<<grid, 256, 0, lc.stream>>>(a, pix_per_split, p_tiles);
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+int launch_colsum(const LaunchCtx& lc, const float* x, int64_t M, int N, float* out) {
+  int splits = (int)cdiv64(M, 512);
+  if (splits > 148 * 2) splits = 148 * 2;
+  if (splits < 1) splits = 1;
+  const int rows = (int)cdiv64(M, splits);
+  dim3 grid((unsigned)cdiv64(M, rows), (unsigned)cdiv(N, 32));
+  colsum_kernel<<<grid, dim3(32, 8), 0, lc.stream>>>(x, M, N, out, rows);
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+int launch_pack_weight(const LaunchCtx& lc, const float* src, float* dst, int taps, int K, int N,
+                       int64_t sk, int64_t sn) {
+  const int64_t total = (int64_t)taps * K * N;
+  int blocks = (int)cdiv64(total, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  pack_weight_kernel<<<blocks, 256, 0, lc.stream>>>(src, dst, taps, K, N, sk, sn);
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+}  // namespace igm

@@ -1,0 +1,509 @@
+// GroupNorm(8)+Mish(+time-embedding add)(+residual) and the channel LayerNorm of the
+// reference U-Net, forward and backward.  All HBM-bound: 128-bit NHWC loads,
+// warp-shuffle reductions, deterministic (no float atomics on statistics).
+//
+// Replaces: nn.GroupNorm + Mish in Block (reference src/models/ddpm.py:116, :62-64),
+// the `h += mlp(time_emb)[:, :, None, None]` add (:140), the residual add (:143),
+// LayerNorm (:85-95) and their autograd.
+#include "common.cuh"
+
+namespace igm {
+namespace {
+
+// Thread layout shared by the GroupNorm kernels: L = C/4 lanes per pixel (one
+// float4 of channels each), PPI = 256/L pixels in flight per iteration.
+// Requires C % 32 == 0 (so a float4 never straddles a group) and C <= 1024.
+struct GnLayout {
+  int L, PPI, c4, pslot, cpg, lpg, group;
+  __device__ GnLayout(int C) {
+    L = C >> 2;
+    PPI = 256 / L;
+    c4 = threadIdx.x % L;
+    pslot = threadIdx.x / L;
+    cpg = C / kGroups;
+    lpg = cpg >> 2;
+    group = c4 / lpg;
+  }
+};
+
+// Deterministic per-group reduction of one (a, b) pair per thread.
+// Exactly 32 threads belong to each group (lpg * PPI == 32): warp g reduces group g.
+__device__ __forceinline__ void group_reduce2(const GnLayout& ly, float a, float b, float (*sm)[2],
+                                              float& ra, float& rb) {
+  sm[threadIdx.x][0] = a;
+  sm[threadIdx.x][1] = b;
+  __syncthreads();
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int src = (lane / ly.lpg) * ly.L + w * ly.lpg + (lane % ly.lpg);
+  ra = warp_sum(sm[src][0]);
+  rb = warp_sum(sm[src][1]);
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict__ y, int HW, int C,
+                                                         int nchunks, float* __restrict__ part) {
+  __shared__ float sm[256][2];
+  const GnLayout ly(C);
+  const int b = blockIdx.x / nchunks, chunk = blockIdx.x % nchunks;
+  const int p0 = chunk * kGnChunk;
+  const int p1 = min(p0 + kGnChunk, HW);
+  float s = 0.f, ss = 0.f;
+  const float* base = y + ((int64_t)b * HW) * C + ly.c4 * 4;
+  for (int p = p0 + ly.pslot; p < p1; p += ly.PPI) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(base + (int64_t)p * C));
+    s += (v.x + v.y) + (v.z + v.w);
+    ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  float rs, rss;
+  group_reduce2(ly, s, ss, sm, rs, rss);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    float* o = part + (((int64_t)b * nchunks + chunk) * kGroups + w) * 2;
+    o[0] = rs;
+    o[1] = rss;
+  }
+}
+
+// mean / rstd of sample b, group g from the chunk partials (fp64 combine)
+__device__ __forceinline__ void finalize_stats(const float* part, int b, int nchunks, int g, int count,
+                                               float& mean, float& rstd) {
+  double s = 0.0, ss = 0.0;
+  for (int c = 0; c < nchunks; ++c) {
+    const float* o = part + (((int64_t)b * nchunks + c) * kGroups + g) * 2;
+    s += (double)o[0];
+    ss += (double)o[1];
+  }
+  const double m = s / count;
+  double var = ss / count - m * m;
+  if (var < 0.0) var = 0.0;
+  mean = (float)m;
+  rstd = (float)(1.0 / sqrt(var + (double)kGnEps));
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ y, const float* __restrict__ part,
+                                                       const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta,
+                                                       const float* __restrict__ temb, int temb_stride,
+                                                       const float* __restrict__ res, float* __restrict__ out,
+                                                       float* __restrict__ stats, int HW, int C, int nchunks) {
+  __shared__ float s_mean[kGroups], s_rstd[kGroups];
+  const GnLayout ly(C);
+  const int b = blockIdx.x / nchunks, chunk = blockIdx.x % nchunks;
+  if (threadIdx.x < kGroups) {
+    float m, r;
+    finalize_stats(part, b, nchunks, threadIdx.x, HW * ly.cpg, m, r);
+    s_mean[threadIdx.x] = m;
+    s_rstd[threadIdx.x] = r;
+    if (chunk == 0 && stats) {
+      stats[((int64_t)b * kGroups + threadIdx.x) * 2 + 0] = m;
+      stats[((int64_t)b * kGroups + threadIdx.x) * 2 + 1] = r;
+    }
+  }
+  __syncthreads();
+  const float mean = s_mean[ly.group], rstd = s_rstd[ly.group];
+  const int c = ly.c4 * 4;
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+  const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+  float4 te = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (temb) te = __ldg(reinterpret_cast<const float4*>(temb + (int64_t)b * temb_stride + c));
+  const int p0 = chunk * kGnChunk;
+  const int p1 = min(p0 + kGnChunk, HW);
+  for (int p = p0 + ly.pslot; p < p1; p += ly.PPI) {
+    const int64_t off = ((int64_t)b * HW + p) * C + c;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(y + off));
+    float4 o;
+    o.x = mish_f((v.x - mean) * rstd * ga.x + be.x) + te.x;
+    o.y = mish_f((v.y - mean) * rstd * ga.y + be.y) + te.y;
+    o.z = mish_f((v.z - mean) * rstd * ga.z + be.z) + te.z;
+    o.w = mish_f((v.w - mean) * rstd * ga.w + be.w) + te.w;
+    if (res) {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(res + off));
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    *reinterpret_cast<float4*>(out + off) = o;
+  }
+}
+
+// ---- backward, pass 1: per-chunk reductions ---------------------------------
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdArgs a, int nchunks) {
+  __shared__ float sm[256][2];
+  __shared__ float4 sc[256][3];
+  const GnLayout ly(a.C);
+  const int b = blockIdx.x / nchunks, chunk = blockIdx.x % nchunks;
+  const float mean = __ldg(a.stats + ((int64_t)b * kGroups + ly.group) * 2 + 0);
+  const float rstd = __ldg(a.stats + ((int64_t)b * kGroups + ly.group) * 2 + 1);
+  const int c = ly.c4 * 4;
+  const float4 ga4 = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
+  const float4 be4 = __ldg(reinterpret_cast<const float4*>(a.beta + c));
+  const float ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w};
+  const float be[4] = {be4.x, be4.y, be4.z, be4.w};
+  float dgam[4] = {0.f, 0.f, 0.f, 0.f}, dbet[4] = {0.f, 0.f, 0.f, 0.f}, dte[4] = {0.f, 0.f, 0.f, 0.f};
+  float s1 = 0.f, s2 = 0.f;
+  const int p0 = chunk * kGnChunk;
+  const int p1 = min(p0 + kGnChunk, a.HW);
+  for (int p = p0 + ly.pslot; p < p1; p += ly.PPI) {
+    const int64_t off = ((int64_t)b * a.HW + p) * a.C + c;
+    const float4 y4 = __ldg(reinterpret_cast<const float4*>(a.y + off));
+    const float4 d4 = __ldg(reinterpret_cast<const float4*>(a.d_out + off));
+    const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+    const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float n = (yv[j] - mean) * rstd;
+      const float g = n * ga[j] + be[j];
+      const float dg = dv[j] * mish_grad_f(g);
+      dgam[j] += dg * n;
+      dbet[j] += dg;
+      dte[j] += dv[j];
+      const float dn = dg * ga[j];
+      s1 += dn;
+      s2 += dn * n;
+    }
+  }
+  float r1, r2;
+  group_reduce2(ly, s1, s2, sm, r1, r2);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    float* o = a.ws_group + (((int64_t)b * nchunks + chunk) * kGroups + w) * 2;
+    o[0] = r1;
+    o[1] = r2;
+  }
+  // per-channel partials: reduce over the PPI pixel slots in a fixed order
+  sc[threadIdx.x][0] = make_float4(dgam[0], dgam[1], dgam[2], dgam[3]);
+  sc[threadIdx.x][1] = make_float4(dbet[0], dbet[1], dbet[2], dbet[3]);
+  sc[threadIdx.x][2] = make_float4(dte[0], dte[1], dte[2], dte[3]);
+  __syncthreads();
+  if (threadIdx.x < ly.L) {
+    float4 acc[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < ly.PPI; ++s) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float4 v = sc[s * ly.L + threadIdx.x][k];
+        acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+      }
+    }
+    // ws_chan layout: [b][chunk][3][C]
+    float* o = a.ws_chan + ((int64_t)b * nchunks + chunk) * 3 * a.C + threadIdx.x * 4;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) *reinterpret_cast<float4*>(o + (int64_t)k * a.C) = acc[k];
+  }
+}
+
+// ---- backward, pass 2: dy ------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a, int nchunks) {
+  __shared__ float s_m1[kGroups], s_m2[kGroups];
+  const GnLayout ly(a.C);
+  const int b = blockIdx.x / nchunks, chunk = blockIdx.x % nchunks;
+  if (threadIdx.x < kGroups) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int c = 0; c < nchunks; ++c) {
+      const float* o = a.ws_group + (((int64_t)b * nchunks + c) * kGroups + threadIdx.x) * 2;
+      s1 += (double)o[0];
+      s2 += (double)o[1];
+    }
+    const double cnt = (double)a.HW * ly.cpg;
+    s_m1[threadIdx.x] = (float)(s1 / cnt);
+    s_m2[threadIdx.x] = (float)(s2 / cnt);
+  }
+  __syncthreads();
+  const float mean = __ldg(a.stats + ((int64_t)b * kGroups + ly.group) * 2 + 0);
+  const float rstd = __ldg(a.stats + ((int64_t)b * kGroups + ly.group) * 2 + 1);
+  const float m1 = s_m1[ly.group], m2 = s_m2[ly.group];
+  const int c = ly.c4 * 4;
+  const float4 ga4 = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
+  const float4 be4 = __ldg(reinterpret_cast<const float4*>(a.beta + c));
+  const float ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w};
+  const float be[4] = {be4.x, be4.y, be4.z, be4.w};
+  const int p0 = chunk * kGnChunk;
+  const int p1 = min(p0 + kGnChunk, a.HW);
+  for (int p = p0 + ly.pslot; p < p1; p += ly.PPI) {
+    const int64_t off = ((int64_t)b * a.HW + p) * a.C + c;
+    const float4 y4 = __ldg(reinterpret_cast<const float4*>(a.y + off));
+    const float4 d4 = __ldg(reinterpret_cast<const float4*>(a.d_out + off));
+    const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+    const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float n = (yv[j] - mean) * rstd;
+      const float g = n * ga[j] + be[j];
+      const float dn = dv[j] * mish_grad_f(g) * ga[j];
+      o[j] = rstd * (dn - m1 - n * m2);
+    }
+    *reinterpret_cast<float4*>(a.dy + off) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---- backward, pass 3: parameter / time-embedding gradients -------------------
+// block (32, 8); grid.x = C/32 column slabs
+__global__ void __launch_bounds__(256) gn_bwd_param_kernel(const GnBwdArgs a, int nchunks) {
+  __shared__ float red[8][2][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int entries = a.B * nchunks;
+  float sg = 0.f, sb = 0.f;
+  if (c < a.C) {
+    for (int e = threadIdx.y; e < entries; e += 8) {
+      const float* o = a.ws_chan + (int64_t)e * 3 * a.C;
+      sg += o[c];
+      sb += o[a.C + c];
+    }
+  }
+  red[threadIdx.y][0][threadIdx.x] = sg;
+  red[threadIdx.y][1][threadIdx.x] = sb;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < a.C) {
+    float tg = 0.f, tb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      tg += red[i][0][threadIdx.x];
+      tb += red[i][1][threadIdx.x];
+    }
+    a.dgamma[c] += tg;   // unique writer per channel
+    a.dbeta[c] += tb;
+  }
+  if (a.dtemb && c < a.C) {
+    for (int b = threadIdx.y; b < a.B; b += 8) {
+      float t = 0.f;
+      for (int ch = 0; ch < nchunks; ++ch) t += a.ws_chan[((int64_t)b * nchunks + ch) * 3 * a.C + 2 * a.C + c];
+      a.dtemb[(int64_t)b * a.dtemb_stride + c] = t;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// LayerNorm over channels, one warp per pixel
+// ---------------------------------------------------------------------------
+constexpr int LN_MAX_V = 8;   // C <= 1024
+
+__global__ void __launch_bounds__(256) ln_forward_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                         const float* __restrict__ bta, float* __restrict__ out,
+                                                         int64_t M, int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int nv = C >> 2;
+  for (int64_t m = warp; m < M; m += nwarps) {
+    float4 v[LN_MAX_V];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAX_V; ++j) {
+      const int c4 = lane + j * 32;
+      if (c4 < nv) {
+        v[j] = __ldg(reinterpret_cast<const float4*>(x + m * C + c4 * 4));
+        s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+      }
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAX_V; ++j) {
+      const int c4 = lane + j * 32;
+      if (c4 < nv) {
+        v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+        q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+      }
+    }
+    const float stdv = sqrtf(warp_sum(q) / C);
+    const float inv = 1.f / (stdv + kLnEps);
+#pragma unroll
+    for (int j = 0; j < LN_MAX_V; ++j) {
+      const int c4 = lane + j * 32;
+      if (c4 < nv) {
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c4 * 4));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(bta + c4 * 4));
+        float4 o;
+        o.x = v[j].x * inv * gg.x + bb.x;
+        o.y = v[j].y * inv * gg.y + bb.y;
+        o.z = v[j].z * inv * gg.z + bb.z;
+        o.w = v[j].w * inv * gg.w + bb.w;
+        *reinterpret_cast<float4*>(out + m * C + c4 * 4) = o;
+      }
+    }
+  }
+}
+
+// ws: [gridDim.x][2][C] per-CTA partial (dg, db)
+__global__ void __launch_bounds__(256) ln_backward_kernel(const float* __restrict__ d_out,
+                                                          const float* __restrict__ x,
+                                                          const float* __restrict__ g,
+                                                          const float* __restrict__ d_res,
+                                                          float* __restrict__ dx, float* __restrict__ ws,
+                                                          int64_t M, int C) {
+  extern __shared__ float sred[];   // [8 warps][2][C]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  const int nv = C >> 2;
+  float4 adg[LN_MAX_V], adb[LN_MAX_V];
+#pragma unroll
+  for (int j = 0; j < LN_MAX_V; ++j) {
+    adg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    adb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int64_t m = warp; m < M; m += nwarps) {
+    float4 v[LN_MAX_V], d[LN_MAX_V];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAX_V; ++j) {
+      const int c4 = lane + j * 32;
+      if (c4 < nv) {
+        v[j] = __ldg(reinterpret_cast<const float4*>(x + m * C + c4 * 4));
+        d[j] = __ldg(reinterpret_cast<const float4*>(d_out + m * C + c4 * 4));
+        s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+      }
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAX_V; ++j) {
+      const int c4 = lane + j * 32;
+      if (c4 < nv) {
+        v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+        q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+      }
+    }
+    const float stdv = sqrtf(warp_sum(q) / C);
+    const float sdn = stdv + kLnEps;
+    const float inv = 1.f / sdn;
+    // dn = d_out * g ; accumulate param grads ; sums for dx
+    float sdnv = 0.f, sdnx = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAX_V; ++j) {
+      const int c4 = lane + j * 32;
+      if (c4 < nv) {
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c4 * 4));
+        adg[j].x += d[j].x * v[j].x * inv; adg[j].y += d[j].y * v[j].y * inv;
+        adg[j].z += d[j].z * v[j].z * inv; adg[j].w += d[j].w * v[j].w * inv;
+        adb[j].x += d[j].x; adb[j].y += d[j].y; adb[j].z += d[j].z; adb[j].w += d[j].w;
+        d[j].x *= gg.x; d[j].y *= gg.y; d[j].z *= gg.z; d[j].w *= gg.w;
+        sdnv += (d[j].x + d[j].y) + (d[j].z + d[j].w);
+        sdnx += (d[j].x * v[j].x + d[j].y * v[j].y) + (d[j].z * v[j].z + d[j].w * v[j].w);
+      }
+    }
+    sdnv = warp_sum(sdnv);
+    sdnx = warp_sum(sdnx);
+    const float k1 = sdnv / (C * sdn);
+    const float k2 = sdnx / ((float)C * fmaxf(stdv, 1e-30f) * sdn * sdn);
+#pragma unroll
+    for (int j = 0; j < LN_MAX_V; ++j) {
+      const int c4 = lane + j * 32;
+      if (c4 < nv) {
+        float4 o;
+        o.x = d[j].x * inv - k1 - v[j].x * k2;
+        o.y = d[j].y * inv - k1 - v[j].y * k2;
+        o.z = d[j].z * inv - k1 - v[j].z * k2;
+        o.w = d[j].w * inv - k1 - v[j].w * k2;
+        if (d_res) {
+          const float4 r = __ldg(reinterpret_cast<const float4*>(d_res + m * C + c4 * 4));
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        *reinterpret_cast<float4*>(dx + m * C + c4 * 4) = o;
+      }
+    }
+  }
+  // CTA-level reduce of parameter partials over the 8 warps (fixed order)
+#pragma unroll
+  for (int j = 0; j < LN_MAX_V; ++j) {
+    const int c4 = lane + j * 32;
+    if (c4 < nv) {
+      *reinterpret_cast<float4*>(&sred[(wib * 2 + 0) * C + c4 * 4]) = adg[j];
+      *reinterpret_cast<float4*>(&sred[(wib * 2 + 1) * C + c4 * 4]) = adb[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    const int which = i / C, c = i - which * C;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sred[(w * 2 + which) * C + c];
+    ws[((int64_t)blockIdx.x * 2 + which) * C + c] = t;
+  }
+}
+
+__global__ void ln_param_finalize_kernel(const float* __restrict__ ws, int nparts, int C, float* __restrict__ dg,
+                                         float* __restrict__ db) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float tg = 0.f, tb = 0.f;
+  for (int p = 0; p < nparts; ++p) {
+    tg += ws[((int64_t)p * 2 + 0) * C + c];
+    tb += ws[((int64_t)p * 2 + 1) * C + c];
+  }
+  dg[c] += tg;
+  db[c] += tb;
+}
+
+}  // namespace
+
+static int check_gn_shape(const LaunchCtx& lc, int C) {
+  if (C % 32 != 0 || C > 1024 || C < 32) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "GroupNorm: C must be a multiple of 32 in [32, 1024]");
+  return IGM_OK;
+}
+
+int launch_gn_partial(const LaunchCtx& lc, const float* y, int B, int HW, int C, float* part) {
+  IGM_TRY(check_gn_shape(lc, C));
+  const int nchunks = cdiv(HW, kGnChunk);
+  gn_partial_kernel<<<B * nchunks, 256, 0, lc.stream>>>(y, HW, C, nchunks, part);
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+int launch_gn_apply(const LaunchCtx& lc, const float* y, const float* part, const float* gamma,
+                    const float* beta, const float* temb, int temb_stride, const float* res, float* out,
+                    float* stats, int B, int HW, int C) {
+  IGM_TRY(check_gn_shape(lc, C));
+  const int nchunks = cdiv(HW, kGnChunk);
+  gn_apply_kernel<<<B * nchunks, 256, 0, lc.stream>>>(y, part, gamma, beta, temb, temb_stride, res, out,
+                                                      stats, HW, C, nchunks);
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+int launch_gn_backward(const LaunchCtx& lc, const GnBwdArgs& a) {
+  IGM_TRY(check_gn_shape(lc, a.C));
+  const int nchunks = cdiv(a.HW, kGnChunk);
+  gn_bwd_reduce_kernel<<<a.B * nchunks, 256, 0, lc.stream>>>(a, nchunks);
+  IGM_POST_LAUNCH(lc);
+  gn_bwd_apply_kernel<<<a.B * nchunks, 256, 0, lc.stream>>>(a, nchunks);
+  IGM_POST_LAUNCH(lc);
+  gn_bwd_param_kernel<<<cdiv(a.C, 32), dim3(32, 8), 0, lc.stream>>>(a, nchunks);
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+static int ln_grid(int64_t M) {
+  int64_t g = cdiv64(M, 8 * 4);
+  if (g > 148 * 8) g = 148 * 8;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+int launch_ln_forward(const LaunchCtx& lc, const float* x, const float* g, const float* b, float* out,
+                      int64_t M, int C) {
+  if (C % 4 != 0 || C > 1024) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "LayerNorm: C must be a multiple of 4, <= 1024");
+  ln_forward_kernel<<<ln_grid(M), 256, 0, lc.stream>>>(x, g, b, out, M, C);
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+int ln_backward_parts(int64_t M) { return ln_grid(M); }
+
+int launch_ln_backward(const LaunchCtx& lc, const float* d_out, const float* x, const float* g,
+                       const float* d_res, float* dx, float* dg, float* db, float* ws, int64_t M, int C) {
+  if (C % 4 != 0 || C > 1024) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "LayerNorm: C must be a multiple of 4, <= 1024");
+  const int grid = ln_grid(M);
+  const size_t smem = (size_t)8 * 2 * C * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(ln_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(e));
+  }
+  ln_backward_kernel<<<grid, 256, smem, lc.stream>>>(d_out, x, g, d_res, dx, ws, M, C);
+  IGM_POST_LAUNCH(lc);
+  ln_param_finalize_kernel<<<cdiv(C, 128), 128, 0, lc.stream>>>(ws, grid, C, dg, db);
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+}  // namespace igm

@@ -1,0 +1,1075 @@
+// Layer plan, forward/backward orchestration and the C ABI of libigm_b200.
+//
+// The plan mirrors reference Unet.__init__ (src/models/ddpm.py:170-236) and the
+// forward mirrors Unet.forward (:238-261); every activation / workspace buffer is
+// carved once from a single HBM arena at igm_unet_create, so a forward, a
+// backward or a sampler step is a fixed launch sequence with no allocation and
+// can be captured into a CUDA graph (igm_ddpm_sample_loop does).
+#include <cuda.h>
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <memory>
+
+#include "common.cuh"
+
+namespace igm {
+
+void set_error(Status& st, int code, const char* file, int line, const char* what) {
+  st.code = code;
+  char buf[512];
+  snprintf(buf, sizeof(buf), "%s:%d: %s", file, line, what ? what : "?");
+  st.msg = buf;
+}
+
+namespace {
+
+Status g_create_status;
+
+struct ParamInfo {
+  std::string name;
+  int64_t offset = 0;
+  int ndim = 0;
+  int64_t shape[4] = {1, 1, 1, 1};
+  int64_t numel() const { return shape[0] * shape[1] * shape[2] * shape[3]; }
+};
+
+// Activation in NHWC; v = value, g = gradient (training only)
+struct Act {
+  float* v = nullptr;
+  float* g = nullptr;
+  int C = 0, H = 0, W = 0;
+};
+
+struct ConvL {
+  int pw = -1, pb = -1;   // parameter indices
+  int Cin = 0, Cout = 0, K = 1;
+  bool convT = false;
+  float* w_fwd = nullptr;   // [K*K][Cin][Cout]
+  float* w_bwd = nullptr;   // [K*K][Cout][Cin]
+};
+
+struct BlockL {
+  ConvL conv;
+  int gn_w = -1, gn_b = -1;
+  float* raw = nullptr;     // conv output (pre-norm), [M, Cout]
+  float* stats = nullptr;   // [B][8][2] mean, rstd
+};
+
+struct ResnetL {
+  std::string name;
+  int Cin = 0, Cout = 0, H = 0, W = 0;
+  int mlp_w = -1, mlp_b = -1, temb_off = 0;
+  BlockL b1, b2;
+  bool has_res = false;
+  ConvL res;
+  Act h1, out;
+  float* r = nullptr;   // res_conv output
+};
+
+struct AttnL {
+  std::string name;
+  int C = 0, H = 0, W = 0;
+  ConvL qkv, outc;
+  int ln_g = -1, ln_b = -1;
+  float* ln = nullptr;     // [M, C]
+  float* qkv_t = nullptr;  // [M, 384]
+  float* att = nullptr;    // [M, 128]
+  float* ctx = nullptr;    // [B, 4, 32, 32]
+  float* kstat = nullptr;  // [B, 4, 32, 2]
+  Act out;
+};
+
+struct ResampleL {
+  std::string name;
+  ConvL conv;
+  int Hin = 0, Win = 0;
+  Act out;
+  bool present = false;
+};
+
+struct Stage {
+  ResnetL r1, r2;
+  AttnL attn;
+  ResampleL rs;
+};
+
+// bump allocator with a measuring pass
+struct Arena {
+  float* base = nullptr;
+  int64_t used = 0;   // floats
+  float* alloc(int64_t n) {
+    n = (n + 63) & ~int64_t(63);   // 256-byte granularity
+    float* p = base ? base + used : nullptr;
+    used += n;
+    return p;
+  }
+};
+
+}  // namespace
+}  // namespace igm
+
+using namespace igm;
+
+struct igm_ctx {
+  igm_unet_cfg cfg{};
+  int device = 0;
+  Status st;
+  int64_t launches = 0;
+  int conv_engine = 0;
+
+  std::vector<ParamInfo> params;
+  int64_t param_elems = 0;
+  float* P = nullptr;   // bound parameter arena (caller-owned)
+  float* G = nullptr;   // bound gradient arena (caller-owned)
+
+  // plan
+  std::vector<int> dims;
+  std::vector<Stage> downs, ups;
+  ResnetL mid1, mid2;
+  AttnL mid_attn;
+  BlockL final_block;
+  Act final_act;
+  ConvL final_conv;
+  float* final_wbwd = nullptr;   // [1][C][K]
+  std::vector<TimeProj> proj_host;
+  TimeProj* proj_dev = nullptr;
+  int n_proj = 0, proj_total = 0;
+  int tm_w1 = -1, tm_b1 = -1, tm_w2 = -1, tm_b2 = -1;
+
+  // buffers
+  float* arena = nullptr;
+  int64_t arena_floats = 0;
+  Act x_in;                 // NHWC network input
+  float *t_emb = nullptr, *t_h1 = nullptr, *t_temb = nullptr, *t_act = nullptr, *t_proj = nullptr;
+  float *t_dproj = nullptr, *t_ws = nullptr;
+  float* gn_part = nullptr;
+  float *ws_group = nullptr, *ws_chan = nullptr, *ws_ln = nullptr;
+  float *scrA = nullptr, *scrB = nullptr, *scrC = nullptr;
+  float* pred = nullptr;        // [B,C,H,W] network output (NCHW)
+  float* noise_copy = nullptr;  // NCHW
+  float* d_pred = nullptr;      // NHWC [M, C]
+  float* loss_ws = nullptr;
+  int64_t* t_vec = nullptr;     // sampler timesteps [B]
+  int* loop_state = nullptr;    // [t, step]
+  igm_schedule sched{};
+  igm_schedule* sched_dev = nullptr;
+  bool have_sched = false;
+
+  std::map<std::string, Act> taps;
+
+  std::vector<float*> skip_g;   // gradient of the skip tensor of down stage i (i >= 1), training only
+
+  int last_B = 0;
+  bool fwd_valid = false, loss_valid = false;
+
+  // sampler graph cache
+  cudaGraphExec_t graph_exec = nullptr;
+  struct GraphKey {
+    float* img = nullptr; const float* noise = nullptr; uint64_t seed = 0; int B = 0, clip = 0;
+    bool operator==(const GraphKey& o) const {
+      return img == o.img && noise == o.noise && seed == o.seed && B == o.B && clip == o.clip;
+    }
+  } graph_key;
+
+  LaunchCtx lc(void* stream) {
+    LaunchCtx l;
+    l.stream = (cudaStream_t)stream;
+    l.st = &st;
+    l.counter = &launches;
+    return l;
+  }
+  float* Pp(int idx) const { return idx < 0 ? nullptr : P + params[idx].offset; }
+  float* Gp(int idx) const { return idx < 0 ? nullptr : G + params[idx].offset; }
+};
+
+namespace igm {
+namespace {
+
+// ---------------------------------------------------------------------------
+// parameter table: same order/shapes as reference Unet(...).state_dict()
+// ---------------------------------------------------------------------------
+struct ParamBuilder {
+  std::vector<ParamInfo>& out;
+  int64_t off = 0;
+  int add(const std::string& name, std::initializer_list<int64_t> shape) {
+    ParamInfo p;
+    p.name = name;
+    p.offset = off;
+    p.ndim = (int)shape.size();
+    int i = 0;
+    for (int64_t s : shape) p.shape[i++] = s;
+    // keep every tensor 16-byte aligned inside the flat arena (float4 loads of bias / gamma)
+    off += (p.numel() + 3) & ~int64_t(3);
+    out.push_back(p);
+    return (int)out.size() - 1;
+  }
+};
+
+struct PlanBuilder {
+  igm_ctx& c;
+  ParamBuilder pb;
+  Arena ar;
+  bool training;
+  int B;
+  int64_t maxMC = 0, maxM = 0, maxGnWs = 0;
+
+  PlanBuilder(igm_ctx& ctx, float* base) : c(ctx), pb{ctx.params} {
+    ar.base = base;
+    training = ctx.cfg.training != 0;
+    B = ctx.cfg.max_batch;
+  }
+
+  int64_t M(int H, int W) const { return (int64_t)B * H * W; }
+
+  Act act(int C, int H, int W, bool grad) {
+    Act a;
+    a.C = C; a.H = H; a.W = W;
+    a.v = ar.alloc(M(H, W) * C);
+    if (grad && training) a.g = ar.alloc(M(H, W) * C);
+    return a;
+  }
+  void tap(const std::string& n, float* v, int C, int H, int W) {
+    Act a; a.v = v; a.C = C; a.H = H; a.W = W;
+    c.taps[n] = a;
+  }
+
+  ConvL conv(const std::string& name, int Cin, int Cout, int K, bool bias, bool convT = false) {
+    ConvL l;
+    l.Cin = Cin; l.Cout = Cout; l.K = K; l.convT = convT;
+    if (convT) l.pw = pb.add(name + ".weight", {Cin, Cout, K, K});
+    else l.pw = pb.add(name + ".weight", {Cout, Cin, K, K});
+    if (bias) l.pb = pb.add(name + ".bias", {Cout});
+    l.w_fwd = ar.alloc((int64_t)K * K * Cin * Cout);
+    if (training) l.w_bwd = ar.alloc((int64_t)K * K * Cin * Cout);
+    return l;
+  }
+
+  BlockL block(const std::string& name, int Cin, int Cout, int H, int W) {
+    BlockL b;
+    b.conv = conv(name + ".block.0", Cin, Cout, 3, true);
+    b.gn_w = pb.add(name + ".block.1.weight", {Cout});
+    b.gn_b = pb.add(name + ".block.1.bias", {Cout});
+    b.raw = ar.alloc(M(H, W) * Cout);
+    b.stats = ar.alloc((int64_t)B * kGroups * 2);
+    tap(name + ".conv", b.raw, Cout, H, W);
+    track(H, W, Cout);
+    return b;
+  }
+  void track(int H, int W, int C) {
+    maxMC = std::max(maxMC, M(H, W) * C);
+    maxM = std::max(maxM, M(H, W));
+    const int64_t chunks = cdiv(H * W, kGnChunk);
+    maxGnWs = std::max(maxGnWs, (int64_t)B * chunks * 3 * C);
+  }
+
+  ResnetL resnet(const std::string& name, int Cin, int Cout, int H, int W) {
+    ResnetL r;
+    r.name = name; r.Cin = Cin; r.Cout = Cout; r.H = H; r.W = W;
+    r.mlp_w = pb.add(name + ".mlp.1.weight", {Cout, c.cfg.dim});
+    r.mlp_b = pb.add(name + ".mlp.1.bias", {Cout});
+    r.temb_off = c.proj_total;
+    c.proj_total += Cout;
+    TimeProj tp{};
+    tp.cout = Cout; tp.offset = r.temb_off;
+    c.proj_host.push_back(tp);   // pointers are filled at bind time
+    r.b1 = block(name + ".block1", Cin, Cout, H, W);
+    r.b2 = block(name + ".block2", Cout, Cout, H, W);
+    r.has_res = Cin != Cout;
+    if (r.has_res) {
+      r.res = conv(name + ".res_conv", Cin, Cout, 1, true);
+      r.r = ar.alloc(M(H, W) * Cout);
+    }
+    r.h1 = act(Cout, H, W, true);
+    r.out = act(Cout, H, W, true);
+    tap(name + ".h1", r.h1.v, Cout, H, W);
+    tap(name + ".out", r.out.v, Cout, H, W);
+    return r;
+  }
+
+  AttnL attn(const std::string& name, int C, int H, int W) {
+    AttnL a;
+    a.name = name; a.C = C; a.H = H; a.W = W;
+    const int hd = kHeads * kDimHead;
+    a.qkv = conv(name + ".fn.fn.to_qkv", C, 3 * hd, 1, false);
+    a.outc = conv(name + ".fn.fn.to_out", hd, C, 1, true);
+    a.ln_g = pb.add(name + ".fn.norm.g", {1, C, 1, 1});
+    a.ln_b = pb.add(name + ".fn.norm.b", {1, C, 1, 1});
+    a.ln = ar.alloc(M(H, W) * C);
+    a.qkv_t = ar.alloc(M(H, W) * 3 * hd);
+    a.att = ar.alloc(M(H, W) * hd);
+    a.ctx = ar.alloc((int64_t)B * kHeads * kDimHead * kDimHead);
+    a.kstat = ar.alloc((int64_t)B * kHeads * kDimHead * 2);
+    a.out = act(C, H, W, true);
+    tap(name + ".ln", a.ln, C, H, W);
+    tap(name + ".out", a.out.v, C, H, W);
+    track(H, W, C);
+    maxMC = std::max(maxMC, M(H, W) * 3 * hd);
+    return a;
+  }
+
+  void build() {
+    const igm_unet_cfg& cfg = c.cfg;
+    c.params.clear();
+    c.taps.clear();
+    c.proj_host.clear();
+    c.proj_total = 0;
+    c.dims.clear();
+    c.dims.push_back(cfg.channels);
+    for (int i = 0; i < cfg.n_mults; ++i) c.dims.push_back(cfg.dim * cfg.dim_mults[i]);
+    const int nres = cfg.n_mults;
+    const int d = cfg.dim;
+
+    c.tm_w1 = pb.add("time_mlp.1.weight", {4 * d, d});
+    c.tm_b1 = pb.add("time_mlp.1.bias", {4 * d});
+    c.tm_w2 = pb.add("time_mlp.3.weight", {d, 4 * d});
+    c.tm_b2 = pb.add("time_mlp.3.bias", {d});
+
+    int H = cfg.height, W = cfg.width;
+    c.x_in = act(cfg.channels, H, W, false);
+    c.downs.assign(nres, Stage());
+    std::vector<int> hs(nres), ws(nres);
+    for (int i = 0; i < nres; ++i) {
+      const int ci = c.dims[i], co = c.dims[i + 1];
+      Stage& s = c.downs[i];
+      const std::string p = "downs." + std::to_string(i);
+      s.r1 = resnet(p + ".0", ci, co, H, W);
+      s.r2 = resnet(p + ".1", co, co, H, W);
+      s.attn = attn(p + ".2", co, H, W);
+      hs[i] = H; ws[i] = W;
+      if (i < nres - 1) {
+        s.rs.present = true;
+        s.rs.name = p + ".3";
+        s.rs.conv = conv(p + ".3.conv", co, co, 3, true);
+        s.rs.Hin = H; s.rs.Win = W;
+        H = (H + 2 - 3) / 2 + 1;
+        W = (W + 2 - 3) / 2 + 1;
+        s.rs.out = act(co, H, W, true);
+        tap(p + ".3.out", s.rs.out.v, co, H, W);
+        track(H, W, co);
+      }
+    }
+    // ups are registered before the mid blocks in the reference (ddpm.py:195-196)
+    c.ups.assign(nres - 1, Stage());
+    {
+      int Hu = H, Wu = W;
+      for (int j = 0; j < nres - 1; ++j) {
+        const int si = nres - 1 - j;              // reversed(in_out[1:])
+        const int ci = c.dims[si], co = c.dims[si + 1];
+        Stage& s = c.ups[j];
+        const std::string p = "ups." + std::to_string(j);
+        s.r1 = resnet(p + ".0", co * 2, ci, Hu, Wu);
+        s.r2 = resnet(p + ".1", ci, ci, Hu, Wu);
+        s.attn = attn(p + ".2", ci, Hu, Wu);
+        s.rs.present = true;
+        s.rs.name = p + ".3";
+        s.rs.conv = conv(p + ".3.conv", ci, ci, 4, true, /*convT=*/true);
+        s.rs.Hin = Hu; s.rs.Win = Wu;
+        Hu *= 2; Wu *= 2;
+        s.rs.out = act(ci, Hu, Wu, true);
+        tap(p + ".3.out", s.rs.out.v, ci, Hu, Wu);
+        track(Hu, Wu, ci);
+      }
+    }
+    const int mid = c.dims.back();
+    c.mid1 = resnet("mid_block1", mid, mid, H, W);
+    c.mid_attn = attn("mid_attn", mid, H, W);
+    c.mid2 = resnet("mid_block2", mid, mid, H, W);
+
+    // final_conv = Block(dims[1], dims[1]) + Conv1x1(dims[1], channels) at full resolution
+    const int fH = cfg.height, fW = cfg.width, fc = c.dims[1];
+    // (with an odd number of halvings the up path may not return to H x W; reject in create)
+    c.final_block = block("final_conv.0", fc, fc, fH, fW);
+    c.final_act = act(fc, fH, fW, true);
+    tap("final_conv.0.out", c.final_act.v, fc, fH, fW);
+    c.final_conv = ConvL();
+    c.final_conv.Cin = fc; c.final_conv.Cout = cfg.channels; c.final_conv.K = 1;
+    c.final_conv.pw = pb.add("final_conv.1.weight", {cfg.channels, fc, 1, 1});
+    c.final_conv.pb = pb.add("final_conv.1.bias", {cfg.channels});
+    if (training) c.final_wbwd = ar.alloc((int64_t)cfg.channels * fc);
+    c.param_elems = pb.off;
+    c.n_proj = (int)c.proj_host.size();
+
+    // time path buffers
+    c.t_emb = ar.alloc((int64_t)B * d);
+    c.t_h1 = ar.alloc((int64_t)B * 4 * d);
+    c.t_temb = ar.alloc((int64_t)B * d);
+    c.t_act = ar.alloc((int64_t)B * d);
+    c.t_proj = ar.alloc((int64_t)B * c.proj_total);
+    tap("time_mlp", c.t_temb, d, 1, 1);
+    const int64_t HW0 = (int64_t)cfg.height * cfg.width;
+    c.gn_part = ar.alloc((int64_t)B * cdiv((int)HW0, kGnChunk) * kGroups * 2);
+    c.pred = ar.alloc((int64_t)B * cfg.channels * HW0);
+    c.loss_ws = ar.alloc(1024);
+    c.t_vec = reinterpret_cast<int64_t*>(ar.alloc(2 * (int64_t)B + 4));
+    c.loop_state = reinterpret_cast<int*>(ar.alloc(64));
+    c.sched_dev = reinterpret_cast<igm_schedule*>(ar.alloc(64));
+    c.proj_dev = reinterpret_cast<TimeProj*>(ar.alloc((int64_t)(sizeof(TimeProj) * c.n_proj + 3) / 4 + 64));
+    if (training) {
+      c.t_dproj = ar.alloc((int64_t)B * c.proj_total);
+      c.t_ws = ar.alloc((int64_t)B * 6 * d);
+      c.ws_group = ar.alloc((int64_t)B * cdiv((int)HW0, kGnChunk) * kGroups * 2);
+      c.ws_chan = ar.alloc(maxGnWs);
+      c.ws_ln = ar.alloc((int64_t)ln_backward_parts(maxM) * 2 * 1024);
+      c.scrA = ar.alloc(maxMC);
+      c.scrB = ar.alloc(maxM * kHeads * kDimHead);
+      c.scrC = ar.alloc(maxM * 3 * kHeads * kDimHead);
+      c.noise_copy = ar.alloc((int64_t)B * cfg.channels * HW0);
+      c.d_pred = ar.alloc((int64_t)B * cfg.channels * HW0);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// conv helpers
+// ---------------------------------------------------------------------------
+struct Runner {
+  igm_ctx& c;
+  LaunchCtx lc;
+  int B;
+
+  int64_t M(int H, int W) const { return (int64_t)B * H * W; }
+
+  // forward of a Conv2d (stride s, pad p) or ConvTranspose2d layer
+  int conv_fwd(const ConvL& l, const float* in0, int C0, const float* in1, int C1, int IH, int IW, int OH,
+               int OW, int stride, int pad, float* out, const float* add) {
+    ConvArgs a;
+    a.in0 = in0; a.in1 = in1; a.C0 = C0; a.C1 = C1;
+    a.B = B; a.IH = IH; a.IW = IW; a.OH = OH; a.OW = OW;
+    a.N = l.Cout; a.N0 = l.Cout;
+    a.KH = a.KW = l.K; a.stride = stride; a.pad = pad; a.dil = 1;
+    a.transposed = l.convT ? 1 : 0;
+    a.w = l.w_fwd;
+    a.bias = c.Pp(l.pb);
+    a.out0 = out; a.add0 = add;
+    return launch_conv(lc, a);
+  }
+  // data gradient: d_out [B,OH,OW,Cout] -> d_in split (d0: C0 channels, d1: C1 channels)
+  int conv_dgrad(const ConvL& l, const float* d_out, int OH, int OW, int IH, int IW, int stride, int pad,
+                 float* d0, int C0, float* d1, int C1, const float* add0, const float* add1) {
+    ConvArgs a;
+    a.in0 = d_out; a.C0 = l.Cout; a.C1 = 0;
+    a.B = B; a.IH = OH; a.IW = OW; a.OH = IH; a.OW = IW;
+    a.N = C0 + C1; a.N0 = C0;
+    a.KH = a.KW = l.K; a.stride = stride; a.pad = pad; a.dil = 1;
+    a.transposed = l.convT ? 0 : 1;
+    a.w = l.w_bwd;
+    a.bias = nullptr;
+    a.out0 = d0; a.out1 = d1; a.add0 = add0; a.add1 = add1;
+    return launch_conv(lc, a);
+  }
+  // weight + bias gradients.  in0/in1: forward inputs; d_out: grad of the conv output
+  int conv_wgrad(const ConvL& l, const float* in0, int C0, const float* in1, int C1, int IH, int IW,
+                 const float* d_out, int OH, int OW, int stride, int pad) {
+    const int KK = l.K * l.K;
+    float* gw = c.Gp(l.pw);
+    if (!l.convT) {
+      // Conv2d: P = d_out (pc = co), Q = input (qc = ci) gathered at oy*s - p + ky;  W[co][ci][tap]
+      const float* srcs[2] = {in0, in1};
+      const int cs[2] = {C0, C1};
+      int coff = 0;
+      for (int i = 0; i < 2; ++i) {
+        if (!srcs[i] || cs[i] == 0) continue;
+        WgradArgs w;
+        w.P = d_out; w.PC = l.Cout; w.PH = OH; w.PW = OW;
+        w.Q = srcs[i]; w.QC = cs[i]; w.QH = IH; w.QW = IW;
+        w.B = B; w.KH = w.KW = l.K; w.stride = stride; w.pad = pad; w.dil = 1;
+        w.grad = gw + (int64_t)coff * KK;
+        w.sq = KK; w.sp = (int64_t)l.Cin * KK;
+        IGM_TRY(launch_wgrad(lc, w));
+        coff += cs[i];
+      }
+    } else {
+      // ConvTranspose2d: oy = iy*s - p + ky.  P = input (pc = ci), Q = d_out (qc = co);  W[ci][co][tap]
+      WgradArgs w;
+      w.P = in0; w.PC = l.Cin; w.PH = IH; w.PW = IW;
+      w.Q = d_out; w.QC = l.Cout; w.QH = OH; w.QW = OW;
+      w.B = B; w.KH = w.KW = l.K; w.stride = stride; w.pad = pad; w.dil = 1;
+      w.grad = gw;
+      w.sq = KK; w.sp = (int64_t)l.Cout * KK;
+      IGM_TRY(launch_wgrad(lc, w));
+    }
+    if (l.pb >= 0) IGM_TRY(launch_colsum(lc, d_out, M(OH, OW), l.Cout, c.Gp(l.pb)));
+    return IGM_OK;
+  }
+
+  // ---- Block: conv3x3 -> GN -> Mish (+temb) (+res) ----
+  int block_fwd(BlockL& b, const float* in0, int C0, const float* in1, int C1, int H, int W, const float* temb,
+                const float* res, float* out) {
+    IGM_TRY(conv_fwd(b.conv, in0, C0, in1, C1, H, W, H, W, 1, 1, b.raw, nullptr));
+    IGM_TRY(launch_gn_partial(lc, b.raw, B, H * W, b.conv.Cout, c.gn_part));
+    IGM_TRY(launch_gn_apply(lc, b.raw, c.gn_part, c.Pp(b.gn_w), c.Pp(b.gn_b), temb, c.proj_total, res, out,
+                            b.stats, B, H * W, b.conv.Cout));
+    return IGM_OK;
+  }
+  // d_out: grad of block output; leaves dy (grad of conv output) in scrA
+  int block_bwd_norm(BlockL& b, const float* d_out, int H, int W, float* dtemb) {
+    GnBwdArgs g;
+    g.d_out = d_out; g.y = b.raw; g.stats = b.stats;
+    g.gamma = c.Pp(b.gn_w); g.beta = c.Pp(b.gn_b);
+    g.dy = c.scrA; g.dgamma = c.Gp(b.gn_w); g.dbeta = c.Gp(b.gn_b);
+    g.dtemb = dtemb; g.dtemb_stride = c.proj_total;
+    g.ws_group = c.ws_group; g.ws_chan = c.ws_chan;
+    g.B = B; g.HW = H * W; g.C = b.conv.Cout;
+    return launch_gn_backward(lc, g);
+  }
+
+  int resnet_fwd(ResnetL& r, const float* in0, int C0, const float* in1, int C1) {
+    const int H = r.H, W = r.W;
+    IGM_TRY(block_fwd(r.b1, in0, C0, in1, C1, H, W, c.t_proj + r.temb_off, nullptr, r.h1.v));
+    const float* res = in0;
+    if (r.has_res) {
+      IGM_TRY(conv_fwd(r.res, in0, C0, in1, C1, H, W, H, W, 1, 0, r.r, nullptr));
+      res = r.r;
+    }
+    IGM_TRY(block_fwd(r.b2, r.h1.v, r.Cout, nullptr, 0, H, W, nullptr, res, r.out.v));
+    return IGM_OK;
+  }
+  // d_out = r.out.g ; writes d_in0 (C0 ch) / d_in1 (C1 ch) unless null
+  int resnet_bwd(ResnetL& r, const float* in0, int C0, const float* in1, int C1, float* d0, float* d1) {
+    const int H = r.H, W = r.W;
+    const float* d_out = r.out.g;
+    // block2
+    IGM_TRY(block_bwd_norm(r.b2, d_out, H, W, nullptr));
+    IGM_TRY(conv_wgrad(r.b2.conv, r.h1.v, r.Cout, nullptr, 0, H, W, c.scrA, H, W, 1, 1));
+    IGM_TRY(conv_dgrad(r.b2.conv, c.scrA, H, W, H, W, 1, 1, r.h1.g, r.Cout, nullptr, 0, nullptr, nullptr));
+    // block1 (+ time-embedding add)
+    IGM_TRY(block_bwd_norm(r.b1, r.h1.g, H, W, c.t_dproj + r.temb_off));
+    IGM_TRY(conv_wgrad(r.b1.conv, in0, C0, in1, C1, H, W, c.scrA, H, W, 1, 1));
+    if (r.has_res) {
+      IGM_TRY(conv_wgrad(r.res, in0, C0, in1, C1, H, W, d_out, H, W, 1, 0));
+      if (d0) {
+        IGM_TRY(conv_dgrad(r.res, d_out, H, W, H, W, 1, 0, d0, C0, d1, C1, nullptr, nullptr));
+        IGM_TRY(conv_dgrad(r.b1.conv, c.scrA, H, W, H, W, 1, 1, d0, C0, d1, C1, d0, d1));
+      }
+    } else if (d0) {
+      IGM_TRY(conv_dgrad(r.b1.conv, c.scrA, H, W, H, W, 1, 1, d0, C0, nullptr, 0, d_out, nullptr));
+    }
+    return IGM_OK;
+  }
+
+  int attn_fwd(AttnL& a, const float* x) {
+    const int H = a.H, W = a.W;
+    const int64_t m = M(H, W);
+    const int hd = kHeads * kDimHead;
+    IGM_TRY(launch_ln_forward(lc, x, c.Pp(a.ln_g), c.Pp(a.ln_b), a.ln, m, a.C));
+    IGM_TRY(conv_fwd(a.qkv, a.ln, a.C, nullptr, 0, H, W, H, W, 1, 0, a.qkv_t, nullptr));
+    IGM_TRY(launch_linattn_forward(lc, a.qkv_t, a.att, a.ctx, a.kstat, B, H * W));
+    IGM_TRY(conv_fwd(a.outc, a.att, hd, nullptr, 0, H, W, H, W, 1, 0, a.out.v, x));
+    return IGM_OK;
+  }
+  int attn_bwd(AttnL& a, const float* x, float* dx) {
+    const int H = a.H, W = a.W;
+    const int64_t m = M(H, W);
+    const int hd = kHeads * kDimHead;
+    const float* d_out = a.out.g;
+    IGM_TRY(conv_wgrad(a.outc, a.att, hd, nullptr, 0, H, W, d_out, H, W, 1, 0));
+    IGM_TRY(conv_dgrad(a.outc, d_out, H, W, H, W, 1, 0, c.scrB, hd, nullptr, 0, nullptr, nullptr));
+    IGM_TRY(launch_linattn_backward(lc, a.qkv_t, a.ctx, a.kstat, c.scrB, c.scrC, B, H * W));
+    IGM_TRY(conv_wgrad(a.qkv, a.ln, a.C, nullptr, 0, H, W, c.scrC, H, W, 1, 0));
+    IGM_TRY(conv_dgrad(a.qkv, c.scrC, H, W, H, W, 1, 0, c.scrA, a.C, nullptr, 0, nullptr, nullptr));
+    IGM_TRY(launch_ln_backward(lc, c.scrA, x, c.Pp(a.ln_g), d_out, dx, c.Gp(a.ln_g), c.Gp(a.ln_b), c.ws_ln, m, a.C));
+    return IGM_OK;
+  }
+
+  int time_params(TimeMlpParams& p) {
+    p.w1 = c.Pp(c.tm_w1); p.b1 = c.Pp(c.tm_b1); p.w2 = c.Pp(c.tm_w2); p.b2 = c.Pp(c.tm_b2);
+    p.gw1 = c.G ? c.Gp(c.tm_w1) : nullptr; p.gb1 = c.G ? c.Gp(c.tm_b1) : nullptr;
+    p.gw2 = c.G ? c.Gp(c.tm_w2) : nullptr; p.gb2 = c.G ? c.Gp(c.tm_b2) : nullptr;
+    p.dim = c.cfg.dim;
+    return IGM_OK;
+  }
+
+  // whole network on c.x_in -> pred_nchw
+  int forward(const int64_t* t, float* pred_nchw) {
+    const igm_unet_cfg& cfg = c.cfg;
+    TimeMlpParams tp;
+    time_params(tp);
+    IGM_TRY(launch_time_mlp_forward(lc, tp, t, B, c.t_emb, c.t_h1, c.t_temb, c.t_act));
+    IGM_TRY(launch_time_proj_forward(lc, c.proj_dev, c.n_proj, c.t_act, cfg.dim, B, c.proj_total, c.t_proj));
+    const float* x = c.x_in.v;
+    int xc = cfg.channels;
+    const int nres = cfg.n_mults;
+    for (int i = 0; i < nres; ++i) {
+      Stage& s = c.downs[i];
+      IGM_TRY(resnet_fwd(s.r1, x, xc, nullptr, 0));
+      IGM_TRY(resnet_fwd(s.r2, s.r1.out.v, s.r1.Cout, nullptr, 0));
+      IGM_TRY(attn_fwd(s.attn, s.r2.out.v));
+      x = s.attn.out.v; xc = s.attn.C;
+      if (s.rs.present) {
+        IGM_TRY(conv_fwd(s.rs.conv, x, xc, nullptr, 0, s.rs.Hin, s.rs.Win, s.rs.out.H, s.rs.out.W, 2, 1,
+                         s.rs.out.v, nullptr));
+        x = s.rs.out.v;
+      }
+    }
+    IGM_TRY(resnet_fwd(c.mid1, x, xc, nullptr, 0));
+    IGM_TRY(attn_fwd(c.mid_attn, c.mid1.out.v));
+    IGM_TRY(resnet_fwd(c.mid2, c.mid_attn.out.v, c.mid_attn.C, nullptr, 0));
+    x = c.mid2.out.v; xc = c.mid2.Cout;
+    for (int j = 0; j < nres - 1; ++j) {
+      Stage& s = c.ups[j];
+      const AttnL& skip = c.downs[nres - 1 - j].attn;   // h.pop()  (ddpm.py:255)
+      IGM_TRY(resnet_fwd(s.r1, x, xc, skip.out.v, skip.C));
+      IGM_TRY(resnet_fwd(s.r2, s.r1.out.v, s.r1.Cout, nullptr, 0));
+      IGM_TRY(attn_fwd(s.attn, s.r2.out.v));
+      IGM_TRY(conv_fwd(s.rs.conv, s.attn.out.v, s.attn.C, nullptr, 0, s.rs.Hin, s.rs.Win, s.rs.out.H,
+                       s.rs.out.W, 2, 1, s.rs.out.v, nullptr));
+      x = s.rs.out.v; xc = s.attn.C;
+    }
+    IGM_TRY(block_fwd(c.final_block, x, xc, nullptr, 0, cfg.height, cfg.width, nullptr, nullptr, c.final_act.v));
+    IGM_TRY(launch_final_conv(lc, c.final_act.v, c.Pp(c.final_conv.pw), c.Pp(c.final_conv.pb), pred_nchw, B,
+                              cfg.height * cfg.width, c.final_conv.Cin, cfg.channels));
+    return IGM_OK;
+  }
+
+  // d_pred: NHWC [M, channels]; d_x_nhwc may be null
+  int backward(const float* d_pred, float* d_x_nhwc) {
+    const igm_unet_cfg& cfg = c.cfg;
+    const int nres = cfg.n_mults;
+    const int H0 = cfg.height, W0 = cfg.width;
+    // final 1x1: W[c][k]
+    {
+      WgradArgs w;
+      w.P = d_pred; w.PC = cfg.channels; w.PH = H0; w.PW = W0;
+      w.Q = c.final_act.v; w.QC = c.final_conv.Cin; w.QH = H0; w.QW = W0;
+      w.B = B; w.grad = c.Gp(c.final_conv.pw);
+      w.sq = 1; w.sp = c.final_conv.Cin;
+      IGM_TRY(launch_wgrad(lc, w));
+      IGM_TRY(launch_colsum(lc, d_pred, M(H0, W0), cfg.channels, c.Gp(c.final_conv.pb)));
+      ConvArgs a;
+      a.in0 = d_pred; a.C0 = cfg.channels; a.B = B; a.IH = a.OH = H0; a.IW = a.OW = W0;
+      a.N = a.N0 = c.final_conv.Cin; a.transposed = 1;
+      a.w = c.final_wbwd; a.out0 = c.final_act.g;
+      IGM_TRY(launch_conv(lc, a));
+    }
+    // input of the final block
+    const float* fin; int finC; float* fin_g;
+    if (nres > 1) { fin = c.ups.back().rs.out.v; finC = c.ups.back().rs.out.C; fin_g = c.ups.back().rs.out.g; }
+    else { fin = c.mid2.out.v; finC = c.mid2.Cout; fin_g = c.mid2.out.g; }
+    IGM_TRY(block_bwd_norm(c.final_block, c.final_act.g, H0, W0, nullptr));
+    IGM_TRY(conv_wgrad(c.final_block.conv, fin, finC, nullptr, 0, H0, W0, c.scrA, H0, W0, 1, 1));
+    IGM_TRY(conv_dgrad(c.final_block.conv, c.scrA, H0, W0, H0, W0, 1, 1, fin_g, finC, nullptr, 0, nullptr, nullptr));
+
+    for (int j = nres - 2; j >= 0; --j) {
+      Stage& s = c.ups[j];
+      AttnL& skip = c.downs[nres - 1 - j].attn;
+      const Act& prev = (j == 0) ? c.mid2.out : c.ups[j - 1].rs.out;
+      // Upsample (ConvTranspose2d 4,2,1)
+      IGM_TRY(conv_wgrad(s.rs.conv, s.attn.out.v, s.attn.C, nullptr, 0, s.rs.Hin, s.rs.Win, s.rs.out.g,
+                         s.rs.out.H, s.rs.out.W, 2, 1));
+      IGM_TRY(conv_dgrad(s.rs.conv, s.rs.out.g, s.rs.out.H, s.rs.out.W, s.rs.Hin, s.rs.Win, 2, 1, s.attn.out.g,
+                         s.attn.C, nullptr, 0, nullptr, nullptr));
+      IGM_TRY(attn_bwd(s.attn, s.r2.out.v, s.r2.out.g));
+      IGM_TRY(resnet_bwd(s.r2, s.r1.out.v, s.r1.Cout, nullptr, 0, s.r1.out.g, nullptr));
+      IGM_TRY(resnet_bwd(s.r1, prev.v, prev.C, skip.out.v, skip.C, prev.g, skip_grad(nres - 1 - j)));
+    }
+    IGM_TRY(resnet_bwd(c.mid2, c.mid_attn.out.v, c.mid_attn.C, nullptr, 0, c.mid_attn.out.g, nullptr));
+    IGM_TRY(attn_bwd(c.mid_attn, c.mid1.out.v, c.mid1.out.g));
+    {
+      Stage& last = c.downs[nres - 1];
+      IGM_TRY(resnet_bwd(c.mid1, last.attn.out.v, last.attn.C, nullptr, 0, last.attn.out.g, nullptr));
+      if (nres > 1) IGM_TRY(launch_add(lc, last.attn.out.g, skip_grad(nres - 1), M(last.attn.H, last.attn.W) * last.attn.C));
+    }
+    for (int i = nres - 1; i >= 0; --i) {
+      Stage& s = c.downs[i];
+      if (s.rs.present) {
+        IGM_TRY(conv_wgrad(s.rs.conv, s.attn.out.v, s.attn.C, nullptr, 0, s.rs.Hin, s.rs.Win, s.rs.out.g,
+                           s.rs.out.H, s.rs.out.W, 2, 1));
+        // h[0] is never consumed by the up path (ddpm.py:254-259): no skip gradient for stage 0
+        const float* add = (i >= 1) ? skip_grad(i) : nullptr;
+        IGM_TRY(conv_dgrad(s.rs.conv, s.rs.out.g, s.rs.out.H, s.rs.out.W, s.rs.Hin, s.rs.Win, 2, 1, s.attn.out.g,
+                           s.attn.C, nullptr, 0, add, nullptr));
+      }
+      IGM_TRY(attn_bwd(s.attn, s.r2.out.v, s.r2.out.g));
+      IGM_TRY(resnet_bwd(s.r2, s.r1.out.v, s.r1.Cout, nullptr, 0, s.r1.out.g, nullptr));
+      if (i > 0) {
+        const Act& prev = c.downs[i - 1].rs.out;
+        IGM_TRY(resnet_bwd(s.r1, prev.v, prev.C, nullptr, 0, prev.g, nullptr));
+      } else {
+        IGM_TRY(resnet_bwd(s.r1, c.x_in.v, cfg.channels, nullptr, 0, d_x_nhwc, nullptr));
+      }
+    }
+    TimeMlpParams tp;
+    time_params(tp);
+    IGM_TRY(launch_time_backward(lc, tp, c.proj_dev, c.n_proj, c.proj_total, B, c.t_emb, c.t_h1, c.t_temb, c.t_act,
+                                 c.t_dproj, c.t_ws));
+    return IGM_OK;
+  }
+
+  float* skip_grad(int stage) { return c.skip_g[stage]; }
+};
+
+}  // namespace
+}  // namespace igm
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int igm_version(void) { return 100; }
+
+const char* igm_last_error(const igm_ctx* ctx) {
+  const Status& st = ctx ? ctx->st : g_create_status;
+  return st.msg.c_str();
+}
+
+static int build_plan(igm_ctx* c, float* base, int64_t* floats_out) {
+  PlanBuilder pb(*c, base);
+  pb.build();
+  // skip-gradient buffers (training): one per down stage >= 1
+  c->skip_g.assign(c->cfg.n_mults, nullptr);
+  if (c->cfg.training) {
+    for (int i = 1; i < c->cfg.n_mults; ++i) {
+      const AttnL& a = c->downs[i].attn;
+      c->skip_g[i] = pb.ar.alloc((int64_t)c->cfg.max_batch * a.H * a.W * a.C);
+    }
+  }
+  *floats_out = pb.ar.used;
+  return IGM_OK;
+}
+
+int igm_unet_create(igm_ctx** out, const igm_unet_cfg* cfg, int device) {
+  Status& st = g_create_status;
+  st = Status();
+  if (!out || !cfg) IGM_FAIL(st, IGM_ERR_INVALID, "null argument");
+  if (cfg->dim <= 0 || cfg->dim % 32 != 0 || 256 % cfg->dim != 0)
+    IGM_FAIL(st, IGM_ERR_INVALID, "dim must be 32, 64, 128 or 256");
+  if (cfg->channels < 1 || cfg->channels > 4) IGM_FAIL(st, IGM_ERR_INVALID, "channels must be in [1,4]");
+  if (cfg->n_mults < 1 || cfg->n_mults > IGM_MAX_MULTS) IGM_FAIL(st, IGM_ERR_INVALID, "bad n_mults");
+  for (int i = 0; i < cfg->n_mults; ++i)
+    if (cfg->dim_mults[i] < 1 || cfg->dim * cfg->dim_mults[i] > 1024)
+      IGM_FAIL(st, IGM_ERR_INVALID, "dim * mult must be in [32, 1024]");
+  if (cfg->height < 1 || cfg->width < 1 || cfg->max_batch < 1) IGM_FAIL(st, IGM_ERR_INVALID, "bad image size / batch");
+  {
+    // the up path doubles what the down path halved: H, W must survive n_mults-1 exact halvings
+    int h = cfg->height, w = cfg->width;
+    for (int i = 0; i + 1 < cfg->n_mults; ++i) {
+      if (h % 2 || w % 2) IGM_FAIL(st, IGM_ERR_INVALID, "height/width must be divisible by 2^(n_mults-1)");
+      h /= 2; w /= 2;
+    }
+  }
+  if (cfg->loss_type != 1 && cfg->loss_type != 2) IGM_FAIL(st, IGM_ERR_INVALID, "loss_type must be 1 (l1) or 2 (l2)");
+  IGM_CUDA(st, cudaSetDevice(device));
+  igm_ctx* c = new igm_ctx();
+  c->cfg = *cfg;
+  c->device = device;
+  int64_t floats = 0;
+  build_plan(c, nullptr, &floats);
+  for (auto& st2 : c->ups)
+    if (!st2.r1.has_res) {
+      delete c;
+      IGM_FAIL(st, IGM_ERR_INVALID, "unsupported dim_mults: an up-path ResnetBlock without res_conv");
+    }
+  cudaError_t e = cudaMalloc(&c->arena, (size_t)floats * sizeof(float));
+  if (e != cudaSuccess) {
+    delete c;
+    set_error(st, IGM_ERR_NOMEM, __FILE__, __LINE__, cudaGetErrorString(e));
+    return st.code;
+  }
+  c->arena_floats = floats;
+  e = cudaMemset(c->arena, 0, (size_t)floats * sizeof(float));
+  if (e != cudaSuccess) {
+    cudaFree(c->arena);
+    delete c;
+    set_error(st, IGM_ERR_CUDA, __FILE__, __LINE__, cudaGetErrorString(e));
+    return st.code;
+  }
+  int64_t floats2 = 0;
+  build_plan(c, c->arena, &floats2);
+  *out = c;
+  return IGM_OK;
+}
+
+void igm_unet_destroy(igm_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  if (c->arena) cudaFree(c->arena);
+  delete c;
+}
+
+int igm_unet_num_params(const igm_ctx* c) { return c ? (int)c->params.size() : IGM_ERR_INVALID; }
+int64_t igm_unet_param_elems(const igm_ctx* c) { return c ? c->param_elems : IGM_ERR_INVALID; }
+
+int igm_unet_param_info(const igm_ctx* c, int index, char* name_buf, int name_cap, int64_t* offset, int32_t* ndim,
+                        int64_t shape[4]) {
+  if (!c || index < 0 || index >= (int)c->params.size()) return IGM_ERR_INVALID;
+  const ParamInfo& p = c->params[index];
+  if (name_buf && name_cap > 0) {
+    strncpy(name_buf, p.name.c_str(), name_cap - 1);
+    name_buf[name_cap - 1] = 0;
+  }
+  if (offset) *offset = p.offset;
+  if (ndim) *ndim = p.ndim;
+  if (shape)
+    for (int i = 0; i < 4; ++i) shape[i] = i < p.ndim ? p.shape[i] : 1;
+  return IGM_OK;
+}
+
+int igm_unet_bind_params(igm_ctx* c, float* params, float* grads) {
+  if (!c || !params) return IGM_ERR_INVALID;
+  if (c->cfg.training && !grads) IGM_FAIL(c->st, IGM_ERR_INVALID, "training context needs a gradient arena");
+  IGM_CUDA(c->st, cudaSetDevice(c->device));
+  c->P = params;
+  c->G = grads;
+  // per-block time projections: fill the device table
+  int k = 0;
+  auto fill = [&](const ResnetL& r) {
+    TimeProj& tp = c->proj_host[k++];
+    tp.w = c->Pp(r.mlp_w); tp.b = c->Pp(r.mlp_b);
+    tp.gw = grads ? c->Gp(r.mlp_w) : nullptr; tp.gb = grads ? c->Gp(r.mlp_b) : nullptr;
+  };
+  for (auto& s : c->downs) { fill(s.r1); fill(s.r2); }
+  for (auto& s : c->ups) { fill(s.r1); fill(s.r2); }
+  fill(c->mid1); fill(c->mid2);
+  IGM_CUDA(c->st, cudaMemcpy(c->proj_dev, c->proj_host.data(), sizeof(TimeProj) * c->n_proj, cudaMemcpyHostToDevice));
+  if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+  return IGM_OK;
+}
+
+static int pack_conv(igm_ctx* c, const LaunchCtx& lc, const ConvL& l) {
+  const int KK = l.K * l.K;
+  const float* w = c->Pp(l.pw);
+  if (!l.convT) {
+    IGM_TRY(launch_pack_weight(lc, w, l.w_fwd, KK, l.Cin, l.Cout, KK, (int64_t)l.Cin * KK));
+    if (l.w_bwd) IGM_TRY(launch_pack_weight(lc, w, l.w_bwd, KK, l.Cout, l.Cin, (int64_t)l.Cin * KK, KK));
+  } else {
+    IGM_TRY(launch_pack_weight(lc, w, l.w_fwd, KK, l.Cin, l.Cout, (int64_t)l.Cout * KK, KK));
+    if (l.w_bwd) IGM_TRY(launch_pack_weight(lc, w, l.w_bwd, KK, l.Cout, l.Cin, KK, (int64_t)l.Cout * KK));
+  }
+  return IGM_OK;
+}
+
+int igm_unet_pack_weights(igm_ctx* c, void* stream) {
+  if (!c) return IGM_ERR_INVALID;
+  if (!c->P) IGM_FAIL(c->st, IGM_ERR_STATE, "bind parameters first");
+  IGM_CUDA(c->st, cudaSetDevice(c->device));
+  LaunchCtx lc = c->lc(stream);
+  auto pack_resnet = [&](const ResnetL& r) -> int {
+    IGM_TRY(pack_conv(c, lc, r.b1.conv));
+    IGM_TRY(pack_conv(c, lc, r.b2.conv));
+    if (r.has_res) IGM_TRY(pack_conv(c, lc, r.res));
+    return IGM_OK;
+  };
+  auto pack_attn = [&](const AttnL& a) -> int {
+    IGM_TRY(pack_conv(c, lc, a.qkv));
+    IGM_TRY(pack_conv(c, lc, a.outc));
+    return IGM_OK;
+  };
+  auto pack_stage = [&](const Stage& s) -> int {
+    IGM_TRY(pack_resnet(s.r1));
+    IGM_TRY(pack_resnet(s.r2));
+    IGM_TRY(pack_attn(s.attn));
+    if (s.rs.present) IGM_TRY(pack_conv(c, lc, s.rs.conv));
+    return IGM_OK;
+  };
+  for (auto& s : c->downs) IGM_TRY(pack_stage(s));
+  for (auto& s : c->ups) IGM_TRY(pack_stage(s));
+  IGM_TRY(pack_resnet(c->mid1));
+  IGM_TRY(pack_attn(c->mid_attn));
+  IGM_TRY(pack_resnet(c->mid2));
+  IGM_TRY(pack_conv(c, lc, c->final_block.conv));
+  if (c->final_wbwd) {
+    // dgrad of the final 1x1: [1][k = c][n = K] = W[c][K]: identical memory order to W itself
+    IGM_TRY(launch_pack_weight(lc, c->Pp(c->final_conv.pw), c->final_wbwd, 1, c->cfg.channels, c->final_conv.Cin,
+                               c->final_conv.Cin, 1));
+  }
+  return IGM_OK;
+}
+
+static int check_ready(igm_ctx* c, int B) {
+  if (!c) return IGM_ERR_INVALID;
+  if (!c->P) IGM_FAIL(c->st, IGM_ERR_STATE, "parameters not bound");
+  if (B < 1 || B > c->cfg.max_batch) IGM_FAIL(c->st, IGM_ERR_INVALID, "batch exceeds max_batch");
+  IGM_CUDA(c->st, cudaSetDevice(c->device));
+  return IGM_OK;
+}
+
+int igm_unet_forward(igm_ctx* c, const float* x, const int64_t* t, float* out, int B, void* stream) {
+  IGM_TRY(check_ready(c, B));
+  if (!x || !t || !out) IGM_FAIL(c->st, IGM_ERR_INVALID, "null tensor");
+  Runner r{*c, c->lc(stream), B};
+  const int HW = c->cfg.height * c->cfg.width;
+  IGM_TRY(launch_input_prep(r.lc, x, nullptr, nullptr, nullptr, nullptr, c->x_in.v, nullptr, B, c->cfg.channels, HW));
+  IGM_TRY(r.forward(t, out));
+  c->last_B = B;
+  c->fwd_valid = true;
+  c->loss_valid = false;
+  return IGM_OK;
+}
+
+int igm_unet_backward(igm_ctx* c, const float* d_out, float* d_x, void* stream) {
+  if (!c) return IGM_ERR_INVALID;
+  if (!c->cfg.training) IGM_FAIL(c->st, IGM_ERR_STATE, "context was created with training = 0");
+  if (!c->fwd_valid) IGM_FAIL(c->st, IGM_ERR_STATE, "backward without a forward");
+  if (!d_out) IGM_FAIL(c->st, IGM_ERR_INVALID, "null tensor");
+  IGM_CUDA(c->st, cudaSetDevice(c->device));
+  const int B = c->last_B;
+  Runner r{*c, c->lc(stream), B};
+  const int HW = c->cfg.height * c->cfg.width;
+  IGM_TRY(launch_nchw_to_nhwc(r.lc, d_out, c->d_pred, B, HW, c->cfg.channels));
+  // d_x (NHWC) is staged in noise_copy, then transposed out
+  float* dx_nhwc = d_x ? c->noise_copy : nullptr;
+  IGM_TRY(r.backward(c->d_pred, dx_nhwc));
+  if (d_x) IGM_TRY(launch_nhwc_to_nchw(r.lc, dx_nhwc, d_x, B, HW, c->cfg.channels));
+  return IGM_OK;
+}
+
+int igm_ddpm_set_schedule(igm_ctx* c, const igm_schedule* s) {
+  if (!c || !s) return IGM_ERR_INVALID;
+  IGM_CUDA(c->st, cudaSetDevice(c->device));
+  c->sched = *s;
+  IGM_CUDA(c->st, cudaMemcpy(c->sched_dev, s, sizeof(igm_schedule), cudaMemcpyHostToDevice));
+  c->have_sched = true;
+  return IGM_OK;
+}
+
+int igm_ddpm_q_sample(igm_ctx* c, const float* x_start, const int64_t* t, const float* noise, float* out, int B,
+                      void* stream) {
+  if (!c) return IGM_ERR_INVALID;
+  if (!c->have_sched) IGM_FAIL(c->st, IGM_ERR_STATE, "schedule not set");
+  if (!x_start || !t || !noise || !out) IGM_FAIL(c->st, IGM_ERR_INVALID, "null tensor");
+  IGM_CUDA(c->st, cudaSetDevice(c->device));
+  LaunchCtx lc = c->lc(stream);
+  return launch_input_prep(lc, x_start, noise, t, c->sched.sqrt_alphas_cumprod, c->sched.sqrt_one_minus_alphas_cumprod,
+                           nullptr, out, B, c->cfg.channels, c->cfg.height * c->cfg.width);
+}
+
+int igm_ddpm_p_losses(igm_ctx* c, const float* x_start, const int64_t* t, const float* noise, float* loss_out, int B,
+                      void* stream) {
+  IGM_TRY(check_ready(c, B));
+  if (!c->have_sched) IGM_FAIL(c->st, IGM_ERR_STATE, "schedule not set");
+  if (!x_start || !t || !noise || !loss_out) IGM_FAIL(c->st, IGM_ERR_INVALID, "null tensor");
+  Runner r{*c, c->lc(stream), B};
+  const int HW = c->cfg.height * c->cfg.width;
+  const int64_t n = (int64_t)B * c->cfg.channels * HW;
+  IGM_TRY(launch_input_prep(r.lc, x_start, noise, t, c->sched.sqrt_alphas_cumprod,
+                            c->sched.sqrt_one_minus_alphas_cumprod, c->x_in.v, nullptr, B, c->cfg.channels, HW));
+  IGM_TRY(r.forward(t, c->pred));
+  IGM_TRY(launch_loss(r.lc, c->pred, noise, n, c->cfg.loss_type, c->loss_ws, loss_out));
+  if (c->cfg.training) {
+    IGM_CUDA(c->st, cudaMemcpyAsync(c->noise_copy, noise, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice,
+                                    (cudaStream_t)stream));
+  }
+  c->last_B = B;
+  c->fwd_valid = true;
+  c->loss_valid = c->cfg.training != 0;
+  return IGM_OK;
+}
+
+int igm_ddpm_p_losses_backward(igm_ctx* c, const float* d_loss, float scale, void* stream) {
+  if (!c) return IGM_ERR_INVALID;
+  if (!c->cfg.training) IGM_FAIL(c->st, IGM_ERR_STATE, "context was created with training = 0");
+  if (!c->loss_valid) IGM_FAIL(c->st, IGM_ERR_STATE, "p_losses_backward without p_losses");
+  IGM_CUDA(c->st, cudaSetDevice(c->device));
+  const int B = c->last_B;
+  Runner r{*c, c->lc(stream), B};
+  const int HW = c->cfg.height * c->cfg.width;
+  const int64_t n = (int64_t)B * c->cfg.channels * HW;
+  IGM_TRY(launch_loss_backward_nhwc(r.lc, c->pred, c->noise_copy, n, c->cfg.channels, HW, c->cfg.loss_type,
+                                    d_loss, scale, c->d_pred));
+  IGM_TRY(r.backward(c->d_pred, nullptr));
+  return IGM_OK;
+}
+
+static int sampler_step(igm_ctx* c, Runner& r, float* img, const float* noise, uint64_t seed, int clip) {
+  const int HW = c->cfg.height * c->cfg.width;
+  const int64_t n = (int64_t)r.B * c->cfg.channels * HW;
+  IGM_TRY(launch_sampler_tick(r.lc, c->t_vec, r.B, c->loop_state));
+  IGM_TRY(launch_input_prep(r.lc, img, nullptr, nullptr, nullptr, nullptr, c->x_in.v, nullptr, r.B, c->cfg.channels, HW));
+  IGM_TRY(r.forward(c->t_vec, c->pred));
+  SamplerStepArgs a;
+  a.img = img; a.eps = c->pred; a.noise = noise; a.t_dev = c->t_vec; a.sched_dev = c->sched_dev;
+  a.seed = seed; a.step_dev = c->loop_state + 1; a.n = n; a.per_sample = c->cfg.channels * HW; a.clip = clip;
+  IGM_TRY(launch_sampler_update(r.lc, a));
+  return IGM_OK;
+}
+
+int igm_ddpm_sample_loop(igm_ctx* c, float* img, const float* noise, uint64_t seed, int B, int t_start, int n_steps,
+                         int clip_denoised, void* stream) {
+  IGM_TRY(check_ready(c, B));
+  if (!c->have_sched) IGM_FAIL(c->st, IGM_ERR_STATE, "schedule not set");
+  if (!img) IGM_FAIL(c->st, IGM_ERR_INVALID, "null tensor");
+  if (t_start < 0 || t_start >= c->cfg.timesteps || n_steps < 0 || n_steps > t_start + 1)
+    IGM_FAIL(c->st, IGM_ERR_INVALID, "bad t_start / n_steps");
+  if (n_steps == 0) return IGM_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  Runner r{*c, c->lc(stream), B};
+  const int init[2] = {t_start, 0};
+  IGM_CUDA(c->st, cudaMemcpyAsync(c->loop_state, init, sizeof(init), cudaMemcpyHostToDevice, s));
+  // first step eagerly (also resolves lazy per-kernel attributes outside of stream capture)
+  const int64_t before = c->launches;
+  IGM_TRY(sampler_step(c, r, img, noise, seed, clip_denoised));
+  const int64_t per_step = c->launches - before;
+  if (n_steps == 1) { c->fwd_valid = false; return IGM_OK; }
+  igm_ctx::GraphKey key;
+  key.img = img; key.noise = noise; key.seed = seed; key.B = B; key.clip = clip_denoised;
+  if (!c->graph_exec || !(c->graph_key == key)) {
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    cudaStream_t cs = s;
+    bool own = false;
+    if (s == 0 || s == cudaStreamLegacy) {   // the legacy stream cannot be captured
+      IGM_CUDA(c->st, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      own = true;
+    }
+    const int64_t saved = c->launches;
+    IGM_CUDA(c->st, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    Runner rc{*c, c->lc((void*)cs), B};
+    int rcode = sampler_step(c, rc, img, noise, seed, clip_denoised);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(cs, &graph);
+    c->launches = saved;   // capture enqueues nothing
+    if (own) cudaStreamDestroy(cs);
+    if (rcode != IGM_OK) { if (graph) cudaGraphDestroy(graph); return rcode; }
+    if (e != cudaSuccess) IGM_FAIL(c->st, IGM_ERR_CUDA, cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { c->graph_exec = nullptr; IGM_FAIL(c->st, IGM_ERR_CUDA, cudaGetErrorString(e)); }
+    c->graph_key = key;
+  }
+  for (int k = 1; k < n_steps; ++k) {
+    IGM_CUDA(c->st, cudaGraphLaunch(c->graph_exec, s));
+  }
+  c->launches += (int64_t)(n_steps - 1) * per_step;   // each replay runs the same kernels as the eager step
+  c->fwd_valid = false;
+  c->loss_valid = false;
+  return IGM_OK;
+}
+
+int igm_adam_step(igm_ctx* c, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
+  if (!c) return IGM_ERR_INVALID;
+  if (!params || !grads || !exp_avg || !exp_avg_sq || n < 0 || step < 1) IGM_FAIL(c->st, IGM_ERR_INVALID, "bad adam args");
+  IGM_CUDA(c->st, cudaSetDevice(c->device));
+  LaunchCtx lc = c->lc(stream);
+  return launch_adam(lc, params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale);
+}
+
+int64_t igm_debug_read_tap(igm_ctx* c, const char* name, float* dst, int64_t cap, void* stream) {
+  if (!c || !name) return IGM_ERR_INVALID;
+  auto it = c->taps.find(name);
+  if (it == c->taps.end()) { set_error(c->st, IGM_ERR_INVALID, __FILE__, __LINE__, "unknown tap"); return IGM_ERR_INVALID; }
+  const Act& a = it->second;
+  const int B = c->last_B > 0 ? c->last_B : c->cfg.max_batch;
+  const int64_t n = (int64_t)B * a.C * a.H * a.W;
+  if (!dst) return n;
+  if (cap < n) { set_error(c->st, IGM_ERR_INVALID, __FILE__, __LINE__, "tap buffer too small"); return IGM_ERR_INVALID; }
+  if (cudaSetDevice(c->device) != cudaSuccess) return IGM_ERR_CUDA;
+  LaunchCtx lc = c->lc(stream);
+  int r = launch_nhwc_to_nchw(lc, a.v, dst, B, a.H * a.W, a.C);
+  return r == IGM_OK ? n : r;
+}
+
+int64_t igm_launch_count(const igm_ctx* c) { return c ? c->launches : IGM_ERR_INVALID; }
+
+int igm_set_conv_engine(igm_ctx* c, int engine) {
+  if (!c) return IGM_ERR_INVALID;
+  if (engine != 0) IGM_FAIL(c->st, IGM_ERR_INVALID, "only the SIMT engine (0) is built in this version");
+  c->conv_engine = engine;
+  return IGM_OK;
+}
+int igm_get_conv_engine(const igm_ctx* c) { return c ? c->conv_engine : IGM_ERR_INVALID; }
+
+}  // extern "C"

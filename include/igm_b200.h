@@ -1,0 +1,153 @@
+/*
+ * igm_b200.h — C ABI of libigm_b200.so: the B200 (sm_100a) implementation of the
+ * DDPM U-Net hot path of Victarry/Image-Generation-models.
+ *
+ * The reference has no FFI (it is 100 % Python on torch ATen); the seam this ABI
+ * attaches to is the Python class surface listed in SURVEY.md section 8(b).
+ * Each entry point below names the reference method (file:line under
+ * /root/reference) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - tensors at the boundary are fp32, NCHW, contiguous; timesteps are int64
+ *     (what torch hands the reference);
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *     all work is enqueued asynchronously on it;
+ *   - every call returns 0 on success or a negative IGM_ERR_* code; the message
+ *     is retrievable with igm_last_error(ctx) (ctx may be NULL for create errors);
+ *   - the caller (PyTorch) owns parameters, gradients, Adam moments and all
+ *     input/output tensors; the context owns packed weights, activations,
+ *     workspaces and CUDA graphs.  No allocation happens after igm_unet_create.
+ *   - one context per (process, device); not thread-safe.
+ */
+#ifndef IGM_B200_H
+#define IGM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IGM_OK 0
+#define IGM_ERR_INVALID (-1)   /* bad argument / unsupported shape            */
+#define IGM_ERR_CUDA (-2)      /* a CUDA runtime / driver call failed         */
+#define IGM_ERR_STATE (-3)     /* call order violated (e.g. backward w/o fwd) */
+#define IGM_ERR_NOMEM (-4)
+
+#define IGM_MAX_MULTS 8
+
+typedef struct igm_ctx igm_ctx;
+
+/* Shape of reference Unet(dim, channels, dim_mults) — src/models/ddpm.py:170-236 —
+ * plus the image size BaseModel reads from the datamodule config
+ * (src/models/base.py:20-22) and the diffusion length (ddpm.py:302). */
+typedef struct igm_unet_cfg {
+  int32_t dim;                       /* hidden_dim, multiple of 32            */
+  int32_t channels;                  /* image channels (1 or 3)               */
+  int32_t n_mults;
+  int32_t dim_mults[IGM_MAX_MULTS];
+  int32_t height, width;
+  int32_t max_batch;                 /* activations are sized for this batch  */
+  int32_t timesteps;                 /* T of GaussianDiffusion                */
+  int32_t loss_type;                 /* 1 = l1 (ddpm.py:453), 2 = l2 (:455)   */
+  int32_t training;                  /* 1: keep activations + grad workspaces */
+} igm_unet_cfg;
+
+/* Names the 12 schedule buffers of GaussianDiffusion.__init__ (ddpm.py:325-350);
+ * each points at T fp32 values (device memory, caller-owned, must outlive ctx). */
+typedef struct igm_schedule {
+  const float* sqrt_alphas_cumprod;            /* ddpm.py:330 */
+  const float* sqrt_one_minus_alphas_cumprod;  /* ddpm.py:331 */
+  const float* sqrt_recip_alphas_cumprod;      /* ddpm.py:333 */
+  const float* sqrt_recipm1_alphas_cumprod;    /* ddpm.py:334 */
+  const float* posterior_log_variance_clipped; /* ddpm.py:344 */
+  const float* posterior_mean_coef1;           /* ddpm.py:345 */
+  const float* posterior_mean_coef2;           /* ddpm.py:346 */
+} igm_schedule;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+int igm_version(void);
+const char* igm_last_error(const igm_ctx* ctx);
+
+/* Builds the layer plan of Unet.__init__ (ddpm.py:170-236) for `cfg` on CUDA
+ * device `device`, allocating every activation / workspace buffer once. */
+int igm_unet_create(igm_ctx** out, const igm_unet_cfg* cfg, int device);
+void igm_unet_destroy(igm_ctx* ctx);
+
+/* ---- parameters ---------------------------------------------------------- */
+/* Number of parameter tensors and total fp32 elements, in the exact order and
+ * shapes of reference Unet(...).state_dict() (the flat arena layout). */
+int igm_unet_num_params(const igm_ctx* ctx);
+int64_t igm_unet_param_elems(const igm_ctx* ctx);
+/* name_buf receives e.g. "downs.0.0.block1.block.0.weight"; shape gets <=4 dims. */
+int igm_unet_param_info(const igm_ctx* ctx, int index, char* name_buf, int name_cap,
+                        int64_t* offset, int32_t* ndim, int64_t shape[4]);
+/* Bind the caller-owned flat fp32 arenas (params, grads: igm_unet_param_elems
+ * elements each; grads may be NULL for inference).  nn.Parameter tensors of the
+ * host-side mirror are views into these arenas, so state_dict() keeps the
+ * reference's keys and NCHW shapes. */
+int igm_unet_bind_params(igm_ctx* ctx, float* params, float* grads);
+/* Re-pack bound parameters into the kernels' tap-major layouts.  Must be called
+ * after the parameters change (load_state_dict, optimizer step). */
+int igm_unet_pack_weights(igm_ctx* ctx, void* stream);
+
+/* ---- U-Net ---------------------------------------------------------------- */
+/* Unet.forward(x, time) — ddpm.py:238-261.  x,out: [B,C,H,W] fp32; t: [B] int64. */
+int igm_unet_forward(igm_ctx* ctx, const float* x, const int64_t* t, float* out, int B,
+                     void* stream);
+/* Autograd of the last igm_unet_forward: d_out [B,C,H,W] -> ACCUMULATES parameter
+ * gradients into the bound grad arena (like torch autograd into .grad) and, if
+ * d_x is not NULL, writes dL/dx. */
+int igm_unet_backward(igm_ctx* ctx, const float* d_out, float* d_x, void* stream);
+
+/* ---- diffusion ------------------------------------------------------------ */
+int igm_ddpm_set_schedule(igm_ctx* ctx, const igm_schedule* sched);
+/* GaussianDiffusion.q_sample — ddpm.py:433-444. */
+int igm_ddpm_q_sample(igm_ctx* ctx, const float* x_start, const int64_t* t, const float* noise,
+                      float* out, int B, void* stream);
+/* GaussianDiffusion.p_losses — ddpm.py:446-460: q_sample + Unet.forward + l1/l2
+ * mean loss, fused.  loss_out: 1 fp32 on the device. */
+int igm_ddpm_p_losses(igm_ctx* ctx, const float* x_start, const int64_t* t, const float* noise,
+                      float* loss_out, int B, void* stream);
+/* d(loss)/d(params) of the last igm_ddpm_p_losses, accumulated into the grad
+ * arena, seeded with  scale * (d_loss ? *d_loss : 1)  where d_loss is the
+ * upstream gradient of the scalar loss as a DEVICE scalar (what autograd hands
+ * loss.backward(); reading it on the device avoids a host sync) and `scale` a
+ * host-side factor (1/world_size for a data-parallel mean). */
+int igm_ddpm_p_losses_backward(igm_ctx* ctx, const float* d_loss, float scale, void* stream);
+/* GaussianDiffusion.p_sample — ddpm.py:378-397 — for n_steps consecutive steps
+ * t = t_start, t_start-1, ... (p_sample_loop, ddpm.py:406-407, when
+ * t_start = T-1 and n_steps = T).  img [B,C,H,W] is updated in place.
+ *   noise != NULL: [n_steps,B,C,H,W] injected draws (parity mode);
+ *   noise == NULL: Philox4x32-10 + Box-Muller draws keyed by (seed, step, element).
+ * The step is captured once into a CUDA graph and replayed n_steps times with
+ * no host work in between. */
+int igm_ddpm_sample_loop(igm_ctx* ctx, float* img, const float* noise, uint64_t seed, int B,
+                         int t_start, int n_steps, int clip_denoised, void* stream);
+
+/* ---- optimiser ------------------------------------------------------------ */
+/* torch.optim.Adam step as configured at ddpm.py:502-512 (no weight decay, no
+ * amsgrad) over n contiguous fp32 elements; grads are multiplied by grad_scale
+ * first (1/world_size after an all-reduce SUM).  `step` is 1-based. */
+int igm_adam_step(igm_ctx* ctx, float* params, const float* grads, float* exp_avg,
+                  float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
+                  int step, float grad_scale, void* stream);
+
+/* ---- introspection (tests / profiling) ------------------------------------ */
+/* Copies the named intermediate of the last forward (same names as
+ * oracle/ddpm_oracle.py taps, e.g. "downs.0.0.block1.conv") to dst as NCHW fp32.
+ * Returns the element count, or a negative error.  dst may be NULL to query. */
+int64_t igm_debug_read_tap(igm_ctx* ctx, const char* name, float* dst_nchw, int64_t cap,
+                           void* stream);
+/* Number of kernels the library launched on behalf of this context so far. */
+int64_t igm_launch_count(const igm_ctx* ctx);
+/* Which conv engine is active: 0 = SIMT fp32 implicit GEMM, 1 = tcgen05 bf16x3. */
+int igm_set_conv_engine(igm_ctx* ctx, int engine);
+int igm_get_conv_engine(const igm_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IGM_B200_H */

@@ -1,0 +1,88 @@
+"""CPU: host-side mirror (module tree, state_dict contract, flat arenas) and the C-ABI
+library surface (loads, exports every symbol include/igm_b200.h declares).  No compute calls."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import igm_b200
+from igm_b200 import _lib
+from oracle import ddpm_oracle as O
+from oracle import ref_loader
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "igm_b200.h")).read()
+    declared = set(re.findall(r"\b(igm_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/igm_b200.h but not exported"
+    assert declared == set(_lib.SYMBOLS), "ctypes table and header disagree"
+    assert _lib.load().igm_version() >= 100
+
+
+@pytest.mark.parametrize("cfg", [(64, 3, (1, 2, 4)), (64, 3, (1, 2, 4, 8)), (64, 1, (2, 4)), (32, 3, (1, 2))])
+def test_state_dict_contract(cfg):
+    dim, ch, mults = cfg
+    u = igm_b200.Unet(dim=dim, channels=ch, dim_mults=mults)
+    shapes = O.param_shapes(O.UnetSpec(dim, ch, mults))
+    sd = u.state_dict()
+    assert list(sd.keys()) == list(shapes.keys())
+    assert all(tuple(sd[k].shape) == shapes[k] for k in sd)
+    # every parameter (and its grad) is a view into the flat arenas at the recorded offset
+    for (name, off, shape), p in zip(u._layout, u.parameters()):
+        assert p.data_ptr() == u._flat.data_ptr() + 4 * off
+        assert p.grad.data_ptr() == u._flat_grad.data_ptr() + 4 * off
+        assert off % 4 == 0
+
+
+def test_flat_arena_tracks_inplace_updates_and_load_state_dict():
+    u = igm_b200.Unet(dim=32, channels=3, dim_mults=(1, 2))
+    v0 = u._flat._version
+    sd = {k: torch.full_like(v, 0.5) for k, v in u.state_dict().items()}
+    u.load_state_dict(sd)
+    assert u._flat._version != v0
+    n = sum(p.numel() for p in u.parameters())
+    assert abs(u._flat.sum().item() - 0.5 * n) < 1e-2
+    opt = torch.optim.SGD(u.parameters(), lr=1.0)
+    for p in u.parameters():
+        p.grad.fill_(0.25)
+    v1 = u._flat._version
+    opt.step()
+    assert u._flat._version != v1
+    assert abs(u._flat.sum().item() - 0.25 * n) < 1e-2
+    opt.zero_grad()          # set_to_none=True drops the views ...
+    u.attach_grads()         # ... and attach_grads() restores them onto a zeroed arena
+    assert all(p.grad is not None for p in u.parameters())
+    assert float(u._flat_grad.abs().sum()) == 0.0
+
+
+def test_ddpm_module_matches_reference_keys_and_schedule():
+    dm = ref_loader.datamodule_cfg(3, 32, 32)
+    torch.manual_seed(0)
+    d = igm_b200.DDPM(dm, hidden_dim=64, dim_mults=(1, 2, 4), lr=1e-4, b1=0.9, b2=0.999)
+    sd = d.state_dict()
+    assert len(sd) == 368          # 368 keys for the CIFAR-10 config
+    buf = O.diffusion_buffers(1000)
+    for k in O.SCHEDULE_KEYS:
+        assert torch.equal(sd[f"diffusion_model.{k}"], buf[k]), k
+    assert d.hparams.lr == 1e-4 and d.hparams.b1 == 0.9
+    if ref_loader.available():
+        ref = ref_loader.load("ddpm")
+        torch.manual_seed(0)
+        r = ref.DDPM(dm, hidden_dim=64, dim_mults=(1, 2, 4), lr=1e-4, b1=0.9, b2=0.999)
+        rs = r.state_dict()
+        assert list(rs.keys()) == list(sd.keys())
+        # same construction order => same default init under the same seed
+        assert all(torch.equal(rs[k], sd[k]) for k in rs)
+
+
+def test_no_cpu_fallback():
+    u = igm_b200.Unet(dim=32, channels=3, dim_mults=(1, 2))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        u(torch.zeros(1, 3, 16, 16), torch.zeros(1, dtype=torch.long))
