@@ -22,6 +22,11 @@ class Schedule(C.Structure):
         "posterior_mean_coef2")]
 
 
+class ProfileEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("ms", C.c_double), ("flops", C.c_double),
+                ("bytes", C.c_double)]
+
+
 # every symbol include/igm_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -45,6 +50,8 @@ SYMBOLS = {
     "igm_adam_step": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_int, C.c_float, _P]),
     "igm_debug_read_tap": (C.c_int64, [_P, C.c_char_p, _P, C.c_int64, _P]),
+    "igm_profile_start": (C.c_int, [_P]),
+    "igm_profile_stop": (C.c_int, [_P, C.POINTER(ProfileEntry), C.c_int]),
     "igm_launch_count": (C.c_int64, [_P]),
     "igm_set_conv_engine": (C.c_int, [_P, C.c_int]),
     "igm_get_conv_engine": (C.c_int, [_P]),

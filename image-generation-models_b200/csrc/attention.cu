@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(256) linattn_bwd_kernel(const float* __restric
 
 int launch_linattn_forward(const LaunchCtx& lc, const float* qkv, float* out, float* ctx, float* kstat,
                            int B, int n) {
+  ProfScope ps_(lc, K_ATTN, 4.0 * B * kHeads * (double)n * D * D, 4.0 * B * (double)n * (QKV + HD));
   linattn_fwd_kernel<<<B * kHeads, 256, 0, lc.stream>>>(qkv, out, ctx, kstat, n);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
@@ -251,6 +252,7 @@ int launch_linattn_forward(const LaunchCtx& lc, const float* qkv, float* out, fl
 
 int launch_linattn_backward(const LaunchCtx& lc, const float* qkv, const float* ctx, const float* kstat,
                             const float* d_out, float* d_qkv, int B, int n) {
+  ProfScope ps_(lc, K_ATTN, 8.0 * B * kHeads * (double)n * D * D, 4.0 * B * (double)n * (2 * QKV + HD));
   linattn_bwd_kernel<<<B * kHeads, 256, 0, lc.stream>>>(qkv, ctx, kstat, d_out, d_qkv, n);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;

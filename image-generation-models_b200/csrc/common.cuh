@@ -42,12 +42,49 @@ void set_error(Status& st, int code, const char* file, int line, const char* wha
     if (_r != IGM_OK) return _r; \
   } while (0)
 
+// Kernel classes for the built-in event profiler (igm_profile_start/stop)
+enum KClass {
+  K_CONV_FPROP = 0, K_CONV_DGRAD, K_CONV_WGRAD, K_NORM, K_ATTN, K_TIME, K_ELEM, K_ADAM, K_PACK, K_NCLASS
+};
+const char* kclass_name(int k);
+
+// CUDA-event profiler: one (start, stop) pair around every launch while enabled.  Used by
+// bench.py's roofline pass only (never during the timed region).
+struct Profiler {
+  bool on = false;
+  struct Rec { cudaEvent_t a, b; int cls; double flops, bytes; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get();
+  void reset();
+};
+
 // Launch bookkeeping: every kernel launch goes through this so that
 // igm_launch_count() is exact and launch errors are caught where they happen.
 struct LaunchCtx {
   cudaStream_t stream = 0;
   Status* st = nullptr;
   int64_t* counter = nullptr;
+  Profiler* prof = nullptr;
+};
+
+struct ProfScope {
+  Profiler* p = nullptr;
+  cudaStream_t s = 0;
+  size_t idx = 0;
+  ProfScope(const LaunchCtx& lc, int cls, double flops, double bytes) {
+    if (lc.prof && lc.prof->on) {
+      p = lc.prof;
+      s = lc.stream;
+      Profiler::Rec r{p->get(), p->get(), cls, flops, bytes};
+      idx = p->recs.size();
+      p->recs.push_back(r);
+      cudaEventRecord(r.a, s);
+    }
+  }
+  ~ProfScope() {
+    if (p) cudaEventRecord(p->recs[idx].b, s);
+  }
 };
 
 inline int post_launch(const LaunchCtx& lc, const char* file, int line) {
@@ -94,6 +131,7 @@ struct ConvArgs {
   float* out0 = nullptr;        // n <  N0 -> out0[m*N0 + n]
   float* out1 = nullptr;        // n >= N0 -> out1[m*(N-N0) + n-N0]   (null when N0 == N)
   int N0 = 0;
+  int kclass = K_CONV_FPROP;    // profiler class (fprop / dgrad)
   const float* add0 = nullptr;  // optional addends with the same split
   const float* add1 = nullptr;
 };

@@ -417,6 +417,10 @@ int launch_conv(const LaunchCtx& lc, const ConvArgs& a) {
   const int OHp = cdiv(a.OH, ps), OWp = cdiv(a.OW, ps);
   const int64_t Mp = (int64_t)a.B * OHp * OWp;
   dim3 grid((unsigned)cdiv64(Mp, BM), (unsigned)cdiv(a.N, BN), (unsigned)(ps * ps));
+  const double flops = 2.0 * a.B * a.OH * a.OW * (double)a.N * Ctot * a.KH * a.KW / (a.transposed ? a.stride * a.stride : 1);
+  const double bytes = 4.0 * ((double)a.B * a.IH * a.IW * Ctot + (double)a.B * a.OH * a.OW * a.N * (a.add0 ? 2 : 1) +
+                              (double)a.KH * a.KW * Ctot * a.N);
+  ProfScope ps_(lc, a.kclass, flops, bytes);
   const bool vec = (a.C0 % BK == 0) && (a.C1 % BK == 0) && (a.N % 4 == 0) && (a.N0 % 4 == 0) && Ctot > 0;
   if (vec)
     conv_igemm_kernel<true><<<grid, 256, 0, lc.stream>>>(a);
@@ -440,6 +444,8 @@ int launch_wgrad(const LaunchCtx& lc, const WgradArgs& a) {
   pix_per_split = cdiv(pix_per_split, WK) * WK;
   split = (int)cdiv64(npix, pix_per_split);
   dim3 grid((unsigned)split, (unsigned)(q_tiles * p_tiles), (unsigned)taps);
+  ProfScope ps_(lc, K_CONV_WGRAD, 2.0 * npix * (double)a.PC * a.QC * taps,
+                4.0 * (npix * (double)a.PC + (double)a.B * a.QH * a.QW * a.QC + (double)taps * a.PC * a.QC));
   const bool qv = a.QC % 4 == 0, pv = a.PC % 4 == 0;
   if (qv && pv)
     wgrad_kernel<true, true><<<grid, 256, 0, lc.stream>>>(a, pix_per_split, p_tiles);
@@ -459,6 +465,7 @@ int launch_colsum(const LaunchCtx& lc, const float* x, int64_t M, int N, float* 
   if (splits < 1) splits = 1;
   const int rows = (int)cdiv64(M, splits);
   dim3 grid((unsigned)cdiv64(M, rows), (unsigned)cdiv(N, 32));
+  ProfScope ps_(lc, K_CONV_WGRAD, (double)M * N, 4.0 * M * N);
   colsum_kernel<<<grid, dim3(32, 8), 0, lc.stream>>>(x, M, N, out, rows);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
@@ -469,6 +476,7 @@ int launch_pack_weight(const LaunchCtx& lc, const float* src, float* dst, int ta
   const int64_t total = (int64_t)taps * K * N;
   int blocks = (int)cdiv64(total, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
+  ProfScope ps_(lc, K_PACK, 0.0, 8.0 * total);
   pack_weight_kernel<<<blocks, 256, 0, lc.stream>>>(src, dst, taps, K, N, sk, sn);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;

@@ -257,6 +257,7 @@ int launch_input_prep(const LaunchCtx& lc, const float* x_nchw, const float* noi
                       const float* sqrt_ac, const float* sqrt_1mac, float* out_nhwc, float* out_nchw, int B,
                       int C, int HW) {
   const int64_t n = (int64_t)B * HW;
+  ProfScope ps_(lc, K_ELEM, 3.0 * n * C, 8.0 * n * C);
   input_prep_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, lc.stream>>>(x_nchw, noise_nchw, t, sqrt_ac, sqrt_1mac,
                                                                      out_nhwc, out_nchw, B, C, HW);
   IGM_POST_LAUNCH(lc);
@@ -267,6 +268,7 @@ int launch_final_conv(const LaunchCtx& lc, const float* act, const float* w, con
                       int B, int HW, int K, int C) {
   if (C > 4 || K % 4 != 0) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "final conv: channels <= 4 and K % 4 == 0 required");
   const int64_t threads = (int64_t)B * HW * 8;
+  ProfScope ps_(lc, K_CONV_FPROP, 2.0 * B * HW * (double)K * C, 4.0 * B * HW * (double)(K + C));
   final_conv_kernel<<<(unsigned)cdiv64(threads, 256), 256, (size_t)C * K * sizeof(float), lc.stream>>>(
       act, w, b, out_nchw, B, HW, K, C);
   IGM_POST_LAUNCH(lc);
@@ -275,6 +277,7 @@ int launch_final_conv(const LaunchCtx& lc, const float* act, const float* w, con
 
 int launch_loss(const LaunchCtx& lc, const float* pred, const float* noise, int64_t n, int loss_type, float* ws,
                 float* loss_out) {
+  ProfScope ps_(lc, K_ELEM, 2.0 * n, 8.0 * n);
   loss_partial_kernel<<<LOSS_CTAS, 256, 0, lc.stream>>>(pred, noise, n, loss_type, ws);
   IGM_POST_LAUNCH(lc);
   loss_final_kernel<<<1, 32, 0, lc.stream>>>(ws, LOSS_CTAS, n, loss_out);
@@ -284,6 +287,7 @@ int launch_loss(const LaunchCtx& lc, const float* pred, const float* noise, int6
 
 int launch_loss_backward_nhwc(const LaunchCtx& lc, const float* pred, const float* noise, int64_t n, int C,
                               int HW, int loss_type, const float* d_loss, float scale, float* d_nhwc) {
+  ProfScope ps_(lc, K_ELEM, 2.0 * n, 12.0 * n);
   loss_backward_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, lc.stream>>>(pred, noise, n, C, HW, loss_type, d_loss,
                                                                         scale / (float)n, d_nhwc);
   IGM_POST_LAUNCH(lc);
@@ -292,6 +296,7 @@ int launch_loss_backward_nhwc(const LaunchCtx& lc, const float* pred, const floa
 
 int launch_nchw_to_nhwc(const LaunchCtx& lc, const float* src, float* dst, int B, int HW, int C) {
   const int64_t n = (int64_t)B * HW * C;
+  ProfScope ps_(lc, K_ELEM, 0.0, 8.0 * n);
   nchw_to_nhwc_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, lc.stream>>>(src, dst, B, HW, C);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
@@ -299,6 +304,7 @@ int launch_nchw_to_nhwc(const LaunchCtx& lc, const float* src, float* dst, int B
 
 int launch_nhwc_to_nchw(const LaunchCtx& lc, const float* src, float* dst, int B, int HW, int C) {
   const int64_t n = (int64_t)B * HW * C;
+  ProfScope ps_(lc, K_ELEM, 0.0, 8.0 * n);
   nhwc_to_nchw_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, lc.stream>>>(src, dst, B, HW, C);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
@@ -306,6 +312,7 @@ int launch_nhwc_to_nchw(const LaunchCtx& lc, const float* src, float* dst, int B
 
 int launch_sampler_update(const LaunchCtx& lc, const SamplerStepArgs& a) {
   const int64_t n4 = cdiv64(a.n, 4);
+  ProfScope ps_(lc, K_ELEM, 12.0 * a.n, 4.0 * a.n * (a.noise ? 4 : 3));
   sampler_update_kernel<<<(unsigned)cdiv64(n4, 256), 256, 0, lc.stream>>>(a);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
@@ -319,6 +326,7 @@ int launch_sampler_tick(const LaunchCtx& lc, int64_t* t_vec, int B, int* state) 
 
 int launch_add(const LaunchCtx& lc, float* dst, const float* src, int64_t n) {
   const int64_t n4 = n / 4;
+  ProfScope ps_(lc, K_ELEM, 1.0 * n, 12.0 * n);
   add_kernel<<<(unsigned)cdiv64(n4 > 0 ? n4 : 1, 256), 256, 0, lc.stream>>>(dst, src, n4, n);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
@@ -333,6 +341,7 @@ int launch_adam(const LaunchCtx& lc, float* p, const float* g, float* m, float* 
   int blocks = (int)cdiv64(n, 256 * 4);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
+  ProfScope ps_(lc, K_ADAM, 12.0 * n, 28.0 * n);
   adam_kernel<<<blocks, 256, 0, lc.stream>>>(p, g, m, v, n, b1, b2, eps, step_size, bc2_sqrt, grad_scale);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;

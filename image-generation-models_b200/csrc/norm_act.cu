@@ -445,6 +445,7 @@ static int check_gn_shape(const LaunchCtx& lc, int C) {
 int launch_gn_partial(const LaunchCtx& lc, const float* y, int B, int HW, int C, float* part) {
   IGM_TRY(check_gn_shape(lc, C));
   const int nchunks = cdiv(HW, kGnChunk);
+  ProfScope ps_(lc, K_NORM, 3.0 * B * HW * C, 4.0 * B * HW * C);
   gn_partial_kernel<<<B * nchunks, 256, 0, lc.stream>>>(y, HW, C, nchunks, part);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
@@ -455,6 +456,7 @@ int launch_gn_apply(const LaunchCtx& lc, const float* y, const float* part, cons
                     float* stats, int B, int HW, int C) {
   IGM_TRY(check_gn_shape(lc, C));
   const int nchunks = cdiv(HW, kGnChunk);
+  ProfScope ps_(lc, K_NORM, 30.0 * B * HW * C, 4.0 * B * HW * C * (res ? 3 : 2));
   gn_apply_kernel<<<B * nchunks, 256, 0, lc.stream>>>(y, part, gamma, beta, temb, temb_stride, res, out,
                                                       stats, HW, C, nchunks);
   IGM_POST_LAUNCH(lc);
@@ -464,6 +466,7 @@ int launch_gn_apply(const LaunchCtx& lc, const float* y, const float* part, cons
 int launch_gn_backward(const LaunchCtx& lc, const GnBwdArgs& a) {
   IGM_TRY(check_gn_shape(lc, a.C));
   const int nchunks = cdiv(a.HW, kGnChunk);
+  ProfScope ps_(lc, K_NORM, 80.0 * a.B * a.HW * a.C, 4.0 * a.B * a.HW * a.C * 5);
   gn_bwd_reduce_kernel<<<a.B * nchunks, 256, 0, lc.stream>>>(a, nchunks);
   IGM_POST_LAUNCH(lc);
   gn_bwd_apply_kernel<<<a.B * nchunks, 256, 0, lc.stream>>>(a, nchunks);
@@ -483,6 +486,7 @@ static int ln_grid(int64_t M) {
 int launch_ln_forward(const LaunchCtx& lc, const float* x, const float* g, const float* b, float* out,
                       int64_t M, int C) {
   if (C % 4 != 0 || C > 1024) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "LayerNorm: C must be a multiple of 4, <= 1024");
+  ProfScope ps_(lc, K_NORM, 8.0 * M * C, 8.0 * M * C);
   ln_forward_kernel<<<ln_grid(M), 256, 0, lc.stream>>>(x, g, b, out, M, C);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
@@ -494,6 +498,7 @@ int launch_ln_backward(const LaunchCtx& lc, const float* d_out, const float* x, 
                        const float* d_res, float* dx, float* dg, float* db, float* ws, int64_t M, int C) {
   if (C % 4 != 0 || C > 1024) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "LayerNorm: C must be a multiple of 4, <= 1024");
   const int grid = ln_grid(M);
+  ProfScope ps_(lc, K_NORM, 20.0 * M * C, 4.0 * M * C * (d_res ? 4 : 3));
   const size_t smem = (size_t)8 * 2 * C * sizeof(float);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(ln_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -187,6 +187,7 @@ __global__ void time_mlp_wgrad_kernel(const TimeMlpParams p, int B, const float*
 int launch_time_mlp_forward(const LaunchCtx& lc, const TimeMlpParams& p, const int64_t* t, int B, float* emb,
                             float* h1, float* temb, float* act) {
   if (p.dim > 256 || 256 % p.dim != 0) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "time_mlp: dim must divide 256");
+  ProfScope ps_(lc, K_TIME, 16.0 * B * p.dim * p.dim, 0.0);
   const size_t smem = (size_t)5 * p.dim * sizeof(float);
   time_mlp_fwd_kernel<<<B, 256, smem, lc.stream>>>(p, t, emb, h1, temb, act);
   IGM_POST_LAUNCH(lc);
@@ -197,6 +198,7 @@ int launch_time_proj_forward(const LaunchCtx& lc, const TimeProj* d_table, int n
                              int dim, int B, int total, float* proj) {
   // every projection width is a multiple of 32, so slabs = total / 32
   const int slabs = total / 32;
+  ProfScope ps_(lc, K_TIME, 2.0 * B * dim * total, 0.0);
   const size_t smem = (size_t)32 * (dim + 1) * sizeof(float);
   time_proj_fwd_kernel<<<slabs, 256, smem, lc.stream>>>(d_table, n_proj, act, dim, B, total, proj);
   IGM_POST_LAUNCH(lc);
@@ -210,6 +212,7 @@ int launch_time_backward(const LaunchCtx& lc, const TimeMlpParams& p, const Time
   float* d_temb = ws;
   float* d_h1 = ws + (int64_t)B * d;
   const int slabs = total / 32;
+  ProfScope ps_(lc, K_TIME, 6.0 * B * d * total, 0.0);
   time_proj_wgrad_kernel<<<slabs, 256, 0, lc.stream>>>(d_table, n_proj, act, d, B, total, d_proj);
   IGM_POST_LAUNCH(lc);
   const size_t smem = (size_t)(total + 256 + d) * sizeof(float);

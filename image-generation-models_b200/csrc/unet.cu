@@ -23,6 +23,31 @@ void set_error(Status& st, int code, const char* file, int line, const char* wha
   st.msg = buf;
 }
 
+const char* kclass_name(int k) {
+  static const char* names[K_NCLASS] = {"conv_fprop", "conv_dgrad", "conv_wgrad", "norm_act", "attention",
+                                        "time_mlp",   "elementwise", "adam",      "pack"};
+  return (k >= 0 && k < K_NCLASS) ? names[k] : "?";
+}
+
+cudaEvent_t Profiler::get() {
+  cudaEvent_t e;
+  if (!pool.empty()) {
+    e = pool.back();
+    pool.pop_back();
+    return e;
+  }
+  cudaEventCreate(&e);
+  return e;
+}
+
+void Profiler::reset() {
+  for (auto& r : recs) {
+    pool.push_back(r.a);
+    pool.push_back(r.b);
+  }
+  recs.clear();
+}
+
 namespace {
 
 Status g_create_status;
@@ -118,6 +143,7 @@ struct igm_ctx {
   Status st;
   int64_t launches = 0;
   int conv_engine = 0;
+  Profiler prof;
 
   std::vector<ParamInfo> params;
   int64_t param_elems = 0;
@@ -178,6 +204,7 @@ struct igm_ctx {
     l.stream = (cudaStream_t)stream;
     l.st = &st;
     l.counter = &launches;
+    l.prof = &prof;
     return l;
   }
   float* Pp(int idx) const { return idx < 0 ? nullptr : P + params[idx].offset; }
@@ -454,6 +481,7 @@ struct Runner {
     a.N = C0 + C1; a.N0 = C0;
     a.KH = a.KW = l.K; a.stride = stride; a.pad = pad; a.dil = 1;
     a.transposed = l.convT ? 0 : 1;
+    a.kclass = K_CONV_DGRAD;
     a.w = l.w_bwd;
     a.bias = nullptr;
     a.out0 = d0; a.out1 = d1; a.add0 = add0; a.add1 = add1;
@@ -639,7 +667,7 @@ struct Runner {
       IGM_TRY(launch_colsum(lc, d_pred, M(H0, W0), cfg.channels, c.Gp(c.final_conv.pb)));
       ConvArgs a;
       a.in0 = d_pred; a.C0 = cfg.channels; a.B = B; a.IH = a.OH = H0; a.IW = a.OW = W0;
-      a.N = a.N0 = c.final_conv.Cin; a.transposed = 1;
+      a.N = a.N0 = c.final_conv.Cin; a.transposed = 1; a.kclass = K_CONV_DGRAD;
       a.w = c.final_wbwd; a.out0 = c.final_act.g;
       IGM_TRY(launch_conv(lc, a));
     }
@@ -786,6 +814,8 @@ void igm_unet_destroy(igm_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  c->prof.reset();
+  for (cudaEvent_t e : c->prof.pool) cudaEventDestroy(e);
   if (c->arena) cudaFree(c->arena);
   delete c;
 }
@@ -1060,6 +1090,39 @@ int64_t igm_debug_read_tap(igm_ctx* c, const char* name, float* dst, int64_t cap
   LaunchCtx lc = c->lc(stream);
   int r = launch_nhwc_to_nchw(lc, a.v, dst, B, a.H * a.W, a.C);
   return r == IGM_OK ? n : r;
+}
+
+int igm_profile_start(igm_ctx* c) {
+  if (!c) return IGM_ERR_INVALID;
+  IGM_CUDA(c->st, cudaSetDevice(c->device));
+  c->prof.reset();
+  c->prof.on = true;
+  return IGM_OK;
+}
+
+int igm_profile_stop(igm_ctx* c, igm_profile_entry* out, int cap) {
+  if (!c) return IGM_ERR_INVALID;
+  IGM_CUDA(c->st, cudaSetDevice(c->device));
+  c->prof.on = false;
+  IGM_CUDA(c->st, cudaDeviceSynchronize());
+  igm_profile_entry acc[K_NCLASS];
+  for (int k = 0; k < K_NCLASS; ++k) {
+    memset(&acc[k], 0, sizeof(acc[k]));
+    strncpy(acc[k].name, kclass_name(k), sizeof(acc[k].name) - 1);
+  }
+  for (auto& r : c->prof.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
+    acc[r.cls].launches += 1;
+    acc[r.cls].ms += ms;
+    acc[r.cls].flops += r.flops;
+    acc[r.cls].bytes += r.bytes;
+  }
+  c->prof.reset();
+  int n = 0;
+  for (int k = 0; k < K_NCLASS && n < cap; ++k)
+    if (out) out[n++] = acc[k];
+  return n;
 }
 
 int64_t igm_launch_count(const igm_ctx* c) { return c ? c->launches : IGM_ERR_INVALID; }

@@ -316,6 +316,20 @@ class Unet(nn.Module):
     def launch_count(self) -> int:
         return 0 if self._engine is None else int(self._engine.lib.igm_launch_count(self._engine.ctx))
 
+    def profile_start(self):
+        e = self._engine
+        e.check(e.lib.igm_profile_start(e.ctx))
+
+    def profile_stop(self):
+        """-> {class: dict(launches, ms, flops, bytes)} for the launches since profile_start()."""
+        e = self._engine
+        buf = (_lib.ProfileEntry * 16)()
+        n = e.lib.igm_profile_stop(e.ctx, buf, 16)
+        if n < 0:
+            e.check(n)
+        return {buf[i].name.decode(): dict(launches=buf[i].launches, ms=buf[i].ms, flops=buf[i].flops,
+                                           bytes=buf[i].bytes) for i in range(n)}
+
     def read_tap(self, name: str) -> torch.Tensor:
         """Named intermediate of the last forward as NCHW (tests / profiling)."""
         e = self._engine

@@ -141,6 +141,19 @@ int igm_adam_step(igm_ctx* ctx, float* params, const float* grads, float* exp_av
  * Returns the element count, or a negative error.  dst may be NULL to query. */
 int64_t igm_debug_read_tap(igm_ctx* ctx, const char* name, float* dst_nchw, int64_t cap,
                            void* stream);
+/* CUDA-event profiler (bench.py's roofline pass): between start and stop every launch of
+ * this context is bracketed by an event pair; stop synchronises the device and returns,
+ * per kernel class, the launch count, summed device time and the ALGORITHMIC flops /
+ * bytes of those launches.  Adds per-launch overhead: never enabled in a timed region. */
+typedef struct igm_profile_entry {
+  char name[32];
+  int64_t launches;
+  double ms;
+  double flops;
+  double bytes;
+} igm_profile_entry;
+int igm_profile_start(igm_ctx* ctx);
+int igm_profile_stop(igm_ctx* ctx, igm_profile_entry* out, int cap);
 /* Number of kernels the library launched on behalf of this context so far. */
 int64_t igm_launch_count(const igm_ctx* ctx);
 /* Which conv engine is active: 0 = SIMT fp32 implicit GEMM, 1 = tcgen05 bf16x3. */
