@@ -20,6 +20,7 @@ struct Status {
 };
 
 void set_error(Status& st, int code, const char* file, int line, const char* what);
+Status& global_status();   // errors raised without a context (igm_unet_create, igm_debug_*)
 
 #define IGM_CUDA(st, expr)                                                      \
   do {                                                                          \

@@ -1,0 +1,489 @@
+// tcgen05 convolution engine for sm_100a: TMA-fed, TMEM-accumulated implicit GEMM.
+//
+// Serves the stride-1 3x3 and 1x1 convolutions of the U-Net and their data gradients
+// (reference src/models/ddpm.py:116, :134, :151-152 and autograd), i.e. >90 % of the FLOPs.
+//
+// Precision: plain bf16 operands miss the 1e-3 parity bound, so every
+// operand is carried as a bf16 hi + lo pair and the product is formed as
+//     hi*hi + hi*lo + lo*hi            (fp32 accumulate in TMEM)
+// which is fp32-accurate to ~2^-17 relative at 1/3 of the bf16 tensor rate.
+//
+// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+//   warp 0      TMA producer: per (tap, 64-channel chunk) loads the A_hi / A_lo activation tiles
+//               with a 4-D tensor map (C, W, H, B) whose out-of-bounds zero fill implements the
+//               conv padding, and the B_hi / B_lo weight tiles with a 2-D map; 128B swizzle.
+//   warp 1      MMA issuer: 12 x tcgen05.mma (M=128, N=BN, K=16) per chunk into a TMEM accumulator;
+//               tcgen05.commit releases the smem stage / publishes the accumulator.
+//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns), + bias, + optional addend, fp32 NHWC
+//               stores; double-buffered accumulators let it overlap the next tile's MMAs.
+#include "conv_tc.cuh"
+
+#include <cudaTypedefs.h>
+
+namespace igm {
+namespace {
+
+constexpr int BM = 128;       // output pixels per tile (TMEM lanes)
+constexpr int KC = 64;        // channels per K chunk: 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_TILE_BYTES = BM * KC * 2;   // 16 KiB
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte-swizzled operand tile: rows of 64 bf16 (128 B), 8-row groups 1024 B apart.
+//   bits [0,14)  start address >> 4      bits [16,30) leading byte offset >> 4 (1: unused for swizzled K-major)
+//   bits [32,46) stride byte offset >> 4 (1024 B)      bits [46,48) version = 1 (sm_100)
+//   bits [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct TcArgs {
+  int B, H, W, K, N, N0;
+  int KH, KW, pad;
+  int BH, BW, BB;
+  int tiles_m, tiles_n, tiles_per_img;
+  int stage_tx_bytes;   // bytes one pipeline stage receives: 2 x (box rows x 128 B) + 2 x weight tile
+  const float* bias;
+  float* out0; float* out1;
+  const float* add0; const float* add1;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_TILE_BYTES = BN * KC * 2;
+  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  static constexpr int STAGES = (BN == 128) ? 3 : 4;
+  static constexpr int TMEM_COLS = 2 * BN;   // two accumulator stages (power of two >= 32)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant__ CUtensorMap ta_lo,
+               const __grid_constant__ CUtensorMap tb_hi, const __grid_constant__ CUtensorMap tb_lo, const TcArgs p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;                       // [STAGES]  TMA -> MMA
+  uint64_t* empty = bars + C::STAGES;          // [STAGES]  MMA -> TMA
+  uint64_t* acc_full = bars + 2 * C::STAGES;   // [2]       MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;          // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);   // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int kchunks = p.K / KC;
+  const int iters = p.KH * p.KW * kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&ta_hi); prefetch_tmap(&ta_lo); prefetch_tmap(&tb_hi); prefetch_tmap(&tb_lo);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+        int b0, y0;
+        if (p.BB > 1) { b0 = tm * p.BB; y0 = 0; }
+        else { b0 = tm / p.tiles_per_img; y0 = (tm - b0 * p.tiles_per_img) * p.BH; }
+        for (int tap = 0; tap < p.KH * p.KW; ++tap) {
+          const int ky = tap / p.KW, kx = tap - ky * p.KW;
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* st = smem + stage * C::STAGE_BYTES;
+            mbar_expect_tx(&full[stage], (uint32_t)p.stage_tx_bytes);
+            tma_load_4d(st, &ta_hi, &full[stage], kc * KC, kx - p.pad, y0 + ky - p.pad, b0);
+            tma_load_4d(st + A_TILE_BYTES, &ta_lo, &full[stage], kc * KC, kx - p.pad, y0 + ky - p.pad, b0);
+            tma_load_2d(st + 2 * A_TILE_BYTES, &tb_hi, &full[stage], tap * p.K + kc * KC, tn * BN);
+            tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &tb_lo, &full[stage], tap * p.K + kc * KC, tn * BN);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major A/B,
+      // N>>3 at bits 17-22, M>>4 at bits 24-28
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        uint32_t accum = 0;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t a_hi = sa, a_lo = sa + A_TILE_BYTES;
+          const uint32_t b_hi = sa + 2 * A_TILE_BYTES, b_lo = b_hi + C::B_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < KC / UMMA_K; ++k) {
+            const uint32_t koff = k * UMMA_K * 2;   // bytes inside the 128-byte swizzle row
+            const uint64_t dah = make_sw128_desc(a_hi + koff), dal = make_sw128_desc(a_lo + koff);
+            const uint64_t dbh = make_sw128_desc(b_hi + koff), dbl = make_sw128_desc(b_lo + koff);
+            umma_bf16(d_tmem, dal, dbh, idesc, accum);   // small terms first
+            umma_bf16(d_tmem, dah, dbl, idesc, 1u);
+            umma_bf16(d_tmem, dah, dbh, idesc, 1u);
+            accum = 1u;
+          }
+          umma_commit(&empty[stage]);   // frees this smem stage when the MMAs above retire
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[as]);     // accumulator complete
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ---- epilogue warps 2..5: TMEM lane quarter = warp % 4 ----
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int N1 = p.N - p.N0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+      int b0, y0;
+      if (p.BB > 1) { b0 = tm * p.BB; y0 = 0; }
+      else { b0 = tm / p.tiles_per_img; y0 = (tm - b0 * p.tiles_per_img) * p.BH; }
+      // row -> (bb, by, bx) in TMA box order
+      const int bx = row % p.BW;
+      const int r2 = row / p.BW;
+      const int by = r2 % p.BH;
+      const int bb = r2 / p.BH;
+      const int oy = y0 + by, b = b0 + bb;
+      const bool valid = (bb < p.BB) && (oy < p.H) && (b < p.B);
+      const int64_t opix = ((int64_t)b * p.H + oy) * p.W + bx;
+
+      mbar_wait(&acc_full[as], aphase);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld_32x32(t_base + (uint32_t)c0, v);
+        const int n = tn * BN + c0;
+        if (valid && n < p.N) {
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+              v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+            }
+          }
+          float* o;
+          const float* ad;
+          if (n < p.N0) { o = p.out0 + opix * p.N0 + n; ad = p.add0 ? p.add0 + opix * p.N0 + n : nullptr; }
+          else { o = p.out1 + opix * N1 + (n - p.N0); ad = p.add1 ? p.add1 + opix * N1 + (n - p.N0) : nullptr; }
+          if (ad) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 av = __ldg(reinterpret_cast<const float4*>(ad + j));
+              v[j] += av.x; v[j + 1] += av.y; v[j + 2] += av.z; v[j + 3] += av.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------
+__global__ void split_bf16_kernel(const float* __restrict__ src, int64_t M, int C, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, int cdst, int coff) {
+  const int c4n = C >> 2;
+  const int64_t total = M * c4n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / c4n;
+    const int c = (int)(i - m * c4n) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + m * C + c));
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = __float2bfloat16_rn(x[j]);
+      l[j] = __float2bfloat16_rn(x[j] - __bfloat162float(h[j]));
+    }
+    const int64_t o = m * cdst + coff + c;
+    *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(l);
+  }
+}
+
+__global__ void pack_weight_tc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
+                                      __nv_bfloat16* __restrict__ lo, int taps, int K, int N, int64_t sk, int64_t sn,
+                                      int flip) {
+  const int64_t total = (int64_t)N * taps * K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const int64_t r = i / K;
+    const int tap = (int)(r % taps);
+    const int n = (int)(r / taps);
+    const int ts = flip ? (taps - 1 - tap) : tap;
+    const float x = src[k * sk + n * sn + ts];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+}  // namespace
+
+bool tc_eligible(int K, int N, int H, int W, int KH) {
+  if (K < KC || K % KC != 0) return false;
+  if (N < 64 || N % 64 != 0) return false;
+  if (W > BM || W < 1 || H < 1) return false;
+  if (KH != 1 && KH != 3) return false;
+  // the 128-row box must tile the image: rows of W pixels, whole images when they are small
+  if (H * W <= BM) return (BM / (H * W)) >= 1;
+  return (BM / W) >= 1;
+}
+
+int tc_plan(Status& st, TcConv& t, int K, int N, int H, int W, int Bmax, int KH, int pad, __nv_bfloat16* a_hi,
+            __nv_bfloat16* a_lo, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo) {
+  t.valid = false;
+  if (!tc_eligible(K, N, H, W, KH)) IGM_FAIL(st, IGM_ERR_INVALID, "shape not eligible for the tcgen05 engine");
+  auto enc = get_encode_fn();
+  if (!enc) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  t.K = K; t.N = N; t.KH = t.KW = KH; t.pad = pad; t.H = H; t.W = W; t.Bmax = Bmax;
+  t.w_hi = w_hi; t.w_lo = w_lo;
+  t.BW = W;
+  if (H * W <= BM) { t.BH = H; t.BB = BM / (H * W); }
+  else { t.BH = BM / W; t.BB = 1; }
+  if (t.BB > Bmax) t.BB = Bmax;
+  t.BN = (N % 128 == 0) ? 128 : 64;
+  // activations: dims innermost-first (C, W, H, B)
+  for (int which = 0; which < 2; ++which) {
+    cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Bmax};
+    cuuint64_t strides[3] = {(cuuint64_t)K * 2, (cuuint64_t)W * K * 2, (cuuint64_t)H * W * K * 2};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)t.BW, (cuuint32_t)t.BH, (cuuint32_t)t.BB};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(which ? &t.a_lo : &t.a_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, which ? (void*)a_lo : (void*)a_hi,
+                     dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled (activations) failed");
+  }
+  // weights: [N rows][taps*K cols], K-major
+  for (int which = 0; which < 2; ++which) {
+    cuuint64_t dims[2] = {(cuuint64_t)KH * KH * K, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)KH * KH * K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)t.BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(which ? &t.b_lo : &t.b_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, which ? (void*)w_lo : (void*)w_hi,
+                     dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled (weights) failed");
+  }
+  t.valid = true;
+  return IGM_OK;
+}
+
+template <int BN>
+static int launch_tc_impl(const LaunchCtx& lc, const TcConv& t, const TcArgs& a, int num_tiles) {
+  using C = Cfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(e));
+    attr_done = true;
+  }
+  int grid = num_tiles < 148 ? num_tiles : 148;
+  conv_tc_kernel<BN><<<grid, 192, C::SMEM_BYTES, lc.stream>>>(t.a_hi, t.a_lo, t.b_hi, t.b_lo, a);
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r) {
+  if (!t.valid) IGM_FAIL(*lc.st, IGM_ERR_STATE, "tcgen05 conv plan not initialised");
+  if (r.B < 1 || r.B > t.Bmax) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "conv_tc: bad batch");
+  if (r.N0 <= 0 || r.N0 > t.N || r.N0 % 32 != 0 || (r.N0 < t.N && !r.out1))
+    IGM_FAIL(*lc.st, IGM_ERR_INVALID, "conv_tc: bad output split");
+  TcArgs a;
+  a.B = r.B; a.H = t.H; a.W = t.W; a.K = t.K; a.N = t.N; a.N0 = r.N0;
+  a.KH = t.KH; a.KW = t.KW; a.pad = t.pad;
+  a.BH = t.BH; a.BW = t.BW; a.BB = t.BB;
+  a.tiles_per_img = (t.BB > 1) ? 1 : cdiv(t.H, t.BH);
+  a.tiles_m = (t.BB > 1) ? cdiv(r.B, t.BB) : r.B * a.tiles_per_img;
+  a.tiles_n = t.N / t.BN;
+  a.stage_tx_bytes = 2 * (t.BB * t.BH * t.BW * KC * 2) + 2 * (t.BN * KC * 2);
+  a.bias = r.bias; a.out0 = r.out0; a.out1 = r.out1; a.add0 = r.add0; a.add1 = r.add1;
+  const double flops = 2.0 * r.B * t.H * t.W * (double)t.N * t.K * t.KH * t.KW;
+  const double bytes = 4.0 * ((double)r.B * t.H * t.W * (t.K + t.N * (r.add0 ? 2 : 1)) + (double)t.KH * t.KW * t.K * t.N);
+  ProfScope ps_(lc, r.kclass, flops, bytes);
+  const int num_tiles = a.tiles_m * a.tiles_n;
+  if (t.BN == 128) return launch_tc_impl<128>(lc, t, a, num_tiles);
+  return launch_tc_impl<64>(lc, t, a, num_tiles);
+}
+
+int launch_split_bf16(const LaunchCtx& lc, const float* src, int64_t M, int C, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                      int cdst, int coff) {
+  if (C % 4 != 0 || coff % 4 != 0 || cdst % 4 != 0) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "split: channels must be multiples of 4");
+  const int64_t total = M * (C / 4);
+  int blocks = (int)cdiv64(total, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  ProfScope ps_(lc, K_ELEM, 2.0 * M * C, 8.0 * M * C);
+  split_bf16_kernel<<<blocks, 256, 0, lc.stream>>>(src, M, C, hi, lo, cdst, coff);
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+int launch_pack_weight_tc(const LaunchCtx& lc, const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, int taps, int K,
+                          int N, int64_t sk, int64_t sn, int flip) {
+  const int64_t total = (int64_t)N * taps * K;
+  int blocks = (int)cdiv64(total, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ProfScope ps_(lc, K_PACK, 0.0, 8.0 * total);
+  pack_weight_tc_kernel<<<blocks, 256, 0, lc.stream>>>(src, hi, lo, taps, K, N, sk, sn, flip);
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+}  // namespace igm

@@ -1,0 +1,48 @@
+// tcgen05 (5th-gen tensor core) convolution engine: declarations shared with unet.cu.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace igm {
+
+// One stride-1 convolution (or its data gradient) lowered to an implicit GEMM
+//   D[m, n] = sum_{tap, k} A[pix(m) + tap, k] * Wt[n, tap*K + k]
+// with every operand split into bf16 hi + lo parts ("bf16x3": hi*hi + hi*lo + lo*hi,
+// fp32 accumulation in TMEM) so the result is fp32-accurate to ~2^-17 relative.
+struct TcConv {
+  bool valid = false;
+  alignas(64) CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  __nv_bfloat16* w_hi = nullptr;   // [N][taps*K]
+  __nv_bfloat16* w_lo = nullptr;
+  int K = 0, N = 0, KH = 1, KW = 1, pad = 0;
+  int H = 0, W = 0, Bmax = 0;
+  int BH = 0, BW = 0, BB = 0, BN = 0;   // M-tile = BB images x BH rows x BW cols (<= 128 pixels)
+};
+
+// Can this (stride-1, non-dilated) conv run on the tensor-core engine?
+bool tc_eligible(int K, int N, int H, int W, int KH);
+
+// Fills `t` (tile shape + the four TMA descriptors).  a_hi/a_lo: bf16 [Bmax, H, W, K] scratch.
+int tc_plan(Status& st, TcConv& t, int K, int N, int H, int W, int Bmax, int KH, int pad,
+            __nv_bfloat16* a_hi, __nv_bfloat16* a_lo, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo);
+
+struct TcRun {
+  int B = 0;
+  const float* bias = nullptr;
+  float* out0 = nullptr; float* out1 = nullptr; int N0 = 0;
+  const float* add0 = nullptr; const float* add1 = nullptr;
+  int kclass = K_CONV_FPROP;
+};
+int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r);
+
+// fp32 [M, C] -> bf16 hi / lo written at channel offset `coff` of rows with `cdst` channels
+int launch_split_bf16(const LaunchCtx& lc, const float* src, int64_t M, int C, __nv_bfloat16* hi,
+                      __nv_bfloat16* lo, int cdst, int coff);
+
+// Wt[n][tap*K + k] (hi, lo) = src[k*sk + n*sn + (flip ? taps-1-tap : tap)]
+int launch_pack_weight_tc(const LaunchCtx& lc, const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, int taps,
+                          int K, int N, int64_t sk, int64_t sn, int flip);
+
+}  // namespace igm

@@ -7,12 +7,14 @@
 // can be captured into a CUDA graph (igm_ddpm_sample_loop does).
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
 #include <memory>
 
 #include "common.cuh"
+#include "conv_tc.cuh"
 
 namespace igm {
 
@@ -48,9 +50,12 @@ void Profiler::reset() {
   recs.clear();
 }
 
-namespace {
+Status& global_status() {
+  static Status s;
+  return s;
+}
 
-Status g_create_status;
+namespace {
 
 struct ParamInfo {
   std::string name;
@@ -73,6 +78,11 @@ struct ConvL {
   bool convT = false;
   float* w_fwd = nullptr;   // [K*K][Cin][Cout]
   float* w_bwd = nullptr;   // [K*K][Cout][Cin]
+  // tcgen05 engine (stride-1 Conv2d only): bf16 hi/lo weights [N][taps*K] and TMA plans
+  int H = 0, W = 0;         // spatial size the layer runs at (0: not a stride-1 conv)
+  bool tc_f_ok = false, tc_b_ok = false;
+  __nv_bfloat16 *wf_hi = nullptr, *wf_lo = nullptr, *wb_hi = nullptr, *wb_lo = nullptr;
+  TcConv tc_f, tc_b;
 };
 
 struct BlockL {
@@ -173,6 +183,8 @@ struct igm_ctx {
   float* gn_part = nullptr;
   float *ws_group = nullptr, *ws_chan = nullptr, *ws_ln = nullptr;
   float *scrA = nullptr, *scrB = nullptr, *scrC = nullptr;
+  __nv_bfloat16 *split_hi = nullptr, *split_lo = nullptr;   // bf16x2 staging of a conv's input (tcgen05 engine)
+  bool tc_available = false;
   float* pred = nullptr;        // [B,C,H,W] network output (NCHW)
   float* noise_copy = nullptr;  // NCHW
   float* d_pred = nullptr;      // NHWC [M, C]
@@ -240,7 +252,7 @@ struct PlanBuilder {
   Arena ar;
   bool training;
   int B;
-  int64_t maxMC = 0, maxM = 0, maxGnWs = 0;
+  int64_t maxMC = 0, maxM = 0, maxGnWs = 0, maxSplit = 0;
 
   PlanBuilder(igm_ctx& ctx, float* base) : c(ctx), pb{ctx.params} {
     ar.base = base;
@@ -262,20 +274,38 @@ struct PlanBuilder {
     c.taps[n] = a;
   }
 
-  ConvL conv(const std::string& name, int Cin, int Cout, int K, bool bias, bool convT = false) {
+  // H, W > 0 marks a stride-1 Conv2d running at that resolution (candidate for the tcgen05 engine)
+  ConvL conv(const std::string& name, int Cin, int Cout, int K, bool bias, bool convT = false, int H = 0, int W = 0,
+             bool need_dgrad = true) {
     ConvL l;
     l.Cin = Cin; l.Cout = Cout; l.K = K; l.convT = convT;
     if (convT) l.pw = pb.add(name + ".weight", {Cin, Cout, K, K});
     else l.pw = pb.add(name + ".weight", {Cout, Cin, K, K});
     if (bias) l.pb = pb.add(name + ".bias", {Cout});
-    l.w_fwd = ar.alloc((int64_t)K * K * Cin * Cout);
-    if (training) l.w_bwd = ar.alloc((int64_t)K * K * Cin * Cout);
+    const int64_t nw = (int64_t)K * K * Cin * Cout;
+    l.w_fwd = ar.alloc(nw);
+    if (training) l.w_bwd = ar.alloc(nw);
+    l.H = H; l.W = W;
+    if (H > 0 && !convT) {
+      l.tc_f_ok = tc_eligible(Cin, Cout, H, W, K);
+      l.tc_b_ok = training && need_dgrad && tc_eligible(Cout, Cin, H, W, K);
+      if (l.tc_f_ok) {
+        l.wf_hi = reinterpret_cast<__nv_bfloat16*>(ar.alloc((nw + 1) / 2));
+        l.wf_lo = reinterpret_cast<__nv_bfloat16*>(ar.alloc((nw + 1) / 2));
+        maxSplit = std::max(maxSplit, M(H, W) * Cin);
+      }
+      if (l.tc_b_ok) {
+        l.wb_hi = reinterpret_cast<__nv_bfloat16*>(ar.alloc((nw + 1) / 2));
+        l.wb_lo = reinterpret_cast<__nv_bfloat16*>(ar.alloc((nw + 1) / 2));
+        maxSplit = std::max(maxSplit, M(H, W) * Cout);
+      }
+    }
     return l;
   }
 
   BlockL block(const std::string& name, int Cin, int Cout, int H, int W) {
     BlockL b;
-    b.conv = conv(name + ".block.0", Cin, Cout, 3, true);
+    b.conv = conv(name + ".block.0", Cin, Cout, 3, true, false, H, W);
     b.gn_w = pb.add(name + ".block.1.weight", {Cout});
     b.gn_b = pb.add(name + ".block.1.bias", {Cout});
     b.raw = ar.alloc(M(H, W) * Cout);
@@ -305,7 +335,7 @@ struct PlanBuilder {
     r.b2 = block(name + ".block2", Cout, Cout, H, W);
     r.has_res = Cin != Cout;
     if (r.has_res) {
-      r.res = conv(name + ".res_conv", Cin, Cout, 1, true);
+      r.res = conv(name + ".res_conv", Cin, Cout, 1, true, false, H, W);
       r.r = ar.alloc(M(H, W) * Cout);
     }
     r.h1 = act(Cout, H, W, true);
@@ -319,8 +349,8 @@ struct PlanBuilder {
     AttnL a;
     a.name = name; a.C = C; a.H = H; a.W = W;
     const int hd = kHeads * kDimHead;
-    a.qkv = conv(name + ".fn.fn.to_qkv", C, 3 * hd, 1, false);
-    a.outc = conv(name + ".fn.fn.to_out", hd, C, 1, true);
+    a.qkv = conv(name + ".fn.fn.to_qkv", C, 3 * hd, 1, false, false, H, W);
+    a.outc = conv(name + ".fn.fn.to_out", hd, C, 1, true, false, H, W);
     a.ln_g = pb.add(name + ".fn.norm.g", {1, C, 1, 1});
     a.ln_b = pb.add(name + ".fn.norm.b", {1, C, 1, 1});
     a.ln = ar.alloc(M(H, W) * C);
@@ -445,6 +475,10 @@ struct PlanBuilder {
       c.noise_copy = ar.alloc((int64_t)B * cfg.channels * HW0);
       c.d_pred = ar.alloc((int64_t)B * cfg.channels * HW0);
     }
+    if (maxSplit > 0) {
+      c.split_hi = reinterpret_cast<__nv_bfloat16*>(ar.alloc((maxSplit + 1) / 2));
+      c.split_lo = reinterpret_cast<__nv_bfloat16*>(ar.alloc((maxSplit + 1) / 2));
+    }
   }
 };
 
@@ -459,8 +493,18 @@ struct Runner {
   int64_t M(int H, int W) const { return (int64_t)B * H * W; }
 
   // forward of a Conv2d (stride s, pad p) or ConvTranspose2d layer
+  bool use_tc(const TcConv& t) const { return c.conv_engine == 1 && t.valid; }
+
   int conv_fwd(const ConvL& l, const float* in0, int C0, const float* in1, int C1, int IH, int IW, int OH,
                int OW, int stride, int pad, float* out, const float* add) {
+    if (stride == 1 && use_tc(l.tc_f)) {
+      const int Ct = C0 + C1;
+      IGM_TRY(launch_split_bf16(lc, in0, M(IH, IW), C0, c.split_hi, c.split_lo, Ct, 0));
+      if (in1 && C1 > 0) IGM_TRY(launch_split_bf16(lc, in1, M(IH, IW), C1, c.split_hi, c.split_lo, Ct, C0));
+      TcRun r;
+      r.B = B; r.bias = c.Pp(l.pb); r.out0 = out; r.N0 = l.Cout; r.add0 = add; r.kclass = K_CONV_FPROP;
+      return launch_conv_tc(lc, l.tc_f, r);
+    }
     ConvArgs a;
     a.in0 = in0; a.in1 = in1; a.C0 = C0; a.C1 = C1;
     a.B = B; a.IH = IH; a.IW = IW; a.OH = OH; a.OW = OW;
@@ -475,6 +519,13 @@ struct Runner {
   // data gradient: d_out [B,OH,OW,Cout] -> d_in split (d0: C0 channels, d1: C1 channels)
   int conv_dgrad(const ConvL& l, const float* d_out, int OH, int OW, int IH, int IW, int stride, int pad,
                  float* d0, int C0, float* d1, int C1, const float* add0, const float* add1) {
+    if (stride == 1 && use_tc(l.tc_b) && C0 % 32 == 0) {
+      IGM_TRY(launch_split_bf16(lc, d_out, M(OH, OW), l.Cout, c.split_hi, c.split_lo, l.Cout, 0));
+      TcRun r;
+      r.B = B; r.bias = nullptr; r.out0 = d0; r.out1 = d1; r.N0 = C0; r.add0 = add0; r.add1 = add1;
+      r.kclass = K_CONV_DGRAD;
+      return launch_conv_tc(lc, l.tc_b, r);
+    }
     ConvArgs a;
     a.in0 = d_out; a.C0 = l.Cout; a.C1 = 0;
     a.B = B; a.IH = OH; a.IW = OW; a.OH = IH; a.OW = IW;
@@ -731,6 +782,52 @@ struct Runner {
 }  // namespace
 }  // namespace igm
 
+template <class F>
+static int for_each_conv(igm_ctx* c, F f) {
+  auto rn = [&](ResnetL& r) -> int {
+    IGM_TRY(f(r.b1.conv));
+    IGM_TRY(f(r.b2.conv));
+    if (r.has_res) IGM_TRY(f(r.res));
+    return IGM_OK;
+  };
+  auto at = [&](AttnL& a) -> int {
+    IGM_TRY(f(a.qkv));
+    IGM_TRY(f(a.outc));
+    return IGM_OK;
+  };
+  auto stg = [&](Stage& s) -> int {
+    IGM_TRY(rn(s.r1));
+    IGM_TRY(rn(s.r2));
+    IGM_TRY(at(s.attn));
+    if (s.rs.present) IGM_TRY(f(s.rs.conv));
+    return IGM_OK;
+  };
+  for (auto& s : c->downs) IGM_TRY(stg(s));
+  for (auto& s : c->ups) IGM_TRY(stg(s));
+  IGM_TRY(rn(c->mid1));
+  IGM_TRY(at(c->mid_attn));
+  IGM_TRY(rn(c->mid2));
+  IGM_TRY(f(c->final_block.conv));
+  return IGM_OK;
+}
+
+// TMA descriptors of the tcgen05 engine for every eligible stride-1 conv (needs a live driver)
+static int plan_tc(igm_ctx* c) {
+  int n_valid = 0;
+  int rc = for_each_conv(c, [&](ConvL& l) -> int {
+    if (l.tc_f_ok)
+      IGM_TRY(tc_plan(c->st, l.tc_f, l.Cin, l.Cout, l.H, l.W, c->cfg.max_batch, l.K, (l.K - 1) / 2, c->split_hi,
+                      c->split_lo, l.wf_hi, l.wf_lo));
+    if (l.tc_b_ok)
+      IGM_TRY(tc_plan(c->st, l.tc_b, l.Cout, l.Cin, l.H, l.W, c->cfg.max_batch, l.K, (l.K - 1) / 2, c->split_hi,
+                      c->split_lo, l.wb_hi, l.wb_lo));
+    n_valid += (l.tc_f.valid ? 1 : 0) + (l.tc_b.valid ? 1 : 0);
+    return IGM_OK;
+  });
+  c->tc_available = (rc == IGM_OK) && n_valid > 0;
+  return rc;
+}
+
 // ---------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------
@@ -739,7 +836,7 @@ extern "C" {
 int igm_version(void) { return 100; }
 
 const char* igm_last_error(const igm_ctx* ctx) {
-  const Status& st = ctx ? ctx->st : g_create_status;
+  const Status& st = ctx ? ctx->st : global_status();
   return st.msg.c_str();
 }
 
@@ -759,7 +856,7 @@ static int build_plan(igm_ctx* c, float* base, int64_t* floats_out) {
 }
 
 int igm_unet_create(igm_ctx** out, const igm_unet_cfg* cfg, int device) {
-  Status& st = g_create_status;
+  Status& st = global_status();
   st = Status();
   if (!out || !cfg) IGM_FAIL(st, IGM_ERR_INVALID, "null argument");
   if (cfg->dim <= 0 || cfg->dim % 32 != 0 || 256 % cfg->dim != 0)
@@ -806,6 +903,17 @@ int igm_unet_create(igm_ctx** out, const igm_unet_cfg* cfg, int device) {
   }
   int64_t floats2 = 0;
   build_plan(c, c->arena, &floats2);
+  // tensor-core engine: on by default when the shapes allow it (IGM_CONV_ENGINE=0 forces the SIMT engine)
+  const char* eng = getenv("IGM_CONV_ENGINE");
+  if (!(eng && eng[0] == '0')) {
+    if (plan_tc(c) != IGM_OK) {
+      st = c->st;
+      cudaFree(c->arena);
+      delete c;
+      return st.code;
+    }
+    c->conv_engine = c->tc_available ? 1 : 0;
+  }
   *out = c;
   return IGM_OK;
 }
@@ -865,6 +973,11 @@ static int pack_conv(igm_ctx* c, const LaunchCtx& lc, const ConvL& l) {
   if (!l.convT) {
     IGM_TRY(launch_pack_weight(lc, w, l.w_fwd, KK, l.Cin, l.Cout, KK, (int64_t)l.Cin * KK));
     if (l.w_bwd) IGM_TRY(launch_pack_weight(lc, w, l.w_bwd, KK, l.Cout, l.Cin, (int64_t)l.Cin * KK, KK));
+    // tcgen05 engine: Wt[n][tap*K + k] as bf16 hi/lo; the data gradient uses flipped taps
+    if (l.tc_f.valid)
+      IGM_TRY(launch_pack_weight_tc(lc, w, l.wf_hi, l.wf_lo, KK, l.Cin, l.Cout, KK, (int64_t)l.Cin * KK, 0));
+    if (l.tc_b.valid)
+      IGM_TRY(launch_pack_weight_tc(lc, w, l.wb_hi, l.wb_lo, KK, l.Cout, l.Cin, (int64_t)l.Cin * KK, KK, 1));
   } else {
     IGM_TRY(launch_pack_weight(lc, w, l.w_fwd, KK, l.Cin, l.Cout, (int64_t)l.Cout * KK, KK));
     if (l.w_bwd) IGM_TRY(launch_pack_weight(lc, w, l.w_bwd, KK, l.Cout, l.Cin, KK, (int64_t)l.Cout * KK));
@@ -877,30 +990,7 @@ int igm_unet_pack_weights(igm_ctx* c, void* stream) {
   if (!c->P) IGM_FAIL(c->st, IGM_ERR_STATE, "bind parameters first");
   IGM_CUDA(c->st, cudaSetDevice(c->device));
   LaunchCtx lc = c->lc(stream);
-  auto pack_resnet = [&](const ResnetL& r) -> int {
-    IGM_TRY(pack_conv(c, lc, r.b1.conv));
-    IGM_TRY(pack_conv(c, lc, r.b2.conv));
-    if (r.has_res) IGM_TRY(pack_conv(c, lc, r.res));
-    return IGM_OK;
-  };
-  auto pack_attn = [&](const AttnL& a) -> int {
-    IGM_TRY(pack_conv(c, lc, a.qkv));
-    IGM_TRY(pack_conv(c, lc, a.outc));
-    return IGM_OK;
-  };
-  auto pack_stage = [&](const Stage& s) -> int {
-    IGM_TRY(pack_resnet(s.r1));
-    IGM_TRY(pack_resnet(s.r2));
-    IGM_TRY(pack_attn(s.attn));
-    if (s.rs.present) IGM_TRY(pack_conv(c, lc, s.rs.conv));
-    return IGM_OK;
-  };
-  for (auto& s : c->downs) IGM_TRY(pack_stage(s));
-  for (auto& s : c->ups) IGM_TRY(pack_stage(s));
-  IGM_TRY(pack_resnet(c->mid1));
-  IGM_TRY(pack_attn(c->mid_attn));
-  IGM_TRY(pack_resnet(c->mid2));
-  IGM_TRY(pack_conv(c, lc, c->final_block.conv));
+  IGM_TRY(for_each_conv(c, [&](ConvL& l) -> int { return pack_conv(c, lc, l); }));
   if (c->final_wbwd) {
     // dgrad of the final 1x1: [1][k = c][n = K] = W[c][K]: identical memory order to W itself
     IGM_TRY(launch_pack_weight(lc, c->Pp(c->final_conv.pw), c->final_wbwd, 1, c->cfg.channels, c->final_conv.Cin,
@@ -1129,7 +1219,13 @@ int64_t igm_launch_count(const igm_ctx* c) { return c ? c->launches : IGM_ERR_IN
 
 int igm_set_conv_engine(igm_ctx* c, int engine) {
   if (!c) return IGM_ERR_INVALID;
-  if (engine != 0) IGM_FAIL(c->st, IGM_ERR_INVALID, "only the SIMT engine (0) is built in this version");
+  if (engine != 0 && engine != 1) IGM_FAIL(c->st, IGM_ERR_INVALID, "conv engine must be 0 (SIMT fp32) or 1 (tcgen05 bf16x3)");
+  if (engine == 1 && !c->tc_available) {
+    IGM_TRY(plan_tc(c));
+    if (!c->tc_available) IGM_FAIL(c->st, IGM_ERR_INVALID, "no layer of this network is eligible for the tcgen05 engine");
+    if (c->P) IGM_TRY(igm_unet_pack_weights(c, nullptr));
+  }
+  if (c->graph_exec && engine != c->conv_engine) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
   c->conv_engine = engine;
   return IGM_OK;
 }

@@ -156,7 +156,15 @@ int igm_profile_start(igm_ctx* ctx);
 int igm_profile_stop(igm_ctx* ctx, igm_profile_entry* out, int cap);
 /* Number of kernels the library launched on behalf of this context so far. */
 int64_t igm_launch_count(const igm_ctx* ctx);
-/* Which conv engine is active: 0 = SIMT fp32 implicit GEMM, 1 = tcgen05 bf16x3. */
+/* One stride-1 KxK (K = 1 or 3, pad (K-1)/2) convolution on NHWC fp32 tensors, for kernel-level
+ * parity tests: mode 0 = forward  x[B,H,W,Cin] -> out[B,H,W,Cout] (+bias, +add);
+ *               mode 1 = data gradient  x = d_out[B,H,W,Cout] -> out = d_in[B,H,W,Cin].
+ * w is the PyTorch OIHW weight.  engine as in igm_set_conv_engine.  Synchronous. */
+int igm_debug_conv(int engine, int mode, const float* x, const float* w_oihw, const float* bias,
+                   const float* add, float* out, int B, int H, int W, int Cin, int Cout, int K,
+                   void* stream);
+/* Which conv engine is active: 0 = SIMT fp32 implicit GEMM, 1 = tcgen05 bf16x3 (default when
+ * the layer shapes allow it; environment IGM_CONV_ENGINE=0 forces the SIMT engine). */
 int igm_set_conv_engine(igm_ctx* ctx, int engine);
 int igm_get_conv_engine(const igm_ctx* ctx);
 

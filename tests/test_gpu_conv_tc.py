@@ -1,0 +1,75 @@
+"""GPU: the tcgen05 (bf16x3) convolution kernel in isolation, through the C ABI's test entry
+igm_debug_conv, against torch's fp64 CPU convolution (the oracle for a single conv) and against
+the SIMT fp32 engine.  Tolerance 1e-4 relative: bf16x3 carries ~16 mantissa bits per operand."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from igm_b200 import _lib
+from tests._util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [
+    # B, H, W, Cin, Cout, K
+    (2, 32, 32, 64, 64, 3),
+    (2, 32, 32, 64, 128, 3),
+    (2, 32, 32, 128, 64, 3),
+    (2, 16, 16, 128, 128, 3),
+    (4, 8, 8, 256, 256, 3),
+    (3, 8, 8, 512, 128, 3),      # two images per tile, odd batch
+    (1, 8, 8, 256, 256, 3),      # batch smaller than the tile's image count
+    (2, 32, 32, 64, 384, 1),     # to_qkv
+    (2, 16, 16, 128, 64, 1),
+    (2, 28, 28, 128, 128, 3),    # ragged: 112-row tiles
+    (2, 14, 14, 256, 256, 3),    # ragged: 9-row tiles over 14 rows
+    (1, 64, 64, 64, 64, 3),      # CelebA resolution: 2-row tiles
+    (5, 4, 4, 64, 64, 3),        # 8 images per tile
+]
+
+
+def _run(engine, mode, x, w, bias, add, B, H, W, Cin, Cout, K):
+    lib = _lib.load()
+    N = Cout if mode == 0 else Cin
+    out = torch.empty(B, H, W, N, device="cuda", dtype=torch.float32)
+    p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    rc = lib.igm_debug_conv(engine, mode, p(x), p(w), p(bias), p(add), p(out), B, H, W, Cin, Cout, K, None)
+    assert rc == 0, lib.igm_last_error(None).decode()
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_conv_tc_forward(shape):
+    B, H, W, Cin, Cout, K = shape
+    g = torch.Generator().manual_seed(hash(shape) % 1000)
+    x = torch.randn(B, H, W, Cin, generator=g)
+    w = torch.randn(Cout, Cin, K, K, generator=g) / (Cin * K * K) ** 0.5
+    bias = torch.randn(Cout, generator=g)
+    add = torch.randn(B, H, W, Cout, generator=g)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), bias.double(), padding=(K - 1) // 2)
+    ref = ref.permute(0, 2, 3, 1) + add.double()
+    xs, ws, bs, ads = x.cuda(), w.cuda(), bias.cuda(), add.cuda()
+    tc = _run(1, 0, xs, ws, bs, ads, B, H, W, Cin, Cout, K).cpu()
+    simt = _run(0, 0, xs, ws, bs, ads, B, H, W, Cin, Cout, K).cpu()
+    l2, mx = rel_err(tc, ref)
+    l2s, mxs = rel_err(simt, ref)
+    assert l2s < 1e-5 and mxs < 1e-5, f"SIMT engine off: {l2s:.2e} {mxs:.2e}"
+    assert l2 < 1e-4 and mx < 1e-4, f"tcgen05 engine: rel-L2 {l2:.2e} max-rel {mx:.2e}"
+
+
+@pytest.mark.parametrize("shape", SHAPES[:8])
+def test_conv_tc_dgrad(shape):
+    B, H, W, Cin, Cout, K = shape
+    g = torch.Generator().manual_seed(1 + hash(shape) % 1000)
+    dy = torch.randn(B, H, W, Cout, generator=g)
+    w = torch.randn(Cout, Cin, K, K, generator=g) / (Cout * K * K) ** 0.5
+    ref = F.conv_transpose2d(dy.permute(0, 3, 1, 2).double(), w.double(), padding=(K - 1) // 2).permute(0, 2, 3, 1)
+    tc = _run(1, 1, dy.cuda(), w.cuda(), None, None, B, H, W, Cin, Cout, K).cpu()
+    simt = _run(0, 1, dy.cuda(), w.cuda(), None, None, B, H, W, Cin, Cout, K).cpu()
+    l2s, mxs = rel_err(simt, ref)
+    assert l2s < 1e-5 and mxs < 1e-5, f"SIMT engine off: {l2s:.2e} {mxs:.2e}"
+    l2, mx = rel_err(tc, ref)
+    assert l2 < 1e-4 and mx < 1e-4, f"tcgen05 engine: rel-L2 {l2:.2e} max-rel {mx:.2e}"

@@ -22,6 +22,13 @@ def _report(line):
             f.write(line + "\n")
 
 
+@pytest.fixture(autouse=True, params=[0, 1], ids=["simt", "tcgen05"])
+def conv_engine(request, monkeypatch):
+    """Every parity test runs on both conv engines (the env var is read at engine creation)."""
+    monkeypatch.setenv("IGM_CONV_ENGINE", str(request.param))
+    return request.param
+
+
 def _build(case, training=True):
     dim, ch, mults, H, W, B, T = CASES[case]
     spec = O.UnetSpec(dim, ch, mults)
