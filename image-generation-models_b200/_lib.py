@@ -53,6 +53,7 @@ SYMBOLS = {
     "igm_profile_start": (C.c_int, [_P]),
     "igm_profile_stop": (C.c_int, [_P, C.POINTER(ProfileEntry), C.c_int]),
     "igm_launch_count": (C.c_int64, [_P]),
+    "igm_debug_wgrad": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "igm_debug_conv": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, _P]),
     "igm_set_conv_engine": (C.c_int, [_P, C.c_int]),

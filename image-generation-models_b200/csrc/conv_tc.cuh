@@ -37,6 +37,21 @@ struct TcRun {
 };
 int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r);
 
+// Weight gradient of the same convolutions on the tensor cores (wgrad_tc.cu): pixels are the
+// reduction axis, fetched as 64-pixel TMA boxes of the bf16 hi/lo copies of dY and X.
+struct TcWgrad {
+  bool valid = false;
+  alignas(64) CUtensorMap dy_hi, dy_lo, x_hi, x_lo;
+  int Cin = 0, Cout = 0, KH = 1, KW = 1, pad = 0, H = 0, W = 0, Bmax = 0;
+  int BW = 0, BH = 0, BB = 0, rows = 0, BN = 0;
+};
+bool tcw_eligible(int Cin, int Cout, int H, int W, int KH);
+int tcw_plan(Status& st, TcWgrad& t, int Cin, int Cout, int H, int W, int Bmax, int KH, int pad,
+             __nv_bfloat16* dy_hi, __nv_bfloat16* dy_lo, __nv_bfloat16* x_hi, __nv_bfloat16* x_lo);
+bool tcw_batch_ok(const TcWgrad& t, int B);
+// grad (PyTorch OIHW fp32) += dW; dY / X must already be staged as bf16 hi/lo in the planned buffers
+int launch_wgrad_tc(const LaunchCtx& lc, const TcWgrad& t, int B, float* grad, int variant = 0);
+
 // fp32 [M, C] -> bf16 hi / lo written at channel offset `coff` of rows with `cdst` channels
 int launch_split_bf16(const LaunchCtx& lc, const float* src, int64_t M, int C, __nv_bfloat16* hi,
                       __nv_bfloat16* lo, int cdst, int coff);

@@ -1,0 +1,287 @@
+// tcgen05 weight-gradient engine for the stride-1 3x3 / 1x1 convolutions (sm_100a).
+//
+//   dW[co][ci][ky][kx] = sum_{b,iy,ix} dY[b, iy+pad-ky, ix+pad-kx, co] * X[b, iy, ix, ci]
+//
+// Lowered to GEMMs whose reduction dimension is the PIXEL axis: both operands are NHWC, so the
+// 64-channel runs are contiguous along M / N and pixels are the strided K axis -> "MN-major" UMMA
+// operands.  The very same TMA boxes as the forward engine are used (64 channels x 64 pixels, 128B
+// swizzle); the (ky,kx) shift is applied to the dY box coordinates and the TMA out-of-bounds zero
+// fill supplies the implicit zero padding.
+//
+// One CTA = one accumulator: M = 128 = two (tap, 64-channel co block) pairs, N = 64/128 input
+// channels, reduced over its split of the pixel tiles; bf16x3 (hi*hi + hi*lo + lo*hi) with fp32
+// accumulation in TMEM; the epilogue adds the partial result into PyTorch's OIHW gradient with
+// fp32 atomics (split-K across CTAs), which also gives torch's accumulate-into-.grad semantics.
+#include "conv_tc.cuh"
+#include "tc_ptx.cuh"
+
+#include <cudaTypedefs.h>
+
+namespace igm {
+namespace {
+
+using namespace tc;
+
+constexpr int PIX = 64;                 // pixels (K rows) per pipeline stage
+constexpr int BOX_BYTES = PIX * 128;    // one 64-channel x 64-pixel bf16 box
+constexpr int UMMA_K = 16;
+
+struct WArgs {
+  int B, H, W, Cin, Cout, KH, KW, pad;
+  int BW, BH, BB, rows;
+  int tiles_per_img, n_ptiles;
+  int n_pairs, n_ci_tiles, splits, tiles_per_split;
+  int cob;            // Cout / 64
+  int zero_smem;      // rows < 64: stale smem rows must read as zero (they are reduced over)
+  int variant;        // descriptor-convention switch for bring-up tests (0 = canonical)
+  float* grad;
+};
+
+template <int NB>   // NB = N / 64
+struct WCfg {
+  static constexpr int BN = NB * 64;
+  static constexpr int STAGE_BYTES = (4 + 2 * NB) * BOX_BYTES;
+  static constexpr int STAGES = (NB == 1) ? 4 : 3;
+  static constexpr int TMEM_COLS = BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int NB>
+__global__ void __launch_bounds__(192, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tdy_hi, const __grid_constant__ CUtensorMap tdy_lo,
+                const __grid_constant__ CUtensorMap tx_hi, const __grid_constant__ CUtensorMap tx_lo, const WArgs p) {
+  using C = WCfg<NB>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::STAGES;
+  uint64_t* acc_full = bars + 2 * C::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- work decode ----
+  int bid = blockIdx.x;
+  const int split = bid % p.splits;
+  bid /= p.splits;
+  const int ci_tile = bid % p.n_ci_tiles;
+  const int pair = bid / p.n_ci_tiles;
+  const int ntaps = p.KH * p.KW;
+  int blk_tap[2], blk_co0[2];
+  bool blk_ok[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int ab = 2 * pair + j;
+    blk_ok[j] = ab < ntaps * p.cob;
+    blk_tap[j] = blk_ok[j] ? ab / p.cob : 0;
+    blk_co0[j] = blk_ok[j] ? (ab % p.cob) * 64 : 0;
+  }
+  const int pt0 = split * p.tiles_per_split;
+  const int pt1 = min(pt0 + p.tiles_per_split, p.n_ptiles);
+  const int n_stages_total = pt1 - pt0;
+
+  if (p.zero_smem || !blk_ok[1]) {
+    // rows the TMA never writes (ragged boxes, missing second block) are part of the reduction
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    for (int i = threadIdx.x; i < C::STAGES * C::STAGE_BYTES / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (n_stages_total > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        prefetch_tmap(&tdy_hi); prefetch_tmap(&tdy_lo); prefetch_tmap(&tx_hi); prefetch_tmap(&tx_lo);
+        const uint32_t tx_bytes = (uint32_t)(((blk_ok[0] ? 2 : 0) + (blk_ok[1] ? 2 : 0) + 2 * NB) * p.rows * 128);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int pt = pt0; pt < pt1; ++pt) {
+          int b0, y0;
+          if (p.BB > 1) { b0 = pt * p.BB; y0 = 0; }
+          else { b0 = pt / p.tiles_per_img; y0 = (pt - b0 * p.tiles_per_img) * p.BH; }
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * C::STAGE_BYTES;
+          mbar_expect_tx(&full[stage], tx_bytes);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (!blk_ok[j]) continue;
+            const int ky = blk_tap[j] / p.KW, kx = blk_tap[j] - ky * p.KW;
+            // dY shifted by (pad - ky, pad - kx); out-of-image pixels are zero-filled by the TMA unit
+            tma_load_4d(st + j * BOX_BYTES, &tdy_hi, &full[stage], blk_co0[j], p.pad - kx, y0 + p.pad - ky, b0);
+            tma_load_4d(st + (2 + j) * BOX_BYTES, &tdy_lo, &full[stage], blk_co0[j], p.pad - kx, y0 + p.pad - ky, b0);
+          }
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) {
+            const int c0 = ci_tile * C::BN + nb * 64;
+            tma_load_4d(st + (4 + nb) * BOX_BYTES, &tx_hi, &full[stage], c0, 0, y0, b0);
+            tma_load_4d(st + (4 + NB + nb) * BOX_BYTES, &tx_lo, &full[stage], c0, 0, y0, b0);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // D = f32, A = B = bf16, both operands MN-major (bits 15, 16), N >> 3 at bit 17, M >> 4 at bit 24
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(C::BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t lbo = p.variant == 1 ? 1024u : (uint32_t)BOX_BYTES;
+        const uint32_t sbo = p.variant == 1 ? (uint32_t)BOX_BYTES : 1024u;
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t accum = 0;
+        for (int it = 0; it < n_stages_total; ++it) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t a_hi = sa, a_lo = sa + 2 * BOX_BYTES;
+          const uint32_t b_hi = sa + 4 * BOX_BYTES, b_lo = b_hi + NB * BOX_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < PIX / UMMA_K; ++ks) {
+            const uint32_t koff = ks * UMMA_K * 128;   // 16 pixel rows of 128 B
+            const uint64_t dah = make_sw128_mn_desc(a_hi + koff, lbo, sbo), dal = make_sw128_mn_desc(a_lo + koff, lbo, sbo);
+            const uint64_t dbh = make_sw128_mn_desc(b_hi + koff, lbo, sbo), dbl = make_sw128_mn_desc(b_lo + koff, lbo, sbo);
+            umma_bf16(tmem_base, dal, dbh, idesc, accum);
+            umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+            umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+            accum = 1u;
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(acc_full);
+      }
+    } else {
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      const int j = row >> 6;
+      const int co = blk_co0[j] + (row & 63);
+      const int KK = ntaps;
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16);
+      float* g = p.grad + ((int64_t)co * p.Cin + ci_tile * C::BN) * KK + blk_tap[j];
+#pragma unroll 1
+      for (int c0 = 0; c0 < C::BN; c0 += 32) {
+        float v[32];
+        tmem_ld_32x32(t_base + (uint32_t)c0, v);
+        if (blk_ok[j]) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) atomicAdd(g + (int64_t)(c0 + jj) * KK, v[jj]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+template <int NB>
+int launch_impl(const LaunchCtx& lc, const TcWgrad& t, const WArgs& a, int grid) {
+  using C = WCfg<NB>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(e));
+    attr_done = true;
+  }
+  wgrad_tc_kernel<NB><<<grid, 192, C::SMEM_BYTES, lc.stream>>>(t.dy_hi, t.dy_lo, t.x_hi, t.x_lo, a);
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+}  // namespace
+
+bool tcw_eligible(int Cin, int Cout, int H, int W, int KH) {
+  if (Cin < 64 || Cin % 64 != 0 || Cout < 64 || Cout % 64 != 0) return false;
+  if (KH != 1 && KH != 3) return false;
+  if (W < 1 || W > PIX || H < 1) return false;
+  return true;
+}
+
+int tcw_plan(Status& st, TcWgrad& t, int Cin, int Cout, int H, int W, int Bmax, int KH, int pad, __nv_bfloat16* dy_hi,
+             __nv_bfloat16* dy_lo, __nv_bfloat16* x_hi, __nv_bfloat16* x_lo) {
+  t.valid = false;
+  if (!tcw_eligible(Cin, Cout, H, W, KH)) IGM_FAIL(st, IGM_ERR_INVALID, "shape not eligible for the tcgen05 wgrad engine");
+  auto enc = encode_fn();
+  if (!enc) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  t.Cin = Cin; t.Cout = Cout; t.KH = t.KW = KH; t.pad = pad; t.H = H; t.W = W; t.Bmax = Bmax;
+  t.BW = W;
+  if (H * W <= PIX) { t.BH = H; t.BB = PIX / (H * W); }
+  else { t.BH = PIX / W; t.BB = 1; }
+  if (t.BB > Bmax) t.BB = Bmax;
+  t.rows = t.BB * t.BH * t.BW;
+  t.BN = (Cin % 128 == 0) ? 128 : 64;
+  struct { CUtensorMap* m; void* ptr; int C; } maps[4] = {
+      {&t.dy_hi, dy_hi, Cout}, {&t.dy_lo, dy_lo, Cout}, {&t.x_hi, x_hi, Cin}, {&t.x_lo, x_lo, Cin}};
+  for (auto& m : maps) {
+    cuuint64_t dims[4] = {(cuuint64_t)m.C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Bmax};
+    cuuint64_t strides[3] = {(cuuint64_t)m.C * 2, (cuuint64_t)W * m.C * 2, (cuuint64_t)H * W * m.C * 2};
+    cuuint32_t box[4] = {64u, (cuuint32_t)t.BW, (cuuint32_t)t.BH, (cuuint32_t)t.BB};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m.m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, m.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled (wgrad) failed");
+  }
+  t.valid = true;
+  return IGM_OK;
+}
+
+bool tcw_batch_ok(const TcWgrad& t, int B) { return t.valid && B >= 1 && B <= t.Bmax && (B % t.BB) == 0; }
+
+int launch_wgrad_tc(const LaunchCtx& lc, const TcWgrad& t, int B, float* grad, int variant) {
+  if (!tcw_batch_ok(t, B)) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "wgrad_tc: batch must be a multiple of the images per box");
+  WArgs a;
+  a.B = B; a.H = t.H; a.W = t.W; a.Cin = t.Cin; a.Cout = t.Cout; a.KH = t.KH; a.KW = t.KW; a.pad = t.pad;
+  a.BW = t.BW; a.BH = t.BH; a.BB = t.BB; a.rows = t.rows;
+  a.tiles_per_img = (t.BB > 1) ? 1 : cdiv(t.H, t.BH);
+  a.n_ptiles = (t.BB > 1) ? B / t.BB : B * a.tiles_per_img;
+  a.cob = t.Cout / 64;
+  a.n_pairs = cdiv(t.KH * t.KW * a.cob, 2);
+  a.n_ci_tiles = t.Cin / t.BN;
+  const int base = a.n_pairs * a.n_ci_tiles;
+  int splits = (2 * 148 + base - 1) / base;
+  if (splits > a.n_ptiles) splits = a.n_ptiles;
+  if (splits < 1) splits = 1;
+  a.tiles_per_split = cdiv(a.n_ptiles, splits);
+  a.splits = cdiv(a.n_ptiles, a.tiles_per_split);
+  a.zero_smem = t.rows < PIX ? 1 : 0;
+  a.variant = variant;
+  a.grad = grad;
+  const double flops = 2.0 * B * t.H * t.W * (double)t.Cin * t.Cout * t.KH * t.KW;
+  const double bytes = 4.0 * ((double)B * t.H * t.W * (t.Cin + t.Cout) + (double)t.KH * t.KW * t.Cin * t.Cout);
+  ProfScope ps_(lc, K_CONV_WGRAD, flops, bytes);
+  const int grid = base * a.splits;
+  if (t.BN == 128) return launch_impl<2>(lc, t, a, grid);
+  return launch_impl<1>(lc, t, a, grid);
+}
+
+}  // namespace igm

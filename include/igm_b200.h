@@ -163,6 +163,10 @@ int64_t igm_launch_count(const igm_ctx* ctx);
 int igm_debug_conv(int engine, int mode, const float* x, const float* w_oihw, const float* bias,
                    const float* add, float* out, int B, int H, int W, int Cin, int Cout, int K,
                    void* stream);
+/* Weight gradient of the same convolution: gw[Cout,Cin,K,K] (fp32, ACCUMULATED) += dY (x) X with
+ * x[B,H,W,Cin], dy[B,H,W,Cout] NHWC.  variant is a bring-up switch of the tcgen05 path (use 0). */
+int igm_debug_wgrad(int engine, int variant, const float* x, const float* dy, float* gw, int B, int H,
+                    int W, int Cin, int Cout, int K, void* stream);
 /* Which conv engine is active: 0 = SIMT fp32 implicit GEMM, 1 = tcgen05 bf16x3 (default when
  * the layer shapes allow it; environment IGM_CONV_ENGINE=0 forces the SIMT engine). */
 int igm_set_conv_engine(igm_ctx* ctx, int engine);
