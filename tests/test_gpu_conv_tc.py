@@ -73,3 +73,48 @@ def test_conv_tc_dgrad(shape):
     assert l2s < 1e-5 and mxs < 1e-5, f"SIMT engine off: {l2s:.2e} {mxs:.2e}"
     l2, mx = rel_err(tc, ref)
     assert l2 < 1e-4 and mx < 1e-4, f"tcgen05 engine: rel-L2 {l2:.2e} max-rel {mx:.2e}"
+
+
+WSHAPES = [
+    # B, H, W, Cin, Cout, K
+    (2, 32, 32, 64, 64, 3),
+    (2, 32, 32, 64, 128, 3),
+    (2, 32, 32, 128, 64, 3),
+    (4, 16, 16, 128, 128, 3),
+    (4, 8, 8, 256, 256, 3),
+    (3, 8, 8, 512, 128, 3),
+    (2, 32, 32, 64, 384, 1),
+    (2, 16, 16, 128, 64, 1),
+    (2, 28, 28, 128, 128, 3),    # ragged 56-row boxes (zero-initialised smem rows)
+    (2, 14, 14, 256, 256, 3),
+    (1, 64, 64, 64, 64, 3),
+    (8, 4, 4, 64, 64, 3),        # 4 images per box
+]
+
+
+def _wgrad(engine, variant, x, dy, B, H, W, Cin, Cout, K):
+    lib = _lib.load()
+    gw = torch.zeros(Cout, Cin, K, K, device="cuda", dtype=torch.float32)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    rc = lib.igm_debug_wgrad(engine, variant, p(x), p(dy), p(gw), B, H, W, Cin, Cout, K, None)
+    assert rc == 0, lib.igm_last_error(None).decode()
+    torch.cuda.synchronize()
+    return gw
+
+
+@pytest.mark.parametrize("shape", WSHAPES)
+def test_wgrad_tc(shape):
+    B, H, W, Cin, Cout, K = shape
+    g = torch.Generator().manual_seed(2 + hash(shape) % 1000)
+    x = torch.randn(B, H, W, Cin, generator=g)
+    dy = torch.randn(B, H, W, Cout, generator=g)
+    xr = x.permute(0, 3, 1, 2).double()
+    w = torch.zeros(Cout, Cin, K, K, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(xr, w, padding=(K - 1) // 2)
+    ref, = torch.autograd.grad(y, w, dy.permute(0, 3, 1, 2).double())
+    simt = _wgrad(0, 0, x.cuda(), dy.cuda(), B, H, W, Cin, Cout, K).cpu()
+    l2s, mxs = rel_err(simt, ref)
+    assert l2s < 1e-5 and mxs < 1e-5, f"SIMT wgrad off: {l2s:.2e} {mxs:.2e}"
+    tc = _wgrad(1, 0, x.cuda(), dy.cuda(), B, H, W, Cin, Cout, K).cpu()
+    l2, mx = rel_err(tc, ref)
+    assert l2 < 1e-4 and mx < 1e-4, f"tcgen05 wgrad: rel-L2 {l2:.2e} max-rel {mx:.2e}"
