@@ -80,9 +80,10 @@ struct ConvL {
   float* w_bwd = nullptr;   // [K*K][Cout][Cin]
   // tcgen05 engine (stride-1 Conv2d only): bf16 hi/lo weights [N][taps*K] and TMA plans
   int H = 0, W = 0;         // spatial size the layer runs at (0: not a stride-1 conv)
-  bool tc_f_ok = false, tc_b_ok = false;
+  bool tc_f_ok = false, tc_b_ok = false, tc_w_ok = false;
   __nv_bfloat16 *wf_hi = nullptr, *wf_lo = nullptr, *wb_hi = nullptr, *wb_lo = nullptr;
   TcConv tc_f, tc_b;
+  TcWgrad tc_w;
 };
 
 struct BlockL {
@@ -184,6 +185,7 @@ struct igm_ctx {
   float *ws_group = nullptr, *ws_chan = nullptr, *ws_ln = nullptr;
   float *scrA = nullptr, *scrB = nullptr, *scrC = nullptr;
   __nv_bfloat16 *split_hi = nullptr, *split_lo = nullptr;   // bf16x2 staging of a conv's input (tcgen05 engine)
+  __nv_bfloat16 *dy_hi = nullptr, *dy_lo = nullptr;         // bf16x2 staging of an output gradient
   bool tc_available = false;
   float* pred = nullptr;        // [B,C,H,W] network output (NCHW)
   float* noise_copy = nullptr;  // NCHW
@@ -252,7 +254,7 @@ struct PlanBuilder {
   Arena ar;
   bool training;
   int B;
-  int64_t maxMC = 0, maxM = 0, maxGnWs = 0, maxSplit = 0;
+  int64_t maxMC = 0, maxM = 0, maxGnWs = 0, maxSplit = 0, maxDy = 0;
 
   PlanBuilder(igm_ctx& ctx, float* base) : c(ctx), pb{ctx.params} {
     ar.base = base;
@@ -297,7 +299,12 @@ struct PlanBuilder {
       if (l.tc_b_ok) {
         l.wb_hi = reinterpret_cast<__nv_bfloat16*>(ar.alloc((nw + 1) / 2));
         l.wb_lo = reinterpret_cast<__nv_bfloat16*>(ar.alloc((nw + 1) / 2));
-        maxSplit = std::max(maxSplit, M(H, W) * Cout);
+        maxDy = std::max(maxDy, M(H, W) * Cout);
+      }
+      l.tc_w_ok = training && tcw_eligible(Cin, Cout, H, W, K);
+      if (l.tc_w_ok) {
+        maxSplit = std::max(maxSplit, M(H, W) * Cin);
+        maxDy = std::max(maxDy, M(H, W) * Cout);
       }
     }
     return l;
@@ -479,6 +486,10 @@ struct PlanBuilder {
       c.split_hi = reinterpret_cast<__nv_bfloat16*>(ar.alloc((maxSplit + 1) / 2));
       c.split_lo = reinterpret_cast<__nv_bfloat16*>(ar.alloc((maxSplit + 1) / 2));
     }
+    if (maxDy > 0) {
+      c.dy_hi = reinterpret_cast<__nv_bfloat16*>(ar.alloc((maxDy + 1) / 2));
+      c.dy_lo = reinterpret_cast<__nv_bfloat16*>(ar.alloc((maxDy + 1) / 2));
+    }
   }
 };
 
@@ -517,10 +528,12 @@ struct Runner {
     return launch_conv(lc, a);
   }
   // data gradient: d_out [B,OH,OW,Cout] -> d_in split (d0: C0 channels, d1: C1 channels)
+  // dy_staged: the bf16 hi/lo copy of d_out already sits in the dy staging buffers (conv_bwd)
   int conv_dgrad(const ConvL& l, const float* d_out, int OH, int OW, int IH, int IW, int stride, int pad,
-                 float* d0, int C0, float* d1, int C1, const float* add0, const float* add1) {
+                 float* d0, int C0, float* d1, int C1, const float* add0, const float* add1,
+                 bool dy_staged = false) {
     if (stride == 1 && use_tc(l.tc_b) && C0 % 32 == 0) {
-      IGM_TRY(launch_split_bf16(lc, d_out, M(OH, OW), l.Cout, c.split_hi, c.split_lo, l.Cout, 0));
+      if (!dy_staged) IGM_TRY(launch_split_bf16(lc, d_out, M(OH, OW), l.Cout, c.dy_hi, c.dy_lo, l.Cout, 0));
       TcRun r;
       r.B = B; r.bias = nullptr; r.out0 = d0; r.out1 = d1; r.N0 = C0; r.add0 = add0; r.add1 = add1;
       r.kclass = K_CONV_DGRAD;
@@ -540,10 +553,17 @@ struct Runner {
   }
   // weight + bias gradients.  in0/in1: forward inputs; d_out: grad of the conv output
   int conv_wgrad(const ConvL& l, const float* in0, int C0, const float* in1, int C1, int IH, int IW,
-                 const float* d_out, int OH, int OW, int stride, int pad) {
+                 const float* d_out, int OH, int OW, int stride, int pad, bool dy_staged = false) {
     const int KK = l.K * l.K;
     float* gw = c.Gp(l.pw);
-    if (!l.convT) {
+    if (stride == 1 && c.conv_engine == 1 && tcw_batch_ok(l.tc_w, B)) {
+      // tensor-core path: stage X (and dY unless the caller already did) as bf16 hi/lo, then split-K GEMM
+      const int Ct = C0 + C1;
+      if (!dy_staged) IGM_TRY(launch_split_bf16(lc, d_out, M(OH, OW), l.Cout, c.dy_hi, c.dy_lo, l.Cout, 0));
+      IGM_TRY(launch_split_bf16(lc, in0, M(IH, IW), C0, c.split_hi, c.split_lo, Ct, 0));
+      if (in1 && C1 > 0) IGM_TRY(launch_split_bf16(lc, in1, M(IH, IW), C1, c.split_hi, c.split_lo, Ct, C0));
+      IGM_TRY(launch_wgrad_tc(lc, l.tc_w, B, gw));
+    } else if (!l.convT) {
       // Conv2d: P = d_out (pc = co), Q = input (qc = ci) gathered at oy*s - p + ky;  W[co][ci][tap]
       const float* srcs[2] = {in0, in1};
       const int cs[2] = {C0, C1};
@@ -570,6 +590,21 @@ struct Runner {
       IGM_TRY(launch_wgrad(lc, w));
     }
     if (l.pb >= 0) IGM_TRY(launch_colsum(lc, d_out, M(OH, OW), l.Cout, c.Gp(l.pb)));
+    return IGM_OK;
+  }
+
+  // Backward of a stride-1 conv: weight/bias gradients, then (if d0) the data gradient.  dY is staged
+  // once as bf16 hi/lo and shared by the tensor-core wgrad and dgrad kernels.
+  int conv_bwd(const ConvL& l, const float* in0, int C0, const float* in1, int C1, int H, int W, const float* dY,
+               float* d0, float* d1, const float* add0, const float* add1) {
+    const int pad = (l.K - 1) / 2;
+    bool staged = false;
+    if (c.conv_engine == 1 && (tcw_batch_ok(l.tc_w, B) || (d0 && l.tc_b.valid && C0 % 32 == 0))) {
+      IGM_TRY(launch_split_bf16(lc, dY, M(H, W), l.Cout, c.dy_hi, c.dy_lo, l.Cout, 0));
+      staged = true;
+    }
+    IGM_TRY(conv_wgrad(l, in0, C0, in1, C1, H, W, dY, H, W, 1, pad, staged));
+    if (d0) IGM_TRY(conv_dgrad(l, dY, H, W, H, W, 1, pad, d0, C0, d1, C1, add0, add1, staged));
     return IGM_OK;
   }
 
@@ -611,19 +646,14 @@ struct Runner {
     const float* d_out = r.out.g;
     // block2
     IGM_TRY(block_bwd_norm(r.b2, d_out, H, W, nullptr));
-    IGM_TRY(conv_wgrad(r.b2.conv, r.h1.v, r.Cout, nullptr, 0, H, W, c.scrA, H, W, 1, 1));
-    IGM_TRY(conv_dgrad(r.b2.conv, c.scrA, H, W, H, W, 1, 1, r.h1.g, r.Cout, nullptr, 0, nullptr, nullptr));
+    IGM_TRY(conv_bwd(r.b2.conv, r.h1.v, r.Cout, nullptr, 0, H, W, c.scrA, r.h1.g, nullptr, nullptr, nullptr));
     // block1 (+ time-embedding add)
     IGM_TRY(block_bwd_norm(r.b1, r.h1.g, H, W, c.t_dproj + r.temb_off));
-    IGM_TRY(conv_wgrad(r.b1.conv, in0, C0, in1, C1, H, W, c.scrA, H, W, 1, 1));
     if (r.has_res) {
-      IGM_TRY(conv_wgrad(r.res, in0, C0, in1, C1, H, W, d_out, H, W, 1, 0));
-      if (d0) {
-        IGM_TRY(conv_dgrad(r.res, d_out, H, W, H, W, 1, 0, d0, C0, d1, C1, nullptr, nullptr));
-        IGM_TRY(conv_dgrad(r.b1.conv, c.scrA, H, W, H, W, 1, 1, d0, C0, d1, C1, d0, d1));
-      }
-    } else if (d0) {
-      IGM_TRY(conv_dgrad(r.b1.conv, c.scrA, H, W, H, W, 1, 1, d0, C0, nullptr, 0, d_out, nullptr));
+      IGM_TRY(conv_bwd(r.res, in0, C0, in1, C1, H, W, d_out, d0, d1, nullptr, nullptr));
+      IGM_TRY(conv_bwd(r.b1.conv, in0, C0, in1, C1, H, W, c.scrA, d0, d1, d0, d1));
+    } else {
+      IGM_TRY(conv_bwd(r.b1.conv, in0, C0, in1, C1, H, W, c.scrA, d0, nullptr, d_out, nullptr));
     }
     return IGM_OK;
   }
@@ -643,11 +673,9 @@ struct Runner {
     const int64_t m = M(H, W);
     const int hd = kHeads * kDimHead;
     const float* d_out = a.out.g;
-    IGM_TRY(conv_wgrad(a.outc, a.att, hd, nullptr, 0, H, W, d_out, H, W, 1, 0));
-    IGM_TRY(conv_dgrad(a.outc, d_out, H, W, H, W, 1, 0, c.scrB, hd, nullptr, 0, nullptr, nullptr));
+    IGM_TRY(conv_bwd(a.outc, a.att, hd, nullptr, 0, H, W, d_out, c.scrB, nullptr, nullptr, nullptr));
     IGM_TRY(launch_linattn_backward(lc, a.qkv_t, a.ctx, a.kstat, c.scrB, c.scrC, B, H * W));
-    IGM_TRY(conv_wgrad(a.qkv, a.ln, a.C, nullptr, 0, H, W, c.scrC, H, W, 1, 0));
-    IGM_TRY(conv_dgrad(a.qkv, c.scrC, H, W, H, W, 1, 0, c.scrA, a.C, nullptr, 0, nullptr, nullptr));
+    IGM_TRY(conv_bwd(a.qkv, a.ln, a.C, nullptr, 0, H, W, c.scrC, c.scrA, nullptr, nullptr, nullptr));
     IGM_TRY(launch_ln_backward(lc, c.scrA, x, c.Pp(a.ln_g), d_out, dx, c.Gp(a.ln_g), c.Gp(a.ln_b), c.ws_ln, m, a.C));
     return IGM_OK;
   }
@@ -727,8 +755,7 @@ struct Runner {
     if (nres > 1) { fin = c.ups.back().rs.out.v; finC = c.ups.back().rs.out.C; fin_g = c.ups.back().rs.out.g; }
     else { fin = c.mid2.out.v; finC = c.mid2.Cout; fin_g = c.mid2.out.g; }
     IGM_TRY(block_bwd_norm(c.final_block, c.final_act.g, H0, W0, nullptr));
-    IGM_TRY(conv_wgrad(c.final_block.conv, fin, finC, nullptr, 0, H0, W0, c.scrA, H0, W0, 1, 1));
-    IGM_TRY(conv_dgrad(c.final_block.conv, c.scrA, H0, W0, H0, W0, 1, 1, fin_g, finC, nullptr, 0, nullptr, nullptr));
+    IGM_TRY(conv_bwd(c.final_block.conv, fin, finC, nullptr, 0, H0, W0, c.scrA, fin_g, nullptr, nullptr, nullptr));
 
     for (int j = nres - 2; j >= 0; --j) {
       Stage& s = c.ups[j];
@@ -819,9 +846,12 @@ static int plan_tc(igm_ctx* c) {
       IGM_TRY(tc_plan(c->st, l.tc_f, l.Cin, l.Cout, l.H, l.W, c->cfg.max_batch, l.K, (l.K - 1) / 2, c->split_hi,
                       c->split_lo, l.wf_hi, l.wf_lo));
     if (l.tc_b_ok)
-      IGM_TRY(tc_plan(c->st, l.tc_b, l.Cout, l.Cin, l.H, l.W, c->cfg.max_batch, l.K, (l.K - 1) / 2, c->split_hi,
-                      c->split_lo, l.wb_hi, l.wb_lo));
-    n_valid += (l.tc_f.valid ? 1 : 0) + (l.tc_b.valid ? 1 : 0);
+      IGM_TRY(tc_plan(c->st, l.tc_b, l.Cout, l.Cin, l.H, l.W, c->cfg.max_batch, l.K, (l.K - 1) / 2, c->dy_hi,
+                      c->dy_lo, l.wb_hi, l.wb_lo));
+    if (l.tc_w_ok)
+      IGM_TRY(tcw_plan(c->st, l.tc_w, l.Cin, l.Cout, l.H, l.W, c->cfg.max_batch, l.K, (l.K - 1) / 2, c->dy_hi,
+                       c->dy_lo, c->split_hi, c->split_lo));
+    n_valid += (l.tc_f.valid ? 1 : 0) + (l.tc_b.valid ? 1 : 0) + (l.tc_w.valid ? 1 : 0);
     return IGM_OK;
   });
   c->tc_available = (rc == IGM_OK) && n_valid > 0;
