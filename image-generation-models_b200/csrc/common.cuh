@@ -161,6 +161,21 @@ int launch_colsum(const LaunchCtx& lc, const float* x, int64_t M, int N, float* 
 int launch_pack_weight(const LaunchCtx& lc, const float* src, float* dst, int taps, int K, int N,
                        int64_t sk, int64_t sn);
 
+// All weight re-packs of a network in ONE launch: a device table of jobs, each either
+//   fp32  dst_f[tap][k][n]              (SIMT engine)            or
+//   bf16  dst_hi/lo[n][tap*K + k]       (tcgen05 engine, optional tap flip)
+// with element (n, tap, k) read from src[k*sk + n*sn + tap'].
+struct PackJob {
+  const float* src;
+  float* dst_f;
+  void* dst_hi;
+  void* dst_lo;
+  int taps, K, N, flip;
+  int64_t sk, sn;
+  int64_t begin;   // prefix sum of element counts
+};
+int launch_pack_jobs(const LaunchCtx& lc, const PackJob* d_jobs, int n_jobs, int64_t total);
+
 // ---------------------------------------------------------------------------
 // normalisation / activation kernels (norm_act.cu)
 // ---------------------------------------------------------------------------
@@ -176,6 +191,7 @@ int launch_gn_apply(const LaunchCtx& lc, const float* y, const float* part, cons
 struct GnBwdArgs {
   const float* d_out; const float* y; const float* stats; const float* gamma; const float* beta;
   float* dy; float* dgamma; float* dbeta; float* dtemb; int dtemb_stride;
+  float* dbias;       // optional: += column sums of dy (gradient of the bias of the conv feeding this norm)
   float* ws_group;    // [B][chunks][G][2]
   float* ws_chan;     // [B][chunks][C][3]
   int B, HW, C;

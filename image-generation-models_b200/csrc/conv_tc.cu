@@ -255,6 +255,35 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ src, __nv_bfloat
   }
 }
 
+__global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJob* __restrict__ jobs, int n_jobs, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n_jobs - 1;
+    while (lo < hi) {   // last job whose begin <= i
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].begin <= i) lo = mid; else hi = mid - 1;
+    }
+    const PackJob& j = jobs[lo];
+    const int64_t e = i - j.begin;
+    if (j.dst_f) {
+      const int n = (int)(e % j.N);
+      const int64_t r = e / j.N;
+      const int k = (int)(r % j.K);
+      const int tap = (int)(r / j.K);
+      j.dst_f[e] = __ldg(j.src + k * j.sk + n * j.sn + tap);
+    } else {
+      const int k = (int)(e % j.K);
+      const int64_t r = e / j.K;
+      const int tap = (int)(r % j.taps);
+      const int n = (int)(r / j.taps);
+      const int ts = j.flip ? (j.taps - 1 - tap) : tap;
+      const float x = __ldg(j.src + k * j.sk + n * j.sn + ts);
+      const __nv_bfloat16 h = __float2bfloat16_rn(x);
+      reinterpret_cast<__nv_bfloat16*>(j.dst_hi)[e] = h;
+      reinterpret_cast<__nv_bfloat16*>(j.dst_lo)[e] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+  }
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (!fn) {
@@ -363,6 +392,16 @@ int launch_split_bf16(const LaunchCtx& lc, const float* src, int64_t M, int C, _
   if (blocks > 148 * 16) blocks = 148 * 16;
   ProfScope ps_(lc, K_ELEM, 2.0 * M * C, 8.0 * M * C);
   split_bf16_kernel<<<blocks, 256, 0, lc.stream>>>(src, M, C, hi, lo, cdst, coff);
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+int launch_pack_jobs(const LaunchCtx& lc, const PackJob* d_jobs, int n_jobs, int64_t total) {
+  if (n_jobs <= 0 || total <= 0) return IGM_OK;
+  int blocks = (int)cdiv64(total, 256 * 4);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  ProfScope ps_(lc, K_PACK, 0.0, 8.0 * total);
+  pack_jobs_kernel<<<blocks, 256, 0, lc.stream>>>(d_jobs, n_jobs, total);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }

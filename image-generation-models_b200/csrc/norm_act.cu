@@ -194,6 +194,8 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdArgs a, i
 // ---- backward, pass 2: dy ------------------------------------------------------
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a, int nchunks) {
   __shared__ float s_m1[kGroups], s_m2[kGroups];
+  __shared__ float4 s_db[256];
+  float dbs[4] = {0.f, 0.f, 0.f, 0.f};
   const GnLayout ly(a.C);
   const int b = blockIdx.x / nchunks, chunk = blockIdx.x % nchunks;
   if (threadIdx.x < kGroups) {
@@ -231,44 +233,56 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a, in
       const float g = n * ga[j] + be[j];
       const float dn = dv[j] * mish_grad_f(g) * ga[j];
       o[j] = rstd * (dn - m1 - n * m2);
+      dbs[j] += o[j];
     }
     *reinterpret_cast<float4*>(a.dy + off) = make_float4(o[0], o[1], o[2], o[3]);
   }
+  if (a.dbias) {
+    // conv-bias gradient = column sums of dy: fold the pixel slots, then one atomic per channel per CTA
+    s_db[threadIdx.x] = make_float4(dbs[0], dbs[1], dbs[2], dbs[3]);
+    __syncthreads();
+    if (threadIdx.x < ly.L) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int sidx = 0; sidx < ly.PPI; ++sidx) {
+        const float4 v = s_db[sidx * ly.L + threadIdx.x];
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      float* d = a.dbias + threadIdx.x * 4;
+      atomicAdd(d + 0, t.x); atomicAdd(d + 1, t.y); atomicAdd(d + 2, t.z); atomicAdd(d + 3, t.w);
+    }
+  }
 }
-
 // ---- backward, pass 3: parameter / time-embedding gradients -------------------
-// block (32, 8); grid.x = C/32 column slabs
+// grid (C/32 column slabs, B samples), block (32, 8): each CTA folds the chunk partials of one
+// sample; dtemb[b, c] is written directly, dgamma/dbeta get one atomic per (sample, channel).
 __global__ void __launch_bounds__(256) gn_bwd_param_kernel(const GnBwdArgs a, int nchunks) {
-  __shared__ float red[8][2][33];
+  __shared__ float red[8][3][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
-  const int entries = a.B * nchunks;
-  float sg = 0.f, sb = 0.f;
+  const int b = blockIdx.y;
+  float sg = 0.f, sb = 0.f, st = 0.f;
   if (c < a.C) {
-    for (int e = threadIdx.y; e < entries; e += 8) {
-      const float* o = a.ws_chan + (int64_t)e * 3 * a.C;
+    for (int ch = threadIdx.y; ch < nchunks; ch += 8) {
+      const float* o = a.ws_chan + ((int64_t)b * nchunks + ch) * 3 * a.C;
       sg += o[c];
       sb += o[a.C + c];
+      st += o[2 * a.C + c];
     }
   }
   red[threadIdx.y][0][threadIdx.x] = sg;
   red[threadIdx.y][1][threadIdx.x] = sb;
+  red[threadIdx.y][2][threadIdx.x] = st;
   __syncthreads();
   if (threadIdx.y == 0 && c < a.C) {
-    float tg = 0.f, tb = 0.f;
+    float tg = 0.f, tb = 0.f, tt = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       tg += red[i][0][threadIdx.x];
       tb += red[i][1][threadIdx.x];
+      tt += red[i][2][threadIdx.x];
     }
-    a.dgamma[c] += tg;   // unique writer per channel
-    a.dbeta[c] += tb;
-  }
-  if (a.dtemb && c < a.C) {
-    for (int b = threadIdx.y; b < a.B; b += 8) {
-      float t = 0.f;
-      for (int ch = 0; ch < nchunks; ++ch) t += a.ws_chan[((int64_t)b * nchunks + ch) * 3 * a.C + 2 * a.C + c];
-      a.dtemb[(int64_t)b * a.dtemb_stride + c] = t;
-    }
+    atomicAdd(a.dgamma + c, tg);
+    atomicAdd(a.dbeta + c, tb);
+    if (a.dtemb) a.dtemb[(int64_t)b * a.dtemb_stride + c] = tt;
   }
 }
 
@@ -422,17 +436,31 @@ __global__ void __launch_bounds__(256) ln_backward_kernel(const float* __restric
   }
 }
 
-__global__ void ln_param_finalize_kernel(const float* __restrict__ ws, int nparts, int C, float* __restrict__ dg,
-                                         float* __restrict__ db) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// grid C/32, block (32, 32): 32 row lanes stride over the per-CTA partials
+__global__ void __launch_bounds__(1024) ln_param_finalize_kernel(const float* __restrict__ ws, int nparts, int C,
+                                                                 float* __restrict__ dg, float* __restrict__ db) {
+  __shared__ float red[32][2][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float tg = 0.f, tb = 0.f;
-  for (int p = 0; p < nparts; ++p) {
-    tg += ws[((int64_t)p * 2 + 0) * C + c];
-    tb += ws[((int64_t)p * 2 + 1) * C + c];
+  if (c < C) {
+    for (int p = threadIdx.y; p < nparts; p += 32) {
+      tg += ws[((int64_t)p * 2 + 0) * C + c];
+      tb += ws[((int64_t)p * 2 + 1) * C + c];
+    }
   }
-  dg[c] += tg;
-  db[c] += tb;
+  red[threadIdx.y][0][threadIdx.x] = tg;
+  red[threadIdx.y][1][threadIdx.x] = tb;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float sg = 0.f, sb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      sg += red[i][0][threadIdx.x];
+      sb += red[i][1][threadIdx.x];
+    }
+    dg[c] += sg;
+    db[c] += sb;
+  }
 }
 
 }  // namespace
@@ -471,7 +499,7 @@ int launch_gn_backward(const LaunchCtx& lc, const GnBwdArgs& a) {
   IGM_POST_LAUNCH(lc);
   gn_bwd_apply_kernel<<<a.B * nchunks, 256, 0, lc.stream>>>(a, nchunks);
   IGM_POST_LAUNCH(lc);
-  gn_bwd_param_kernel<<<cdiv(a.C, 32), dim3(32, 8), 0, lc.stream>>>(a, nchunks);
+  gn_bwd_param_kernel<<<dim3(cdiv(a.C, 32), a.B), dim3(32, 8), 0, lc.stream>>>(a, nchunks);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }
@@ -506,7 +534,7 @@ int launch_ln_backward(const LaunchCtx& lc, const float* d_out, const float* x, 
   }
   ln_backward_kernel<<<grid, 256, smem, lc.stream>>>(d_out, x, g, d_res, dx, ws, M, C);
   IGM_POST_LAUNCH(lc);
-  ln_param_finalize_kernel<<<cdiv(C, 128), 128, 0, lc.stream>>>(ws, grid, C, dg, db);
+  ln_param_finalize_kernel<<<cdiv(C, 32), dim3(32, 32), 0, lc.stream>>>(ws, grid, C, dg, db);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }

@@ -84,6 +84,7 @@ struct ConvL {
   __nv_bfloat16 *wf_hi = nullptr, *wf_lo = nullptr, *wb_hi = nullptr, *wb_lo = nullptr;
   TcConv tc_f, tc_b;
   TcWgrad tc_w;
+  bool bias_in_norm = false;   // bias gradient is produced by the GroupNorm backward that follows this conv
 };
 
 struct BlockL {
@@ -187,6 +188,9 @@ struct igm_ctx {
   __nv_bfloat16 *split_hi = nullptr, *split_lo = nullptr;   // bf16x2 staging of a conv's input (tcgen05 engine)
   __nv_bfloat16 *dy_hi = nullptr, *dy_lo = nullptr;         // bf16x2 staging of an output gradient
   bool tc_available = false;
+  PackJob* pack_dev = nullptr;        // device job table of igm_unet_pack_weights
+  int pack_n = 0, pack_engine = -1;
+  int64_t pack_total = 0;
   float* pred = nullptr;        // [B,C,H,W] network output (NCHW)
   float* noise_copy = nullptr;  // NCHW
   float* d_pred = nullptr;      // NHWC [M, C]
@@ -313,6 +317,7 @@ struct PlanBuilder {
   BlockL block(const std::string& name, int Cin, int Cout, int H, int W) {
     BlockL b;
     b.conv = conv(name + ".block.0", Cin, Cout, 3, true, false, H, W);
+    b.conv.bias_in_norm = true;
     b.gn_w = pb.add(name + ".block.1.weight", {Cout});
     b.gn_b = pb.add(name + ".block.1.bias", {Cout});
     b.raw = ar.alloc(M(H, W) * Cout);
@@ -470,6 +475,7 @@ struct PlanBuilder {
     c.loop_state = reinterpret_cast<int*>(ar.alloc(64));
     c.sched_dev = reinterpret_cast<igm_schedule*>(ar.alloc(64));
     c.proj_dev = reinterpret_cast<TimeProj*>(ar.alloc((int64_t)(sizeof(TimeProj) * c.n_proj + 3) / 4 + 64));
+    c.pack_dev = reinterpret_cast<PackJob*>(ar.alloc((int64_t)(sizeof(PackJob) * 1024) / 4));
     if (training) {
       c.t_dproj = ar.alloc((int64_t)B * c.proj_total);
       c.t_ws = ar.alloc((int64_t)B * 6 * d);
@@ -589,7 +595,7 @@ struct Runner {
       w.sq = KK; w.sp = (int64_t)l.Cout * KK;
       IGM_TRY(launch_wgrad(lc, w));
     }
-    if (l.pb >= 0) IGM_TRY(launch_colsum(lc, d_out, M(OH, OW), l.Cout, c.Gp(l.pb)));
+    if (l.pb >= 0 && !l.bias_in_norm) IGM_TRY(launch_colsum(lc, d_out, M(OH, OW), l.Cout, c.Gp(l.pb)));
     return IGM_OK;
   }
 
@@ -624,6 +630,7 @@ struct Runner {
     g.gamma = c.Pp(b.gn_w); g.beta = c.Pp(b.gn_b);
     g.dy = c.scrA; g.dgamma = c.Gp(b.gn_w); g.dbeta = c.Gp(b.gn_b);
     g.dtemb = dtemb; g.dtemb_stride = c.proj_total;
+    g.dbias = c.Gp(b.conv.pb);
     g.ws_group = c.ws_group; g.ws_chan = c.ws_chan;
     g.B = B; g.HW = H * W; g.C = b.conv.Cout;
     return launch_gn_backward(lc, g);
@@ -994,24 +1001,47 @@ int igm_unet_bind_params(igm_ctx* c, float* params, float* grads) {
   fill(c->mid1); fill(c->mid2);
   IGM_CUDA(c->st, cudaMemcpy(c->proj_dev, c->proj_host.data(), sizeof(TimeProj) * c->n_proj, cudaMemcpyHostToDevice));
   if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+  c->pack_engine = -1;   // job table holds raw parameter pointers: rebuild at the next pack
   return IGM_OK;
 }
 
-static int pack_conv(igm_ctx* c, const LaunchCtx& lc, const ConvL& l) {
-  const int KK = l.K * l.K;
-  const float* w = c->Pp(l.pw);
-  if (!l.convT) {
-    IGM_TRY(launch_pack_weight(lc, w, l.w_fwd, KK, l.Cin, l.Cout, KK, (int64_t)l.Cin * KK));
-    if (l.w_bwd) IGM_TRY(launch_pack_weight(lc, w, l.w_bwd, KK, l.Cout, l.Cin, (int64_t)l.Cin * KK, KK));
-    // tcgen05 engine: Wt[n][tap*K + k] as bf16 hi/lo; the data gradient uses flipped taps
-    if (l.tc_f.valid)
-      IGM_TRY(launch_pack_weight_tc(lc, w, l.wf_hi, l.wf_lo, KK, l.Cin, l.Cout, KK, (int64_t)l.Cin * KK, 0));
-    if (l.tc_b.valid)
-      IGM_TRY(launch_pack_weight_tc(lc, w, l.wb_hi, l.wb_lo, KK, l.Cout, l.Cin, (int64_t)l.Cin * KK, KK, 1));
-  } else {
-    IGM_TRY(launch_pack_weight(lc, w, l.w_fwd, KK, l.Cin, l.Cout, (int64_t)l.Cout * KK, KK));
-    if (l.w_bwd) IGM_TRY(launch_pack_weight(lc, w, l.w_bwd, KK, l.Cout, l.Cin, KK, (int64_t)l.Cout * KK));
-  }
+// Job list of one full re-pack for the active engine (only the layouts that engine reads).
+static int build_pack_jobs(igm_ctx* c) {
+  std::vector<PackJob> jobs;
+  int64_t total = 0;
+  auto add = [&](const float* src, float* dst_f, void* hi, void* lo, int taps, int K, int N, int64_t sk, int64_t sn,
+                 int flip) {
+    PackJob j{};
+    j.src = src; j.dst_f = dst_f; j.dst_hi = hi; j.dst_lo = lo;
+    j.taps = taps; j.K = K; j.N = N; j.flip = flip; j.sk = sk; j.sn = sn; j.begin = total;
+    total += (int64_t)taps * K * N;
+    jobs.push_back(j);
+  };
+  const bool tc = c->conv_engine == 1;
+  for_each_conv(c, [&](ConvL& l) -> int {
+    const int KK = l.K * l.K;
+    const float* w = c->Pp(l.pw);
+    if (!l.convT) {
+      // Conv2d OIHW: fprop contracts ci (sk = KK, sn = Cin*KK); dgrad contracts co
+      if (tc && l.tc_f.valid) add(w, nullptr, l.wf_hi, l.wf_lo, KK, l.Cin, l.Cout, KK, (int64_t)l.Cin * KK, 0);
+      else add(w, l.w_fwd, nullptr, nullptr, KK, l.Cin, l.Cout, KK, (int64_t)l.Cin * KK, 0);
+      if (tc && l.tc_b.valid) add(w, nullptr, l.wb_hi, l.wb_lo, KK, l.Cout, l.Cin, (int64_t)l.Cin * KK, KK, 1);
+      else if (l.w_bwd) add(w, l.w_bwd, nullptr, nullptr, KK, l.Cout, l.Cin, (int64_t)l.Cin * KK, KK, 0);
+    } else {
+      // ConvTranspose2d IOHW
+      add(w, l.w_fwd, nullptr, nullptr, KK, l.Cin, l.Cout, (int64_t)l.Cout * KK, KK, 0);
+      if (l.w_bwd) add(w, l.w_bwd, nullptr, nullptr, KK, l.Cout, l.Cin, KK, (int64_t)l.Cout * KK, 0);
+    }
+    return IGM_OK;
+  });
+  if (c->final_wbwd)   // dgrad of the final 1x1: [1][k = c][n = K] = W[c][K]
+    add(c->Pp(c->final_conv.pw), c->final_wbwd, nullptr, nullptr, 1, c->cfg.channels, c->final_conv.Cin,
+        c->final_conv.Cin, 1, 0);
+  if (jobs.size() > 1024) IGM_FAIL(c->st, IGM_ERR_INVALID, "too many pack jobs");
+  IGM_CUDA(c->st, cudaMemcpy(c->pack_dev, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
+  c->pack_n = (int)jobs.size();
+  c->pack_total = total;
+  c->pack_engine = c->conv_engine;
   return IGM_OK;
 }
 
@@ -1019,14 +1049,9 @@ int igm_unet_pack_weights(igm_ctx* c, void* stream) {
   if (!c) return IGM_ERR_INVALID;
   if (!c->P) IGM_FAIL(c->st, IGM_ERR_STATE, "bind parameters first");
   IGM_CUDA(c->st, cudaSetDevice(c->device));
+  if (c->pack_engine != c->conv_engine) IGM_TRY(build_pack_jobs(c));
   LaunchCtx lc = c->lc(stream);
-  IGM_TRY(for_each_conv(c, [&](ConvL& l) -> int { return pack_conv(c, lc, l); }));
-  if (c->final_wbwd) {
-    // dgrad of the final 1x1: [1][k = c][n = K] = W[c][K]: identical memory order to W itself
-    IGM_TRY(launch_pack_weight(lc, c->Pp(c->final_conv.pw), c->final_wbwd, 1, c->cfg.channels, c->final_conv.Cin,
-                               c->final_conv.Cin, 1));
-  }
-  return IGM_OK;
+  return launch_pack_jobs(lc, c->pack_dev, c->pack_n, c->pack_total);
 }
 
 static int check_ready(igm_ctx* c, int B) {
@@ -1253,10 +1278,11 @@ int igm_set_conv_engine(igm_ctx* c, int engine) {
   if (engine == 1 && !c->tc_available) {
     IGM_TRY(plan_tc(c));
     if (!c->tc_available) IGM_FAIL(c->st, IGM_ERR_INVALID, "no layer of this network is eligible for the tcgen05 engine");
-    if (c->P) IGM_TRY(igm_unet_pack_weights(c, nullptr));
   }
   if (c->graph_exec && engine != c->conv_engine) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+  const bool changed = engine != c->conv_engine;
   c->conv_engine = engine;
+  if (changed && c->P) IGM_TRY(igm_unet_pack_weights(c, nullptr));   // the other engine reads other layouts
   return IGM_OK;
 }
 int igm_get_conv_engine(const igm_ctx* c) { return c ? c->conv_engine : IGM_ERR_INVALID; }
