@@ -50,6 +50,13 @@ SYMBOLS = {
     "igm_adam_step": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_int, C.c_float, _P]),
     "igm_debug_read_tap": (C.c_int64, [_P, C.c_char_p, _P, C.c_int64, _P]),
+    "igm_vq_workspace_floats": (C.c_int, [C.c_int, C.c_int]),
+    "igm_vq_forward": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P]),
+    "igm_vq_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_float, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "igm_pixelcnn_weight_floats": (C.c_int64, [C.c_int, C.c_int]),
+    "igm_pixelcnn_workspace_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "igm_pixelcnn_run": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, _P]),
     "igm_profile_start": (C.c_int, [_P]),
     "igm_profile_stop": (C.c_int, [_P, C.POINTER(ProfileEntry), C.c_int]),
     "igm_launch_count": (C.c_int64, [_P]),

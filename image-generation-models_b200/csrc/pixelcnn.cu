@@ -1,0 +1,371 @@
+// Incremental PixelCNN engine (reference src/models/pixelcnn.py): one persistent kernel, one CTA
+// per image, walks the H x W raster once.
+//
+// The reference sampler (pixelcnn.py:167-195) re-runs the whole network on the top h+1 rows for each
+// of the H*W pixels (784 forwards, 843 GFLOP/sample on MNIST).  The masked convolutions make the
+// logits at (h, w) depend only on already generated pixels, so the same result is obtained by
+//   * once per row h: the vertical stack of all 12 layers for that row (it only sees rows < h of the
+//     image), plus the v->h link conv1x1_1 of every layer;
+//   * once per pixel: one column of the horizontal stack (11 gated layers) and the 1x1 head,
+// with per-layer feature rows cached in HBM/L2 (~2.1 GFLOP/sample in total).  The same walk in
+// teacher-forced mode (pixels given, nothing drawn) IS PixelCNN.forward (pixelcnn.py:128-154).
+// fp32 CUDA-core arithmetic throughout: sampled pixels must match the fp32 reference decisions.
+#include "common.cuh"
+
+namespace igm {
+namespace {
+
+constexpr int NLAYERS = 11;
+__constant__ int c_dil[NLAYERS] = {1, 2, 1, 4, 1, 2, 1, 4, 1, 2, 1};   // pixelcnn.py:108-122
+constexpr int PPT = 14;       // output positions per thread in the row GEMMs
+constexpr int MAX_W = 64;
+constexpr int MAX_HD = 128;
+
+struct PcnnOffsets {
+  int64_t vs0_w, vs0_b, hs0_w, hs0_b;
+  int64_t vert_w[NLAYERS], vert_b[NLAYERS], v2h_w[NLAYERS], v2h_b[NLAYERS];
+  int64_t horiz_w[NLAYERS], horiz_b[NLAYERS], h2_w[NLAYERS], h2_b[NLAYERS];
+  int64_t out_w, out_b, total;
+};
+
+PcnnOffsets make_offsets(int C, int Hd) {
+  PcnnOffsets o;
+  int64_t p = 0;
+  auto take = [&](int64_t n) { int64_t r = p; p += (n + 3) & ~int64_t(3); return r; };
+  o.vs0_w = take((int64_t)10 * C * Hd); o.vs0_b = take(Hd);
+  o.hs0_w = take((int64_t)2 * C * Hd); o.hs0_b = take(Hd);
+  for (int i = 0; i < NLAYERS; ++i) {
+    o.vert_w[i] = take((int64_t)6 * Hd * 2 * Hd); o.vert_b[i] = take(2 * Hd);
+    o.v2h_w[i] = take((int64_t)2 * Hd * 2 * Hd); o.v2h_b[i] = take(2 * Hd);
+    o.horiz_w[i] = take((int64_t)2 * Hd * 2 * Hd); o.horiz_b[i] = take(2 * Hd);
+    o.h2_w[i] = take((int64_t)Hd * Hd); o.h2_b[i] = take(Hd);
+  }
+  o.out_w = take((int64_t)Hd * 256 * C); o.out_b = take(256 * C);
+  o.total = p;
+  return o;
+}
+
+struct PcnnArgs {
+  const float* Wt;           // packed weights, every matrix [K][N] (N contiguous), see make_offsets
+  PcnnOffsets off;
+  float* img;                // [N, C, H, W] in/out
+  const float* uniforms;     // [H*W][N*C] or null
+  const uint8_t* skip;       // [H*W]: 1 = keep the given pixel (reference :185) or null
+  float* logits;             // [N, 256, C, H, W] or null
+  float* ws;                 // per-image workspace
+  int64_t ws_per_img;
+  uint64_t seed;
+  int N, C, H, W, Hd;
+  int mode;                  // 0 inverse-CDF draw, 1 greedy argmax, 2 teacher forced (no draw)
+  int normalize;             // pixel value k/255 (0) or 2k/255 - 1 (1)
+};
+
+// y[n] = bias[n] + extra[n] + sum_k Wt[k][n] * x[k]   for n < N (N <= 256 per call), all 256 threads
+__device__ __forceinline__ void cta_gemv(const float* __restrict__ Wt, const float* __restrict__ bias,
+                                         const float* __restrict__ extra, const float* x_s, int K, int N,
+                                         float* red_s /*[256]*/, float* y_s) {
+  const int tid = threadIdx.x;
+  int parts = 256 / N;
+  if (parts < 1) parts = 1;
+  const int n = tid % N, part = tid / N;
+  float acc = 0.f;
+  if (part < parts && tid < parts * N) {
+    const int kb = (K * part) / parts, ke = (K * (part + 1)) / parts;
+    const float* wp = Wt + (int64_t)kb * N + n;
+#pragma unroll 8
+    for (int k = kb; k < ke; ++k) {
+      acc = fmaf(__ldg(wp), x_s[k], acc);
+      wp += N;
+    }
+  }
+  red_s[tid] = acc;
+  __syncthreads();
+  if (tid < N) {
+    float s = bias ? __ldg(bias + tid) : 0.f;
+    if (extra) s += extra[tid];
+    for (int q = 0; q < parts; ++q) s += red_s[q * N + tid];
+    y_s[tid] = s;
+  }
+  __syncthreads();
+}
+
+// out[w][n] = bias[n] + sum_{taps} sum_ci Wt[(tap*Kc + ci)][n] * in(tap, w)[ci]  for all w < W, n < N.
+// `rows[t]` points at the smem row (W x Kc, ci contiguous) tap t reads, or null (zero); `shift[t]`
+// is the column offset of tap t.  N divides 256.
+__device__ __forceinline__ void cta_row_gemm(const float* __restrict__ Wt, const float* __restrict__ bias,
+                                             const float* const* rows, const int* shift, int ntaps, int Kc,
+                                             int N, int W, float* out_s /*[W][N]*/) {
+  const int tid = threadIdx.x;
+  const int groups = 256 / N;
+  const int n = tid % N, grp = tid / N;
+  const float b = bias ? __ldg(bias + n) : 0.f;
+  for (int w0 = grp * PPT; w0 < W; w0 += groups * PPT) {
+    float acc[PPT];
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) acc[p] = b;
+    for (int t = 0; t < ntaps; ++t) {
+      const float* row = rows[t];
+      if (!row) continue;
+      const int sh = shift[t];
+      const float* wp = Wt + ((int64_t)t * Kc) * N + n;
+      for (int c4 = 0; c4 < Kc; c4 += 4) {
+        const float w0v = __ldg(wp + (int64_t)(c4 + 0) * N), w1v = __ldg(wp + (int64_t)(c4 + 1) * N);
+        const float w2v = __ldg(wp + (int64_t)(c4 + 2) * N), w3v = __ldg(wp + (int64_t)(c4 + 3) * N);
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+          const int col = w0 + p + sh;
+          if (w0 + p < W && col >= 0 && col < W) {
+            const float4 x = *reinterpret_cast<const float4*>(row + (int64_t)col * Kc + c4);
+            acc[p] = fmaf(w0v, x.x, acc[p]);
+            acc[p] = fmaf(w1v, x.y, acc[p]);
+            acc[p] = fmaf(w2v, x.z, acc[p]);
+            acc[p] = fmaf(w3v, x.w, acc[p]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < PPT; ++p)
+      if (w0 + p < W) out_s[(w0 + p) * N + n] = acc[p];
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t a, uint32_t b) {
+  // Philox4x32-10 keyed by seed, counter (a, b, 0, 0) -> one uniform in [0, 1)
+  uint32_t c0 = a, c1 = b, c2 = 0, c3 = 0, k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return (float)(c0 >> 8) * (1.0f / 16777216.0f);
+}
+
+__global__ void __launch_bounds__(256) pixelcnn_kernel(const PcnnArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int n_img = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int C = a.C, H = a.H, W = a.W, Hd = a.Hd, N2 = 2 * a.Hd;
+  // shared memory carve-up
+  float* in_s = sm;                         // [2][W][Hd]   two input rows of the vertical conv
+  float* vc_s = in_s + 2 * W * Hd;          // [W][2Hd]     vert_conv output of the current layer
+  float* t_s = vc_s + W * N2;               // [W][2Hd]     scratch row (v2h result / gated row)
+  float* x_s = t_s + W * N2;                // [2Hd]        gemv input
+  float* y_s = x_s + N2;                    // [256]        gemv output
+  float* red_s = y_s + 256;                 // [256]
+  float* cur_s = red_s + 256;               // [Hd]         running h-stack column
+  float* lg_s = cur_s + Hd;                 // [256]        logits of one channel
+  __shared__ int s_pick;
+
+  float* ws = a.ws + (int64_t)n_img * a.ws_per_img;
+  float* Vc = ws;                                        // [12][H][W][Hd]   vertical-stack features
+  float* V2H = Vc + (int64_t)12 * H * W * Hd;            // [11][W][2Hd]     conv1x1_1(vert_conv) of row h
+  float* Hs = V2H + (int64_t)NLAYERS * W * N2;           // [12][W][Hd]      horizontal-stack features of row h
+  float* img = a.img + (int64_t)n_img * C * H * W;
+  const float* Wt = a.Wt;
+
+  for (int h = 0; h < H; ++h) {
+    // ================= row pass: vertical stack =================
+    // layer 0: conv_vstack 5x5, rows ky = 0,1 live (image rows h-2, h-1), pad 2   (pixelcnn.py:98-100)
+    for (int i = tid; i < W * Hd; i += 256) {
+      const int w = i / Hd, co = i - w * Hd;
+      float s = __ldg(Wt + a.off.vs0_b + co);
+      for (int ky = 0; ky < 2; ++ky) {
+        const int r = h - 2 + ky;
+        if (r < 0) continue;
+        for (int kx = 0; kx < 5; ++kx) {
+          const int col = w - 2 + kx;
+          if (col < 0 || col >= W) continue;
+          for (int ci = 0; ci < C; ++ci)
+            s = fmaf(__ldg(Wt + a.off.vs0_w + (int64_t)((ky * 5 + kx) * C + ci) * Hd + co),
+                     img[((int64_t)ci * H + r) * W + col], s);
+        }
+      }
+      Vc[(((int64_t)0 * H + h) * W + w) * Hd + co] = s;
+    }
+    __syncthreads();
+    for (int l = 0; l < NLAYERS; ++l) {
+      const int d = c_dil[l];
+      // stage rows h-d and h of the previous layer's vertical features
+      const float* prev = Vc + ((int64_t)l * H) * W * Hd;
+      const bool top_ok = (h - d) >= 0;
+      for (int i = tid; i < W * Hd / 4; i += 256) {
+        reinterpret_cast<float4*>(in_s + W * Hd)[i] = reinterpret_cast<const float4*>(prev + (int64_t)h * W * Hd)[i];
+        if (top_ok) reinterpret_cast<float4*>(in_s)[i] = reinterpret_cast<const float4*>(prev + (int64_t)(h - d) * W * Hd)[i];
+      }
+      __syncthreads();
+      // vert_conv 3x3 dilated, rows ky = 0 (h-d), 1 (h); cols w-d, w, w+d      (pixelcnn.py:51-53)
+      const float* rows[6];
+      int shift[6];
+      for (int ky = 0; ky < 2; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          rows[ky * 3 + kx] = (ky == 0) ? (top_ok ? in_s : nullptr) : (in_s + W * Hd);
+          shift[ky * 3 + kx] = (kx - 1) * d;
+        }
+      cta_row_gemm(Wt + a.off.vert_w[l], Wt + a.off.vert_b[l], rows, shift, 6, Hd, N2, W, vc_s);
+      // gated vertical output: tanh(a) * sigmoid(b)                            (pixelcnn.py:69)
+      float* vout = Vc + (((int64_t)(l + 1) * H + h) * W) * Hd;
+      for (int i = tid; i < W * Hd; i += 256) {
+        const int w = i / Hd, c = i - w * Hd;
+        const float av = vc_s[w * N2 + c], bv = vc_s[w * N2 + Hd + c];
+        vout[i] = tanhf(av) * (1.f / (1.f + expf(-bv)));
+      }
+      // v -> h link: conv1x1_1 on the PRE-gate features                         (pixelcnn.py:74)
+      const float* rows1[1] = {vc_s};
+      const int shift1[1] = {0};
+      cta_row_gemm(Wt + a.off.v2h_w[l], Wt + a.off.v2h_b[l], rows1, shift1, 1, N2, N2, W, t_s);
+      float* v2h = V2H + (int64_t)l * W * N2;
+      for (int i = tid; i < W * N2 / 4; i += 256) reinterpret_cast<float4*>(v2h)[i] = reinterpret_cast<const float4*>(t_s)[i];
+      __syncthreads();
+    }
+
+    // ================= pixel pass: horizontal stack, one column at a time =================
+    for (int w = 0; w < W; ++w) {
+      // layer 0: conv_hstack 1x5, cols kx = 0,1 live (w-2, w-1), pad 2           (pixelcnn.py:101-103)
+      if (tid < Hd) {
+        float s = __ldg(Wt + a.off.hs0_b + tid);
+        for (int kx = 0; kx < 2; ++kx) {
+          const int col = w - 2 + kx;
+          if (col < 0) continue;
+          for (int ci = 0; ci < C; ++ci)
+            s = fmaf(__ldg(Wt + a.off.hs0_w + (int64_t)(kx * C + ci) * Hd + tid), img[((int64_t)ci * H + h) * W + col], s);
+        }
+        cur_s[tid] = s;
+        Hs[((int64_t)0 * W + w) * Hd + tid] = s;
+      }
+      __syncthreads();
+      for (int l = 0; l < NLAYERS; ++l) {
+        const int d = c_dil[l];
+        // horiz_conv 1x3 dilated, cols kx = 0 (w-d), 1 (w)                        (pixelcnn.py:48-50)
+        if (tid < Hd) {
+          x_s[Hd + tid] = cur_s[tid];
+          x_s[tid] = (w - d >= 0) ? Hs[((int64_t)l * W + (w - d)) * Hd + tid] : 0.f;
+        }
+        __syncthreads();
+        cta_gemv(Wt + a.off.horiz_w[l], Wt + a.off.horiz_b[l], V2H + ((int64_t)l * W + w) * N2, x_s, N2, N2, red_s, y_s);
+        // gated horizontal output: tanh(a) * tanh(b)  (sic)                      (pixelcnn.py:77)
+        if (tid < Hd) x_s[tid] = tanhf(y_s[tid]) * tanhf(y_s[Hd + tid]);
+        __syncthreads();
+        // conv1x1_2 + residual                                                    (pixelcnn.py:80)
+        cta_gemv(Wt + a.off.h2_w[l], Wt + a.off.h2_b[l], cur_s, x_s, Hd, Hd, red_s, y_s);
+        if (tid < Hd) {
+          cur_s[tid] = y_s[tid];
+          Hs[((int64_t)(l + 1) * W + w) * Hd + tid] = y_s[tid];
+        }
+        __syncthreads();
+      }
+      // head: conv_out(elu(h_stack))                                              (pixelcnn.py:148)
+      if (tid < Hd) {
+        const float v = cur_s[tid];
+        x_s[tid] = v > 0.f ? v : expm1f(v);
+      }
+      __syncthreads();
+      const bool keep = a.mode == 2 || (a.skip && a.skip[h * W + w]);
+      for (int ch = 0; ch < C; ++ch) {
+        // logits of channel ch: conv_out channel o = cls*C + ch  (reshape at pixelcnn.py:151-153)
+        {
+          float s = __ldg(Wt + a.off.out_b + (int64_t)tid * C + ch);
+          const float* wp = Wt + a.off.out_w + (int64_t)tid * C + ch;
+          for (int k = 0; k < Hd; ++k) s = fmaf(__ldg(wp + (int64_t)k * 256 * C), x_s[k], s);
+          lg_s[tid] = s;
+          if (a.logits) a.logits[((((int64_t)n_img * 256 + tid) * C + ch) * H + h) * W + w] = s;
+        }
+        __syncthreads();
+        if (!keep && tid < 32) {
+          // softmax over 256 classes + draw, one warp; lane owns classes [8*lane, 8*lane+8)
+          float v[8];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { v[j] = lg_s[tid * 8 + j]; mx = fmaxf(mx, v[j]); }
+          mx = warp_max(mx);
+          int pickk;
+          if (a.mode == 1) {
+            // greedy: first index of the maximum
+            int best = 1 << 30;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (v[j] == mx) best = min(best, tid * 8 + j);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+            pickk = best;
+          } else {
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v[j] = expf(v[j] - mx); sum += v[j]; }
+            const float tot = warp_sum(sum);
+            // inclusive scan of lane sums -> exclusive offset of this lane
+            float run = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const float t = __shfl_up_sync(0xffffffffu, run, o);
+              if (tid >= o) run += t;
+            }
+            float cdf = run - sum;
+            float u;
+            if (a.uniforms) u = __ldg(a.uniforms + (int64_t)(h * W + w) * a.N * C + (int64_t)n_img * C + ch);
+            else u = philox_uniform(a.seed, (uint32_t)(h * W + w), (uint32_t)(n_img * C + ch));
+            const float inv = 1.f / tot;
+            int cnt = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              cdf += v[j];
+              cnt += (cdf * inv <= u) ? 1 : 0;   // k = #{j : cdf_j <= u}
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            pickk = min(cnt, 255);
+          }
+          if (tid == 0) s_pick = pickk;
+        }
+        __syncthreads();
+        if (!keep && tid == 0) {
+          float val = (float)s_pick / 255.f;
+          if (a.normalize) val = val * 2.f - 1.f;
+          img[((int64_t)ch * H + h) * W + w] = val;
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
+}  // namespace
+}  // namespace igm
+
+using namespace igm;
+
+extern "C" int64_t igm_pixelcnn_weight_floats(int C, int Hd) { return make_offsets(C, Hd).total; }
+
+extern "C" int64_t igm_pixelcnn_workspace_floats(int N, int C, int H, int W, int Hd) {
+  (void)C;
+  const int64_t per = (int64_t)12 * H * W * Hd + (int64_t)NLAYERS * W * 2 * Hd + (int64_t)12 * W * Hd;
+  return per * N;
+}
+
+// mode 0: inverse-CDF draws (uniforms [H*W][N*C] or Philox(seed)); 1: greedy; 2: teacher forced.
+extern "C" int igm_pixelcnn_run(const float* weights, float* img, const float* uniforms, const uint8_t* skip,
+                                float* logits, float* ws, uint64_t seed, int N, int C, int H, int W, int Hd,
+                                int mode, int normalize, void* stream) {
+  Status& st = global_status();
+  st = Status();
+  if (!weights || !img || !ws) IGM_FAIL(st, IGM_ERR_INVALID, "null tensor");
+  if (Hd != 32 && Hd != 64 && Hd != 128) IGM_FAIL(st, IGM_ERR_INVALID, "hidden_dim must be 32, 64 or 128");
+  if (W < 1 || W > MAX_W || H < 1 || N < 1 || C < 1 || C > 4) IGM_FAIL(st, IGM_ERR_INVALID, "unsupported image shape");
+  if (mode < 0 || mode > 2) IGM_FAIL(st, IGM_ERR_INVALID, "mode must be 0, 1 or 2");
+  PcnnArgs a;
+  a.Wt = weights; a.off = make_offsets(C, Hd);
+  a.img = img; a.uniforms = uniforms; a.skip = skip; a.logits = logits; a.ws = ws;
+  a.ws_per_img = igm_pixelcnn_workspace_floats(1, C, H, W, Hd);
+  a.seed = seed; a.N = N; a.C = C; a.H = H; a.W = W; a.Hd = Hd; a.mode = mode; a.normalize = normalize;
+  const size_t smem = sizeof(float) * ((size_t)2 * W * Hd + (size_t)2 * W * 2 * Hd + 2 * Hd + 256 + 256 + Hd + 256);
+  cudaError_t e = cudaFuncSetAttribute(pixelcnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) IGM_FAIL(st, IGM_ERR_CUDA, cudaGetErrorString(e));
+  pixelcnn_kernel<<<N, 256, smem, (cudaStream_t)stream>>>(a);
+  e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { cudaGetLastError(); IGM_FAIL(st, IGM_ERR_CUDA, cudaGetErrorString(e)); }
+  return IGM_OK;
+}

@@ -135,6 +135,36 @@ int igm_adam_step(igm_ctx* ctx, float* params, const float* grads, float* exp_av
                   float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
                   int step, float grad_scale, void* stream);
 
+/* ---- VQ-VAE quantiser ------------------------------------------------------- */
+/* VectorQuantizer.forward — src/models/vqvae.py:24-43.  z, quant: [N, D, h, w] fp32 NCHW (HW = h*w);
+ * codebook: [K, D]; idx: [N*h*w] int64 = argmin_k ||z - e_k|| with the FIRST index on ties;
+ * losses[0] = vq_loss = mse(z, q), losses[1] = commit_loss = beta * mse(z, q)  (device floats).
+ * ws: igm_vq_workspace_floats(N, HW) floats of scratch.  Context-free; errors via igm_last_error(NULL). */
+int igm_vq_workspace_floats(int N, int HW);
+int igm_vq_forward(const float* z, const float* codebook, int64_t* idx, float* quant, float* losses,
+                   int N, int D, int HW, int K, float beta, float* ws, void* stream);
+/* Autograd of the above: dz = d_commit*beta*2(z-q)/n (may be NULL); d_codebook[idx] +=
+ * d_vq*2(q-z)/n + d_quant (ACCUMULATED; d_quant / d_vq / d_commit may be NULL = zero). */
+int igm_vq_backward(const float* z, const float* codebook, const int64_t* idx, const float* d_quant,
+                    const float* d_vq, const float* d_commit, float beta, float* dz, float* d_codebook,
+                    int N, int D, int HW, int K, void* stream);
+
+/* ---- PixelCNN ---------------------------------------------------------------- */
+/* Incremental raster walk of the gated PixelCNN (src/models/pixelcnn.py:85-195), one CTA per image.
+ *   mode 0: PixelCNN.sample (:167-195) with inverse-CDF draws k = #{j : cdf_j <= u}; u from
+ *           uniforms[H*W][N*C] or, when NULL, Philox4x32-10 keyed by (seed, pixel, image*C+channel);
+ *   mode 1: greedy argmax decode (first index on ties);
+ *   mode 2: teacher forced, nothing drawn: with logits != NULL this is PixelCNN.forward (:128-154).
+ * img [N,C,H,W] in/out (pixels k/255, or 2k/255-1 when normalize); skip[H*W] = 1 keeps a given pixel
+ * (:185); logits [N,256,C,H,W] optional; weights = the live taps of every conv as [K][N] matrices in
+ * the order documented in csrc/pixelcnn.cu (igm_pixelcnn_weight_floats elements);
+ * ws = igm_pixelcnn_workspace_floats(N,C,H,W,Hd) floats.  Context-free; errors via igm_last_error(NULL). */
+int64_t igm_pixelcnn_weight_floats(int C, int Hd);
+int64_t igm_pixelcnn_workspace_floats(int N, int C, int H, int W, int Hd);
+int igm_pixelcnn_run(const float* weights, float* img, const float* uniforms, const uint8_t* skip,
+                     float* logits, float* ws, uint64_t seed, int N, int C, int H, int W, int Hd,
+                     int mode, int normalize, void* stream);
+
 /* ---- introspection (tests / profiling) ------------------------------------ */
 /* Copies the named intermediate of the last forward (same names as
  * oracle/ddpm_oracle.py taps, e.g. "downs.0.0.block1.conv") to dst as NCHW fp32.
