@@ -57,7 +57,8 @@ __device__ __forceinline__ void outer_accumulate(const float* __restrict__ base,
 
 __global__ void __launch_bounds__(256) linattn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out,
                                                           float* __restrict__ ctx, float* __restrict__ kstat,
-                                                          int N) {
+                                                          int N, __nv_bfloat16* __restrict__ out_hi,
+                                                          __nv_bfloat16* __restrict__ out_lo) {
   __shared__ float Xs[32][D + 1];
   __shared__ __align__(16) float Ys[32][D];
   __shared__ float ctxs[D][D + 1];
@@ -125,7 +126,15 @@ __global__ void __launch_bounds__(256) linattn_fwd_kernel(const float* __restric
       float a = 0.f;
 #pragma unroll
       for (int dd = 0; dd < D; ++dd) a = fmaf(ctxs[dd][e], Xs[nn][dd], a);
-      if (n < N) out[((int64_t)b * N + n) * HD + h * D + e] = a;
+      if (n < N) {
+        const int64_t o = ((int64_t)b * N + n) * HD + h * D + e;
+        out[o] = a;
+        if (out_hi) {
+          const __nv_bfloat16 hv = __float2bfloat16_rn(a);
+          out_hi[o] = hv;
+          out_lo[o] = __float2bfloat16_rn(a - __bfloat162float(hv));
+        }
+      }
     }
     __syncthreads();
   }
@@ -243,9 +252,9 @@ __global__ void __launch_bounds__(256) linattn_bwd_kernel(const float* __restric
 }  // namespace
 
 int launch_linattn_forward(const LaunchCtx& lc, const float* qkv, float* out, float* ctx, float* kstat,
-                           int B, int n) {
+                           int B, int n, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
   ProfScope ps_(lc, K_ATTN, 4.0 * B * kHeads * (double)n * D * D, 4.0 * B * (double)n * (QKV + HD));
-  linattn_fwd_kernel<<<B * kHeads, 256, 0, lc.stream>>>(qkv, out, ctx, kstat, n);
+  linattn_fwd_kernel<<<B * kHeads, 256, 0, lc.stream>>>(qkv, out, ctx, kstat, n, out_hi, out_lo);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }

@@ -1,5 +1,6 @@
 // Shared declarations for libigm_b200 (sm_100a only).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -183,15 +184,18 @@ int launch_pack_jobs(const LaunchCtx& lc, const PackJob* d_jobs, int n_jobs, int
 int launch_gn_partial(const LaunchCtx& lc, const float* y, int B, int HW, int C, float* part);
 // Finalise statistics (stats[b][g] = mean, rstd), then out = mish(gn(y)) [+ temb[b, c]] [+ res[m, c]].
 // temb has row stride temb_stride.
+// out_hi / out_lo (optional): bf16 hi/lo copy of `out` for the tensor-core conv that consumes it.
 int launch_gn_apply(const LaunchCtx& lc, const float* y, const float* part, const float* gamma,
                     const float* beta, const float* temb, int temb_stride, const float* res,
-                    float* out, float* stats, int B, int HW, int C);
+                    float* out, float* stats, int B, int HW, int C, __nv_bfloat16* out_hi = nullptr,
+                    __nv_bfloat16* out_lo = nullptr);
 // Backward of the above.  d_out: grad of `out`.  Produces dy (grad of conv output y),
 // accumulates dgamma/dbeta into the grad arena, and (optionally) dtemb[b, c] (+= over pixels).
 struct GnBwdArgs {
   const float* d_out; const float* y; const float* stats; const float* gamma; const float* beta;
   float* dy; float* dgamma; float* dbeta; float* dtemb; int dtemb_stride;
   float* dbias;       // optional: += column sums of dy (gradient of the bias of the conv feeding this norm)
+  __nv_bfloat16* dy_hi; __nv_bfloat16* dy_lo;   // optional bf16 hi/lo copy of dy (tensor-core wgrad / dgrad operand)
   float* ws_group;    // [B][chunks][G][2]
   float* ws_chan;     // [B][chunks][C][3]
   int B, HW, C;
@@ -200,7 +204,7 @@ int launch_gn_backward(const LaunchCtx& lc, const GnBwdArgs& a);
 
 // Channel LayerNorm of reference ddpm.py:85-95 (eps added to std).  x,out: [M, C]
 int launch_ln_forward(const LaunchCtx& lc, const float* x, const float* g, const float* b, float* out,
-                      int64_t M, int C);
+                      int64_t M, int C, __nv_bfloat16* out_hi = nullptr, __nv_bfloat16* out_lo = nullptr);
 // dx = d_res + LN'(d_out)  (the Residual branch add is fused); dg/db accumulated via ws partials.
 int launch_ln_backward(const LaunchCtx& lc, const float* d_out, const float* x, const float* g,
                        const float* d_res, float* dx, float* dg, float* db, float* ws, int64_t M, int C);
@@ -212,7 +216,7 @@ int ln_backward_parts(int64_t M);   // CTAs (= partial rows of ws [parts][2][C])
 // ctx: [B, heads, 32, 32], kstat: [B, heads, 32, 2] (max, sum of exp)
 // ---------------------------------------------------------------------------
 int launch_linattn_forward(const LaunchCtx& lc, const float* qkv, float* out, float* ctx, float* kstat,
-                           int B, int n);
+                           int B, int n, __nv_bfloat16* out_hi = nullptr, __nv_bfloat16* out_lo = nullptr);
 int launch_linattn_backward(const LaunchCtx& lc, const float* qkv, const float* ctx, const float* kstat,
                             const float* d_out, float* d_qkv, int B, int n);
 
@@ -289,6 +293,19 @@ __device__ __forceinline__ float mish_grad_f(float x) {
   float th = tanhf(sp);
   float sg = x > 20.f ? 1.f : 1.f / (1.f + expf(-x));
   return th + x * (1.f - th * th) * sg;
+}
+// bf16 hi/lo staging of four consecutive fp32 values (operands of the tcgen05 bf16x3 engine)
+__device__ __forceinline__ void store_split4(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                             int64_t off, const float4& o) {
+  __align__(8) __nv_bfloat16 h[4], l[4];
+  const float x[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = __float2bfloat16_rn(x[j]);
+    l[j] = __float2bfloat16_rn(x[j] - __bfloat162float(h[j]));
+  }
+  *reinterpret_cast<uint2*>(hi + off) = *reinterpret_cast<const uint2*>(h);
+  *reinterpret_cast<uint2*>(lo + off) = *reinterpret_cast<const uint2*>(l);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

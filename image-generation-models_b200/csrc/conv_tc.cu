@@ -32,7 +32,7 @@ constexpr int A_TILE_BYTES = BM * KC * 2;   // 16 KiB
 using namespace tc;
 
 struct TcArgs {
-  int B, H, W, K, N, N0;
+  int B, H, W, K, K0, N, N0;
   int KH, KW, pad;
   int BH, BW, BB;
   int tiles_m, tiles_n, tiles_per_img;
@@ -40,6 +40,7 @@ struct TcArgs {
   const float* bias;
   float* out0; float* out1;
   const float* add0; const float* add1;
+  __nv_bfloat16* hi0; __nv_bfloat16* lo0;
 };
 
 template <int BN>
@@ -54,6 +55,7 @@ struct Cfg {
 template <int BN>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant__ CUtensorMap ta_lo,
+               const __grid_constant__ CUtensorMap ta1_hi, const __grid_constant__ CUtensorMap ta1_lo,
                const __grid_constant__ CUtensorMap tb_hi, const __grid_constant__ CUtensorMap tb_lo, const TcArgs p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -90,6 +92,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
   if (warp == 0) {
     if (lane == 0) {
       prefetch_tmap(&ta_hi); prefetch_tmap(&ta_lo); prefetch_tmap(&tb_hi); prefetch_tmap(&tb_lo);
+      prefetch_tmap(&ta1_hi); prefetch_tmap(&ta1_lo);
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -103,8 +106,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* st = smem + stage * C::STAGE_BYTES;
             mbar_expect_tx(&full[stage], (uint32_t)p.stage_tx_bytes);
-            tma_load_4d(st, &ta_hi, &full[stage], kc * KC, kx - p.pad, y0 + ky - p.pad, b0);
-            tma_load_4d(st + A_TILE_BYTES, &ta_lo, &full[stage], kc * KC, kx - p.pad, y0 + ky - p.pad, b0);
+            const int ch = kc * KC;
+            if (ch < p.K0) {
+              tma_load_4d(st, &ta_hi, &full[stage], ch, kx - p.pad, y0 + ky - p.pad, b0);
+              tma_load_4d(st + A_TILE_BYTES, &ta_lo, &full[stage], ch, kx - p.pad, y0 + ky - p.pad, b0);
+            } else {   // second tensor of a channel concat
+              tma_load_4d(st, &ta1_hi, &full[stage], ch - p.K0, kx - p.pad, y0 + ky - p.pad, b0);
+              tma_load_4d(st + A_TILE_BYTES, &ta1_lo, &full[stage], ch - p.K0, kx - p.pad, y0 + ky - p.pad, b0);
+            }
             tma_load_2d(st + 2 * A_TILE_BYTES, &tb_hi, &full[stage], tap * p.K + kc * KC, tn * BN);
             tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &tb_lo, &full[stage], tap * p.K + kc * KC, tn * BN);
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -200,6 +209,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          if (p.hi0 && n < p.N0) {
+            // bf16 hi/lo copy of the output row segment: the next tensor-core conv reads it directly
+            __nv_bfloat16* oh = p.hi0 + opix * p.N0 + n;
+            __nv_bfloat16* ol = p.lo0 + opix * p.N0 + n;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                h[q] = __float2bfloat16_rn(v[j + q]);
+                l[q] = __float2bfloat16_rn(v[j + q] - __bfloat162float(h[q]));
+              }
+              *reinterpret_cast<uint4*>(oh + j) = *reinterpret_cast<const uint4*>(h);
+              *reinterpret_cast<uint4*>(ol + j) = *reinterpret_cast<const uint4*>(l);
+            }
+          }
         }
       }
       tc_fence_before();
@@ -309,27 +334,34 @@ bool tc_eligible(int K, int N, int H, int W, int KH) {
 }
 
 int tc_plan(Status& st, TcConv& t, int K, int N, int H, int W, int Bmax, int KH, int pad, __nv_bfloat16* a_hi,
-            __nv_bfloat16* a_lo, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo) {
+            __nv_bfloat16* a_lo, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, int K0, __nv_bfloat16* a1_hi,
+            __nv_bfloat16* a1_lo) {
   t.valid = false;
   if (!tc_eligible(K, N, H, W, KH)) IGM_FAIL(st, IGM_ERR_INVALID, "shape not eligible for the tcgen05 engine");
+  if (K0 <= 0 || !a1_hi) K0 = K;
+  if (K0 % KC != 0 || (K - K0) % KC != 0) IGM_FAIL(st, IGM_ERR_INVALID, "concat split must be a multiple of 64 channels");
   auto enc = get_encode_fn();
   if (!enc) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  t.K = K; t.N = N; t.KH = t.KW = KH; t.pad = pad; t.H = H; t.W = W; t.Bmax = Bmax;
+  t.K = K; t.K0 = K0; t.N = N; t.KH = t.KW = KH; t.pad = pad; t.H = H; t.W = W; t.Bmax = Bmax;
   t.w_hi = w_hi; t.w_lo = w_lo;
   t.BW = W;
   if (H * W <= BM) { t.BH = H; t.BB = BM / (H * W); }
   else { t.BH = BM / W; t.BB = 1; }
   if (t.BB > Bmax) t.BB = Bmax;
   t.BN = (N % 128 == 0) ? 128 : 64;
-  // activations: dims innermost-first (C, W, H, B)
-  for (int which = 0; which < 2; ++which) {
-    cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Bmax};
-    cuuint64_t strides[3] = {(cuuint64_t)K * 2, (cuuint64_t)W * K * 2, (cuuint64_t)H * W * K * 2};
+  // activations: dims innermost-first (C, W, H, B); one descriptor pair per source tensor
+  struct { CUtensorMap* m; void* ptr; int C; } amaps[4] = {
+      {&t.a_hi, a_hi, K0}, {&t.a_lo, a_lo, K0},
+      {&t.a1_hi, K0 < K ? (void*)a1_hi : (void*)a_hi, K0 < K ? K - K0 : K0},
+      {&t.a1_lo, K0 < K ? (void*)a1_lo : (void*)a_lo, K0 < K ? K - K0 : K0}};
+  for (auto& m : amaps) {
+    cuuint64_t dims[4] = {(cuuint64_t)m.C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Bmax};
+    cuuint64_t strides[3] = {(cuuint64_t)m.C * 2, (cuuint64_t)W * m.C * 2, (cuuint64_t)H * W * m.C * 2};
     cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)t.BW, (cuuint32_t)t.BH, (cuuint32_t)t.BB};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(which ? &t.a_lo : &t.a_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, which ? (void*)a_lo : (void*)a_hi,
-                     dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(m.m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, m.ptr, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled (activations) failed");
   }
   // weights: [N rows][taps*K cols], K-major
@@ -357,7 +389,7 @@ static int launch_tc_impl(const LaunchCtx& lc, const TcConv& t, const TcArgs& a,
     attr_done = true;
   }
   int grid = num_tiles < 148 ? num_tiles : 148;
-  conv_tc_kernel<BN><<<grid, 192, C::SMEM_BYTES, lc.stream>>>(t.a_hi, t.a_lo, t.b_hi, t.b_lo, a);
+  conv_tc_kernel<BN><<<grid, 192, C::SMEM_BYTES, lc.stream>>>(t.a_hi, t.a_lo, t.a1_hi, t.a1_lo, t.b_hi, t.b_lo, a);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }
@@ -368,7 +400,7 @@ int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r) {
   if (r.N0 <= 0 || r.N0 > t.N || r.N0 % 32 != 0 || (r.N0 < t.N && !r.out1))
     IGM_FAIL(*lc.st, IGM_ERR_INVALID, "conv_tc: bad output split");
   TcArgs a;
-  a.B = r.B; a.H = t.H; a.W = t.W; a.K = t.K; a.N = t.N; a.N0 = r.N0;
+  a.B = r.B; a.H = t.H; a.W = t.W; a.K = t.K; a.K0 = t.K0; a.N = t.N; a.N0 = r.N0;
   a.KH = t.KH; a.KW = t.KW; a.pad = t.pad;
   a.BH = t.BH; a.BW = t.BW; a.BB = t.BB;
   a.tiles_per_img = (t.BB > 1) ? 1 : cdiv(t.H, t.BH);
@@ -376,6 +408,7 @@ int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r) {
   a.tiles_n = t.N / t.BN;
   a.stage_tx_bytes = 2 * (t.BB * t.BH * t.BW * KC * 2) + 2 * (t.BN * KC * 2);
   a.bias = r.bias; a.out0 = r.out0; a.out1 = r.out1; a.add0 = r.add0; a.add1 = r.add1;
+  a.hi0 = r.hi0; a.lo0 = r.lo0;
   const double flops = 2.0 * r.B * t.H * t.W * (double)t.N * t.K * t.KH * t.KW;
   const double bytes = 4.0 * ((double)r.B * t.H * t.W * (t.K + t.N * (r.add0 ? 2 : 1)) + (double)t.KH * t.KW * t.K * t.N);
   ProfScope ps_(lc, r.kclass, flops, bytes);

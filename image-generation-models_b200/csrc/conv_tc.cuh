@@ -13,7 +13,10 @@ namespace igm {
 // fp32 accumulation in TMEM) so the result is fp32-accurate to ~2^-17 relative.
 struct TcConv {
   bool valid = false;
-  alignas(64) CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  // activations may come from two tensors concatenated along channels (skip connections):
+  // channels [0, K0) from source 0, [K0, K) from source 1 (a1_* = a0_* when there is one source)
+  alignas(64) CUtensorMap a_hi, a_lo, a1_hi, a1_lo, b_hi, b_lo;
+  int K0 = 0;
   __nv_bfloat16* w_hi = nullptr;   // [N][taps*K]
   __nv_bfloat16* w_lo = nullptr;
   int K = 0, N = 0, KH = 1, KW = 1, pad = 0;
@@ -24,15 +27,19 @@ struct TcConv {
 // Can this (stride-1, non-dilated) conv run on the tensor-core engine?
 bool tc_eligible(int K, int N, int H, int W, int KH);
 
-// Fills `t` (tile shape + the four TMA descriptors).  a_hi/a_lo: bf16 [Bmax, H, W, K] scratch.
+// Fills `t` (tile shape + the TMA descriptors).  Source 0: bf16 hi/lo [Bmax, H, W, K0]; optional
+// source 1: [Bmax, H, W, K - K0] (pass K0 = K and null pointers for a single source).
 int tc_plan(Status& st, TcConv& t, int K, int N, int H, int W, int Bmax, int KH, int pad,
-            __nv_bfloat16* a_hi, __nv_bfloat16* a_lo, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo);
+            __nv_bfloat16* a_hi, __nv_bfloat16* a_lo, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo,
+            int K0 = 0, __nv_bfloat16* a1_hi = nullptr, __nv_bfloat16* a1_lo = nullptr);
 
 struct TcRun {
   int B = 0;
   const float* bias = nullptr;
   float* out0 = nullptr; float* out1 = nullptr; int N0 = 0;
   const float* add0 = nullptr; const float* add1 = nullptr;
+  __nv_bfloat16* hi0 = nullptr;   // optional: also emit out0 as bf16 hi/lo (operand staging for the
+  __nv_bfloat16* lo0 = nullptr;   // next tensor-core conv), same [M, N0] layout
   int kclass = K_CONV_FPROP;
 };
 int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r);
@@ -41,13 +48,15 @@ int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r);
 // reduction axis, fetched as 64-pixel TMA boxes of the bf16 hi/lo copies of dY and X.
 struct TcWgrad {
   bool valid = false;
-  alignas(64) CUtensorMap dy_hi, dy_lo, x_hi, x_lo;
+  alignas(64) CUtensorMap dy_hi, dy_lo, x_hi, x_lo, x1_hi, x1_lo;   // X may be a 2-tensor channel concat
+  int C0 = 0;
   int Cin = 0, Cout = 0, KH = 1, KW = 1, pad = 0, H = 0, W = 0, Bmax = 0;
   int BW = 0, BH = 0, BB = 0, rows = 0, BN = 0;
 };
 bool tcw_eligible(int Cin, int Cout, int H, int W, int KH);
 int tcw_plan(Status& st, TcWgrad& t, int Cin, int Cout, int H, int W, int Bmax, int KH, int pad,
-             __nv_bfloat16* dy_hi, __nv_bfloat16* dy_lo, __nv_bfloat16* x_hi, __nv_bfloat16* x_lo);
+             __nv_bfloat16* dy_hi, __nv_bfloat16* dy_lo, __nv_bfloat16* x_hi, __nv_bfloat16* x_lo,
+             int C0 = 0, __nv_bfloat16* x1_hi = nullptr, __nv_bfloat16* x1_lo = nullptr);
 bool tcw_batch_ok(const TcWgrad& t, int B);
 // grad (PyTorch OIHW fp32) += dW; dY / X must already be staged as bf16 hi/lo in the planned buffers
 int launch_wgrad_tc(const LaunchCtx& lc, const TcWgrad& t, int B, float* grad, int variant = 0);

@@ -85,7 +85,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
                                                        const float* __restrict__ beta,
                                                        const float* __restrict__ temb, int temb_stride,
                                                        const float* __restrict__ res, float* __restrict__ out,
-                                                       float* __restrict__ stats, int HW, int C, int nchunks) {
+                                                       float* __restrict__ stats, int HW, int C, int nchunks,
+                                                       __nv_bfloat16* __restrict__ out_hi,
+                                                       __nv_bfloat16* __restrict__ out_lo) {
   __shared__ float s_mean[kGroups], s_rstd[kGroups];
   const GnLayout ly(C);
   const int b = blockIdx.x / nchunks, chunk = blockIdx.x % nchunks;
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
       o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
     }
     *reinterpret_cast<float4*>(out + off) = o;
+    if (out_hi) store_split4(out_hi, out_lo, off, o);
   }
 }
 
@@ -236,6 +239,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a, in
       dbs[j] += o[j];
     }
     *reinterpret_cast<float4*>(a.dy + off) = make_float4(o[0], o[1], o[2], o[3]);
+    if (a.dy_hi) store_split4(a.dy_hi, a.dy_lo, off, make_float4(o[0], o[1], o[2], o[3]));
   }
   if (a.dbias) {
     // conv-bias gradient = column sums of dy: fold the pixel slots, then one atomic per channel per CTA
@@ -293,7 +297,8 @@ constexpr int LN_MAX_V = 8;   // C <= 1024
 
 __global__ void __launch_bounds__(256) ln_forward_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                          const float* __restrict__ bta, float* __restrict__ out,
-                                                         int64_t M, int C) {
+                                                         int64_t M, int C, __nv_bfloat16* __restrict__ out_hi,
+                                                         __nv_bfloat16* __restrict__ out_lo) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -333,6 +338,7 @@ __global__ void __launch_bounds__(256) ln_forward_kernel(const float* __restrict
         o.z = v[j].z * inv * gg.z + bb.z;
         o.w = v[j].w * inv * gg.w + bb.w;
         *reinterpret_cast<float4*>(out + m * C + c4 * 4) = o;
+        if (out_hi) store_split4(out_hi, out_lo, m * C + c4 * 4, o);
       }
     }
   }
@@ -481,12 +487,12 @@ int launch_gn_partial(const LaunchCtx& lc, const float* y, int B, int HW, int C,
 
 int launch_gn_apply(const LaunchCtx& lc, const float* y, const float* part, const float* gamma,
                     const float* beta, const float* temb, int temb_stride, const float* res, float* out,
-                    float* stats, int B, int HW, int C) {
+                    float* stats, int B, int HW, int C, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
   IGM_TRY(check_gn_shape(lc, C));
   const int nchunks = cdiv(HW, kGnChunk);
   ProfScope ps_(lc, K_NORM, 30.0 * B * HW * C, 4.0 * B * HW * C * (res ? 3 : 2));
   gn_apply_kernel<<<B * nchunks, 256, 0, lc.stream>>>(y, part, gamma, beta, temb, temb_stride, res, out,
-                                                      stats, HW, C, nchunks);
+                                                      stats, HW, C, nchunks, out_hi, out_lo);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }
@@ -512,10 +518,10 @@ static int ln_grid(int64_t M) {
 }
 
 int launch_ln_forward(const LaunchCtx& lc, const float* x, const float* g, const float* b, float* out,
-                      int64_t M, int C) {
+                      int64_t M, int C, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
   if (C % 4 != 0 || C > 1024) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "LayerNorm: C must be a multiple of 4, <= 1024");
   ProfScope ps_(lc, K_NORM, 8.0 * M * C, 8.0 * M * C);
-  ln_forward_kernel<<<ln_grid(M), 256, 0, lc.stream>>>(x, g, b, out, M, C);
+  ln_forward_kernel<<<ln_grid(M), 256, 0, lc.stream>>>(x, g, b, out, M, C, out_hi, out_lo);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }

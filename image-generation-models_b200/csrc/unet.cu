@@ -69,6 +69,8 @@ struct ParamInfo {
 struct Act {
   float* v = nullptr;
   float* g = nullptr;
+  __nv_bfloat16* hi = nullptr;   // bf16 hi/lo staging of v, written by the producing kernel when the
+  __nv_bfloat16* lo = nullptr;   // tcgen05 engine is active (operand of the convs that consume v)
   int C = 0, H = 0, W = 0;
 };
 
@@ -85,6 +87,8 @@ struct ConvL {
   TcConv tc_f, tc_b;
   TcWgrad tc_w;
   bool bias_in_norm = false;   // bias gradient is produced by the GroupNorm backward that follows this conv
+  const Act* src0 = nullptr;   // input tensor(s) of the layer (wired once the plan is final)
+  const Act* src1 = nullptr;
 };
 
 struct BlockL {
@@ -103,6 +107,8 @@ struct ResnetL {
   ConvL res;
   Act h1, out;
   float* r = nullptr;   // res_conv output
+  const Act* in0 = nullptr;   // wired inputs (in1: skip tensor concatenated along channels)
+  const Act* in1 = nullptr;
 };
 
 struct AttnL {
@@ -110,9 +116,10 @@ struct AttnL {
   int C = 0, H = 0, W = 0;
   ConvL qkv, outc;
   int ln_g = -1, ln_b = -1;
-  float* ln = nullptr;     // [M, C]
+  Act ln;                  // [M, C]   pre-norm output (input of to_qkv)
   float* qkv_t = nullptr;  // [M, 384]
-  float* att = nullptr;    // [M, 128]
+  Act att;                 // [M, 128] attention output (input of to_out)
+  const Act* in = nullptr;
   float* ctx = nullptr;    // [B, 4, 32, 32]
   float* kstat = nullptr;  // [B, 4, 32, 2]
   Act out;
@@ -124,6 +131,7 @@ struct ResampleL {
   int Hin = 0, Win = 0;
   Act out;
   bool present = false;
+  const Act* in = nullptr;
 };
 
 struct Stage {
@@ -185,7 +193,6 @@ struct igm_ctx {
   float* gn_part = nullptr;
   float *ws_group = nullptr, *ws_chan = nullptr, *ws_ln = nullptr;
   float *scrA = nullptr, *scrB = nullptr, *scrC = nullptr;
-  __nv_bfloat16 *split_hi = nullptr, *split_lo = nullptr;   // bf16x2 staging of a conv's input (tcgen05 engine)
   __nv_bfloat16 *dy_hi = nullptr, *dy_lo = nullptr;         // bf16x2 staging of an output gradient
   bool tc_available = false;
   PackJob* pack_dev = nullptr;        // device job table of igm_unet_pack_weights
@@ -204,6 +211,7 @@ struct igm_ctx {
   std::map<std::string, Act> taps;
 
   std::vector<float*> skip_g;   // gradient of the skip tensor of down stage i (i >= 1), training only
+  const Act* final_in = nullptr;   // input of final_conv.0
 
   int last_B = 0;
   bool fwd_valid = false, loss_valid = false;
@@ -258,7 +266,7 @@ struct PlanBuilder {
   Arena ar;
   bool training;
   int B;
-  int64_t maxMC = 0, maxM = 0, maxGnWs = 0, maxSplit = 0, maxDy = 0;
+  int64_t maxMC = 0, maxM = 0, maxGnWs = 0, maxDy = 0;
 
   PlanBuilder(igm_ctx& ctx, float* base) : c(ctx), pb{ctx.params} {
     ar.base = base;
@@ -268,11 +276,15 @@ struct PlanBuilder {
 
   int64_t M(int H, int W) const { return (int64_t)B * H * W; }
 
-  Act act(int C, int H, int W, bool grad) {
+  Act act(int C, int H, int W, bool grad, bool staged = true) {
     Act a;
     a.C = C; a.H = H; a.W = W;
     a.v = ar.alloc(M(H, W) * C);
     if (grad && training) a.g = ar.alloc(M(H, W) * C);
+    if (staged && C % 64 == 0) {   // may feed a tensor-core conv: room for its bf16 hi/lo copy
+      a.hi = reinterpret_cast<__nv_bfloat16*>(ar.alloc((M(H, W) * C + 1) / 2));
+      a.lo = reinterpret_cast<__nv_bfloat16*>(ar.alloc((M(H, W) * C + 1) / 2));
+    }
     return a;
   }
   void tap(const std::string& n, float* v, int C, int H, int W) {
@@ -298,7 +310,6 @@ struct PlanBuilder {
       if (l.tc_f_ok) {
         l.wf_hi = reinterpret_cast<__nv_bfloat16*>(ar.alloc((nw + 1) / 2));
         l.wf_lo = reinterpret_cast<__nv_bfloat16*>(ar.alloc((nw + 1) / 2));
-        maxSplit = std::max(maxSplit, M(H, W) * Cin);
       }
       if (l.tc_b_ok) {
         l.wb_hi = reinterpret_cast<__nv_bfloat16*>(ar.alloc((nw + 1) / 2));
@@ -306,10 +317,7 @@ struct PlanBuilder {
         maxDy = std::max(maxDy, M(H, W) * Cout);
       }
       l.tc_w_ok = training && tcw_eligible(Cin, Cout, H, W, K);
-      if (l.tc_w_ok) {
-        maxSplit = std::max(maxSplit, M(H, W) * Cin);
-        maxDy = std::max(maxDy, M(H, W) * Cout);
-      }
+      if (l.tc_w_ok) maxDy = std::max(maxDy, M(H, W) * Cout);
     }
     return l;
   }
@@ -324,6 +332,7 @@ struct PlanBuilder {
     b.stats = ar.alloc((int64_t)B * kGroups * 2);
     tap(name + ".conv", b.raw, Cout, H, W);
     track(H, W, Cout);
+    if (training) maxDy = std::max(maxDy, M(H, W) * Cout);   // the GroupNorm backward stages dy for every block
     return b;
   }
   void track(int H, int W, int C) {
@@ -365,13 +374,13 @@ struct PlanBuilder {
     a.outc = conv(name + ".fn.fn.to_out", hd, C, 1, true, false, H, W);
     a.ln_g = pb.add(name + ".fn.norm.g", {1, C, 1, 1});
     a.ln_b = pb.add(name + ".fn.norm.b", {1, C, 1, 1});
-    a.ln = ar.alloc(M(H, W) * C);
+    a.ln = act(C, H, W, false);
     a.qkv_t = ar.alloc(M(H, W) * 3 * hd);
-    a.att = ar.alloc(M(H, W) * hd);
+    a.att = act(hd, H, W, false);
     a.ctx = ar.alloc((int64_t)B * kHeads * kDimHead * kDimHead);
     a.kstat = ar.alloc((int64_t)B * kHeads * kDimHead * 2);
     a.out = act(C, H, W, true);
-    tap(name + ".ln", a.ln, C, H, W);
+    tap(name + ".ln", a.ln.v, C, H, W);
     tap(name + ".out", a.out.v, C, H, W);
     track(H, W, C);
     maxMC = std::max(maxMC, M(H, W) * 3 * hd);
@@ -396,7 +405,7 @@ struct PlanBuilder {
     c.tm_b2 = pb.add("time_mlp.3.bias", {d});
 
     int H = cfg.height, W = cfg.width;
-    c.x_in = act(cfg.channels, H, W, false);
+    c.x_in = act(cfg.channels, H, W, false, false);
     c.downs.assign(nres, Stage());
     std::vector<int> hs(nres), ws(nres);
     for (int i = 0; i < nres; ++i) {
@@ -488,10 +497,6 @@ struct PlanBuilder {
       c.noise_copy = ar.alloc((int64_t)B * cfg.channels * HW0);
       c.d_pred = ar.alloc((int64_t)B * cfg.channels * HW0);
     }
-    if (maxSplit > 0) {
-      c.split_hi = reinterpret_cast<__nv_bfloat16*>(ar.alloc((maxSplit + 1) / 2));
-      c.split_lo = reinterpret_cast<__nv_bfloat16*>(ar.alloc((maxSplit + 1) / 2));
-    }
     if (maxDy > 0) {
       c.dy_hi = reinterpret_cast<__nv_bfloat16*>(ar.alloc((maxDy + 1) / 2));
       c.dy_lo = reinterpret_cast<__nv_bfloat16*>(ar.alloc((maxDy + 1) / 2));
@@ -500,7 +505,7 @@ struct PlanBuilder {
 };
 
 // ---------------------------------------------------------------------------
-// conv helpers
+// launch sequences
 // ---------------------------------------------------------------------------
 struct Runner {
   igm_ctx& c;
@@ -508,22 +513,32 @@ struct Runner {
   int B;
 
   int64_t M(int H, int W) const { return (int64_t)B * H * W; }
+  bool tc_on() const { return c.conv_engine == 1; }
+  bool use_tc(const TcConv& t) const { return tc_on() && t.valid; }
+  // bf16 staging pointers of an activation: only handed to producers while the tcgen05 engine is on
+  __nv_bfloat16* hi(const Act& a) const { return tc_on() ? a.hi : nullptr; }
+  __nv_bfloat16* lo(const Act& a) const { return tc_on() ? a.lo : nullptr; }
+  // producers that cannot emit the staging copy themselves (SIMT convs) are followed by a split pass
+  int stage_act(const Act& a) {
+    if (!tc_on() || !a.hi) return IGM_OK;
+    return launch_split_bf16(lc, a.v, M(a.H, a.W), a.C, a.hi, a.lo, a.C, 0);
+  }
 
-  // forward of a Conv2d (stride s, pad p) or ConvTranspose2d layer
-  bool use_tc(const TcConv& t) const { return c.conv_engine == 1 && t.valid; }
-
-  int conv_fwd(const ConvL& l, const float* in0, int C0, const float* in1, int C1, int IH, int IW, int OH,
-               int OW, int stride, int pad, float* out, const float* add) {
+  // forward of a layer conv reading its wired sources.  `out_act`: when the output is an activation
+  // that later feeds tensor-core convs, its bf16 hi/lo copy is produced here as well.
+  int conv_fwd(const ConvL& l, int IH, int IW, int OH, int OW, int stride, int pad, float* out, const float* add,
+               const Act* out_act = nullptr) {
+    const Act* s0 = l.src0;
+    const Act* s1 = l.src1;
     if (stride == 1 && use_tc(l.tc_f)) {
-      const int Ct = C0 + C1;
-      IGM_TRY(launch_split_bf16(lc, in0, M(IH, IW), C0, c.split_hi, c.split_lo, Ct, 0));
-      if (in1 && C1 > 0) IGM_TRY(launch_split_bf16(lc, in1, M(IH, IW), C1, c.split_hi, c.split_lo, Ct, C0));
       TcRun r;
       r.B = B; r.bias = c.Pp(l.pb); r.out0 = out; r.N0 = l.Cout; r.add0 = add; r.kclass = K_CONV_FPROP;
+      if (out_act) { r.hi0 = hi(*out_act); r.lo0 = lo(*out_act); }
       return launch_conv_tc(lc, l.tc_f, r);
     }
     ConvArgs a;
-    a.in0 = in0; a.in1 = in1; a.C0 = C0; a.C1 = C1;
+    a.in0 = s0->v; a.C0 = s0->C;
+    a.in1 = s1 ? s1->v : nullptr; a.C1 = s1 ? s1->C : 0;
     a.B = B; a.IH = IH; a.IW = IW; a.OH = OH; a.OW = OW;
     a.N = l.Cout; a.N0 = l.Cout;
     a.KH = a.KW = l.K; a.stride = stride; a.pad = pad; a.dil = 1;
@@ -531,10 +546,12 @@ struct Runner {
     a.w = l.w_fwd;
     a.bias = c.Pp(l.pb);
     a.out0 = out; a.add0 = add;
-    return launch_conv(lc, a);
+    IGM_TRY(launch_conv(lc, a));
+    if (out_act) IGM_TRY(stage_act(*out_act));
+    return IGM_OK;
   }
   // data gradient: d_out [B,OH,OW,Cout] -> d_in split (d0: C0 channels, d1: C1 channels)
-  // dy_staged: the bf16 hi/lo copy of d_out already sits in the dy staging buffers (conv_bwd)
+  // dy_staged: the bf16 hi/lo copy of d_out already sits in the dy staging buffers
   int conv_dgrad(const ConvL& l, const float* d_out, int OH, int OW, int IH, int IW, int stride, int pad,
                  float* d0, int C0, float* d1, int C1, const float* add0, const float* add1,
                  bool dy_staged = false) {
@@ -557,38 +574,36 @@ struct Runner {
     a.out0 = d0; a.out1 = d1; a.add0 = add0; a.add1 = add1;
     return launch_conv(lc, a);
   }
-  // weight + bias gradients.  in0/in1: forward inputs; d_out: grad of the conv output
-  int conv_wgrad(const ConvL& l, const float* in0, int C0, const float* in1, int C1, int IH, int IW,
-                 const float* d_out, int OH, int OW, int stride, int pad, bool dy_staged = false) {
+  // weight + bias gradients of a layer conv (forward inputs = its wired sources)
+  int conv_wgrad(const ConvL& l, int IH, int IW, const float* d_out, int OH, int OW, int stride, int pad,
+                 bool dy_staged = false) {
     const int KK = l.K * l.K;
     float* gw = c.Gp(l.pw);
-    if (stride == 1 && c.conv_engine == 1 && tcw_batch_ok(l.tc_w, B)) {
-      // tensor-core path: stage X (and dY unless the caller already did) as bf16 hi/lo, then split-K GEMM
-      const int Ct = C0 + C1;
+    const Act* s0 = l.src0;
+    const Act* s1 = l.src1;
+    if (stride == 1 && tc_on() && tcw_batch_ok(l.tc_w, B)) {
+      // tensor-core path: X is already staged (forward), dY is staged by the caller or here
       if (!dy_staged) IGM_TRY(launch_split_bf16(lc, d_out, M(OH, OW), l.Cout, c.dy_hi, c.dy_lo, l.Cout, 0));
-      IGM_TRY(launch_split_bf16(lc, in0, M(IH, IW), C0, c.split_hi, c.split_lo, Ct, 0));
-      if (in1 && C1 > 0) IGM_TRY(launch_split_bf16(lc, in1, M(IH, IW), C1, c.split_hi, c.split_lo, Ct, C0));
       IGM_TRY(launch_wgrad_tc(lc, l.tc_w, B, gw));
     } else if (!l.convT) {
       // Conv2d: P = d_out (pc = co), Q = input (qc = ci) gathered at oy*s - p + ky;  W[co][ci][tap]
-      const float* srcs[2] = {in0, in1};
-      const int cs[2] = {C0, C1};
+      const Act* srcs[2] = {s0, s1};
       int coff = 0;
       for (int i = 0; i < 2; ++i) {
-        if (!srcs[i] || cs[i] == 0) continue;
+        if (!srcs[i]) continue;
         WgradArgs w;
         w.P = d_out; w.PC = l.Cout; w.PH = OH; w.PW = OW;
-        w.Q = srcs[i]; w.QC = cs[i]; w.QH = IH; w.QW = IW;
+        w.Q = srcs[i]->v; w.QC = srcs[i]->C; w.QH = IH; w.QW = IW;
         w.B = B; w.KH = w.KW = l.K; w.stride = stride; w.pad = pad; w.dil = 1;
         w.grad = gw + (int64_t)coff * KK;
         w.sq = KK; w.sp = (int64_t)l.Cin * KK;
         IGM_TRY(launch_wgrad(lc, w));
-        coff += cs[i];
+        coff += srcs[i]->C;
       }
     } else {
       // ConvTranspose2d: oy = iy*s - p + ky.  P = input (pc = ci), Q = d_out (qc = co);  W[ci][co][tap]
       WgradArgs w;
-      w.P = in0; w.PC = l.Cin; w.PH = IH; w.PW = IW;
+      w.P = s0->v; w.PC = l.Cin; w.PH = IH; w.PW = IW;
       w.Q = d_out; w.QC = l.Cout; w.QH = OH; w.QW = OW;
       w.B = B; w.KH = w.KW = l.K; w.stride = stride; w.pad = pad; w.dil = 1;
       w.grad = gw;
@@ -600,30 +615,29 @@ struct Runner {
   }
 
   // Backward of a stride-1 conv: weight/bias gradients, then (if d0) the data gradient.  dY is staged
-  // once as bf16 hi/lo and shared by the tensor-core wgrad and dgrad kernels.
-  int conv_bwd(const ConvL& l, const float* in0, int C0, const float* in1, int C1, int H, int W, const float* dY,
-               float* d0, float* d1, const float* add0, const float* add1) {
+  // once as bf16 hi/lo (by the producer when `staged`, else here) and shared by wgrad and dgrad.
+  int conv_bwd(const ConvL& l, int H, int W, const float* dY, float* d0, float* d1, const float* add0,
+               const float* add1, bool staged = false) {
     const int pad = (l.K - 1) / 2;
-    bool staged = false;
-    if (c.conv_engine == 1 && (tcw_batch_ok(l.tc_w, B) || (d0 && l.tc_b.valid && C0 % 32 == 0))) {
+    const int C0 = l.src0->C, C1 = l.src1 ? l.src1->C : 0;
+    if (!staged && tc_on() && (tcw_batch_ok(l.tc_w, B) || (d0 && l.tc_b.valid && C0 % 32 == 0))) {
       IGM_TRY(launch_split_bf16(lc, dY, M(H, W), l.Cout, c.dy_hi, c.dy_lo, l.Cout, 0));
       staged = true;
     }
-    IGM_TRY(conv_wgrad(l, in0, C0, in1, C1, H, W, dY, H, W, 1, pad, staged));
+    IGM_TRY(conv_wgrad(l, H, W, dY, H, W, 1, pad, staged));
     if (d0) IGM_TRY(conv_dgrad(l, dY, H, W, H, W, 1, pad, d0, C0, d1, C1, add0, add1, staged));
     return IGM_OK;
   }
 
   // ---- Block: conv3x3 -> GN -> Mish (+temb) (+res) ----
-  int block_fwd(BlockL& b, const float* in0, int C0, const float* in1, int C1, int H, int W, const float* temb,
-                const float* res, float* out) {
-    IGM_TRY(conv_fwd(b.conv, in0, C0, in1, C1, H, W, H, W, 1, 1, b.raw, nullptr));
+  int block_fwd(BlockL& b, int H, int W, const float* temb, const float* res, const Act& out) {
+    IGM_TRY(conv_fwd(b.conv, H, W, H, W, 1, 1, b.raw, nullptr));
     IGM_TRY(launch_gn_partial(lc, b.raw, B, H * W, b.conv.Cout, c.gn_part));
-    IGM_TRY(launch_gn_apply(lc, b.raw, c.gn_part, c.Pp(b.gn_w), c.Pp(b.gn_b), temb, c.proj_total, res, out,
-                            b.stats, B, H * W, b.conv.Cout));
+    IGM_TRY(launch_gn_apply(lc, b.raw, c.gn_part, c.Pp(b.gn_w), c.Pp(b.gn_b), temb, c.proj_total, res, out.v,
+                            b.stats, B, H * W, b.conv.Cout, hi(out), lo(out)));
     return IGM_OK;
   }
-  // d_out: grad of block output; leaves dy (grad of conv output) in scrA
+  // d_out: grad of block output; leaves dy (grad of conv output) in scrA (+ its bf16 staging copy)
   int block_bwd_norm(BlockL& b, const float* d_out, int H, int W, float* dtemb) {
     GnBwdArgs g;
     g.d_out = d_out; g.y = b.raw; g.stats = b.stats;
@@ -631,59 +645,62 @@ struct Runner {
     g.dy = c.scrA; g.dgamma = c.Gp(b.gn_w); g.dbeta = c.Gp(b.gn_b);
     g.dtemb = dtemb; g.dtemb_stride = c.proj_total;
     g.dbias = c.Gp(b.conv.pb);
+    g.dy_hi = tc_on() ? c.dy_hi : nullptr; g.dy_lo = tc_on() ? c.dy_lo : nullptr;
     g.ws_group = c.ws_group; g.ws_chan = c.ws_chan;
     g.B = B; g.HW = H * W; g.C = b.conv.Cout;
     return launch_gn_backward(lc, g);
   }
+  bool dy_is_staged() const { return tc_on() && c.dy_hi != nullptr; }
 
-  int resnet_fwd(ResnetL& r, const float* in0, int C0, const float* in1, int C1) {
+  int resnet_fwd(ResnetL& r) {
     const int H = r.H, W = r.W;
-    IGM_TRY(block_fwd(r.b1, in0, C0, in1, C1, H, W, c.t_proj + r.temb_off, nullptr, r.h1.v));
-    const float* res = in0;
+    IGM_TRY(block_fwd(r.b1, H, W, c.t_proj + r.temb_off, nullptr, r.h1));
+    const float* res = r.in0->v;
     if (r.has_res) {
-      IGM_TRY(conv_fwd(r.res, in0, C0, in1, C1, H, W, H, W, 1, 0, r.r, nullptr));
+      IGM_TRY(conv_fwd(r.res, H, W, H, W, 1, 0, r.r, nullptr));
       res = r.r;
     }
-    IGM_TRY(block_fwd(r.b2, r.h1.v, r.Cout, nullptr, 0, H, W, nullptr, res, r.out.v));
+    IGM_TRY(block_fwd(r.b2, H, W, nullptr, res, r.out));
     return IGM_OK;
   }
-  // d_out = r.out.g ; writes d_in0 (C0 ch) / d_in1 (C1 ch) unless null
-  int resnet_bwd(ResnetL& r, const float* in0, int C0, const float* in1, int C1, float* d0, float* d1) {
+  // d_out = r.out.g ; writes d_in0 / d_in1 unless null
+  int resnet_bwd(ResnetL& r, float* d0, float* d1) {
     const int H = r.H, W = r.W;
     const float* d_out = r.out.g;
     // block2
     IGM_TRY(block_bwd_norm(r.b2, d_out, H, W, nullptr));
-    IGM_TRY(conv_bwd(r.b2.conv, r.h1.v, r.Cout, nullptr, 0, H, W, c.scrA, r.h1.g, nullptr, nullptr, nullptr));
+    IGM_TRY(conv_bwd(r.b2.conv, H, W, c.scrA, r.h1.g, nullptr, nullptr, nullptr, dy_is_staged()));
     // block1 (+ time-embedding add)
-    IGM_TRY(block_bwd_norm(r.b1, r.h1.g, H, W, c.t_dproj + r.temb_off));
     if (r.has_res) {
-      IGM_TRY(conv_bwd(r.res, in0, C0, in1, C1, H, W, d_out, d0, d1, nullptr, nullptr));
-      IGM_TRY(conv_bwd(r.b1.conv, in0, C0, in1, C1, H, W, c.scrA, d0, d1, d0, d1));
+      // res_conv first (its dY is d_out), then block1 accumulates on top of its data gradient
+      IGM_TRY(conv_bwd(r.res, H, W, d_out, d0, d1, nullptr, nullptr));
+      IGM_TRY(block_bwd_norm(r.b1, r.h1.g, H, W, c.t_dproj + r.temb_off));
+      IGM_TRY(conv_bwd(r.b1.conv, H, W, c.scrA, d0, d1, d0, d1, dy_is_staged()));
     } else {
-      IGM_TRY(conv_bwd(r.b1.conv, in0, C0, in1, C1, H, W, c.scrA, d0, nullptr, d_out, nullptr));
+      IGM_TRY(block_bwd_norm(r.b1, r.h1.g, H, W, c.t_dproj + r.temb_off));
+      IGM_TRY(conv_bwd(r.b1.conv, H, W, c.scrA, d0, nullptr, d_out, nullptr, dy_is_staged()));
     }
     return IGM_OK;
   }
 
-  int attn_fwd(AttnL& a, const float* x) {
+  int attn_fwd(AttnL& a) {
     const int H = a.H, W = a.W;
     const int64_t m = M(H, W);
-    const int hd = kHeads * kDimHead;
-    IGM_TRY(launch_ln_forward(lc, x, c.Pp(a.ln_g), c.Pp(a.ln_b), a.ln, m, a.C));
-    IGM_TRY(conv_fwd(a.qkv, a.ln, a.C, nullptr, 0, H, W, H, W, 1, 0, a.qkv_t, nullptr));
-    IGM_TRY(launch_linattn_forward(lc, a.qkv_t, a.att, a.ctx, a.kstat, B, H * W));
-    IGM_TRY(conv_fwd(a.outc, a.att, hd, nullptr, 0, H, W, H, W, 1, 0, a.out.v, x));
+    const float* x = a.in->v;
+    IGM_TRY(launch_ln_forward(lc, x, c.Pp(a.ln_g), c.Pp(a.ln_b), a.ln.v, m, a.C, hi(a.ln), lo(a.ln)));
+    IGM_TRY(conv_fwd(a.qkv, H, W, H, W, 1, 0, a.qkv_t, nullptr));
+    IGM_TRY(launch_linattn_forward(lc, a.qkv_t, a.att.v, a.ctx, a.kstat, B, H * W, hi(a.att), lo(a.att)));
+    IGM_TRY(conv_fwd(a.outc, H, W, H, W, 1, 0, a.out.v, x, &a.out));
     return IGM_OK;
   }
-  int attn_bwd(AttnL& a, const float* x, float* dx) {
+  int attn_bwd(AttnL& a, float* dx) {
     const int H = a.H, W = a.W;
     const int64_t m = M(H, W);
-    const int hd = kHeads * kDimHead;
     const float* d_out = a.out.g;
-    IGM_TRY(conv_bwd(a.outc, a.att, hd, nullptr, 0, H, W, d_out, c.scrB, nullptr, nullptr, nullptr));
+    IGM_TRY(conv_bwd(a.outc, H, W, d_out, c.scrB, nullptr, nullptr, nullptr));
     IGM_TRY(launch_linattn_backward(lc, a.qkv_t, a.ctx, a.kstat, c.scrB, c.scrC, B, H * W));
-    IGM_TRY(conv_bwd(a.qkv, a.ln, a.C, nullptr, 0, H, W, c.scrC, c.scrA, nullptr, nullptr, nullptr));
-    IGM_TRY(launch_ln_backward(lc, c.scrA, x, c.Pp(a.ln_g), d_out, dx, c.Gp(a.ln_g), c.Gp(a.ln_b), c.ws_ln, m, a.C));
+    IGM_TRY(conv_bwd(a.qkv, H, W, c.scrC, c.scrA, nullptr, nullptr, nullptr));
+    IGM_TRY(launch_ln_backward(lc, c.scrA, a.in->v, c.Pp(a.ln_g), d_out, dx, c.Gp(a.ln_g), c.Gp(a.ln_b), c.ws_ln, m, a.C));
     return IGM_OK;
   }
 
@@ -695,43 +712,36 @@ struct Runner {
     return IGM_OK;
   }
 
-  // whole network on c.x_in -> pred_nchw
+  int resample_fwd(ResampleL& rs) {
+    return conv_fwd(rs.conv, rs.Hin, rs.Win, rs.out.H, rs.out.W, 2, 1, rs.out.v, nullptr, &rs.out);
+  }
+  // weight/bias gradients + data gradient (into rs.in->g, plus an optional addend) of a resample conv
+  int resample_bwd(ResampleL& rs, const float* add) {
+    IGM_TRY(conv_wgrad(rs.conv, rs.Hin, rs.Win, rs.out.g, rs.out.H, rs.out.W, 2, 1));
+    return conv_dgrad(rs.conv, rs.out.g, rs.out.H, rs.out.W, rs.Hin, rs.Win, 2, 1, rs.in->g, rs.in->C, nullptr, 0, add,
+                      nullptr);
+  }
+
+  // whole network on c.x_in -> pred_nchw   (topology: wire_plan())
   int forward(const int64_t* t, float* pred_nchw) {
     const igm_unet_cfg& cfg = c.cfg;
     TimeMlpParams tp;
     time_params(tp);
     IGM_TRY(launch_time_mlp_forward(lc, tp, t, B, c.t_emb, c.t_h1, c.t_temb, c.t_act));
     IGM_TRY(launch_time_proj_forward(lc, c.proj_dev, c.n_proj, c.t_act, cfg.dim, B, c.proj_total, c.t_proj));
-    const float* x = c.x_in.v;
-    int xc = cfg.channels;
-    const int nres = cfg.n_mults;
-    for (int i = 0; i < nres; ++i) {
-      Stage& s = c.downs[i];
-      IGM_TRY(resnet_fwd(s.r1, x, xc, nullptr, 0));
-      IGM_TRY(resnet_fwd(s.r2, s.r1.out.v, s.r1.Cout, nullptr, 0));
-      IGM_TRY(attn_fwd(s.attn, s.r2.out.v));
-      x = s.attn.out.v; xc = s.attn.C;
-      if (s.rs.present) {
-        IGM_TRY(conv_fwd(s.rs.conv, x, xc, nullptr, 0, s.rs.Hin, s.rs.Win, s.rs.out.H, s.rs.out.W, 2, 1,
-                         s.rs.out.v, nullptr));
-        x = s.rs.out.v;
-      }
-    }
-    IGM_TRY(resnet_fwd(c.mid1, x, xc, nullptr, 0));
-    IGM_TRY(attn_fwd(c.mid_attn, c.mid1.out.v));
-    IGM_TRY(resnet_fwd(c.mid2, c.mid_attn.out.v, c.mid_attn.C, nullptr, 0));
-    x = c.mid2.out.v; xc = c.mid2.Cout;
-    for (int j = 0; j < nres - 1; ++j) {
-      Stage& s = c.ups[j];
-      const AttnL& skip = c.downs[nres - 1 - j].attn;   // h.pop()  (ddpm.py:255)
-      IGM_TRY(resnet_fwd(s.r1, x, xc, skip.out.v, skip.C));
-      IGM_TRY(resnet_fwd(s.r2, s.r1.out.v, s.r1.Cout, nullptr, 0));
-      IGM_TRY(attn_fwd(s.attn, s.r2.out.v));
-      IGM_TRY(conv_fwd(s.rs.conv, s.attn.out.v, s.attn.C, nullptr, 0, s.rs.Hin, s.rs.Win, s.rs.out.H,
-                       s.rs.out.W, 2, 1, s.rs.out.v, nullptr));
-      x = s.rs.out.v; xc = s.attn.C;
-    }
-    IGM_TRY(block_fwd(c.final_block, x, xc, nullptr, 0, cfg.height, cfg.width, nullptr, nullptr, c.final_act.v));
+    auto stage = [&](Stage& s) -> int {
+      IGM_TRY(resnet_fwd(s.r1));
+      IGM_TRY(resnet_fwd(s.r2));
+      IGM_TRY(attn_fwd(s.attn));
+      if (s.rs.present) IGM_TRY(resample_fwd(s.rs));
+      return IGM_OK;
+    };
+    for (auto& s : c.downs) IGM_TRY(stage(s));
+    IGM_TRY(resnet_fwd(c.mid1));
+    IGM_TRY(attn_fwd(c.mid_attn));
+    IGM_TRY(resnet_fwd(c.mid2));
+    for (auto& s : c.ups) IGM_TRY(stage(s));
+    IGM_TRY(block_fwd(c.final_block, cfg.height, cfg.width, nullptr, nullptr, c.final_act));
     IGM_TRY(launch_final_conv(lc, c.final_act.v, c.Pp(c.final_conv.pw), c.Pp(c.final_conv.pb), pred_nchw, B,
                               cfg.height * cfg.width, c.final_conv.Cin, cfg.channels));
     return IGM_OK;
@@ -757,51 +767,30 @@ struct Runner {
       a.w = c.final_wbwd; a.out0 = c.final_act.g;
       IGM_TRY(launch_conv(lc, a));
     }
-    // input of the final block
-    const float* fin; int finC; float* fin_g;
-    if (nres > 1) { fin = c.ups.back().rs.out.v; finC = c.ups.back().rs.out.C; fin_g = c.ups.back().rs.out.g; }
-    else { fin = c.mid2.out.v; finC = c.mid2.Cout; fin_g = c.mid2.out.g; }
     IGM_TRY(block_bwd_norm(c.final_block, c.final_act.g, H0, W0, nullptr));
-    IGM_TRY(conv_bwd(c.final_block.conv, fin, finC, nullptr, 0, H0, W0, c.scrA, fin_g, nullptr, nullptr, nullptr));
+    IGM_TRY(conv_bwd(c.final_block.conv, H0, W0, c.scrA, c.final_in->g, nullptr, nullptr, nullptr, dy_is_staged()));
 
     for (int j = nres - 2; j >= 0; --j) {
       Stage& s = c.ups[j];
-      AttnL& skip = c.downs[nres - 1 - j].attn;
-      const Act& prev = (j == 0) ? c.mid2.out : c.ups[j - 1].rs.out;
-      // Upsample (ConvTranspose2d 4,2,1)
-      IGM_TRY(conv_wgrad(s.rs.conv, s.attn.out.v, s.attn.C, nullptr, 0, s.rs.Hin, s.rs.Win, s.rs.out.g,
-                         s.rs.out.H, s.rs.out.W, 2, 1));
-      IGM_TRY(conv_dgrad(s.rs.conv, s.rs.out.g, s.rs.out.H, s.rs.out.W, s.rs.Hin, s.rs.Win, 2, 1, s.attn.out.g,
-                         s.attn.C, nullptr, 0, nullptr, nullptr));
-      IGM_TRY(attn_bwd(s.attn, s.r2.out.v, s.r2.out.g));
-      IGM_TRY(resnet_bwd(s.r2, s.r1.out.v, s.r1.Cout, nullptr, 0, s.r1.out.g, nullptr));
-      IGM_TRY(resnet_bwd(s.r1, prev.v, prev.C, skip.out.v, skip.C, prev.g, skip_grad(nres - 1 - j)));
+      IGM_TRY(resample_bwd(s.rs, nullptr));                      // Upsample (ConvTranspose2d 4,2,1)
+      IGM_TRY(attn_bwd(s.attn, s.r2.out.g));
+      IGM_TRY(resnet_bwd(s.r2, s.r1.out.g, nullptr));
+      IGM_TRY(resnet_bwd(s.r1, s.r1.in0->g, c.skip_g[nres - 1 - j]));   // concat: (x, skip)
     }
-    IGM_TRY(resnet_bwd(c.mid2, c.mid_attn.out.v, c.mid_attn.C, nullptr, 0, c.mid_attn.out.g, nullptr));
-    IGM_TRY(attn_bwd(c.mid_attn, c.mid1.out.v, c.mid1.out.g));
+    IGM_TRY(resnet_bwd(c.mid2, c.mid_attn.out.g, nullptr));
+    IGM_TRY(attn_bwd(c.mid_attn, c.mid1.out.g));
     {
       Stage& last = c.downs[nres - 1];
-      IGM_TRY(resnet_bwd(c.mid1, last.attn.out.v, last.attn.C, nullptr, 0, last.attn.out.g, nullptr));
-      if (nres > 1) IGM_TRY(launch_add(lc, last.attn.out.g, skip_grad(nres - 1), M(last.attn.H, last.attn.W) * last.attn.C));
+      IGM_TRY(resnet_bwd(c.mid1, last.attn.out.g, nullptr));
+      if (nres > 1) IGM_TRY(launch_add(lc, last.attn.out.g, c.skip_g[nres - 1], M(last.attn.H, last.attn.W) * last.attn.C));
     }
     for (int i = nres - 1; i >= 0; --i) {
       Stage& s = c.downs[i];
-      if (s.rs.present) {
-        IGM_TRY(conv_wgrad(s.rs.conv, s.attn.out.v, s.attn.C, nullptr, 0, s.rs.Hin, s.rs.Win, s.rs.out.g,
-                           s.rs.out.H, s.rs.out.W, 2, 1));
-        // h[0] is never consumed by the up path (ddpm.py:254-259): no skip gradient for stage 0
-        const float* add = (i >= 1) ? skip_grad(i) : nullptr;
-        IGM_TRY(conv_dgrad(s.rs.conv, s.rs.out.g, s.rs.out.H, s.rs.out.W, s.rs.Hin, s.rs.Win, 2, 1, s.attn.out.g,
-                           s.attn.C, nullptr, 0, add, nullptr));
-      }
-      IGM_TRY(attn_bwd(s.attn, s.r2.out.v, s.r2.out.g));
-      IGM_TRY(resnet_bwd(s.r2, s.r1.out.v, s.r1.Cout, nullptr, 0, s.r1.out.g, nullptr));
-      if (i > 0) {
-        const Act& prev = c.downs[i - 1].rs.out;
-        IGM_TRY(resnet_bwd(s.r1, prev.v, prev.C, nullptr, 0, prev.g, nullptr));
-      } else {
-        IGM_TRY(resnet_bwd(s.r1, c.x_in.v, cfg.channels, nullptr, 0, d_x_nhwc, nullptr));
-      }
+      // h[0] is never consumed by the up path (ddpm.py:254-259): no skip gradient for stage 0
+      if (s.rs.present) IGM_TRY(resample_bwd(s.rs, (i >= 1) ? c.skip_g[i] : nullptr));
+      IGM_TRY(attn_bwd(s.attn, s.r2.out.g));
+      IGM_TRY(resnet_bwd(s.r2, s.r1.out.g, nullptr));
+      IGM_TRY(resnet_bwd(s.r1, i > 0 ? s.r1.in0->g : d_x_nhwc, nullptr));
     }
     TimeMlpParams tp;
     time_params(tp);
@@ -809,8 +798,6 @@ struct Runner {
                                  c.t_dproj, c.t_ws));
     return IGM_OK;
   }
-
-  float* skip_grad(int stage) { return c.skip_g[stage]; }
 };
 
 }  // namespace
@@ -845,19 +832,62 @@ static int for_each_conv(igm_ctx* c, F f) {
   return IGM_OK;
 }
 
-// TMA descriptors of the tcgen05 engine for every eligible stride-1 conv (needs a live driver)
+// Topology of Unet.forward (reference ddpm.py:238-261): which activation feeds which layer.
+static void wire_plan(igm_ctx* c) {
+  const int nres = c->cfg.n_mults;
+  auto wire_resnet = [](ResnetL& r, const Act* in0, const Act* in1) {
+    r.in0 = in0; r.in1 = in1;
+    r.b1.conv.src0 = in0; r.b1.conv.src1 = in1;
+    r.b2.conv.src0 = &r.h1; r.b2.conv.src1 = nullptr;
+    r.res.src0 = in0; r.res.src1 = in1;
+  };
+  auto wire_attn = [](AttnL& a, const Act* in) {
+    a.in = in;
+    a.qkv.src0 = &a.ln; a.outc.src0 = &a.att;
+  };
+  const Act* cur = &c->x_in;
+  for (int i = 0; i < nres; ++i) {
+    Stage& s = c->downs[i];
+    wire_resnet(s.r1, cur, nullptr);
+    wire_resnet(s.r2, &s.r1.out, nullptr);
+    wire_attn(s.attn, &s.r2.out);
+    cur = &s.attn.out;
+    if (s.rs.present) { s.rs.in = cur; s.rs.conv.src0 = cur; cur = &s.rs.out; }
+  }
+  wire_resnet(c->mid1, cur, nullptr);
+  wire_attn(c->mid_attn, &c->mid1.out);
+  wire_resnet(c->mid2, &c->mid_attn.out, nullptr);
+  cur = &c->mid2.out;
+  for (int j = 0; j < nres - 1; ++j) {
+    Stage& s = c->ups[j];
+    wire_resnet(s.r1, cur, &c->downs[nres - 1 - j].attn.out);   // torch.cat((x, h.pop()), dim=1)  (:255)
+    wire_resnet(s.r2, &s.r1.out, nullptr);
+    wire_attn(s.attn, &s.r2.out);
+    s.rs.in = &s.attn.out; s.rs.conv.src0 = &s.attn.out;
+    cur = &s.rs.out;
+  }
+  c->final_in = cur;
+  c->final_block.conv.src0 = cur;
+}
+
+// TMA descriptors of the tcgen05 engine for every eligible stride-1 conv (needs a live driver).
+// Operands are the producers' bf16 hi/lo staging copies of the wired source activations.
 static int plan_tc(igm_ctx* c) {
   int n_valid = 0;
   int rc = for_each_conv(c, [&](ConvL& l) -> int {
-    if (l.tc_f_ok)
-      IGM_TRY(tc_plan(c->st, l.tc_f, l.Cin, l.Cout, l.H, l.W, c->cfg.max_batch, l.K, (l.K - 1) / 2, c->split_hi,
-                      c->split_lo, l.wf_hi, l.wf_lo));
+    const Act* s0 = l.src0;
+    const Act* s1 = l.src1;
+    const bool staged = s0 && s0->hi && (!s1 || s1->hi);
+    const int pad = (l.K - 1) / 2;
+    if (l.tc_f_ok && staged)
+      IGM_TRY(tc_plan(c->st, l.tc_f, l.Cin, l.Cout, l.H, l.W, c->cfg.max_batch, l.K, pad, s0->hi, s0->lo, l.wf_hi,
+                      l.wf_lo, s0->C, s1 ? s1->hi : nullptr, s1 ? s1->lo : nullptr));
     if (l.tc_b_ok)
-      IGM_TRY(tc_plan(c->st, l.tc_b, l.Cout, l.Cin, l.H, l.W, c->cfg.max_batch, l.K, (l.K - 1) / 2, c->dy_hi,
-                      c->dy_lo, l.wb_hi, l.wb_lo));
-    if (l.tc_w_ok)
-      IGM_TRY(tcw_plan(c->st, l.tc_w, l.Cin, l.Cout, l.H, l.W, c->cfg.max_batch, l.K, (l.K - 1) / 2, c->dy_hi,
-                       c->dy_lo, c->split_hi, c->split_lo));
+      IGM_TRY(tc_plan(c->st, l.tc_b, l.Cout, l.Cin, l.H, l.W, c->cfg.max_batch, l.K, pad, c->dy_hi, c->dy_lo, l.wb_hi,
+                      l.wb_lo));
+    if (l.tc_w_ok && staged)
+      IGM_TRY(tcw_plan(c->st, l.tc_w, l.Cin, l.Cout, l.H, l.W, c->cfg.max_batch, l.K, pad, c->dy_hi, c->dy_lo, s0->hi,
+                       s0->lo, s0->C, s1 ? s1->hi : nullptr, s1 ? s1->lo : nullptr));
     n_valid += (l.tc_f.valid ? 1 : 0) + (l.tc_b.valid ? 1 : 0) + (l.tc_w.valid ? 1 : 0);
     return IGM_OK;
   });
@@ -940,6 +970,7 @@ int igm_unet_create(igm_ctx** out, const igm_unet_cfg* cfg, int device) {
   }
   int64_t floats2 = 0;
   build_plan(c, c->arena, &floats2);
+  wire_plan(c);
   // tensor-core engine: on by default when the shapes allow it (IGM_CONV_ENGINE=0 forces the SIMT engine)
   const char* eng = getenv("IGM_CONV_ENGINE");
   if (!(eng && eng[0] == '0')) {
@@ -1282,6 +1313,7 @@ int igm_set_conv_engine(igm_ctx* c, int engine) {
   if (c->graph_exec && engine != c->conv_engine) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
   const bool changed = engine != c->conv_engine;
   c->conv_engine = engine;
+  if (changed) c->fwd_valid = c->loss_valid = false;   // staged operands of the last forward belong to the old engine
   if (changed && c->P) IGM_TRY(igm_unet_pack_weights(c, nullptr));   // the other engine reads other layouts
   return IGM_OK;
 }

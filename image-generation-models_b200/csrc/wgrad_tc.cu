@@ -27,7 +27,7 @@ constexpr int BOX_BYTES = PIX * 128;    // one 64-channel x 64-pixel bf16 box
 constexpr int UMMA_K = 16;
 
 struct WArgs {
-  int B, H, W, Cin, Cout, KH, KW, pad;
+  int B, H, W, Cin, C0, Cout, KH, KW, pad;
   int BW, BH, BB, rows;
   int tiles_per_img, n_ptiles;
   int n_pairs, n_ci_tiles, splits, tiles_per_split;
@@ -49,7 +49,8 @@ struct WCfg {
 template <int NB>
 __global__ void __launch_bounds__(192, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tdy_hi, const __grid_constant__ CUtensorMap tdy_lo,
-                const __grid_constant__ CUtensorMap tx_hi, const __grid_constant__ CUtensorMap tx_lo, const WArgs p) {
+                const __grid_constant__ CUtensorMap tx_hi, const __grid_constant__ CUtensorMap tx_lo,
+                const __grid_constant__ CUtensorMap tx1_hi, const __grid_constant__ CUtensorMap tx1_lo, const WArgs p) {
   using C = WCfg<NB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -126,8 +127,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tdy_hi, const __grid_constan
 #pragma unroll
           for (int nb = 0; nb < NB; ++nb) {
             const int c0 = ci_tile * C::BN + nb * 64;
-            tma_load_4d(st + (4 + nb) * BOX_BYTES, &tx_hi, &full[stage], c0, 0, y0, b0);
-            tma_load_4d(st + (4 + NB + nb) * BOX_BYTES, &tx_lo, &full[stage], c0, 0, y0, b0);
+            if (c0 < p.C0) {
+              tma_load_4d(st + (4 + nb) * BOX_BYTES, &tx_hi, &full[stage], c0, 0, y0, b0);
+              tma_load_4d(st + (4 + NB + nb) * BOX_BYTES, &tx_lo, &full[stage], c0, 0, y0, b0);
+            } else {   // second tensor of a channel concat
+              tma_load_4d(st + (4 + nb) * BOX_BYTES, &tx1_hi, &full[stage], c0 - p.C0, 0, y0, b0);
+              tma_load_4d(st + (4 + NB + nb) * BOX_BYTES, &tx1_lo, &full[stage], c0 - p.C0, 0, y0, b0);
+            }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -213,7 +219,7 @@ int launch_impl(const LaunchCtx& lc, const TcWgrad& t, const WArgs& a, int grid)
     if (e != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(e));
     attr_done = true;
   }
-  wgrad_tc_kernel<NB><<<grid, 192, C::SMEM_BYTES, lc.stream>>>(t.dy_hi, t.dy_lo, t.x_hi, t.x_lo, a);
+  wgrad_tc_kernel<NB><<<grid, 192, C::SMEM_BYTES, lc.stream>>>(t.dy_hi, t.dy_lo, t.x_hi, t.x_lo, t.x1_hi, t.x1_lo, a);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }
@@ -228,20 +234,26 @@ bool tcw_eligible(int Cin, int Cout, int H, int W, int KH) {
 }
 
 int tcw_plan(Status& st, TcWgrad& t, int Cin, int Cout, int H, int W, int Bmax, int KH, int pad, __nv_bfloat16* dy_hi,
-             __nv_bfloat16* dy_lo, __nv_bfloat16* x_hi, __nv_bfloat16* x_lo) {
+             __nv_bfloat16* dy_lo, __nv_bfloat16* x_hi, __nv_bfloat16* x_lo, int C0, __nv_bfloat16* x1_hi,
+             __nv_bfloat16* x1_lo) {
   t.valid = false;
   if (!tcw_eligible(Cin, Cout, H, W, KH)) IGM_FAIL(st, IGM_ERR_INVALID, "shape not eligible for the tcgen05 wgrad engine");
+  if (C0 <= 0 || !x1_hi) C0 = Cin;
+  if (C0 % 64 != 0 || (Cin - C0) % 64 != 0) IGM_FAIL(st, IGM_ERR_INVALID, "concat split must be a multiple of 64 channels");
   auto enc = encode_fn();
   if (!enc) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  t.Cin = Cin; t.Cout = Cout; t.KH = t.KW = KH; t.pad = pad; t.H = H; t.W = W; t.Bmax = Bmax;
+  t.Cin = Cin; t.C0 = C0; t.Cout = Cout; t.KH = t.KW = KH; t.pad = pad; t.H = H; t.W = W; t.Bmax = Bmax;
   t.BW = W;
   if (H * W <= PIX) { t.BH = H; t.BB = PIX / (H * W); }
   else { t.BH = PIX / W; t.BB = 1; }
   if (t.BB > Bmax) t.BB = Bmax;
   t.rows = t.BB * t.BH * t.BW;
   t.BN = (Cin % 128 == 0) ? 128 : 64;
-  struct { CUtensorMap* m; void* ptr; int C; } maps[4] = {
-      {&t.dy_hi, dy_hi, Cout}, {&t.dy_lo, dy_lo, Cout}, {&t.x_hi, x_hi, Cin}, {&t.x_lo, x_lo, Cin}};
+  const bool two = C0 < Cin;
+  struct { CUtensorMap* m; void* ptr; int C; } maps[6] = {
+      {&t.dy_hi, dy_hi, Cout}, {&t.dy_lo, dy_lo, Cout}, {&t.x_hi, x_hi, C0}, {&t.x_lo, x_lo, C0},
+      {&t.x1_hi, two ? (void*)x1_hi : (void*)x_hi, two ? Cin - C0 : C0},
+      {&t.x1_lo, two ? (void*)x1_lo : (void*)x_lo, two ? Cin - C0 : C0}};
   for (auto& m : maps) {
     cuuint64_t dims[4] = {(cuuint64_t)m.C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Bmax};
     cuuint64_t strides[3] = {(cuuint64_t)m.C * 2, (cuuint64_t)W * m.C * 2, (cuuint64_t)H * W * m.C * 2};
@@ -260,7 +272,7 @@ bool tcw_batch_ok(const TcWgrad& t, int B) { return t.valid && B >= 1 && B <= t.
 int launch_wgrad_tc(const LaunchCtx& lc, const TcWgrad& t, int B, float* grad, int variant) {
   if (!tcw_batch_ok(t, B)) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "wgrad_tc: batch must be a multiple of the images per box");
   WArgs a;
-  a.B = B; a.H = t.H; a.W = t.W; a.Cin = t.Cin; a.Cout = t.Cout; a.KH = t.KH; a.KW = t.KW; a.pad = t.pad;
+  a.B = B; a.H = t.H; a.W = t.W; a.Cin = t.Cin; a.C0 = t.C0; a.Cout = t.Cout; a.KH = t.KH; a.KW = t.KW; a.pad = t.pad;
   a.BW = t.BW; a.BH = t.BH; a.BB = t.BB; a.rows = t.rows;
   a.tiles_per_img = (t.BB > 1) ? 1 : cdiv(t.H, t.BH);
   a.n_ptiles = (t.BB > 1) ? B / t.BB : B * a.tiles_per_img;
