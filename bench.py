@@ -277,10 +277,12 @@ def run_ours(args):
     prof = None
     if rank == 0:
         P = peaks()
+        unet.ddp_sync = False      # rank 0 profiles alone: no collective may be issued here
         unet.profile_start()
         for i in range(3):
             train_step(i)
         prof = unet.profile_stop()
+        unet.ddp_sync = True
         tot = sum(v["ms"] for v in prof.values()) or 1.0
         conv = {k: v for k, v in prof.items() if k.startswith("conv")}
         dom = max(conv, key=lambda k: conv[k]["ms"])

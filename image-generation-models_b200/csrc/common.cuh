@@ -282,17 +282,23 @@ int launch_nhwc_to_nchw(const LaunchCtx& lc, const float* src, float* dst, int B
 // device helpers
 // ---------------------------------------------------------------------------
 #ifdef __CUDACC__
-__device__ __forceinline__ float softplus_f(float x) {
-  // F.softplus(beta=1, threshold=20): x > 20 -> x, else log1p(exp(x))
-  return x > 20.f ? x : log1pf(expf(x));
+// Mish (reference ddpm.py:62-64): x * tanh(softplus(x)), F.softplus(beta=1, threshold=20).
+// With w = e^x:  tanh(log(1 + w)) = ((1+w)^2 - 1) / ((1+w)^2 + 1) = n / (n + 2),  n = w (w + 2),
+// so one exp and one division replace exp + log1p + tanh (the GroupNorm kernels were ALU-bound on
+// those three library calls).  Above the softplus threshold tanh(x) == 1 in fp32, so mish(x) = x.
+__device__ __forceinline__ float mish_f(float x) {
+  if (x > 20.f) return x;
+  const float w = expf(x);
+  const float n = w * (w + 2.f);
+  return x * __fdividef(n, n + 2.f);
 }
-__device__ __forceinline__ float mish_f(float x) { return x * tanhf(softplus_f(x)); }
+// d/dx mish = t + x * dt/dx,  t = n/(n+2),  dt/dx = 2 n' / (n+2)^2,  n' = 2 w (w + 1)
 __device__ __forceinline__ float mish_grad_f(float x) {
-  // d/dx [x * tanh(sp(x))] = tanh(sp) + x * (1 - tanh(sp)^2) * sp'(x);  sp' = sigmoid (1 above threshold)
-  float sp = softplus_f(x);
-  float th = tanhf(sp);
-  float sg = x > 20.f ? 1.f : 1.f / (1.f + expf(-x));
-  return th + x * (1.f - th * th) * sg;
+  if (x > 20.f) return 1.f;
+  const float w = expf(x);
+  const float n = w * (w + 2.f);
+  const float r = __fdividef(1.f, n + 2.f);
+  return n * r + x * (4.f * w * (w + 1.f)) * (r * r);
 }
 // bf16 hi/lo staging of four consecutive fp32 values (operands of the tcgen05 bf16x3 engine)
 __device__ __forceinline__ void store_split4(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
