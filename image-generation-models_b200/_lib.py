@@ -61,6 +61,8 @@ SYMBOLS = {
     "igm_profile_stop": (C.c_int, [_P, C.POINTER(ProfileEntry), C.c_int]),
     "igm_launch_count": (C.c_int64, [_P]),
     "igm_debug_wgrad": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "igm_debug_resample": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, _P]),
     "igm_debug_conv": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, _P]),
     "igm_set_conv_engine": (C.c_int, [_P, C.c_int]),

@@ -33,7 +33,9 @@ using namespace tc;
 
 struct TcArgs {
   int B, H, W, K, K0, N, N0;
-  int KH, KW, pad;
+  int ntaps, Csrc;
+  TcTap taps[kTcMaxTaps];
+  int out_H, out_W, sy, sx, oy_off, ox_off;
   int BH, BW, BB;
   int tiles_m, tiles_n, tiles_per_img;
   int stage_tx_bytes;   // bytes one pipeline stage receives: 2 x (box rows x 128 B) + 2 x weight tile
@@ -87,7 +89,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
 
   const int num_tiles = p.tiles_m * p.tiles_n;
   const int kchunks = p.K / KC;
-  const int iters = p.KH * p.KW * kchunks;
+  const int iters = p.ntaps * kchunks;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -100,22 +102,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
         int b0, y0;
         if (p.BB > 1) { b0 = tm * p.BB; y0 = 0; }
         else { b0 = tm / p.tiles_per_img; y0 = (tm - b0 * p.tiles_per_img) * p.BH; }
-        for (int tap = 0; tap < p.KH * p.KW; ++tap) {
-          const int ky = tap / p.KW, kx = tap - ky * p.KW;
+        for (int ti = 0; ti < p.ntaps; ++ti) {
+          const TcTap tp = p.taps[ti];
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* st = smem + stage * C::STAGE_BYTES;
             mbar_expect_tx(&full[stage], (uint32_t)p.stage_tx_bytes);
             const int ch = kc * KC;
+            // activation box: (channel, x, sub-lattice row py, y, image); px selects a channel block
             if (ch < p.K0) {
-              tma_load_4d(st, &ta_hi, &full[stage], ch, kx - p.pad, y0 + ky - p.pad, b0);
-              tma_load_4d(st + A_TILE_BYTES, &ta_lo, &full[stage], ch, kx - p.pad, y0 + ky - p.pad, b0);
+              tma_load_5d(st, &ta_hi, &full[stage], ch + tp.px * p.Csrc, tp.dx, tp.py, y0 + tp.dy, b0);
+              tma_load_5d(st + A_TILE_BYTES, &ta_lo, &full[stage], ch + tp.px * p.Csrc, tp.dx, tp.py, y0 + tp.dy, b0);
             } else {   // second tensor of a channel concat
-              tma_load_4d(st, &ta1_hi, &full[stage], ch - p.K0, kx - p.pad, y0 + ky - p.pad, b0);
-              tma_load_4d(st + A_TILE_BYTES, &ta1_lo, &full[stage], ch - p.K0, kx - p.pad, y0 + ky - p.pad, b0);
+              tma_load_5d(st, &ta1_hi, &full[stage], ch - p.K0, tp.dx, tp.py, y0 + tp.dy, b0);
+              tma_load_5d(st + A_TILE_BYTES, &ta1_lo, &full[stage], ch - p.K0, tp.dx, tp.py, y0 + tp.dy, b0);
             }
-            tma_load_2d(st + 2 * A_TILE_BYTES, &tb_hi, &full[stage], tap * p.K + kc * KC, tn * BN);
-            tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &tb_lo, &full[stage], tap * p.K + kc * KC, tn * BN);
+            tma_load_2d(st + 2 * A_TILE_BYTES, &tb_hi, &full[stage], tp.wtap * p.K + ch, tn * BN);
+            tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &tb_lo, &full[stage], tp.wtap * p.K + ch, tn * BN);
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -177,7 +180,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
       const int bb = r2 / p.BH;
       const int oy = y0 + by, b = b0 + bb;
       const bool valid = (bb < p.BB) && (oy < p.H) && (b < p.B);
-      const int64_t opix = ((int64_t)b * p.H + oy) * p.W + bx;
+      const int64_t opix = ((int64_t)b * p.out_H + (oy * p.sy + p.oy_off)) * p.out_W + (bx * p.sx + p.ox_off);
 
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
@@ -323,15 +326,73 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 }  // namespace
 
+static bool tile_grid_ok(int GH, int GW) { return GW >= 1 && GW <= BM && GH >= 1; }
+
 bool tc_eligible(int K, int N, int H, int W, int KH) {
   if (K < KC || K % KC != 0) return false;
   if (N < 64 || N % 64 != 0) return false;
-  if (W > BM || W < 1 || H < 1) return false;
   if (KH != 1 && KH != 3) return false;
-  // the 128-row box must tile the image: rows of W pixels, whole images when they are small
-  if (H * W <= BM) return (BM / (H * W)) >= 1;
-  return (BM / W) >= 1;
+  return tile_grid_ok(H, W);
 }
+
+bool tc_strided_eligible(int K, int N, int SH, int SW, int KH) {
+  if (K < KC || K % KC != 0 || N < 64 || N % 64 != 0) return false;
+  if (KH != 3 && KH != 4) return false;
+  if (SH % 2 != 0 || SW % 2 != 0) return false;
+  return tile_grid_ok(SH / 2, SW / 2);
+}
+
+namespace {
+
+// Tile shape over a GH x GW grid and the weight descriptors; shared by every plan flavour.
+int plan_common(Status& st, TcConv& t, int K, int K0, int N, int GH, int GW, int Bmax, int wtaps,
+                __nv_bfloat16* w_hi, __nv_bfloat16* w_lo) {
+  auto enc = get_encode_fn();
+  if (!enc) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  t.K = K; t.K0 = K0; t.N = N; t.H = GH; t.W = GW; t.Bmax = Bmax;
+  t.w_hi = w_hi; t.w_lo = w_lo;
+  t.BW = GW;
+  if (GH * GW <= BM) { t.BH = GH; t.BB = BM / (GH * GW); }
+  else { t.BH = BM / GW; t.BB = 1; }
+  if (t.BB > Bmax) t.BB = Bmax;
+  t.BN = (N % 128 == 0) ? 128 : 64;
+  // weights: [N rows][wtaps*K cols], K-major
+  for (int which = 0; which < 2; ++which) {
+    cuuint64_t dims[2] = {(cuuint64_t)wtaps * K, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)wtaps * K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)t.BN};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(which ? &t.b_lo : &t.b_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, which ? (void*)w_lo : (void*)w_hi,
+                     dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled (weights) failed");
+  }
+  return IGM_OK;
+}
+
+// Rank-5 activation descriptor (channel, x, sub-lattice row, y, image) of a [Bmax, SH, SW, C] bf16 tensor.
+// s2d = false: plain view (C, SW, 1, SH, B).  s2d = true: stride-2 view (2C, SW/2, 2, SH/2, B), where
+// channel index px*C + c addresses pixel column 2x + px and the third coordinate py row 2y + py.
+int encode_act(Status& st, CUtensorMap* m, void* ptr, int C, int SH, int SW, int Bmax, bool s2d, const TcConv& t) {
+  auto enc = get_encode_fn();
+  const cuuint64_t rowB = (cuuint64_t)SW * C * 2;
+  cuuint64_t dims[5], strides[4];
+  if (!s2d) {
+    dims[0] = C; dims[1] = SW; dims[2] = 1; dims[3] = SH; dims[4] = Bmax;
+    strides[0] = (cuuint64_t)C * 2; strides[1] = rowB; strides[2] = rowB; strides[3] = rowB * SH;
+  } else {
+    dims[0] = 2 * (cuuint64_t)C; dims[1] = SW / 2; dims[2] = 2; dims[3] = SH / 2; dims[4] = Bmax;
+    strides[0] = (cuuint64_t)C * 4; strides[1] = rowB; strides[2] = 2 * rowB; strides[3] = rowB * SH;
+  }
+  cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)t.BW, 1u, (cuuint32_t)t.BH, (cuuint32_t)t.BB};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled (activations) failed");
+  return IGM_OK;
+}
+
+}  // namespace
 
 int tc_plan(Status& st, TcConv& t, int K, int N, int H, int W, int Bmax, int KH, int pad, __nv_bfloat16* a_hi,
             __nv_bfloat16* a_lo, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, int K0, __nv_bfloat16* a1_hi,
@@ -340,41 +401,74 @@ int tc_plan(Status& st, TcConv& t, int K, int N, int H, int W, int Bmax, int KH,
   if (!tc_eligible(K, N, H, W, KH)) IGM_FAIL(st, IGM_ERR_INVALID, "shape not eligible for the tcgen05 engine");
   if (K0 <= 0 || !a1_hi) K0 = K;
   if (K0 % KC != 0 || (K - K0) % KC != 0) IGM_FAIL(st, IGM_ERR_INVALID, "concat split must be a multiple of 64 channels");
-  auto enc = get_encode_fn();
-  if (!enc) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  t.K = K; t.K0 = K0; t.N = N; t.KH = t.KW = KH; t.pad = pad; t.H = H; t.W = W; t.Bmax = Bmax;
-  t.w_hi = w_hi; t.w_lo = w_lo;
-  t.BW = W;
-  if (H * W <= BM) { t.BH = H; t.BB = BM / (H * W); }
-  else { t.BH = BM / W; t.BB = 1; }
-  if (t.BB > Bmax) t.BB = Bmax;
-  t.BN = (N % 128 == 0) ? 128 : 64;
-  // activations: dims innermost-first (C, W, H, B); one descriptor pair per source tensor
-  struct { CUtensorMap* m; void* ptr; int C; } amaps[4] = {
-      {&t.a_hi, a_hi, K0}, {&t.a_lo, a_lo, K0},
-      {&t.a1_hi, K0 < K ? (void*)a1_hi : (void*)a_hi, K0 < K ? K - K0 : K0},
-      {&t.a1_lo, K0 < K ? (void*)a1_lo : (void*)a_lo, K0 < K ? K - K0 : K0}};
-  for (auto& m : amaps) {
-    cuuint64_t dims[4] = {(cuuint64_t)m.C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Bmax};
-    cuuint64_t strides[3] = {(cuuint64_t)m.C * 2, (cuuint64_t)W * m.C * 2, (cuuint64_t)H * W * m.C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)t.BW, (cuuint32_t)t.BH, (cuuint32_t)t.BB};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(m.m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, m.ptr, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled (activations) failed");
+  IGM_TRY(plan_common(st, t, K, K0, N, H, W, Bmax, KH * KH, w_hi, w_lo));
+  t.KH = t.KW = KH; t.pad = pad;
+  t.ntaps = KH * KH;
+  for (int ky = 0; ky < KH; ++ky)
+    for (int kx = 0; kx < KH; ++kx) t.taps[ky * KH + kx] = TcTap{kx - pad, ky - pad, 0, 0, ky * KH + kx};
+  t.Csrc = K0;
+  t.out_H = H; t.out_W = W; t.sy = t.sx = 1; t.oy_off = t.ox_off = 0;
+  const bool two = K0 < K;
+  IGM_TRY(encode_act(st, &t.a_hi, a_hi, K0, H, W, Bmax, false, t));
+  IGM_TRY(encode_act(st, &t.a_lo, a_lo, K0, H, W, Bmax, false, t));
+  IGM_TRY(encode_act(st, &t.a1_hi, two ? (void*)a1_hi : (void*)a_hi, two ? K - K0 : K0, H, W, Bmax, false, t));
+  IGM_TRY(encode_act(st, &t.a1_lo, two ? (void*)a1_lo : (void*)a_lo, two ? K - K0 : K0, H, W, Bmax, false, t));
+  t.valid = true;
+  return IGM_OK;
+}
+
+int tc_plan_strided(Status& st, TcConv& t, int K, int N, int SH, int SW, int Bmax, int KH, int pad,
+                    __nv_bfloat16* a_hi, __nv_bfloat16* a_lo, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo) {
+  t.valid = false;
+  if (!tc_strided_eligible(K, N, SH, SW, KH)) IGM_FAIL(st, IGM_ERR_INVALID, "shape not eligible for the strided tcgen05 conv");
+  const int GH = SH / 2, GW = SW / 2;
+  IGM_TRY(plan_common(st, t, K, K, N, GH, GW, Bmax, KH * KH, w_hi, w_lo));
+  t.KH = t.KW = KH; t.pad = pad;
+  t.ntaps = KH * KH;
+  // source row 2*oy - pad + ky = 2*(oy + dy) + py  with  py = (ky - pad) mod 2,  dy = floor((ky - pad) / 2)
+  auto split2 = [](int v, int& d, int& ph) { ph = ((v % 2) + 2) % 2; d = (v - ph) / 2; };
+  for (int ky = 0; ky < KH; ++ky)
+    for (int kx = 0; kx < KH; ++kx) {
+      TcTap tp;
+      split2(ky - pad, tp.dy, tp.py);
+      split2(kx - pad, tp.dx, tp.px);
+      tp.wtap = ky * KH + kx;
+      t.taps[ky * KH + kx] = tp;
+    }
+  t.Csrc = K;
+  t.out_H = GH; t.out_W = GW; t.sy = t.sx = 1; t.oy_off = t.ox_off = 0;
+  IGM_TRY(encode_act(st, &t.a_hi, a_hi, K, SH, SW, Bmax, true, t));
+  IGM_TRY(encode_act(st, &t.a_lo, a_lo, K, SH, SW, Bmax, true, t));
+  t.a1_hi = t.a_hi; t.a1_lo = t.a_lo;
+  t.valid = true;
+  return IGM_OK;
+}
+
+int tc_plan_phase(Status& st, TcConv& t, int K, int N, int GH, int GW, int Bmax, int KH, int pad, int py, int px,
+                  __nv_bfloat16* a_hi, __nv_bfloat16* a_lo, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo) {
+  t.valid = false;
+  if (K < KC || K % KC != 0 || N < 64 || N % 64 != 0 || !tile_grid_ok(GH, GW) || (KH != 3 && KH != 4))
+    IGM_FAIL(st, IGM_ERR_INVALID, "shape not eligible for the phase tcgen05 conv");
+  IGM_TRY(plan_common(st, t, K, K, N, GH, GW, Bmax, KH * KH, w_hi, w_lo));
+  t.KH = t.KW = KH; t.pad = pad;
+  // output row 2a + py receives source row (2a + py + pad - ky) / 2 = a + (py + pad - ky) / 2 for the ky of right parity
+  t.ntaps = 0;
+  for (int ky = 0; ky < KH; ++ky) {
+    if (((py + pad - ky) % 2 + 2) % 2 != 0) continue;
+    for (int kx = 0; kx < KH; ++kx) {
+      if (((px + pad - kx) % 2 + 2) % 2 != 0) continue;
+      TcTap tp;
+      tp.dy = (py + pad - ky) / 2; tp.dx = (px + pad - kx) / 2; tp.py = tp.px = 0;
+      tp.wtap = ky * KH + kx;
+      t.taps[t.ntaps++] = tp;
+    }
   }
-  // weights: [N rows][taps*K cols], K-major
-  for (int which = 0; which < 2; ++which) {
-    cuuint64_t dims[2] = {(cuuint64_t)KH * KH * K, (cuuint64_t)N};
-    cuuint64_t strides[1] = {(cuuint64_t)KH * KH * K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)t.BN};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(which ? &t.b_lo : &t.b_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, which ? (void*)w_lo : (void*)w_hi,
-                     dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled (weights) failed");
-  }
+  if (t.ntaps == 0) IGM_FAIL(st, IGM_ERR_INVALID, "phase without taps");
+  t.Csrc = K;
+  t.out_H = 2 * GH; t.out_W = 2 * GW; t.sy = t.sx = 2; t.oy_off = py; t.ox_off = px;
+  IGM_TRY(encode_act(st, &t.a_hi, a_hi, K, GH, GW, Bmax, false, t));
+  IGM_TRY(encode_act(st, &t.a_lo, a_lo, K, GH, GW, Bmax, false, t));
+  t.a1_hi = t.a_hi; t.a1_lo = t.a_lo;
   t.valid = true;
   return IGM_OK;
 }
@@ -401,7 +495,9 @@ int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r) {
     IGM_FAIL(*lc.st, IGM_ERR_INVALID, "conv_tc: bad output split");
   TcArgs a;
   a.B = r.B; a.H = t.H; a.W = t.W; a.K = t.K; a.K0 = t.K0; a.N = t.N; a.N0 = r.N0;
-  a.KH = t.KH; a.KW = t.KW; a.pad = t.pad;
+  a.ntaps = t.ntaps; a.Csrc = t.Csrc;
+  for (int i = 0; i < t.ntaps; ++i) a.taps[i] = t.taps[i];
+  a.out_H = t.out_H; a.out_W = t.out_W; a.sy = t.sy; a.sx = t.sx; a.oy_off = t.oy_off; a.ox_off = t.ox_off;
   a.BH = t.BH; a.BW = t.BW; a.BB = t.BB;
   a.tiles_per_img = (t.BB > 1) ? 1 : cdiv(t.H, t.BH);
   a.tiles_m = (t.BB > 1) ? cdiv(r.B, t.BB) : r.B * a.tiles_per_img;
@@ -409,8 +505,8 @@ int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r) {
   a.stage_tx_bytes = 2 * (t.BB * t.BH * t.BW * KC * 2) + 2 * (t.BN * KC * 2);
   a.bias = r.bias; a.out0 = r.out0; a.out1 = r.out1; a.add0 = r.add0; a.add1 = r.add1;
   a.hi0 = r.hi0; a.lo0 = r.lo0;
-  const double flops = 2.0 * r.B * t.H * t.W * (double)t.N * t.K * t.KH * t.KW;
-  const double bytes = 4.0 * ((double)r.B * t.H * t.W * (t.K + t.N * (r.add0 ? 2 : 1)) + (double)t.KH * t.KW * t.K * t.N);
+  const double flops = 2.0 * r.B * t.H * t.W * (double)t.N * t.K * t.ntaps;
+  const double bytes = 4.0 * ((double)r.B * t.H * t.W * (t.K + t.N * (r.add0 ? 2 : 1)) + (double)t.ntaps * t.K * t.N);
   ProfScope ps_(lc, r.kclass, flops, bytes);
   const int num_tiles = a.tiles_m * a.tiles_n;
   if (t.BN == 128) return launch_tc_impl<128>(lc, t, a, num_tiles);

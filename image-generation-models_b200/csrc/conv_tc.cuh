@@ -11,6 +11,14 @@ namespace igm {
 //   D[m, n] = sum_{tap, k} A[pix(m) + tap, k] * Wt[n, tap*K + k]
 // with every operand split into bf16 hi + lo parts ("bf16x3": hi*hi + hi*lo + lo*hi,
 // fp32 accumulation in TMEM) so the result is fp32-accurate to ~2^-17 relative.
+// One (tap) term of the implicit GEMM: the activation box is fetched at tile origin + (dx, dy) on the
+// source grid, from sub-lattice (px, py) when the source is read with stride 2 ("space-to-depth"
+// view), and multiplied by column block `wtap` of the packed weight matrix.
+struct TcTap {
+  int dx, dy, px, py, wtap;
+};
+constexpr int kTcMaxTaps = 16;
+
 struct TcConv {
   bool valid = false;
   // activations may come from two tensors concatenated along channels (skip connections):
@@ -20,9 +28,25 @@ struct TcConv {
   __nv_bfloat16* w_hi = nullptr;   // [N][taps*K]
   __nv_bfloat16* w_lo = nullptr;
   int K = 0, N = 0, KH = 1, KW = 1, pad = 0;
-  int H = 0, W = 0, Bmax = 0;
+  int H = 0, W = 0, Bmax = 0;           // tile grid (= output grid of one launch) per image
   int BH = 0, BW = 0, BB = 0, BN = 0;   // M-tile = BB images x BH rows x BW cols (<= 128 pixels)
+  int ntaps = 0;
+  TcTap taps[kTcMaxTaps];
+  int Csrc = 0;                         // channels of source 0 (sub-lattice px selects channel block px*Csrc)
+  // output pixel of tile position (oy, ox):  (oy*sy + oy_off, ox*sx + ox_off) on an out_H x out_W image
+  int out_H = 0, out_W = 0, sy = 1, sx = 1, oy_off = 0, ox_off = 0;
 };
+
+// Stride-2 convolution read (Conv2d k3 s2 p1 forward / ConvTranspose2d k4 s2 p1 data gradient):
+// source [Bmax, SH, SW, K] sampled at (2*oy - pad + ky, 2*ox - pad + kx); output grid SH/2 x SW/2.
+bool tc_strided_eligible(int K, int N, int SH, int SW, int KH);
+int tc_plan_strided(Status& st, TcConv& t, int K, int N, int SH, int SW, int Bmax, int KH, int pad,
+                    __nv_bfloat16* a_hi, __nv_bfloat16* a_lo, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo);
+// One output-parity phase (py, px) of a stride-2 transposed convolution (ConvTranspose2d k4 s2 p1
+// forward / Conv2d k3 s2 p1 data gradient): source grid GH x GW at unit stride, output written at
+// (2*a + py, 2*b + px) of a 2GH x 2GW image; only the taps ky with (py + pad - ky) even contribute.
+int tc_plan_phase(Status& st, TcConv& t, int K, int N, int GH, int GW, int Bmax, int KH, int pad, int py, int px,
+                  __nv_bfloat16* a_hi, __nv_bfloat16* a_lo, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo);
 
 // Can this (stride-1, non-dilated) conv run on the tensor-core engine?
 bool tc_eligible(int K, int N, int H, int W, int KH);
@@ -44,21 +68,35 @@ struct TcRun {
 };
 int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r);
 
-// Weight gradient of the same convolutions on the tensor cores (wgrad_tc.cu): pixels are the
-// reduction axis, fetched as 64-pixel TMA boxes of the bf16 hi/lo copies of dY and X.
+// Weight gradients on the tensor cores (wgrad_tc.cu).  Pixels are the reduction axis:
+//   G[tap][cs][cp] = sum_pixels S[pixel shifted by tap][cs] * P[pixel][cp]
+// S ("shifted") is fetched with the per-tap offsets / stride-2 sub-lattices of TcTap, P ("plain") is
+// walked pixel tile by pixel tile (64-pixel TMA boxes, optionally a 2-tensor channel concat).
+// The result is ACCUMULATED at grad[cs*s_shift + cp*s_plain + wtap] (PyTorch OIHW / IOHW directly).
 struct TcWgrad {
   bool valid = false;
-  alignas(64) CUtensorMap dy_hi, dy_lo, x_hi, x_lo, x1_hi, x1_lo;   // X may be a 2-tensor channel concat
-  int C0 = 0;
-  int Cin = 0, Cout = 0, KH = 1, KW = 1, pad = 0, H = 0, W = 0, Bmax = 0;
+  alignas(64) CUtensorMap s_hi, s_lo, p_hi, p_lo, p1_hi, p1_lo;
+  int CS = 0, CP = 0, P0 = 0;          // channels of S, of P, of P's first tensor
+  int GH = 0, GW = 0, Bmax = 0;        // pixel grid of P per image
   int BW = 0, BH = 0, BB = 0, rows = 0, BN = 0;
+  int ntaps = 0;
+  TcTap taps[kTcMaxTaps];
+  int64_t s_shift = 0, s_plain = 0;
+  double flops_per_image = 0;
 };
 bool tcw_eligible(int Cin, int Cout, int H, int W, int KH);
+// stride-1 KxK conv: S = dY [Bmax,H,W,Cout] (staging), P = X [Bmax,H,W,Cin] (optionally 2 tensors)
 int tcw_plan(Status& st, TcWgrad& t, int Cin, int Cout, int H, int W, int Bmax, int KH, int pad,
              __nv_bfloat16* dy_hi, __nv_bfloat16* dy_lo, __nv_bfloat16* x_hi, __nv_bfloat16* x_lo,
              int C0 = 0, __nv_bfloat16* x1_hi = nullptr, __nv_bfloat16* x1_lo = nullptr);
+// stride-2 gather (Conv2d k3 s2 p1: S = X, P = dY, grad OIHW; ConvTranspose2d k4 s2 p1: S = dY, P = X,
+// grad IOHW).  S lives on the fine grid [Bmax, 2GH, 2GW, CS], P on the coarse grid [Bmax, GH, GW, CP].
+bool tcw_strided_eligible(int CS, int CP, int GH, int GW, int KH);
+int tcw_plan_strided(Status& st, TcWgrad& t, int CS, int CP, int GH, int GW, int Bmax, int KH, int pad,
+                     __nv_bfloat16* s_hi, __nv_bfloat16* s_lo, __nv_bfloat16* p_hi, __nv_bfloat16* p_lo,
+                     int64_t s_shift, int64_t s_plain);
 bool tcw_batch_ok(const TcWgrad& t, int B);
-// grad (PyTorch OIHW fp32) += dW; dY / X must already be staged as bf16 hi/lo in the planned buffers
+// grad (fp32) += G; both operands must already be staged as bf16 hi/lo in the planned buffers
 int launch_wgrad_tc(const LaunchCtx& lc, const TcWgrad& t, int B, float* grad, int variant = 0);
 
 // fp32 [M, C] -> bf16 hi / lo written at channel offset `coff` of rows with `cdst` channels

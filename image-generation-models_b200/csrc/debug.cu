@@ -108,3 +108,107 @@ extern "C" int igm_debug_wgrad(int engine, int variant, const float* x, const fl
   cudaFree(dh); cudaFree(dl); cudaFree(xh); cudaFree(xl);
   return rc;
 }
+
+// Stride-2 resampling convolutions of the U-Net on either engine (kernel-level parity tests).
+//   kind 0: Downsample  Conv2d(C, C2, 3, stride 2, pad 1)           weight OIHW [C2][C][3][3]
+//   kind 1: Upsample    ConvTranspose2d(C, C2, 4, stride 2, pad 1)  weight IOHW [C][C2][4][4]
+//   mode 0: forward      x [B,H,W,C]        -> out [B,OH,OW,C2]   (+bias)
+//   mode 1: data grad    x = dY [B,OH,OW,C2] -> out = dX [B,H,W,C] (+add)
+//   mode 2: weight grad  x [B,H,W,C], aux = dY [B,OH,OW,C2]       -> out = dW (accumulated, weight layout)
+// (OH, OW) = (H/2, W/2) for kind 0 and (2H, 2W) for kind 1.
+extern "C" int igm_debug_resample(int engine, int kind, int mode, const float* x, const float* aux, const float* w,
+                                  const float* bias, const float* add, float* out, int B, int H, int W, int C, int C2,
+                                  void* stream) {
+  Status& st = global_status();
+  st = Status();
+  int64_t launches = 0;
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  lc.st = &st;
+  lc.counter = &launches;
+  const int K = kind == 0 ? 3 : 4, KK = K * K, pad = 1;
+  const int OH = kind == 0 ? H / 2 : 2 * H, OW = kind == 0 ? W / 2 : 2 * W;
+  const int64_t Min = (int64_t)B * H * W, Mout = (int64_t)B * OH * OW;
+  const int64_t nw = (int64_t)KK * C * C2;
+  int rc = IGM_OK;
+  // strides of (input channel ci in C, output channel co in C2) inside the PyTorch weight
+  const int64_t s_ci = kind == 0 ? KK : (int64_t)C2 * KK;
+  const int64_t s_co = kind == 0 ? (int64_t)C * KK : KK;
+  if (engine == 0) {
+    if (mode == 2) {
+      WgradArgs g;
+      if (kind == 0) { g.P = aux; g.PC = C2; g.PH = OH; g.PW = OW; g.Q = x; g.QC = C; g.QH = H; g.QW = W; g.sq = s_ci; g.sp = s_co; }
+      else { g.P = x; g.PC = C; g.PH = H; g.PW = W; g.Q = aux; g.QC = C2; g.QH = OH; g.QW = OW; g.sq = s_co; g.sp = s_ci; }
+      g.B = B; g.KH = g.KW = K; g.stride = 2; g.pad = pad; g.dil = 1; g.grad = out;
+      rc = launch_wgrad(lc, g);
+      cudaStreamSynchronize(lc.stream);
+      return rc;
+    }
+    float* wp = nullptr;
+    IGM_CUDA(st, cudaMalloc(&wp, nw * sizeof(float)));
+    ConvArgs a;
+    a.B = B; a.KH = a.KW = K; a.stride = 2; a.pad = pad; a.bias = bias; a.out0 = out; a.add0 = add;
+    if (mode == 0) {
+      rc = launch_pack_weight(lc, w, wp, KK, C, C2, s_ci, s_co);
+      a.in0 = x; a.C0 = C; a.IH = H; a.IW = W; a.OH = OH; a.OW = OW; a.N = a.N0 = C2; a.transposed = kind;
+    } else {
+      rc = launch_pack_weight(lc, w, wp, KK, C2, C, s_co, s_ci);
+      a.in0 = x; a.C0 = C2; a.IH = OH; a.IW = OW; a.OH = H; a.OW = W; a.N = a.N0 = C; a.transposed = 1 - kind;
+    }
+    a.w = wp;
+    if (rc == IGM_OK) rc = launch_conv(lc, a);
+    cudaStreamSynchronize(lc.stream);
+    cudaFree(wp);
+    return rc;
+  }
+  // ---- tcgen05 engine ----
+  __nv_bfloat16 *wh = nullptr, *wl = nullptr, *xh = nullptr, *xl = nullptr, *ah = nullptr, *al = nullptr;
+  IGM_CUDA(st, cudaMalloc(&wh, nw * 2));
+  IGM_CUDA(st, cudaMalloc(&wl, nw * 2));
+  const int64_t nx = (mode == 1) ? Mout * C2 : Min * C;
+  IGM_CUDA(st, cudaMalloc(&xh, nx * 2));
+  IGM_CUDA(st, cudaMalloc(&xl, nx * 2));
+  rc = launch_split_bf16(lc, x, mode == 1 ? Mout : Min, mode == 1 ? C2 : C, xh, xl, mode == 1 ? C2 : C, 0);
+  if (mode == 2) {
+    IGM_CUDA(st, cudaMalloc(&ah, Mout * C2 * 2));
+    IGM_CUDA(st, cudaMalloc(&al, Mout * C2 * 2));
+    if (rc == IGM_OK) rc = launch_split_bf16(lc, aux, Mout, C2, ah, al, C2, 0);
+    TcWgrad t;
+    if (rc == IGM_OK) {
+      if (kind == 0) rc = tcw_plan_strided(st, t, C, C2, OH, OW, B, K, pad, xh, xl, ah, al, s_ci, s_co);   // S = X (fine), P = dY
+      else rc = tcw_plan_strided(st, t, C2, C, H, W, B, K, pad, ah, al, xh, xl, s_co, s_ci);                  // S = dY (fine), P = X
+    }
+    if (rc == IGM_OK) rc = launch_wgrad_tc(lc, t, B, out);
+  } else {
+    // forward contracts over C (n = C2), data gradient over C2 (n = C); taps are never flipped here
+    if (mode == 0) { if (rc == IGM_OK) rc = launch_pack_weight_tc(lc, w, wh, wl, KK, C, C2, s_ci, s_co, 0); }
+    else { if (rc == IGM_OK) rc = launch_pack_weight_tc(lc, w, wh, wl, KK, C2, C, s_co, s_ci, 0); }
+    TcRun r;
+    r.B = B; r.bias = bias; r.out0 = out; r.add0 = add;
+    const bool strided = (kind == 0 && mode == 0) || (kind == 1 && mode == 1);
+    if (strided) {
+      TcConv t;
+      const int Kc = mode == 0 ? C : C2, N = mode == 0 ? C2 : C;
+      const int SH = mode == 0 ? H : OH, SW = mode == 0 ? W : OW;
+      if (rc == IGM_OK) rc = tc_plan_strided(st, t, Kc, N, SH, SW, B, K, pad, xh, xl, wh, wl);
+      r.N0 = N;
+      if (rc == IGM_OK) rc = launch_conv_tc(lc, t, r);
+    } else {
+      const int Kc = mode == 0 ? C : C2, N = mode == 0 ? C2 : C;
+      const int GH = mode == 0 ? H : OH, GW = mode == 0 ? W : OW;
+      r.N0 = N;
+      for (int ph = 0; ph < 4 && rc == IGM_OK; ++ph) {
+        TcConv t;
+        rc = tc_plan_phase(st, t, Kc, N, GH, GW, B, K, pad, ph / 2, ph % 2, xh, xl, wh, wl);
+        if (rc == IGM_OK) rc = launch_conv_tc(lc, t, r);
+      }
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(lc.stream);
+  if (rc == IGM_OK && e != cudaSuccess) {
+    set_error(st, IGM_ERR_CUDA, __FILE__, __LINE__, cudaGetErrorString(e));
+    rc = IGM_ERR_CUDA;
+  }
+  cudaFree(wh); cudaFree(wl); cudaFree(xh); cudaFree(xl); cudaFree(ah); cudaFree(al);
+  return rc;
+}

@@ -27,11 +27,14 @@ constexpr int BOX_BYTES = PIX * 128;    // one 64-channel x 64-pixel bf16 box
 constexpr int UMMA_K = 16;
 
 struct WArgs {
-  int B, H, W, Cin, C0, Cout, KH, KW, pad;
+  int B, H, W, CS, CP, P0;
+  int ntaps;
+  TcTap taps[kTcMaxTaps];
+  int64_t s_shift, s_plain;
   int BW, BH, BB, rows;
   int tiles_per_img, n_ptiles;
   int n_pairs, n_ci_tiles, splits, tiles_per_split;
-  int cob;            // Cout / 64
+  int cob;            // CS / 64
   int zero_smem;      // rows < 64: stale smem rows must read as zero (they are reduced over)
   int variant;        // descriptor-convention switch for bring-up tests (0 = canonical)
   float* grad;
@@ -51,6 +54,7 @@ __global__ void __launch_bounds__(192, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tdy_hi, const __grid_constant__ CUtensorMap tdy_lo,
                 const __grid_constant__ CUtensorMap tx_hi, const __grid_constant__ CUtensorMap tx_lo,
                 const __grid_constant__ CUtensorMap tx1_hi, const __grid_constant__ CUtensorMap tx1_lo, const WArgs p) {
+  // tdy_* = the SHIFTED operand S (A blocks), tx_* / tx1_* = the PLAIN operand P (B blocks)
   using C = WCfg<NB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -68,7 +72,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tdy_hi, const __grid_constan
   bid /= p.splits;
   const int ci_tile = bid % p.n_ci_tiles;
   const int pair = bid / p.n_ci_tiles;
-  const int ntaps = p.KH * p.KW;
+  const int ntaps = p.ntaps;
   int blk_tap[2], blk_co0[2];
   bool blk_ok[2];
 #pragma unroll
@@ -119,20 +123,22 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tdy_hi, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             if (!blk_ok[j]) continue;
-            const int ky = blk_tap[j] / p.KW, kx = blk_tap[j] - ky * p.KW;
-            // dY shifted by (pad - ky, pad - kx); out-of-image pixels are zero-filled by the TMA unit
-            tma_load_4d(st + j * BOX_BYTES, &tdy_hi, &full[stage], blk_co0[j], p.pad - kx, y0 + p.pad - ky, b0);
-            tma_load_4d(st + (2 + j) * BOX_BYTES, &tdy_lo, &full[stage], blk_co0[j], p.pad - kx, y0 + p.pad - ky, b0);
+            const TcTap tp = p.taps[blk_tap[j]];
+            // S shifted by the tap (and taken from sub-lattice (px, py) for stride-2 gathers);
+            // out-of-image pixels are zero-filled by the TMA unit
+            const int cc = blk_co0[j] + tp.px * p.CS;
+            tma_load_5d(st + j * BOX_BYTES, &tdy_hi, &full[stage], cc, tp.dx, tp.py, y0 + tp.dy, b0);
+            tma_load_5d(st + (2 + j) * BOX_BYTES, &tdy_lo, &full[stage], cc, tp.dx, tp.py, y0 + tp.dy, b0);
           }
 #pragma unroll
           for (int nb = 0; nb < NB; ++nb) {
             const int c0 = ci_tile * C::BN + nb * 64;
-            if (c0 < p.C0) {
-              tma_load_4d(st + (4 + nb) * BOX_BYTES, &tx_hi, &full[stage], c0, 0, y0, b0);
-              tma_load_4d(st + (4 + NB + nb) * BOX_BYTES, &tx_lo, &full[stage], c0, 0, y0, b0);
+            if (c0 < p.P0) {
+              tma_load_5d(st + (4 + nb) * BOX_BYTES, &tx_hi, &full[stage], c0, 0, 0, y0, b0);
+              tma_load_5d(st + (4 + NB + nb) * BOX_BYTES, &tx_lo, &full[stage], c0, 0, 0, y0, b0);
             } else {   // second tensor of a channel concat
-              tma_load_4d(st + (4 + nb) * BOX_BYTES, &tx1_hi, &full[stage], c0 - p.C0, 0, y0, b0);
-              tma_load_4d(st + (4 + NB + nb) * BOX_BYTES, &tx1_lo, &full[stage], c0 - p.C0, 0, y0, b0);
+              tma_load_5d(st + (4 + nb) * BOX_BYTES, &tx1_hi, &full[stage], c0 - p.P0, 0, 0, y0, b0);
+              tma_load_5d(st + (4 + NB + nb) * BOX_BYTES, &tx1_lo, &full[stage], c0 - p.P0, 0, 0, y0, b0);
             }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -173,19 +179,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tdy_hi, const __grid_constan
       const int q = warp & 3;
       const int row = q * 32 + lane;
       const int j = row >> 6;
-      const int co = blk_co0[j] + (row & 63);
-      const int KK = ntaps;
+      const int cs = blk_co0[j] + (row & 63);
       mbar_wait(acc_full, 0);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16);
-      float* g = p.grad + ((int64_t)co * p.Cin + ci_tile * C::BN) * KK + blk_tap[j];
+      float* g = p.grad + (int64_t)cs * p.s_shift + (int64_t)(ci_tile * C::BN) * p.s_plain + p.taps[blk_tap[j]].wtap;
 #pragma unroll 1
       for (int c0 = 0; c0 < C::BN; c0 += 32) {
         float v[32];
         tmem_ld_32x32(t_base + (uint32_t)c0, v);
         if (blk_ok[j]) {
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) atomicAdd(g + (int64_t)(c0 + jj) * KK, v[jj]);
+          for (int jj = 0; jj < 32; ++jj) atomicAdd(g + (int64_t)(c0 + jj) * p.s_plain, v[jj]);
         }
       }
     }
@@ -219,7 +224,7 @@ int launch_impl(const LaunchCtx& lc, const TcWgrad& t, const WArgs& a, int grid)
     if (e != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(e));
     attr_done = true;
   }
-  wgrad_tc_kernel<NB><<<grid, 192, C::SMEM_BYTES, lc.stream>>>(t.dy_hi, t.dy_lo, t.x_hi, t.x_lo, t.x1_hi, t.x1_lo, a);
+  wgrad_tc_kernel<NB><<<grid, 192, C::SMEM_BYTES, lc.stream>>>(t.s_hi, t.s_lo, t.p_hi, t.p_lo, t.p1_hi, t.p1_lo, a);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }
@@ -233,6 +238,46 @@ bool tcw_eligible(int Cin, int Cout, int H, int W, int KH) {
   return true;
 }
 
+bool tcw_strided_eligible(int CS, int CP, int GH, int GW, int KH) {
+  if (CS < 64 || CS % 64 != 0 || CP < 64 || CP % 64 != 0) return false;
+  if (KH != 3 && KH != 4) return false;
+  return GW >= 1 && GW <= PIX && GH >= 1;
+}
+
+namespace {
+
+void tile_shape(TcWgrad& t, int GH, int GW, int Bmax) {
+  t.GH = GH; t.GW = GW; t.Bmax = Bmax;
+  t.BW = GW;
+  if (GH * GW <= PIX) { t.BH = GH; t.BB = PIX / (GH * GW); }
+  else { t.BH = PIX / GW; t.BB = 1; }
+  if (t.BB > Bmax) t.BB = Bmax;
+  t.rows = t.BB * t.BH * t.BW;
+}
+
+// rank-5 descriptor (channel, x, sub-lattice row, y, image) of a [Bmax, SH, SW, C] bf16 tensor; see conv_tc.cu
+int encode_act5(Status& st, CUtensorMap* m, void* ptr, int C, int SH, int SW, int Bmax, bool s2d, const TcWgrad& t) {
+  auto enc = encode_fn();
+  if (!enc) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t rowB = (cuuint64_t)SW * C * 2;
+  cuuint64_t dims[5], strides[4];
+  if (!s2d) {
+    dims[0] = C; dims[1] = SW; dims[2] = 1; dims[3] = SH; dims[4] = Bmax;
+    strides[0] = (cuuint64_t)C * 2; strides[1] = rowB; strides[2] = rowB; strides[3] = rowB * SH;
+  } else {
+    dims[0] = 2 * (cuuint64_t)C; dims[1] = SW / 2; dims[2] = 2; dims[3] = SH / 2; dims[4] = Bmax;
+    strides[0] = (cuuint64_t)C * 4; strides[1] = rowB; strides[2] = 2 * rowB; strides[3] = rowB * SH;
+  }
+  cuuint32_t box[5] = {64u, (cuuint32_t)t.BW, 1u, (cuuint32_t)t.BH, (cuuint32_t)t.BB};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled (wgrad) failed");
+  return IGM_OK;
+}
+
+}  // namespace
+
 int tcw_plan(Status& st, TcWgrad& t, int Cin, int Cout, int H, int W, int Bmax, int KH, int pad, __nv_bfloat16* dy_hi,
              __nv_bfloat16* dy_lo, __nv_bfloat16* x_hi, __nv_bfloat16* x_lo, int C0, __nv_bfloat16* x1_hi,
              __nv_bfloat16* x1_lo) {
@@ -240,29 +285,54 @@ int tcw_plan(Status& st, TcWgrad& t, int Cin, int Cout, int H, int W, int Bmax, 
   if (!tcw_eligible(Cin, Cout, H, W, KH)) IGM_FAIL(st, IGM_ERR_INVALID, "shape not eligible for the tcgen05 wgrad engine");
   if (C0 <= 0 || !x1_hi) C0 = Cin;
   if (C0 % 64 != 0 || (Cin - C0) % 64 != 0) IGM_FAIL(st, IGM_ERR_INVALID, "concat split must be a multiple of 64 channels");
-  auto enc = encode_fn();
-  if (!enc) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  t.Cin = Cin; t.C0 = C0; t.Cout = Cout; t.KH = t.KW = KH; t.pad = pad; t.H = H; t.W = W; t.Bmax = Bmax;
-  t.BW = W;
-  if (H * W <= PIX) { t.BH = H; t.BB = PIX / (H * W); }
-  else { t.BH = PIX / W; t.BB = 1; }
-  if (t.BB > Bmax) t.BB = Bmax;
-  t.rows = t.BB * t.BH * t.BW;
+  tile_shape(t, H, W, Bmax);
+  t.CS = Cout; t.CP = Cin; t.P0 = C0;
   t.BN = (Cin % 128 == 0) ? 128 : 64;
+  const int KK = KH * KH;
+  // dW[co][ci][ky][kx] = sum dY[iy + pad - ky, ix + pad - kx, co] * X[iy, ix, ci]
+  t.ntaps = KK;
+  for (int ky = 0; ky < KH; ++ky)
+    for (int kx = 0; kx < KH; ++kx) t.taps[ky * KH + kx] = TcTap{pad - kx, pad - ky, 0, 0, ky * KH + kx};
+  t.s_shift = (int64_t)Cin * KK;   // co stride in OIHW
+  t.s_plain = KK;                  // ci stride
+  t.flops_per_image = 2.0 * H * W * (double)Cin * Cout * KK;
   const bool two = C0 < Cin;
-  struct { CUtensorMap* m; void* ptr; int C; } maps[6] = {
-      {&t.dy_hi, dy_hi, Cout}, {&t.dy_lo, dy_lo, Cout}, {&t.x_hi, x_hi, C0}, {&t.x_lo, x_lo, C0},
-      {&t.x1_hi, two ? (void*)x1_hi : (void*)x_hi, two ? Cin - C0 : C0},
-      {&t.x1_lo, two ? (void*)x1_lo : (void*)x_lo, two ? Cin - C0 : C0}};
-  for (auto& m : maps) {
-    cuuint64_t dims[4] = {(cuuint64_t)m.C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Bmax};
-    cuuint64_t strides[3] = {(cuuint64_t)m.C * 2, (cuuint64_t)W * m.C * 2, (cuuint64_t)H * W * m.C * 2};
-    cuuint32_t box[4] = {64u, (cuuint32_t)t.BW, (cuuint32_t)t.BH, (cuuint32_t)t.BB};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(m.m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, m.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled (wgrad) failed");
-  }
+  IGM_TRY(encode_act5(st, &t.s_hi, dy_hi, Cout, H, W, Bmax, false, t));
+  IGM_TRY(encode_act5(st, &t.s_lo, dy_lo, Cout, H, W, Bmax, false, t));
+  IGM_TRY(encode_act5(st, &t.p_hi, x_hi, C0, H, W, Bmax, false, t));
+  IGM_TRY(encode_act5(st, &t.p_lo, x_lo, C0, H, W, Bmax, false, t));
+  IGM_TRY(encode_act5(st, &t.p1_hi, two ? (void*)x1_hi : (void*)x_hi, two ? Cin - C0 : C0, H, W, Bmax, false, t));
+  IGM_TRY(encode_act5(st, &t.p1_lo, two ? (void*)x1_lo : (void*)x_lo, two ? Cin - C0 : C0, H, W, Bmax, false, t));
+  t.valid = true;
+  return IGM_OK;
+}
+
+int tcw_plan_strided(Status& st, TcWgrad& t, int CS, int CP, int GH, int GW, int Bmax, int KH, int pad,
+                     __nv_bfloat16* s_hi, __nv_bfloat16* s_lo, __nv_bfloat16* p_hi, __nv_bfloat16* p_lo,
+                     int64_t s_shift, int64_t s_plain) {
+  t.valid = false;
+  if (!tcw_strided_eligible(CS, CP, GH, GW, KH)) IGM_FAIL(st, IGM_ERR_INVALID, "shape not eligible for the strided tcgen05 wgrad");
+  tile_shape(t, GH, GW, Bmax);
+  t.CS = CS; t.CP = CP; t.P0 = CP;
+  t.BN = (CP % 128 == 0) ? 128 : 64;
+  // G[ky][kx][cs][cp] = sum_{a,b} S[2a - pad + ky, 2b - pad + kx, cs] * P[a, b, cp]
+  t.ntaps = KH * KH;
+  auto split2 = [](int v, int& d, int& ph) { ph = ((v % 2) + 2) % 2; d = (v - ph) / 2; };
+  for (int ky = 0; ky < KH; ++ky)
+    for (int kx = 0; kx < KH; ++kx) {
+      TcTap tp;
+      split2(ky - pad, tp.dy, tp.py);
+      split2(kx - pad, tp.dx, tp.px);
+      tp.wtap = ky * KH + kx;
+      t.taps[ky * KH + kx] = tp;
+    }
+  t.s_shift = s_shift; t.s_plain = s_plain;
+  t.flops_per_image = 2.0 * GH * GW * (double)CS * CP * KH * KH;
+  IGM_TRY(encode_act5(st, &t.s_hi, s_hi, CS, 2 * GH, 2 * GW, Bmax, true, t));
+  IGM_TRY(encode_act5(st, &t.s_lo, s_lo, CS, 2 * GH, 2 * GW, Bmax, true, t));
+  IGM_TRY(encode_act5(st, &t.p_hi, p_hi, CP, GH, GW, Bmax, false, t));
+  IGM_TRY(encode_act5(st, &t.p_lo, p_lo, CP, GH, GW, Bmax, false, t));
+  t.p1_hi = t.p_hi; t.p1_lo = t.p_lo;
   t.valid = true;
   return IGM_OK;
 }
@@ -272,13 +342,16 @@ bool tcw_batch_ok(const TcWgrad& t, int B) { return t.valid && B >= 1 && B <= t.
 int launch_wgrad_tc(const LaunchCtx& lc, const TcWgrad& t, int B, float* grad, int variant) {
   if (!tcw_batch_ok(t, B)) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "wgrad_tc: batch must be a multiple of the images per box");
   WArgs a;
-  a.B = B; a.H = t.H; a.W = t.W; a.Cin = t.Cin; a.C0 = t.C0; a.Cout = t.Cout; a.KH = t.KH; a.KW = t.KW; a.pad = t.pad;
+  a.B = B; a.H = t.GH; a.W = t.GW; a.CS = t.CS; a.CP = t.CP; a.P0 = t.P0;
+  a.ntaps = t.ntaps;
+  for (int i = 0; i < t.ntaps; ++i) a.taps[i] = t.taps[i];
+  a.s_shift = t.s_shift; a.s_plain = t.s_plain;
   a.BW = t.BW; a.BH = t.BH; a.BB = t.BB; a.rows = t.rows;
-  a.tiles_per_img = (t.BB > 1) ? 1 : cdiv(t.H, t.BH);
+  a.tiles_per_img = (t.BB > 1) ? 1 : cdiv(t.GH, t.BH);
   a.n_ptiles = (t.BB > 1) ? B / t.BB : B * a.tiles_per_img;
-  a.cob = t.Cout / 64;
-  a.n_pairs = cdiv(t.KH * t.KW * a.cob, 2);
-  a.n_ci_tiles = t.Cin / t.BN;
+  a.cob = t.CS / 64;
+  a.n_pairs = cdiv(t.ntaps * a.cob, 2);
+  a.n_ci_tiles = t.CP / t.BN;
   const int base = a.n_pairs * a.n_ci_tiles;
   int splits = (2 * 148 + base - 1) / base;
   if (splits > a.n_ptiles) splits = a.n_ptiles;
@@ -288,8 +361,8 @@ int launch_wgrad_tc(const LaunchCtx& lc, const TcWgrad& t, int B, float* grad, i
   a.zero_smem = t.rows < PIX ? 1 : 0;
   a.variant = variant;
   a.grad = grad;
-  const double flops = 2.0 * B * t.H * t.W * (double)t.Cin * t.Cout * t.KH * t.KW;
-  const double bytes = 4.0 * ((double)B * t.H * t.W * (t.Cin + t.Cout) + (double)t.KH * t.KW * t.Cin * t.Cout);
+  const double flops = t.flops_per_image * B;
+  const double bytes = 4.0 * ((double)B * t.GH * t.GW * (t.CS + t.CP) + (double)t.ntaps * t.CS * t.CP);
   ProfScope ps_(lc, K_CONV_WGRAD, flops, bytes);
   const int grid = base * a.splits;
   if (t.BN == 128) return launch_impl<2>(lc, t, a, grid);

@@ -197,6 +197,13 @@ int igm_debug_conv(int engine, int mode, const float* x, const float* w_oihw, co
  * x[B,H,W,Cin], dy[B,H,W,Cout] NHWC.  variant is a bring-up switch of the tcgen05 path (use 0). */
 int igm_debug_wgrad(int engine, int variant, const float* x, const float* dy, float* gw, int B, int H,
                     int W, int Cin, int Cout, int K, void* stream);
+/* The stride-2 resampling convs (kind 0: Conv2d(C,C2,3,2,1) weight OIHW; kind 1:
+ * ConvTranspose2d(C,C2,4,2,1) weight IOHW) on either engine, NHWC fp32:
+ *   mode 0 forward x[B,H,W,C] -> out[B,OH,OW,C2] (+bias); mode 1 data gradient x = dY -> out = dX (+add);
+ *   mode 2 weight gradient (x, aux = dY) -> out = dW in the weight's own layout, ACCUMULATED. */
+int igm_debug_resample(int engine, int kind, int mode, const float* x, const float* aux, const float* w,
+                       const float* bias, const float* add, float* out, int B, int H, int W, int C, int C2,
+                       void* stream);
 /* Which conv engine is active: 0 = SIMT fp32 implicit GEMM, 1 = tcgen05 bf16x3 (default when
  * the layer shapes allow it; environment IGM_CONV_ENGINE=0 forces the SIMT engine). */
 int igm_set_conv_engine(igm_ctx* ctx, int engine);

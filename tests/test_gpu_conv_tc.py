@@ -118,3 +118,63 @@ def test_wgrad_tc(shape):
     tc = _wgrad(1, 0, x.cuda(), dy.cuda(), B, H, W, Cin, Cout, K).cpu()
     l2, mx = rel_err(tc, ref)
     assert l2 < 1e-4 and mx < 1e-4, f"tcgen05 wgrad: rel-L2 {l2:.2e} max-rel {mx:.2e}"
+
+
+RSHAPES = [
+    # kind, B, H, W, C, C2     (H, W = INPUT size of the layer)
+    (0, 2, 32, 32, 64, 64),      # Downsample 32 -> 16
+    (0, 4, 16, 16, 128, 128),    # Downsample 16 -> 8 (two images per tile)
+    (0, 2, 28, 28, 128, 128),    # ragged 14x14 output
+    (0, 1, 64, 64, 64, 64),      # CelebA 64 -> 32
+    (1, 4, 8, 8, 128, 128),      # Upsample 8 -> 16
+    (1, 2, 16, 16, 64, 64),      # Upsample 16 -> 32
+    (1, 2, 14, 14, 128, 128),    # ragged
+    (1, 3, 8, 8, 256, 64),       # C != C2 (not in the U-Net, exercises the layout strides)
+]
+
+
+def _resample(engine, kind, mode, x, aux, w, bias, add, B, H, W, Cc, C2):
+    lib = _lib.load()
+    OH, OW = (H // 2, W // 2) if kind == 0 else (2 * H, 2 * W)
+    if mode == 0:
+        out = torch.empty(B, OH, OW, C2, device="cuda")
+    elif mode == 1:
+        out = torch.empty(B, H, W, Cc, device="cuda")
+    else:
+        out = torch.zeros_like(w)
+    p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    rc = lib.igm_debug_resample(engine, kind, mode, p(x), p(aux), p(w), p(bias), p(add), p(out), B, H, W, Cc, C2, None)
+    assert rc == 0, lib.igm_last_error(None).decode()
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("shape", RSHAPES)
+def test_resample_tc(shape):
+    kind, B, H, W, Cc, C2 = shape
+    K = 3 if kind == 0 else 4
+    OH, OW = (H // 2, W // 2) if kind == 0 else (2 * H, 2 * W)
+    g = torch.Generator().manual_seed(3 + hash(shape) % 1000)
+    x = torch.randn(B, H, W, Cc, generator=g)
+    dy = torch.randn(B, OH, OW, C2, generator=g)
+    wshape = (C2, Cc, K, K) if kind == 0 else (Cc, C2, K, K)
+    w = torch.randn(wshape, generator=g) / (Cc * K * K / (1 if kind == 0 else 4)) ** 0.5
+    bias = torch.randn(C2, generator=g)
+    add = torch.randn(B, H, W, Cc, generator=g)
+    xr = x.permute(0, 3, 1, 2).double().requires_grad_(True)
+    wr = w.double().requires_grad_(True)
+    if kind == 0:
+        y = F.conv2d(xr, wr, bias.double(), stride=2, padding=1)
+    else:
+        y = F.conv_transpose2d(xr, wr, bias.double(), stride=2, padding=1)
+    gx, gw = torch.autograd.grad(y, [xr, wr], dy.permute(0, 3, 1, 2).double())
+    ref = {0: y.detach().permute(0, 2, 3, 1), 1: gx.permute(0, 2, 3, 1) + add.double(), 2: gw}
+    xs, dys, ws, bs, ads = x.cuda(), dy.cuda(), w.cuda(), bias.cuda(), add.cuda()
+    for mode in (0, 1, 2):
+        args = {0: (xs, None, ws, bs, None), 1: (dys, None, ws, None, ads), 2: (xs, dys, ws, None, None)}[mode]
+        simt = _resample(0, kind, mode, *args, B, H, W, Cc, C2).cpu()
+        l2s, mxs = rel_err(simt, ref[mode])
+        assert l2s < 1e-5 and mxs < 1e-5, f"SIMT kind {kind} mode {mode}: {l2s:.2e} {mxs:.2e}"
+        tc = _resample(1, kind, mode, *args, B, H, W, Cc, C2).cpu()
+        l2, mx = rel_err(tc, ref[mode])
+        assert l2 < 1e-4 and mx < 1e-4, f"tcgen05 kind {kind} mode {mode}: rel-L2 {l2:.2e} max-rel {mx:.2e}"
