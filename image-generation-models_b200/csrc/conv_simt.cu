@@ -372,6 +372,60 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a, int pix_p
   }
 }
 
+// Weight gradient of the stem conv (C_in = 1..4 image channels, 3x3, stride 1, pad 1):
+//   dW[co][ci][ky][kx] += sum_pix dY[pix][co] * X[pix + (ky-1, kx-1)][ci]
+// The generic 64x64-tile kernel wastes >90 % of its tile on 3 input channels; here a thread owns one
+// output channel and keeps its 9*C_in partial sums in registers.  grid (pixel splits, C_out/64).
+template <int CI>
+__global__ void __launch_bounds__(256) wgrad_stem_kernel(const float* __restrict__ X, const float* __restrict__ dY,
+                                                         float* __restrict__ grad, int B, int H, int W, int Cout,
+                                                         int pix_per_cta) {
+  __shared__ float red[4][64][9 * CI + 1];
+  const int co = blockIdx.y * 64 + (threadIdx.x & 63);
+  const int lane4 = threadIdx.x >> 6;
+  const int64_t npix = (int64_t)B * H * W;
+  const int64_t p0 = (int64_t)blockIdx.x * pix_per_cta;
+  int64_t p1 = p0 + pix_per_cta;
+  if (p1 > npix) p1 = npix;
+  float acc[9 * CI];
+#pragma unroll
+  for (int i = 0; i < 9 * CI; ++i) acc[i] = 0.f;
+  if (co < Cout) {
+    for (int64_t p = p0 + lane4; p < p1; p += 4) {
+      const float g = __ldg(dY + p * Cout + co);
+      const int b = (int)(p / (H * W));
+      const int r = (int)(p - (int64_t)b * H * W);
+      const int y = r / W, x = r - y * W;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = y + ky - 1;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = x + kx - 1;
+          if (ix < 0 || ix >= W) continue;
+          const float* xp = X + (((int64_t)b * H + iy) * W + ix) * CI;
+#pragma unroll
+          for (int ci = 0; ci < CI; ++ci) acc[(ky * 3 + kx) * CI + ci] = fmaf(g, __ldg(xp + ci), acc[(ky * 3 + kx) * CI + ci]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 9 * CI; ++i) red[lane4][threadIdx.x & 63][i] = acc[i];
+  __syncthreads();
+  if (lane4 == 0 && co < Cout) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int ci = 0; ci < CI; ++ci) {
+        const int i = t * CI + ci;
+        const float v = red[0][threadIdx.x][i] + red[1][threadIdx.x][i] + red[2][threadIdx.x][i] + red[3][threadIdx.x][i];
+        atomicAdd(grad + ((int64_t)co * CI + ci) * 9 + t, v);   // OIHW
+      }
+  }
+}
+
 // out[n] += sum_m x[m, n]; grid.x = row splits; block (32 x 8): 32 columns x 8 row lanes
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int64_t M, int N,
                                                      float* __restrict__ out, int rows_per_cta) {
@@ -432,6 +486,23 @@ int launch_conv(const LaunchCtx& lc, const ConvArgs& a) {
 
 int launch_wgrad(const LaunchCtx& lc, const WgradArgs& a) {
   const int64_t npix = (int64_t)a.B * a.PH * a.PW;
+  if (a.QC <= 4 && a.KH == 3 && a.KW == 3 && a.stride == 1 && a.pad == 1 && a.dil == 1 && a.PH == a.QH && a.PW == a.QW &&
+      a.sq == 9 && a.sp == (int64_t)a.QC * 9) {
+    // stem: few input channels gathered (Q), C_out enumerated (P)
+    int ctas = 148 * 4;
+    int per = (int)cdiv64(npix, ctas);
+    per = (per + 3) & ~3;
+    dim3 grid((unsigned)cdiv64(npix, per), (unsigned)cdiv(a.PC, 64));
+    ProfScope ps_(lc, K_CONV_WGRAD, 2.0 * npix * (double)a.PC * a.QC * 9, 4.0 * npix * (a.PC + a.QC));
+    switch (a.QC) {
+      case 1: wgrad_stem_kernel<1><<<grid, 256, 0, lc.stream>>>(a.Q, a.P, a.grad, a.B, a.PH, a.PW, a.PC, per); break;
+      case 2: wgrad_stem_kernel<2><<<grid, 256, 0, lc.stream>>>(a.Q, a.P, a.grad, a.B, a.PH, a.PW, a.PC, per); break;
+      case 3: wgrad_stem_kernel<3><<<grid, 256, 0, lc.stream>>>(a.Q, a.P, a.grad, a.B, a.PH, a.PW, a.PC, per); break;
+      default: wgrad_stem_kernel<4><<<grid, 256, 0, lc.stream>>>(a.Q, a.P, a.grad, a.B, a.PH, a.PW, a.PC, per); break;
+    }
+    IGM_POST_LAUNCH(lc);
+    return IGM_OK;
+  }
   const int q_tiles = cdiv(a.QC, WB), p_tiles = cdiv(a.PC, WB);
   const int taps = a.KH * a.KW;
   // aim for ~4 CTAs per SM in total

@@ -89,6 +89,10 @@ struct ConvL {
   bool bias_in_norm = false;   // bias gradient is produced by the GroupNorm backward that follows this conv
   const Act* src0 = nullptr;   // input tensor(s) of the layer (wired once the plan is final)
   const Act* src1 = nullptr;
+  // stride-2 resampling convs on the tcgen05 engine (ResampleL holds the plans)
+  int rs_kind = 0;             // 0: not a resample conv, 1: Conv2d k3 s2 p1, 2: ConvTranspose2d k4 s2 p1
+  bool rs_ok = false;          // shapes eligible (bf16 weight buffers allocated)
+  bool rs_f_valid = false, rs_b_valid = false;
 };
 
 struct BlockL {
@@ -132,6 +136,10 @@ struct ResampleL {
   Act out;
   bool present = false;
   const Act* in = nullptr;
+  // tcgen05 plans: forward / data gradient are either one strided conv or four output-parity phases
+  TcConv tcf[4], tcb[4];
+  int n_tcf = 0, n_tcb = 0;
+  TcWgrad tcw;
 };
 
 struct Stage {
@@ -335,6 +343,24 @@ struct PlanBuilder {
     if (training) maxDy = std::max(maxDy, M(H, W) * Cout);   // the GroupNorm backward stages dy for every block
     return b;
   }
+  // bf16 weight buffers + staging room of a stride-2 resampling conv eligible for the tcgen05 engine
+  void rs_alloc(ResampleL& rs, int kind) {
+    ConvL& l = rs.conv;
+    l.rs_kind = kind;
+    const int C = l.Cin;
+    const int gh = kind == 1 ? rs.out.H : rs.Hin, gw = kind == 1 ? rs.out.W : rs.Win;   // coarse grid
+    l.rs_ok = (l.Cin == l.Cout) && C % 64 == 0 && gw <= 64 && (kind == 2 || (rs.Hin % 2 == 0 && rs.Win % 2 == 0));
+    if (!l.rs_ok) return;
+    const int64_t nw = (int64_t)l.K * l.K * l.Cin * l.Cout;
+    l.wf_hi = reinterpret_cast<__nv_bfloat16*>(ar.alloc((nw + 1) / 2));
+    l.wf_lo = reinterpret_cast<__nv_bfloat16*>(ar.alloc((nw + 1) / 2));
+    if (training) {
+      l.wb_hi = reinterpret_cast<__nv_bfloat16*>(ar.alloc((nw + 1) / 2));
+      l.wb_lo = reinterpret_cast<__nv_bfloat16*>(ar.alloc((nw + 1) / 2));
+      maxDy = std::max(maxDy, M(rs.out.H, rs.out.W) * l.Cout);
+    }
+    (void)gh;
+  }
   void track(int H, int W, int C) {
     maxMC = std::max(maxMC, M(H, W) * C);
     maxM = std::max(maxM, M(H, W));
@@ -426,6 +452,7 @@ struct PlanBuilder {
         s.rs.out = act(co, H, W, true);
         tap(p + ".3.out", s.rs.out.v, co, H, W);
         track(H, W, co);
+        rs_alloc(s.rs, 1);
       }
     }
     // ups are registered before the mid blocks in the reference (ddpm.py:195-196)
@@ -448,6 +475,7 @@ struct PlanBuilder {
         s.rs.out = act(ci, Hu, Wu, true);
         tap(p + ".3.out", s.rs.out.v, ci, Hu, Wu);
         track(Hu, Wu, ci);
+        rs_alloc(s.rs, 2);
       }
     }
     const int mid = c.dims.back();
@@ -713,12 +741,35 @@ struct Runner {
   }
 
   int resample_fwd(ResampleL& rs) {
+    if (tc_on() && rs.n_tcf > 0) {
+      TcRun r;
+      r.B = B; r.bias = c.Pp(rs.conv.pb); r.out0 = rs.out.v; r.N0 = rs.conv.Cout; r.kclass = K_CONV_FPROP;
+      r.hi0 = hi(rs.out); r.lo0 = lo(rs.out);
+      for (int i = 0; i < rs.n_tcf; ++i) IGM_TRY(launch_conv_tc(lc, rs.tcf[i], r));
+      return IGM_OK;
+    }
     return conv_fwd(rs.conv, rs.Hin, rs.Win, rs.out.H, rs.out.W, 2, 1, rs.out.v, nullptr, &rs.out);
   }
   // weight/bias gradients + data gradient (into rs.in->g, plus an optional addend) of a resample conv
   int resample_bwd(ResampleL& rs, const float* add) {
-    IGM_TRY(conv_wgrad(rs.conv, rs.Hin, rs.Win, rs.out.g, rs.out.H, rs.out.W, 2, 1));
-    return conv_dgrad(rs.conv, rs.out.g, rs.out.H, rs.out.W, rs.Hin, rs.Win, 2, 1, rs.in->g, rs.in->C, nullptr, 0, add,
+    const ConvL& l = rs.conv;
+    const bool tcw = tc_on() && tcw_batch_ok(rs.tcw, B);
+    const bool tcb = tc_on() && rs.n_tcb > 0;
+    if (tcw || tcb)   // stage dY once for both tensor-core kernels
+      IGM_TRY(launch_split_bf16(lc, rs.out.g, M(rs.out.H, rs.out.W), l.Cout, c.dy_hi, c.dy_lo, l.Cout, 0));
+    if (tcw) {
+      IGM_TRY(launch_wgrad_tc(lc, rs.tcw, B, c.Gp(l.pw)));
+      if (l.pb >= 0) IGM_TRY(launch_colsum(lc, rs.out.g, M(rs.out.H, rs.out.W), l.Cout, c.Gp(l.pb)));
+    } else {
+      IGM_TRY(conv_wgrad(l, rs.Hin, rs.Win, rs.out.g, rs.out.H, rs.out.W, 2, 1));
+    }
+    if (tcb) {
+      TcRun r;
+      r.B = B; r.out0 = rs.in->g; r.N0 = rs.in->C; r.add0 = add; r.kclass = K_CONV_DGRAD;
+      for (int i = 0; i < rs.n_tcb; ++i) IGM_TRY(launch_conv_tc(lc, rs.tcb[i], r));
+      return IGM_OK;
+    }
+    return conv_dgrad(l, rs.out.g, rs.out.H, rs.out.W, rs.Hin, rs.Win, 2, 1, rs.in->g, rs.in->C, nullptr, 0, add,
                       nullptr);
   }
 
@@ -891,6 +942,48 @@ static int plan_tc(igm_ctx* c) {
     n_valid += (l.tc_f.valid ? 1 : 0) + (l.tc_b.valid ? 1 : 0) + (l.tc_w.valid ? 1 : 0);
     return IGM_OK;
   });
+  // stride-2 resampling convs
+  auto plan_rs = [&](ResampleL& rs) -> int {
+    ConvL& l = rs.conv;
+    if (!rs.present || !l.rs_ok || !rs.in || !rs.in->hi) return IGM_OK;
+    const int Bm = c->cfg.max_batch, C = l.Cin;
+    const int64_t KK = (int64_t)l.K * l.K;
+    if (l.rs_kind == 1) {
+      // Downsample Conv2d(C, C, 3, 2, 1): forward = strided conv; data gradient = 4 parity phases over dY
+      IGM_TRY(tc_plan_strided(c->st, rs.tcf[0], C, C, rs.Hin, rs.Win, Bm, 3, 1, rs.in->hi, rs.in->lo, l.wf_hi, l.wf_lo));
+      rs.n_tcf = 1;
+      if (c->cfg.training) {
+        for (int ph = 0; ph < 4; ++ph)
+          IGM_TRY(tc_plan_phase(c->st, rs.tcb[ph], C, C, rs.out.H, rs.out.W, Bm, 3, 1, ph / 2, ph % 2, c->dy_hi, c->dy_lo,
+                                l.wb_hi, l.wb_lo));
+        rs.n_tcb = 4;
+        // S = X (fine grid, ci), P = dY (coarse grid, co); OIHW: ci stride KK, co stride C*KK
+        IGM_TRY(tcw_plan_strided(c->st, rs.tcw, C, C, rs.out.H, rs.out.W, Bm, 3, 1, rs.in->hi, rs.in->lo, c->dy_hi, c->dy_lo,
+                                 KK, (int64_t)C * KK));
+      }
+    } else {
+      // Upsample ConvTranspose2d(C, C, 4, 2, 1): forward = 4 parity phases over X; data gradient = strided conv over dY
+      for (int ph = 0; ph < 4; ++ph)
+        IGM_TRY(tc_plan_phase(c->st, rs.tcf[ph], C, C, rs.Hin, rs.Win, Bm, 4, 1, ph / 2, ph % 2, rs.in->hi, rs.in->lo,
+                              l.wf_hi, l.wf_lo));
+      rs.n_tcf = 4;
+      if (c->cfg.training) {
+        IGM_TRY(tc_plan_strided(c->st, rs.tcb[0], C, C, rs.out.H, rs.out.W, Bm, 4, 1, c->dy_hi, c->dy_lo, l.wb_hi, l.wb_lo));
+        rs.n_tcb = 1;
+        // S = dY (fine grid, co), P = X (coarse grid, ci); IOHW: co stride KK, ci stride C*KK
+        IGM_TRY(tcw_plan_strided(c->st, rs.tcw, C, C, rs.Hin, rs.Win, Bm, 4, 1, c->dy_hi, c->dy_lo, rs.in->hi, rs.in->lo,
+                                 KK, (int64_t)C * KK));
+      }
+    }
+    l.rs_f_valid = rs.n_tcf > 0;
+    l.rs_b_valid = rs.n_tcb > 0;
+    n_valid += rs.n_tcf + rs.n_tcb;
+    return IGM_OK;
+  };
+  if (rc == IGM_OK)
+    for (auto& s : c->downs) { rc = plan_rs(s.rs); if (rc != IGM_OK) break; }
+  if (rc == IGM_OK)
+    for (auto& s : c->ups) { rc = plan_rs(s.rs); if (rc != IGM_OK) break; }
   c->tc_available = (rc == IGM_OK) && n_valid > 0;
   return rc;
 }
@@ -1054,14 +1147,18 @@ static int build_pack_jobs(igm_ctx* c) {
     const float* w = c->Pp(l.pw);
     if (!l.convT) {
       // Conv2d OIHW: fprop contracts ci (sk = KK, sn = Cin*KK); dgrad contracts co
-      if (tc && l.tc_f.valid) add(w, nullptr, l.wf_hi, l.wf_lo, KK, l.Cin, l.Cout, KK, (int64_t)l.Cin * KK, 0);
+      // (the stride-2 Downsample keeps its taps un-flipped: its phase plans carry explicit offsets)
+      if (tc && (l.tc_f.valid || l.rs_f_valid)) add(w, nullptr, l.wf_hi, l.wf_lo, KK, l.Cin, l.Cout, KK, (int64_t)l.Cin * KK, 0);
       else add(w, l.w_fwd, nullptr, nullptr, KK, l.Cin, l.Cout, KK, (int64_t)l.Cin * KK, 0);
       if (tc && l.tc_b.valid) add(w, nullptr, l.wb_hi, l.wb_lo, KK, l.Cout, l.Cin, (int64_t)l.Cin * KK, KK, 1);
+      else if (tc && l.rs_b_valid) add(w, nullptr, l.wb_hi, l.wb_lo, KK, l.Cout, l.Cin, (int64_t)l.Cin * KK, KK, 0);
       else if (l.w_bwd) add(w, l.w_bwd, nullptr, nullptr, KK, l.Cout, l.Cin, (int64_t)l.Cin * KK, KK, 0);
     } else {
       // ConvTranspose2d IOHW
-      add(w, l.w_fwd, nullptr, nullptr, KK, l.Cin, l.Cout, (int64_t)l.Cout * KK, KK, 0);
-      if (l.w_bwd) add(w, l.w_bwd, nullptr, nullptr, KK, l.Cout, l.Cin, KK, (int64_t)l.Cout * KK, 0);
+      if (tc && l.rs_f_valid) add(w, nullptr, l.wf_hi, l.wf_lo, KK, l.Cin, l.Cout, (int64_t)l.Cout * KK, KK, 0);
+      else add(w, l.w_fwd, nullptr, nullptr, KK, l.Cin, l.Cout, (int64_t)l.Cout * KK, KK, 0);
+      if (tc && l.rs_b_valid) add(w, nullptr, l.wb_hi, l.wb_lo, KK, l.Cout, l.Cin, KK, (int64_t)l.Cout * KK, 0);
+      else if (l.w_bwd) add(w, l.w_bwd, nullptr, nullptr, KK, l.Cout, l.Cin, KK, (int64_t)l.Cout * KK, 0);
     }
     return IGM_OK;
   });
