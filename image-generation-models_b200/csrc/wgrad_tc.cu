@@ -353,7 +353,8 @@ int launch_wgrad_tc(const LaunchCtx& lc, const TcWgrad& t, int B, float* grad, i
   a.n_pairs = cdiv(t.ntaps * a.cob, 2);
   a.n_ci_tiles = t.CP / t.BN;
   const int base = a.n_pairs * a.n_ci_tiles;
-  int splits = (2 * 148 + base - 1) / base;
+  // one CTA per SM (192 KB of smem): aim at <= 2 full waves of 148 CTAs, never a ragged third one
+  int splits = (2 * 148) / base;
   if (splits > a.n_ptiles) splits = a.n_ptiles;
   if (splits < 1) splits = 1;
   a.tiles_per_split = cdiv(a.n_ptiles, splits);
