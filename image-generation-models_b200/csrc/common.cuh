@@ -188,7 +188,7 @@ int launch_gn_partial(const LaunchCtx& lc, const float* y, int B, int HW, int C,
 int launch_gn_apply(const LaunchCtx& lc, const float* y, const float* part, const float* gamma,
                     const float* beta, const float* temb, int temb_stride, const float* res,
                     float* out, float* stats, int B, int HW, int C, __nv_bfloat16* out_hi = nullptr,
-                    __nv_bfloat16* out_lo = nullptr);
+                    __nv_bfloat16* out_lo = nullptr, int nparts = 0 /* partial slots per image; 0 = 64-pixel chunks */);
 // Backward of the above.  d_out: grad of `out`.  Produces dy (grad of conv output y),
 // accumulates dgamma/dbeta into the grad arena, and (optionally) dtemb[b, c] (+= over pixels).
 struct GnBwdArgs {

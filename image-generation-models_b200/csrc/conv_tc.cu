@@ -43,7 +43,30 @@ struct TcArgs {
   float* out0; float* out1;
   const float* add0; const float* add1;
   __nv_bfloat16* hi0; __nv_bfloat16* lo0;
+  float* gn_part; int gn_cpg, gn_slots;
 };
+
+// (sum, sum of squares) of the SEG-channel segments of a 32-column chunk, reduced over the warp's
+// 32 pixels and written by lane 0: dst[seg][2]
+template <int SEG>
+__device__ __forceinline__ void gn_chunk_stats(const float (&v)[32], bool valid, int lane, float* dst) {
+#pragma unroll
+  for (int s0 = 0; s0 < 32; s0 += SEG) {
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < SEG; ++j) {
+      s += v[s0 + j];
+      ss = fmaf(v[s0 + j], v[s0 + j], ss);
+    }
+    if (!valid) { s = 0.f; ss = 0.f; }
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    if (lane == 0 && dst) {
+      dst[(s0 / SEG) * 2 + 0] = s;
+      dst[(s0 / SEG) * 2 + 1] = ss;
+    }
+  }
+}
 
 template <int BN>
 struct Cfg {
@@ -185,19 +208,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      float gs = 0.f, gss = 0.f;   // running GroupNorm sums for groups wider than one 32-column chunk
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
         tmem_ld_32x32(t_base + (uint32_t)c0, v);
         const int n = tn * BN + c0;
-        if (valid && n < p.N) {
-          if (p.bias) {
+        if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-              v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+            v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+          }
+        }
+        if (p.gn_part) {
+          // GroupNorm partials of (conv + bias): this warp's 32 pixels lie in one image and one 32-pixel slot
+          const int slot = (oy * p.W + bx) >> 5;     // uniform across the warp (taken from lane 0 below)
+          const int slot0 = __shfl_sync(0xffffffffu, slot, 0);
+          const int bw = __shfl_sync(0xffffffffu, b, 0);
+          const bool wok = __shfl_sync(0xffffffffu, valid ? 1 : 0, 0) != 0;
+          float* dst = wok ? p.gn_part + (((int64_t)bw * p.gn_slots + slot0) * kGroups + n / p.gn_cpg) * 2 : nullptr;
+          if (p.gn_cpg == 8) gn_chunk_stats<8>(v, valid, lane, dst);
+          else if (p.gn_cpg == 16) gn_chunk_stats<16>(v, valid, lane, dst);
+          else {
+            // groups of >= 32 channels: accumulate chunk sums until the group is complete
+            float s = 0.f, ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { s += v[j]; ss = fmaf(v[j], v[j], ss); }
+            if (!valid) { s = 0.f; ss = 0.f; }
+            gs += warp_sum(s);
+            gss += warp_sum(ss);
+            if (((n + 32) % p.gn_cpg) == 0) {
+              if (lane == 0 && dst) { dst[0] = gs; dst[1] = gss; }
+              gs = 0.f; gss = 0.f;
             }
           }
+        }
+        if (valid && n < p.N) {
           float* o;
           const float* ad;
           if (n < p.N0) { o = p.out0 + opix * p.N0 + n; ad = p.add0 ? p.add0 + opix * p.N0 + n : nullptr; }
@@ -488,6 +535,18 @@ static int launch_tc_impl(const LaunchCtx& lc, const TcConv& t, const TcArgs& a,
   return IGM_OK;
 }
 
+bool tc_gn_fusable(const TcConv& t, int B) {
+  (void)B;
+  if (!t.valid || t.sy != 1 || t.sx != 1 || t.out_H != t.H || t.out_W != t.W) return false;
+  if (t.BB * t.BH * t.BW != BM) return false;                 // full tiles only
+  const int hw = t.H * t.W;
+  if (hw % 32 != 0) return false;                              // a warp's 32 pixels stay inside one image
+  if (t.BB == 1 && (t.H % t.BH) != 0) return false;
+  const int cpg = t.N / kGroups;
+  if (t.N % kGroups != 0 || (cpg != 8 && cpg != 16 && cpg % 32 != 0) || cpg > t.BN) return false;
+  return true;
+}
+
 int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r) {
   if (!t.valid) IGM_FAIL(*lc.st, IGM_ERR_STATE, "tcgen05 conv plan not initialised");
   if (r.B < 1 || r.B > t.Bmax) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "conv_tc: bad batch");
@@ -505,6 +564,11 @@ int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r) {
   a.stage_tx_bytes = 2 * (t.BB * t.BH * t.BW * KC * 2) + 2 * (t.BN * KC * 2);
   a.bias = r.bias; a.out0 = r.out0; a.out1 = r.out1; a.add0 = r.add0; a.add1 = r.add1;
   a.hi0 = r.hi0; a.lo0 = r.lo0;
+  a.gn_part = nullptr; a.gn_cpg = 0; a.gn_slots = 0;
+  if (r.gn_part) {
+    if (!tc_gn_fusable(t, r.B) || r.N0 != t.N) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "conv_tc: GroupNorm statistics cannot be fused for this plan");
+    a.gn_part = r.gn_part; a.gn_cpg = t.N / kGroups; a.gn_slots = tc_gn_slots(t);
+  }
   const double flops = 2.0 * r.B * t.H * t.W * (double)t.N * t.K * t.ntaps;
   const double bytes = 4.0 * ((double)r.B * t.H * t.W * (t.K + t.N * (r.add0 ? 2 : 1)) + (double)t.ntaps * t.K * t.N);
   ProfScope ps_(lc, r.kclass, flops, bytes);

@@ -64,8 +64,14 @@ struct TcRun {
   const float* add0 = nullptr; const float* add1 = nullptr;
   __nv_bfloat16* hi0 = nullptr;   // optional: also emit out0 as bf16 hi/lo (operand staging for the
   __nv_bfloat16* lo0 = nullptr;   // next tensor-core conv), same [M, N0] layout
+  // optional fused GroupNorm(8) partial statistics of the output (sum, sum of squares per image,
+  // 32-pixel slot and group), layout part[b][slot][8][2]; see tc_gn_fusable()
+  float* gn_part = nullptr;
   int kclass = K_CONV_FPROP;
 };
+// Can the epilogue of plan `t` produce the GroupNorm partials (full 128-pixel tiles, warps inside one image)?
+bool tc_gn_fusable(const TcConv& t, int B);
+inline int tc_gn_slots(const TcConv& t) { return t.H * t.W / 32; }
 int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r);
 
 // Weight gradients on the tensor cores (wgrad_tc.cu).  Pixels are the reduction axis:

@@ -87,13 +87,13 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
                                                        const float* __restrict__ res, float* __restrict__ out,
                                                        float* __restrict__ stats, int HW, int C, int nchunks,
                                                        __nv_bfloat16* __restrict__ out_hi,
-                                                       __nv_bfloat16* __restrict__ out_lo) {
+                                                       __nv_bfloat16* __restrict__ out_lo, int nparts) {
   __shared__ float s_mean[kGroups], s_rstd[kGroups];
   const GnLayout ly(C);
   const int b = blockIdx.x / nchunks, chunk = blockIdx.x % nchunks;
   if (threadIdx.x < kGroups) {
     float m, r;
-    finalize_stats(part, b, nchunks, threadIdx.x, HW * ly.cpg, m, r);
+    finalize_stats(part, b, nparts, threadIdx.x, HW * ly.cpg, m, r);
     s_mean[threadIdx.x] = m;
     s_rstd[threadIdx.x] = r;
     if (chunk == 0 && stats) {
@@ -487,12 +487,13 @@ int launch_gn_partial(const LaunchCtx& lc, const float* y, int B, int HW, int C,
 
 int launch_gn_apply(const LaunchCtx& lc, const float* y, const float* part, const float* gamma,
                     const float* beta, const float* temb, int temb_stride, const float* res, float* out,
-                    float* stats, int B, int HW, int C, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
+                    float* stats, int B, int HW, int C, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int nparts) {
   IGM_TRY(check_gn_shape(lc, C));
   const int nchunks = cdiv(HW, kGnChunk);
+  if (nparts <= 0) nparts = nchunks;
   ProfScope ps_(lc, K_NORM, 30.0 * B * HW * C, 4.0 * B * HW * C * (res ? 3 : 2));
   gn_apply_kernel<<<B * nchunks, 256, 0, lc.stream>>>(y, part, gamma, beta, temb, temb_stride, res, out,
-                                                      stats, HW, C, nchunks, out_hi, out_lo);
+                                                      stats, HW, C, nchunks, out_hi, out_lo, nparts);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(256) time_proj_fwd_kernel(const TimeProj* __re
   for (int b = bs; b < B; b += 8) {
     const float* a = act + (int64_t)b * dim;
     float s = bias;
+#pragma unroll 8
     for (int k = 0; k < dim; ++k) s = fmaf(ws[c * (dim + 1) + k], __ldg(a + k), s);
     proj[(int64_t)b * total + tp.offset + c0 + c] = s;
   }
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(256) time_proj_wgrad_kernel(const TimeProj* __
     const int c = c0 + i / dim, k = i % dim;
     if (c >= tp.cout) continue;
     float s = 0.f;
+#pragma unroll 8
     for (int b = 0; b < B; ++b)
       s = fmaf(__ldg(d_proj + (int64_t)b * total + tp.offset + c), __ldg(act + (int64_t)b * dim + k), s);
     tp.gw[(int64_t)c * dim + k] += s;
@@ -128,6 +130,7 @@ __global__ void __launch_bounds__(256) time_bwd_sample_kernel(const TimeMlpParam
   if (part < parts) {
     for (int j = 0; j < n_proj; ++j) {
       const TimeProj tp = table[j];
+#pragma unroll 8
       for (int c = part; c < tp.cout; c += parts) s = fmaf(s_dp[tp.offset + c], __ldg(tp.w + (int64_t)c * d + k), s);
     }
   }
@@ -143,6 +146,7 @@ __global__ void __launch_bounds__(256) time_bwd_sample_kernel(const TimeMlpParam
   __syncthreads();
   for (int j = threadIdx.x; j < d4; j += blockDim.x) {
     float a = 0.f;
+#pragma unroll 8
     for (int kk = 0; kk < d; ++kk) a = fmaf(s_dt[kk], __ldg(p.w2 + (int64_t)kk * d4 + j), a);
     d_h1[(int64_t)b * d4 + j] = a * mish_grad_f(__ldg(h1 + (int64_t)b * d4 + j));
   }
@@ -159,6 +163,7 @@ __global__ void time_mlp_wgrad_kernel(const TimeMlpParams p, int B, const float*
   if (i < n2) {
     const int k = i / d4, j = i - k * d4;
     float s = 0.f;
+#pragma unroll 8
     for (int b = 0; b < B; ++b)
       s = fmaf(__ldg(d_temb + (int64_t)b * d + k), mish_f(__ldg(h1 + (int64_t)b * d4 + j)), s);
     p.gw2[i] += s;
@@ -166,6 +171,7 @@ __global__ void time_mlp_wgrad_kernel(const TimeMlpParams p, int B, const float*
     const int r = i - n2;
     const int j = r / d, ii = r - j * d;
     float s = 0.f;
+#pragma unroll 8
     for (int b = 0; b < B; ++b)
       s = fmaf(__ldg(d_h1 + (int64_t)b * d4 + j), __ldg(emb + (int64_t)b * d + ii), s);
     p.gw1[r] += s;

@@ -505,7 +505,7 @@ struct PlanBuilder {
     c.t_proj = ar.alloc((int64_t)B * c.proj_total);
     tap("time_mlp", c.t_temb, d, 1, 1);
     const int64_t HW0 = (int64_t)cfg.height * cfg.width;
-    c.gn_part = ar.alloc((int64_t)B * cdiv((int)HW0, kGnChunk) * kGroups * 2);
+    c.gn_part = ar.alloc((int64_t)B * cdiv((int)HW0, 32) * kGroups * 2);   // 32-pixel slots (fused) or 64-pixel chunks
     c.pred = ar.alloc((int64_t)B * cfg.channels * HW0);
     c.loss_ws = ar.alloc(1024);
     c.t_vec = reinterpret_cast<int64_t*>(ar.alloc(2 * (int64_t)B + 4));
@@ -555,12 +555,13 @@ struct Runner {
   // forward of a layer conv reading its wired sources.  `out_act`: when the output is an activation
   // that later feeds tensor-core convs, its bf16 hi/lo copy is produced here as well.
   int conv_fwd(const ConvL& l, int IH, int IW, int OH, int OW, int stride, int pad, float* out, const float* add,
-               const Act* out_act = nullptr) {
+               const Act* out_act = nullptr, float* gn_part = nullptr) {
     const Act* s0 = l.src0;
     const Act* s1 = l.src1;
     if (stride == 1 && use_tc(l.tc_f)) {
       TcRun r;
       r.B = B; r.bias = c.Pp(l.pb); r.out0 = out; r.N0 = l.Cout; r.add0 = add; r.kclass = K_CONV_FPROP;
+      r.gn_part = gn_part;
       if (out_act) { r.hi0 = hi(*out_act); r.lo0 = lo(*out_act); }
       return launch_conv_tc(lc, l.tc_f, r);
     }
@@ -659,10 +660,14 @@ struct Runner {
 
   // ---- Block: conv3x3 -> GN -> Mish (+temb) (+res) ----
   int block_fwd(BlockL& b, int H, int W, const float* temb, const float* res, const Act& out) {
-    IGM_TRY(conv_fwd(b.conv, H, W, H, W, 1, 1, b.raw, nullptr));
-    IGM_TRY(launch_gn_partial(lc, b.raw, B, H * W, b.conv.Cout, c.gn_part));
+    // GroupNorm partial statistics come out of the conv epilogue when the tensor-core plan allows it
+    const bool fused = use_tc(b.conv.tc_f) && tc_gn_fusable(b.conv.tc_f, B);
+    IGM_TRY(conv_fwd(b.conv, H, W, H, W, 1, 1, b.raw, nullptr, nullptr, fused ? c.gn_part : nullptr));
+    int nparts = 0;
+    if (fused) nparts = tc_gn_slots(b.conv.tc_f);
+    else IGM_TRY(launch_gn_partial(lc, b.raw, B, H * W, b.conv.Cout, c.gn_part));
     IGM_TRY(launch_gn_apply(lc, b.raw, c.gn_part, c.Pp(b.gn_w), c.Pp(b.gn_b), temb, c.proj_total, res, out.v,
-                            b.stats, B, H * W, b.conv.Cout, hi(out), lo(out)));
+                            b.stats, B, H * W, b.conv.Cout, hi(out), lo(out), nparts));
     return IGM_OK;
   }
   // d_out: grad of block output; leaves dy (grad of conv output) in scrA (+ its bf16 staging copy)
