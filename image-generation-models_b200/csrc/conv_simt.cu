@@ -372,6 +372,55 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a, int pix_p
   }
 }
 
+// Forward of the stem convs (C_in = 1..4 image channels; 3x3 pad 1 or 1x1): a thread owns one output
+// channel, keeps its KS*KS*C_in weights in registers and walks pixels; the image patch loads are warp
+// broadcasts and the stores are 256-byte coalesced.  grid (pixel splits, C_out/64).
+template <int CI, int KS>
+__global__ void __launch_bounds__(256) conv_stem_kernel(const float* __restrict__ X, const float* __restrict__ Wp,
+                                                        const float* __restrict__ bias, float* __restrict__ out, int B,
+                                                        int H, int W, int Cout, int pix_per_cta) {
+  constexpr int T = KS * KS, PAD = (KS - 1) / 2;
+  const int co = blockIdx.y * 64 + (threadIdx.x & 63);
+  const int lane4 = threadIdx.x >> 6;
+  if (co >= Cout) return;
+  float w[T * CI];
+#pragma unroll
+  for (int i = 0; i < T * CI; ++i) w[i] = __ldg(Wp + (int64_t)i * Cout + co);   // packed [tap][ci][co]
+  const float bv = bias ? __ldg(bias + co) : 0.f;
+  const int64_t npix = (int64_t)B * H * W;
+  const int64_t p0 = (int64_t)blockIdx.x * pix_per_cta;
+  int64_t p1 = p0 + pix_per_cta;
+  if (p1 > npix) p1 = npix;
+  for (int64_t p = p0 + lane4; p < p1; p += 4) {
+    const int b = (int)(p / (H * W));
+    const int r = (int)(p - (int64_t)b * H * W);
+    const int y = r / W, x = r - y * W;
+    float acc = bv;
+#pragma unroll
+    for (int ky = 0; ky < KS; ++ky) {
+      const int iy = y + ky - PAD;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < KS; ++kx) {
+        const int ix = x + kx - PAD;
+        if (ix < 0 || ix >= W) continue;
+        const float* xp = X + (((int64_t)b * H + iy) * W + ix) * CI;
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci) acc = fmaf(__ldg(xp + ci), w[(ky * KS + kx) * CI + ci], acc);
+      }
+    }
+    out[p * Cout + co] = acc;
+  }
+}
+
+template <int CI>
+static void launch_stem(const ConvArgs& a, dim3 grid, int per, cudaStream_t st) {
+  if (a.KH == 3)
+    conv_stem_kernel<CI, 3><<<grid, 256, 0, st>>>(a.in0, a.w, a.bias, a.out0, a.B, a.IH, a.IW, a.N, per);
+  else
+    conv_stem_kernel<CI, 1><<<grid, 256, 0, st>>>(a.in0, a.w, a.bias, a.out0, a.B, a.IH, a.IW, a.N, per);
+}
+
 // Weight gradient of the stem conv (C_in = 1..4 image channels, 3x3, stride 1, pad 1):
 //   dW[co][ci][ky][kx] += sum_pix dY[pix][co] * X[pix + (ky-1, kx-1)][ci]
 // The generic 64x64-tile kernel wastes >90 % of its tile on 3 input channels; here a thread owns one
@@ -467,6 +516,22 @@ int launch_conv(const LaunchCtx& lc, const ConvArgs& a) {
   if (a.KH * a.KW > MAX_TAPS) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "conv: too many taps");
   if (a.N0 <= 0 || a.N0 > a.N || (a.N0 < a.N && !a.out1))
     IGM_FAIL(*lc.st, IGM_ERR_INVALID, "conv: bad output split");
+  if (!a.in1 && a.C1 == 0 && a.C0 >= 1 && a.C0 <= 4 && !a.transposed && a.stride == 1 && a.dil == 1 && a.KH == a.KW &&
+      ((a.KH == 3 && a.pad == 1) || (a.KH == 1 && a.pad == 0)) && a.IH == a.OH && a.IW == a.OW && !a.add0 && a.N0 == a.N) {
+    const int64_t npix = (int64_t)a.B * a.OH * a.OW;
+    int per = (int)cdiv64(npix, 148 * 8);
+    per = (per + 3) & ~3;
+    dim3 grid((unsigned)cdiv64(npix, per), (unsigned)cdiv(a.N, 64));
+    ProfScope ps_(lc, a.kclass, 2.0 * npix * (double)a.N * a.C0 * a.KH * a.KW, 4.0 * npix * (a.N + a.C0));
+    switch (a.C0) {
+      case 1: launch_stem<1>(a, grid, per, lc.stream); break;
+      case 2: launch_stem<2>(a, grid, per, lc.stream); break;
+      case 3: launch_stem<3>(a, grid, per, lc.stream); break;
+      default: launch_stem<4>(a, grid, per, lc.stream); break;
+    }
+    IGM_POST_LAUNCH(lc);
+    return IGM_OK;
+  }
   const int ps = (a.transposed && a.stride > 1) ? a.stride : 1;
   const int OHp = cdiv(a.OH, ps), OWp = cdiv(a.OW, ps);
   const int64_t Mp = (int64_t)a.B * OHp * OWp;

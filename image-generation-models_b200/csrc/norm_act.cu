@@ -469,6 +469,161 @@ __global__ void __launch_bounds__(1024) ln_param_finalize_kernel(const float* __
   }
 }
 
+
+// ---- specialised LayerNorm kernels: LPP lanes per pixel, V float4 per lane (C = 4 * LPP * V) --------
+// The generic kernels above keep LN_MAX_V float4 slots per lane alive (168 registers in backward) and idle
+// half a warp at C = 64; these keep exactly what the channel count needs and pack 32/LPP pixels per warp.
+template <int LPP>
+__device__ __forceinline__ float sub_sum(float v) {
+#pragma unroll
+  for (int o = LPP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int LPP, int V>
+__global__ void __launch_bounds__(256) ln_forward_t_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                           const float* __restrict__ bta, float* __restrict__ out,
+                                                           int64_t M, __nv_bfloat16* __restrict__ out_hi,
+                                                           __nv_bfloat16* __restrict__ out_lo) {
+  constexpr int C = 4 * LPP * V, PPW = 32 / LPP;
+  const int lane = threadIdx.x & 31, sub = lane / LPP, l = lane % LPP;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float4 gg[V], bb[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    gg[j] = __ldg(reinterpret_cast<const float4*>(g + (l + j * LPP) * 4));
+    bb[j] = __ldg(reinterpret_cast<const float4*>(bta + (l + j * LPP) * 4));
+  }
+  for (int64_t m0 = warp * PPW; m0 < M; m0 += nwarps * PPW) {
+    const int64_t m = m0 + sub;
+    const bool ok = m < M;
+    float4 v[V];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      v[j] = ok ? __ldg(reinterpret_cast<const float4*>(x + m * C + (l + j * LPP) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+    const float mean = sub_sum<LPP>(s) * (1.f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+      q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+    }
+    const float stdv = sqrtf(sub_sum<LPP>(q) * (1.f / C));
+    const float inv = 1.f / (stdv + kLnEps);
+    if (ok) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float4 o;
+        o.x = v[j].x * inv * gg[j].x + bb[j].x;
+        o.y = v[j].y * inv * gg[j].y + bb[j].y;
+        o.z = v[j].z * inv * gg[j].z + bb[j].z;
+        o.w = v[j].w * inv * gg[j].w + bb[j].w;
+        const int64_t off = m * C + (l + j * LPP) * 4;
+        *reinterpret_cast<float4*>(out + off) = o;
+        if (out_hi) store_split4(out_hi, out_lo, off, o);
+      }
+    }
+  }
+}
+
+template <int LPP, int V>
+__global__ void __launch_bounds__(256) ln_backward_t_kernel(const float* __restrict__ d_out, const float* __restrict__ x,
+                                                            const float* __restrict__ g, const float* __restrict__ d_res,
+                                                            float* __restrict__ dx, float* __restrict__ ws, int64_t M) {
+  constexpr int C = 4 * LPP * V, PPW = 32 / LPP;
+  extern __shared__ float sred[];   // [8 warps][2][C]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, sub = lane / LPP, l = lane % LPP;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  float4 gg[V], adg[V], adb[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    gg[j] = __ldg(reinterpret_cast<const float4*>(g + (l + j * LPP) * 4));
+    adg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    adb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int64_t m0 = warp * PPW; m0 < M; m0 += nwarps * PPW) {
+    const int64_t m = m0 + sub;
+    const bool ok = m < M;
+    float4 v[V], d[V];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int64_t off = m * C + (l + j * LPP) * 4;
+      v[j] = ok ? __ldg(reinterpret_cast<const float4*>(x + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      d[j] = ok ? __ldg(reinterpret_cast<const float4*>(d_out + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+    const float mean = sub_sum<LPP>(s) * (1.f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+      q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+    }
+    const float stdv = sqrtf(sub_sum<LPP>(q) * (1.f / C));
+    const float sdn = stdv + kLnEps;
+    const float inv = 1.f / sdn;
+    float sdnv = 0.f, sdnx = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      adg[j].x += d[j].x * v[j].x * inv; adg[j].y += d[j].y * v[j].y * inv;
+      adg[j].z += d[j].z * v[j].z * inv; adg[j].w += d[j].w * v[j].w * inv;
+      adb[j].x += d[j].x; adb[j].y += d[j].y; adb[j].z += d[j].z; adb[j].w += d[j].w;
+      d[j].x *= gg[j].x; d[j].y *= gg[j].y; d[j].z *= gg[j].z; d[j].w *= gg[j].w;
+      sdnv += (d[j].x + d[j].y) + (d[j].z + d[j].w);
+      sdnx += (d[j].x * v[j].x + d[j].y * v[j].y) + (d[j].z * v[j].z + d[j].w * v[j].w);
+    }
+    sdnv = sub_sum<LPP>(sdnv);
+    sdnx = sub_sum<LPP>(sdnx);
+    const float k1 = sdnv / (C * sdn);
+    const float k2 = sdnx / ((float)C * fmaxf(stdv, 1e-30f) * sdn * sdn);
+    if (ok) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const int64_t off = m * C + (l + j * LPP) * 4;
+        float4 o;
+        o.x = d[j].x * inv - k1 - v[j].x * k2;
+        o.y = d[j].y * inv - k1 - v[j].y * k2;
+        o.z = d[j].z * inv - k1 - v[j].z * k2;
+        o.w = d[j].w * inv - k1 - v[j].w * k2;
+        if (d_res) {
+          const float4 r = __ldg(reinterpret_cast<const float4*>(d_res + off));
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        *reinterpret_cast<float4*>(dx + off) = o;
+      }
+    }
+  }
+  // fold the PPW pixel sub-groups of the warp (same channels), then the 8 warps, in a fixed order
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+#pragma unroll
+    for (int o = LPP; o < 32; o <<= 1) {
+      adg[j].x += __shfl_xor_sync(0xffffffffu, adg[j].x, o); adg[j].y += __shfl_xor_sync(0xffffffffu, adg[j].y, o);
+      adg[j].z += __shfl_xor_sync(0xffffffffu, adg[j].z, o); adg[j].w += __shfl_xor_sync(0xffffffffu, adg[j].w, o);
+      adb[j].x += __shfl_xor_sync(0xffffffffu, adb[j].x, o); adb[j].y += __shfl_xor_sync(0xffffffffu, adb[j].y, o);
+      adb[j].z += __shfl_xor_sync(0xffffffffu, adb[j].z, o); adb[j].w += __shfl_xor_sync(0xffffffffu, adb[j].w, o);
+    }
+    if (sub == 0) {
+      *reinterpret_cast<float4*>(&sred[(wib * 2 + 0) * C + (l + j * LPP) * 4]) = adg[j];
+      *reinterpret_cast<float4*>(&sred[(wib * 2 + 1) * C + (l + j * LPP) * 4]) = adb[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    const int which = i / C, c = i - which * C;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sred[(w * 2 + which) * C + c];
+    ws[((int64_t)blockIdx.x * 2 + which) * C + c] = t;
+  }
+}
+
 }  // namespace
 
 static int check_gn_shape(const LaunchCtx& lc, int C) {
@@ -522,7 +677,15 @@ int launch_ln_forward(const LaunchCtx& lc, const float* x, const float* g, const
                       int64_t M, int C, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
   if (C % 4 != 0 || C > 1024) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "LayerNorm: C must be a multiple of 4, <= 1024");
   ProfScope ps_(lc, K_NORM, 8.0 * M * C, 8.0 * M * C);
-  ln_forward_kernel<<<ln_grid(M), 256, 0, lc.stream>>>(x, g, b, out, M, C, out_hi, out_lo);
+  const int grid = ln_grid(M);
+  switch (C) {
+    case 32:   ln_forward_t_kernel<8, 1><<<grid, 256, 0, lc.stream>>>(x, g, b, out, M, out_hi, out_lo); break;
+    case 64:   ln_forward_t_kernel<16, 1><<<grid, 256, 0, lc.stream>>>(x, g, b, out, M, out_hi, out_lo); break;
+    case 128:  ln_forward_t_kernel<32, 1><<<grid, 256, 0, lc.stream>>>(x, g, b, out, M, out_hi, out_lo); break;
+    case 256:  ln_forward_t_kernel<32, 2><<<grid, 256, 0, lc.stream>>>(x, g, b, out, M, out_hi, out_lo); break;
+    case 512:  ln_forward_t_kernel<32, 4><<<grid, 256, 0, lc.stream>>>(x, g, b, out, M, out_hi, out_lo); break;
+    default:   ln_forward_kernel<<<grid, 256, 0, lc.stream>>>(x, g, b, out, M, C, out_hi, out_lo); break;
+  }
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }
@@ -539,7 +702,14 @@ int launch_ln_backward(const LaunchCtx& lc, const float* d_out, const float* x, 
     cudaError_t e = cudaFuncSetAttribute(ln_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(e));
   }
-  ln_backward_kernel<<<grid, 256, smem, lc.stream>>>(d_out, x, g, d_res, dx, ws, M, C);
+  switch (C) {
+    case 32:   ln_backward_t_kernel<8, 1><<<grid, 256, smem, lc.stream>>>(d_out, x, g, d_res, dx, ws, M); break;
+    case 64:   ln_backward_t_kernel<16, 1><<<grid, 256, smem, lc.stream>>>(d_out, x, g, d_res, dx, ws, M); break;
+    case 128:  ln_backward_t_kernel<32, 1><<<grid, 256, smem, lc.stream>>>(d_out, x, g, d_res, dx, ws, M); break;
+    case 256:  ln_backward_t_kernel<32, 2><<<grid, 256, smem, lc.stream>>>(d_out, x, g, d_res, dx, ws, M); break;
+    case 512:  ln_backward_t_kernel<32, 4><<<grid, 256, smem, lc.stream>>>(d_out, x, g, d_res, dx, ws, M); break;
+    default:   ln_backward_kernel<<<grid, 256, smem, lc.stream>>>(d_out, x, g, d_res, dx, ws, M, C); break;
+  }
   IGM_POST_LAUNCH(lc);
   ln_param_finalize_kernel<<<cdiv(C, 32), dim3(32, 32), 0, lc.stream>>>(ws, grid, C, dg, db);
   IGM_POST_LAUNCH(lc);
