@@ -127,6 +127,7 @@ struct ConvArgs {
   int B = 0, IH = 0, IW = 0, OH = 0, OW = 0;
   int N = 0;                    // output channels
   int KH = 1, KW = 1, stride = 1, pad = 0, dil = 1;
+  int pad_w = -1;               // horizontal padding when it differs from `pad` (rectangular kernels); -1: same
   int transposed = 0;
   const float* w = nullptr;     // packed [KH*KW][C0+C1][N]
   const float* bias = nullptr;  // [N] or null
@@ -150,6 +151,7 @@ struct WgradArgs {
   const float* Q = nullptr;  int QC = 0, QH = 0, QW = 0;   // [B, QH, QW, QC]
   int B = 0;
   int KH = 1, KW = 1, stride = 1, pad = 0, dil = 1;
+  int pad_w = -1;
   float* grad = nullptr;
   int64_t sq = 0, sp = 0;
 };

@@ -27,13 +27,14 @@ struct RowCoord {
 // decode a K-step (tap) into an input coordinate for one output pixel
 __device__ __forceinline__ bool gather_coord(const ConvArgs& a, int oy, int ox, int ky, int kx, int& iy,
                                              int& ix) {
+  const int pw = a.pad_w < 0 ? a.pad : a.pad_w;
   if (!a.transposed) {
     iy = oy * a.stride - a.pad + ky * a.dil;
-    ix = ox * a.stride - a.pad + kx * a.dil;
+    ix = ox * a.stride - pw + kx * a.dil;
     return iy >= 0 && iy < a.IH && ix >= 0 && ix < a.IW;
   } else {
     int ty = oy + a.pad - ky * a.dil;
-    int tx = ox + a.pad - kx * a.dil;
+    int tx = ox + pw - kx * a.dil;
     if (ty < 0 || tx < 0) return false;
     if (a.stride > 1 && ((ty % a.stride) != 0 || (tx % a.stride) != 0)) return false;
     iy = ty / a.stride;
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(256) conv_igemm_kernel(const ConvArgs a) {
         bool live = true;
         if (ps > 1) {
           int ry = ((py + a.pad - ky * a.dil) % ps + ps) % ps;
-          int rx = ((px + a.pad - kx * a.dil) % ps + ps) % ps;
+          int rx = ((px + (a.pad_w < 0 ? a.pad : a.pad_w) - kx * a.dil) % ps + ps) % ps;
           live = (ry == 0) && (rx == 0);
         }
         if (live) s_taps[nt++] = ky * a.KW + kx;
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a, int pix_p
         }
       }
       const int iy = y * a.stride - a.pad + ky * a.dil;
-      const int ix = x * a.stride - a.pad + kx * a.dil;
+      const int ix = x * a.stride - (a.pad_w < 0 ? a.pad : a.pad_w) + kx * a.dil;
       if (iy >= 0 && iy < a.QH && ix >= 0 && ix < a.QW) {
         const int c = q0 + lc4;
         const float* src = a.Q + (((int64_t)b * a.QH + iy) * a.QW + ix) * a.QC + c;
@@ -380,22 +381,28 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(const float* __restrict_
                                                         const float* __restrict__ bias, float* __restrict__ out, int B,
                                                         int H, int W, int Cout, int pix_per_cta) {
   constexpr int T = KS * KS, PAD = (KS - 1) / 2;
-  const int co = blockIdx.y * 64 + (threadIdx.x & 63);
-  const int lane4 = threadIdx.x >> 6;
+  __shared__ __align__(16) float sw[T * CI][64];   // this CTA's 64-channel slab of the packed [tap][ci][co] weights
+  const int co0 = blockIdx.y * 64;
+  for (int i = threadIdx.x; i < T * CI * 64; i += 256) {
+    const int r = i >> 6, c = i & 63;
+    sw[r][c] = (co0 + c < Cout) ? __ldg(Wp + (int64_t)r * Cout + co0 + c) : 0.f;
+  }
+  __syncthreads();
+  const int q4 = (threadIdx.x & 15) * 4;   // 4 output channels per thread
+  const int pl = threadIdx.x >> 4;         // 16 pixels in flight
+  const int co = co0 + q4;
   if (co >= Cout) return;
-  float w[T * CI];
-#pragma unroll
-  for (int i = 0; i < T * CI; ++i) w[i] = __ldg(Wp + (int64_t)i * Cout + co);   // packed [tap][ci][co]
-  const float bv = bias ? __ldg(bias + co) : 0.f;
+  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + co));
   const int64_t npix = (int64_t)B * H * W;
   const int64_t p0 = (int64_t)blockIdx.x * pix_per_cta;
   int64_t p1 = p0 + pix_per_cta;
   if (p1 > npix) p1 = npix;
-  for (int64_t p = p0 + lane4; p < p1; p += 4) {
+  for (int64_t p = p0 + pl; p < p1; p += 16) {
     const int b = (int)(p / (H * W));
     const int r = (int)(p - (int64_t)b * H * W);
     const int y = r / W, x = r - y * W;
-    float acc = bv;
+    float4 acc = bv;
 #pragma unroll
     for (int ky = 0; ky < KS; ++ky) {
       const int iy = y + ky - PAD;
@@ -406,10 +413,15 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(const float* __restrict_
         if (ix < 0 || ix >= W) continue;
         const float* xp = X + (((int64_t)b * H + iy) * W + ix) * CI;
 #pragma unroll
-        for (int ci = 0; ci < CI; ++ci) acc = fmaf(__ldg(xp + ci), w[(ky * KS + kx) * CI + ci], acc);
+        for (int ci = 0; ci < CI; ++ci) {
+          const float xv = __ldg(xp + ci);
+          const float4 w4 = *reinterpret_cast<const float4*>(&sw[(ky * KS + kx) * CI + ci][q4]);
+          acc.x = fmaf(xv, w4.x, acc.x); acc.y = fmaf(xv, w4.y, acc.y);
+          acc.z = fmaf(xv, w4.z, acc.z); acc.w = fmaf(xv, w4.w, acc.w);
+        }
       }
     }
-    out[p * Cout + co] = acc;
+    *reinterpret_cast<float4*>(out + p * Cout + co) = acc;
   }
 }
 
@@ -517,10 +529,12 @@ int launch_conv(const LaunchCtx& lc, const ConvArgs& a) {
   if (a.N0 <= 0 || a.N0 > a.N || (a.N0 < a.N && !a.out1))
     IGM_FAIL(*lc.st, IGM_ERR_INVALID, "conv: bad output split");
   if (!a.in1 && a.C1 == 0 && a.C0 >= 1 && a.C0 <= 4 && !a.transposed && a.stride == 1 && a.dil == 1 && a.KH == a.KW &&
-      ((a.KH == 3 && a.pad == 1) || (a.KH == 1 && a.pad == 0)) && a.IH == a.OH && a.IW == a.OW && !a.add0 && a.N0 == a.N) {
+      a.pad_w < 0 &&
+      ((a.KH == 3 && a.pad == 1) || (a.KH == 1 && a.pad == 0)) && a.IH == a.OH && a.IW == a.OW && !a.add0 && a.N0 == a.N &&
+      a.N % 4 == 0) {
     const int64_t npix = (int64_t)a.B * a.OH * a.OW;
     int per = (int)cdiv64(npix, 148 * 8);
-    per = (per + 3) & ~3;
+    per = (per + 15) & ~15;
     dim3 grid((unsigned)cdiv64(npix, per), (unsigned)cdiv(a.N, 64));
     ProfScope ps_(lc, a.kclass, 2.0 * npix * (double)a.N * a.C0 * a.KH * a.KW, 4.0 * npix * (a.N + a.C0));
     switch (a.C0) {
@@ -551,7 +565,7 @@ int launch_conv(const LaunchCtx& lc, const ConvArgs& a) {
 
 int launch_wgrad(const LaunchCtx& lc, const WgradArgs& a) {
   const int64_t npix = (int64_t)a.B * a.PH * a.PW;
-  if (a.QC <= 4 && a.KH == 3 && a.KW == 3 && a.stride == 1 && a.pad == 1 && a.dil == 1 && a.PH == a.QH && a.PW == a.QW &&
+  if (a.QC <= 4 && a.KH == 3 && a.KW == 3 && a.stride == 1 && a.pad == 1 && a.pad_w < 0 && a.dil == 1 && a.PH == a.QH && a.PW == a.QW &&
       a.sq == 9 && a.sp == (int64_t)a.QC * 9) {
     // stem: few input channels gathered (Q), C_out enumerated (P)
     int ctas = 148 * 4;

@@ -28,7 +28,6 @@ constexpr int BM = 128;       // output pixels per tile (TMEM lanes)
 constexpr int KC = 64;        // channels per K chunk: 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_TILE_BYTES = BM * KC * 2;   // 16 KiB
-constexpr int EPI_PITCH = 36;               // floats per row of an epilogue transpose tile (conflict-free float4)
 
 using namespace tc;
 
@@ -75,8 +74,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   static constexpr int STAGES = (BN == 128) ? 3 : 4;
   static constexpr int TMEM_COLS = 2 * BN;   // two accumulator stages (power of two >= 32)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                    4 * 32 * EPI_PITCH * 4 /*epilogue transpose tiles*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN>
@@ -191,7 +189,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int N1 = p.N - p.N0;
-    float* ts = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256) + (warp - 2) * (32 * EPI_PITCH);
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -206,7 +203,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
       const int bb = r2 / p.BH;
       const int oy = y0 + by, b = b0 + bb;
       const bool valid = (bb < p.BB) && (oy < p.H) && (b < p.B);
-      const int opix32 = (b * p.out_H + (oy * p.sy + p.oy_off)) * p.out_W + (bx * p.sx + p.ox_off);
+      const int64_t opix = ((int64_t)b * p.out_H + (oy * p.sy + p.oy_off)) * p.out_W + (bx * p.sx + p.ox_off);
 
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
@@ -247,40 +244,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
             }
           }
         }
-        // ---- coalesced store: transpose the warp's 32 x 32 chunk through shared memory so that eight
-        // lanes write one pixel's 128 contiguous bytes (a thread-per-row store touches 32 half-used sectors)
-        {
+        if (valid) {
+          // thread-per-pixel stores: each thread owns 128 contiguous bytes of its output row.  (A shared-
+          // memory transpose to 8-lanes-per-row stores was measured 15-20 % SLOWER on every layer, r1h.)
+          float* o;
+          const float* ad;
+          if (n < p.N0) { o = p.out0 + opix * p.N0 + n; ad = p.add0 ? p.add0 + opix * p.N0 + n : nullptr; }
+          else { o = p.out1 + opix * N1 + (n - p.N0); ad = p.add1 ? p.add1 + opix * N1 + (n - p.N0) : nullptr; }
+          if (ad) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 av = __ldg(reinterpret_cast<const float4*>(ad + j));
+              v[j] += av.x; v[j + 1] += av.y; v[j + 2] += av.z; v[j + 3] += av.w;
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(&ts[lane * EPI_PITCH + j]) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          __syncwarp();
-          const int sub = lane >> 3, c4 = (lane & 7) * 4;
-          const int nn = n + c4;
+            *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          if (p.hi0 && n < p.N0) {
+            // bf16 hi/lo copy of the output row segment: the next tensor-core conv reads it directly
+            __nv_bfloat16* oh = p.hi0 + opix * p.N0 + n;
+            __nv_bfloat16* ol = p.lo0 + opix * p.N0 + n;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + sub;
-            const int opix_r = __shfl_sync(0xffffffffu, opix32, rr);
-            const int valid_r = __shfl_sync(0xffffffffu, valid ? 1 : 0, rr);
-            if (!valid_r) continue;
-            float4 x = *reinterpret_cast<const float4*>(&ts[rr * EPI_PITCH + c4]);
-            float* o;
-            const float* ad;
-            if (nn < p.N0) {
-              o = p.out0 + (int64_t)opix_r * p.N0 + nn;
-              ad = p.add0 ? p.add0 + (int64_t)opix_r * p.N0 + nn : nullptr;
-            } else {
-              o = p.out1 + (int64_t)opix_r * N1 + (nn - p.N0);
-              ad = p.add1 ? p.add1 + (int64_t)opix_r * N1 + (nn - p.N0) : nullptr;
+            for (int j = 0; j < 32; j += 8) {
+              __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                h[e] = __float2bfloat16_rn(v[j + e]);
+                l[e] = __float2bfloat16_rn(v[j + e] - __bfloat162float(h[e]));
+              }
+              *reinterpret_cast<uint4*>(oh + j) = *reinterpret_cast<const uint4*>(h);
+              *reinterpret_cast<uint4*>(ol + j) = *reinterpret_cast<const uint4*>(l);
             }
-            if (ad) {
-              const float4 av = __ldg(reinterpret_cast<const float4*>(ad));
-              x.x += av.x; x.y += av.y; x.z += av.z; x.w += av.w;
-            }
-            *reinterpret_cast<float4*>(o) = x;
-            // bf16 hi/lo copy of the output: the next tensor-core conv reads it directly
-            if (p.hi0 && nn < p.N0) store_split4(p.hi0, p.lo0, (int64_t)opix_r * p.N0 + nn, x);
           }
-          __syncwarp();
         }
       }
       tc_fence_before();
