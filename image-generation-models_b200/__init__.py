@@ -9,7 +9,7 @@ library raises.
 """
 from . import _lib  # noqa: F401
 from .ddpm import DDPM, FusedAdam, GaussianDiffusion, Unet, ValidationResult  # noqa: F401
-from .vqvae import VectorQuantizer  # noqa: F401
+from .vqvae import VQVAE, Decoder, Encoder, VectorQuantizer  # noqa: F401
 from .pixelcnn import PixelCNN  # noqa: F401
 
-__all__ = ["Unet", "GaussianDiffusion", "DDPM", "FusedAdam", "ValidationResult", "VectorQuantizer", "PixelCNN"]
+__all__ = ["Unet", "GaussianDiffusion", "DDPM", "FusedAdam", "ValidationResult", "VectorQuantizer", "VQVAE", "Encoder", "Decoder", "PixelCNN"]

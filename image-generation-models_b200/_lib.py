@@ -55,8 +55,16 @@ SYMBOLS = {
     "igm_vq_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_float, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "igm_pixelcnn_weight_floats": (C.c_int64, [C.c_int, C.c_int]),
     "igm_pixelcnn_workspace_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
-    "igm_pixelcnn_run": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+    "igm_pixelcnn_run": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, _P]),
+    "igm_conv2d_workspace_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "igm_conv2d_forward": (C.c_int, [_P, _P, _P, _P, _P] + [C.c_int] * 14 + [_P, _P]),
+    "igm_conv2d_backward": (C.c_int, [_P, _P, _P, _P, _P, _P] + [C.c_int] * 14 + [_P, _P]),
+    "igm_act_forward": (C.c_int, [C.c_int, _P, _P, C.c_int64, _P, C.c_int64, C.c_int, _P]),
+    "igm_act_backward": (C.c_int, [C.c_int, _P, _P, C.c_int64, _P, _P, _P, C.c_int64, C.c_int, _P]),
+    "igm_ewise": (C.c_int, [C.c_int, _P, _P, _P, C.c_int64, _P]),
+    "igm_mse": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P]),
+    "igm_ce256": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int, _P]),
     "igm_profile_start": (C.c_int, [_P]),
     "igm_profile_stop": (C.c_int, [_P, C.POINTER(ProfileEntry), C.c_int]),
     "igm_launch_count": (C.c_int64, [_P]),

@@ -51,6 +51,7 @@ struct PcnnArgs {
   float* img;                // [N, C, H, W] in/out
   const float* uniforms;     // [H*W][N*C] or null
   const uint8_t* skip;       // [H*W]: 1 = keep the given pixel (reference :185) or null
+  const float* cond;         // [NLAYERS][2 (vert, horiz)][N][2*Hd] class-conditioning pre-gate addends (:71,:79) or null
   float* logits;             // [N, 256, C, H, W] or null
   float* ws;                 // per-image workspace
   int64_t ws_per_img;
@@ -211,7 +212,12 @@ __global__ void __launch_bounds__(256) pixelcnn_kernel(const PcnnArgs a) {
       float* vout = Vc + (((int64_t)(l + 1) * H + h) * W) * Hd;
       for (int i = tid; i < W * Hd; i += 256) {
         const int w = i / Hd, c = i - w * Hd;
-        const float av = vc_s[w * N2 + c], bv = vc_s[w * N2 + Hd + c];
+        float av = vc_s[w * N2 + c], bv = vc_s[w * N2 + Hd + c];
+        if (a.cond) {
+          const float* cp = a.cond + ((int64_t)(l * 2 + 0) * a.N + blockIdx.x) * N2;
+          av = __fadd_rn(av, __ldg(cp + c));
+          bv = __fadd_rn(bv, __ldg(cp + Hd + c));
+        }
         vout[i] = tanhf(av) * (1.f / (1.f + expf(-bv)));
       }
       // v -> h link: conv1x1_1 on the PRE-gate features                         (pixelcnn.py:74)
@@ -248,7 +254,15 @@ __global__ void __launch_bounds__(256) pixelcnn_kernel(const PcnnArgs a) {
         __syncthreads();
         cta_gemv(Wt + a.off.horiz_w[l], Wt + a.off.horiz_b[l], V2H + ((int64_t)l * W + w) * N2, x_s, N2, N2, red_s, y_s);
         // gated horizontal output: tanh(a) * tanh(b)  (sic)                      (pixelcnn.py:77)
-        if (tid < Hd) x_s[tid] = tanhf(y_s[tid]) * tanhf(y_s[Hd + tid]);
+        if (tid < Hd) {
+          float ah = y_s[tid], bh = y_s[Hd + tid];
+          if (a.cond) {
+            const float* cp = a.cond + ((int64_t)(l * 2 + 1) * a.N + blockIdx.x) * N2;
+            ah = __fadd_rn(ah, __ldg(cp + tid));
+            bh = __fadd_rn(bh, __ldg(cp + Hd + tid));
+          }
+          x_s[tid] = tanhf(ah) * tanhf(bh);
+        }
         __syncthreads();
         // conv1x1_2 + residual                                                    (pixelcnn.py:80)
         cta_gemv(Wt + a.off.h2_w[l], Wt + a.off.h2_b[l], cur_s, x_s, Hd, Hd, red_s, y_s);
@@ -347,8 +361,9 @@ extern "C" int64_t igm_pixelcnn_workspace_floats(int N, int C, int H, int W, int
 }
 
 // mode 0: inverse-CDF draws (uniforms [H*W][N*C] or Philox(seed)); 1: greedy; 2: teacher forced.
+// cond (nullable): [11][2][N][2*Hd] per-image conditioning addends (cond_proj_* outputs, vert then horiz).
 extern "C" int igm_pixelcnn_run(const float* weights, float* img, const float* uniforms, const uint8_t* skip,
-                                float* logits, float* ws, uint64_t seed, int N, int C, int H, int W, int Hd,
+                                const float* cond, float* logits, float* ws, uint64_t seed, int N, int C, int H, int W, int Hd,
                                 int mode, int normalize, void* stream) {
   Status& st = global_status();
   st = Status();
@@ -358,7 +373,7 @@ extern "C" int igm_pixelcnn_run(const float* weights, float* img, const float* u
   if (mode < 0 || mode > 2) IGM_FAIL(st, IGM_ERR_INVALID, "mode must be 0, 1 or 2");
   PcnnArgs a;
   a.Wt = weights; a.off = make_offsets(C, Hd);
-  a.img = img; a.uniforms = uniforms; a.skip = skip; a.logits = logits; a.ws = ws;
+  a.img = img; a.uniforms = uniforms; a.skip = skip; a.cond = cond; a.logits = logits; a.ws = ws;
   a.ws_per_img = igm_pixelcnn_workspace_floats(1, C, H, W, Hd);
   a.seed = seed; a.N = N; a.C = C; a.H = H; a.W = W; a.Hd = Hd; a.mode = mode; a.normalize = normalize;
   const size_t smem = sizeof(float) * ((size_t)2 * W * Hd + (size_t)2 * W * 2 * Hd + 2 * Hd + 256 + 256 + Hd + 256);

@@ -6,7 +6,11 @@ the reference; ``forward`` (logits [N,256,C,H,W]) and ``sample`` run in ONE pers
 the raster once instead of re-running the network per pixel.  ``sample`` draws with the kernel's own
 Philox stream (``torch.multinomial``'s stream cannot be reproduced inside a kernel); pass ``uniforms``
 ([H*W, N*C]) or ``greedy=True`` for reproducible / parity runs.  No CPU fallback.
-Training (``training_step`` backward) and class conditioning are the next rows of SURVEY.md 8(f).
+
+Training: when autograd is recording, ``forward`` / ``calc_likelihood`` run layer by layer on the CUDA
+operators of ``ops`` (masked convolutions incl. the in-place weight masking of :23, gates, ELU, the
+256-way cross entropy) so ``training_step(...).backward()`` fills every ``.grad`` like the reference.
+Class conditioning (``class_condition=True``) is supported on both paths.
 """
 import ctypes as C
 from functools import partial
@@ -15,7 +19,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import _lib
+from . import _lib, ops
 from .ddpm import ValidationResult, _Holder, _LightningModule, _HAVE_LIGHTNING
 
 DILATIONS = (1, 2, 1, 4, 1, 2, 1, 4, 1, 2, 1)   # reference pixelcnn.py:108-122
@@ -55,22 +59,32 @@ def _hmask(k, center):
     return m
 
 
-def _gated(channels, dilation=1):
+def _gated(channels, dilation=1, cond_channel=None):
     g = _Holder()
     g.horiz_conv = _masked_conv(channels, 2 * channels, _hmask(3, False), dilation)
     g.vert_conv = _masked_conv(channels, 2 * channels, _vmask(3, False), dilation)
     g.conv1x1_1 = nn.Conv2d(2 * channels, 2 * channels, 1)
     g.conv1x1_2 = nn.Conv2d(channels, channels, 1)
+    if cond_channel is not None:   # reference :58-62, same registration order
+        g.cond_proj_vert1 = nn.Conv2d(cond_channel, channels, kernel_size=1, bias=False)
+        g.cond_proj_vert2 = nn.Conv2d(cond_channel, channels, kernel_size=1, bias=False)
+        g.cond_proj_horiz1 = nn.Conv2d(cond_channel, channels, kernel_size=1, bias=False)
+        g.cond_proj_horiz2 = nn.Conv2d(cond_channel, channels, kernel_size=1, bias=False)
     return g
 
 
+def _mconv(m, x):
+    """MaskedConvolution.forward (:22-24): mask the weight IN PLACE, then convolve."""
+    c = m.conv
+    c.weight.data *= m.mask
+    return ops.conv2d(x, c.weight, c.bias, 1, c.padding, c.dilation)
+
+
 class PixelCNN(_LightningModule):
-    """Drop-in for reference ``PixelCNN`` (class_condition=False)."""
+    """Drop-in for reference ``PixelCNN``."""
 
     def __init__(self, datamodule, hidden_dim, class_condition=False, n_classes=None, lr=1e-3):
         super().__init__()
-        if class_condition:
-            raise NotImplementedError("class-conditional PixelCNN is a later row (SURVEY.md 8(f).1)")
         self.width, self.height, self.channels = datamodule.width, datamodule.height, datamodule.channels
         self.input_normalize = datamodule.transforms.normalize
         self.output_act = "tanh" if self.input_normalize else "sigmoid"
@@ -80,7 +94,7 @@ class PixelCNN(_LightningModule):
             self.save_hyperparameters(hidden_dim=hidden_dim, class_condition=class_condition, n_classes=n_classes, lr=lr)
         self.conv_vstack = _masked_conv(self.channels, hidden_dim, _vmask(5, True))
         self.conv_hstack = _masked_conv(self.channels, hidden_dim, _hmask(5, True))
-        self.conv_layers = nn.ModuleList([_gated(hidden_dim, d) for d in DILATIONS])
+        self.conv_layers = nn.ModuleList([_gated(hidden_dim, d, n_classes if class_condition else None) for d in DILATIONS])
         self.conv_out = nn.Conv2d(hidden_dim, self.channels * 256, kernel_size=1, padding=0)
         self.register_buffer("log2", torch.log(torch.tensor(2, dtype=torch.float32)))
         self._packed = None
@@ -119,7 +133,35 @@ class PixelCNN(_LightningModule):
         self._packed, self._packed_key = flat, key
         return flat
 
-    def _run(self, img, mode, uniforms=None, skip=None, want_logits=False, seed=0):
+    def _cond_addends(self, y, N):
+        """[11][2][N][2*Hd]: cat(cond_proj_*1(y), cond_proj_*2(y)) per layer for the vertical, then the horizontal gate."""
+        y4 = y.reshape(N, self.hparams.n_classes, 1, 1).float()
+        rows = []
+        for g in self.conv_layers:
+            for a, b in ((g.cond_proj_vert1, g.cond_proj_vert2), (g.cond_proj_horiz1, g.cond_proj_horiz2)):
+                rows.append(torch.cat([ops.conv2d(y4, a.weight).reshape(N, -1), ops.conv2d(y4, b.weight).reshape(N, -1)], 1))
+        return rows
+
+    def _layers(self, x, y=None):
+        """Layer-by-layer forward on the CUDA operators (autograd-capable); returns conv_out [N, 256*C, H, W]."""
+        N = x.shape[0]
+        x = x.float()
+        v = _mconv(self.conv_vstack, x)
+        h = _mconv(self.conv_hstack, x)
+        cond = self._cond_addends(y, N) if y is not None else None
+        for i, g in enumerate(self.conv_layers):
+            vc = _mconv(g.vert_conv, v)
+            v = ops.gate_tanh_sigmoid(vc, None if cond is None else cond[2 * i])
+            hz = _mconv(g.horiz_conv, h)
+            hz = ops.conv2d(vc, g.conv1x1_1.weight, g.conv1x1_1.bias, residual=hz)       # :74
+            hg = ops.gate_tanh_tanh(hz, None if cond is None else cond[2 * i + 1])      # :77 (tanh*tanh, sic)
+            h = ops.conv2d(hg, g.conv1x1_2.weight, g.conv1x1_2.bias, residual=h)         # :80
+        return ops.conv2d(ops.elu(h), self.conv_out.weight, self.conv_out.bias)
+
+    def _recording(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    def _run(self, img, mode, uniforms=None, skip=None, want_logits=False, seed=0, cond=None):
         if img.device.type != "cuda":
             raise RuntimeError("libigm_b200 runs on CUDA (B200, sm_100a) only; there is no CPU fallback")
         lib = _lib.load()
@@ -129,28 +171,36 @@ class PixelCNN(_LightningModule):
         logits = torch.empty(N, 256, Cc, H, W, device=img.device) if want_logits else None
         n_ws = lib.igm_pixelcnn_workspace_floats(N, Cc, H, W, Hd)
         ws = torch.empty(int(n_ws), device=img.device)
-        rc = lib.igm_pixelcnn_run(_ptr(wts), _ptr(img), _ptr(uniforms), _ptr(skip), _ptr(logits), _ptr(ws),
+        if cond is not None:
+            with torch.no_grad():
+                cond = torch.stack(self._cond_addends(cond.to(img.device), N)).contiguous()   # [22, N, 2*Hd]
+        rc = lib.igm_pixelcnn_run(_ptr(wts), _ptr(img), _ptr(uniforms), _ptr(skip), _ptr(cond), _ptr(logits), _ptr(ws),
                                   C.c_uint64(seed), N, Cc, H, W, Hd, mode, int(bool(self.input_normalize)), _stream())
         _lib.check(None, rc)
         return logits
 
     def forward(self, x, y=None):
         """Logits [N, 256, C, H, W] (reference :128-154) via the teacher-forced raster walk."""
-        if y is not None:
-            raise NotImplementedError("class conditioning")
-        return self._run(x.contiguous().float().clone(), 2, want_logits=True)
+        if self._recording():
+            out = self._layers(x, y)
+            return out.reshape(out.shape[0], 256, out.shape[1] // 256, out.shape[2], out.shape[3])
+        for m in [self.conv_vstack, self.conv_hstack] + [c for g in self.conv_layers for c in (g.horiz_conv, g.vert_conv)]:
+            m.conv.weight.data *= m.mask          # the reference masks in place on every forward (:23)
+        return self._run(x.contiguous().float().clone(), 2, want_logits=True, cond=y)
 
     def calc_likelihood(self, x, label=None):
-        pred = self.forward(x, label)
         target = ((x + 1) / 2 * 255).to(torch.long) if self.input_normalize else (x * 255).to(torch.long)
-        nll = F.cross_entropy(pred, target, reduction="none")
+        if self._recording():
+            nll = ops.cross_entropy_256(self._layers(x, label), target)      # (N, C, H, W)
+        else:
+            pred = self.forward(x, label)
+            out = pred.reshape(pred.shape[0], -1, pred.shape[3], pred.shape[4])
+            nll = ops.cross_entropy_256(out, target)
         return (nll.mean(dim=[1, 2, 3]) / self.log2).mean()
 
     @torch.no_grad()
     def sample(self, img_shape, cond=None, img=None, uniforms=None, greedy=False, seed=None):
         """reference :167-195.  Pixels equal to -1 are generated, the others kept (:185)."""
-        if cond is not None:
-            raise NotImplementedError("class conditioning")
         dev = self.conv_out.weight.device
         if img is None:
             img = torch.zeros(img_shape, dtype=torch.float32, device=dev) - 1
@@ -161,15 +211,38 @@ class PixelCNN(_LightningModule):
             uniforms = uniforms.to(dev).float().contiguous()
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-        self._run(img, 1 if greedy else 0, uniforms=uniforms, skip=skip, seed=seed)
+        self._run(img, 1 if greedy else 0, uniforms=uniforms, skip=skip, seed=seed, cond=cond)
         return img
+
+    def configure_optimizers(self):
+        optimizer = torch.optim.Adam(self.parameters(), lr=self.hparams.lr)
+        scheduler = torch.optim.lr_scheduler.StepLR(optimizer, 1, gamma=0.99)
+        return [optimizer], [scheduler]
+
+    def _likelihood_of_batch(self, batch):
+        img, label = batch
+        if self.hparams.class_condition:
+            label = F.one_hot(label, num_classes=self.hparams.n_classes).to(torch.float32)
+            return self.calc_likelihood(img, label)
+        return self.calc_likelihood(img)
+
+    def training_step(self, batch, batch_idx):
+        loss = self._likelihood_of_batch(batch)
+        self.log("train_bpd", loss)
+        return loss
 
     def validation_step(self, batch, batch_idx):
         img, label = batch
-        loss = self.calc_likelihood(img)
+        N, Cc, H, W = img.shape
+        loss = self._likelihood_of_batch(batch)
         self.log("val_bpd", loss)
-        sample_img = self.sample(img.shape) if batch_idx == 0 else None
+        sample_img = None
+        if batch_idx == 0:
+            if self.hparams.class_condition:
+                nc = self.hparams.n_classes
+                sample_label = torch.arange(nc, device=img.device).reshape(nc, 1).repeat(1, 8)
+                sample_label = F.one_hot(sample_label, num_classes=nc).to(torch.float32)
+                sample_img = self.sample((nc * 8, Cc, H, W), cond=sample_label)
+            else:
+                sample_img = self.sample(img.shape)
         return ValidationResult(real_image=img, fake_image=sample_img)
-
-    def training_step(self, batch, batch_idx):
-        raise NotImplementedError("PixelCNN training (backward of the masked convs) is the next row, SURVEY.md 8(f).1")

@@ -161,9 +161,40 @@ int igm_vq_backward(const float* z, const float* codebook, const int64_t* idx, c
  * ws = igm_pixelcnn_workspace_floats(N,C,H,W,Hd) floats.  Context-free; errors via igm_last_error(NULL). */
 int64_t igm_pixelcnn_weight_floats(int C, int Hd);
 int64_t igm_pixelcnn_workspace_floats(int N, int C, int H, int W, int Hd);
+/* cond (nullable): [11][2][N][2*Hd] class-conditioning pre-gate addends, per layer the vertical then the
+ * horizontal gate: cat(cond_proj_*1(y), cond_proj_*2(y)) of pixelcnn.py:71,:79. */
 int igm_pixelcnn_run(const float* weights, float* img, const float* uniforms, const uint8_t* skip,
-                     float* logits, float* ws, uint64_t seed, int N, int C, int H, int W, int Hd,
+                     const float* cond, float* logits, float* ws, uint64_t seed, int N, int C, int H, int W, int Hd,
                      int mode, int normalize, void* stream);
+
+/* ---- generic operators (secondary models: VQ-VAE encoder/decoder, PixelCNN training) --------- */
+/* NHWC fp32 tensors (= torch channels_last); fp32 CUDA-core engine; context-free, errors via
+ * igm_last_error(NULL).  ws: igm_conv2d_workspace_floats(...) floats of scratch (packed weights).
+ * transposed = 0: nn.Conv2d (weight OIHW, dilation allowed); 1: nn.ConvTranspose2d (weight IOHW).
+ * Used behind src/networks/vqvae.py:5-136 and src/models/pixelcnn.py:12-82,:128-165. */
+int64_t igm_conv2d_workspace_floats(int Cin, int Cout, int KH, int KW);
+int igm_conv2d_forward(const float* x, const float* w, const float* bias, const float* residual, float* y,
+                       int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_h,
+                       int pad_w, int dil, int transposed, int OH, int OW, float* ws, void* stream);
+/* dx (nullable) = dL/dx; dw += dL/dw in the weight's own layout; db (nullable) += dL/dbias. */
+int igm_conv2d_backward(const float* x, const float* w, const float* dy, float* dx, float* dw, float* db,
+                        int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_h,
+                        int pad_w, int dil, int transposed, int OH, int OW, float* ws, void* stream);
+/* kind 0 ReLU, 1 ELU, 2 tanh(a)*sigmoid(b), 3 tanh(a)*tanh(b) (gates: x [M,2C] -> y [M,C]).
+ * backward: ref = ReLU OUTPUT for kind 0, the pre-activation x otherwise. */
+int igm_act_forward(int kind, const float* x, const float* cond, int64_t hw, float* y, int64_t M, int C,
+                    void* stream);
+int igm_act_backward(int kind, const float* ref, const float* cond, int64_t hw, const float* dy, float* dx,
+                     float* dcond, int64_t M, int C, void* stream);
+/* kind 0: y = a + b; 1: y = a + (b - a), the straight-through value of src/models/vqvae.py:103. */
+int igm_ewise(int kind, const float* a, const float* b, float* y, int64_t n, void* stream);
+/* F.mse_loss (src/models/vqvae.py:106): loss[1] (nullable); da (nullable) = d_loss[0] * 2 (a-b) / n. */
+int igm_mse(const float* a, const float* b, int64_t n, float* loss, const float* d_loss, float* da,
+            void* stream);
+/* PixelCNN.calc_likelihood's F.cross_entropy (pixelcnn.py:163) on NHWC logits [M, 256*C] with
+ * channel = cls*C + ch and int64 targets [M, C]: nll[M*C] and/or d_logits = d_nll * (softmax - onehot). */
+int igm_ce256(const float* logits, const int64_t* target, float* nll, float* d_logits, const float* d_nll,
+              int64_t M, int C, void* stream);
 
 /* ---- introspection (tests / profiling) ------------------------------------ */
 /* Copies the named intermediate of the last forward (same names as

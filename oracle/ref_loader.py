@@ -92,7 +92,13 @@ def _install_stubs():
     hyu = types.ModuleType("hydra.utils")
 
     def _instantiate(cfg, *a, **k):
-        raise RuntimeError("hydra.utils.instantiate is stubbed; build networks by hand")
+        # minimal stand-in: import cfg["_target_"] and call it with the remaining keys overridden by **k
+        import importlib
+
+        kw = {key: v for key, v in dict(cfg).items() if key != "_target_"}
+        kw.update(k)
+        mod, _, attr = cfg["_target_"].rpartition(".")
+        return getattr(importlib.import_module(mod), attr)(*a, **kw)
 
     hyu.instantiate = _instantiate
     hy.utils = hyu

@@ -22,8 +22,23 @@ CASES = {
     # name: (channels, hidden, N, H, W, normalize)
     "mnist": (1, 64, 2, 28, 28, False),
     "rgb_small": (3, 32, 2, 9, 11, True),
+    "cond_small": (1, 32, 3, 8, 8, False),
 }
-SAMPLE_HW = {"mnist": (12, 28), "rgb_small": (9, 11)}   # sampled crop (full width, fewer rows: CPU time)
+N_CLASSES = {"cond_small": 4}                            # class_condition=True cases
+SAMPLE_HW = {"mnist": (12, 28), "rgb_small": (9, 11), "cond_small": (8, 8)}   # sampled crop (full width, fewer rows)
+
+
+def labels(case):
+    C, Hd, N, H, W, norm = CASES[case]
+    if case not in N_CLASSES:
+        return None
+    return torch.arange(N) % N_CLASSES[case]
+
+
+def sub(t, n=256):
+    f = t.detach().reshape(-1)
+    step = max(1, f.numel() // n)
+    return f[::step].numpy().copy()
 
 
 def inputs(case):
@@ -40,14 +55,24 @@ def inputs(case):
 def main():
     ref = ref_loader.load("pixelcnn")
     for case, (C, Hd, N, H, W, norm) in CASES.items():
-        p = PO.init_params(C, Hd, seed=1)
-        m = ref.PixelCNN(ref_loader.datamodule_cfg(C, H, W, normalize=norm), hidden_dim=Hd)
+        nc = N_CLASSES.get(case)
+        p = PO.init_params(C, Hd, seed=1, n_classes=nc)
+        m = ref.PixelCNN(ref_loader.datamodule_cfg(C, H, W, normalize=norm), hidden_dim=Hd, class_condition=nc is not None,
+                         n_classes=nc)
         m.load_state_dict(p)
         x, u = inputs(case)
         sh, sw = SAMPLE_HW[case]
+        lab = labels(case)
+        y = None if lab is None else torch.nn.functional.one_hot(lab, nc).float()
         with torch.no_grad():
-            logits = m(x)
-            bpd = m.calc_likelihood(x)
+            logits = m(x, y)
+            bpd = m.calc_likelihood(x, y)
+        # one training step of the reference: loss + every parameter gradient (masked taps included)
+        loss = m.training_step((x, lab), 0)
+        loss.backward()
+        # (the last layer's vertical gate output is unused, so its cond_proj_vert* never get a gradient)
+        grads = {"grad:" + k: sub(q.grad) for k, q in m.named_parameters() if q.grad is not None}
+        grads["no_grad"] = np.array([k for k, q in m.named_parameters() if q.grad is None])
         state = {"i": 0}
         real = torch.multinomial
 
@@ -58,12 +83,13 @@ def main():
 
         torch.multinomial = fake
         try:
-            s_u = m.sample((N, C, sh, sw))
+            s_u = m.sample((N, C, sh, sw), cond=y)
         finally:
             torch.multinomial = real
-        s_g = PO.sample(p, (N, C, sh, sw), None, input_normalize=norm)
+        s_g = PO.sample(p, (N, C, sh, sw), None, input_normalize=norm, y=y)
         np.savez_compressed(os.path.join(HERE, f"pixelcnn_{case}.npz"), logits_sub=logits[:, :, :, ::3, ::3].numpy(),
-                            bpd=np.float32(bpd.item()), sample_u=s_u.numpy(), sample_greedy=s_g.numpy())
+                            bpd=np.float32(bpd.item()), train_loss=np.float32(loss.item()), sample_u=s_u.numpy(),
+                            sample_greedy=s_g.numpy(), **grads)
         print(case, "bpd", bpd.item(), "sampled", tuple(s_u.shape))
 
 

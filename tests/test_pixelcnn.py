@@ -22,20 +22,53 @@ def _golden(case):
     return dict(np.load(os.path.join(GOLDEN, f"pixelcnn_{case}.npz")))
 
 
+def _params(case):
+    C, Hd, N, H, W, norm = mg.CASES[case]
+    return PO.init_params(C, Hd, seed=1, n_classes=mg.N_CLASSES.get(case))
+
+
+def _onehot(case):
+    lab = mg.labels(case)
+    return None if lab is None else F.one_hot(lab, mg.N_CLASSES[case]).float()
+
+
+def _sub(t, n=256):
+    f = t.detach().cpu().reshape(-1)
+    return f[:: max(1, f.numel() // n)]
+
+
 @pytest.mark.parametrize("case", list(mg.CASES))
 def test_oracle_matches_golden(case):
     C, Hd, N, H, W, norm = mg.CASES[case]
-    p = PO.init_params(C, Hd, seed=1)
+    p = _params(case)
+    y = _onehot(case)
     x, u = mg.inputs(case)
     g = _golden(case)
     with torch.no_grad():
-        logits = PO.forward(p, x)
+        logits = PO.forward(p, x, y)
     assert_close(logits[:, :, :, ::3, ::3], g["logits_sub"], "logits", 1e-5)
-    assert abs(PO.calc_likelihood(p, x, norm).item() - g["bpd"]) < 1e-4
+    assert abs(PO.calc_likelihood(p, x, norm, y).item() - g["bpd"]) < 1e-4
     sh, sw = mg.SAMPLE_HW[case]
-    if case == "rgb_small":   # the MNIST crop costs ~1 min of CPU: covered by the fixture + GPU test instead
-        assert np.array_equal(PO.sample(p, (N, C, sh, sw), u, input_normalize=norm).numpy(), g["sample_u"])
-        assert np.array_equal(PO.sample(p, (N, C, sh, sw), None, input_normalize=norm).numpy(), g["sample_greedy"])
+    if case != "mnist":   # the MNIST crop costs ~1 min of CPU: covered by the fixture + GPU test instead
+        assert np.array_equal(PO.sample(p, (N, C, sh, sw), u, input_normalize=norm, y=y).numpy(), g["sample_u"])
+        assert np.array_equal(PO.sample(p, (N, C, sh, sw), None, input_normalize=norm, y=y).numpy(), g["sample_greedy"])
+
+
+@pytest.mark.parametrize("case", ["rgb_small", "cond_small"])
+def test_oracle_training_gradients_match_golden(case):
+    """training_step (:202-210) gradients of the reference, masked taps included (weight.data *= mask, :23)."""
+    C, Hd, N, H, W, norm = mg.CASES[case]
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "mask" not in k and k != "log2" else v)
+         for k, v in _params(case).items()}
+    x, _ = mg.inputs(case)
+    g = _golden(case)
+    loss = PO.calc_likelihood(p, x, norm, _onehot(case))
+    loss.backward()
+    assert abs(loss.item() - g["train_loss"]) < 1e-5
+    for k in [k for k in g if k.startswith("grad:")]:
+        assert_close(_sub(p[k[5:]].grad), g[k], k, 1e-4)
+    for k in g["no_grad"]:
+        assert p[str(k)].grad is None
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")
@@ -50,6 +83,29 @@ def test_oracle_bit_exact_vs_live_reference():
     with torch.no_grad():
         assert torch.equal(m(x), PO.forward(sd, x))
         assert torch.equal(m.calc_likelihood(x), PO.calc_likelihood(sd, x, False))
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")
+def test_conditional_oracle_bit_exact_vs_live_reference():
+    ref = ref_loader.load("pixelcnn")
+    torch.manual_seed(0)
+    m = ref.PixelCNN(ref_loader.datamodule_cfg(1, 10, 10, normalize=False), hidden_dim=32, class_condition=True, n_classes=5)
+    sd = m.state_dict()
+    shapes = PO.param_shapes(1, 32, 5)
+    assert list(sd.keys()) == list(shapes.keys()) and all(tuple(sd[k].shape) == shapes[k] for k in sd)
+    x = torch.rand(3, 1, 10, 10)
+    y = F.one_hot(torch.tensor([0, 3, 4]), 5).float()
+    with torch.no_grad():
+        assert torch.equal(m(x, y), PO.forward(sd, x, y))
+
+
+def test_conditional_mirror_state_dict():
+    import igm_b200
+    torch.manual_seed(0)
+    m = igm_b200.PixelCNN(ref_loader.datamodule_cfg(1, 8, 8, normalize=False), hidden_dim=32, class_condition=True, n_classes=4)
+    shapes = PO.param_shapes(1, 32, 4)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(shapes.keys()) and all(tuple(sd[k].shape) == shapes[k] for k in sd)
 
 
 def test_mirror_state_dict_and_packing():
@@ -75,10 +131,16 @@ def test_mirror_state_dict_and_packing():
 def _mirror(case):
     import igm_b200
     C, Hd, N, H, W, norm = mg.CASES[case]
-    p = PO.init_params(C, Hd, seed=1)
-    m = igm_b200.PixelCNN(ref_loader.datamodule_cfg(C, H, W, normalize=norm), hidden_dim=Hd)
+    p = _params(case)
+    nc = mg.N_CLASSES.get(case)
+    m = igm_b200.PixelCNN(ref_loader.datamodule_cfg(C, H, W, normalize=norm), hidden_dim=Hd, class_condition=nc is not None,
+                          n_classes=nc)
     m.load_state_dict(p)
     return p, m.cuda()
+
+
+def _cuda(t):
+    return None if t is None else t.cuda()
 
 
 @pytest.mark.gpu
@@ -87,12 +149,46 @@ def test_gpu_forward_logits(case):
     C, Hd, N, H, W, norm = mg.CASES[case]
     p, m = _mirror(case)
     x, u = mg.inputs(case)
+    y = _onehot(case)
     with torch.no_grad():
-        ref = PO.forward(p, x)
-        got = m(x.cuda()).cpu()
+        ref = PO.forward(p, x, y)
+        got = m(x.cuda(), _cuda(y)).cpu()
     assert_close(got, ref, f"{case} logits")
     assert_close(got[:, :, :, ::3, ::3], _golden(case)["logits_sub"], f"{case} logits vs reference fixture")
-    assert abs(m.calc_likelihood(x.cuda()).item() - _golden(case)["bpd"]) < 1e-3 * _golden(case)["bpd"]
+    with torch.no_grad():
+        assert abs(m.calc_likelihood(x.cuda(), _cuda(y)).item() - _golden(case)["bpd"]) < 1e-3 * _golden(case)["bpd"]
+    # the layer-by-layer (training) path produces the same logits as the raster engine
+    lay = m(x.cuda(), _cuda(y)).detach().cpu()
+    assert_close(lay, ref, f"{case} logits (operator path)")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", list(mg.CASES))
+def test_gpu_training_step_gradients(case):
+    """training_step + backward on the CUDA operators vs the oracle's autograd and the reference fixture."""
+    C, Hd, N, H, W, norm = mg.CASES[case]
+    p, m = _mirror(case)
+    x, _ = mg.inputs(case)
+    g = _golden(case)
+    lab = mg.labels(case)
+    loss = m.training_step((x.cuda(), _cuda(lab)), 0)
+    loss.backward()
+    assert abs(loss.item() - g["train_loss"]) < 1e-3 * g["train_loss"]
+    po = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "mask" not in k and k != "log2" else v)
+          for k, v in p.items()}
+    PO.calc_likelihood(po, x, norm, _onehot(case)).backward()
+    gmax = max(float(v.grad.abs().max()) for v in po.values() if getattr(v, "grad", None) is not None)
+    for k, q in m.named_parameters():
+        if po[k].grad is None:
+            assert q.grad is None, k
+            continue
+        ref = po[k].grad
+        err = float((q.grad.cpu() - ref).abs().max())
+        # 1e-3 relative to the tensor's own scale, with a floor for gradients that are ~0 against the model's largest
+        assert err <= 1e-3 * max(float(ref.abs().max()), 1e-2 * gmax), f"{k}: {err:.3e} vs max {float(ref.abs().max()):.3e}"
+        assert_close(_sub(q.grad), g["grad:" + k], f"{k} vs reference fixture", 2e-3) if float(ref.abs().max()) > 1e-2 * gmax else None
+    # masked taps were zeroed in place like the reference does (:23)
+    assert float((m.conv_vstack.conv.weight.data * (1 - m.conv_vstack.mask)).abs().max()) == 0.0
 
 
 @pytest.mark.gpu
@@ -104,13 +200,14 @@ def test_gpu_sampler_pixels(case):
     g = _golden(case)
     sh, sw = mg.SAMPLE_HW[case]
     # greedy decode: bit-exact pixels
-    s_g = m.sample((N, C, sh, sw), greedy=True).cpu()
+    y = _onehot(case)
+    s_g = m.sample((N, C, sh, sw), greedy=True, cond=_cuda(y)).cpu()
     assert np.array_equal(s_g.numpy(), g["sample_greedy"]), "greedy pixels differ from the reference fixture"
     # inverse-CDF with shared uniforms: bit-exact, or decided by < 1e-5 of probability mass
-    s_u = m.sample((N, C, sh, sw), uniforms=u.cuda()).cpu()
+    s_u = m.sample((N, C, sh, sw), uniforms=u.cuda(), cond=_cuda(y)).cpu()
     if not np.array_equal(s_u.numpy(), g["sample_u"]):
         with torch.no_grad():
-            logits = PO.forward(p, s_u)          # teacher-forced oracle on the GPU's own pixels
+            logits = PO.forward(p, s_u, y)       # teacher-forced oracle on the GPU's own pixels
         probs = F.softmax(logits, dim=1)         # [N, 256, C, h, w]
         cdf = torch.cumsum(probs, dim=1)
         k = ((s_u + 1) / 2 * 255 if norm else s_u * 255).round().long()
@@ -125,7 +222,7 @@ def test_gpu_sampler_pixels(case):
     # given pixels are kept, -1 pixels are generated (reference :179-186)
     start = torch.full((N, C, sh, sw), -1.0)
     start[:, :, : sh // 2, :] = torch.from_numpy(g["sample_greedy"])[:, :, : sh // 2, :]
-    cont = m.sample((N, C, sh, sw), img=start.clone(), greedy=True).cpu()
+    cont = m.sample((N, C, sh, sw), img=start.clone(), greedy=True, cond=_cuda(y)).cpu()
     assert np.array_equal(cont.numpy(), g["sample_greedy"])
 
 
@@ -140,7 +237,8 @@ def test_gpu_full_size_sample_is_causally_consistent():
     u = torch.rand(784, 64, generator=g).cuda()
     img = m.sample((64, 1, 28, 28), uniforms=u)
     assert float(img.min()) >= 0 and float(img.max()) <= 1
-    logits = m(img)
+    with torch.no_grad():
+        logits = m(img)
     cdf = torch.cumsum(F.softmax(logits, dim=1), dim=1)[:, :, 0]          # [64, 256, 28, 28]
     k = (img[:, 0] * 255).round().long()
     uu = u.reshape(28, 28, 64).permute(2, 0, 1)

@@ -1,0 +1,155 @@
+"""VQ-VAE model path (encoder -> quantiser -> decoder, one training_step): oracle vs reference/golden on CPU,
+the CUDA operator path vs the oracle on the GPU.  Bars: chosen codes bit-exact wherever the top-2 distance gap
+exceeds 1e-5 relative; losses, reconstructions and gradients within 1e-3 relative (fp32)."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_loader, vq_oracle
+from oracle import vqvae_oracle as VO
+from tests._util import GOLDEN, assert_close
+
+_spec = importlib.util.spec_from_file_location("make_golden_vqvae", os.path.join(GOLDEN, "make_golden_vqvae.py"))
+mg = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(mg)
+
+
+def _golden(case):
+    return dict(np.load(os.path.join(GOLDEN, f"vqvae_{case}.npz"), allow_pickle=False))
+
+
+def _leaf_params(c):
+    """oracle params with ONE leaf per distinct tensor (tied residual layers stay tied)."""
+    p = mg.params_of(c)
+    leaves = {}
+    out = {}
+    for k, v in p.items():
+        if id(v) not in leaves:
+            leaves[id(v)] = v.clone().requires_grad_(True)
+        out[k] = leaves[id(v)]
+    return out
+
+
+@pytest.mark.parametrize("case", list(mg.CASES))
+def test_oracle_matches_golden(case):
+    c = mg.CASES[case]
+    g = _golden(case)
+    p = _leaf_params(c)
+    x = mg.build_inputs(c)
+    total, recon, vq, commit, idx, ez = VO.training_losses(p, x, 0.25)
+    total.backward()
+    for name, val in (("total", total), ("recon_loss", recon), ("vq_loss", vq), ("commit_loss", commit)):
+        assert abs(val.item() - g[name]) <= 1e-6 * max(1.0, abs(float(g[name]))), name
+    assert np.array_equal(idx.numpy(), g["indices"])
+    assert_close(mg.sub(ez), g["encoder_z_sub"], "encoder_z", 1e-6)
+    with torch.no_grad():
+        assert_close(mg.sub(VO.forward(p, x)), g["recon_sub"], "reconstruction", 1e-6)
+    for k in [k for k in g if k.startswith("grad:")]:
+        gr = p[k[5:]].grad
+        assert_close(gr if case == "small" else mg.sub(gr), g[k], k, 1e-5)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")
+def test_oracle_vs_live_reference_and_key_order():
+    c = mg.CASES["small"]
+    m = mg.reference_model(c)
+    shapes = VO.param_shapes(c["C"], c["D"], c["K"], c["h"], c["rh"], c["n_res"])
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(shapes.keys()) and all(tuple(sd[k].shape) == shapes[k] for k in sd)
+    x = mg.build_inputs(c)
+    with torch.no_grad():
+        assert torch.equal(m.encoder(x.clone()), VO.encoder(sd, x))
+        assert torch.equal(m(x.clone()), VO.forward(sd, x))
+
+
+def test_mirror_state_dict_matches_oracle_layout():
+    import igm_b200
+    c = mg.CASES["small"]
+    m = igm_b200.VQVAE(ref_loader.datamodule_cfg(c["C"], c["S"], c["S"]), latent_dim=c["D"], num_embeddings=c["K"],
+                       encoder={"_target_": "src.networks.vqvae.Encoder", "n_res_layers": c["n_res"], "res_h_dim": c["rh"]},
+                       decoder={"_target_": "src.networks.vqvae.Decoder", "h_dim": c["h"], "n_res_layers": c["n_res"],
+                                "res_h_dim": c["rh"]})
+    shapes = VO.param_shapes(c["C"], c["D"], c["K"], c["h"], c["rh"], c["n_res"])
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(shapes.keys()) and all(tuple(sd[k].shape) == shapes[k] for k in sd)
+    # weight tying survives load_state_dict, and the optimiser sees each tensor once
+    m.load_state_dict(mg.params_of(c))
+    st = m.encoder.conv_stack[5].stack
+    assert st[0] is st[1]
+    n_opt = sum(len(gr["params"]) for gr in m.configure_optimizers().param_groups)
+    assert n_opt == len({id(q) for q in m.parameters()})
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, c["C"], c["S"], c["S"]))
+
+
+def _mirror(c):
+    import igm_b200
+    m = igm_b200.VQVAE(ref_loader.datamodule_cfg(c["C"], c["S"], c["S"], normalize=c["norm"]), latent_dim=c["D"],
+                       num_embeddings=c["K"], beta=0.25,
+                       encoder={"_target_": "src.networks.vqvae.Encoder", "n_res_layers": c["n_res"], "res_h_dim": c["rh"]},
+                       decoder={"_target_": "src.networks.vqvae.Decoder", "h_dim": c["h"], "n_res_layers": c["n_res"],
+                                "res_h_dim": c["rh"]})
+    m.load_state_dict(mg.params_of(c))
+    return m.cuda()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", list(mg.CASES))
+def test_gpu_training_step(case):
+    c = mg.CASES[case]
+    g = _golden(case)
+    m = _mirror(c)
+    x = mg.build_inputs(c)
+    total = m.training_step((x.cuda(), None), 0)
+    total.backward()
+    p = _leaf_params(c)
+    t_o, r_o, v_o, c_o, idx_o, ez_o = VO.training_losses(p, x, 0.25)
+    t_o.backward()
+    # codes: exact wherever the decision is not a rounding-level tie
+    idx = m.vector_quntizer.last_indices.cpu()
+    gap = vq_oracle.top2_gap(ez_o.detach(), p["vector_quntizer.embedding"].detach())
+    clear = gap > 1e-5
+    assert torch.equal(idx[clear], idx_o[clear]) and bool(clear.float().mean() > 0.99)
+    same = torch.equal(idx, idx_o)
+    for name, ref in (("total", t_o), ("recon_loss", r_o), ("vq_loss", v_o), ("commit_loss", c_o)):
+        got = total if name == "total" else m.logged["train_loss/" + name]
+        assert abs(got.item() - ref.item()) <= 1e-3 * abs(ref.item()), name
+    assert abs(total.item() - g["total"]) <= 1e-3 * abs(float(g["total"]))
+    if same:
+        gmax = max(float(v.grad.abs().max()) for v in p.values())
+        seen = set()
+        for k, q in m.named_parameters():
+            if id(q) in seen:
+                continue
+            seen.add(id(q))
+            ref = p[k].grad
+            err = float((q.grad.cpu() - ref).abs().max())
+            assert err <= 1e-3 * max(float(ref.abs().max()), 1e-2 * gmax), f"{k}: {err:.3e} vs {float(ref.abs().max()):.3e}"
+            if float(ref.abs().max()) > 1e-2 * gmax:
+                assert_close(q.grad.cpu() if case == "small" else mg.sub(q.grad.cpu()), g["grad:" + k], f"{k} vs fixture", 2e-3)
+    with torch.no_grad():
+        recon = m(x.cuda()).cpu()
+        assert recon.shape == x.shape
+        if same:
+            assert_close(recon, VO.forward(p, x), "reconstruction")
+            assert_close(mg.sub(recon), g["recon_sub"], "reconstruction vs fixture")
+
+
+@pytest.mark.gpu
+def test_gpu_training_reduces_loss():
+    """A few Adam steps through the public API (configure_optimizers) lower the total loss."""
+    c = mg.CASES["small"]
+    m = _mirror(c)
+    opt = m.configure_optimizers()
+    x = mg.build_inputs(c).cuda()
+    first = None
+    for i in range(12):
+        opt.zero_grad()
+        loss = m.training_step((x, None), i)
+        loss.backward()
+        opt.step()
+        first = loss.item() if first is None else first
+    assert loss.item() < first
