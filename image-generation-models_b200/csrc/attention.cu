@@ -20,12 +20,13 @@ constexpr int D = kDimHead;          // 32
 constexpr int QKV = 3 * kHeads * D;  // 384
 constexpr int HD = kHeads * D;       // 128
 
-// acc[i][j] += sum_{rows nn == grp (mod 4)} X[nn][d0+i] * Y[nn][e0+j]   (4x4 register tile)
-__device__ __forceinline__ void outer4x4(const float (*Xs)[D], const float (*Ys)[D], int grp, int d0, int e0,
+constexpr int CH = 128;   // pixels per CTA: the spatial axis of one (batch, head) is split over ceil(n / CH) CTAs
+
+// acc[i][j] += sum_{rows nn == grp (mod 4), nn < rows} X[nn][d0+i] * Y[nn][e0+j]   (4x4 register tile)
+__device__ __forceinline__ void outer4x4(const float (*Xs)[D], const float (*Ys)[D], int rows, int grp, int d0, int e0,
                                          float (&acc)[4][4], float (&xsum)[4]) {
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int nn = grp + r * 4;
+#pragma unroll 4
+  for (int nn = grp; nn < rows; nn += 4) {
     const float4 x = *reinterpret_cast<const float4*>(&Xs[nn][d0]);
     const float4 y = *reinterpret_cast<const float4*>(&Ys[nn][e0]);
     const float xv[4] = {x.x, x.y, x.z, x.w};
@@ -71,26 +72,60 @@ __device__ __forceinline__ void reduce_groups(float (&acc)[4][4], float (&xsum)[
   }
 }
 
-__global__ void __launch_bounds__(256) linattn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out,
-                                                          float* __restrict__ ctx, float* __restrict__ kstat,
-                                                          int N, __nv_bfloat16* __restrict__ out_hi,
-                                                          __nv_bfloat16* __restrict__ out_lo) {
-  __shared__ __align__(16) float Xs[32][D];
-  __shared__ __align__(16) float Ys[32][D];
+// rows [n0, n0+rows) of one 32-wide column block of an [n, ld] tensor -> smem tile (128-bit loads, zero fill)
+template <int R = CH>
+__device__ __forceinline__ void load_tile(float (*dst)[D], const float* __restrict__ src, int ld, int rows, int tid) {
+  for (int i = tid; i < R * (D / 4); i += 256) {
+    const int nn = i >> 3, c4 = (i & 7) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nn < rows) v = __ldg(reinterpret_cast<const float4*>(src + (int64_t)nn * ld + c4));
+    *reinterpret_cast<float4*>(&dst[nn][c4]) = v;
+  }
+}
+
+constexpr int PART = 2 * D + D * D;   // per-chunk partial: max[32] | sum[32] | S[32][32]
+
+// "last CTA of the group finishes the job": returns true in exactly one CTA of the gridDim.y CTAs that
+// share blockIdx.x, after all the others have published their partials; the counter re-arms itself.
+__device__ __forceinline__ bool last_chunk_done(unsigned int* counter, int tid) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int prev = atomicAdd(counter, 1u);
+    s_last = (prev + 1 == gridDim.y);
+    if (s_last) *counter = 0;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
+// Pass 1, grid (B*heads, nsplit): chunk-local softmax statistics of k and the unnormalised context
+//   m[d] = max_n k[n][d],  l[d] = sum_n exp(k - m),  S[d][e] = sum_n exp(k[n][d] - m[d]) v[n][e];
+// the last CTA of each (batch, head) merges the chunk partials into ctx / kstat.
+__global__ void __launch_bounds__(256) linattn_ctx_kernel(const float* __restrict__ qkv, float* __restrict__ part_ws,
+                                                          unsigned int* __restrict__ counters, float* __restrict__ ctx,
+                                                          float* __restrict__ kstat, int N) {
+  __shared__ __align__(16) float buf[2 * CH * D];   // k | v tiles, later the reduction scratch
+  float (*Xs)[D] = reinterpret_cast<float (*)[D]>(buf);
+  float (*Ys)[D] = reinterpret_cast<float (*)[D]>(buf + CH * D);
+  float (*part)[64][17] = reinterpret_cast<float (*)[64][17]>(buf);
   __shared__ float ctxs[D][D + 1];
-  __shared__ float part[4][64][17];
   __shared__ float red[8][D];
   __shared__ float s_kmax[D], s_ksum[D];
-  const int b = blockIdx.x / kHeads, h = blockIdx.x % kHeads;
+  const int bh = blockIdx.x, b = bh / kHeads, h = bh % kHeads;
+  const int nsplit = gridDim.y;
+  const int n0 = blockIdx.y * CH, rows = min(CH, N - n0);
   const int tid = threadIdx.x;
-  const float* base = qkv + (int64_t)b * N * QKV;
-  const int qcol = h * D, kcol = HD + h * D, vcol = 2 * HD + h * D;
-
-  // 1) max over n of k[:, d]
+  const float* base = qkv + ((int64_t)b * N + n0) * QKV;
+  load_tile(Xs, base + HD + h * D, QKV, rows, tid);
+  load_tile(Ys, base + 2 * HD + h * D, QKV, rows, tid);
+  __syncthreads();
   {
     const int d = tid & 31, r = tid >> 5;
     float m = -INFINITY;
-    for (int n = r; n < N; n += 8) m = fmaxf(m, __ldg(base + (int64_t)n * QKV + kcol + d));
+    for (int nn = r; nn < rows; nn += 8) m = fmaxf(m, Xs[nn][d]);
     red[r][d] = m;
     __syncthreads();
     if (tid < D) {
@@ -100,208 +135,222 @@ __global__ void __launch_bounds__(256) linattn_fwd_kernel(const float* __restric
       s_kmax[tid] = t;
     }
     __syncthreads();
+    for (int nn = r; nn < rows; nn += 8) Xs[nn][d] = expf(Xs[nn][d] - s_kmax[d]);
+    __syncthreads();
   }
-  // 2) unnormalised context sum_n exp(k - max)[n][d] * v[n][e] and the softmax denominators
   const int grp = tid >> 6, t64 = tid & 63;
   const int d0 = (t64 >> 3) * 4, e0 = (t64 & 7) * 4;
-  {
-    float acc[4][4], xsum[4];
+  float acc[4][4], xsum[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      xsum[i] = 0.f;
+  for (int i = 0; i < 4; ++i) {
+    xsum[i] = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    }
-    for (int n0 = 0; n0 < N; n0 += 32) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int idx = tid + i * 256;
-        const int nn = idx >> 5, c = idx & 31;
-        const int n = n0 + nn;
-        float xv = 0.f, yv = 0.f;
-        if (n < N) {
-          xv = expf(__ldg(base + (int64_t)n * QKV + kcol + c) - s_kmax[c]);
-          yv = __ldg(base + (int64_t)n * QKV + vcol + c);
-        }
-        Xs[nn][c] = xv;
-        Ys[nn][c] = yv;
-      }
-      __syncthreads();
-      outer4x4(Xs, Ys, grp, d0, e0, acc, xsum);
-      __syncthreads();
-    }
-    reduce_groups(acc, xsum, grp, t64, d0, e0, part, ctxs, s_ksum);
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   }
-  // normalise, publish ctx / statistics
-  for (int i = tid; i < D * D; i += 256) {
-    const int d = i >> 5, e = i & 31;
-    const float v = ctxs[d][e] / s_ksum[d];
-    ctxs[d][e] = v;
-    ctx[((int64_t)b * kHeads + h) * D * D + i] = v;
+  outer4x4(Xs, Ys, rows, grp, d0, e0, acc, xsum);
+  __syncthreads();   // `part` aliases the tiles
+  reduce_groups(acc, xsum, grp, t64, d0, e0, part, ctxs, s_ksum);
+  float* cdst = ctx + (int64_t)bh * D * D;
+  float* kdst = kstat + (int64_t)bh * D * 2;
+  if (nsplit == 1) {
+    for (int i = tid; i < D * D; i += 256) cdst[i] = ctxs[i >> 5][i & 31] / s_ksum[i >> 5];
+    if (tid < D) { kdst[tid * 2] = s_kmax[tid]; kdst[tid * 2 + 1] = s_ksum[tid]; }
+    return;
   }
+  float* dst = part_ws + ((int64_t)bh * nsplit + blockIdx.y) * PART;
+  if (tid < D) { dst[tid] = s_kmax[tid]; dst[D + tid] = s_ksum[tid]; }
+  for (int i = tid; i < D * D; i += 256) dst[2 * D + i] = ctxs[i >> 5][i & 31];
+  if (!last_chunk_done(counters + bh, tid)) return;
+  // merge: global max / denominator, rescaled sum of the partial contexts (fixed order -> deterministic)
+  const float* src = part_ws + (int64_t)bh * nsplit * PART;
+  float (*s_scale)[D] = reinterpret_cast<float (*)[D]>(buf);   // [nsplit][32]
   if (tid < D) {
-    float* ksd = kstat + (((int64_t)b * kHeads + h) * D + tid) * 2;
-    ksd[0] = s_kmax[tid];
-    ksd[1] = s_ksum[tid];
+    float m = -INFINITY;
+    for (int sp = 0; sp < nsplit; ++sp) m = fmaxf(m, __ldcg(src + (int64_t)sp * PART + tid));
+    float l = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) {
+      const float sc = expf(__ldcg(src + (int64_t)sp * PART + tid) - m);
+      s_scale[sp][tid] = sc;
+      l = fmaf(__ldcg(src + (int64_t)sp * PART + D + tid), sc, l);
+    }
+    s_kmax[tid] = m;
+    s_ksum[tid] = l;
+    kdst[tid * 2] = m;
+    kdst[tid * 2 + 1] = l;
   }
   __syncthreads();
-  // 3) out[n][e] = sum_d ctx[d][e] * q[n][d]; the context column of this thread sits in registers
-  const int e = tid & 31, r = tid >> 5;
-  float col[D];
-#pragma unroll
-  for (int dd = 0; dd < D; ++dd) col[dd] = ctxs[dd][e];
-  for (int n0 = 0; n0 < N; n0 += 32) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = tid + i * 256;
-      const int nn = idx >> 5, c = idx & 31;
-      const int n = n0 + nn;
-      Xs[nn][c] = (n < N) ? __ldg(base + (int64_t)n * QKV + qcol + c) : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int nn = r + i * 8;
-      const int n = n0 + nn;
-      float a = 0.f;
-#pragma unroll
-      for (int d4 = 0; d4 < D; d4 += 4) {
-        const float4 x = *reinterpret_cast<const float4*>(&Xs[nn][d4]);
-        a = fmaf(col[d4], x.x, a);
-        a = fmaf(col[d4 + 1], x.y, a);
-        a = fmaf(col[d4 + 2], x.z, a);
-        a = fmaf(col[d4 + 3], x.w, a);
-      }
-      if (n < N) {
-        const int64_t o = ((int64_t)b * N + n) * HD + h * D + e;
-        out[o] = a;
-        if (out_hi) {
-          const __nv_bfloat16 hv = __float2bfloat16_rn(a);
-          out_hi[o] = hv;
-          out_lo[o] = __float2bfloat16_rn(a - __bfloat162float(hv));
-        }
-      }
-    }
-    __syncthreads();
+  for (int i = tid; i < D * D; i += 256) {
+    const int d = i >> 5;
+    float a = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) a = fmaf(__ldcg(src + (int64_t)sp * PART + 2 * D + i), s_scale[sp][d], a);
+    cdst[i] = a / s_ksum[d];
   }
 }
 
-__global__ void __launch_bounds__(256) linattn_bwd_kernel(const float* __restrict__ qkv,
-                                                          const float* __restrict__ ctx,
-                                                          const float* __restrict__ kstat,
-                                                          const float* __restrict__ d_out,
-                                                          float* __restrict__ d_qkv, int N) {
-  __shared__ __align__(16) float Xs[32][D];   // q (pass A) / softmax(k) (pass B)
-  __shared__ __align__(16) float Ys[32][D];   // dO
-  __shared__ __align__(16) float Vs[32][D];   // v
+constexpr int kMaxSplit = 64;   // n <= 8192 pixels per image (s_scale fits the tile buffer)
+
+// Pass 2, grid (B*heads, nsplit): out[n][e] = sum_d ctx[d][e] * q[n][d] on this CTA's pixel chunk
+__global__ void __launch_bounds__(256) linattn_out_kernel(const float* __restrict__ qkv, const float* __restrict__ ctx,
+                                                          float* __restrict__ out, int N,
+                                                          __nv_bfloat16* __restrict__ out_hi,
+                                                          __nv_bfloat16* __restrict__ out_lo) {
+  __shared__ __align__(16) float Xs[CH][D];
+  const int bh = blockIdx.x, b = bh / kHeads, h = bh % kHeads;
+  const int n0 = blockIdx.y * CH, rows = min(CH, N - n0);
+  const int tid = threadIdx.x;
+  load_tile(Xs, qkv + ((int64_t)b * N + n0) * QKV + h * D, QKV, rows, tid);
+  // lane e keeps column e of the context in registers
+  const int e = tid & 31, r = tid >> 5;
+  float col[D];
+#pragma unroll
+  for (int dd = 0; dd < D; ++dd) col[dd] = __ldg(ctx + (int64_t)bh * D * D + dd * D + e);
+  __syncthreads();
+  for (int nn = r; nn < rows; nn += 8) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int d4 = 0; d4 < D; d4 += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(&Xs[nn][d4]);
+      a0 = fmaf(col[d4], x.x, a0);
+      a1 = fmaf(col[d4 + 1], x.y, a1);
+      a0 = fmaf(col[d4 + 2], x.z, a0);
+      a1 = fmaf(col[d4 + 3], x.w, a1);
+    }
+    const float a = a0 + a1;
+    const int64_t o = ((int64_t)b * N + n0 + nn) * HD + h * D + e;
+    out[o] = a;
+    if (out_hi) {
+      const __nv_bfloat16 hv = __float2bfloat16_rn(a);
+      out_hi[o] = hv;
+      out_lo[o] = __float2bfloat16_rn(a - __bfloat162float(hv));
+    }
+  }
+}
+
+// Backward pass 1, grid (B*heads, nsplit): dctx[d][e] = sum_n q[n][d] * dO[n][e]; the last CTA of each
+// (batch, head) sums the chunk partials into dctx_full.
+__global__ void __launch_bounds__(256) linattn_bwd_dctx_kernel(const float* __restrict__ qkv,
+                                                               const float* __restrict__ d_out,
+                                                               float* __restrict__ part_ws,
+                                                               unsigned int* __restrict__ counters,
+                                                               float* __restrict__ dctx_full, int N) {
+  __shared__ __align__(16) float buf[2 * CH * D];   // q | dO tiles, later the reduction scratch
+  float (*Xs)[D] = reinterpret_cast<float (*)[D]>(buf);
+  float (*Ys)[D] = reinterpret_cast<float (*)[D]>(buf + CH * D);
+  float (*part)[64][17] = reinterpret_cast<float (*)[64][17]>(buf);
+  __shared__ float full[D][D + 1];
+  const int bh = blockIdx.x, b = bh / kHeads, h = bh % kHeads;
+  const int nsplit = gridDim.y;
+  const int n0 = blockIdx.y * CH, rows = min(CH, N - n0);
+  const int tid = threadIdx.x;
+  load_tile(Xs, qkv + ((int64_t)b * N + n0) * QKV + h * D, QKV, rows, tid);
+  load_tile(Ys, d_out + ((int64_t)b * N + n0) * HD + h * D, HD, rows, tid);
+  __syncthreads();
+  const int grp = tid >> 6, t64 = tid & 63;
+  const int d0 = (t64 >> 3) * 4, e0 = (t64 & 7) * 4;
+  float acc[4][4], xsum[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    xsum[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  }
+  outer4x4(Xs, Ys, rows, grp, d0, e0, acc, xsum);
+  __syncthreads();   // `part` aliases the tiles
+  reduce_groups(acc, xsum, grp, t64, d0, e0, part, full, nullptr);
+  float* fdst = dctx_full + (int64_t)bh * D * D;
+  if (nsplit == 1) {
+    for (int i = tid; i < D * D; i += 256) fdst[i] = full[i >> 5][i & 31];
+    return;
+  }
+  float* dst = part_ws + ((int64_t)bh * nsplit + blockIdx.y) * (D * D);
+  for (int i = tid; i < D * D; i += 256) dst[i] = full[i >> 5][i & 31];
+  if (!last_chunk_done(counters + bh, tid)) return;
+  const float* src = part_ws + (int64_t)bh * nsplit * (D * D);
+  for (int i = tid; i < D * D; i += 256) {
+    float a = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) a += __ldcg(src + (int64_t)sp * (D * D) + i);
+    fdst[i] = a;
+  }
+}
+
+// Backward pass 2, grid (B*heads, nsplit): per-pixel gradients of q, k, v on this CTA's chunk
+//   dq[n][d] = sum_e ctx[d][e] dO[n][e];  dv[n][e] = sum_d dctx[d][e] p[n][d]
+//   dk[n][d] = p[n][d] * (sum_e dctx[d][e] v[n][e] - sum_e dctx[d][e] ctx[d][e]),  p = softmax_n(k)
+// Three sweeps over the staged rows, each with ONE 32-entry row/column of ctx or dctx in registers.
+__global__ void __launch_bounds__(256, 3) linattn_bwd_rows_kernel(const float* __restrict__ qkv, const float* __restrict__ ctx,
+                                                               const float* __restrict__ kstat,
+                                                               const float* __restrict__ d_out,
+                                                               const float* __restrict__ dctx_full,
+                                                               float* __restrict__ d_qkv, int N) {
+  constexpr int SUB = 64;                      // rows staged at a time (three tiles must fit 48 KB of static smem)
+  __shared__ __align__(16) float Xs[SUB][D];   // softmax(k)
+  __shared__ __align__(16) float Ys[SUB][D];   // dO
+  __shared__ __align__(16) float Vs[SUB][D];   // v
   __shared__ float ctxs[D][D + 1];
   __shared__ float dctxs[D][D + 1];
-  __shared__ float part[4][64][17];
-  __shared__ float s_kmax[D], s_kinv[D], s_cdot[D];
-  const int b = blockIdx.x / kHeads, h = blockIdx.x % kHeads;
+  const int bh = blockIdx.x, b = bh / kHeads, h = bh % kHeads;
   const int tid = threadIdx.x;
-  const float* base = qkv + (int64_t)b * N * QKV;
-  const float* dob = d_out + (int64_t)b * N * HD + h * D;
-  float* dqb = d_qkv + (int64_t)b * N * QKV;
-  const int qcol = h * D, kcol = HD + h * D, vcol = 2 * HD + h * D;
-
-  for (int i = tid; i < D * D; i += 256) ctxs[i >> 5][i & 31] = __ldg(ctx + ((int64_t)b * kHeads + h) * D * D + i);
-  if (tid < D) {
-    const float* ksd = kstat + (((int64_t)b * kHeads + h) * D + tid) * 2;
-    s_kmax[tid] = ksd[0];
-    s_kinv[tid] = 1.f / ksd[1];
+  for (int i = tid; i < D * D; i += 256) {
+    ctxs[i >> 5][i & 31] = __ldg(ctx + (int64_t)bh * D * D + i);
+    dctxs[i >> 5][i & 31] = __ldg(dctx_full + (int64_t)bh * D * D + i);
   }
   __syncthreads();
-
-  // A) dctx[d][e] = sum_n q[n][d] * dO[n][e]
-  {
-    const int grp = tid >> 6, t64 = tid & 63;
-    const int d0 = (t64 >> 3) * 4, e0 = (t64 & 7) * 4;
-    float acc[4][4], xsum[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      xsum[i] = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    }
-    for (int n0 = 0; n0 < N; n0 += 32) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int idx = tid + i * 256;
-        const int nn = idx >> 5, c = idx & 31;
-        const int n = n0 + nn;
-        float xv = 0.f, yv = 0.f;
-        if (n < N) {
-          xv = __ldg(base + (int64_t)n * QKV + qcol + c);
-          yv = __ldg(dob + (int64_t)n * HD + c);
-        }
-        Xs[nn][c] = xv;
-        Ys[nn][c] = yv;
-      }
-      __syncthreads();
-      outer4x4(Xs, Ys, grp, d0, e0, acc, xsum);
-      __syncthreads();
-    }
-    reduce_groups(acc, xsum, grp, t64, d0, e0, part, dctxs, nullptr);
-  }
-  if (tid < D) {
-    float t = 0.f;
-#pragma unroll
-    for (int e = 0; e < D; ++e) t = fmaf(dctxs[tid][e], ctxs[tid][e], t);
-    s_cdot[tid] = t;
-  }
-  __syncthreads();
-
-  // B) per-row gradients; thread (c, r) keeps row c of ctx and dctx and column c of dctx in registers
   const int c = tid & 31, r = tid >> 5;
-  float crow[D], drow[D], dcol[D];
+  float cdot = 0.f;
 #pragma unroll
-  for (int j = 0; j < D; ++j) {
-    crow[j] = ctxs[c][j];
-    drow[j] = dctxs[c][j];
-    dcol[j] = dctxs[j][c];
-  }
-  const float cdot = s_cdot[c];
-  for (int n0 = 0; n0 < N; n0 += 32) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = tid + i * 256;
-      const int nn = idx >> 5, cc = idx & 31;
-      const int n = n0 + nn;
-      float p = 0.f, v = 0.f, g = 0.f;
-      if (n < N) {
-        p = expf(__ldg(base + (int64_t)n * QKV + kcol + cc) - s_kmax[cc]) * s_kinv[cc];
-        v = __ldg(base + (int64_t)n * QKV + vcol + cc);
-        g = __ldg(dob + (int64_t)n * HD + cc);
-      }
-      Xs[nn][cc] = p;
-      Vs[nn][cc] = v;
-      Ys[nn][cc] = g;
-    }
+  for (int e = 0; e < D; ++e) cdot = fmaf(dctxs[c][e], ctxs[c][e], cdot);
+  const float kmax = kstat[((int64_t)bh * D + c) * 2 + 0], kinv = 1.f / kstat[((int64_t)bh * D + c) * 2 + 1];
+  const int qcol = h * D, kcol = HD + h * D, vcol = 2 * HD + h * D;
+  const int n_end = min((int)(blockIdx.y + 1) * CH, N);
+  for (int n0 = blockIdx.y * CH; n0 < n_end; n0 += SUB) {
+    const int rows = min(SUB, n_end - n0);
+    const float* base = qkv + ((int64_t)b * N + n0) * QKV;
+    load_tile<SUB>(Xs, base + kcol, QKV, rows, tid);
+    load_tile<SUB>(Vs, base + vcol, QKV, rows, tid);
+    load_tile<SUB>(Ys, d_out + ((int64_t)b * N + n0) * HD + h * D, HD, rows, tid);
     __syncthreads();
+    for (int nn = r; nn < rows; nn += 8) Xs[nn][c] = expf(Xs[nn][c] - kmax) * kinv;
+    __syncthreads();
+    float* dqb = d_qkv + ((int64_t)b * N + n0) * QKV;
+    float w[D];
+    // dq = ctx[c][:] . dO[n][:]
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int nn = r + i * 8;
-      const int n = n0 + nn;
-      float dq = 0.f, dp = 0.f, dv = 0.f;
+    for (int j = 0; j < D; ++j) w[j] = ctxs[c][j];
+    for (int nn = r; nn < rows; nn += 8) {
+      float a0 = 0.f, a1 = 0.f;
 #pragma unroll
       for (int j4 = 0; j4 < D; j4 += 4) {
         const float4 g4 = *reinterpret_cast<const float4*>(&Ys[nn][j4]);
+        a0 = fmaf(w[j4], g4.x, a0); a1 = fmaf(w[j4 + 1], g4.y, a1);
+        a0 = fmaf(w[j4 + 2], g4.z, a0); a1 = fmaf(w[j4 + 3], g4.w, a1);
+      }
+      dqb[(int64_t)nn * QKV + qcol + c] = a0 + a1;
+    }
+    // dk = p * (dctx[c][:] . v[n][:] - cdot)
+#pragma unroll
+    for (int j = 0; j < D; ++j) w[j] = dctxs[c][j];
+    for (int nn = r; nn < rows; nn += 8) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int j4 = 0; j4 < D; j4 += 4) {
         const float4 v4 = *reinterpret_cast<const float4*>(&Vs[nn][j4]);
+        a0 = fmaf(w[j4], v4.x, a0); a1 = fmaf(w[j4 + 1], v4.y, a1);
+        a0 = fmaf(w[j4 + 2], v4.z, a0); a1 = fmaf(w[j4 + 3], v4.w, a1);
+      }
+      dqb[(int64_t)nn * QKV + kcol + c] = Xs[nn][c] * ((a0 + a1) - cdot);
+    }
+    // dv = dctx[:][c] . p[n][:]
+#pragma unroll
+    for (int j = 0; j < D; ++j) w[j] = dctxs[j][c];
+    for (int nn = r; nn < rows; nn += 8) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int j4 = 0; j4 < D; j4 += 4) {
         const float4 p4 = *reinterpret_cast<const float4*>(&Xs[nn][j4]);
-        dq = fmaf(crow[j4], g4.x, dq); dq = fmaf(crow[j4 + 1], g4.y, dq);
-        dq = fmaf(crow[j4 + 2], g4.z, dq); dq = fmaf(crow[j4 + 3], g4.w, dq);
-        dp = fmaf(drow[j4], v4.x, dp); dp = fmaf(drow[j4 + 1], v4.y, dp);
-        dp = fmaf(drow[j4 + 2], v4.z, dp); dp = fmaf(drow[j4 + 3], v4.w, dp);
-        dv = fmaf(dcol[j4], p4.x, dv); dv = fmaf(dcol[j4 + 1], p4.y, dv);
-        dv = fmaf(dcol[j4 + 2], p4.z, dv); dv = fmaf(dcol[j4 + 3], p4.w, dv);
+        a0 = fmaf(w[j4], p4.x, a0); a1 = fmaf(w[j4 + 1], p4.y, a1);
+        a0 = fmaf(w[j4 + 2], p4.z, a0); a1 = fmaf(w[j4 + 3], p4.w, a1);
       }
-      if (n < N) {
-        float* o = dqb + (int64_t)n * QKV;
-        o[qcol + c] = dq;
-        o[kcol + c] = Xs[nn][c] * (dp - cdot);
-        o[vcol + c] = dv;
-      }
+      dqb[(int64_t)nn * QKV + vcol + c] = a0 + a1;
     }
     __syncthreads();
   }
@@ -309,18 +358,34 @@ __global__ void __launch_bounds__(256) linattn_bwd_kernel(const float* __restric
 
 }  // namespace
 
+// scratch layout: [B*heads] chunk counters (zero on entry, self re-arming) | [B*heads][32*32] dctx | chunk partials
+int linattn_ws_floats(int B, int n) { return B * kHeads * (64 + D * D + cdiv(n, CH) * PART); }
+
 int launch_linattn_forward(const LaunchCtx& lc, const float* qkv, float* out, float* ctx, float* kstat,
-                           int B, int n, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
+                           int B, int n, float* ws, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
+  const int nsplit = cdiv(n, CH);
+  if (nsplit > kMaxSplit) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linear attention: more than 8192 pixels per image");
   ProfScope ps_(lc, K_ATTN, 4.0 * B * kHeads * (double)n * D * D, 4.0 * B * (double)n * (QKV + HD));
-  linattn_fwd_kernel<<<B * kHeads, 256, 0, lc.stream>>>(qkv, out, ctx, kstat, n, out_hi, out_lo);
+  unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
+  float* parts = ws + (int64_t)B * kHeads * (64 + D * D);
+  linattn_ctx_kernel<<<dim3(B * kHeads, nsplit), 256, 0, lc.stream>>>(qkv, parts, counters, ctx, kstat, n);
+  IGM_POST_LAUNCH(lc);
+  linattn_out_kernel<<<dim3(B * kHeads, nsplit), 256, 0, lc.stream>>>(qkv, ctx, out, n, out_hi, out_lo);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }
 
 int launch_linattn_backward(const LaunchCtx& lc, const float* qkv, const float* ctx, const float* kstat,
-                            const float* d_out, float* d_qkv, int B, int n) {
+                            const float* d_out, float* d_qkv, int B, int n, float* ws) {
+  const int nsplit = cdiv(n, CH);
+  if (nsplit > kMaxSplit) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linear attention: more than 8192 pixels per image");
   ProfScope ps_(lc, K_ATTN, 8.0 * B * kHeads * (double)n * D * D, 4.0 * B * (double)n * (2 * QKV + HD));
-  linattn_bwd_kernel<<<B * kHeads, 256, 0, lc.stream>>>(qkv, ctx, kstat, d_out, d_qkv, n);
+  unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
+  float* dctx = ws + (int64_t)B * kHeads * 64;
+  float* parts = ws + (int64_t)B * kHeads * (64 + D * D);
+  linattn_bwd_dctx_kernel<<<dim3(B * kHeads, nsplit), 256, 0, lc.stream>>>(qkv, d_out, parts, counters, dctx, n);
+  IGM_POST_LAUNCH(lc);
+  linattn_bwd_rows_kernel<<<dim3(B * kHeads, nsplit), 256, 0, lc.stream>>>(qkv, ctx, kstat, d_out, dctx, d_qkv, n);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }

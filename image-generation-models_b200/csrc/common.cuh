@@ -109,7 +109,8 @@ constexpr int kHeads = 4;           // reference ddpm.py:147
 constexpr int kDimHead = 32;        // reference ddpm.py:147
 constexpr float kGnEps = 1e-5f;     // torch.nn.GroupNorm default
 constexpr float kLnEps = 1e-5f;     // reference ddpm.py:86
-constexpr int kGnChunk = 64;        // pixels per GroupNorm partial-statistics chunk
+constexpr int kGnChunk = 64;        // pixels per GroupNorm partial-statistics chunk (launch_gn_partial layout)
+constexpr int kGnChunkMin = 16;     // smallest pixel chunk a GroupNorm CTA works on (workspace sizing)
 
 // ---------------------------------------------------------------------------
 // Generic implicit-GEMM convolution (gather form) on NHWC fp32 activations.
@@ -217,10 +218,12 @@ int ln_backward_parts(int64_t M);   // CTAs (= partial rows of ws [parts][2][C])
 // qkv: [B, n, 384] (q | k | v, each heads*32), out: [B, n, 128]
 // ctx: [B, heads, 32, 32], kstat: [B, heads, 32, 2] (max, sum of exp)
 // ---------------------------------------------------------------------------
+// ws: linattn_ws_floats(B, n) floats of scratch (per-chunk partial statistics / contexts)
+int linattn_ws_floats(int B, int n);
 int launch_linattn_forward(const LaunchCtx& lc, const float* qkv, float* out, float* ctx, float* kstat,
-                           int B, int n, __nv_bfloat16* out_hi = nullptr, __nv_bfloat16* out_lo = nullptr);
+                           int B, int n, float* ws, __nv_bfloat16* out_hi = nullptr, __nv_bfloat16* out_lo = nullptr);
 int launch_linattn_backward(const LaunchCtx& lc, const float* qkv, const float* ctx, const float* kstat,
-                            const float* d_out, float* d_qkv, int B, int n);
+                            const float* d_out, float* d_qkv, int B, int n, float* ws);
 
 // ---------------------------------------------------------------------------
 // time embedding MLP (time_mlp.cu) — reference ddpm.py:47-59, :188-193, :126-130
@@ -241,7 +244,7 @@ int launch_time_proj_forward(const LaunchCtx& lc, const TimeProj* d_table, int n
                              int dim, int B, int total, float* proj);
 int launch_time_backward(const LaunchCtx& lc, const TimeMlpParams& p, const TimeProj* d_table, int n_proj,
                          int total, int B, const float* emb, const float* h1, const float* temb,
-                         const float* act, const float* d_proj, float* ws /* [B, d + 4d + d] */);
+                         const float* act, const float* d_proj, float* ws /* [B, 10d]: d_temb, d_h1, d_act accumulator (zero), mish(h1) */);
 
 // ---------------------------------------------------------------------------
 // boundary + diffusion elementwise (diffusion.cu)

@@ -73,7 +73,12 @@ struct Cfg {
   static constexpr int B_TILE_BYTES = BN * KC * 2;
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   static constexpr int STAGES = (BN == 128) ? 3 : 4;
-  static constexpr int TMEM_COLS = 2 * BN;   // two accumulator stages (power of two >= 32)
+  // BN = 64: tcgen05.mma at N = 64 issues at the N = 128 rate (measured 60 vs 64 cycles, tools/mma_rate_probe.cu),
+  // so the hi and lo weight tiles (adjacent in smem) are fed as ONE N = 128 operand: columns [0,64) accumulate
+  // a*w_hi, columns [64,128) a*w_lo, and two instructions (a_hi, a_lo) replace three; the epilogue adds the halves.
+  static constexpr bool STACKED = (BN == 64);
+  static constexpr int ACC_COLS = STACKED ? 2 * BN : BN;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;   // two accumulator stages (power of two >= 32)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -151,7 +156,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
     if (lane == 0) {
       // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major A/B,
       // N>>3 at bits 17-22, M>>4 at bits 24-28
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C::ACC_COLS >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -159,7 +164,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&acc_empty[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * C::ACC_COLS);
         uint32_t accum = 0;
         for (int it = 0; it < iters; ++it) {
           mbar_wait(&full[stage], phase);
@@ -172,9 +177,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
             const uint32_t koff = k * UMMA_K * 2;   // bytes inside the 128-byte swizzle row
             const uint64_t dah = make_sw128_desc(a_hi + koff), dal = make_sw128_desc(a_lo + koff);
             const uint64_t dbh = make_sw128_desc(b_hi + koff), dbl = make_sw128_desc(b_lo + koff);
-            umma_bf16(d_tmem, dal, dbh, idesc, accum);   // small terms first
-            umma_bf16(d_tmem, dah, dbl, idesc, 1u);
-            umma_bf16(d_tmem, dah, dbh, idesc, 1u);
+            if (C::STACKED) {
+              umma_bf16(d_tmem, dal, dbh, idesc, accum);   // [a_lo*w_hi | a_lo*w_lo]
+              umma_bf16(d_tmem, dah, dbh, idesc, 1u);      // [a_hi*w_hi | a_hi*w_lo]
+            } else {
+              umma_bf16(d_tmem, dal, dbh, idesc, accum);   // small terms first
+              umma_bf16(d_tmem, dah, dbl, idesc, 1u);
+              umma_bf16(d_tmem, dah, dbh, idesc, 1u);
+            }
             accum = 1u;
           }
           umma_commit(&empty[stage]);   // frees this smem stage when the MMAs above retire
@@ -207,12 +217,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
 
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
-      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * C::ACC_COLS);
       float gs = 0.f, gss = 0.f;   // running GroupNorm sums for groups wider than one 32-column chunk
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
         tmem_ld_32x32(t_base + (uint32_t)c0, v);
+        if (C::STACKED) {
+          float w[32];
+          tmem_ld_32x32(t_base + (uint32_t)(BN + c0), w);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += w[j];
+        }
         const int n = tn * BN + c0;
         if (p.bias) {
 #pragma unroll
@@ -312,6 +328,42 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, int64_t M, int 
     const int64_t o = m * cdst + coff + c;
     *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(h);
     *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(l);
+  }
+}
+
+// split + column sums in one pass over a gradient tensor (bias gradient of the conv whose dY is being staged):
+// L = C/4 lanes per row, 256/L rows in flight per CTA; per-CTA partial sums -> one atomic per channel per CTA
+__global__ void __launch_bounds__(256) split_colsum_kernel(const float* __restrict__ src, int64_t M, int C,
+                                                           __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                           float* __restrict__ colsum) {
+  __shared__ float4 red[256];
+  const int L = C >> 2, R = 256 / L;
+  const int c4 = threadIdx.x % L, slot = threadIdx.x / L;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t m = (int64_t)blockIdx.x * R + slot; m < M; m += (int64_t)gridDim.x * R) {
+    const int64_t o = m * C + c4 * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + o));
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    __align__(8) __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = __float2bfloat16_rn(x[j]);
+      l[j] = __float2bfloat16_rn(x[j] - __bfloat162float(h[j]));
+    }
+    *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(l);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < L) {
+    float4 t = red[threadIdx.x];
+    for (int r = 1; r < R; ++r) {
+      const float4 v = red[r * L + threadIdx.x];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    float* d = colsum + threadIdx.x * 4;
+    atomicAdd(d + 0, t.x); atomicAdd(d + 1, t.y); atomicAdd(d + 2, t.z); atomicAdd(d + 3, t.w);
   }
 }
 
@@ -594,6 +646,21 @@ int launch_split_bf16(const LaunchCtx& lc, const float* src, int64_t M, int C, _
   if (blocks > 148 * 16) blocks = 148 * 16;
   ProfScope ps_(lc, K_ELEM, 2.0 * M * C, 8.0 * M * C);
   split_bf16_kernel<<<blocks, 256, 0, lc.stream>>>(src, M, C, hi, lo, cdst, coff);
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+bool split_colsum_ok(int C) { return C >= 32 && C <= 1024 && (C & (C - 1)) == 0; }
+
+int launch_split_bf16_colsum(const LaunchCtx& lc, const float* src, int64_t M, int C, __nv_bfloat16* hi,
+                             __nv_bfloat16* lo, float* colsum) {
+  if (!split_colsum_ok(C)) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "split+colsum: channels must be a power of two in [32, 1024]");
+  const int R = 256 / (C >> 2);
+  int blocks = (int)cdiv64(M, (int64_t)R * 4);   // >= 4 rows per thread
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  ProfScope ps_(lc, K_ELEM, 3.0 * M * C, 8.0 * M * C);
+  split_colsum_kernel<<<blocks, 256, 0, lc.stream>>>(src, M, C, hi, lo, colsum);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }

@@ -109,6 +109,11 @@ int launch_wgrad_tc(const LaunchCtx& lc, const TcWgrad& t, int B, float* grad, i
 int launch_split_bf16(const LaunchCtx& lc, const float* src, int64_t M, int C, __nv_bfloat16* hi,
                       __nv_bfloat16* lo, int cdst, int coff);
 
+// the same split (dense rows, cdst = C) fused with colsum[c] += sum_m src[m][c]; C must satisfy split_colsum_ok
+bool split_colsum_ok(int C);
+int launch_split_bf16_colsum(const LaunchCtx& lc, const float* src, int64_t M, int C, __nv_bfloat16* hi,
+                             __nv_bfloat16* lo, float* colsum);
+
 // Wt[n][tap*K + k] (hi, lo) = src[k*sk + n*sn + (flip ? taps-1-tap : tap)]
 int launch_pack_weight_tc(const LaunchCtx& lc, const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, int taps,
                           int K, int N, int64_t sk, int64_t sn, int flip);

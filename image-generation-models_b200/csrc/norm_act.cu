@@ -41,7 +41,7 @@ __device__ __forceinline__ void group_reduce2(const GnLayout& ly, float a, float
 }
 
 __global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict__ y, int HW, int C,
-                                                         int nchunks, float* __restrict__ part) {
+                                                         int nchunks, float* __restrict__ part, int kGnChunk) {
   __shared__ float sm[256][2];
   const GnLayout ly(C);
   const int b = blockIdx.x / nchunks, chunk = blockIdx.x % nchunks;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
                                                        const float* __restrict__ res, float* __restrict__ out,
                                                        float* __restrict__ stats, int HW, int C, int nchunks,
                                                        __nv_bfloat16* __restrict__ out_hi,
-                                                       __nv_bfloat16* __restrict__ out_lo, int nparts) {
+                                                       __nv_bfloat16* __restrict__ out_lo, int nparts, int kGnChunk) {
   __shared__ float s_mean[kGroups], s_rstd[kGroups];
   const GnLayout ly(C);
   const int b = blockIdx.x / nchunks, chunk = blockIdx.x % nchunks;
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
 }
 
 // ---- backward, pass 1: per-chunk reductions ---------------------------------
-__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdArgs a, int nchunks) {
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdArgs a, int nchunks, int kGnChunk) {
   __shared__ float sm[256][2];
   __shared__ float4 sc[256][3];
   const GnLayout ly(a.C);
@@ -187,15 +187,15 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdArgs a, i
         acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
       }
     }
-    // ws_chan layout: [b][chunk][3][C]
-    float* o = a.ws_chan + ((int64_t)b * nchunks + chunk) * 3 * a.C + threadIdx.x * 4;
+    // ws_chan layout: [b][chunk][4][C]  (dgamma, dbeta, dtemb partials; slot 3 = conv-bias partial of pass 2)
+    float* o = a.ws_chan + ((int64_t)b * nchunks + chunk) * 4 * a.C + threadIdx.x * 4;
 #pragma unroll
     for (int k = 0; k < 3; ++k) *reinterpret_cast<float4*>(o + (int64_t)k * a.C) = acc[k];
   }
 }
 
 // ---- backward, pass 2: dy ------------------------------------------------------
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a, int nchunks) {
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a, int nchunks, int kGnChunk) {
   __shared__ float s_m1[kGroups], s_m2[kGroups];
   __shared__ float4 s_db[256];
   float dbs[4] = {0.f, 0.f, 0.f, 0.f};
@@ -238,11 +238,12 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a, in
       o[j] = rstd * (dn - m1 - n * m2);
       dbs[j] += o[j];
     }
-    *reinterpret_cast<float4*>(a.dy + off) = make_float4(o[0], o[1], o[2], o[3]);
+    if (a.dy) *reinterpret_cast<float4*>(a.dy + off) = make_float4(o[0], o[1], o[2], o[3]);
     if (a.dy_hi) store_split4(a.dy_hi, a.dy_lo, off, make_float4(o[0], o[1], o[2], o[3]));
   }
   if (a.dbias) {
-    // conv-bias gradient = column sums of dy: fold the pixel slots, then one atomic per channel per CTA
+    // conv-bias gradient = column sums of dy: fold the pixel slots; the per-CTA partial goes to slot 3 of
+    // ws_chan and is summed by pass 3 (same-address atomics from thousands of CTAs serialise)
     s_db[threadIdx.x] = make_float4(dbs[0], dbs[1], dbs[2], dbs[3]);
     __syncthreads();
     if (threadIdx.x < ly.L) {
@@ -251,8 +252,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a, in
         const float4 v = s_db[sidx * ly.L + threadIdx.x];
         t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
       }
-      float* d = a.dbias + threadIdx.x * 4;
-      atomicAdd(d + 0, t.x); atomicAdd(d + 1, t.y); atomicAdd(d + 2, t.z); atomicAdd(d + 3, t.w);
+      *reinterpret_cast<float4*>(a.ws_chan + (((int64_t)b * nchunks + chunk) * 4 + 3) * a.C + threadIdx.x * 4) = t;
     }
   }
 }
@@ -260,32 +260,36 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a, in
 // grid (C/32 column slabs, B samples), block (32, 8): each CTA folds the chunk partials of one
 // sample; dtemb[b, c] is written directly, dgamma/dbeta get one atomic per (sample, channel).
 __global__ void __launch_bounds__(256) gn_bwd_param_kernel(const GnBwdArgs a, int nchunks) {
-  __shared__ float red[8][3][33];
+  __shared__ float red[8][4][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int b = blockIdx.y;
-  float sg = 0.f, sb = 0.f, st = 0.f;
+  float sg = 0.f, sb = 0.f, st = 0.f, sc = 0.f;
   if (c < a.C) {
     for (int ch = threadIdx.y; ch < nchunks; ch += 8) {
-      const float* o = a.ws_chan + ((int64_t)b * nchunks + ch) * 3 * a.C;
+      const float* o = a.ws_chan + ((int64_t)b * nchunks + ch) * 4 * a.C;
       sg += o[c];
       sb += o[a.C + c];
       st += o[2 * a.C + c];
+      if (a.dbias) sc += o[3 * a.C + c];
     }
   }
   red[threadIdx.y][0][threadIdx.x] = sg;
   red[threadIdx.y][1][threadIdx.x] = sb;
   red[threadIdx.y][2][threadIdx.x] = st;
+  red[threadIdx.y][3][threadIdx.x] = sc;
   __syncthreads();
   if (threadIdx.y == 0 && c < a.C) {
-    float tg = 0.f, tb = 0.f, tt = 0.f;
+    float tg = 0.f, tb = 0.f, tt = 0.f, tc = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       tg += red[i][0][threadIdx.x];
       tb += red[i][1][threadIdx.x];
       tt += red[i][2][threadIdx.x];
+      tc += red[i][3][threadIdx.x];
     }
     atomicAdd(a.dgamma + c, tg);
     atomicAdd(a.dbeta + c, tb);
+    if (a.dbias) atomicAdd(a.dbias + c, tc);
     if (a.dtemb) a.dtemb[(int64_t)b * a.dtemb_stride + c] = tt;
   }
 }
@@ -442,14 +446,14 @@ __global__ void __launch_bounds__(256) ln_backward_kernel(const float* __restric
   }
 }
 
-// grid C/32, block (32, 32): 32 row lanes stride over the per-CTA partials
+// grid (C/32, splits), block (32, 32): 32 row lanes stride over this split's share of the per-CTA partials
 __global__ void __launch_bounds__(1024) ln_param_finalize_kernel(const float* __restrict__ ws, int nparts, int C,
                                                                  float* __restrict__ dg, float* __restrict__ db) {
   __shared__ float red[32][2][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float tg = 0.f, tb = 0.f;
   if (c < C) {
-    for (int p = threadIdx.y; p < nparts; p += 32) {
+    for (int p = blockIdx.y * 32 + threadIdx.y; p < nparts; p += 32 * gridDim.y) {
       tg += ws[((int64_t)p * 2 + 0) * C + c];
       tb += ws[((int64_t)p * 2 + 1) * C + c];
     }
@@ -464,8 +468,8 @@ __global__ void __launch_bounds__(1024) ln_param_finalize_kernel(const float* __
       sg += red[i][0][threadIdx.x];
       sb += red[i][1][threadIdx.x];
     }
-    dg[c] += sg;
-    db[c] += sb;
+    atomicAdd(dg + c, sg);
+    atomicAdd(db + c, sb);
   }
 }
 
@@ -631,11 +635,22 @@ static int check_gn_shape(const LaunchCtx& lc, int C) {
   return IGM_OK;
 }
 
+// pixels per CTA: enough CTAs for a few waves of 8 resident CTAs per SM, never below kGnChunkMin
+// (the workspaces are sized for kGnChunkMin) and always a multiple of the pixels in flight per iteration
+int gn_chunk(int B, int HW, int C) {
+  int chunk = kGnChunk;
+  while (chunk > kGnChunkMin && (int64_t)B * cdiv(HW, chunk) < 4096) chunk >>= 1;
+  const int ppi = 256 / (C >> 2);
+  if (chunk < ppi) chunk = ppi;
+  return chunk;
+}
+
 int launch_gn_partial(const LaunchCtx& lc, const float* y, int B, int HW, int C, float* part) {
   IGM_TRY(check_gn_shape(lc, C));
+  const int kGnChunk = igm::kGnChunk;   // the partial layout of this entry point is fixed (64-pixel chunks)
   const int nchunks = cdiv(HW, kGnChunk);
   ProfScope ps_(lc, K_NORM, 3.0 * B * HW * C, 4.0 * B * HW * C);
-  gn_partial_kernel<<<B * nchunks, 256, 0, lc.stream>>>(y, HW, C, nchunks, part);
+  gn_partial_kernel<<<B * nchunks, 256, 0, lc.stream>>>(y, HW, C, nchunks, part, kGnChunk);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }
@@ -644,22 +659,24 @@ int launch_gn_apply(const LaunchCtx& lc, const float* y, const float* part, cons
                     const float* beta, const float* temb, int temb_stride, const float* res, float* out,
                     float* stats, int B, int HW, int C, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int nparts) {
   IGM_TRY(check_gn_shape(lc, C));
+  if (nparts <= 0) nparts = cdiv(HW, igm::kGnChunk);   // partials written by launch_gn_partial
+  const int kGnChunk = gn_chunk(B, HW, C);
   const int nchunks = cdiv(HW, kGnChunk);
-  if (nparts <= 0) nparts = nchunks;
   ProfScope ps_(lc, K_NORM, 30.0 * B * HW * C, 4.0 * B * HW * C * (res ? 3 : 2));
   gn_apply_kernel<<<B * nchunks, 256, 0, lc.stream>>>(y, part, gamma, beta, temb, temb_stride, res, out,
-                                                      stats, HW, C, nchunks, out_hi, out_lo, nparts);
+                                                      stats, HW, C, nchunks, out_hi, out_lo, nparts, kGnChunk);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }
 
 int launch_gn_backward(const LaunchCtx& lc, const GnBwdArgs& a) {
   IGM_TRY(check_gn_shape(lc, a.C));
+  const int kGnChunk = gn_chunk(a.B, a.HW, a.C);
   const int nchunks = cdiv(a.HW, kGnChunk);
   ProfScope ps_(lc, K_NORM, 80.0 * a.B * a.HW * a.C, 4.0 * a.B * a.HW * a.C * 5);
-  gn_bwd_reduce_kernel<<<a.B * nchunks, 256, 0, lc.stream>>>(a, nchunks);
+  gn_bwd_reduce_kernel<<<a.B * nchunks, 256, 0, lc.stream>>>(a, nchunks, kGnChunk);
   IGM_POST_LAUNCH(lc);
-  gn_bwd_apply_kernel<<<a.B * nchunks, 256, 0, lc.stream>>>(a, nchunks);
+  gn_bwd_apply_kernel<<<a.B * nchunks, 256, 0, lc.stream>>>(a, nchunks, kGnChunk);
   IGM_POST_LAUNCH(lc);
   gn_bwd_param_kernel<<<dim3(cdiv(a.C, 32), a.B), dim3(32, 8), 0, lc.stream>>>(a, nchunks);
   IGM_POST_LAUNCH(lc);
@@ -711,7 +728,7 @@ int launch_ln_backward(const LaunchCtx& lc, const float* d_out, const float* x, 
     default:   ln_backward_kernel<<<grid, 256, smem, lc.stream>>>(d_out, x, g, d_res, dx, ws, M, C); break;
   }
   IGM_POST_LAUNCH(lc);
-  ln_param_finalize_kernel<<<cdiv(C, 32), dim3(32, 32), 0, lc.stream>>>(ws, grid, C, dg, db);
+  ln_param_finalize_kernel<<<dim3(cdiv(C, 32), cdiv(grid, 128)), dim3(32, 32), 0, lc.stream>>>(ws, grid, C, dg, db);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }

@@ -9,11 +9,11 @@
 namespace igm {
 namespace {
 
-// one CTA per sample
+// one CTA per sample; every dot product reads its weight row with independent 128-bit loads
 __global__ void __launch_bounds__(256) time_mlp_fwd_kernel(const TimeMlpParams p, const int64_t* __restrict__ t,
                                                            float* __restrict__ emb, float* __restrict__ h1,
                                                            float* __restrict__ temb, float* __restrict__ act) {
-  extern __shared__ float sm[];   // emb[d] | a1[4d]
+  extern __shared__ __align__(16) float sm[];   // emb[d] | a1[4d]
   const int d = p.dim, d4 = 4 * p.dim;
   float* s_emb = sm;
   float* s_a1 = sm + d;
@@ -31,161 +31,203 @@ __global__ void __launch_bounds__(256) time_mlp_fwd_kernel(const TimeMlpParams p
   }
   __syncthreads();
   for (int j = threadIdx.x; j < d4; j += blockDim.x) {
-    const float* w = p.w1 + (int64_t)j * d;
-    float a = __ldg(p.b1 + j);
-    for (int i = 0; i < d; ++i) a = fmaf(__ldg(w + i), s_emb[i], a);
+    const float4* w = reinterpret_cast<const float4*>(p.w1 + (int64_t)j * d);
+    float a0 = __ldg(p.b1 + j), a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < d / 4; ++i) {
+      const float4 wv = __ldg(w + i);
+      const float4 e = *reinterpret_cast<const float4*>(s_emb + 4 * i);
+      a0 = fmaf(wv.x, e.x, a0); a1 = fmaf(wv.y, e.y, a1); a2 = fmaf(wv.z, e.z, a2); a3 = fmaf(wv.w, e.w, a3);
+    }
+    const float a = (a0 + a1) + (a2 + a3);
     h1[(int64_t)b * d4 + j] = a;
     s_a1[j] = mish_f(a);
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < d; k += blockDim.x) {
-    const float* w = p.w2 + (int64_t)k * d4;
-    float a = __ldg(p.b2 + k);
-    for (int j = 0; j < d4; ++j) a = fmaf(__ldg(w + j), s_a1[j], a);
-    temb[(int64_t)b * d + k] = a;
-    act[(int64_t)b * d + k] = mish_f(a);
+  // layer 2: four threads per output, each over a quarter of the 4d inputs
+  for (int o = threadIdx.x; o < 4 * d; o += blockDim.x) {
+    const int k = o >> 2, part = o & 3;
+    const float4* w = reinterpret_cast<const float4*>(p.w2 + (int64_t)k * d4 + part * d);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < d / 4; ++i) {
+      const float4 wv = __ldg(w + i);
+      const float4 e = *reinterpret_cast<const float4*>(s_a1 + part * d + 4 * i);
+      a0 = fmaf(wv.x, e.x, a0); a1 = fmaf(wv.y, e.y, a1); a2 = fmaf(wv.z, e.z, a2); a3 = fmaf(wv.w, e.w, a3);
+    }
+    float a = (a0 + a1) + (a2 + a3);
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    if (part == 0) {
+      a += __ldg(p.b2 + k);
+      temb[(int64_t)b * d + k] = a;
+      act[(int64_t)b * d + k] = mish_f(a);
+    }
   }
 }
 
-// grid.x enumerates (projection, 32-channel slab) pairs via a prefix table walk
-__global__ void __launch_bounds__(256) time_proj_fwd_kernel(const TimeProj* __restrict__ table, int n_proj,
-                                                            const float* __restrict__ act, int dim, int B,
-                                                            int total, float* __restrict__ proj) {
-  extern __shared__ float ws[];   // [32][dim+1]
-  int slab = blockIdx.x, j = 0;
+constexpr int kProjSamples = 32;   // samples per CTA of the projection kernels
+
+// walk the projection table: slab (32 output channels) -> (projection j, first channel c0)
+__device__ __forceinline__ bool find_slab(const TimeProj* __restrict__ table, int n_proj, int slab, TimeProj& tp, int& c0) {
+  int j = 0;
   for (; j < n_proj; ++j) {
     const int ns = (table[j].cout + 31) / 32;
     if (slab < ns) break;
     slab -= ns;
   }
-  if (j >= n_proj) return;
-  const TimeProj tp = table[j];
-  const int c0 = slab * 32;
+  if (j >= n_proj) return false;
+  tp = table[j];
+  c0 = slab * 32;
+  return true;
+}
+
+// grid (slabs, ceil(B / 32)): proj[b][off + c] = bias[c] + sum_k W[c][k] * act[b][k]
+__global__ void __launch_bounds__(256) time_proj_fwd_kernel(const TimeProj* __restrict__ table, int n_proj,
+                                                            const float* __restrict__ act, int dim, int B,
+                                                            int total, float* __restrict__ proj) {
+  extern __shared__ __align__(16) float ws[];   // W[32][dim+1] | act[32][dim]
+  float* s_act = ws + 32 * (dim + 1);
+  TimeProj tp;
+  int c0;
+  if (!find_slab(table, n_proj, blockIdx.x, tp, c0)) return;
+  const int b0 = blockIdx.y * kProjSamples;
   for (int i = threadIdx.x; i < 32 * dim; i += blockDim.x) {
     const int c = i / dim, k = i - c * dim;
     ws[c * (dim + 1) + k] = (c0 + c < tp.cout) ? __ldg(tp.w + (int64_t)(c0 + c) * dim + k) : 0.f;
+    s_act[i] = (b0 + c < B) ? __ldg(act + (int64_t)(b0 + c) * dim + k) : 0.f;
   }
   __syncthreads();
   const int c = threadIdx.x & 31, bs = threadIdx.x >> 5;
   if (c0 + c >= tp.cout) return;
   const float bias = __ldg(tp.b + c0 + c);
-  for (int b = bs; b < B; b += 8) {
-    const float* a = act + (int64_t)b * dim;
-    float s = bias;
-#pragma unroll 8
-    for (int k = 0; k < dim; ++k) s = fmaf(ws[c * (dim + 1) + k], __ldg(a + k), s);
-    proj[(int64_t)b * total + tp.offset + c0 + c] = s;
+  float s[4] = {bias, bias, bias, bias};
+  for (int k = 0; k < dim; ++k) {
+    const float w = ws[c * (dim + 1) + k];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s[q] = fmaf(w, s_act[(bs + 8 * q) * dim + k], s[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int b = b0 + bs + 8 * q;
+    if (b < B) proj[(int64_t)b * total + tp.offset + c0 + c] = s[q];
   }
 }
 
-// (1) projection parameter gradients
-__global__ void __launch_bounds__(256) time_proj_wgrad_kernel(const TimeProj* __restrict__ table, int n_proj,
-                                                              const float* __restrict__ act, int dim, int B,
-                                                              int total, const float* __restrict__ d_proj) {
-  int slab = blockIdx.x, j = 0;
-  for (; j < n_proj; ++j) {
-    const int ns = (table[j].cout + 31) / 32;
-    if (slab < ns) break;
-    slab -= ns;
-  }
-  if (j >= n_proj) return;
-  const TimeProj tp = table[j];
-  const int c0 = slab * 32;
+// (1) grid (slabs, ceil(B / 32)).  For its 32 channels x 32 samples the CTA produces
+//     * the projection weight / bias gradients   gW[c][k] += sum_b dproj[b][c] * act[b][k]
+//     * its share of d_act[b][k] += sum_c dproj[b][c] * W[c][k]  (fp32 atomics into a zeroed accumulator)
+__global__ void __launch_bounds__(256) time_proj_bwd_kernel(const TimeProj* __restrict__ table, int n_proj,
+                                                            const float* __restrict__ act, int dim, int B, int total,
+                                                            const float* __restrict__ d_proj, float* __restrict__ d_act) {
+  extern __shared__ __align__(16) float ws[];   // W[32][dim+1] | act[32][dim+1] | dp[32 samples][33]
+  float* s_act = ws + 32 * (dim + 1);
+  float* s_dp = s_act + 32 * (dim + 1);
+  TimeProj tp;
+  int c0;
+  if (!find_slab(table, n_proj, blockIdx.x, tp, c0)) return;
+  const int b0 = blockIdx.y * kProjSamples;
   for (int i = threadIdx.x; i < 32 * dim; i += blockDim.x) {
-    const int c = c0 + i / dim, k = i % dim;
-    if (c >= tp.cout) continue;
+    const int c = i / dim, k = i - c * dim;
+    ws[c * (dim + 1) + k] = (c0 + c < tp.cout) ? __ldg(tp.w + (int64_t)(c0 + c) * dim + k) : 0.f;
+    s_act[c * (dim + 1) + k] = (b0 + c < B) ? __ldg(act + (int64_t)(b0 + c) * dim + k) : 0.f;
+  }
+  for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
+    const int bb = i >> 5, c = i & 31;
+    s_dp[bb * 33 + c] = (b0 + bb < B && c0 + c < tp.cout) ? __ldg(d_proj + (int64_t)(b0 + bb) * total + tp.offset + c0 + c) : 0.f;
+  }
+  __syncthreads();
+  // weight gradient: 32 x dim outputs
+  for (int o = threadIdx.x; o < 32 * dim; o += blockDim.x) {
+    const int c = o / dim, k = o - c * dim;
     float s = 0.f;
 #pragma unroll 8
-    for (int b = 0; b < B; ++b)
-      s = fmaf(__ldg(d_proj + (int64_t)b * total + tp.offset + c), __ldg(act + (int64_t)b * dim + k), s);
-    tp.gw[(int64_t)c * dim + k] += s;
+    for (int bb = 0; bb < 32; ++bb) s = fmaf(s_dp[bb * 33 + c], s_act[bb * (dim + 1) + k], s);
+    if (c0 + c < tp.cout) atomicAdd(tp.gw + (int64_t)(c0 + c) * dim + k, s);
   }
   if (threadIdx.x < 32 && c0 + threadIdx.x < tp.cout) {
-    const int c = c0 + threadIdx.x;
     float s = 0.f;
-    for (int b = 0; b < B; ++b) s += __ldg(d_proj + (int64_t)b * total + tp.offset + c);
-    tp.gb[c] += s;
+#pragma unroll 8
+    for (int bb = 0; bb < 32; ++bb) s += s_dp[bb * 33 + threadIdx.x];
+    atomicAdd(tp.gb + c0 + threadIdx.x, s);
+  }
+  // data gradient: 32 samples x dim outputs
+  for (int o = threadIdx.x; o < 32 * dim; o += blockDim.x) {
+    const int bb = o / dim, k = o - bb * dim;
+    float s = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < 32; ++c) s = fmaf(s_dp[bb * 33 + c], ws[c * (dim + 1) + k], s);
+    if (b0 + bb < B) atomicAdd(d_act + (int64_t)(b0 + bb) * dim + k, s);
   }
 }
 
-// (2) per-sample back-propagation to d_temb [B,d] and d_h1 [B,4d]; one CTA per sample
-__global__ void __launch_bounds__(256) time_bwd_sample_kernel(const TimeMlpParams p,
-                                                              const TimeProj* __restrict__ table, int n_proj,
-                                                              int total, const float* __restrict__ h1,
-                                                              const float* __restrict__ temb,
-                                                              const float* __restrict__ d_proj,
-                                                              float* __restrict__ d_temb, float* __restrict__ d_h1) {
-  extern __shared__ float sm[];   // dproj[total] | red[256] | dtemb[d]
+// (2) one CTA per sample: d_temb = d_act * mish'(temb) (and re-zero the accumulator); a1 = mish(h1);
+//     d_h1 = (d_temb . W2) * mish'(h1)
+__global__ void __launch_bounds__(256) time_bwd_sample_kernel(const TimeMlpParams p, const float* __restrict__ h1,
+                                                              const float* __restrict__ temb, float* __restrict__ d_act,
+                                                              float* __restrict__ d_temb, float* __restrict__ d_h1,
+                                                              float* __restrict__ a1) {
+  extern __shared__ __align__(16) float sm[];   // dtemb[d]
   const int d = p.dim, d4 = 4 * p.dim;
-  float* s_dp = sm;
-  float* s_red = sm + total;
-  float* s_dt = s_red + 256;
   const int b = blockIdx.x;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) s_dp[i] = __ldg(d_proj + (int64_t)b * total + i);
-  __syncthreads();
-  // d_act[k] = sum_{j,c} dproj[off_j + c] * W_j[c][k]
-  const int parts = blockDim.x / d;          // requires d <= 256 and 256 % d == 0
-  const int k = threadIdx.x % d, part = threadIdx.x / d;
-  float s = 0.f;
-  if (part < parts) {
-    for (int j = 0; j < n_proj; ++j) {
-      const TimeProj tp = table[j];
-#pragma unroll 8
-      for (int c = part; c < tp.cout; c += parts) s = fmaf(s_dp[tp.offset + c], __ldg(tp.w + (int64_t)c * d + k), s);
-    }
-  }
-  s_red[threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.x < d) {
-    float a = 0.f;
-    for (int q = 0; q < parts; ++q) a += s_red[q * d + threadIdx.x];
-    const float g = a * mish_grad_f(__ldg(temb + (int64_t)b * d + threadIdx.x));
-    s_dt[threadIdx.x] = g;
-    d_temb[(int64_t)b * d + threadIdx.x] = g;
+  for (int k = threadIdx.x; k < d; k += blockDim.x) {
+    const float g = d_act[(int64_t)b * d + k] * mish_grad_f(__ldg(temb + (int64_t)b * d + k));
+    d_act[(int64_t)b * d + k] = 0.f;
+    sm[k] = g;
+    d_temb[(int64_t)b * d + k] = g;
   }
   __syncthreads();
   for (int j = threadIdx.x; j < d4; j += blockDim.x) {
     float a = 0.f;
 #pragma unroll 8
-    for (int kk = 0; kk < d; ++kk) a = fmaf(s_dt[kk], __ldg(p.w2 + (int64_t)kk * d4 + j), a);
-    d_h1[(int64_t)b * d4 + j] = a * mish_grad_f(__ldg(h1 + (int64_t)b * d4 + j));
+    for (int kk = 0; kk < d; ++kk) a = fmaf(sm[kk], __ldg(p.w2 + (int64_t)kk * d4 + j), a);
+    const float h = __ldg(h1 + (int64_t)b * d4 + j);
+    d_h1[(int64_t)b * d4 + j] = a * mish_grad_f(h);
+    a1[(int64_t)b * d4 + j] = mish_f(h);
   }
 }
 
-// (3) time_mlp parameter gradients; one thread per weight element, loop over the batch
-__global__ void time_mlp_wgrad_kernel(const TimeMlpParams p, int B, const float* __restrict__ emb,
-                                      const float* __restrict__ h1, const float* __restrict__ d_temb,
-                                      const float* __restrict__ d_h1) {
+// (3) time_mlp parameter gradients as batch-reduced outer products, 32 x 32 output tiles:
+//     C[m][n] += sum_b A[b][m] * Bm[b][n]   (tiles 0..n2-1: gw2 = d_temb^T a1; then gw1 = d_h1^T emb); biases = column sums of A
+__global__ void __launch_bounds__(256) time_mlp_wgrad_kernel(const TimeMlpParams p, int B, const float* __restrict__ emb,
+                                                             const float* __restrict__ a1, const float* __restrict__ d_temb,
+                                                             const float* __restrict__ d_h1) {
+  __shared__ float As[32][33], Bs[32][33];
   const int d = p.dim, d4 = 4 * p.dim;
-  const int n2 = d * d4;          // w2 [d][4d]
-  const int n1 = d4 * d;          // w1 [4d][d]
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n2) {
-    const int k = i / d4, j = i - k * d4;
-    float s = 0.f;
+  const int tiles2 = (d / 32) * (d4 / 32);
+  int tile = blockIdx.x;
+  const float* A; const float* Bm; float* C; float* bias;
+  int lda, ldb, ldc, tn;
+  if (tile < tiles2) { A = d_temb; lda = d; Bm = a1; ldb = d4; C = p.gw2; ldc = d4; bias = p.gb2; tn = d4 / 32; }
+  else { tile -= tiles2; A = d_h1; lda = d4; Bm = emb; ldb = d; C = p.gw1; ldc = d; bias = p.gb1; tn = d / 32; }
+  const int m0 = (tile / tn) * 32, n0 = (tile % tn) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // thread -> column n0+tx, rows ty, ty+8, ty+16, ty+24
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float bsum = 0.f;
+  for (int b0 = 0; b0 < B; b0 += 32) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int bb = ty + 8 * q;
+      const bool ok = b0 + bb < B;
+      As[bb][tx] = ok ? __ldg(A + (int64_t)(b0 + bb) * lda + m0 + tx) : 0.f;
+      Bs[bb][tx] = ok ? __ldg(Bm + (int64_t)(b0 + bb) * ldb + n0 + tx) : 0.f;
+    }
+    __syncthreads();
 #pragma unroll 8
-    for (int b = 0; b < B; ++b)
-      s = fmaf(__ldg(d_temb + (int64_t)b * d + k), mish_f(__ldg(h1 + (int64_t)b * d4 + j)), s);
-    p.gw2[i] += s;
-  } else if (i < n2 + n1) {
-    const int r = i - n2;
-    const int j = r / d, ii = r - j * d;
-    float s = 0.f;
+    for (int bb = 0; bb < 32; ++bb) {
+      const float bv = Bs[bb][tx];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = fmaf(As[bb][ty + 8 * q], bv, acc[q]);
+    }
+    if (n0 == 0 && ty == 0) {
 #pragma unroll 8
-    for (int b = 0; b < B; ++b)
-      s = fmaf(__ldg(d_h1 + (int64_t)b * d4 + j), __ldg(emb + (int64_t)b * d + ii), s);
-    p.gw1[r] += s;
-  } else if (i < n2 + n1 + d) {
-    const int k = i - n2 - n1;
-    float s = 0.f;
-    for (int b = 0; b < B; ++b) s += __ldg(d_temb + (int64_t)b * d + k);
-    p.gb2[k] += s;
-  } else if (i < n2 + n1 + d + d4) {
-    const int j = i - n2 - n1 - d;
-    float s = 0.f;
-    for (int b = 0; b < B; ++b) s += __ldg(d_h1 + (int64_t)b * d4 + j);
-    p.gb1[j] += s;
+      for (int bb = 0; bb < 32; ++bb) bsum += As[bb][tx];
+    }
+    __syncthreads();
   }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) C[(int64_t)(m0 + ty + 8 * q) * ldc + n0 + tx] += acc[q];
+  if (n0 == 0 && ty == 0) bias[m0 + tx] += bsum;
 }
 
 }  // namespace
@@ -205,8 +247,8 @@ int launch_time_proj_forward(const LaunchCtx& lc, const TimeProj* d_table, int n
   // every projection width is a multiple of 32, so slabs = total / 32
   const int slabs = total / 32;
   ProfScope ps_(lc, K_TIME, 2.0 * B * dim * total, 0.0);
-  const size_t smem = (size_t)32 * (dim + 1) * sizeof(float);
-  time_proj_fwd_kernel<<<slabs, 256, smem, lc.stream>>>(d_table, n_proj, act, dim, B, total, proj);
+  const size_t smem = (size_t)(32 * (dim + 1) + 32 * dim) * sizeof(float);
+  time_proj_fwd_kernel<<<dim3(slabs, cdiv(B, kProjSamples)), 256, smem, lc.stream>>>(d_table, n_proj, act, dim, B, total, proj);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }
@@ -215,21 +257,21 @@ int launch_time_backward(const LaunchCtx& lc, const TimeMlpParams& p, const Time
                          int total, int B, const float* emb, const float* h1, const float* temb,
                          const float* act, const float* d_proj, float* ws) {
   const int d = p.dim, d4 = 4 * p.dim;
+  if (d % 32 != 0) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "time_mlp: dim must be a multiple of 32");
   float* d_temb = ws;
-  float* d_h1 = ws + (int64_t)B * d;
+  float* d_h1 = d_temb + (int64_t)B * d;
+  float* d_act = d_h1 + (int64_t)B * d4;   // accumulator: zero on entry, re-zeroed by time_bwd_sample_kernel
+  float* a1 = d_act + (int64_t)B * d;
   const int slabs = total / 32;
   ProfScope ps_(lc, K_TIME, 6.0 * B * d * total, 0.0);
-  time_proj_wgrad_kernel<<<slabs, 256, 0, lc.stream>>>(d_table, n_proj, act, d, B, total, d_proj);
+  const size_t smem = (size_t)(2 * 32 * (d + 1) + 32 * 33) * sizeof(float);
+  time_proj_bwd_kernel<<<dim3(slabs, cdiv(B, kProjSamples)), 256, smem, lc.stream>>>(d_table, n_proj, act, d, B, total,
+                                                                                       d_proj, d_act);
   IGM_POST_LAUNCH(lc);
-  const size_t smem = (size_t)(total + 256 + d) * sizeof(float);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(time_bwd_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(e));
-  }
-  time_bwd_sample_kernel<<<B, 256, smem, lc.stream>>>(p, d_table, n_proj, total, h1, temb, d_proj, d_temb, d_h1);
+  time_bwd_sample_kernel<<<B, 256, d * sizeof(float), lc.stream>>>(p, h1, temb, d_act, d_temb, d_h1, a1);
   IGM_POST_LAUNCH(lc);
-  const int n = 2 * d * d4 + d + d4;
-  time_mlp_wgrad_kernel<<<cdiv(n, 256), 256, 0, lc.stream>>>(p, B, emb, h1, d_temb, d_h1);
+  const int tiles = 2 * (d / 32) * (d4 / 32);
+  time_mlp_wgrad_kernel<<<tiles, 256, 0, lc.stream>>>(p, B, emb, a1, d_temb, d_h1);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }

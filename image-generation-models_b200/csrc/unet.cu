@@ -199,6 +199,7 @@ struct igm_ctx {
   float *t_emb = nullptr, *t_h1 = nullptr, *t_temb = nullptr, *t_act = nullptr, *t_proj = nullptr;
   float *t_dproj = nullptr, *t_ws = nullptr;
   float* gn_part = nullptr;
+  float* attn_ws = nullptr;   // per-chunk partials of the linear-attention kernels
   float *ws_group = nullptr, *ws_chan = nullptr, *ws_ln = nullptr;
   float *scrA = nullptr, *scrB = nullptr, *scrC = nullptr;
   __nv_bfloat16 *dy_hi = nullptr, *dy_lo = nullptr;         // bf16x2 staging of an output gradient
@@ -364,8 +365,8 @@ struct PlanBuilder {
   void track(int H, int W, int C) {
     maxMC = std::max(maxMC, M(H, W) * C);
     maxM = std::max(maxM, M(H, W));
-    const int64_t chunks = cdiv(H * W, kGnChunk);
-    maxGnWs = std::max(maxGnWs, (int64_t)B * chunks * 3 * C);
+    const int64_t chunks = cdiv(H * W, kGnChunkMin);
+    maxGnWs = std::max(maxGnWs, (int64_t)B * chunks * 4 * C);
   }
 
   ResnetL resnet(const std::string& name, int Cin, int Cout, int H, int W) {
@@ -506,6 +507,7 @@ struct PlanBuilder {
     tap("time_mlp", c.t_temb, d, 1, 1);
     const int64_t HW0 = (int64_t)cfg.height * cfg.width;
     c.gn_part = ar.alloc((int64_t)B * cdiv((int)HW0, 32) * kGroups * 2);   // 32-pixel slots (fused) or 64-pixel chunks
+    c.attn_ws = ar.alloc(linattn_ws_floats(B, (int)HW0));
     c.pred = ar.alloc((int64_t)B * cfg.channels * HW0);
     c.loss_ws = ar.alloc(1024);
     c.t_vec = reinterpret_cast<int64_t*>(ar.alloc(2 * (int64_t)B + 4));
@@ -515,8 +517,8 @@ struct PlanBuilder {
     c.pack_dev = reinterpret_cast<PackJob*>(ar.alloc((int64_t)(sizeof(PackJob) * 1024) / 4));
     if (training) {
       c.t_dproj = ar.alloc((int64_t)B * c.proj_total);
-      c.t_ws = ar.alloc((int64_t)B * 6 * d);
-      c.ws_group = ar.alloc((int64_t)B * cdiv((int)HW0, kGnChunk) * kGroups * 2);
+      c.t_ws = ar.alloc((int64_t)B * 10 * d);
+      c.ws_group = ar.alloc((int64_t)B * cdiv((int)HW0, kGnChunkMin) * kGroups * 2);
       c.ws_chan = ar.alloc(maxGnWs);
       c.ws_ln = ar.alloc((int64_t)ln_backward_parts(maxM) * 2 * 1024);
       c.scrA = ar.alloc(maxMC);
@@ -605,7 +607,7 @@ struct Runner {
   }
   // weight + bias gradients of a layer conv (forward inputs = its wired sources)
   int conv_wgrad(const ConvL& l, int IH, int IW, const float* d_out, int OH, int OW, int stride, int pad,
-                 bool dy_staged = false) {
+                 bool dy_staged = false, bool bias_done = false) {
     const int KK = l.K * l.K;
     float* gw = c.Gp(l.pw);
     const Act* s0 = l.src0;
@@ -639,8 +641,17 @@ struct Runner {
       w.sq = KK; w.sp = (int64_t)l.Cout * KK;
       IGM_TRY(launch_wgrad(lc, w));
     }
-    if (l.pb >= 0 && !l.bias_in_norm) IGM_TRY(launch_colsum(lc, d_out, M(OH, OW), l.Cout, c.Gp(l.pb)));
+    if (l.pb >= 0 && !l.bias_in_norm && !bias_done) IGM_TRY(launch_colsum(lc, d_out, M(OH, OW), l.Cout, c.Gp(l.pb)));
     return IGM_OK;
+  }
+  // stage dY as bf16 hi/lo; when the layer has its own bias gradient the column sums ride along (sets bias_done)
+  int stage_dy(const ConvL& l, const float* dY, int64_t m, bool& bias_done) {
+    bias_done = false;
+    if (l.pb >= 0 && !l.bias_in_norm && split_colsum_ok(l.Cout)) {
+      bias_done = true;
+      return launch_split_bf16_colsum(lc, dY, m, l.Cout, c.dy_hi, c.dy_lo, c.Gp(l.pb));
+    }
+    return launch_split_bf16(lc, dY, m, l.Cout, c.dy_hi, c.dy_lo, l.Cout, 0);
   }
 
   // Backward of a stride-1 conv: weight/bias gradients, then (if d0) the data gradient.  dY is staged
@@ -649,11 +660,12 @@ struct Runner {
                const float* add1, bool staged = false) {
     const int pad = (l.K - 1) / 2;
     const int C0 = l.src0->C, C1 = l.src1 ? l.src1->C : 0;
+    bool bias_done = false;
     if (!staged && tc_on() && (tcw_batch_ok(l.tc_w, B) || (d0 && l.tc_b.valid && C0 % 32 == 0))) {
-      IGM_TRY(launch_split_bf16(lc, dY, M(H, W), l.Cout, c.dy_hi, c.dy_lo, l.Cout, 0));
+      IGM_TRY(stage_dy(l, dY, M(H, W), bias_done));
       staged = true;
     }
-    IGM_TRY(conv_wgrad(l, H, W, dY, H, W, 1, pad, staged));
+    IGM_TRY(conv_wgrad(l, H, W, dY, H, W, 1, pad, staged, bias_done));
     if (d0) IGM_TRY(conv_dgrad(l, dY, H, W, H, W, 1, pad, d0, C0, d1, C1, add0, add1, staged));
     return IGM_OK;
   }
@@ -675,7 +687,9 @@ struct Runner {
     GnBwdArgs g;
     g.d_out = d_out; g.y = b.raw; g.stats = b.stats;
     g.gamma = c.Pp(b.gn_w); g.beta = c.Pp(b.gn_b);
-    g.dy = c.scrA; g.dgamma = c.Gp(b.gn_w); g.dbeta = c.Gp(b.gn_b);
+    // the fp32 copy of dy is only read by the SIMT fallbacks; the tcgen05 wgrad / dgrad read the bf16 hi/lo staging
+    const bool tc_only = tc_on() && tcw_batch_ok(b.conv.tc_w, B) && b.conv.tc_b.valid && b.conv.src0->C % 32 == 0;
+    g.dy = tc_only ? nullptr : c.scrA; g.dgamma = c.Gp(b.gn_w); g.dbeta = c.Gp(b.gn_b);
     g.dtemb = dtemb; g.dtemb_stride = c.proj_total;
     g.dbias = c.Gp(b.conv.pb);
     g.dy_hi = tc_on() ? c.dy_hi : nullptr; g.dy_lo = tc_on() ? c.dy_lo : nullptr;
@@ -722,7 +736,7 @@ struct Runner {
     const float* x = a.in->v;
     IGM_TRY(launch_ln_forward(lc, x, c.Pp(a.ln_g), c.Pp(a.ln_b), a.ln.v, m, a.C, hi(a.ln), lo(a.ln)));
     IGM_TRY(conv_fwd(a.qkv, H, W, H, W, 1, 0, a.qkv_t, nullptr));
-    IGM_TRY(launch_linattn_forward(lc, a.qkv_t, a.att.v, a.ctx, a.kstat, B, H * W, hi(a.att), lo(a.att)));
+    IGM_TRY(launch_linattn_forward(lc, a.qkv_t, a.att.v, a.ctx, a.kstat, B, H * W, c.attn_ws, hi(a.att), lo(a.att)));
     IGM_TRY(conv_fwd(a.outc, H, W, H, W, 1, 0, a.out.v, x, &a.out));
     return IGM_OK;
   }
@@ -731,7 +745,7 @@ struct Runner {
     const int64_t m = M(H, W);
     const float* d_out = a.out.g;
     IGM_TRY(conv_bwd(a.outc, H, W, d_out, c.scrB, nullptr, nullptr, nullptr));
-    IGM_TRY(launch_linattn_backward(lc, a.qkv_t, a.ctx, a.kstat, c.scrB, c.scrC, B, H * W));
+    IGM_TRY(launch_linattn_backward(lc, a.qkv_t, a.ctx, a.kstat, c.scrB, c.scrC, B, H * W, c.attn_ws));
     IGM_TRY(conv_bwd(a.qkv, H, W, c.scrC, c.scrA, nullptr, nullptr, nullptr));
     IGM_TRY(launch_ln_backward(lc, c.scrA, a.in->v, c.Pp(a.ln_g), d_out, dx, c.Gp(a.ln_g), c.Gp(a.ln_b), c.ws_ln, m, a.C));
     return IGM_OK;
@@ -760,13 +774,14 @@ struct Runner {
     const ConvL& l = rs.conv;
     const bool tcw = tc_on() && tcw_batch_ok(rs.tcw, B);
     const bool tcb = tc_on() && rs.n_tcb > 0;
+    bool bias_done = false;
     if (tcw || tcb)   // stage dY once for both tensor-core kernels
-      IGM_TRY(launch_split_bf16(lc, rs.out.g, M(rs.out.H, rs.out.W), l.Cout, c.dy_hi, c.dy_lo, l.Cout, 0));
+      IGM_TRY(stage_dy(l, rs.out.g, M(rs.out.H, rs.out.W), bias_done));
     if (tcw) {
       IGM_TRY(launch_wgrad_tc(lc, rs.tcw, B, c.Gp(l.pw)));
-      if (l.pb >= 0) IGM_TRY(launch_colsum(lc, rs.out.g, M(rs.out.H, rs.out.W), l.Cout, c.Gp(l.pb)));
+      if (l.pb >= 0 && !bias_done) IGM_TRY(launch_colsum(lc, rs.out.g, M(rs.out.H, rs.out.W), l.Cout, c.Gp(l.pb)));
     } else {
-      IGM_TRY(conv_wgrad(l, rs.Hin, rs.Win, rs.out.g, rs.out.H, rs.out.W, 2, 1));
+      IGM_TRY(conv_wgrad(l, rs.Hin, rs.Win, rs.out.g, rs.out.H, rs.out.W, 2, 1, false, bias_done));
     }
     if (tcb) {
       TcRun r;

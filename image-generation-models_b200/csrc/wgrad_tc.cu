@@ -45,7 +45,11 @@ struct WCfg {
   static constexpr int BN = NB * 64;
   static constexpr int STAGE_BYTES = (4 + 2 * NB) * BOX_BYTES;
   static constexpr int STAGES = (NB == 1) ? 4 : 3;
-  static constexpr int TMEM_COLS = BN;
+  // NB = 1: the hi and lo boxes of the plain operand (adjacent in smem) form ONE N = 128 MN-major operand, because
+  // tcgen05.mma at N = 64 issues at the N = 128 rate (tools/mma_rate_probe.cu): two instructions instead of three
+  static constexpr bool STACKED = (NB == 1);
+  static constexpr int ACC_COLS = STACKED ? 2 * BN : BN;
+  static constexpr int TMEM_COLS = ACC_COLS;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
@@ -148,7 +152,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tdy_hi, const __grid_constan
       if (lane == 0) {
         // D = f32, A = B = bf16, both operands MN-major (bits 15, 16), N >> 3 at bit 17, M >> 4 at bit 24
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                               ((uint32_t)(C::BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                               ((uint32_t)(C::ACC_COLS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t lbo = p.variant == 1 ? 1024u : (uint32_t)BOX_BYTES;
         const uint32_t sbo = p.variant == 1 ? (uint32_t)BOX_BYTES : 1024u;
         int stage = 0;
@@ -165,9 +169,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tdy_hi, const __grid_constan
             const uint32_t koff = ks * UMMA_K * 128;   // 16 pixel rows of 128 B
             const uint64_t dah = make_sw128_mn_desc(a_hi + koff, lbo, sbo), dal = make_sw128_mn_desc(a_lo + koff, lbo, sbo);
             const uint64_t dbh = make_sw128_mn_desc(b_hi + koff, lbo, sbo), dbl = make_sw128_mn_desc(b_lo + koff, lbo, sbo);
-            umma_bf16(tmem_base, dal, dbh, idesc, accum);
-            umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-            umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+            if (C::STACKED) {
+              umma_bf16(tmem_base, dal, dbh, idesc, accum);   // [s_lo*p_hi | s_lo*p_lo]
+              umma_bf16(tmem_base, dah, dbh, idesc, 1u);      // [s_hi*p_hi | s_hi*p_lo]
+            } else {
+              umma_bf16(tmem_base, dal, dbh, idesc, accum);
+              umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+              umma_bf16(tmem_base, dah, dbh, idesc, 1u);
+            }
             accum = 1u;
           }
           umma_commit(&empty[stage]);
@@ -188,6 +197,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tdy_hi, const __grid_constan
       for (int c0 = 0; c0 < C::BN; c0 += 32) {
         float v[32];
         tmem_ld_32x32(t_base + (uint32_t)c0, v);
+        if (C::STACKED) {
+          float w[32];
+          tmem_ld_32x32(t_base + (uint32_t)(C::BN + c0), w);
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) v[jj] += w[jj];
+        }
         if (blk_ok[j]) {
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) atomicAdd(g + (int64_t)(c0 + jj) * p.s_plain, v[jj]);
