@@ -157,6 +157,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
       // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major A/B,
       // N>>3 at bits 17-22, M>>4 at bits 24-28
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C::ACC_COLS >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // One thread issues every MMA: descriptors are formed by adding 16-byte-unit offsets to four descriptors built
+      // once (the 14-bit start-address field never carries out below 256 KB), so only a handful of scalar
+      // instructions separate two tcgen05.mma (the issue loop, not the tensor pipe, was the bottleneck otherwise).
+      const uint32_t s0 = smem_u32(smem);
+      const uint64_t dA_hi0 = make_sw128_desc(s0), dA_lo0 = make_sw128_desc(s0 + A_TILE_BYTES);
+      const uint64_t dB_hi0 = make_sw128_desc(s0 + 2 * A_TILE_BYTES);
+      const uint64_t dB_lo0 = make_sw128_desc(s0 + 2 * A_TILE_BYTES + C::B_TILE_BYTES);
+      constexpr uint32_t STAGE16 = (uint32_t)C::STAGE_BYTES >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -169,14 +177,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
         for (int it = 0; it < iters; ++it) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t a_hi = sa, a_lo = sa + A_TILE_BYTES;
-          const uint32_t b_hi = sa + 2 * A_TILE_BYTES, b_lo = b_hi + C::B_TILE_BYTES;
+          const uint32_t soff = (uint32_t)stage * STAGE16;
 #pragma unroll
           for (int k = 0; k < KC / UMMA_K; ++k) {
-            const uint32_t koff = k * UMMA_K * 2;   // bytes inside the 128-byte swizzle row
-            const uint64_t dah = make_sw128_desc(a_hi + koff), dal = make_sw128_desc(a_lo + koff);
-            const uint64_t dbh = make_sw128_desc(b_hi + koff), dbl = make_sw128_desc(b_lo + koff);
+            const uint32_t off = soff + (uint32_t)(k * UMMA_K * 2 >> 4);   // 32 bytes inside the 128-byte swizzle row
+            const uint64_t dah = dA_hi0 + off, dal = dA_lo0 + off;
+            const uint64_t dbh = dB_hi0 + off, dbl = dB_lo0 + off;
             if (C::STACKED) {
               umma_bf16(d_tmem, dal, dbh, idesc, accum);   // [a_lo*w_hi | a_lo*w_lo]
               umma_bf16(d_tmem, dah, dbh, idesc, 1u);      // [a_hi*w_hi | a_hi*w_lo]

@@ -105,6 +105,28 @@ bool tcw_batch_ok(const TcWgrad& t, int B);
 // grad (fp32) += G; both operands must already be staged as bf16 hi/lo in the planned buffers
 int launch_wgrad_tc(const LaunchCtx& lc, const TcWgrad& t, int B, float* grad, int variant = 0);
 
+// Halo-reuse weight gradients of the stride-1 3x3 convs (wgrad_halo.cu): one zero-padded dY tile per pixel
+// tile feeds all nine taps through shifted shared-memory descriptors; partial results are reduced into the
+// per-layer workspace ws[ky][kx][ci][co] and folded into the OIHW gradient by launch_wgrad_halo_finalize.
+struct TcWgradHalo {
+  bool valid = false;
+  alignas(64) CUtensorMap s_hi, s_lo, p_hi, p_lo, p1_hi, p1_lo;
+  int Cin = 0, Cout = 0, P0 = 0, H = 0, W = 0, Bmax = 0;
+  bool stacked = false;               // Cin == 64: the hi and lo copies of X form one M = 128 operand
+  int BH = 0, stages = 0;
+  int prows = 0, prows_pad = 0, p_blk_bytes = 0, s_box_bytes = 0, s_off = 0, stage_bytes = 0;
+  float* ws = nullptr;
+};
+struct HaloFinJob {
+  float* ws; float* grad; int Cin, Cout, tile_begin;
+};
+bool tcwh_eligible(int Cin, int Cout, int H, int W, int KH);
+int tcwh_plan(Status& st, TcWgradHalo& t, int Cin, int Cout, int H, int W, int Bmax, __nv_bfloat16* dy_hi,
+              __nv_bfloat16* dy_lo, __nv_bfloat16* x_hi, __nv_bfloat16* x_lo, int C0, __nv_bfloat16* x1_hi,
+              __nv_bfloat16* x1_lo, float* ws);
+int launch_wgrad_halo(const LaunchCtx& lc, const TcWgradHalo& t, int B);
+int launch_wgrad_halo_finalize(const LaunchCtx& lc, const HaloFinJob* d_jobs, int n_jobs, int total_tiles, double elems);
+
 // fp32 [M, C] -> bf16 hi / lo written at channel offset `coff` of rows with `cdst` channels
 int launch_split_bf16(const LaunchCtx& lc, const float* src, int64_t M, int C, __nv_bfloat16* hi,
                       __nv_bfloat16* lo, int cdst, int coff);

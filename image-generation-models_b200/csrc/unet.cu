@@ -7,6 +7,7 @@
 // can be captured into a CUDA graph (igm_ddpm_sample_loop does).
 #include <cuda.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -86,6 +87,9 @@ struct ConvL {
   __nv_bfloat16 *wf_hi = nullptr, *wf_lo = nullptr, *wb_hi = nullptr, *wb_lo = nullptr;
   TcConv tc_f, tc_b;
   TcWgrad tc_w;
+  bool tc_wh_ok = false;       // 3x3 stride-1: halo-reuse weight-gradient engine (wgrad_halo.cu)
+  TcWgradHalo tc_wh;
+  float* wg_ws = nullptr;      // its [3][3][Cin][Cout] reduction workspace
   bool bias_in_norm = false;   // bias gradient is produced by the GroupNorm backward that follows this conv
   const Act* src0 = nullptr;   // input tensor(s) of the layer (wired once the plan is final)
   const Act* src1 = nullptr;
@@ -204,6 +208,10 @@ struct igm_ctx {
   float *scrA = nullptr, *scrB = nullptr, *scrC = nullptr;
   __nv_bfloat16 *dy_hi = nullptr, *dy_lo = nullptr;         // bf16x2 staging of an output gradient
   bool tc_available = false;
+  HaloFinJob* fin_dev = nullptr;      // device job table of the halo-wgrad finalize pass
+  int fin_n = 0, fin_tiles = 0;
+  double fin_elems = 0;
+  bool halo_on = true;
   PackJob* pack_dev = nullptr;        // device job table of igm_unet_pack_weights
   int pack_n = 0, pack_engine = -1;
   int64_t pack_total = 0;
@@ -327,6 +335,8 @@ struct PlanBuilder {
       }
       l.tc_w_ok = training && tcw_eligible(Cin, Cout, H, W, K);
       if (l.tc_w_ok) maxDy = std::max(maxDy, M(H, W) * Cout);
+      l.tc_wh_ok = training && tcwh_eligible(Cin, Cout, H, W, K);
+      if (l.tc_wh_ok) l.wg_ws = ar.alloc(nw);
     }
     return l;
   }
@@ -515,6 +525,7 @@ struct PlanBuilder {
     c.sched_dev = reinterpret_cast<igm_schedule*>(ar.alloc(64));
     c.proj_dev = reinterpret_cast<TimeProj*>(ar.alloc((int64_t)(sizeof(TimeProj) * c.n_proj + 3) / 4 + 64));
     c.pack_dev = reinterpret_cast<PackJob*>(ar.alloc((int64_t)(sizeof(PackJob) * 1024) / 4));
+    c.fin_dev = reinterpret_cast<HaloFinJob*>(ar.alloc((int64_t)(sizeof(HaloFinJob) * 256) / 4));
     if (training) {
       c.t_dproj = ar.alloc((int64_t)B * c.proj_total);
       c.t_ws = ar.alloc((int64_t)B * 10 * d);
@@ -615,7 +626,8 @@ struct Runner {
     if (stride == 1 && tc_on() && tcw_batch_ok(l.tc_w, B)) {
       // tensor-core path: X is already staged (forward), dY is staged by the caller or here
       if (!dy_staged) IGM_TRY(launch_split_bf16(lc, d_out, M(OH, OW), l.Cout, c.dy_hi, c.dy_lo, l.Cout, 0));
-      IGM_TRY(launch_wgrad_tc(lc, l.tc_w, B, gw));
+      if (c.halo_on && l.tc_wh.valid) IGM_TRY(launch_wgrad_halo(lc, l.tc_wh, B));   // folded into gw by wgrad_finalize()
+      else IGM_TRY(launch_wgrad_tc(lc, l.tc_w, B, gw));
     } else if (!l.convT) {
       // Conv2d: P = d_out (pc = co), Q = input (qc = ci) gathered at oy*s - p + ky;  W[co][ci][tap]
       const Act* srcs[2] = {s0, s1};
@@ -867,6 +879,7 @@ struct Runner {
     time_params(tp);
     IGM_TRY(launch_time_backward(lc, tp, c.proj_dev, c.n_proj, c.proj_total, B, c.t_emb, c.t_h1, c.t_temb, c.t_act,
                                  c.t_dproj, c.t_ws));
+    if (tc_on() && c.halo_on) IGM_TRY(launch_wgrad_halo_finalize(lc, c.fin_dev, c.fin_n, c.fin_tiles, c.fin_elems));
     return IGM_OK;
   }
 };
@@ -959,6 +972,9 @@ static int plan_tc(igm_ctx* c) {
     if (l.tc_w_ok && staged)
       IGM_TRY(tcw_plan(c->st, l.tc_w, l.Cin, l.Cout, l.H, l.W, c->cfg.max_batch, l.K, pad, c->dy_hi, c->dy_lo, s0->hi,
                        s0->lo, s0->C, s1 ? s1->hi : nullptr, s1 ? s1->lo : nullptr));
+    if (l.tc_wh_ok && l.tc_w_ok && staged)
+      IGM_TRY(tcwh_plan(c->st, l.tc_wh, l.Cin, l.Cout, l.H, l.W, c->cfg.max_batch, c->dy_hi, c->dy_lo, s0->hi, s0->lo, s0->C,
+                        s1 ? s1->hi : nullptr, s1 ? s1->lo : nullptr, l.wg_ws));
     n_valid += (l.tc_f.valid ? 1 : 0) + (l.tc_b.valid ? 1 : 0) + (l.tc_w.valid ? 1 : 0);
     return IGM_OK;
   });
@@ -1085,6 +1101,11 @@ int igm_unet_create(igm_ctx** out, const igm_unet_cfg* cfg, int device) {
   build_plan(c, c->arena, &floats2);
   wire_plan(c);
   // tensor-core engine: on by default when the shapes allow it (IGM_CONV_ENGINE=0 forces the SIMT engine)
+  if (const char* ps = getenv("IGM_PREFER_SHARED")) {
+    if (ps[0] == '1') cudaDeviceSetCacheConfig(cudaFuncCachePreferShared);
+  }
+  const char* halo = getenv("IGM_WGRAD_HALO");
+  c->halo_on = !(halo && halo[0] == '0');
   const char* eng = getenv("IGM_CONV_ENGINE");
   if (!(eng && eng[0] == '0')) {
     if (plan_tc(c) != IGM_OK) {
@@ -1146,6 +1167,23 @@ int igm_unet_bind_params(igm_ctx* c, float* params, float* grads) {
   IGM_CUDA(c->st, cudaMemcpy(c->proj_dev, c->proj_host.data(), sizeof(TimeProj) * c->n_proj, cudaMemcpyHostToDevice));
   if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
   c->pack_engine = -1;   // job table holds raw parameter pointers: rebuild at the next pack
+  // halo weight-gradient workspaces -> OIHW gradients
+  c->fin_n = 0; c->fin_tiles = 0; c->fin_elems = 0;
+  if (grads) {
+    std::vector<HaloFinJob> jobs;
+    for_each_conv(c, [&](ConvL& l) -> int {
+      if (!l.tc_wh.valid) return IGM_OK;
+      HaloFinJob j{l.wg_ws, c->Gp(l.pw), l.Cin, l.Cout, c->fin_tiles};
+      c->fin_tiles += (l.Cin / 32) * (l.Cout / 32);
+      c->fin_elems += 9.0 * l.Cin * l.Cout;
+      jobs.push_back(j);
+      return IGM_OK;
+    });
+    if (jobs.size() > 256) IGM_FAIL(c->st, IGM_ERR_INVALID, "too many halo-wgrad layers");
+    if (!jobs.empty())
+      IGM_CUDA(c->st, cudaMemcpy(c->fin_dev, jobs.data(), jobs.size() * sizeof(HaloFinJob), cudaMemcpyHostToDevice));
+    c->fin_n = (int)jobs.size();
+  }
   return IGM_OK;
 }
 
@@ -1403,14 +1441,20 @@ int igm_profile_stop(igm_ctx* c, igm_profile_entry* out, int cap) {
     memset(&acc[k], 0, sizeof(acc[k]));
     strncpy(acc[k].name, kclass_name(k), sizeof(acc[k].name) - 1);
   }
+  // IGM_PROFILE_DUMP=<file>: also append one line per launch scope (index, class, ms, flops, bytes) for tuning
+  FILE* dump = nullptr;
+  if (const char* path = getenv("IGM_PROFILE_DUMP")) dump = fopen(path, "a");
+  int ridx = 0;
   for (auto& r : c->prof.recs) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
+    if (dump) fprintf(dump, "%d %s %.4f %.4g %.4g\n", ridx++, kclass_name(r.cls), ms, r.flops, r.bytes);
     acc[r.cls].launches += 1;
     acc[r.cls].ms += ms;
     acc[r.cls].flops += r.flops;
     acc[r.cls].bytes += r.bytes;
   }
+  if (dump) { fprintf(dump, "#\n"); fclose(dump); }
   c->prof.reset();
   int n = 0;
   for (int k = 0; k < K_NCLASS && n < cap; ++k)

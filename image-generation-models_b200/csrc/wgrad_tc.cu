@@ -155,20 +155,24 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tdy_hi, const __grid_constan
                                ((uint32_t)(C::ACC_COLS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t lbo = p.variant == 1 ? 1024u : (uint32_t)BOX_BYTES;
         const uint32_t sbo = p.variant == 1 ? (uint32_t)BOX_BYTES : 1024u;
+        // descriptors by offset arithmetic on four descriptors built once (see conv_tc.cu: the issue loop is one thread)
+        const uint32_t s0 = smem_u32(smem);
+        const uint64_t dA_hi0 = make_sw128_mn_desc(s0, lbo, sbo), dA_lo0 = make_sw128_mn_desc(s0 + 2 * BOX_BYTES, lbo, sbo);
+        const uint64_t dB_hi0 = make_sw128_mn_desc(s0 + 4 * BOX_BYTES, lbo, sbo);
+        const uint64_t dB_lo0 = make_sw128_mn_desc(s0 + (4 + NB) * BOX_BYTES, lbo, sbo);
+        constexpr uint32_t STAGE16 = (uint32_t)C::STAGE_BYTES >> 4;
         int stage = 0;
         uint32_t phase = 0;
         uint32_t accum = 0;
         for (int it = 0; it < n_stages_total; ++it) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t a_hi = sa, a_lo = sa + 2 * BOX_BYTES;
-          const uint32_t b_hi = sa + 4 * BOX_BYTES, b_lo = b_hi + NB * BOX_BYTES;
+          const uint32_t soff = (uint32_t)stage * STAGE16;
 #pragma unroll
           for (int ks = 0; ks < PIX / UMMA_K; ++ks) {
-            const uint32_t koff = ks * UMMA_K * 128;   // 16 pixel rows of 128 B
-            const uint64_t dah = make_sw128_mn_desc(a_hi + koff, lbo, sbo), dal = make_sw128_mn_desc(a_lo + koff, lbo, sbo);
-            const uint64_t dbh = make_sw128_mn_desc(b_hi + koff, lbo, sbo), dbl = make_sw128_mn_desc(b_lo + koff, lbo, sbo);
+            const uint32_t off = soff + (uint32_t)(ks * UMMA_K * 128 >> 4);   // 16 pixel rows of 128 B
+            const uint64_t dah = dA_hi0 + off, dal = dA_lo0 + off;
+            const uint64_t dbh = dB_hi0 + off, dbl = dB_lo0 + off;
             if (C::STACKED) {
               umma_bf16(tmem_base, dal, dbh, idesc, accum);   // [s_lo*p_hi | s_lo*p_lo]
               umma_bf16(tmem_base, dah, dbh, idesc, 1u);      // [s_hi*p_hi | s_hi*p_lo]
