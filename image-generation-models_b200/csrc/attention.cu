@@ -281,7 +281,9 @@ __global__ void __launch_bounds__(256, 3) linattn_bwd_rows_kernel(const float* _
                                                                const float* __restrict__ kstat,
                                                                const float* __restrict__ d_out,
                                                                const float* __restrict__ dctx_full,
-                                                               float* __restrict__ d_qkv, int N) {
+                                                               float* __restrict__ d_qkv, int N,
+                                                               __nv_bfloat16* __restrict__ d_hi,
+                                                               __nv_bfloat16* __restrict__ d_lo) {
   constexpr int SUB = 64;                      // rows staged at a time (three tiles must fit 48 KB of static smem)
   __shared__ __align__(16) float Xs[SUB][D];   // softmax(k)
   __shared__ __align__(16) float Ys[SUB][D];   // dO
@@ -311,7 +313,16 @@ __global__ void __launch_bounds__(256, 3) linattn_bwd_rows_kernel(const float* _
     __syncthreads();
     for (int nn = r; nn < rows; nn += 8) Xs[nn][c] = expf(Xs[nn][c] - kmax) * kinv;
     __syncthreads();
-    float* dqb = d_qkv + ((int64_t)b * N + n0) * QKV;
+    const int64_t obase = ((int64_t)b * N + n0) * QKV;
+    // gradient element -> fp32 tensor and/or the bf16 hi/lo staging copy the to_qkv backward convs read
+    auto emit = [&](int64_t o, float val) {
+      if (d_qkv) d_qkv[o] = val;
+      if (d_hi) {
+        const __nv_bfloat16 hv = __float2bfloat16_rn(val);
+        d_hi[o] = hv;
+        d_lo[o] = __float2bfloat16_rn(val - __bfloat162float(hv));
+      }
+    };
     float w[D];
     // dq = ctx[c][:] . dO[n][:]
 #pragma unroll
@@ -324,7 +335,7 @@ __global__ void __launch_bounds__(256, 3) linattn_bwd_rows_kernel(const float* _
         a0 = fmaf(w[j4], g4.x, a0); a1 = fmaf(w[j4 + 1], g4.y, a1);
         a0 = fmaf(w[j4 + 2], g4.z, a0); a1 = fmaf(w[j4 + 3], g4.w, a1);
       }
-      dqb[(int64_t)nn * QKV + qcol + c] = a0 + a1;
+      emit(obase + (int64_t)nn * QKV + qcol + c, a0 + a1);
     }
     // dk = p * (dctx[c][:] . v[n][:] - cdot)
 #pragma unroll
@@ -337,7 +348,7 @@ __global__ void __launch_bounds__(256, 3) linattn_bwd_rows_kernel(const float* _
         a0 = fmaf(w[j4], v4.x, a0); a1 = fmaf(w[j4 + 1], v4.y, a1);
         a0 = fmaf(w[j4 + 2], v4.z, a0); a1 = fmaf(w[j4 + 3], v4.w, a1);
       }
-      dqb[(int64_t)nn * QKV + kcol + c] = Xs[nn][c] * ((a0 + a1) - cdot);
+      emit(obase + (int64_t)nn * QKV + kcol + c, Xs[nn][c] * ((a0 + a1) - cdot));
     }
     // dv = dctx[:][c] . p[n][:]
 #pragma unroll
@@ -350,7 +361,7 @@ __global__ void __launch_bounds__(256, 3) linattn_bwd_rows_kernel(const float* _
         a0 = fmaf(w[j4], p4.x, a0); a1 = fmaf(w[j4 + 1], p4.y, a1);
         a0 = fmaf(w[j4 + 2], p4.z, a0); a1 = fmaf(w[j4 + 3], p4.w, a1);
       }
-      dqb[(int64_t)nn * QKV + vcol + c] = a0 + a1;
+      emit(obase + (int64_t)nn * QKV + vcol + c, a0 + a1);
     }
     __syncthreads();
   }
@@ -376,7 +387,8 @@ int launch_linattn_forward(const LaunchCtx& lc, const float* qkv, float* out, fl
 }
 
 int launch_linattn_backward(const LaunchCtx& lc, const float* qkv, const float* ctx, const float* kstat,
-                            const float* d_out, float* d_qkv, int B, int n, float* ws) {
+                            const float* d_out, float* d_qkv, int B, int n, float* ws, __nv_bfloat16* d_hi,
+                            __nv_bfloat16* d_lo) {
   const int nsplit = cdiv(n, CH);
   if (nsplit > kMaxSplit) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linear attention: more than 8192 pixels per image");
   ProfScope ps_(lc, K_ATTN, 8.0 * B * kHeads * (double)n * D * D, 4.0 * B * (double)n * (2 * QKV + HD));
@@ -385,7 +397,7 @@ int launch_linattn_backward(const LaunchCtx& lc, const float* qkv, const float* 
   float* parts = ws + (int64_t)B * kHeads * (64 + D * D);
   linattn_bwd_dctx_kernel<<<dim3(B * kHeads, nsplit), 256, 0, lc.stream>>>(qkv, d_out, parts, counters, dctx, n);
   IGM_POST_LAUNCH(lc);
-  linattn_bwd_rows_kernel<<<dim3(B * kHeads, nsplit), 256, 0, lc.stream>>>(qkv, ctx, kstat, d_out, dctx, d_qkv, n);
+  linattn_bwd_rows_kernel<<<dim3(B * kHeads, nsplit), 256, 0, lc.stream>>>(qkv, ctx, kstat, d_out, dctx, d_qkv, n, d_hi, d_lo);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }

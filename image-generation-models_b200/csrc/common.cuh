@@ -223,7 +223,9 @@ int linattn_ws_floats(int B, int n);
 int launch_linattn_forward(const LaunchCtx& lc, const float* qkv, float* out, float* ctx, float* kstat,
                            int B, int n, float* ws, __nv_bfloat16* out_hi = nullptr, __nv_bfloat16* out_lo = nullptr);
 int launch_linattn_backward(const LaunchCtx& lc, const float* qkv, const float* ctx, const float* kstat,
-                            const float* d_out, float* d_qkv, int B, int n, float* ws);
+                            const float* d_out, float* d_qkv, int B, int n, float* ws,
+                            __nv_bfloat16* d_hi = nullptr, __nv_bfloat16* d_lo = nullptr);
+// (d_qkv may be null when d_hi / d_lo are given: the gradient is then only emitted as the bf16 hi/lo staging copy)
 
 // ---------------------------------------------------------------------------
 // time embedding MLP (time_mlp.cu) — reference ddpm.py:47-59, :188-193, :126-130

@@ -757,8 +757,12 @@ struct Runner {
     const int64_t m = M(H, W);
     const float* d_out = a.out.g;
     IGM_TRY(conv_bwd(a.outc, H, W, d_out, c.scrB, nullptr, nullptr, nullptr));
-    IGM_TRY(launch_linattn_backward(lc, a.qkv_t, a.ctx, a.kstat, c.scrB, c.scrC, B, H * W, c.attn_ws));
-    IGM_TRY(conv_bwd(a.qkv, H, W, c.scrC, c.scrA, nullptr, nullptr, nullptr));
+    // to_qkv has no bias: when both of its backward convs run on the tensor cores they only read the bf16 hi/lo
+    // staging copy of d(qkv), which the attention backward then writes directly (no fp32 tensor, no split pass)
+    const bool direct = tc_on() && tcw_batch_ok(a.qkv.tc_w, B) && a.qkv.tc_b.valid && a.qkv.pb < 0;
+    IGM_TRY(launch_linattn_backward(lc, a.qkv_t, a.ctx, a.kstat, c.scrB, direct ? nullptr : c.scrC, B, H * W, c.attn_ws,
+                                    direct ? c.dy_hi : nullptr, direct ? c.dy_lo : nullptr));
+    IGM_TRY(conv_bwd(a.qkv, H, W, c.scrC, c.scrA, nullptr, nullptr, nullptr, direct));
     IGM_TRY(launch_ln_backward(lc, c.scrA, a.in->v, c.Pp(a.ln_g), d_out, dx, c.Gp(a.ln_g), c.Gp(a.ln_b), c.ws_ln, m, a.C));
     return IGM_OK;
   }

@@ -213,6 +213,9 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap ts_hi, const __grid_consta
       tc_fence_after();
       // The CTAs of one split group finish together and reduce into the same workspace: rotate the order in
       // which each CTA walks its (ky, 32-column chunk) pieces so that they do not hammer the same sectors.
+      // Stacked operand: accumulator rows r and r + 64 are the hi and lo halves of the SAME input channel; the
+      // lo-half warps hand their values over through the (now idle) pipeline memory, so each element is reduced once.
+      float* xbuf = reinterpret_cast<float*>(smem);   // [2 buffers][2 warps][32 values][32 lanes]
       const int nchunks = nky * 6;
       for (int it = 0; it < nchunks; ++it) {
         const int piece = (it + split) % nchunks;
@@ -221,6 +224,17 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap ts_hi, const __grid_consta
         const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(k * 192);
         float v[32];
         tmem_ld_32x32(t_base + (uint32_t)c0, v);
+        if (p.stacked) {
+          float* xb = xbuf + ((it & 1) * 2 + (q & 1)) * 1024 + lane;
+          if (q >= 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) xb[j * 32] = v[j];
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (q >= 2) continue;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += xb[j * 32];
+        }
         const int kx = 2 - c0 / 64;   // N block 0 <-> dx = -1 <-> kx = 2
         float* dst = p.ws + (((int64_t)(ky * 3 + kx) * p.Cin + ci) * p.Cout + co0 + (c0 & 63));
 #pragma unroll
@@ -257,10 +271,20 @@ __global__ void __launch_bounds__(1024) wgrad_halo_finalize_kernel(const HaloFin
     *src = 0.f;
   }
   __syncthreads();
-  // thread (tx = ci, ty = co): nine consecutive floats of the OIHW gradient
-  float* g = j.grad + ((int64_t)(co0 + ty) * j.Cin + ci0 + tx) * 9;
+  // OIHW gradient of this tile: 32 co rows x (32 ci x 9 taps = 288 contiguous floats), updated with 128-bit accesses
+  for (int i = threadIdx.x; i < 32 * 72; i += 1024) {
+    const int row = i / 72, q4 = i - row * 72;
+    float4* gp = reinterpret_cast<float4*>(j.grad + ((int64_t)(co0 + row) * j.Cin + ci0) * 9) + q4;
+    float4 g = *gp;
+    float* ge = reinterpret_cast<float*>(&g);
 #pragma unroll
-  for (int tap = 0; tap < 9; ++tap) g[tap] += tile[tap][tx][ty];
+    for (int e = 0; e < 4; ++e) {
+      const int f = q4 * 4 + e;
+      const int ci = f / 9, tap = f - ci * 9;
+      ge[e] += tile[tap][ci][row];
+    }
+    *gp = g;
+  }
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 encode_fn_h() {

@@ -208,8 +208,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tdy_hi, const __grid_constan
           for (int jj = 0; jj < 32; ++jj) v[jj] += w[jj];
         }
         if (blk_ok[j]) {
+          if (p.s_plain == 1) {
+            // 1x1 convolutions: the plain-operand channels are contiguous in the gradient -> 128-bit reductions
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) atomicAdd(g + (int64_t)(c0 + jj) * p.s_plain, v[jj]);
+            for (int jj = 0; jj < 32; jj += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g + c0 + jj), "f"(v[jj]), "f"(v[jj + 1]),
+                           "f"(v[jj + 2]), "f"(v[jj + 3]) : "memory");
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) atomicAdd(g + (int64_t)(c0 + jj) * p.s_plain, v[jj]);
+          }
         }
       }
     }
@@ -373,7 +381,8 @@ int launch_wgrad_tc(const LaunchCtx& lc, const TcWgrad& t, int B, float* grad, i
   a.n_ci_tiles = t.CP / t.BN;
   const int base = a.n_pairs * a.n_ci_tiles;
   // one CTA per SM (192 KB of smem): aim at <= 2 full waves of 148 CTAs, never a ragged third one
-  int splits = (2 * 148) / base;
+  // (1x1 convs: a single wave -- their cost is dominated by the reduction traffic, which grows with the CTA count)
+  int splits = ((t.s_plain == 1 ? 1 : 2) * 148) / base;
   if (splits > a.n_ptiles) splits = a.n_ptiles;
   if (splits < 1) splits = 1;
   a.tiles_per_split = cdiv(a.n_ptiles, splits);
