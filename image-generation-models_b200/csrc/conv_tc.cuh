@@ -125,7 +125,8 @@ int tcwh_plan(Status& st, TcWgradHalo& t, int Cin, int Cout, int H, int W, int B
               __nv_bfloat16* dy_lo, __nv_bfloat16* x_hi, __nv_bfloat16* x_lo, int C0, __nv_bfloat16* x1_hi,
               __nv_bfloat16* x1_lo, float* ws);
 int launch_wgrad_halo(const LaunchCtx& lc, const TcWgradHalo& t, int B);
-int launch_wgrad_halo_finalize(const LaunchCtx& lc, const HaloFinJob* d_jobs, int n_jobs, int total_tiles, double elems);
+// tile_begin = first CTA of the layer; d_cta_job[cta] = layer index (a layer spans (Cin/32)*(Cout/32) CTAs)
+int launch_wgrad_halo_finalize(const LaunchCtx& lc, const HaloFinJob* d_jobs, const int* d_cta_job, int n_ctas, double elems);
 
 // fp32 [M, C] -> bf16 hi / lo written at channel offset `coff` of rows with `cdst` channels
 int launch_split_bf16(const LaunchCtx& lc, const float* src, int64_t M, int C, __nv_bfloat16* hi,

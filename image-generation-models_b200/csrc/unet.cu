@@ -209,6 +209,8 @@ struct igm_ctx {
   __nv_bfloat16 *dy_hi = nullptr, *dy_lo = nullptr;         // bf16x2 staging of an output gradient
   bool tc_available = false;
   HaloFinJob* fin_dev = nullptr;      // device job table of the halo-wgrad finalize pass
+  int* fin_cta_dev = nullptr;         // CTA -> job
+  int fin_cta_cap = 0;
   int fin_n = 0, fin_tiles = 0;
   double fin_elems = 0;
   bool halo_on = true;
@@ -283,7 +285,7 @@ struct PlanBuilder {
   Arena ar;
   bool training;
   int B;
-  int64_t maxMC = 0, maxM = 0, maxGnWs = 0, maxDy = 0;
+  int64_t maxMC = 0, maxM = 0, maxGnWs = 0, maxDy = 0, halo_w_elems = 0;
 
   PlanBuilder(igm_ctx& ctx, float* base) : c(ctx), pb{ctx.params} {
     ar.base = base;
@@ -336,7 +338,7 @@ struct PlanBuilder {
       l.tc_w_ok = training && tcw_eligible(Cin, Cout, H, W, K);
       if (l.tc_w_ok) maxDy = std::max(maxDy, M(H, W) * Cout);
       l.tc_wh_ok = training && tcwh_eligible(Cin, Cout, H, W, K);
-      if (l.tc_wh_ok) l.wg_ws = ar.alloc(nw);
+      if (l.tc_wh_ok) halo_w_elems += nw;   // workspaces are carved from ONE contiguous block (build_plan)
     }
     return l;
   }
@@ -526,6 +528,8 @@ struct PlanBuilder {
     c.proj_dev = reinterpret_cast<TimeProj*>(ar.alloc((int64_t)(sizeof(TimeProj) * c.n_proj + 3) / 4 + 64));
     c.pack_dev = reinterpret_cast<PackJob*>(ar.alloc((int64_t)(sizeof(PackJob) * 1024) / 4));
     c.fin_dev = reinterpret_cast<HaloFinJob*>(ar.alloc((int64_t)(sizeof(HaloFinJob) * 256) / 4));
+    c.fin_cta_cap = (int)(halo_w_elems / 1024) + 64;
+    c.fin_cta_dev = reinterpret_cast<int*>(ar.alloc(c.fin_cta_cap));
     if (training) {
       c.t_dproj = ar.alloc((int64_t)B * c.proj_total);
       c.t_ws = ar.alloc((int64_t)B * 10 * d);
@@ -883,7 +887,7 @@ struct Runner {
     time_params(tp);
     IGM_TRY(launch_time_backward(lc, tp, c.proj_dev, c.n_proj, c.proj_total, B, c.t_emb, c.t_h1, c.t_temb, c.t_act,
                                  c.t_dproj, c.t_ws));
-    if (tc_on() && c.halo_on) IGM_TRY(launch_wgrad_halo_finalize(lc, c.fin_dev, c.fin_n, c.fin_tiles, c.fin_elems));
+    if (tc_on() && c.halo_on) IGM_TRY(launch_wgrad_halo_finalize(lc, c.fin_dev, c.fin_cta_dev, c.fin_n > 0 ? c.fin_tiles : 0, c.fin_elems));
     return IGM_OK;
   }
 };
@@ -1051,6 +1055,19 @@ static int build_plan(igm_ctx* c, float* base, int64_t* floats_out) {
       c->skip_g[i] = pb.ar.alloc((int64_t)c->cfg.max_batch * a.H * a.W * a.C);
     }
   }
+  // halo-wgrad workspaces: one contiguous block (the finalize pass walks all of them; scattered over the
+  // multi-GB arena it was TLB-latency bound)
+  {
+    float* blk = pb.ar.alloc(pb.halo_w_elems + 64);
+    int64_t off = 0;
+    for_each_conv(c, [&](ConvL& l) -> int {
+      if (l.tc_wh_ok) {
+        l.wg_ws = blk ? blk + off : nullptr;
+        off += (int64_t)l.K * l.K * l.Cin * l.Cout;
+      }
+      return IGM_OK;
+    });
+  }
   *floats_out = pb.ar.used;
   return IGM_OK;
 }
@@ -1175,17 +1192,22 @@ int igm_unet_bind_params(igm_ctx* c, float* params, float* grads) {
   c->fin_n = 0; c->fin_tiles = 0; c->fin_elems = 0;
   if (grads) {
     std::vector<HaloFinJob> jobs;
+    std::vector<int> cta_job;
     for_each_conv(c, [&](ConvL& l) -> int {
       if (!l.tc_wh.valid) return IGM_OK;
       HaloFinJob j{l.wg_ws, c->Gp(l.pw), l.Cin, l.Cout, c->fin_tiles};
-      c->fin_tiles += (l.Cin / 32) * (l.Cout / 32);
+      const int n_ctas = (l.Cin / 32) * (l.Cout / 32);   // one CTA per 32 x 32 (ci, co) tile
+      c->fin_tiles += n_ctas;
       c->fin_elems += 9.0 * l.Cin * l.Cout;
+      cta_job.insert(cta_job.end(), n_ctas, (int)jobs.size());
       jobs.push_back(j);
       return IGM_OK;
     });
-    if (jobs.size() > 256) IGM_FAIL(c->st, IGM_ERR_INVALID, "too many halo-wgrad layers");
-    if (!jobs.empty())
+    if (jobs.size() > 256 || (int)cta_job.size() > c->fin_cta_cap) IGM_FAIL(c->st, IGM_ERR_INVALID, "too many halo-wgrad layers");
+    if (!jobs.empty()) {
       IGM_CUDA(c->st, cudaMemcpy(c->fin_dev, jobs.data(), jobs.size() * sizeof(HaloFinJob), cudaMemcpyHostToDevice));
+      IGM_CUDA(c->st, cudaMemcpy(c->fin_cta_dev, cta_job.data(), cta_job.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     c->fin_n = (int)jobs.size();
   }
   return IGM_OK;

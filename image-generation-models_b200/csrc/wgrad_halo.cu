@@ -251,24 +251,23 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap ts_hi, const __grid_consta
   }
 }
 
-// grad[co][ci][tap] += ws[tap][ci][co]; ws = 0.   One CTA per 32(ci) x 32(co) tile of one layer.
-__global__ void __launch_bounds__(1024) wgrad_halo_finalize_kernel(const HaloFinJob* __restrict__ jobs, int n_jobs) {
+// grad[co][ci][tap] += ws[tap][ci][co]; ws = 0.   One CTA per 32(ci) x 32(co) tile of one layer (transposed
+// through shared memory so that both sides move whole 128-byte lines); CTA -> layer through a per-CTA table.
+__global__ void __launch_bounds__(1024) wgrad_halo_finalize_kernel(const HaloFinJob* __restrict__ jobs,
+                                                                   const int* __restrict__ cta_job) {
   __shared__ float tile[9][32][33];
-  int lo = 0, hi = n_jobs - 1;
-  while (lo < hi) {   // last job whose first tile <= blockIdx.x
-    const int mid = (lo + hi + 1) >> 1;
-    if (jobs[mid].tile_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
-  }
-  const HaloFinJob j = jobs[lo];
+  const HaloFinJob j = jobs[cta_job[blockIdx.x]];
   const int t = blockIdx.x - j.tile_begin;
   const int tco = j.Cout / 32;
   const int ci0 = (t / tco) * 32, co0 = (t % tco) * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float v[9];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) v[tap] = j.ws[((int64_t)tap * j.Cin + ci0 + ty) * j.Cout + co0 + tx];
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
-    float* src = j.ws + ((int64_t)tap * j.Cin + ci0 + ty) * j.Cout + co0 + tx;
-    tile[tap][ty][tx] = *src;
-    *src = 0.f;
+    j.ws[((int64_t)tap * j.Cin + ci0 + ty) * j.Cout + co0 + tx] = 0.f;
+    tile[tap][ty][tx] = v[tap];
   }
   __syncthreads();
   // OIHW gradient of this tile: 32 co rows x (32 ci x 9 taps = 288 contiguous floats), updated with 128-bit accesses
@@ -420,10 +419,10 @@ int launch_wgrad_halo(const LaunchCtx& lc, const TcWgradHalo& t, int B) {
   return IGM_OK;
 }
 
-int launch_wgrad_halo_finalize(const LaunchCtx& lc, const HaloFinJob* d_jobs, int n_jobs, int total_tiles, double elems) {
-  if (n_jobs <= 0 || total_tiles <= 0) return IGM_OK;
+int launch_wgrad_halo_finalize(const LaunchCtx& lc, const HaloFinJob* d_jobs, const int* d_cta_job, int n_ctas, double elems) {
+  if (n_ctas <= 0) return IGM_OK;
   ProfScope ps_(lc, K_CONV_WGRAD, elems, 16.0 * elems);
-  wgrad_halo_finalize_kernel<<<total_tiles, 1024, 0, lc.stream>>>(d_jobs, n_jobs);
+  wgrad_halo_finalize_kernel<<<n_ctas, 1024, 0, lc.stream>>>(d_jobs, d_cta_job);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }
