@@ -7,6 +7,9 @@
 // LayerNorm (:85-95) and their autograd.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 namespace igm {
 namespace {
 
@@ -256,6 +259,135 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdArgs a, in
     }
   }
 }
+// ---- backward, fused: one thread-block cluster per sample ----------------------------------------
+// The two-pass scheme above reads y and d_out twice and needs three launches.  When a sample splits into
+// CS <= 8 CTAs of exactly 8192 elements, each thread keeps its NV = 8 float4 of (n, dn) in registers, the
+// group sums cross the cluster through distributed shared memory, and dy / the parameter gradients come out of
+// the same kernel: y and d_out are read once.  NV = float4 per thread (8 unless the tensor is too small).
+template <int GN_NV>
+__global__ void __launch_bounds__(256) gn_bwd_fused_kernel(const GnBwdArgs a, int cs) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ float sm[256][2];
+  __shared__ float cl_grp[kGroups][2];    // this CTA's (sum dn, sum dn*n) per group, read by the whole cluster
+  __shared__ float s_m[kGroups][2];
+  __shared__ float4 sc[256][4];           // per-thread channel partials -> per-channel CTA totals in sc[0..L)
+  const GnLayout ly(a.C);
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.x / cs;
+  const int npix = a.HW / cs;             // pixels of this CTA: NV * PPI
+  const int p0 = rank * npix;
+  const float mean = __ldg(a.stats + ((int64_t)b * kGroups + ly.group) * 2 + 0);
+  const float rstd = __ldg(a.stats + ((int64_t)b * kGroups + ly.group) * 2 + 1);
+  const int c = ly.c4 * 4;
+  const float4 ga4 = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
+  const float4 be4 = __ldg(reinterpret_cast<const float4*>(a.beta + c));
+  const float ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w};
+  const float be[4] = {be4.x, be4.y, be4.z, be4.w};
+  float4 nv[GN_NV], dnv[GN_NV];
+  const int64_t base = ((int64_t)b * a.HW + p0 + ly.pslot) * a.C + c;
+  const int64_t step = (int64_t)ly.PPI * a.C;
+#pragma unroll
+  for (int i = 0; i < GN_NV; ++i) {
+    nv[i] = __ldg(reinterpret_cast<const float4*>(a.y + base + i * step));
+    dnv[i] = __ldg(reinterpret_cast<const float4*>(a.d_out + base + i * step));
+  }
+  float dgam[4] = {0.f, 0.f, 0.f, 0.f}, dbet[4] = {0.f, 0.f, 0.f, 0.f}, dte[4] = {0.f, 0.f, 0.f, 0.f};
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < GN_NV; ++i) {
+    float* yv = reinterpret_cast<float*>(&nv[i]);
+    float* dv = reinterpret_cast<float*>(&dnv[i]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float n = (yv[j] - mean) * rstd;
+      const float g = n * ga[j] + be[j];
+      const float dg = dv[j] * mish_grad_f(g);
+      dgam[j] += dg * n;
+      dbet[j] += dg;
+      dte[j] += dv[j];
+      const float dn = dg * ga[j];
+      s1 += dn;
+      s2 += dn * n;
+      yv[j] = n;
+      dv[j] = dn;
+    }
+  }
+  float r1, r2;
+  group_reduce2(ly, s1, s2, sm, r1, r2);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { cl_grp[w][0] = r1; cl_grp[w][1] = r2; }
+  cluster.sync();
+  if (threadIdx.x < kGroups * 2) {
+    const int g = threadIdx.x >> 1, k = threadIdx.x & 1;
+    float t = 0.f;
+    for (int r = 0; r < cs; ++r) t += cluster.map_shared_rank(&cl_grp[0][0], r)[g * 2 + k];   // fixed order
+    s_m[g][k] = t / ((float)a.HW * ly.cpg);
+  }
+  __syncthreads();
+  const float m1 = s_m[ly.group][0], m2 = s_m[ly.group][1];
+  float dbs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < GN_NV; ++i) {
+    const float* n = reinterpret_cast<const float*>(&nv[i]);
+    const float* dn = reinterpret_cast<const float*>(&dnv[i]);
+    float4 o;
+    o.x = rstd * (dn[0] - m1 - n[0] * m2);
+    o.y = rstd * (dn[1] - m1 - n[1] * m2);
+    o.z = rstd * (dn[2] - m1 - n[2] * m2);
+    o.w = rstd * (dn[3] - m1 - n[3] * m2);
+    dbs[0] += o.x; dbs[1] += o.y; dbs[2] += o.z; dbs[3] += o.w;
+    const int64_t off = base + i * step;
+    if (a.dy) *reinterpret_cast<float4*>(a.dy + off) = o;
+    if (a.dy_hi) store_split4(a.dy_hi, a.dy_lo, off, o);
+  }
+  // per-channel sums: fold the pixel slots of the CTA, then the CTAs of the cluster (rank 0), then one atomic per
+  // (sample, channel) -- dtemb is per sample and written directly
+  sc[threadIdx.x][0] = make_float4(dgam[0], dgam[1], dgam[2], dgam[3]);
+  sc[threadIdx.x][1] = make_float4(dbet[0], dbet[1], dbet[2], dbet[3]);
+  sc[threadIdx.x][2] = make_float4(dte[0], dte[1], dte[2], dte[3]);
+  sc[threadIdx.x][3] = make_float4(dbs[0], dbs[1], dbs[2], dbs[3]);
+  __syncthreads();
+  float4 acc[4];
+  if (threadIdx.x < ly.L) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = sc[threadIdx.x][k];
+    for (int sl = 1; sl < ly.PPI; ++sl) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 v = sc[sl * ly.L + threadIdx.x][k];
+        acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < ly.L) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sc[threadIdx.x][k] = acc[k];
+  }
+  cluster.sync();
+  if (rank == 0 && threadIdx.x < ly.L) {
+    for (int r = 1; r < cs; ++r) {
+      const float4* rs = cluster.map_shared_rank(&sc[0][0], r) + threadIdx.x * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 v = rs[k];
+        acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+      }
+    }
+    atomicAdd(a.dgamma + c + 0, acc[0].x); atomicAdd(a.dgamma + c + 1, acc[0].y);
+    atomicAdd(a.dgamma + c + 2, acc[0].z); atomicAdd(a.dgamma + c + 3, acc[0].w);
+    atomicAdd(a.dbeta + c + 0, acc[1].x); atomicAdd(a.dbeta + c + 1, acc[1].y);
+    atomicAdd(a.dbeta + c + 2, acc[1].z); atomicAdd(a.dbeta + c + 3, acc[1].w);
+    if (a.dtemb) *reinterpret_cast<float4*>(a.dtemb + (int64_t)b * a.dtemb_stride + c) = acc[2];
+    if (a.dbias) {
+      atomicAdd(a.dbias + c + 0, acc[3].x); atomicAdd(a.dbias + c + 1, acc[3].y);
+      atomicAdd(a.dbias + c + 2, acc[3].z); atomicAdd(a.dbias + c + 3, acc[3].w);
+    }
+  }
+  cluster.sync();   // remote shared memory stays valid until rank 0 has read it
+}
+
 // ---- backward, pass 3: parameter / time-embedding gradients -------------------
 // grid (C/32 column slabs, B samples), block (32, 8): each CTA folds the chunk partials of one
 // sample; dtemb[b, c] is written directly, dgamma/dbeta get one atomic per (sample, channel).
@@ -669,8 +801,52 @@ int launch_gn_apply(const LaunchCtx& lc, const float* y, const float* part, cons
   return IGM_OK;
 }
 
+// cluster size and float4-per-thread of the fused backward (0: shape not covered -> two-pass path)
+static int gn_fused_cluster(const GnBwdArgs& a, int& nv) {
+  const int64_t E = (int64_t)a.HW * a.C;
+  if (a.dtemb && (a.dtemb_stride % 4 != 0)) return 0;
+  const int ppi = 256 / (a.C >> 2);
+  for (int v : {8, 4, 2, 1}) {   // large per-thread tiles first: clusters of 8 measured slower than 8 float4 per thread
+    if (E % (1024 * v) != 0) continue;
+    const int64_t cs = E / (1024 * v);
+    if (cs != 1 && cs != 2 && cs != 4 && cs != 8) continue;
+    if (a.HW % cs != 0 || a.HW / cs != v * ppi) continue;
+    nv = v;
+    return (int)cs;
+  }
+  return 0;
+}
+
 int launch_gn_backward(const LaunchCtx& lc, const GnBwdArgs& a) {
   IGM_TRY(check_gn_shape(lc, a.C));
+  static const bool fused_off = [] { const char* e = getenv("IGM_GN_FUSED"); return e && e[0] == '0'; }();
+  int nv = 0;
+  const int cs = fused_off ? 0 : gn_fused_cluster(a, nv);
+  if (cs > 0) {
+    ProfScope ps_(lc, K_NORM, 80.0 * a.B * a.HW * a.C, 4.0 * a.B * a.HW * a.C * 3);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(a.B * cs));
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = lc.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e;
+    switch (nv) {
+      case 1: e = cudaLaunchKernelEx(&cfg, gn_bwd_fused_kernel<1>, a, cs); break;
+      case 2: e = cudaLaunchKernelEx(&cfg, gn_bwd_fused_kernel<2>, a, cs); break;
+      case 4: e = cudaLaunchKernelEx(&cfg, gn_bwd_fused_kernel<4>, a, cs); break;
+      default: e = cudaLaunchKernelEx(&cfg, gn_bwd_fused_kernel<8>, a, cs); break;
+    }
+    if (e != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(e));
+    IGM_POST_LAUNCH(lc);
+    return IGM_OK;
+  }
   const int kGnChunk = gn_chunk(a.B, a.HW, a.C);
   const int nchunks = cdiv(a.HW, kGnChunk);
   ProfScope ps_(lc, K_NORM, 80.0 * a.B * a.HW * a.C, 4.0 * a.B * a.HW * a.C * 5);
