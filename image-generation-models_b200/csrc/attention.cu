@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256) linattn_out_kernel(const float* __restric
     }
     const float a = a0 + a1;
     const int64_t o = ((int64_t)b * N + n0 + nn) * HD + h * D + e;
-    out[o] = a;
+    if (out) out[o] = a;
     if (out_hi) {
       const __nv_bfloat16 hv = __float2bfloat16_rn(a);
       out_hi[o] = hv;

@@ -373,6 +373,12 @@ __global__ void __launch_bounds__(256) split_colsum_kernel(const float* __restri
   }
 }
 
+__global__ void merge_bf16_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                  float* __restrict__ dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
+}
+
 __global__ void pack_weight_tc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
                                       __nv_bfloat16* __restrict__ lo, int taps, int K, int N, int64_t sk, int64_t sn,
                                       int flip) {
@@ -652,6 +658,14 @@ int launch_split_bf16(const LaunchCtx& lc, const float* src, int64_t M, int C, _
   if (blocks > 148 * 16) blocks = 148 * 16;
   ProfScope ps_(lc, K_ELEM, 2.0 * M * C, 8.0 * M * C);
   split_bf16_kernel<<<blocks, 256, 0, lc.stream>>>(src, M, C, hi, lo, cdst, coff);
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+int launch_merge_bf16(const LaunchCtx& lc, const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* dst, int64_t n) {
+  int blocks = (int)cdiv64(n, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  merge_bf16_kernel<<<blocks, 256, 0, lc.stream>>>(hi, lo, dst, n);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }

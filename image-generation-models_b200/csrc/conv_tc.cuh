@@ -132,6 +132,8 @@ int launch_wgrad_halo_finalize(const LaunchCtx& lc, const HaloFinJob* d_jobs, co
 int launch_split_bf16(const LaunchCtx& lc, const float* src, int64_t M, int C, __nv_bfloat16* hi,
                       __nv_bfloat16* lo, int cdst, int coff);
 
+// dst = hi + lo (debug taps of tensors whose fp32 copy was skipped)
+int launch_merge_bf16(const LaunchCtx& lc, const __nv_bfloat16* hi, const __nv_bfloat16* lo, float* dst, int64_t n);
 // the same split (dense rows, cdst = C) fused with colsum[c] += sum_m src[m][c]; C must satisfy split_colsum_ok
 bool split_colsum_ok(int C);
 int launch_split_bf16_colsum(const LaunchCtx& lc, const float* src, int64_t M, int C, __nv_bfloat16* hi,

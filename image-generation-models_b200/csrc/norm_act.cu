@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
       const float4 r = __ldg(reinterpret_cast<const float4*>(res + off));
       o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
     }
-    *reinterpret_cast<float4*>(out + off) = o;
+    if (out) *reinterpret_cast<float4*>(out + off) = o;
     if (out_hi) store_split4(out_hi, out_lo, off, o);
   }
 }
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(256) ln_forward_kernel(const float* __restrict
         o.y = v[j].y * inv * gg.y + bb.y;
         o.z = v[j].z * inv * gg.z + bb.z;
         o.w = v[j].w * inv * gg.w + bb.w;
-        *reinterpret_cast<float4*>(out + m * C + c4 * 4) = o;
+        if (out) *reinterpret_cast<float4*>(out + m * C + c4 * 4) = o;
         if (out_hi) store_split4(out_hi, out_lo, m * C + c4 * 4, o);
       }
     }
@@ -659,7 +659,7 @@ __global__ void __launch_bounds__(256) ln_forward_t_kernel(const float* __restri
         o.z = v[j].z * inv * gg[j].z + bb[j].z;
         o.w = v[j].w * inv * gg[j].w + bb[j].w;
         const int64_t off = m * C + (l + j * LPP) * 4;
-        *reinterpret_cast<float4*>(out + off) = o;
+        if (out) *reinterpret_cast<float4*>(out + off) = o;
         if (out_hi) store_split4(out_hi, out_lo, off, o);
       }
     }

@@ -306,8 +306,11 @@ struct PlanBuilder {
     }
     return a;
   }
-  void tap(const std::string& n, float* v, int C, int H, int W) {
+  // `lean`: in tensor-core mode the fp32 copy of this tensor may be skipped (only its bf16 hi/lo staging is
+  // consumed); igm_debug_read_tap then rebuilds it from hi + lo
+  void tap(const std::string& n, float* v, int C, int H, int W, const Act* lean = nullptr) {
     Act a; a.v = v; a.C = C; a.H = H; a.W = W;
+    if (lean) { a.hi = lean->hi; a.lo = lean->lo; }
     c.taps[n] = a;
   }
 
@@ -400,7 +403,7 @@ struct PlanBuilder {
     }
     r.h1 = act(Cout, H, W, true);
     r.out = act(Cout, H, W, true);
-    tap(name + ".h1", r.h1.v, Cout, H, W);
+    tap(name + ".h1", r.h1.v, Cout, H, W, &r.h1);
     tap(name + ".out", r.out.v, Cout, H, W);
     return r;
   }
@@ -419,7 +422,7 @@ struct PlanBuilder {
     a.ctx = ar.alloc((int64_t)B * kHeads * kDimHead * kDimHead);
     a.kstat = ar.alloc((int64_t)B * kHeads * kDimHead * 2);
     a.out = act(C, H, W, true);
-    tap(name + ".ln", a.ln.v, C, H, W);
+    tap(name + ".ln", a.ln.v, C, H, W, &a.ln);
     tap(name + ".out", a.out.v, C, H, W);
     track(H, W, C);
     maxMC = std::max(maxMC, M(H, W) * 3 * hd);
@@ -569,6 +572,12 @@ struct Runner {
     return launch_split_bf16(lc, a.v, M(a.H, a.W), a.C, a.hi, a.lo, a.C, 0);
   }
 
+  // May the producer of `consumer`'s input skip the fp32 copy?  Yes when every reader (forward conv, and in
+  // training its weight-gradient GEMM) runs on the tensor cores, which only read the bf16 hi/lo staging.
+  bool lean_ok(const ConvL& consumer) const {
+    return tc_on() && consumer.tc_f.valid && (!c.cfg.training || tcw_batch_ok(consumer.tc_w, B));
+  }
+
   // forward of a layer conv reading its wired sources.  `out_act`: when the output is an activation
   // that later feeds tensor-core convs, its bf16 hi/lo copy is produced here as well.
   int conv_fwd(const ConvL& l, int IH, int IW, int OH, int OW, int stride, int pad, float* out, const float* add,
@@ -687,14 +696,14 @@ struct Runner {
   }
 
   // ---- Block: conv3x3 -> GN -> Mish (+temb) (+res) ----
-  int block_fwd(BlockL& b, int H, int W, const float* temb, const float* res, const Act& out) {
+  int block_fwd(BlockL& b, int H, int W, const float* temb, const float* res, const Act& out, bool lean = false) {
     // GroupNorm partial statistics come out of the conv epilogue when the tensor-core plan allows it
     const bool fused = use_tc(b.conv.tc_f) && tc_gn_fusable(b.conv.tc_f, B);
     IGM_TRY(conv_fwd(b.conv, H, W, H, W, 1, 1, b.raw, nullptr, nullptr, fused ? c.gn_part : nullptr));
     int nparts = 0;
     if (fused) nparts = tc_gn_slots(b.conv.tc_f);
     else IGM_TRY(launch_gn_partial(lc, b.raw, B, H * W, b.conv.Cout, c.gn_part));
-    IGM_TRY(launch_gn_apply(lc, b.raw, c.gn_part, c.Pp(b.gn_w), c.Pp(b.gn_b), temb, c.proj_total, res, out.v,
+    IGM_TRY(launch_gn_apply(lc, b.raw, c.gn_part, c.Pp(b.gn_w), c.Pp(b.gn_b), temb, c.proj_total, res, lean ? nullptr : out.v,
                             b.stats, B, H * W, b.conv.Cout, hi(out), lo(out), nparts));
     return IGM_OK;
   }
@@ -717,7 +726,7 @@ struct Runner {
 
   int resnet_fwd(ResnetL& r) {
     const int H = r.H, W = r.W;
-    IGM_TRY(block_fwd(r.b1, H, W, c.t_proj + r.temb_off, nullptr, r.h1));
+    IGM_TRY(block_fwd(r.b1, H, W, c.t_proj + r.temb_off, nullptr, r.h1, lean_ok(r.b2.conv)));
     const float* res = r.in0->v;
     if (r.has_res) {
       IGM_TRY(conv_fwd(r.res, H, W, H, W, 1, 0, r.r, nullptr));
@@ -750,9 +759,10 @@ struct Runner {
     const int H = a.H, W = a.W;
     const int64_t m = M(H, W);
     const float* x = a.in->v;
-    IGM_TRY(launch_ln_forward(lc, x, c.Pp(a.ln_g), c.Pp(a.ln_b), a.ln.v, m, a.C, hi(a.ln), lo(a.ln)));
+    IGM_TRY(launch_ln_forward(lc, x, c.Pp(a.ln_g), c.Pp(a.ln_b), lean_ok(a.qkv) ? nullptr : a.ln.v, m, a.C, hi(a.ln), lo(a.ln)));
     IGM_TRY(conv_fwd(a.qkv, H, W, H, W, 1, 0, a.qkv_t, nullptr));
-    IGM_TRY(launch_linattn_forward(lc, a.qkv_t, a.att.v, a.ctx, a.kstat, B, H * W, c.attn_ws, hi(a.att), lo(a.att)));
+    IGM_TRY(launch_linattn_forward(lc, a.qkv_t, lean_ok(a.outc) ? nullptr : a.att.v, a.ctx, a.kstat, B, H * W, c.attn_ws,
+                                   hi(a.att), lo(a.att)));
     IGM_TRY(conv_fwd(a.outc, H, W, H, W, 1, 0, a.out.v, x, &a.out));
     return IGM_OK;
   }
@@ -1445,6 +1455,10 @@ int64_t igm_debug_read_tap(igm_ctx* c, const char* name, float* dst, int64_t cap
   if (cap < n) { set_error(c->st, IGM_ERR_INVALID, __FILE__, __LINE__, "tap buffer too small"); return IGM_ERR_INVALID; }
   if (cudaSetDevice(c->device) != cudaSuccess) return IGM_ERR_CUDA;
   LaunchCtx lc = c->lc(stream);
+  if (c->conv_engine == 1 && a.hi) {   // the fp32 copy may have been skipped: rebuild it from the bf16 hi + lo staging
+    int rr = launch_merge_bf16(lc, a.hi, a.lo, a.v, n);
+    if (rr != IGM_OK) return rr;
+  }
   int r = launch_nhwc_to_nchw(lc, a.v, dst, B, a.H * a.W, a.C);
   return r == IGM_OK ? n : r;
 }
