@@ -20,6 +20,7 @@
 #include "tc_ptx.cuh"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 namespace igm {
 namespace {
@@ -44,6 +45,9 @@ struct TcArgs {
   const float* add0; const float* add1;
   __nv_bfloat16* hi0; __nv_bfloat16* lo0;
   float* gn_part; int gn_cpg, gn_slots;
+  // TMA-store epilogue: each epilogue warp stages its 32 rows x 32 channels in swizzled shared memory and one
+  // lane issues cp.async.bulk.tensor stores (a warp = box wb x hb x ib pixels of the [B, H, W, C] output)
+  int tma_out, wb, hb, ib;
 };
 
 // (sum, sum of squares) of the SEG-channel segments of a 32-column chunk, reduced over the warp's
@@ -79,18 +83,22 @@ struct Cfg {
   static constexpr bool STACKED = (BN == 64);
   static constexpr int ACC_COLS = STACKED ? 2 * BN : BN;
   static constexpr int TMEM_COLS = 2 * ACC_COLS;   // two accumulator stages (power of two >= 32)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STORE_STAGE_BYTES = 4 * (4096 + 2048 + 2048);   // per epilogue warp: fp32 | bf16 hi | bf16 lo tiles
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant__ CUtensorMap ta_lo,
                const __grid_constant__ CUtensorMap ta1_hi, const __grid_constant__ CUtensorMap ta1_lo,
-               const __grid_constant__ CUtensorMap tb_hi, const __grid_constant__ CUtensorMap tb_lo, const TcArgs p) {
+               const __grid_constant__ CUtensorMap tb_hi, const __grid_constant__ CUtensorMap tb_lo,
+               const __grid_constant__ CUtensorMap to0, const __grid_constant__ CUtensorMap to1,
+               const __grid_constant__ CUtensorMap to_hi, const __grid_constant__ CUtensorMap to_lo, const TcArgs p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* store_stage = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(store_stage + C::STORE_STAGE_BYTES);
   uint64_t* full = bars;                       // [STAGES]  TMA -> MMA
   uint64_t* empty = bars + C::STAGES;          // [STAGES]  MMA -> TMA
   uint64_t* acc_full = bars + 2 * C::STAGES;   // [2]       MMA -> epilogue
@@ -266,6 +274,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
             }
           }
         }
+        if (p.tma_out) {
+          // ---- TMA-store epilogue: registers -> swizzled smem tile -> cp.async.bulk.tensor (coalesced, asynchronous) ----
+          const bool first_half = n < p.N0;
+          const float* ad = nullptr;
+          if (valid) {
+            if (first_half) ad = p.add0 ? p.add0 + opix * p.N0 + n : nullptr;
+            else ad = p.add1 ? p.add1 + opix * N1 + (n - p.N0) : nullptr;
+          }
+          if (ad) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 av = __ldg(reinterpret_cast<const float4*>(ad + j));
+              v[j] += av.x; v[j + 1] += av.y; v[j + 2] += av.z; v[j + 3] += av.w;
+            }
+          }
+          uint8_t* st_f = store_stage + q * 8192;          // 32 rows x 128 B, SWIZZLE_128B
+          uint8_t* st_h = st_f + 4096;                     // 32 rows x 64 B, SWIZZLE_64B
+          uint8_t* st_l = st_f + 6144;
+          if (lane == 0) tma_store_wait_read<0>();         // the previous chunk's stores have drained this staging tile
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(st_f + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          const bool want_hi = p.hi0 && first_half;
+          if (want_hi) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                h[e] = __float2bfloat16_rn(v[8 * j + e]);
+                l[e] = __float2bfloat16_rn(v[8 * j + e] - __bfloat162float(h[e]));
+              }
+              const int off = lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
+              *reinterpret_cast<uint4*>(st_h + off) = *reinterpret_cast<const uint4*>(h);
+              *reinterpret_cast<uint4*>(st_l + off) = *reinterpret_cast<const uint4*>(l);
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            // first pixel of this warp's 32 rows: row q*32 of the tile in (image, y, x) order
+            const int r0 = q * 32;
+            const int x0 = r0 % p.BW;
+            const int r2 = r0 / p.BW;
+            const int yy = y0 + r2 % p.BH, bb0 = b0 + r2 / p.BH;
+            if (first_half) tma_store_4d(&to0, st_f, n, x0, yy, bb0);
+            else tma_store_4d(&to1, st_f, n - p.N0, x0, yy, bb0);
+            if (want_hi) {
+              tma_store_4d(&to_hi, st_h, n, x0, yy, bb0);
+              tma_store_4d(&to_lo, st_l, n, x0, yy, bb0);
+            }
+            tma_store_commit();
+          }
+        } else
         if (valid) {
           // thread-per-pixel stores: each thread owns 128 contiguous bytes of its output row.  (A shared-
           // memory transpose to 8-lanes-per-row stores was measured 15-20 % SLOWER on every layer, r1h.)
@@ -306,6 +370,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
       if (lane == 0) mbar_arrive(&acc_empty[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (p.tma_out && lane == 0) tma_store_wait<0>();   // outstanding bulk stores complete before the CTA retires
   }
   tc_fence_before();
   __syncthreads();
@@ -593,6 +658,37 @@ int tc_plan_phase(Status& st, TcConv& t, int K, int N, int GH, int GW, int Bmax,
   return IGM_OK;
 }
 
+// [Bmax, H, W, C] output tensor as a rank-4 map (C, W, H, B) whose box is one epilogue warp's 32 pixels x 32 channels
+static int encode_out(Status& st, CUtensorMap* m, const void* ptr, int C, int H, int W, int Bmax, int wb, int hb, int ib,
+                      bool bf16) {
+  auto enc = get_encode_fn();
+  if (!enc) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t es_b = bf16 ? 2 : 4;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Bmax};
+  cuuint64_t strides[3] = {(cuuint64_t)C * es_b, (cuuint64_t)W * C * es_b, (cuuint64_t)H * W * C * es_b};
+  cuuint32_t box[4] = {32u, (cuuint32_t)wb, (cuuint32_t)hb, (cuuint32_t)ib};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims,
+                   strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled (conv output) failed");
+  return IGM_OK;
+}
+
+// Can the epilogue of plan `t` leave through TMA stores?  A warp's 32 tile rows must form one box of the output.
+static bool tma_out_geometry(const TcConv& t, int& wb, int& hb, int& ib) {
+  if (t.sy != 1 || t.sx != 1 || t.oy_off != 0 || t.ox_off != 0 || t.out_H != t.H || t.out_W != t.W) return false;
+  wb = t.BW < 32 ? t.BW : 32;
+  if (32 % wb != 0 || t.BW % wb != 0) return false;
+  hb = 32 / wb < t.BH ? 32 / wb : t.BH;
+  if (t.BH % hb != 0) return false;
+  ib = 32 / (wb * hb);
+  if (wb * hb * ib != 32) return false;
+  if (ib > 1 && (t.BB % ib != 0)) return false;
+  if (ib == 1 && hb < 32 / wb) return false;   // a warp would straddle two images inside one box row range
+  return true;
+}
+
 template <int BN>
 static int launch_tc_impl(const LaunchCtx& lc, const TcConv& t, const TcArgs& a, int num_tiles) {
   using C = Cfg<BN>;
@@ -603,7 +699,8 @@ static int launch_tc_impl(const LaunchCtx& lc, const TcConv& t, const TcArgs& a,
     attr_done = true;
   }
   int grid = num_tiles < 148 ? num_tiles : 148;
-  conv_tc_kernel<BN><<<grid, 192, C::SMEM_BYTES, lc.stream>>>(t.a_hi, t.a_lo, t.a1_hi, t.a1_lo, t.b_hi, t.b_lo, a);
+  conv_tc_kernel<BN><<<grid, 192, C::SMEM_BYTES, lc.stream>>>(t.a_hi, t.a_lo, t.a1_hi, t.a1_lo, t.b_hi, t.b_lo, t.om.m0, t.om.m1,
+                                                              t.om.mh, t.om.ml, a);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }
@@ -641,6 +738,30 @@ int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r) {
   if (r.gn_part) {
     if (!tc_gn_fusable(t, r.B) || r.N0 != t.N) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "conv_tc: GroupNorm statistics cannot be fused for this plan");
     a.gn_part = r.gn_part; a.gn_cpg = t.N / kGroups; a.gn_slots = tc_gn_slots(t);
+  }
+  // TMA-store epilogue when the tile geometry allows it (IGM_TMA_STORE=0 keeps the thread-per-row stores)
+  static const bool tma_store_off = [] { const char* e = getenv("IGM_TMA_STORE"); return e && e[0] == '0'; }();
+  a.tma_out = 0; a.wb = a.hb = a.ib = 0;
+  int wb, hb, ib;
+  if (!tma_store_off && tma_out_geometry(t, wb, hb, ib)) {
+    TcConv::OutMaps& om = t.om;
+    const int N1 = t.N - r.N0;
+    if (om.p0 != r.out0 || om.n0 != r.N0) {
+      IGM_TRY(encode_out(*lc.st, &om.m0, r.out0, r.N0, t.out_H, t.out_W, t.Bmax, wb, hb, ib, false));
+      om.p0 = r.out0; om.n0 = r.N0;
+      if (!om.p1) om.m1 = om.m0;
+      if (!om.ph) { om.mh = om.m0; om.ml = om.m0; }
+    }
+    if (N1 > 0 && (om.p1 != r.out1 || om.n1 != N1)) {
+      IGM_TRY(encode_out(*lc.st, &om.m1, r.out1, N1, t.out_H, t.out_W, t.Bmax, wb, hb, ib, false));
+      om.p1 = r.out1; om.n1 = N1;
+    }
+    if (r.hi0 && (om.ph != r.hi0 || om.pl != r.lo0)) {
+      IGM_TRY(encode_out(*lc.st, &om.mh, r.hi0, r.N0, t.out_H, t.out_W, t.Bmax, wb, hb, ib, true));
+      IGM_TRY(encode_out(*lc.st, &om.ml, r.lo0, r.N0, t.out_H, t.out_W, t.Bmax, wb, hb, ib, true));
+      om.ph = r.hi0; om.pl = r.lo0;
+    }
+    a.tma_out = 1; a.wb = wb; a.hb = hb; a.ib = ib;
   }
   const double flops = 2.0 * r.B * t.H * t.W * (double)t.N * t.K * t.ntaps;
   const double bytes = 4.0 * ((double)r.B * t.H * t.W * (t.K + t.N * (r.add0 ? 2 : 1)) + (double)t.ntaps * t.K * t.N);

@@ -35,6 +35,13 @@ struct TcConv {
   int Csrc = 0;                         // channels of source 0 (sub-lattice px selects channel block px*Csrc)
   // output pixel of tile position (oy, ox):  (oy*sy + oy_off, ox*sx + ox_off) on an out_H x out_W image
   int out_H = 0, out_W = 0, sy = 1, sx = 1, oy_off = 0, ox_off = 0;
+  // TMA-store epilogue: output tensor maps, (re-)encoded when a launch passes a new output pointer
+  struct OutMaps {
+    const void* p0 = nullptr; const void* p1 = nullptr; const void* ph = nullptr; const void* pl = nullptr;
+    int n0 = 0, n1 = 0;
+    alignas(64) CUtensorMap m0, m1, mh, ml;
+  };
+  mutable OutMaps om;
 };
 
 // Stride-2 convolution read (Conv2d k3 s2 p1 forward / ConvTranspose2d k4 s2 p1 data gradient):
