@@ -179,6 +179,8 @@ struct PackJob {
   int64_t begin;   // prefix sum of element counts
 };
 int launch_pack_jobs(const LaunchCtx& lc, const PackJob* d_jobs, int n_jobs, int64_t total);
+// tiled variant for the bf16 hi/lo layouts with N, K multiples of 32: job.begin = first CTA, d_cta_job[cta] = job index
+int launch_pack_tiles(const LaunchCtx& lc, const PackJob* d_jobs, const int* d_cta_job, int n_ctas, int max_taps, double elems);
 
 // ---------------------------------------------------------------------------
 // normalisation / activation kernels (norm_act.cu)

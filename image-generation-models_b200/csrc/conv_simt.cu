@@ -487,6 +487,133 @@ __global__ void __launch_bounds__(256) wgrad_stem_kernel(const float* __restrict
   }
 }
 
+// "Thin" weight gradients: one operand has <= 4 channels (the image / the predicted noise), the other is wide.
+//   grad[w*s_wide + t*s_thin + tap] += sum_pix Wide[pix][w] * Thin[pix + tap][t]
+// (stem 3x3 and 1x1 convs: Wide = dY, Thin = X gathered through the taps; final 1x1 conv: Wide = activations,
+// Thin = d_pred, KS = 1).  A CTA owns RB image rows of one image and 64 wide channels; the zero-padded thin tile
+// sits in shared memory, so the inner loop is one coalesced load of the wide value and KS*KS*TC broadcast LDS + FMA.
+template <int TC, int KS>
+__global__ void __launch_bounds__(256) wgrad_thin_kernel(const float* __restrict__ Wide, const float* __restrict__ Thin,
+                                                         float* __restrict__ grad, int H, int W, int WC, int RB,
+                                                         int64_t s_wide, int64_t s_thin) {
+  constexpr int T = KS * KS, PAD = (KS - 1) / 2, NA = T * TC;
+  extern __shared__ __align__(16) float smem_thin[];   // tile [(RB + 2 PAD)][(W + 2 PAD)] of float4 (TC padded to 4), then red
+  const int TW = W + 2 * PAD, TH = RB + 2 * PAD;
+  float4* tile = reinterpret_cast<float4*>(smem_thin);
+  float (*red)[64][NA + 1] = reinterpret_cast<float (*)[64][NA + 1]>(smem_thin + TH * TW * 4);
+  const int tiles_per_img = (H + RB - 1) / RB;
+  const int b = blockIdx.x / tiles_per_img, y0 = (blockIdx.x % tiles_per_img) * RB;
+  for (int i = threadIdx.x; i < TH * TW; i += 256) {
+    const int tx = i % TW, ty = i / TW;
+    const int y = y0 + ty - PAD, x = tx - PAD;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      const float* src = Thin + (((int64_t)b * H + y) * W + x) * TC;
+#pragma unroll
+      for (int ci = 0; ci < TC; ++ci) v[ci] = __ldg(src + ci);
+    }
+    tile[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  __syncthreads();
+  const int c = blockIdx.y * 64 + (threadIdx.x & 63);
+  const int lane4 = threadIdx.x >> 6;
+  float acc[NA];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) acc[i] = 0.f;
+  if (c < WC) {
+    // each of the 4 pixel lanes walks a contiguous run of pixels: along a row the KS x KS window of thin values
+    // slides, so only its new column (KS 128-bit LDS) is fetched per pixel
+    const int npix = min(RB, H - y0) * W;
+    const int per = (npix + 3) >> 2;
+    const int i0 = lane4 * per, i1 = min(i0 + per, npix);
+    int yy = i0 / W, xx = i0 - yy * W;
+    float4 win[KS][KS];
+    bool fresh = true;
+    const float* wp = Wide + (((int64_t)b * H + y0) * W + i0) * WC + c;
+    constexpr int UB = 8;   // wide values requested per batch (memory-level parallelism: the loop is otherwise latency-bound)
+    for (int ib = i0; ib < i1; ib += UB, wp += (int64_t)UB * WC) {
+      float gb[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) gb[u] = (ib + u < i1) ? __ldg(wp + (int64_t)u * WC) : 0.f;
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        if (ib + u >= i1) break;
+        const float g = gb[u];
+
+        if (fresh) {
+#pragma unroll
+          for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < KS; ++kx) win[ky][kx] = tile[(yy + ky) * TW + xx + kx];
+          fresh = false;
+        } else {
+#pragma unroll
+          for (int ky = 0; ky < KS; ++ky) {
+#pragma unroll
+            for (int kx = 0; kx + 1 < KS; ++kx) win[ky][kx] = win[ky][kx + 1];
+            win[ky][KS - 1] = tile[(yy + ky) * TW + xx + KS - 1];
+          }
+        }
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < KS; ++kx) {
+            const float tv[4] = {win[ky][kx].x, win[ky][kx].y, win[ky][kx].z, win[ky][kx].w};
+#pragma unroll
+            for (int ci = 0; ci < TC; ++ci) acc[(ky * KS + kx) * TC + ci] = fmaf(g, tv[ci], acc[(ky * KS + kx) * TC + ci]);
+          }
+        if (++xx == W) { xx = 0; ++yy; fresh = true; }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NA; ++i) red[lane4][threadIdx.x & 63][i] = acc[i];
+  __syncthreads();
+  if (lane4 == 0 && c < WC) {
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+#pragma unroll
+      for (int ci = 0; ci < TC; ++ci) {
+        const int i = t * TC + ci;
+        const float v = red[0][threadIdx.x][i] + red[1][threadIdx.x][i] + red[2][threadIdx.x][i] + red[3][threadIdx.x][i];
+        atomicAdd(grad + (int64_t)c * s_wide + (int64_t)ci * s_thin + t, v);
+      }
+  }
+}
+
+template <int TC, int KS>
+static int launch_thin_impl(const LaunchCtx& lc, const float* wide, const float* thin, float* grad, int B, int H, int W, int WC,
+                            int64_t s_wide, int64_t s_thin) {
+  constexpr int PAD = (KS - 1) / 2, NA = KS * KS * TC;
+  int RB = (int)cdiv64((int64_t)B * H, 296);   // ~2 CTAs per SM and 64-channel slab (fewer same-address atomics)
+  if (RB < 1) RB = 1;
+  if (RB > H) RB = H;
+  while (RB > 1 && (RB + 2 * PAD) * (W + 2 * PAD) * 4 > 4096) --RB;
+  const int tile_f = (RB + 2 * PAD) * (W + 2 * PAD) * 4;
+  const size_t smem = (size_t)(tile_f + 4 * 64 * (NA + 1)) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(wgrad_thin_kernel<TC, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr = true;
+  }
+  if (smem > 64 * 1024) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "thin wgrad: image row too wide");
+  dim3 grid((unsigned)(B * cdiv(H, RB)), (unsigned)cdiv(WC, 64));
+  wgrad_thin_kernel<TC, KS><<<grid, 256, smem, lc.stream>>>(wide, thin, grad, H, W, WC, RB, s_wide, s_thin);
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+template <int KS>
+static int launch_thin(const LaunchCtx& lc, int TC, const float* wide, const float* thin, float* grad, int B, int H, int W,
+                       int WC, int64_t s_wide, int64_t s_thin) {
+  switch (TC) {
+    case 1: return launch_thin_impl<1, KS>(lc, wide, thin, grad, B, H, W, WC, s_wide, s_thin);
+    case 2: return launch_thin_impl<2, KS>(lc, wide, thin, grad, B, H, W, WC, s_wide, s_thin);
+    case 3: return launch_thin_impl<3, KS>(lc, wide, thin, grad, B, H, W, WC, s_wide, s_thin);
+    default: return launch_thin_impl<4, KS>(lc, wide, thin, grad, B, H, W, WC, s_wide, s_thin);
+  }
+}
+
 // out[n] += sum_m x[m, n]; grid.x = row splits; block (32 x 8): 32 columns x 8 row lanes
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int64_t M, int N,
                                                      float* __restrict__ out, int rows_per_cta) {
@@ -565,22 +692,17 @@ int launch_conv(const LaunchCtx& lc, const ConvArgs& a) {
 
 int launch_wgrad(const LaunchCtx& lc, const WgradArgs& a) {
   const int64_t npix = (int64_t)a.B * a.PH * a.PW;
-  if (a.QC <= 4 && a.KH == 3 && a.KW == 3 && a.stride == 1 && a.pad == 1 && a.pad_w < 0 && a.dil == 1 && a.PH == a.QH && a.PW == a.QW &&
-      a.sq == 9 && a.sp == (int64_t)a.QC * 9) {
-    // stem: few input channels gathered (Q), C_out enumerated (P)
-    int ctas = 148 * 4;
-    int per = (int)cdiv64(npix, ctas);
-    per = (per + 3) & ~3;
-    dim3 grid((unsigned)cdiv64(npix, per), (unsigned)cdiv(a.PC, 64));
-    ProfScope ps_(lc, K_CONV_WGRAD, 2.0 * npix * (double)a.PC * a.QC * 9, 4.0 * npix * (a.PC + a.QC));
-    switch (a.QC) {
-      case 1: wgrad_stem_kernel<1><<<grid, 256, 0, lc.stream>>>(a.Q, a.P, a.grad, a.B, a.PH, a.PW, a.PC, per); break;
-      case 2: wgrad_stem_kernel<2><<<grid, 256, 0, lc.stream>>>(a.Q, a.P, a.grad, a.B, a.PH, a.PW, a.PC, per); break;
-      case 3: wgrad_stem_kernel<3><<<grid, 256, 0, lc.stream>>>(a.Q, a.P, a.grad, a.B, a.PH, a.PW, a.PC, per); break;
-      default: wgrad_stem_kernel<4><<<grid, 256, 0, lc.stream>>>(a.Q, a.P, a.grad, a.B, a.PH, a.PW, a.PC, per); break;
-    }
-    IGM_POST_LAUNCH(lc);
-    return IGM_OK;
+  const bool same_grid = a.stride == 1 && a.dil == 1 && a.pad_w < 0 && a.PH == a.QH && a.PW == a.QW && a.KH == a.KW;
+  if (same_grid && a.QC <= 4 && a.PC >= 32 && ((a.KH == 3 && a.pad == 1) || (a.KH == 1 && a.pad == 0))) {
+    // few input channels gathered (Q = image), C_out enumerated (P = dY): stem 3x3 / 1x1 convs
+    ProfScope ps_(lc, K_CONV_WGRAD, 2.0 * npix * (double)a.PC * a.QC * a.KH * a.KW, 4.0 * npix * (a.PC + a.QC));
+    if (a.KH == 3) return launch_thin<3>(lc, a.QC, a.P, a.Q, a.grad, a.B, a.PH, a.PW, a.PC, a.sp, a.sq);
+    return launch_thin<1>(lc, a.QC, a.P, a.Q, a.grad, a.B, a.PH, a.PW, a.PC, a.sp, a.sq);
+  }
+  if (same_grid && a.PC <= 4 && a.QC >= 32 && a.KH == 1 && a.pad == 0) {
+    // few output channels (P = d_pred), wide input (Q): the final 1x1 conv
+    ProfScope ps_(lc, K_CONV_WGRAD, 2.0 * npix * (double)a.PC * a.QC, 4.0 * npix * (a.PC + a.QC));
+    return launch_thin<1>(lc, a.PC, a.Q, a.P, a.grad, a.B, a.PH, a.PW, a.QC, a.sq, a.sp);
   }
   const int q_tiles = cdiv(a.QC, WB), p_tiles = cdiv(a.PC, WB);
   const int taps = a.KH * a.KW;

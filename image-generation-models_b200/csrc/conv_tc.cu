@@ -490,6 +490,56 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJob* __restric
   }
 }
 
+// Tiled re-pack of the tensor-core weight layouts: a CTA moves a 32(n) x 32(k) x taps tile through shared memory,
+// so both the fp32 source (runs of 32*taps contiguous floats) and the bf16 hi/lo destinations (32 contiguous k per
+// (n, tap) row) are accessed in whole lines.  job.begin = first CTA of the job; cta_job[cta] = job index.
+__global__ void __launch_bounds__(256) pack_tiles_kernel(const PackJob* __restrict__ jobs, const int* __restrict__ cta_job) {
+  extern __shared__ float ptile[];   // [32 outer][32 * taps + 1]
+  const PackJob j = jobs[cta_job[blockIdx.x]];
+  const int t = blockIdx.x - (int)j.begin;
+  const int tk = j.K / 32;
+  const int n0 = (t / tk) * 32, k0 = (t % tk) * 32;
+  const int KK = j.taps, L = 32 * KK, pitch = L + 1;
+  const bool outer_n = j.sn > j.sk;            // fprop layout of a Conv2d: each n owns a contiguous run of k x taps
+  const int64_t so = outer_n ? j.sn : j.sk;    // stride between outer rows
+  const float* base = j.src + (outer_n ? (int64_t)n0 * j.sn + (int64_t)k0 * j.sk : (int64_t)k0 * j.sk + (int64_t)n0 * j.sn);
+  // 128-bit loads, four in flight per thread (runs are 16-byte aligned: k0, n0 are multiples of 32)
+  const int L4 = L >> 2;
+  for (int i0 = threadIdx.x; i0 < 32 * L4; i0 += 4 * 256) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 256;
+      if (i < 32 * L4) {
+        const int o = i / L4, r4 = i - o * L4;
+        v[u] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)o * so) + r4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 256;
+      if (i < 32 * L4) {
+        const int o = i / L4, r4 = i - o * L4;
+        float* d = ptile + o * pitch + r4 * 4;
+        d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+      }
+    }
+  }
+  __syncthreads();
+  const int k = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(j.dst_hi);
+  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(j.dst_lo);
+  for (int pr = w; pr < 32 * KK; pr += 8) {    // (n, tap) rows of the destination
+    const int n = pr / KK, tap = pr - n * KK;
+    const float x = outer_n ? ptile[n * pitch + k * KK + tap] : ptile[k * pitch + n * KK + tap];
+    const int td = j.flip ? (KK - 1 - tap) : tap;
+    const int64_t d = ((int64_t)(n0 + n) * KK + td) * j.K + k0 + k;
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi[d] = h;
+    lo[d] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (!fn) {
@@ -812,6 +862,21 @@ int launch_pack_jobs(const LaunchCtx& lc, const PackJob* d_jobs, int n_jobs, int
   if (blocks > 148 * 16) blocks = 148 * 16;
   ProfScope ps_(lc, K_PACK, 0.0, 8.0 * total);
   pack_jobs_kernel<<<blocks, 256, 0, lc.stream>>>(d_jobs, n_jobs, total);
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+int launch_pack_tiles(const LaunchCtx& lc, const PackJob* d_jobs, const int* d_cta_job, int n_ctas, int max_taps, double elems) {
+  if (n_ctas <= 0) return IGM_OK;
+  const int smem = 32 * (32 * max_taps + 1) * (int)sizeof(float);
+  static int attr_smem = 0;
+  if (smem > 48 * 1024 && smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(pack_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(e));
+    attr_smem = smem;
+  }
+  ProfScope ps_(lc, K_PACK, 0.0, 8.0 * elems);
+  pack_tiles_kernel<<<n_ctas, 256, smem, lc.stream>>>(d_jobs, d_cta_job);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }

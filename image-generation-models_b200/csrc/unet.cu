@@ -217,6 +217,10 @@ struct igm_ctx {
   PackJob* pack_dev = nullptr;        // device job table of igm_unet_pack_weights
   int pack_n = 0, pack_engine = -1;
   int64_t pack_total = 0;
+  PackJob* packt_dev = nullptr;       // tiled re-pack (bf16 layouts): jobs, CTA -> job table
+  int* packt_cta_dev = nullptr;
+  int packt_ctas = 0, packt_taps = 1, packt_cap = 0;
+  double packt_elems = 0;
   float* pred = nullptr;        // [B,C,H,W] network output (NCHW)
   float* noise_copy = nullptr;  // NCHW
   float* d_pred = nullptr;      // NHWC [M, C]
@@ -530,6 +534,9 @@ struct PlanBuilder {
     c.sched_dev = reinterpret_cast<igm_schedule*>(ar.alloc(64));
     c.proj_dev = reinterpret_cast<TimeProj*>(ar.alloc((int64_t)(sizeof(TimeProj) * c.n_proj + 3) / 4 + 64));
     c.pack_dev = reinterpret_cast<PackJob*>(ar.alloc((int64_t)(sizeof(PackJob) * 1024) / 4));
+    c.packt_dev = reinterpret_cast<PackJob*>(ar.alloc((int64_t)(sizeof(PackJob) * 1024) / 4));
+    c.packt_cap = (int)(2 * pb.off / 1024) + 1024;
+    c.packt_cta_dev = reinterpret_cast<int*>(ar.alloc(c.packt_cap));
     c.fin_dev = reinterpret_cast<HaloFinJob*>(ar.alloc((int64_t)(sizeof(HaloFinJob) * 256) / 4));
     c.fin_cta_cap = (int)(halo_w_elems / 1024) + 64;
     c.fin_cta_dev = reinterpret_cast<int*>(ar.alloc(c.fin_cta_cap));
@@ -1225,13 +1232,27 @@ int igm_unet_bind_params(igm_ctx* c, float* params, float* grads) {
 
 // Job list of one full re-pack for the active engine (only the layouts that engine reads).
 static int build_pack_jobs(igm_ctx* c) {
-  std::vector<PackJob> jobs;
+  std::vector<PackJob> jobs, tjobs;
+  std::vector<int> cta_job;
   int64_t total = 0;
+  c->packt_taps = 1; c->packt_elems = 0;
   auto add = [&](const float* src, float* dst_f, void* hi, void* lo, int taps, int K, int N, int64_t sk, int64_t sn,
                  int flip) {
     PackJob j{};
     j.src = src; j.dst_f = dst_f; j.dst_hi = hi; j.dst_lo = lo;
-    j.taps = taps; j.K = K; j.N = N; j.flip = flip; j.sk = sk; j.sn = sn; j.begin = total;
+    j.taps = taps; j.K = K; j.N = N; j.flip = flip; j.sk = sk; j.sn = sn;
+    const int n_ctas = (N / 32) * (K / 32);
+    if (hi && N % 32 == 0 && K % 32 == 0 && taps <= 16 && (sk == taps || sn == taps) &&
+        (int)cta_job.size() + n_ctas <= c->packt_cap && tjobs.size() < 1024) {
+      // tiled path: whole-line accesses through shared memory
+      j.begin = (int64_t)cta_job.size();
+      cta_job.insert(cta_job.end(), n_ctas, (int)tjobs.size());
+      tjobs.push_back(j);
+      c->packt_taps = std::max(c->packt_taps, taps);
+      c->packt_elems += (double)taps * K * N;
+      return;
+    }
+    j.begin = total;
     total += (int64_t)taps * K * N;
     jobs.push_back(j);
   };
@@ -1260,9 +1281,15 @@ static int build_pack_jobs(igm_ctx* c) {
     add(c->Pp(c->final_conv.pw), c->final_wbwd, nullptr, nullptr, 1, c->cfg.channels, c->final_conv.Cin,
         c->final_conv.Cin, 1, 0);
   if (jobs.size() > 1024) IGM_FAIL(c->st, IGM_ERR_INVALID, "too many pack jobs");
-  IGM_CUDA(c->st, cudaMemcpy(c->pack_dev, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
+  if (!jobs.empty())
+    IGM_CUDA(c->st, cudaMemcpy(c->pack_dev, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
   c->pack_n = (int)jobs.size();
   c->pack_total = total;
+  if (!tjobs.empty()) {
+    IGM_CUDA(c->st, cudaMemcpy(c->packt_dev, tjobs.data(), tjobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
+    IGM_CUDA(c->st, cudaMemcpy(c->packt_cta_dev, cta_job.data(), cta_job.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  c->packt_ctas = (int)cta_job.size();
   c->pack_engine = c->conv_engine;
   return IGM_OK;
 }
@@ -1273,6 +1300,7 @@ int igm_unet_pack_weights(igm_ctx* c, void* stream) {
   IGM_CUDA(c->st, cudaSetDevice(c->device));
   if (c->pack_engine != c->conv_engine) IGM_TRY(build_pack_jobs(c));
   LaunchCtx lc = c->lc(stream);
+  IGM_TRY(launch_pack_tiles(lc, c->packt_dev, c->packt_cta_dev, c->packt_ctas, c->packt_taps, c->packt_elems));
   return launch_pack_jobs(lc, c->pack_dev, c->pack_n, c->pack_total);
 }
 
