@@ -25,6 +25,8 @@ CASES = {
     "tiny": (32, 3, (1, 2), 16, 16, 2, 1000),
     "mnist_like": (32, 1, (2, 4), 28, 28, 2, 1000),
     "cifar10": (64, 3, (1, 2, 4), 32, 32, 2, 1000),
+    # BASELINE.json configs[2] topology (CelebA 64x64, dim_mults 1-2-4-8, 29.8 M parameters) at batch 1
+    "celeba64": (64, 3, (1, 2, 4, 8), 64, 64, 1, 1000),
 }
 
 
