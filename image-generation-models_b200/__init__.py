@@ -11,5 +11,6 @@ from . import _lib  # noqa: F401
 from .ddpm import DDPM, FusedAdam, GaussianDiffusion, Unet, ValidationResult  # noqa: F401
 from .vqvae import VQVAE, Decoder, Encoder, VectorQuantizer  # noqa: F401
 from .pixelcnn import PixelCNN  # noqa: F401
+from .callbacks import SampleImagesCallback, get_grid_images  # noqa: F401
 
-__all__ = ["Unet", "GaussianDiffusion", "DDPM", "FusedAdam", "ValidationResult", "VectorQuantizer", "VQVAE", "Encoder", "Decoder", "PixelCNN"]
+__all__ = ["Unet", "GaussianDiffusion", "DDPM", "FusedAdam", "ValidationResult", "VectorQuantizer", "VQVAE", "Encoder", "Decoder", "PixelCNN", "SampleImagesCallback", "get_grid_images"]
