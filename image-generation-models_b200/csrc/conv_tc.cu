@@ -48,6 +48,8 @@ struct TcArgs {
   // TMA-store epilogue: each epilogue warp stages its 32 rows x 32 channels in swizzled shared memory and one
   // lane issues cp.async.bulk.tensor stores (a warp = box wb x hb x ib pixels of the [B, H, W, C] output)
   int tma_out, wb, hb, ib;
+  // output-parity phases merged into one launch: phase ph owns taps [ph_tap0, ph_tap0 + ph_ntaps) and writes at (ph_oy, ph_ox)
+  int nph, ph_tap0[4], ph_ntaps[4], ph_oy[4], ph_ox[4];
 };
 
 // (sum, sum of squares) of the SEG-channel segments of a 32-column chunk, reduced over the warp's
@@ -123,9 +125,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int tiles_ph = p.tiles_m * p.tiles_n;
+  const int num_tiles = tiles_ph * p.nph;
   const int kchunks = p.K / KC;
-  const int iters = p.ntaps * kchunks;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -134,11 +136,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+        const int ph = tile / tiles_ph, tt = tile - ph * tiles_ph;
+        const int tm = tt / p.tiles_n, tn = tt - tm * p.tiles_n;
         int b0, y0;
         if (p.BB > 1) { b0 = tm * p.BB; y0 = 0; }
         else { b0 = tm / p.tiles_per_img; y0 = (tm - b0 * p.tiles_per_img) * p.BH; }
-        for (int ti = 0; ti < p.ntaps; ++ti) {
+        for (int ti = p.ph_tap0[ph]; ti < p.ph_tap0[ph] + p.ph_ntaps[ph]; ++ti) {
           const TcTap tp = p.taps[ti];
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(&empty[stage], phase ^ 1);
@@ -182,6 +185,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * C::ACC_COLS);
         uint32_t accum = 0;
+        const int iters = p.ph_ntaps[tile / tiles_ph] * kchunks;
         for (int it = 0; it < iters; ++it) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -216,7 +220,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+      const int ph = tile / tiles_ph, tt = tile - ph * tiles_ph;
+      const int tm = tt / p.tiles_n, tn = tt - tm * p.tiles_n;
       int b0, y0;
       if (p.BB > 1) { b0 = tm * p.BB; y0 = 0; }
       else { b0 = tm / p.tiles_per_img; y0 = (tm - b0 * p.tiles_per_img) * p.BH; }
@@ -227,7 +232,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
       const int bb = r2 / p.BH;
       const int oy = y0 + by, b = b0 + bb;
       const bool valid = (bb < p.BB) && (oy < p.H) && (b < p.B);
-      const int64_t opix = ((int64_t)b * p.out_H + (oy * p.sy + p.oy_off)) * p.out_W + (bx * p.sx + p.ox_off);
+      const int64_t opix = ((int64_t)b * p.out_H + (oy * p.sy + p.ph_oy[ph])) * p.out_W + (bx * p.sx + p.ph_ox[ph]);
 
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
@@ -739,6 +744,41 @@ static bool tma_out_geometry(const TcConv& t, int& wb, int& hb, int& ib) {
   return true;
 }
 
+int tc_plan_phases4(Status& st, TcConv& t, int K, int N, int GH, int GW, int Bmax, int KH, int pad, __nv_bfloat16* a_hi,
+                    __nv_bfloat16* a_lo, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo) {
+  t.valid = false;
+  if (K < KC || K % KC != 0 || N < 64 || N % 64 != 0 || !tile_grid_ok(GH, GW) || (KH != 3 && KH != 4))
+    IGM_FAIL(st, IGM_ERR_INVALID, "shape not eligible for the phase tcgen05 conv");
+  IGM_TRY(plan_common(st, t, K, K, N, GH, GW, Bmax, KH * KH, w_hi, w_lo));
+  t.KH = t.KW = KH; t.pad = pad;
+  t.ntaps = 0;
+  t.nph = 4;
+  for (int ph = 0; ph < 4; ++ph) {
+    const int py = ph / 2, px = ph % 2;
+    t.ph_tap0[ph] = t.ntaps; t.ph_oy[ph] = py; t.ph_ox[ph] = px;
+    for (int ky = 0; ky < KH; ++ky) {
+      if (((py + pad - ky) % 2 + 2) % 2 != 0) continue;
+      for (int kx = 0; kx < KH; ++kx) {
+        if (((px + pad - kx) % 2 + 2) % 2 != 0) continue;
+        if (t.ntaps >= kTcMaxTaps) IGM_FAIL(st, IGM_ERR_INVALID, "too many taps");
+        TcTap tp;
+        tp.dy = (py + pad - ky) / 2; tp.dx = (px + pad - kx) / 2; tp.py = tp.px = 0;
+        tp.wtap = ky * KH + kx;
+        t.taps[t.ntaps++] = tp;
+      }
+    }
+    t.ph_ntaps[ph] = t.ntaps - t.ph_tap0[ph];
+    if (t.ph_ntaps[ph] == 0) IGM_FAIL(st, IGM_ERR_INVALID, "phase without taps");
+  }
+  t.Csrc = K;
+  t.out_H = 2 * GH; t.out_W = 2 * GW; t.sy = t.sx = 2; t.oy_off = t.ox_off = 0;
+  IGM_TRY(encode_act(st, &t.a_hi, a_hi, K, GH, GW, Bmax, false, t));
+  IGM_TRY(encode_act(st, &t.a_lo, a_lo, K, GH, GW, Bmax, false, t));
+  t.a1_hi = t.a_hi; t.a1_lo = t.a_lo;
+  t.valid = true;
+  return IGM_OK;
+}
+
 template <int BN>
 static int launch_tc_impl(const LaunchCtx& lc, const TcConv& t, const TcArgs& a, int num_tiles) {
   using C = Cfg<BN>;
@@ -778,6 +818,9 @@ int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r) {
   for (int i = 0; i < t.ntaps; ++i) a.taps[i] = t.taps[i];
   a.out_H = t.out_H; a.out_W = t.out_W; a.sy = t.sy; a.sx = t.sx; a.oy_off = t.oy_off; a.ox_off = t.ox_off;
   a.BH = t.BH; a.BW = t.BW; a.BB = t.BB;
+  a.nph = t.nph;
+  for (int i = 0; i < 4; ++i) { a.ph_tap0[i] = t.ph_tap0[i]; a.ph_ntaps[i] = t.ph_ntaps[i]; a.ph_oy[i] = t.ph_oy[i]; a.ph_ox[i] = t.ph_ox[i]; }
+  if (t.nph == 1) { a.ph_tap0[0] = 0; a.ph_ntaps[0] = t.ntaps; a.ph_oy[0] = t.oy_off; a.ph_ox[0] = t.ox_off; }
   a.tiles_per_img = (t.BB > 1) ? 1 : cdiv(t.H, t.BH);
   a.tiles_m = (t.BB > 1) ? cdiv(r.B, t.BB) : r.B * a.tiles_per_img;
   a.tiles_n = t.N / t.BN;
@@ -813,10 +856,10 @@ int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r) {
     }
     a.tma_out = 1; a.wb = wb; a.hb = hb; a.ib = ib;
   }
-  const double flops = 2.0 * r.B * t.H * t.W * (double)t.N * t.K * t.ntaps;
+  const double flops = 2.0 * r.B * t.H * t.W * (double)t.N * t.K * t.ntaps;   // (merged phases: ntaps = all taps of all phases)
   const double bytes = 4.0 * ((double)r.B * t.H * t.W * (t.K + t.N * (r.add0 ? 2 : 1)) + (double)t.ntaps * t.K * t.N);
   ProfScope ps_(lc, r.kclass, flops, bytes);
-  const int num_tiles = a.tiles_m * a.tiles_n;
+  const int num_tiles = a.tiles_m * a.tiles_n * a.nph;
   if (t.BN == 128) return launch_tc_impl<128>(lc, t, a, num_tiles);
   return launch_tc_impl<64>(lc, t, a, num_tiles);
 }

@@ -35,6 +35,8 @@ struct TcConv {
   int Csrc = 0;                         // channels of source 0 (sub-lattice px selects channel block px*Csrc)
   // output pixel of tile position (oy, ox):  (oy*sy + oy_off, ox*sx + ox_off) on an out_H x out_W image
   int out_H = 0, out_W = 0, sy = 1, sx = 1, oy_off = 0, ox_off = 0;
+  // all four output-parity phases in ONE launch (tc_plan_phases4): per-phase tap ranges and output offsets
+  int nph = 1, ph_tap0[4] = {0, 0, 0, 0}, ph_ntaps[4] = {0, 0, 0, 0}, ph_oy[4] = {0, 0, 0, 0}, ph_ox[4] = {0, 0, 0, 0};
   // TMA-store epilogue: output tensor maps, (re-)encoded when a launch passes a new output pointer
   struct OutMaps {
     const void* p0 = nullptr; const void* p1 = nullptr; const void* ph = nullptr; const void* pl = nullptr;
@@ -54,6 +56,10 @@ int tc_plan_strided(Status& st, TcConv& t, int K, int N, int SH, int SW, int Bma
 // (2*a + py, 2*b + px) of a 2GH x 2GW image; only the taps ky with (py + pad - ky) even contribute.
 int tc_plan_phase(Status& st, TcConv& t, int K, int N, int GH, int GW, int Bmax, int KH, int pad, int py, int px,
                   __nv_bfloat16* a_hi, __nv_bfloat16* a_lo, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo);
+
+// the four phases (py, px) of tc_plan_phase as one plan / one launch (tiles of the four phases interleave on the SMs)
+int tc_plan_phases4(Status& st, TcConv& t, int K, int N, int GH, int GW, int Bmax, int KH, int pad, __nv_bfloat16* a_hi,
+                    __nv_bfloat16* a_lo, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo);
 
 // Can this (stride-1, non-dilated) conv run on the tensor-core engine?
 bool tc_eligible(int K, int N, int H, int W, int KH);

@@ -1014,20 +1014,16 @@ static int plan_tc(igm_ctx* c) {
       IGM_TRY(tc_plan_strided(c->st, rs.tcf[0], C, C, rs.Hin, rs.Win, Bm, 3, 1, rs.in->hi, rs.in->lo, l.wf_hi, l.wf_lo));
       rs.n_tcf = 1;
       if (c->cfg.training) {
-        for (int ph = 0; ph < 4; ++ph)
-          IGM_TRY(tc_plan_phase(c->st, rs.tcb[ph], C, C, rs.out.H, rs.out.W, Bm, 3, 1, ph / 2, ph % 2, c->dy_hi, c->dy_lo,
-                                l.wb_hi, l.wb_lo));
-        rs.n_tcb = 4;
+        IGM_TRY(tc_plan_phases4(c->st, rs.tcb[0], C, C, rs.out.H, rs.out.W, Bm, 3, 1, c->dy_hi, c->dy_lo, l.wb_hi, l.wb_lo));
+        rs.n_tcb = 1;
         // S = X (fine grid, ci), P = dY (coarse grid, co); OIHW: ci stride KK, co stride C*KK
         IGM_TRY(tcw_plan_strided(c->st, rs.tcw, C, C, rs.out.H, rs.out.W, Bm, 3, 1, rs.in->hi, rs.in->lo, c->dy_hi, c->dy_lo,
                                  KK, (int64_t)C * KK));
       }
     } else {
       // Upsample ConvTranspose2d(C, C, 4, 2, 1): forward = 4 parity phases over X; data gradient = strided conv over dY
-      for (int ph = 0; ph < 4; ++ph)
-        IGM_TRY(tc_plan_phase(c->st, rs.tcf[ph], C, C, rs.Hin, rs.Win, Bm, 4, 1, ph / 2, ph % 2, rs.in->hi, rs.in->lo,
-                              l.wf_hi, l.wf_lo));
-      rs.n_tcf = 4;
+      IGM_TRY(tc_plan_phases4(c->st, rs.tcf[0], C, C, rs.Hin, rs.Win, Bm, 4, 1, rs.in->hi, rs.in->lo, l.wf_hi, l.wf_lo));
+      rs.n_tcf = 1;
       if (c->cfg.training) {
         IGM_TRY(tc_plan_strided(c->st, rs.tcb[0], C, C, rs.out.H, rs.out.W, Bm, 4, 1, c->dy_hi, c->dy_lo, l.wb_hi, l.wb_lo));
         rs.n_tcb = 1;
