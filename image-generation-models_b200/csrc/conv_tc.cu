@@ -416,19 +416,30 @@ __global__ void __launch_bounds__(256) split_colsum_kernel(const float* __restri
   const int L = C >> 2, R = 256 / L;
   const int c4 = threadIdx.x % L, slot = threadIdx.x / L;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int64_t m = (int64_t)blockIdx.x * R + slot; m < M; m += (int64_t)gridDim.x * R) {
-    const int64_t o = m * C + c4 * 4;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(src + o));
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    const float x[4] = {v.x, v.y, v.z, v.w};
-    __align__(8) __nv_bfloat16 h[4], l[4];
+  const int64_t stride = (int64_t)gridDim.x * R;
+  for (int64_t m0 = (int64_t)blockIdx.x * R + slot; m0 < M; m0 += 4 * stride) {
+    float4 v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      h[j] = __float2bfloat16_rn(x[j]);
-      l[j] = __float2bfloat16_rn(x[j] - __bfloat162float(h[j]));
+    for (int u = 0; u < 4; ++u) {   // four independent 128-bit loads in flight per thread
+      const int64_t m = m0 + u * stride;
+      v[u] = (m < M) ? __ldg(reinterpret_cast<const float4*>(src + m * C + c4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(h);
-    *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(l);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t m = m0 + u * stride;
+      if (m >= M) break;
+      const int64_t o = m * C + c4 * 4;
+      acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+      const float x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      __align__(8) __nv_bfloat16 h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        h[j] = __float2bfloat16_rn(x[j]);
+        l[j] = __float2bfloat16_rn(x[j] - __bfloat162float(h[j]));
+      }
+      *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(h);
+      *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(l);
+    }
   }
   red[threadIdx.x] = acc;
   __syncthreads();
@@ -890,8 +901,8 @@ int launch_split_bf16_colsum(const LaunchCtx& lc, const float* src, int64_t M, i
                              __nv_bfloat16* lo, float* colsum) {
   if (!split_colsum_ok(C)) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "split+colsum: channels must be a power of two in [32, 1024]");
   const int R = 256 / (C >> 2);
-  int blocks = (int)cdiv64(M, (int64_t)R * 4);   // >= 4 rows per thread
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  int blocks = (int)cdiv64(M, (int64_t)R * 8);   // >= 8 rows per thread
+  if (blocks > 148 * 2) blocks = 148 * 2;        // one atomic per channel and CTA: keep the same-address count low
   if (blocks < 1) blocks = 1;
   ProfScope ps_(lc, K_ELEM, 3.0 * M * C, 8.0 * M * C);
   split_colsum_kernel<<<blocks, 256, 0, lc.stream>>>(src, M, C, hi, lo, colsum);
