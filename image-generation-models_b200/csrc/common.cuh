@@ -101,6 +101,26 @@ inline int post_launch(const LaunchCtx& lc, const char* file, int line) {
 }
 #define IGM_POST_LAUNCH(lc) IGM_TRY(::igm::post_launch((lc), __FILE__, __LINE__))
 
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream is still draining
+// (launch latency and the kernel's own prologue overlap the predecessor's tail); the kernel MUST execute pdl_wait()
+// before it touches anything the predecessor wrote.  IGM_PDL=0 launches such kernels the ordinary way.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -124,6 +124,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   const int tiles_ph = p.tiles_m * p.tiles_n;
   const int num_tiles = tiles_ph * p.nph;
@@ -800,8 +801,9 @@ static int launch_tc_impl(const LaunchCtx& lc, const TcConv& t, const TcArgs& a,
     attr_done = true;
   }
   int grid = num_tiles < 148 ? num_tiles : 148;
-  conv_tc_kernel<BN><<<grid, 192, C::SMEM_BYTES, lc.stream>>>(t.a_hi, t.a_lo, t.a1_hi, t.a1_lo, t.b_hi, t.b_lo, t.om.m0, t.om.m1,
-                                                              t.om.mh, t.om.ml, a);
+  cudaError_t le = launch_pdl(conv_tc_kernel<BN>, dim3(grid), dim3(192), (size_t)C::SMEM_BYTES, lc.stream, t.a_hi, t.a_lo, t.a1_hi,
+                              t.a1_lo, t.b_hi, t.b_lo, t.om.m0, t.om.m1, t.om.mh, t.om.ml, a);
+  if (le != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le));
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }

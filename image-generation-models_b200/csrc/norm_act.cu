@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
   __shared__ float s_mean[kGroups], s_rstd[kGroups];
   const GnLayout ly(C);
   const int b = blockIdx.x / nchunks, chunk = blockIdx.x % nchunks;
+  pdl_wait();
   if (threadIdx.x < kGroups) {
     float m, r;
     finalize_stats(part, b, nparts, threadIdx.x, HW * ly.cpg, m, r);
@@ -795,8 +796,9 @@ int launch_gn_apply(const LaunchCtx& lc, const float* y, const float* part, cons
   const int kGnChunk = gn_chunk(B, HW, C);
   const int nchunks = cdiv(HW, kGnChunk);
   ProfScope ps_(lc, K_NORM, 30.0 * B * HW * C, 4.0 * B * HW * C * (res ? 3 : 2));
-  gn_apply_kernel<<<B * nchunks, 256, 0, lc.stream>>>(y, part, gamma, beta, temb, temb_stride, res, out,
-                                                      stats, HW, C, nchunks, out_hi, out_lo, nparts, kGnChunk);
+  cudaError_t le = launch_pdl(gn_apply_kernel, dim3(B * nchunks), dim3(256), 0, lc.stream, y, part, gamma, beta, temb, temb_stride,
+                              res, out, stats, HW, C, nchunks, out_hi, out_lo, nparts, kGnChunk);
+  if (le != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le));
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }

@@ -51,6 +51,11 @@ void Profiler::reset() {
   recs.clear();
 }
 
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("IGM_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 Status& global_status() {
   static Status s;
   return s;

@@ -156,6 +156,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap ts_hi, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (n_my > 0) {
     if (warp == 0) {
@@ -414,7 +415,9 @@ int launch_wgrad_halo(const LaunchCtx& lc, const TcWgradHalo& t, int B) {
   const double flops = 2.0 * B * t.H * t.W * (double)t.Cin * t.Cout * 9;
   const double bytes = 4.0 * ((double)B * t.H * t.W * (t.Cin + t.Cout) + 9.0 * t.Cin * t.Cout);
   ProfScope ps_(lc, K_CONV_WGRAD, flops, bytes);
-  wgrad_halo_kernel<<<grid, 192, smem, lc.stream>>>(t.s_hi, t.s_lo, t.p_hi, t.p_lo, t.p1_hi, t.p1_lo, a);
+  cudaError_t le = launch_pdl(wgrad_halo_kernel, dim3(grid), dim3(192), (size_t)smem, lc.stream, t.s_hi, t.s_lo, t.p_hi, t.p_lo,
+                              t.p1_hi, t.p1_lo, a);
+  if (le != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le));
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }

@@ -109,6 +109,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tdy_hi, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (n_stages_total > 0) {
     if (warp == 0) {
@@ -251,7 +252,9 @@ int launch_impl(const LaunchCtx& lc, const TcWgrad& t, const WArgs& a, int grid)
     if (e != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(e));
     attr_done = true;
   }
-  wgrad_tc_kernel<NB><<<grid, 192, C::SMEM_BYTES, lc.stream>>>(t.s_hi, t.s_lo, t.p_hi, t.p_lo, t.p1_hi, t.p1_lo, a);
+  cudaError_t le = launch_pdl(wgrad_tc_kernel<NB>, dim3(grid), dim3(192), (size_t)C::SMEM_BYTES, lc.stream, t.s_hi, t.s_lo, t.p_hi,
+                              t.p_lo, t.p1_hi, t.p1_lo, a);
+  if (le != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le));
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }
