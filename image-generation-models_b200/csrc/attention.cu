@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(256) linattn_ctx_kernel(const float* __restric
   __shared__ float ctxs[D][D + 1];
   __shared__ float red[8][D];
   __shared__ float s_kmax[D], s_ksum[D];
+  pdl_wait();
   const int bh = blockIdx.x, b = bh / kHeads, h = bh % kHeads;
   const int nsplit = gridDim.y;
   const int n0 = blockIdx.y * CH, rows = min(CH, N - n0);
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(256) linattn_out_kernel(const float* __restric
                                                           __nv_bfloat16* __restrict__ out_hi,
                                                           __nv_bfloat16* __restrict__ out_lo) {
   __shared__ __align__(16) float Xs[CH][D];
+  pdl_wait();
   const int bh = blockIdx.x, b = bh / kHeads, h = bh % kHeads;
   const int n0 = blockIdx.y * CH, rows = min(CH, N - n0);
   const int tid = threadIdx.x;
@@ -238,6 +240,7 @@ __global__ void __launch_bounds__(256) linattn_bwd_dctx_kernel(const float* __re
   float (*Ys)[D] = reinterpret_cast<float (*)[D]>(buf + CH * D);
   float (*part)[64][17] = reinterpret_cast<float (*)[64][17]>(buf);
   __shared__ float full[D][D + 1];
+  pdl_wait();
   const int bh = blockIdx.x, b = bh / kHeads, h = bh % kHeads;
   const int nsplit = gridDim.y;
   const int n0 = blockIdx.y * CH, rows = min(CH, N - n0);
@@ -290,6 +293,7 @@ __global__ void __launch_bounds__(256, 3) linattn_bwd_rows_kernel(const float* _
   __shared__ __align__(16) float Vs[SUB][D];   // v
   __shared__ float ctxs[D][D + 1];
   __shared__ float dctxs[D][D + 1];
+  pdl_wait();
   const int bh = blockIdx.x, b = bh / kHeads, h = bh % kHeads;
   const int tid = threadIdx.x;
   for (int i = tid; i < D * D; i += 256) {
@@ -379,9 +383,9 @@ int launch_linattn_forward(const LaunchCtx& lc, const float* qkv, float* out, fl
   ProfScope ps_(lc, K_ATTN, 4.0 * B * kHeads * (double)n * D * D, 4.0 * B * (double)n * (QKV + HD));
   unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
   float* parts = ws + (int64_t)B * kHeads * (64 + D * D);
-  linattn_ctx_kernel<<<dim3(B * kHeads, nsplit), 256, 0, lc.stream>>>(qkv, parts, counters, ctx, kstat, n);
+  { cudaError_t le_ = launch_pdl(linattn_ctx_kernel, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, parts, counters, ctx, kstat, n); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
-  linattn_out_kernel<<<dim3(B * kHeads, nsplit), 256, 0, lc.stream>>>(qkv, ctx, out, n, out_hi, out_lo);
+  { cudaError_t le_ = launch_pdl(linattn_out_kernel, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, ctx, out, n, out_hi, out_lo); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }
@@ -395,9 +399,9 @@ int launch_linattn_backward(const LaunchCtx& lc, const float* qkv, const float* 
   unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
   float* dctx = ws + (int64_t)B * kHeads * 64;
   float* parts = ws + (int64_t)B * kHeads * (64 + D * D);
-  linattn_bwd_dctx_kernel<<<dim3(B * kHeads, nsplit), 256, 0, lc.stream>>>(qkv, d_out, parts, counters, dctx, n);
+  { cudaError_t le_ = launch_pdl(linattn_bwd_dctx_kernel, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, d_out, parts, counters, dctx, n); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
-  linattn_bwd_rows_kernel<<<dim3(B * kHeads, nsplit), 256, 0, lc.stream>>>(qkv, ctx, kstat, d_out, dctx, d_qkv, n, d_hi, d_lo);
+  { cudaError_t le_ = launch_pdl(linattn_bwd_rows_kernel, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, ctx, kstat, d_out, dctx, d_qkv, n, d_hi, d_lo); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }

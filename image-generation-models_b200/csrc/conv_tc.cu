@@ -389,6 +389,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
 // ---------------------------------------------------------------------------
 __global__ void split_bf16_kernel(const float* __restrict__ src, int64_t M, int C, __nv_bfloat16* __restrict__ hi,
                                   __nv_bfloat16* __restrict__ lo, int cdst, int coff) {
+  pdl_wait();
   const int c4n = C >> 2;
   const int64_t total = M * c4n;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -414,6 +415,7 @@ __global__ void __launch_bounds__(256) split_colsum_kernel(const float* __restri
                                                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                                            float* __restrict__ colsum) {
   __shared__ float4 red[256];
+  pdl_wait();
   const int L = C >> 2, R = 256 / L;
   const int c4 = threadIdx.x % L, slot = threadIdx.x / L;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -884,7 +886,7 @@ int launch_split_bf16(const LaunchCtx& lc, const float* src, int64_t M, int C, _
   int blocks = (int)cdiv64(total, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   ProfScope ps_(lc, K_ELEM, 2.0 * M * C, 8.0 * M * C);
-  split_bf16_kernel<<<blocks, 256, 0, lc.stream>>>(src, M, C, hi, lo, cdst, coff);
+  { cudaError_t le_ = launch_pdl(split_bf16_kernel, dim3(blocks), dim3(256), (size_t)(0), lc.stream, src, M, C, hi, lo, cdst, coff); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }
@@ -907,7 +909,7 @@ int launch_split_bf16_colsum(const LaunchCtx& lc, const float* src, int64_t M, i
   if (blocks > 148 * 2) blocks = 148 * 2;        // one atomic per channel and CTA: keep the same-address count low
   if (blocks < 1) blocks = 1;
   ProfScope ps_(lc, K_ELEM, 3.0 * M * C, 8.0 * M * C);
-  split_colsum_kernel<<<blocks, 256, 0, lc.stream>>>(src, M, C, hi, lo, colsum);
+  { cudaError_t le_ = launch_pdl(split_colsum_kernel, dim3(blocks), dim3(256), (size_t)(0), lc.stream, src, M, C, hi, lo, colsum); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }

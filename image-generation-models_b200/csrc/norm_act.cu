@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(256) gn_bwd_fused_kernel(const GnBwdArgs a, in
   __shared__ float cl_grp[kGroups][2];    // this CTA's (sum dn, sum dn*n) per group, read by the whole cluster
   __shared__ float s_m[kGroups][2];
   __shared__ float4 sc[256][4];           // per-thread channel partials -> per-channel CTA totals in sc[0..L)
+  pdl_wait();
   const GnLayout ly(a.C);
   const int rank = (int)cluster.block_rank();
   const int b = blockIdx.x / cs;
@@ -436,6 +437,7 @@ __global__ void __launch_bounds__(256) ln_forward_kernel(const float* __restrict
                                                          const float* __restrict__ bta, float* __restrict__ out,
                                                          int64_t M, int C, __nv_bfloat16* __restrict__ out_hi,
                                                          __nv_bfloat16* __restrict__ out_lo) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -489,6 +491,7 @@ __global__ void __launch_bounds__(256) ln_backward_kernel(const float* __restric
                                                           float* __restrict__ dx, float* __restrict__ ws,
                                                           int64_t M, int C) {
   extern __shared__ float sred[];   // [8 warps][2][C]
+  pdl_wait();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = (int64_t)blockIdx.x * 8 + wib;
   const int64_t nwarps = (int64_t)gridDim.x * 8;
@@ -583,6 +586,7 @@ __global__ void __launch_bounds__(256) ln_backward_kernel(const float* __restric
 __global__ void __launch_bounds__(1024) ln_param_finalize_kernel(const float* __restrict__ ws, int nparts, int C,
                                                                  float* __restrict__ dg, float* __restrict__ db) {
   __shared__ float red[32][2][33];
+  pdl_wait();
   const int c = blockIdx.x * 32 + threadIdx.x;
   float tg = 0.f, tb = 0.f;
   if (c < C) {
@@ -623,6 +627,7 @@ __global__ void __launch_bounds__(256) ln_forward_t_kernel(const float* __restri
                                                            int64_t M, __nv_bfloat16* __restrict__ out_hi,
                                                            __nv_bfloat16* __restrict__ out_lo) {
   constexpr int C = 4 * LPP * V, PPW = 32 / LPP;
+  pdl_wait();
   const int lane = threadIdx.x & 31, sub = lane / LPP, l = lane % LPP;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -673,6 +678,7 @@ __global__ void __launch_bounds__(256) ln_backward_t_kernel(const float* __restr
                                                             float* __restrict__ dx, float* __restrict__ ws, int64_t M) {
   constexpr int C = 4 * LPP * V, PPW = 32 / LPP;
   extern __shared__ float sred[];   // [8 warps][2][C]
+  pdl_wait();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, sub = lane / LPP, l = lane % LPP;
   const int64_t warp = (int64_t)blockIdx.x * 8 + wib;
   const int64_t nwarps = (int64_t)gridDim.x * 8;
@@ -831,13 +837,15 @@ int launch_gn_backward(const LaunchCtx& lc, const GnBwdArgs& a) {
     cfg.blockDim = dim3(256);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = lc.stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e;
     switch (nv) {
       case 1: e = cudaLaunchKernelEx(&cfg, gn_bwd_fused_kernel<1>, a, cs); break;
@@ -874,12 +882,12 @@ int launch_ln_forward(const LaunchCtx& lc, const float* x, const float* g, const
   ProfScope ps_(lc, K_NORM, 8.0 * M * C, 8.0 * M * C);
   const int grid = ln_grid(M);
   switch (C) {
-    case 32:   ln_forward_t_kernel<8, 1><<<grid, 256, 0, lc.stream>>>(x, g, b, out, M, out_hi, out_lo); break;
-    case 64:   ln_forward_t_kernel<16, 1><<<grid, 256, 0, lc.stream>>>(x, g, b, out, M, out_hi, out_lo); break;
-    case 128:  ln_forward_t_kernel<32, 1><<<grid, 256, 0, lc.stream>>>(x, g, b, out, M, out_hi, out_lo); break;
-    case 256:  ln_forward_t_kernel<32, 2><<<grid, 256, 0, lc.stream>>>(x, g, b, out, M, out_hi, out_lo); break;
-    case 512:  ln_forward_t_kernel<32, 4><<<grid, 256, 0, lc.stream>>>(x, g, b, out, M, out_hi, out_lo); break;
-    default:   ln_forward_kernel<<<grid, 256, 0, lc.stream>>>(x, g, b, out, M, C, out_hi, out_lo); break;
+    case 32:   { cudaError_t le_ = launch_pdl(ln_forward_t_kernel<8, 1>, dim3(grid), dim3(256), (size_t)(0), lc.stream, x, g, b, out, M, out_hi, out_lo); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); } break;
+    case 64:   { cudaError_t le_ = launch_pdl(ln_forward_t_kernel<16, 1>, dim3(grid), dim3(256), (size_t)(0), lc.stream, x, g, b, out, M, out_hi, out_lo); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); } break;
+    case 128:  { cudaError_t le_ = launch_pdl(ln_forward_t_kernel<32, 1>, dim3(grid), dim3(256), (size_t)(0), lc.stream, x, g, b, out, M, out_hi, out_lo); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); } break;
+    case 256:  { cudaError_t le_ = launch_pdl(ln_forward_t_kernel<32, 2>, dim3(grid), dim3(256), (size_t)(0), lc.stream, x, g, b, out, M, out_hi, out_lo); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); } break;
+    case 512:  { cudaError_t le_ = launch_pdl(ln_forward_t_kernel<32, 4>, dim3(grid), dim3(256), (size_t)(0), lc.stream, x, g, b, out, M, out_hi, out_lo); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); } break;
+    default:   { cudaError_t le_ = launch_pdl(ln_forward_kernel, dim3(grid), dim3(256), (size_t)(0), lc.stream, x, g, b, out, M, C, out_hi, out_lo); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); } break;
   }
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
@@ -898,15 +906,15 @@ int launch_ln_backward(const LaunchCtx& lc, const float* d_out, const float* x, 
     if (e != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(e));
   }
   switch (C) {
-    case 32:   ln_backward_t_kernel<8, 1><<<grid, 256, smem, lc.stream>>>(d_out, x, g, d_res, dx, ws, M); break;
-    case 64:   ln_backward_t_kernel<16, 1><<<grid, 256, smem, lc.stream>>>(d_out, x, g, d_res, dx, ws, M); break;
-    case 128:  ln_backward_t_kernel<32, 1><<<grid, 256, smem, lc.stream>>>(d_out, x, g, d_res, dx, ws, M); break;
-    case 256:  ln_backward_t_kernel<32, 2><<<grid, 256, smem, lc.stream>>>(d_out, x, g, d_res, dx, ws, M); break;
-    case 512:  ln_backward_t_kernel<32, 4><<<grid, 256, smem, lc.stream>>>(d_out, x, g, d_res, dx, ws, M); break;
-    default:   ln_backward_kernel<<<grid, 256, smem, lc.stream>>>(d_out, x, g, d_res, dx, ws, M, C); break;
+    case 32:   { cudaError_t le_ = launch_pdl(ln_backward_t_kernel<8, 1>, dim3(grid), dim3(256), (size_t)(smem), lc.stream, d_out, x, g, d_res, dx, ws, M); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); } break;
+    case 64:   { cudaError_t le_ = launch_pdl(ln_backward_t_kernel<16, 1>, dim3(grid), dim3(256), (size_t)(smem), lc.stream, d_out, x, g, d_res, dx, ws, M); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); } break;
+    case 128:  { cudaError_t le_ = launch_pdl(ln_backward_t_kernel<32, 1>, dim3(grid), dim3(256), (size_t)(smem), lc.stream, d_out, x, g, d_res, dx, ws, M); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); } break;
+    case 256:  { cudaError_t le_ = launch_pdl(ln_backward_t_kernel<32, 2>, dim3(grid), dim3(256), (size_t)(smem), lc.stream, d_out, x, g, d_res, dx, ws, M); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); } break;
+    case 512:  { cudaError_t le_ = launch_pdl(ln_backward_t_kernel<32, 4>, dim3(grid), dim3(256), (size_t)(smem), lc.stream, d_out, x, g, d_res, dx, ws, M); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); } break;
+    default:   { cudaError_t le_ = launch_pdl(ln_backward_kernel, dim3(grid), dim3(256), (size_t)(smem), lc.stream, d_out, x, g, d_res, dx, ws, M, C); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); } break;
   }
   IGM_POST_LAUNCH(lc);
-  ln_param_finalize_kernel<<<dim3(cdiv(C, 32), cdiv(grid, 128)), dim3(32, 32), 0, lc.stream>>>(ws, grid, C, dg, db);
+  { cudaError_t le_ = launch_pdl(ln_param_finalize_kernel, dim3(cdiv(C, 32), cdiv(grid, 128)), dim3(32, 32), (size_t)0, lc.stream, ws, grid, C, dg, db); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }
