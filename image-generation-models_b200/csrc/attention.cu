@@ -371,6 +371,73 @@ __global__ void __launch_bounds__(256, 3) linattn_bwd_rows_kernel(const float* _
   }
 }
 
+// Inference shortcut for n >= 2C: out = ctx^T q and y = W_out out + b collapse into one per-image C x C matrix
+//   M_b = A_b W_q,   A_b[c][(h,d)] = sum_e W_out[c][(h,e)] ctx_b[h][d][e]        (y[:, n] = M_b LN(x)[:, n] + b)
+// so the attention output never exists; the to_out conv then runs with per-image weights M_b on LN(x).
+// grid (B, C / 32): 32 rows of M_b per CTA; emitted as bf16 hi / lo rows [b * C + c][c'] (K-major weight tile rows).
+__global__ void __launch_bounds__(256) linattn_mb_kernel(const float* __restrict__ ctx, const float* __restrict__ w_out,
+                                                         const float* __restrict__ w_q, int C,
+                                                         __nv_bfloat16* __restrict__ mb_hi, __nv_bfloat16* __restrict__ mb_lo) {
+  extern __shared__ __align__(16) float msm[];
+  float* s_ctx = msm;               // [4 * 32 rows][33]  (padded: the 8 lanes of a row group read 8 different d rows)
+  float* s_wo = msm + 4224;         // [32 rows][128]
+  float* s_a = msm + 4224 + 4096;   // [32 rows][128]
+  pdl_wait();
+  const int b = blockIdx.x, c0 = blockIdx.y * 32, tid = threadIdx.x;
+  for (int i = tid; i < 4096; i += 256) {
+    s_ctx[(i >> 5) * 33 + (i & 31)] = __ldg(ctx + (int64_t)b * 4096 + i);
+    s_wo[i] = __ldg(w_out + (int64_t)(c0 + (i >> 7)) * HD + (i & 127));
+  }
+  __syncthreads();
+  // A[c][(h,d)]: warp -> 4 rows, lane -> d; W_out values are warp-wide broadcasts, ctx rows are 33 floats apart
+  {
+    const int w = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int r = w * 4 + rr;
+#pragma unroll
+      for (int h = 0; h < kHeads; ++h) {
+        const float* wo = s_wo + r * HD + h * D;
+        const float* cx = s_ctx + (h * D + lane) * 33;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int e = 0; e < D; e += 2) {
+          a0 = fmaf(wo[e], cx[e], a0);
+          a1 = fmaf(wo[e + 1], cx[e + 1], a1);
+        }
+        s_a[r * HD + h * D + lane] = a0 + a1;
+      }
+    }
+  }
+  __syncthreads();
+  // M[c][c'] = sum_k A[c][k] Wq[k][c']: thread -> column c' (coalesced Wq rows) x 4 rows, k in steps of 4
+  for (int o = tid; o < 8 * C; o += 256) {
+    const int cp = o % C, rg = o / C;       // rows rg*4 .. rg*4+3
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int k = 0; k < HD; k += 4) {
+      float wq[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) wq[u] = __ldg(w_q + (int64_t)(k + u) * C + cp);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 av = *reinterpret_cast<const float4*>(s_a + (rg * 4 + i) * HD + k);
+        acc[i] = fmaf(av.x, wq[0], acc[i]);
+        acc[i] = fmaf(av.y, wq[1], acc[i]);
+        acc[i] = fmaf(av.z, wq[2], acc[i]);
+        acc[i] = fmaf(av.w, wq[3], acc[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t dst = ((int64_t)b * C + c0 + rg * 4 + i) * C + cp;
+      const __nv_bfloat16 hv = __float2bfloat16_rn(acc[i]);
+      mb_hi[dst] = hv;
+      mb_lo[dst] = __float2bfloat16_rn(acc[i] - __bfloat162float(hv));
+    }
+  }
+}
+
 }  // namespace
 
 // scratch layout: [B*heads] chunk counters (zero on entry, self re-arming) | [B*heads][32*32] dctx | chunk partials
@@ -386,6 +453,34 @@ int launch_linattn_forward(const LaunchCtx& lc, const float* qkv, float* out, fl
   { cudaError_t le_ = launch_pdl(linattn_ctx_kernel, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, parts, counters, ctx, kstat, n); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
   { cudaError_t le_ = launch_pdl(linattn_out_kernel, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, ctx, out, n, out_hi, out_lo); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+// statistics + context only (the first half of launch_linattn_forward)
+int launch_linattn_ctx(const LaunchCtx& lc, const float* qkv, float* ctx, float* kstat, int B, int n, float* ws) {
+  const int nsplit = cdiv(n, CH);
+  if (nsplit > kMaxSplit) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linear attention: more than 8192 pixels per image");
+  ProfScope ps_(lc, K_ATTN, 2.0 * B * kHeads * (double)n * D * D, 4.0 * B * (double)n * 2 * HD);
+  unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
+  float* parts = ws + (int64_t)B * kHeads * (64 + D * D);
+  { cudaError_t le_ = launch_pdl(linattn_ctx_kernel, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, parts, counters, ctx, kstat, n); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+int launch_linattn_mb(const LaunchCtx& lc, const float* ctx, const float* w_out, const float* w_q, int B, int C,
+                      __nv_bfloat16* mb_hi, __nv_bfloat16* mb_lo) {
+  if (C % 32 != 0) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linattn_mb: C must be a multiple of 32");
+  const size_t smem = (4224 + 2 * 4096) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(linattn_mb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(e));
+    attr = true;
+  }
+  ProfScope ps_(lc, K_ATTN, 2.0 * B * C * (double)HD * (D + C), 4.0 * B * (4096.0 + C * C));
+  { cudaError_t le_ = launch_pdl(linattn_mb_kernel, dim3(B, C / 32), dim3(256), smem, lc.stream, ctx, w_out, w_q, C, mb_hi, mb_lo); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }

@@ -244,6 +244,10 @@ int ln_backward_parts(int64_t M);   // CTAs (= partial rows of ws [parts][2][C])
 int linattn_ws_floats(int B, int n);
 int launch_linattn_forward(const LaunchCtx& lc, const float* qkv, float* out, float* ctx, float* kstat,
                            int B, int n, float* ws, __nv_bfloat16* out_hi = nullptr, __nv_bfloat16* out_lo = nullptr);
+// inference shortcut (attention.cu: linattn_mb_kernel): context only, then the per-image matrix M_b = W_out ctx^T W_q
+int launch_linattn_ctx(const LaunchCtx& lc, const float* qkv, float* ctx, float* kstat, int B, int n, float* ws);
+int launch_linattn_mb(const LaunchCtx& lc, const float* ctx, const float* w_out, const float* w_q, int B, int C,
+                      __nv_bfloat16* mb_hi, __nv_bfloat16* mb_lo);
 int launch_linattn_backward(const LaunchCtx& lc, const float* qkv, const float* ctx, const float* kstat,
                             const float* d_out, float* d_qkv, int B, int n, float* ws,
                             __nv_bfloat16* d_hi = nullptr, __nv_bfloat16* d_lo = nullptr);

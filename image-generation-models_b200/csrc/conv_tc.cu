@@ -50,6 +50,7 @@ struct TcArgs {
   int tma_out, wb, hb, ib;
   // output-parity phases merged into one launch: phase ph owns taps [ph_tap0, ph_tap0 + ph_ntaps) and writes at (ph_oy, ph_ox)
   int nph, ph_tap0[4], ph_ntaps[4], ph_oy[4], ph_ox[4];
+  int w_img_rows;   // > 0: every image has its own weight matrix (rows b * w_img_rows + n of the weight tensor)
 };
 
 // (sum, sum of squares) of the SEG-channel segments of a 32-column chunk, reduced over the warp's
@@ -157,8 +158,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
               tma_load_5d(st, &ta1_hi, &full[stage], ch - p.K0, tp.dx, tp.py, y0 + tp.dy, b0);
               tma_load_5d(st + A_TILE_BYTES, &ta1_lo, &full[stage], ch - p.K0, tp.dx, tp.py, y0 + tp.dy, b0);
             }
-            tma_load_2d(st + 2 * A_TILE_BYTES, &tb_hi, &full[stage], tp.wtap * p.K + ch, tn * BN);
-            tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &tb_lo, &full[stage], tp.wtap * p.K + ch, tn * BN);
+            const int wrow = tn * BN + b0 * p.w_img_rows;
+            tma_load_2d(st + 2 * A_TILE_BYTES, &tb_hi, &full[stage], tp.wtap * p.K + ch, wrow);
+            tma_load_2d(st + 2 * A_TILE_BYTES + C::B_TILE_BYTES, &tb_lo, &full[stage], tp.wtap * p.K + ch, wrow);
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -593,7 +595,7 @@ namespace {
 
 // Tile shape over a GH x GW grid and the weight descriptors; shared by every plan flavour.
 int plan_common(Status& st, TcConv& t, int K, int K0, int N, int GH, int GW, int Bmax, int wtaps,
-                __nv_bfloat16* w_hi, __nv_bfloat16* w_lo) {
+                __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, bool per_image = false) {
   auto enc = get_encode_fn();
   if (!enc) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   t.K = K; t.K0 = K0; t.N = N; t.H = GH; t.W = GW; t.Bmax = Bmax;
@@ -602,6 +604,8 @@ int plan_common(Status& st, TcConv& t, int K, int K0, int N, int GH, int GW, int
   if (GH * GW <= BM) { t.BH = GH; t.BB = BM / (GH * GW); }
   else { t.BH = BM / GW; t.BB = 1; }
   if (t.BB > Bmax) t.BB = Bmax;
+  if (per_image) t.BB = 1;   // a tile must not span images when every image has its own weights
+  t.w_img_rows = per_image ? N : 0;
   t.BN = (N % 128 == 0) ? 128 : 64;
   if (t.BN == 128) {
     // one CTA per SM: prefer 64-wide tiles when 128-wide ones leave most of a wave empty
@@ -612,7 +616,7 @@ int plan_common(Status& st, TcConv& t, int K, int K0, int N, int GH, int GW, int
   }
   // weights: [N rows][wtaps*K cols], K-major
   for (int which = 0; which < 2; ++which) {
-    cuuint64_t dims[2] = {(cuuint64_t)wtaps * K, (cuuint64_t)N};
+    cuuint64_t dims[2] = {(cuuint64_t)wtaps * K, (cuuint64_t)N * (per_image ? Bmax : 1)};
     cuuint64_t strides[1] = {(cuuint64_t)wtaps * K * 2};
     cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)t.BN};
     cuuint32_t es[2] = {1, 1};
@@ -667,6 +671,23 @@ int tc_plan(Status& st, TcConv& t, int K, int N, int H, int W, int Bmax, int KH,
   IGM_TRY(encode_act(st, &t.a_lo, a_lo, K0, H, W, Bmax, false, t));
   IGM_TRY(encode_act(st, &t.a1_hi, two ? (void*)a1_hi : (void*)a_hi, two ? K - K0 : K0, H, W, Bmax, false, t));
   IGM_TRY(encode_act(st, &t.a1_lo, two ? (void*)a1_lo : (void*)a_lo, two ? K - K0 : K0, H, W, Bmax, false, t));
+  t.valid = true;
+  return IGM_OK;
+}
+
+int tc_plan_img(Status& st, TcConv& t, int K, int N, int H, int W, int Bmax, __nv_bfloat16* a_hi, __nv_bfloat16* a_lo,
+                __nv_bfloat16* w_hi, __nv_bfloat16* w_lo) {
+  t.valid = false;
+  if (!tc_eligible(K, N, H, W, 1)) IGM_FAIL(st, IGM_ERR_INVALID, "shape not eligible for the tcgen05 engine");
+  IGM_TRY(plan_common(st, t, K, K, N, H, W, Bmax, 1, w_hi, w_lo, /*per_image=*/true));
+  t.KH = t.KW = 1; t.pad = 0;
+  t.ntaps = 1;
+  t.taps[0] = TcTap{0, 0, 0, 0, 0};
+  t.Csrc = K;
+  t.out_H = H; t.out_W = W; t.sy = t.sx = 1; t.oy_off = t.ox_off = 0;
+  IGM_TRY(encode_act(st, &t.a_hi, a_hi, K, H, W, Bmax, false, t));
+  IGM_TRY(encode_act(st, &t.a_lo, a_lo, K, H, W, Bmax, false, t));
+  t.a1_hi = t.a_hi; t.a1_lo = t.a_lo;
   t.valid = true;
   return IGM_OK;
 }
@@ -834,6 +855,7 @@ int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r) {
   a.out_H = t.out_H; a.out_W = t.out_W; a.sy = t.sy; a.sx = t.sx; a.oy_off = t.oy_off; a.ox_off = t.ox_off;
   a.BH = t.BH; a.BW = t.BW; a.BB = t.BB;
   a.nph = t.nph;
+  a.w_img_rows = t.w_img_rows;
   for (int i = 0; i < 4; ++i) { a.ph_tap0[i] = t.ph_tap0[i]; a.ph_ntaps[i] = t.ph_ntaps[i]; a.ph_oy[i] = t.ph_oy[i]; a.ph_ox[i] = t.ph_ox[i]; }
   if (t.nph == 1) { a.ph_tap0[0] = 0; a.ph_ntaps[0] = t.ntaps; a.ph_oy[0] = t.oy_off; a.ph_ox[0] = t.ox_off; }
   a.tiles_per_img = (t.BB > 1) ? 1 : cdiv(t.H, t.BH);

@@ -36,6 +36,7 @@ struct TcConv {
   // output pixel of tile position (oy, ox):  (oy*sy + oy_off, ox*sx + ox_off) on an out_H x out_W image
   int out_H = 0, out_W = 0, sy = 1, sx = 1, oy_off = 0, ox_off = 0;
   // all four output-parity phases in ONE launch (tc_plan_phases4): per-phase tap ranges and output offsets
+  int w_img_rows = 0;   // > 0: per-image weight matrices (tc_plan_img)
   int nph = 1, ph_tap0[4] = {0, 0, 0, 0}, ph_ntaps[4] = {0, 0, 0, 0}, ph_oy[4] = {0, 0, 0, 0}, ph_ox[4] = {0, 0, 0, 0};
   // TMA-store epilogue: output tensor maps, (re-)encoded when a launch passes a new output pointer
   struct OutMaps {
@@ -60,6 +61,10 @@ int tc_plan_phase(Status& st, TcConv& t, int K, int N, int GH, int GW, int Bmax,
 // the four phases (py, px) of tc_plan_phase as one plan / one launch (tiles of the four phases interleave on the SMs)
 int tc_plan_phases4(Status& st, TcConv& t, int K, int N, int GH, int GW, int Bmax, int KH, int pad, __nv_bfloat16* a_hi,
                     __nv_bfloat16* a_lo, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo);
+
+// 1x1 convolution whose weights differ per image: weight tensor [Bmax * N rows][K] (image b owns rows b*N .. b*N+N-1)
+int tc_plan_img(Status& st, TcConv& t, int K, int N, int H, int W, int Bmax, __nv_bfloat16* a_hi, __nv_bfloat16* a_lo,
+                __nv_bfloat16* w_hi, __nv_bfloat16* w_lo);
 
 // Can this (stride-1, non-dilated) conv run on the tensor-core engine?
 bool tc_eligible(int K, int N, int H, int W, int KH);

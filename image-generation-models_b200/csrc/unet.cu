@@ -136,6 +136,10 @@ struct AttnL {
   float* ctx = nullptr;    // [B, 4, 32, 32]
   float* kstat = nullptr;  // [B, 4, 32, 2]
   Act out;
+  // inference shortcut (n >= 2C): to_out runs with the per-image matrix M_b on LN(x); no attention output tensor
+  bool mb_ok = false;
+  __nv_bfloat16 *mb_hi = nullptr, *mb_lo = nullptr;   // [B][C][C]
+  TcConv tc_mb;
 };
 
 struct ResampleL {
@@ -219,6 +223,7 @@ struct igm_ctx {
   int fin_n = 0, fin_tiles = 0;
   double fin_elems = 0;
   bool halo_on = true;
+  bool attn_mb = true;                // IGM_ATTN_MB=0: always materialise the attention output
   PackJob* pack_dev = nullptr;        // device job table of igm_unet_pack_weights
   int pack_n = 0, pack_engine = -1;
   int64_t pack_total = 0;
@@ -431,6 +436,11 @@ struct PlanBuilder {
     a.ctx = ar.alloc((int64_t)B * kHeads * kDimHead * kDimHead);
     a.kstat = ar.alloc((int64_t)B * kHeads * kDimHead * 2);
     a.out = act(C, H, W, true);
+    a.mb_ok = H * W >= 8 * C   /* measured: only pays off when the image has many more pixels than channels */ && H * W >= 128 && C % 64 == 0 && tc_eligible(C, C, H, W, 1);
+    if (a.mb_ok) {
+      a.mb_hi = reinterpret_cast<__nv_bfloat16*>(ar.alloc(((int64_t)B * C * C + 1) / 2));
+      a.mb_lo = reinterpret_cast<__nv_bfloat16*>(ar.alloc(((int64_t)B * C * C + 1) / 2));
+    }
     tap(name + ".ln", a.ln.v, C, H, W, &a.ln);
     tap(name + ".out", a.out.v, C, H, W);
     track(H, W, C);
@@ -571,6 +581,7 @@ struct Runner {
   igm_ctx& c;
   LaunchCtx lc;
   int B;
+  bool infer = false;   // no backward pass will read this forward's intermediates (sampler steps)
 
   int64_t M(int H, int W) const { return (int64_t)B * H * W; }
   bool tc_on() const { return c.conv_engine == 1; }
@@ -773,6 +784,15 @@ struct Runner {
     const float* x = a.in->v;
     IGM_TRY(launch_ln_forward(lc, x, c.Pp(a.ln_g), c.Pp(a.ln_b), lean_ok(a.qkv) ? nullptr : a.ln.v, m, a.C, hi(a.ln), lo(a.ln)));
     IGM_TRY(conv_fwd(a.qkv, H, W, H, W, 1, 0, a.qkv_t, nullptr));
+    if (c.attn_mb && (infer || !c.cfg.training) && tc_on() && a.tc_mb.valid && use_tc(a.qkv.tc_f)) {
+      // inference, n >= 2C: y = (W_out ctx^T W_q) LN(x) + b + x with one C x C matrix per image
+      IGM_TRY(launch_linattn_ctx(lc, a.qkv_t, a.ctx, a.kstat, B, H * W, c.attn_ws));
+      IGM_TRY(launch_linattn_mb(lc, a.ctx, c.Pp(a.outc.pw), c.Pp(a.qkv.pw), B, a.C, a.mb_hi, a.mb_lo));
+      TcRun r;
+      r.B = B; r.bias = c.Pp(a.outc.pb); r.out0 = a.out.v; r.N0 = a.C; r.add0 = x; r.kclass = K_CONV_FPROP;
+      r.hi0 = hi(a.out); r.lo0 = lo(a.out);
+      return launch_conv_tc(lc, a.tc_mb, r);
+    }
     IGM_TRY(launch_linattn_forward(lc, a.qkv_t, lean_ok(a.outc) ? nullptr : a.att.v, a.ctx, a.kstat, B, H * W, c.attn_ws,
                                    hi(a.att), lo(a.att)));
     IGM_TRY(conv_fwd(a.outc, H, W, H, W, 1, 0, a.out.v, x, &a.out));
@@ -1008,6 +1028,14 @@ static int plan_tc(igm_ctx* c) {
     n_valid += (l.tc_f.valid ? 1 : 0) + (l.tc_b.valid ? 1 : 0) + (l.tc_w.valid ? 1 : 0);
     return IGM_OK;
   });
+  // per-image to_out convs of the inference attention shortcut
+  auto plan_mb = [&](AttnL& a) -> int {
+    if (!a.mb_ok || !a.ln.hi) return IGM_OK;
+    return tc_plan_img(c->st, a.tc_mb, a.C, a.C, a.H, a.W, c->cfg.max_batch, a.ln.hi, a.ln.lo, a.mb_hi, a.mb_lo);
+  };
+  if (rc == IGM_OK) for (auto& s : c->downs) { rc = plan_mb(s.attn); if (rc != IGM_OK) break; }
+  if (rc == IGM_OK) for (auto& s : c->ups) { rc = plan_mb(s.attn); if (rc != IGM_OK) break; }
+  if (rc == IGM_OK) rc = plan_mb(c->mid_attn);
   // stride-2 resampling convs
   auto plan_rs = [&](ResampleL& rs) -> int {
     ConvL& l = rs.conv;
@@ -1143,6 +1171,7 @@ int igm_unet_create(igm_ctx** out, const igm_unet_cfg* cfg, int device) {
   if (const char* ps = getenv("IGM_PREFER_SHARED")) {
     if (ps[0] == '1') cudaDeviceSetCacheConfig(cudaFuncCachePreferShared);
   }
+  if (const char* mbe = getenv("IGM_ATTN_MB")) c->attn_mb = !(mbe[0] == '0');
   const char* halo = getenv("IGM_WGRAD_HALO");
   c->halo_on = !(halo && halo[0] == '0');
   const char* eng = getenv("IGM_CONV_ENGINE");
@@ -1423,6 +1452,7 @@ int igm_ddpm_sample_loop(igm_ctx* c, float* img, const float* noise, uint64_t se
   if (n_steps == 0) return IGM_OK;
   cudaStream_t s = (cudaStream_t)stream;
   Runner r{*c, c->lc(stream), B};
+  r.infer = true;
   const int init[2] = {t_start, 0};
   IGM_CUDA(c->st, cudaMemcpyAsync(c->loop_state, init, sizeof(init), cudaMemcpyHostToDevice, s));
   // first step eagerly (also resolves lazy per-kernel attributes outside of stream capture)
@@ -1443,6 +1473,7 @@ int igm_ddpm_sample_loop(igm_ctx* c, float* img, const float* noise, uint64_t se
     const int64_t saved = c->launches;
     IGM_CUDA(c->st, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
     Runner rc{*c, c->lc((void*)cs), B};
+    rc.infer = true;
     int rcode = sampler_step(c, rc, img, noise, seed, clip_denoised);
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(cs, &graph);
