@@ -217,6 +217,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap ts_hi, const __grid_consta
       // Stacked operand: accumulator rows r and r + 64 are the hi and lo halves of the SAME input channel; the
       // lo-half warps hand their values over through the (now idle) pipeline memory, so each element is reduced once.
       float* xbuf = reinterpret_cast<float*>(smem);   // [2 buffers][2 warps][32 values][32 lanes]
+      float* tbuf = xbuf + 4096;                      // [4 warps][32][33] transpose tiles
       const int nchunks = nky * 6;
       for (int it = 0; it < nchunks; ++it) {
         const int piece = (it + split) % nchunks;
@@ -237,10 +238,22 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap ts_hi, const __grid_consta
           for (int j = 0; j < 32; ++j) v[j] += xb[j * 32];
         }
         const int kx = 2 - c0 / 64;   // N block 0 <-> dx = -1 <-> kx = 2
-        float* dst = p.ws + (((int64_t)(ky * 3 + kx) * p.Cin + ci) * p.Cout + co0 + (c0 & 63));
+        // A lane owns one accumulator row (input channel) x 32 output channels; reducing straight from there makes
+        // every warp instruction touch 32 different rows (32 L2 transactions).  Transpose through shared memory so that
+        // eight lanes cover one row's 128 contiguous bytes: 4 transactions per instruction.
+        float* tb = tbuf + q * (32 * 33);
+        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          if (!(p.dbg & 2)) red_add_v4(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        for (int j = 0; j < 32; ++j) tb[lane * 33 + j] = v[j];
+        __syncwarp();
+        const int ci_w = ci - lane;   // input channel of this warp's row 0
+        float* dst = p.ws + (((int64_t)(ky * 3 + kx) * p.Cin + ci_w) * p.Cout + co0 + (c0 & 63));
+        const int rr = lane >> 3, cc = (lane & 7) * 4;
+#pragma unroll
+        for (int r0 = 0; r0 < 32; r0 += 4) {
+          const float* src = tb + (r0 + rr) * 33 + cc;
+          if (!(p.dbg & 2)) red_add_v4(dst + (int64_t)(r0 + rr) * p.Cout + cc, src[0], src[1], src[2], src[3]);
+        }
       }
     }
   }

@@ -210,11 +210,22 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tdy_hi, const __grid_constan
         }
         if (blk_ok[j]) {
           if (p.s_plain == 1) {
-            // 1x1 convolutions: the plain-operand channels are contiguous in the gradient -> 128-bit reductions
+            // 1x1 convolutions: the plain-operand channels are contiguous in the gradient -> 128-bit reductions, and the
+            // 32 x 32 chunk is transposed through (idle) pipeline memory so that eight lanes cover one row's 128 bytes
+            // (4 L2 transactions per warp instruction instead of 32)
+            float* tb = reinterpret_cast<float*>(smem) + q * (32 * 33);
+            __syncwarp();
 #pragma unroll
-            for (int jj = 0; jj < 32; jj += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g + c0 + jj), "f"(v[jj]), "f"(v[jj + 1]),
-                           "f"(v[jj + 2]), "f"(v[jj + 3]) : "memory");
+            for (int jj = 0; jj < 32; ++jj) tb[lane * 33 + jj] = v[jj];
+            __syncwarp();
+            float* g0 = g - (int64_t)lane * p.s_shift;   // row of lane 0 (the warp's 32 rows share block j)
+            const int rr = lane >> 3, cc = (lane & 7) * 4;
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 4) {
+              const float* src = tb + (r0 + rr) * 33 + cc;
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g0 + (int64_t)(r0 + rr) * p.s_shift + c0 + cc),
+                           "f"(src[0]), "f"(src[1]), "f"(src[2]), "f"(src[3]) : "memory");
+            }
           } else {
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) atomicAdd(g + (int64_t)(c0 + jj) * p.s_plain, v[jj]);
