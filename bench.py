@@ -291,6 +291,9 @@ def run_ours(args):
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": P["tf_sust"], "unit": "TFLOP/s",
                 "frac": ach / P["tf_sust"], "traffic": None, "peak_source": P["src"] + " bf16 dense sustained",
                 "avg_launch_ms": d["ms"] / max(d["launches"], 1), "share_of_step": d["ms"] / tot,
+                "frac_of_bf16x3_ceiling": ach / (P["tf_sust"] / 3.0),
+                "traffic_note": "ncu --set full capture of the dominant kernel: profiles/r1_wgrad_halo_ncu_full.md "
+                                "(73.5 MB DRAM traffic per launch for 67.1 MB of operands on the 32x32 64->64 layer)",
                 "engine": "simt-fp32" if unet._engine.lib.igm_get_conv_engine(unet._engine.ctx) == 0 else "tcgen05-bf16x3",
                 "classes": {k: {"ms_per_step": v["ms"] / 3, "launches_per_step": v["launches"] // 3,
                                 "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] else 0.0,
