@@ -83,8 +83,11 @@ struct Cfg {
   // BN = 64: tcgen05.mma at N = 64 issues at the N = 128 rate (measured 60 vs 64 cycles, tools/mma_rate_probe.cu),
   // so the hi and lo weight tiles (adjacent in smem) are fed as ONE N = 128 operand: columns [0,64) accumulate
   // a*w_hi, columns [64,128) a*w_lo, and two instructions (a_hi, a_lo) replace three; the epilogue adds the halves.
+  // BN = 128: the same stacking for the a_hi operand only -- a_hi x [w_hi ; w_lo] as ONE N = 256 instruction plus
+  // a_lo x w_hi at N = 128 cost the same 192 tensor cycles per k-step as three N = 128 instructions but read 20 KB
+  // instead of 24 KB of shared memory (the engine is shared-memory-bandwidth bound: operand reads + TMA fills > 128 B/clk).
   static constexpr bool STACKED = (BN == 64);
-  static constexpr int ACC_COLS = STACKED ? 2 * BN : BN;
+  static constexpr int ACC_COLS = 2 * BN;
   static constexpr int TMEM_COLS = 2 * ACC_COLS;   // two accumulator stages (power of two >= 32)
   static constexpr int STORE_STAGE_BYTES = 4 * (4096 + 2048 + 2048);   // per epilogue warp: fp32 | bf16 hi | bf16 lo tiles
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -171,6 +174,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
       // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major A/B,
       // N>>3 at bits 17-22, M>>4 at bits 24-28
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C::ACC_COLS >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t idesc_n = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       // One thread issues every MMA: descriptors are formed by adding 16-byte-unit offsets to four descriptors built
       // once (the 14-bit start-address field never carries out below 256 KB), so only a handful of scalar
       // instructions separate two tcgen05.mma (the issue loop, not the tensor pipe, was the bottleneck otherwise).
@@ -202,9 +206,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
               umma_bf16(d_tmem, dal, dbh, idesc, accum);   // [a_lo*w_hi | a_lo*w_lo]
               umma_bf16(d_tmem, dah, dbh, idesc, 1u);      // [a_hi*w_hi | a_hi*w_lo]
             } else {
-              umma_bf16(d_tmem, dal, dbh, idesc, accum);   // small terms first
-              umma_bf16(d_tmem, dah, dbl, idesc, 1u);
-              umma_bf16(d_tmem, dah, dbh, idesc, 1u);
+              umma_bf16(d_tmem, dah, dbh, idesc, accum);     // [a_hi*w_hi | a_hi*w_lo]   (N = 2 BN)
+              umma_bf16(d_tmem, dal, dbh, idesc_n, 1u);      //  a_lo*w_hi into the first half
             }
             accum = 1u;
           }
@@ -245,8 +248,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
         tmem_ld_32x32(t_base + (uint32_t)c0, v);
-        if (C::STACKED) {
-          float w[32];
+        {
+          float w[32];   // second accumulator half (products with w_lo)
           tmem_ld_32x32(t_base + (uint32_t)(BN + c0), w);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += w[j];
