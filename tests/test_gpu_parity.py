@@ -216,3 +216,35 @@ def test_ddpm_lightning_surface():
     assert out.fake_image is None and out.others["diffusion"].shape == imgs.shape
     fake = d.diffusion_model.sample(2)
     assert fake.shape == (2, 3, 16, 16) and torch.isfinite(fake).all()
+
+
+@pytest.mark.parametrize("case,B", [("tiny", 3), ("cifar10", 5)])
+def test_odd_batch_loss_gradients_and_sampler(case, B):
+    """Batches that do not fill the tile / box granularities (two 8x8 images per MMA tile, image pairs per TMA box,
+    per-image pixel tiles of the halo weight-gradient kernel): loss, every gradient and a 2-step sampler chain.
+    L2 loss: the L1 gradient sign(pred - noise) flips on rounding-level differences wherever a residual is ~0, which
+    moves every gradient by O(1/sqrt(#elements)) and says nothing about the kernels."""
+    dim, ch, mults, H, W, _, T = CASES[case]
+    spec = O.UnetSpec(dim, ch, mults)
+    params = O.init_params(spec, seed=7)
+    unet = igm_b200.Unet(dim=dim, channels=ch, dim_mults=mults)
+    unet.load_state_dict(params)
+    gd = igm_b200.GaussianDiffusion(unet, image_size=(H, W), channels=ch, timesteps=T, loss_type="l2").cuda()
+    g = torch.Generator().manual_seed(4321)
+    x = (torch.randn(B, ch, H, W, generator=g) * 0.5).clamp(-1, 1)
+    t = torch.randint(0, T, (B,), generator=g)
+    noise = torch.randn(B, ch, H, W, generator=g)
+    step_noise = torch.randn(2, B, ch, H, W, generator=g)
+    buf = O.diffusion_buffers(T)
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    ref_loss = O.p_losses(p, spec, buf, x, t, noise, "l2")
+    ref_grads = torch.autograd.grad(ref_loss, list(p.values()))
+    loss = gd.p_losses(x.cuda(), t.cuda(), noise.cuda())
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= REL_TOL * abs(ref_loss.item())
+    for (name, prm), rg in zip(gd.denoise_fn.named_parameters(), ref_grads):
+        assert_close(prm.grad, rg, f"{case} B={B} grad {name}")
+    img = gd._run_sampler(noise.clone().cuda(), 500, 2, noise=step_noise.cuda())
+    with torch.no_grad():
+        ref = O.p_sample_loop(params, spec, buf, noise.clone(), step_noise, t_start=500, n_steps=2)
+    assert_close(img.cpu(), ref, f"{case} B={B} sampler")
