@@ -30,9 +30,16 @@ CASES = {
 }
 
 
+# Input seed per case.  The L1 loss gradient is sign(noise - pred): an element whose residual is at rounding level
+# flips its sign between two correct fp32 implementations and moves EVERY gradient by O(1/sqrt(#elements)).
+# Seed 1234 leaves a residual of 8.9e-6 in the one-image celeba64 case, so that case uses a seed whose smallest
+# |noise - pred| is 6.0e-4 (tiny 7.7e-4, mnist_like 2.8e-4, cifar10 4.5e-4); the GPU test asserts the margin.
+SEEDS = {"celeba64": 2000}
+
+
 def inputs(case):
     dim, ch, mults, H, W, B, T = CASES[case]
-    g = torch.Generator().manual_seed(1234)
+    g = torch.Generator().manual_seed(SEEDS.get(case, 1234))
     x = (torch.randn(B, ch, H, W, generator=g) * 0.5).clamp(-1, 1)
     t = torch.randint(0, T, (B,), generator=g)
     noise = torch.randn(B, ch, H, W, generator=g)
@@ -42,7 +49,10 @@ def inputs(case):
 
 def main():
     ref = ref_loader.load("ddpm")
+    only = sys.argv[1:]
     for case, (dim, ch, mults, H, W, B, T) in CASES.items():
+        if only and case not in only:
+            continue
         spec = O.UnetSpec(dim, ch, mults)
         params = O.init_params(spec, seed=7)
         unet = ref.Unet(dim=dim, channels=ch, dim_mults=mults)
