@@ -81,6 +81,7 @@ struct Act {
 };
 
 struct ConvL {
+  int dyb = 0;   // slot of the dY staging ring this layer's gradient is staged in
   int pw = -1, pb = -1;   // parameter indices
   int Cin = 0, Cout = 0, K = 1;
   bool convT = false;
@@ -215,7 +216,17 @@ struct igm_ctx {
   float* attn_ws = nullptr;   // per-chunk partials of the linear-attention kernels
   float *ws_group = nullptr, *ws_chan = nullptr, *ws_ln = nullptr;
   float *scrA = nullptr, *scrB = nullptr, *scrC = nullptr;
-  __nv_bfloat16 *dy_hi = nullptr, *dy_lo = nullptr;         // bf16x2 staging of an output gradient
+  // bf16x2 staging of an output gradient: a small ring, each conv layer owns one slot (ConvL::dyb, assigned in backward
+  // order) so that a weight-gradient GEMM on the side stream can still read slot k while the main stream stages the next
+  // layer's gradient into slot k+1
+  static constexpr int kDyBufs = 3;
+  __nv_bfloat16 *dy_hi[kDyBufs] = {nullptr, nullptr, nullptr}, *dy_lo[kDyBufs] = {nullptr, nullptr, nullptr};
+  // side stream of the tensor-core weight-gradient kernels (IGM_WGRAD_STREAM=0: everything on the caller's stream)
+  bool side_on = true;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_wr = nullptr, ev_join = nullptr, ev_rd[kDyBufs] = {nullptr, nullptr, nullptr};
+  bool rd_pending[kDyBufs] = {false, false, false};
+  bool side_dirty = false;
   bool tc_available = false;
   HaloFinJob* fin_dev = nullptr;      // device job table of the halo-wgrad finalize pass
   int* fin_cta_dev = nullptr;         // CTA -> job
@@ -568,8 +579,10 @@ struct PlanBuilder {
       c.d_pred = ar.alloc((int64_t)B * cfg.channels * HW0);
     }
     if (maxDy > 0) {
-      c.dy_hi = reinterpret_cast<__nv_bfloat16*>(ar.alloc((maxDy + 1) / 2));
-      c.dy_lo = reinterpret_cast<__nv_bfloat16*>(ar.alloc((maxDy + 1) / 2));
+      for (int k = 0; k < igm_ctx::kDyBufs; ++k) {
+        c.dy_hi[k] = reinterpret_cast<__nv_bfloat16*>(ar.alloc((maxDy + 1) / 2));
+        c.dy_lo[k] = reinterpret_cast<__nv_bfloat16*>(ar.alloc((maxDy + 1) / 2));
+      }
     }
   }
 };
@@ -582,6 +595,49 @@ struct Runner {
   LaunchCtx lc;
   int B;
   bool infer = false;   // no backward pass will read this forward's intermediates (sampler steps)
+
+  // ---- side stream of the tensor-core weight-gradient kernels -------------------------------------------------
+  // A weight gradient feeds nothing until the optimizer step, so it leaves the critical path: the kernel is enqueued on
+  // c.side behind an event that marks "dY slot staged", and the main stream only waits for it (ev_rd[slot]) when it is
+  // about to overwrite that slot of the staging ring, and once at the end of backward (ev_join).  Off while profiling
+  // (per-scope event timing wants kernels alone) and on the SIMT engine.
+  bool side_active() const { return c.side_on && c.side && tc_on() && !(c.prof.on); }
+  __nv_bfloat16* dyh(const ConvL& l) const { return c.dy_hi[l.dyb]; }
+  __nv_bfloat16* dyl(const ConvL& l) const { return c.dy_lo[l.dyb]; }
+  // call before any kernel that writes slot l.dyb of the staging ring
+  int before_dy_write(const ConvL& l) {
+    if (c.rd_pending[l.dyb]) {
+      IGM_CUDA(c.st, cudaStreamWaitEvent(lc.stream, c.ev_rd[l.dyb], 0));
+      c.rd_pending[l.dyb] = false;
+    }
+    return IGM_OK;
+  }
+  // launch context for a weight-gradient kernel of layer l (reads slot l.dyb, already staged on the main stream)
+  int wgrad_begin(const ConvL& l, LaunchCtx& out) {
+    out = lc;
+    if (!side_active()) return IGM_OK;
+    IGM_CUDA(c.st, cudaEventRecord(c.ev_wr, lc.stream));
+    IGM_CUDA(c.st, cudaStreamWaitEvent(c.side, c.ev_wr, 0));
+    out.stream = c.side;
+    return IGM_OK;
+  }
+  int wgrad_end(const ConvL& l, const LaunchCtx& used) {
+    if (used.stream == lc.stream) return IGM_OK;
+    IGM_CUDA(c.st, cudaEventRecord(c.ev_rd[l.dyb], c.side));
+    c.rd_pending[l.dyb] = true;
+    c.side_dirty = true;
+    return IGM_OK;
+  }
+  // everything the side stream was given is done before the main stream continues
+  int side_join() {
+    if (c.side_dirty) {
+      IGM_CUDA(c.st, cudaEventRecord(c.ev_join, c.side));
+      IGM_CUDA(c.st, cudaStreamWaitEvent(lc.stream, c.ev_join, 0));
+      c.side_dirty = false;
+      for (bool& b : c.rd_pending) b = false;
+    }
+    return IGM_OK;
+  }
 
   int64_t M(int H, int W) const { return (int64_t)B * H * W; }
   bool tc_on() const { return c.conv_engine == 1; }
@@ -634,7 +690,10 @@ struct Runner {
                  float* d0, int C0, float* d1, int C1, const float* add0, const float* add1,
                  bool dy_staged = false) {
     if (stride == 1 && use_tc(l.tc_b) && C0 % 32 == 0) {
-      if (!dy_staged) IGM_TRY(launch_split_bf16(lc, d_out, M(OH, OW), l.Cout, c.dy_hi, c.dy_lo, l.Cout, 0));
+      if (!dy_staged) {
+        IGM_TRY(before_dy_write(l));
+        IGM_TRY(launch_split_bf16(lc, d_out, M(OH, OW), l.Cout, dyh(l), dyl(l), l.Cout, 0));
+      }
       TcRun r;
       r.B = B; r.bias = nullptr; r.out0 = d0; r.out1 = d1; r.N0 = C0; r.add0 = add0; r.add1 = add1;
       r.kclass = K_CONV_DGRAD;
@@ -661,9 +720,15 @@ struct Runner {
     const Act* s1 = l.src1;
     if (stride == 1 && tc_on() && tcw_batch_ok(l.tc_w, B)) {
       // tensor-core path: X is already staged (forward), dY is staged by the caller or here
-      if (!dy_staged) IGM_TRY(launch_split_bf16(lc, d_out, M(OH, OW), l.Cout, c.dy_hi, c.dy_lo, l.Cout, 0));
-      if (c.halo_on && l.tc_wh.valid) IGM_TRY(launch_wgrad_halo(lc, l.tc_wh, B));   // folded into gw by wgrad_finalize()
-      else IGM_TRY(launch_wgrad_tc(lc, l.tc_w, B, gw));
+      if (!dy_staged) {
+        IGM_TRY(before_dy_write(l));
+        IGM_TRY(launch_split_bf16(lc, d_out, M(OH, OW), l.Cout, dyh(l), dyl(l), l.Cout, 0));
+      }
+      LaunchCtx wl;
+      IGM_TRY(wgrad_begin(l, wl));
+      if (c.halo_on && l.tc_wh.valid) IGM_TRY(launch_wgrad_halo(wl, l.tc_wh, B));   // folded into gw by wgrad_finalize()
+      else IGM_TRY(launch_wgrad_tc(wl, l.tc_w, B, gw));
+      IGM_TRY(wgrad_end(l, wl));
     } else if (!l.convT) {
       // Conv2d: P = d_out (pc = co), Q = input (qc = ci) gathered at oy*s - p + ky;  W[co][ci][tap]
       const Act* srcs[2] = {s0, s1};
@@ -695,11 +760,12 @@ struct Runner {
   // stage dY as bf16 hi/lo; when the layer has its own bias gradient the column sums ride along (sets bias_done)
   int stage_dy(const ConvL& l, const float* dY, int64_t m, bool& bias_done) {
     bias_done = false;
+    IGM_TRY(before_dy_write(l));
     if (l.pb >= 0 && !l.bias_in_norm && split_colsum_ok(l.Cout)) {
       bias_done = true;
-      return launch_split_bf16_colsum(lc, dY, m, l.Cout, c.dy_hi, c.dy_lo, c.Gp(l.pb));
+      return launch_split_bf16_colsum(lc, dY, m, l.Cout, dyh(l), dyl(l), c.Gp(l.pb));
     }
-    return launch_split_bf16(lc, dY, m, l.Cout, c.dy_hi, c.dy_lo, l.Cout, 0);
+    return launch_split_bf16(lc, dY, m, l.Cout, dyh(l), dyl(l), l.Cout, 0);
   }
 
   // Backward of a stride-1 conv: weight/bias gradients, then (if d0) the data gradient.  dY is staged
@@ -740,12 +806,13 @@ struct Runner {
     g.dy = tc_only ? nullptr : c.scrA; g.dgamma = c.Gp(b.gn_w); g.dbeta = c.Gp(b.gn_b);
     g.dtemb = dtemb; g.dtemb_stride = c.proj_total;
     g.dbias = c.Gp(b.conv.pb);
-    g.dy_hi = tc_on() ? c.dy_hi : nullptr; g.dy_lo = tc_on() ? c.dy_lo : nullptr;
+    if (tc_on()) IGM_TRY(before_dy_write(b.conv));
+    g.dy_hi = tc_on() ? dyh(b.conv) : nullptr; g.dy_lo = tc_on() ? dyl(b.conv) : nullptr;
     g.ws_group = c.ws_group; g.ws_chan = c.ws_chan;
     g.B = B; g.HW = H * W; g.C = b.conv.Cout;
     return launch_gn_backward(lc, g);
   }
-  bool dy_is_staged() const { return tc_on() && c.dy_hi != nullptr; }
+  bool dy_is_staged() const { return tc_on() && c.dy_hi[0] != nullptr; }
 
   int resnet_fwd(ResnetL& r) {
     const int H = r.H, W = r.W;
@@ -806,8 +873,9 @@ struct Runner {
     // to_qkv has no bias: when both of its backward convs run on the tensor cores they only read the bf16 hi/lo
     // staging copy of d(qkv), which the attention backward then writes directly (no fp32 tensor, no split pass)
     const bool direct = tc_on() && tcw_batch_ok(a.qkv.tc_w, B) && a.qkv.tc_b.valid && a.qkv.pb < 0;
+    if (direct) IGM_TRY(before_dy_write(a.qkv));
     IGM_TRY(launch_linattn_backward(lc, a.qkv_t, a.ctx, a.kstat, c.scrB, direct ? nullptr : c.scrC, B, H * W, c.attn_ws,
-                                    direct ? c.dy_hi : nullptr, direct ? c.dy_lo : nullptr));
+                                    direct ? dyh(a.qkv) : nullptr, direct ? dyl(a.qkv) : nullptr));
     IGM_TRY(conv_bwd(a.qkv, H, W, c.scrC, c.scrA, nullptr, nullptr, nullptr, direct));
     IGM_TRY(launch_ln_backward(lc, c.scrA, a.in->v, c.Pp(a.ln_g), d_out, dx, c.Gp(a.ln_g), c.Gp(a.ln_b), c.ws_ln, m, a.C));
     return IGM_OK;
@@ -840,7 +908,10 @@ struct Runner {
     if (tcw || tcb)   // stage dY once for both tensor-core kernels
       IGM_TRY(stage_dy(l, rs.out.g, M(rs.out.H, rs.out.W), bias_done));
     if (tcw) {
-      IGM_TRY(launch_wgrad_tc(lc, rs.tcw, B, c.Gp(l.pw)));
+      LaunchCtx wl;
+      IGM_TRY(wgrad_begin(l, wl));
+      IGM_TRY(launch_wgrad_tc(wl, rs.tcw, B, c.Gp(l.pw)));
+      IGM_TRY(wgrad_end(l, wl));
       if (l.pb >= 0 && !bias_done) IGM_TRY(launch_colsum(lc, rs.out.g, M(rs.out.H, rs.out.W), l.Cout, c.Gp(l.pb)));
     } else {
       IGM_TRY(conv_wgrad(l, rs.Hin, rs.Win, rs.out.g, rs.out.H, rs.out.W, 2, 1, false, bias_done));
@@ -929,6 +1000,7 @@ struct Runner {
     time_params(tp);
     IGM_TRY(launch_time_backward(lc, tp, c.proj_dev, c.n_proj, c.proj_total, B, c.t_emb, c.t_h1, c.t_temb, c.t_act,
                                  c.t_dproj, c.t_ws));
+    IGM_TRY(side_join());
     if (tc_on() && c.halo_on) IGM_TRY(launch_wgrad_halo_finalize(lc, c.fin_dev, c.fin_cta_dev, c.fin_n > 0 ? c.fin_tiles : 0, c.fin_elems));
     return IGM_OK;
   }
@@ -1004,6 +1076,20 @@ static void wire_plan(igm_ctx* c) {
   c->final_block.conv.src0 = cur;
 }
 
+// Slots of the dY staging ring, handed out round-robin in the order Runner::backward visits the convs, so that
+// consecutive layers of the backward pass never share a slot.
+static void assign_dy_slots(igm_ctx* c) {
+  int k = 0;
+  auto f = [&](ConvL& l) { l.dyb = (k++) % igm_ctx::kDyBufs; };
+  auto rn = [&](ResnetL& r) { f(r.b2.conv); if (r.has_res) f(r.res); f(r.b1.conv); };
+  auto at = [&](AttnL& a) { f(a.outc); f(a.qkv); };
+  auto stg = [&](Stage& s) { if (s.rs.present) f(s.rs.conv); at(s.attn); rn(s.r2); rn(s.r1); };
+  f(c->final_block.conv);
+  for (int j = (int)c->ups.size() - 1; j >= 0; --j) stg(c->ups[j]);
+  rn(c->mid2); at(c->mid_attn); rn(c->mid1);
+  for (int i = (int)c->downs.size() - 1; i >= 0; --i) stg(c->downs[i]);
+}
+
 // TMA descriptors of the tcgen05 engine for every eligible stride-1 conv (needs a live driver).
 // Operands are the producers' bf16 hi/lo staging copies of the wired source activations.
 static int plan_tc(igm_ctx* c) {
@@ -1017,13 +1103,13 @@ static int plan_tc(igm_ctx* c) {
       IGM_TRY(tc_plan(c->st, l.tc_f, l.Cin, l.Cout, l.H, l.W, c->cfg.max_batch, l.K, pad, s0->hi, s0->lo, l.wf_hi,
                       l.wf_lo, s0->C, s1 ? s1->hi : nullptr, s1 ? s1->lo : nullptr));
     if (l.tc_b_ok)
-      IGM_TRY(tc_plan(c->st, l.tc_b, l.Cout, l.Cin, l.H, l.W, c->cfg.max_batch, l.K, pad, c->dy_hi, c->dy_lo, l.wb_hi,
+      IGM_TRY(tc_plan(c->st, l.tc_b, l.Cout, l.Cin, l.H, l.W, c->cfg.max_batch, l.K, pad, c->dy_hi[l.dyb], c->dy_lo[l.dyb], l.wb_hi,
                       l.wb_lo));
     if (l.tc_w_ok && staged)
-      IGM_TRY(tcw_plan(c->st, l.tc_w, l.Cin, l.Cout, l.H, l.W, c->cfg.max_batch, l.K, pad, c->dy_hi, c->dy_lo, s0->hi,
+      IGM_TRY(tcw_plan(c->st, l.tc_w, l.Cin, l.Cout, l.H, l.W, c->cfg.max_batch, l.K, pad, c->dy_hi[l.dyb], c->dy_lo[l.dyb], s0->hi,
                        s0->lo, s0->C, s1 ? s1->hi : nullptr, s1 ? s1->lo : nullptr));
     if (l.tc_wh_ok && l.tc_w_ok && staged)
-      IGM_TRY(tcwh_plan(c->st, l.tc_wh, l.Cin, l.Cout, l.H, l.W, c->cfg.max_batch, c->dy_hi, c->dy_lo, s0->hi, s0->lo, s0->C,
+      IGM_TRY(tcwh_plan(c->st, l.tc_wh, l.Cin, l.Cout, l.H, l.W, c->cfg.max_batch, c->dy_hi[l.dyb], c->dy_lo[l.dyb], s0->hi, s0->lo, s0->C,
                         s1 ? s1->hi : nullptr, s1 ? s1->lo : nullptr, l.wg_ws));
     n_valid += (l.tc_f.valid ? 1 : 0) + (l.tc_b.valid ? 1 : 0) + (l.tc_w.valid ? 1 : 0);
     return IGM_OK;
@@ -1047,10 +1133,10 @@ static int plan_tc(igm_ctx* c) {
       IGM_TRY(tc_plan_strided(c->st, rs.tcf[0], C, C, rs.Hin, rs.Win, Bm, 3, 1, rs.in->hi, rs.in->lo, l.wf_hi, l.wf_lo));
       rs.n_tcf = 1;
       if (c->cfg.training) {
-        IGM_TRY(tc_plan_phases4(c->st, rs.tcb[0], C, C, rs.out.H, rs.out.W, Bm, 3, 1, c->dy_hi, c->dy_lo, l.wb_hi, l.wb_lo));
+        IGM_TRY(tc_plan_phases4(c->st, rs.tcb[0], C, C, rs.out.H, rs.out.W, Bm, 3, 1, c->dy_hi[l.dyb], c->dy_lo[l.dyb], l.wb_hi, l.wb_lo));
         rs.n_tcb = 1;
         // S = X (fine grid, ci), P = dY (coarse grid, co); OIHW: ci stride KK, co stride C*KK
-        IGM_TRY(tcw_plan_strided(c->st, rs.tcw, C, C, rs.out.H, rs.out.W, Bm, 3, 1, rs.in->hi, rs.in->lo, c->dy_hi, c->dy_lo,
+        IGM_TRY(tcw_plan_strided(c->st, rs.tcw, C, C, rs.out.H, rs.out.W, Bm, 3, 1, rs.in->hi, rs.in->lo, c->dy_hi[l.dyb], c->dy_lo[l.dyb],
                                  KK, (int64_t)C * KK));
       }
     } else {
@@ -1058,10 +1144,10 @@ static int plan_tc(igm_ctx* c) {
       IGM_TRY(tc_plan_phases4(c->st, rs.tcf[0], C, C, rs.Hin, rs.Win, Bm, 4, 1, rs.in->hi, rs.in->lo, l.wf_hi, l.wf_lo));
       rs.n_tcf = 1;
       if (c->cfg.training) {
-        IGM_TRY(tc_plan_strided(c->st, rs.tcb[0], C, C, rs.out.H, rs.out.W, Bm, 4, 1, c->dy_hi, c->dy_lo, l.wb_hi, l.wb_lo));
+        IGM_TRY(tc_plan_strided(c->st, rs.tcb[0], C, C, rs.out.H, rs.out.W, Bm, 4, 1, c->dy_hi[l.dyb], c->dy_lo[l.dyb], l.wb_hi, l.wb_lo));
         rs.n_tcb = 1;
         // S = dY (fine grid, co), P = X (coarse grid, ci); IOHW: co stride KK, ci stride C*KK
-        IGM_TRY(tcw_plan_strided(c->st, rs.tcw, C, C, rs.Hin, rs.Win, Bm, 4, 1, c->dy_hi, c->dy_lo, rs.in->hi, rs.in->lo,
+        IGM_TRY(tcw_plan_strided(c->st, rs.tcw, C, C, rs.Hin, rs.Win, Bm, 4, 1, c->dy_hi[l.dyb], c->dy_lo[l.dyb], rs.in->hi, rs.in->lo,
                                  KK, (int64_t)C * KK));
       }
     }
@@ -1167,6 +1253,7 @@ int igm_unet_create(igm_ctx** out, const igm_unet_cfg* cfg, int device) {
   int64_t floats2 = 0;
   build_plan(c, c->arena, &floats2);
   wire_plan(c);
+  assign_dy_slots(c);
   // tensor-core engine: on by default when the shapes allow it (IGM_CONV_ENGINE=0 forces the SIMT engine)
   if (const char* ps = getenv("IGM_PREFER_SHARED")) {
     if (ps[0] == '1') cudaDeviceSetCacheConfig(cudaFuncCachePreferShared);
@@ -1184,6 +1271,19 @@ int igm_unet_create(igm_ctx** out, const igm_unet_cfg* cfg, int device) {
     }
     c->conv_engine = c->tc_available ? 1 : 0;
   }
+  if (const char* ws = getenv("IGM_WGRAD_STREAM")) c->side_on = !(ws[0] == '0');
+  if (c->cfg.training && c->side_on) {
+    cudaError_t se = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+    if (se == cudaSuccess) se = cudaEventCreateWithFlags(&c->ev_wr, cudaEventDisableTiming);
+    if (se == cudaSuccess) se = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+    for (int k = 0; k < igm_ctx::kDyBufs && se == cudaSuccess; ++k)
+      se = cudaEventCreateWithFlags(&c->ev_rd[k], cudaEventDisableTiming);
+    if (se != cudaSuccess) {
+      set_error(st, IGM_ERR_CUDA, __FILE__, __LINE__, cudaGetErrorString(se));
+      igm_unet_destroy(c);
+      return st.code;
+    }
+  }
   *out = c;
   return IGM_OK;
 }
@@ -1192,6 +1292,10 @@ void igm_unet_destroy(igm_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+  if (c->ev_wr) cudaEventDestroy(c->ev_wr);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  for (cudaEvent_t e : c->ev_rd) if (e) cudaEventDestroy(e);
   c->prof.reset();
   for (cudaEvent_t e : c->prof.pool) cudaEventDestroy(e);
   if (c->arena) cudaFree(c->arena);
