@@ -324,7 +324,8 @@ def run_ours(args):
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * CH * H * W * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
-                    "api": "DDPM.training_step(pinned-host batch) + loss.backward() + FusedAdam.step()"},
+                    "api": "H2D of the pinned batch + DDPM.training_step (enqueues fwd+bwd, reads the loss back on a copy stream) "
+                           "+ loss.backward() + FusedAdam.step()"},
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": cpu,

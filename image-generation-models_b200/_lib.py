@@ -47,6 +47,7 @@ SYMBOLS = {
     "igm_ddpm_p_losses": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P]),
     "igm_ddpm_p_losses_backward": (C.c_int, [_P, _P, C.c_float, _P]),
     "igm_ddpm_sample_loop": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "igm_grad_axpy": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_int64, _P]),
     "igm_adam_step": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_int, C.c_float, _P]),
     "igm_debug_read_tap": (C.c_int64, [_P, C.c_char_p, _P, C.c_int64, _P]),

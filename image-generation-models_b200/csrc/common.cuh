@@ -306,6 +306,7 @@ int launch_sampler_update(const LaunchCtx& lc, const SamplerStepArgs& a);
 // t[b] = *t_scalar for all b; then (*t_scalar)--, (*step)++   (device-side loop state for graph replay)
 int launch_sampler_tick(const LaunchCtx& lc, int64_t* t_vec, int B, int* state /* [t, step] */);
 int launch_add(const LaunchCtx& lc, float* dst, const float* src, int64_t n);
+int launch_axpy(const LaunchCtx& lc, float* dst, const float* src, const float* alpha_dev, float scale, int64_t n);
 int launch_adam(const LaunchCtx& lc, float* p, const float* g, float* m, float* v, int64_t n, float lr,
                 float b1, float b2, float eps, int step, float grad_scale);
 // NHWC -> NCHW copy (debug taps, d_x)

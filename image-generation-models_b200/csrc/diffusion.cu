@@ -348,6 +348,33 @@ int launch_sampler_tick(const LaunchCtx& lc, int64_t* t_vec, int B, int* state) 
   return IGM_OK;
 }
 
+// dst += src * scale * (*alpha_dev if given): the deferred half of an eagerly computed backward pass
+__global__ void __launch_bounds__(256) axpy_kernel(float* __restrict__ dst, const float* __restrict__ src,
+                                                    const float* __restrict__ alpha_dev, float scale, int64_t n4, int64_t n) {
+  const float a = alpha_dev ? scale * __ldg(alpha_dev) : scale;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 s = __ldg(reinterpret_cast<const float4*>(src) + i);
+    float4 d = reinterpret_cast<float4*>(dst)[i];
+    d.x = fmaf(s.x, a, d.x); d.y = fmaf(s.y, a, d.y); d.z = fmaf(s.z, a, d.z); d.w = fmaf(s.w, a, d.w);
+    reinterpret_cast<float4*>(dst)[i] = d;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n - n4 * 4)) {
+    const int64_t i = n4 * 4 + threadIdx.x;
+    dst[i] = fmaf(src[i], a, dst[i]);
+  }
+}
+
+int launch_axpy(const LaunchCtx& lc, float* dst, const float* src, const float* alpha_dev, float scale, int64_t n) {
+  const int64_t n4 = n / 4;
+  ProfScope ps_(lc, K_ELEM, 2.0 * n, 12.0 * n);
+  int64_t blocks = cdiv64(n4 > 0 ? n4 : 1, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  axpy_kernel<<<(unsigned)blocks, 256, 0, lc.stream>>>(dst, src, alpha_dev, scale, n4, n);
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
 int launch_add(const LaunchCtx& lc, float* dst, const float* src, int64_t n) {
   const int64_t n4 = n / 4;
   ProfScope ps_(lc, K_ELEM, 1.0 * n, 12.0 * n);

@@ -1608,6 +1608,15 @@ int igm_adam_step(igm_ctx* c, float* params, const float* grads, float* exp_avg,
   return launch_adam(lc, params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale);
 }
 
+int igm_grad_axpy(igm_ctx* c, float* dst, const float* src, const float* alpha, float scale, int64_t n, void* stream) {
+  if (!c) return IGM_ERR_INVALID;
+  if (!dst || !src || n < 0) IGM_FAIL(c->st, IGM_ERR_INVALID, "bad axpy args");
+  if ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) IGM_FAIL(c->st, IGM_ERR_INVALID, "axpy arenas must be 16-byte aligned");
+  IGM_CUDA(c->st, cudaSetDevice(c->device));
+  LaunchCtx lc = c->lc(stream);
+  return launch_axpy(lc, dst, src, alpha, scale, n);
+}
+
 int64_t igm_debug_read_tap(igm_ctx* c, const char* name, float* dst, int64_t cap, void* stream) {
   if (!c || !name) return IGM_ERR_INVALID;
   auto it = c->taps.find(name);

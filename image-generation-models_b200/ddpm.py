@@ -23,7 +23,11 @@ import numpy as np
 import torch
 from torch import nn
 
+import os
+
 from . import _lib
+
+_EAGER_BWD = os.environ.get("IGM_EAGER_BWD", "1") != "0"
 
 try:  # the real Lightning base class when it is installed, a minimal stand-in otherwise
     from pytorch_lightning import LightningModule as _LightningModule  # type: ignore
@@ -243,6 +247,7 @@ class Unet(nn.Module):
                 q.grad = grad[off:off + n].view(p.shape)
                 mod._parameters[key] = q
         self._flat, self._flat_grad, self._layout = flat, grad, layout
+        self._pend, self._pend_gen = None, 0
         self._anchor = torch.zeros(1, device=dev, requires_grad=True)
         if self._engine is not None:
             self._engine.close()
@@ -266,6 +271,20 @@ class Unet(nn.Module):
                 p.grad = self._flat_grad[off:off + p.numel()].view(shape)
         if zero:
             self._flat_grad.zero_()
+
+    def _bind_grad_target(self, which: str):
+        """Point the engine's weight-gradient kernels at ``.grad``'s arena ("grad") or at the pending arena of an eager
+        backward ("pend").  A switch re-uploads the engine's pointer tables (synchronous, rare: a training loop stays
+        in one mode)."""
+        e = self._engine
+        if e.grad_target == which:
+            return
+        if which == "pend" and (self._pend is None or self._pend.device != self._flat.device or
+                                self._pend.numel() != self._flat.numel()):
+            self._pend = torch.zeros_like(self._flat)
+        arena = self._flat_grad if which == "grad" else self._pend
+        e.check(e.lib.igm_unet_bind_params(e.ctx, _ptr(self._flat), _ptr(arena)))
+        e.grad_target = which
 
     def mark_dirty(self):
         """Call after editing parameters through ``.data`` (which bypasses the version counter)."""
@@ -300,6 +319,7 @@ class Unet(nn.Module):
                 e.close()
                 raise RuntimeError("parameter layout of the module tree and of libigm_b200 disagree")
             e.check(e.lib.igm_unet_bind_params(e.ctx, _ptr(self._flat), _ptr(self._flat_grad)))
+            e.grad_target = "grad"
             self._engine = e
         if e.packed_version != self._flat._version:
             e.check(e.lib.igm_unet_pack_weights(e.ctx, _stream()))
@@ -367,6 +387,7 @@ class _UnetFn(torch.autograd.Function):
         unet = ctx.unet
         e = unet._engine
         unet.attach_grads()
+        unet._bind_grad_target("grad")
         d_out = _f32c(d_out)
         dx = torch.empty_like(d_out) if ctx.need_dx else None
         e.check(e.lib.igm_unet_backward(e.ctx, _ptr(d_out), _ptr(dx), _stream()))
@@ -415,6 +436,8 @@ class GaussianDiffusion(nn.Module):
         self.channels = channels
         self.image_size = image_size
         self.denoise_fn = denoise_fn
+        self.eager_backward = False   # True inside DDPM.training_step: see _PLossesFn
+        self._rb, self._rb_pending = None, False
         if betas is not None:
             betas = betas.detach().cpu().numpy() if isinstance(betas, torch.Tensor) else np.asarray(betas)
         else:
@@ -439,6 +462,31 @@ class GaussianDiffusion(nn.Module):
             self.register_buffer(name, torch.tensor(val, dtype=torch.float32))
         denoise_fn._timesteps = self.num_timesteps
         denoise_fn._loss_type = 1 if loss_type == "l1" else 2
+
+    # ---- loss read-back that does not queue behind the eager backward ----------------
+    def _start_loss_readback(self, loss: torch.Tensor):
+        """Copy the scalar loss to pinned host memory on a side stream as soon as the forward has produced it; a
+        ``loss.item()`` on the compute stream would wait for the backward kernels enqueued behind the forward."""
+        dev = loss.device
+        if self._rb is None or self._rb[0] != dev:
+            self._rb = (dev, torch.cuda.Stream(device=dev), torch.empty(1, dtype=torch.float32).pin_memory(),
+                        torch.cuda.Event(), torch.cuda.Event())
+        _, side, host, ready, done = self._rb
+        ready.record(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            host.copy_(loss.detach().reshape(1), non_blocking=True)
+            done.record(side)
+        loss.record_stream(side)
+        self._rb_pending = True
+
+    def loss_value(self, loss: torch.Tensor) -> float:
+        """``loss.item()`` of the most recent eager p_losses (4 bytes device->host per step either way)."""
+        if not self._rb_pending:
+            return loss.item()
+        self._rb_pending = False
+        self._rb[4].synchronize()
+        return float(self._rb[2][0])
 
     # ---- engine plumbing --------------------------------------------------------
     def _engine(self, B, H, W, device, training) -> _Engine:
@@ -562,7 +610,7 @@ class GaussianDiffusion(nn.Module):
         if noise is None:
             noise = torch.randn_like(x_start)
         if torch.is_grad_enabled():
-            return _PLossesFn.apply(self.denoise_fn._anchor, self, x_start, t, noise)
+            return _PLossesFn.apply(self.denoise_fn._anchor, self, x_start, t, noise, bool(self.eager_backward))
         return _p_losses_forward(self, x_start, t, noise, training=False)
 
     def forward(self, x, *args, **kwargs):
@@ -582,10 +630,36 @@ def _p_losses_forward(gd: GaussianDiffusion, x_start, t, noise, training):
 
 
 class _PLossesFn(torch.autograd.Function):
+    """Loss forward + backward.  ``eager`` (set by DDPM.training_step): the backward kernels (and the gradient
+    all-reduce) are enqueued right behind the forward, with d_loss = 1, into the pending arena ``unet._pend`` — so the
+    host's ``loss.item()`` read-back that the reference does between forward and backward (ddpm.py:499) no longer leaves
+    the GPU idle while Python walks back into autograd.  ``backward`` is then ``.grad += d_loss * pending``: same
+    accumulate semantics, and a ``zero_grad()`` between training_step and backward (Lightning's closure order) is safe."""
+
     @staticmethod
-    def forward(ctx, anchor, gd, x_start, t, noise):
+    def forward(ctx, anchor, gd, x_start, t, noise, eager):
         ctx.gd = gd
-        return _p_losses_forward(gd, x_start, t, noise, training=True)
+        ctx.eager = eager
+        if not eager:
+            return _p_losses_forward(gd, x_start, t, noise, training=True)
+        unet = gd.denoise_fn
+        x_start, noise = _f32c(x_start), _f32c(noise)
+        B, _, H, W = x_start.shape
+        e = gd._engine(B, H, W, x_start.device, True)
+        unet._bind_grad_target("pend")
+        loss = torch.empty((), dtype=torch.float32, device=x_start.device)
+        e.check(e.lib.igm_ddpm_p_losses(e.ctx, _ptr(x_start), _ptr(t.to(torch.int64).contiguous()), _ptr(noise),
+                                        _ptr(loss), B, _stream()))
+        gd._start_loss_readback(loss)   # D2H of the scalar on a copy stream, ahead of the backward kernels
+        unet._pend.zero_()
+        sync = _world() > 1 and getattr(unet, "ddp_sync", True)
+        e.check(e.lib.igm_ddpm_p_losses_backward(e.ctx, None, C.c_float(1.0 / _world() if sync else 1.0), _stream()))
+        if sync:
+            import torch.distributed as dist
+            dist.all_reduce(unet._pend, op=dist.ReduceOp.SUM)
+        unet._pend_gen += 1
+        ctx.gen = unet._pend_gen
+        return loss
 
     @staticmethod
     def backward(ctx, d_loss):
@@ -593,10 +667,18 @@ class _PLossesFn(torch.autograd.Function):
         e = unet._engine
         unet.attach_grads()
         d_loss = d_loss.to(torch.float32).contiguous()
+        if ctx.eager:
+            if ctx.gen != unet._pend_gen:
+                raise RuntimeError("the eagerly computed gradients of this loss were overwritten by a later "
+                                   "training_step; call backward() before the next one")
+            e.check(e.lib.igm_grad_axpy(e.ctx, _ptr(unet._flat_grad), _ptr(unet._pend), _ptr(d_loss), C.c_float(1.0),
+                                        unet._flat_grad.numel(), _stream()))
+            return None, None, None, None, None, None
+        unet._bind_grad_target("grad")
         scale = 1.0 / _world() if getattr(unet, "ddp_sync", True) else 1.0
         e.check(e.lib.igm_ddpm_p_losses_backward(e.ctx, _ptr(d_loss), C.c_float(scale), _stream()))
         _allreduce_grads(unet)
-        return None, None, None, None, None
+        return None, None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------
@@ -690,8 +772,13 @@ class DDPM(_LightningModule):
 
     def training_step(self, batch, batch_idx):
         imgs, _ = batch
-        loss = self.diffusion_model(imgs)
-        self.log("train_loss/loss", loss.item())
+        # forward AND backward kernels go out before the loss is read back (see _PLossesFn); IGM_EAGER_BWD=0 disables
+        self.diffusion_model.eager_backward = _EAGER_BWD
+        try:
+            loss = self.diffusion_model(imgs)
+        finally:
+            self.diffusion_model.eager_backward = False
+        self.log("train_loss/loss", self.diffusion_model.loss_value(loss))
         return loss
 
     def configure_optimizers(self):

@@ -135,6 +135,13 @@ int igm_adam_step(igm_ctx* ctx, float* params, const float* grads, float* exp_av
                   float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
                   int step, float grad_scale, void* stream);
 
+/* dst[i] += src[i] * scale * (alpha ? *alpha : 1) over n fp32 elements (both 16-byte aligned; alpha is a DEVICE scalar).
+ * Host use: DDPM.training_step (ddpm.py:495-500) enqueues forward AND backward before it reads the loss back
+ * (loss.item(), :499), with the gradients going to a pending arena; autograd's later loss.backward() — the point where
+ * the reference computes them — is then this one kernel: .grad += d_loss * pending. */
+int igm_grad_axpy(igm_ctx* ctx, float* dst, const float* src, const float* alpha, float scale, int64_t n,
+                  void* stream);
+
 /* ---- VQ-VAE quantiser ------------------------------------------------------- */
 /* VectorQuantizer.forward — src/models/vqvae.py:24-43.  z, quant: [N, D, h, w] fp32 NCHW (HW = h*w);
  * codebook: [K, D]; idx: [N*h*w] int64 = argmin_k ||z - e_k|| with the FIRST index on ties;

@@ -252,3 +252,53 @@ def test_odd_batch_loss_gradients_and_sampler(case, B):
     with torch.no_grad():
         ref = O.p_sample_loop(params, spec, buf, noise.clone(), step_noise, t_start=500, n_steps=2)
     assert_close(img.cpu(), ref, f"{case} B={B} sampler")
+
+
+def test_eager_training_step_equals_lazy_backward():
+    """DDPM.training_step enqueues the backward pass before it reads the loss back and parks the gradients in a pending
+    arena; loss.backward() adds d_loss * pending to .grad.  Same gradients as the lazy path, for Lightning's closure order
+    (training_step -> zero_grad -> backward), for a scaled loss, and accumulated over two steps; a stale loss raises."""
+    from oracle import ref_loader
+    torch.manual_seed(0)
+    d = igm_b200.DDPM(ref_loader.datamodule_cfg(3, 16, 16), hidden_dim=32, dim_mults=(1, 2), lr=1e-4, b1=0.9,
+                      b2=0.999, timesteps=50, loss_type="l2").cuda()
+    unet, gd = d.denoising_model, d.diffusion_model
+    opt = d.configure_optimizers()
+    imgs = (torch.randn(4, 3, 16, 16) * 0.5).clamp(-1, 1).cuda()
+
+    def lazy(scale):
+        torch.manual_seed(123)                      # same t / noise draws as the eager call below
+        opt.zero_grad()
+        loss = gd(imgs)
+        (scale * loss).backward()
+        return loss.item(), unet._flat_grad.clone()
+
+    def eager(scale):
+        torch.manual_seed(123)
+        unet._flat_grad.fill_(7.0)                  # stale content that Lightning's zero_grad() clears AFTER training_step
+        loss = d.training_step((imgs, None), 0)
+        assert unet._engine.grad_target == "pend"
+        assert d.logged["train_loss/loss"] == loss.item()     # read back on the copy stream, same 4 bytes
+        opt.zero_grad()
+        (scale * loss).backward()
+        return loss.item(), unet._flat_grad.clone()
+
+    for scale in (1.0, 0.25):
+        l0, g0 = lazy(scale)
+        l1, g1 = eager(scale)
+        assert l0 == l1
+        assert_close(g1, g0, f"eager vs lazy gradients, scale {scale}", 1e-5)
+    # accumulation over two micro-batches
+    opt.zero_grad()
+    torch.manual_seed(5); d.training_step((imgs, None), 0).backward()
+    torch.manual_seed(6); d.training_step((imgs, None), 1).backward()
+    acc = unet._flat_grad.clone()
+    opt.zero_grad()
+    torch.manual_seed(5); gd(imgs).backward()
+    torch.manual_seed(6); gd(imgs).backward()
+    assert_close(acc, unet._flat_grad, "eager accumulation", 1e-5)
+    # a loss whose pending gradients were overwritten must not silently use the newer ones
+    stale = d.training_step((imgs, None), 0)
+    d.training_step((imgs, None), 1)
+    with pytest.raises(RuntimeError, match="overwritten"):
+        stale.backward()
