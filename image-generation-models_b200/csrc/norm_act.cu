@@ -131,6 +131,106 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
   }
 }
 
+// ---- forward apply, fast path: C/4 a power of two -------------------------------------------------------------------
+// The generic kernel above was bound by instruction issue and by its prologue, not by HBM (ncu: 61 % issue-active,
+// barrier the top stall, DRAM 16 % busy): eight threads folded the HW/32 statistics slots serially in fp64 while 248
+// waited, index arithmetic used integer divisions, and Mish / the bf16 split carried range-handling code.  Here the
+// thread layout is shifts and masks, all four pixel loads of a thread are in flight before the statistics are touched,
+// warp g folds group g's slots with one load round and five shuffles (fp32 tree, fixed order; mean / variance arithmetic
+// in fp64 as before), Mish is ex2.approx + rcp.approx with a select, and the split packs two values per cvt.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mish_fast(float x) {
+  const float w = ex2_approx(x * 1.4426950408889634f);
+  const float n = w * (w + 2.f);
+  const float m = x * (n * rcp_approx(n + 2.f));
+  return x > 20.f ? x : m;        // softplus threshold (F.softplus, threshold = 20): tanh(x) == 1 in fp32 there
+}
+// (a, b) -> packed bf16 hi pair and packed bf16 lo pair (element a in the low half: lower address)
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - bh), "f"(a - ah));
+}
+
+constexpr int kGnIter = 4;   // float4 per thread
+
+__global__ void __launch_bounds__(256) gn_apply_fast_kernel(const float* __restrict__ y, const float* __restrict__ part,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ temb, int temb_stride,
+                                                            const float* __restrict__ res, float* __restrict__ out,
+                                                            float* __restrict__ stats, int HW, int C, int lgL,
+                                                            __nv_bfloat16* __restrict__ out_hi,
+                                                            __nv_bfloat16* __restrict__ out_lo, int nparts, double inv_count) {
+  __shared__ float s_mean[kGroups], s_rstd[kGroups];
+  const int tid = threadIdx.x, b = blockIdx.y;
+  const int c4 = tid & ((1 << lgL) - 1), pslot = tid >> lgL, ppi = 256 >> lgL;
+  const int group = c4 >> (lgL - 3);
+  const int c = c4 * 4;
+  // parameters and the time-embedding projection were written at least two kernels back: load them before the wait
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+  const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+  float4 te = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (temb) te = __ldg(reinterpret_cast<const float4*>(temb + (int64_t)b * temb_stride + c));
+  const int p0 = blockIdx.x * (ppi * kGnIter) + pslot;
+  const int64_t off0 = ((int64_t)b * HW + p0) * C + c;
+  const int64_t step = (int64_t)ppi * C;
+  pdl_wait();
+  float4 v[kGnIter], r[kGnIter];
+#pragma unroll
+  for (int i = 0; i < kGnIter; ++i) {
+    const bool ok = p0 + i * ppi < HW;
+    v[i] = ok ? __ldg(reinterpret_cast<const float4*>(y + off0 + i * step)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    r[i] = (ok && res) ? __ldg(reinterpret_cast<const float4*>(res + off0 + i * step)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  {
+    const int g = tid >> 5, lane = tid & 31;
+    float s = 0.f, ss = 0.f;
+    for (int k = lane; k < nparts; k += 32) {
+      const float2 o = __ldg(reinterpret_cast<const float2*>(part + (((int64_t)b * nparts + k) * kGroups + g) * 2));
+      s += o.x;
+      ss += o.y;
+    }
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    if (lane == 0) {
+      const double m = (double)s * inv_count;
+      double var = (double)ss * inv_count - m * m;
+      if (var < 0.0) var = 0.0;
+      const float mean = (float)m, rstd = rsqrtf((float)var + kGnEps);
+      s_mean[g] = mean;
+      s_rstd[g] = rstd;
+      if (blockIdx.x == 0 && stats) {
+        stats[((int64_t)b * kGroups + g) * 2 + 0] = mean;
+        stats[((int64_t)b * kGroups + g) * 2 + 1] = rstd;
+      }
+    }
+  }
+  __syncthreads();
+  const float mean = s_mean[group], rstd = s_rstd[group];
+  // (x - mean) * rstd * gamma + beta  ==  x * a + d
+  const float4 sa = make_float4(rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w);
+  const float4 sd = make_float4(be.x - mean * sa.x, be.y - mean * sa.y, be.z - mean * sa.z, be.w - mean * sa.w);
+#pragma unroll
+  for (int i = 0; i < kGnIter; ++i) {
+    if (p0 + i * ppi >= HW) break;
+    float4 o;
+    o.x = mish_fast(fmaf(v[i].x, sa.x, sd.x)) + te.x + r[i].x;
+    o.y = mish_fast(fmaf(v[i].y, sa.y, sd.y)) + te.y + r[i].y;
+    o.z = mish_fast(fmaf(v[i].z, sa.z, sd.z)) + te.z + r[i].z;
+    o.w = mish_fast(fmaf(v[i].w, sa.w, sd.w)) + te.w + r[i].w;
+    const int64_t off = off0 + i * step;
+    if (out) *reinterpret_cast<float4*>(out + off) = o;
+    if (out_hi) {
+      uint2 h, l;
+      split_pair(o.x, o.y, h.x, l.x);
+      split_pair(o.z, o.w, h.y, l.y);
+      *reinterpret_cast<uint2*>(out_hi + off) = h;
+      *reinterpret_cast<uint2*>(out_lo + off) = l;
+    }
+  }
+}
+
 // ---- backward, pass 1: per-chunk reductions ---------------------------------
 __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdArgs a, int nchunks, int kGnChunk) {
   __shared__ float sm[256][2];
@@ -799,6 +899,20 @@ int launch_gn_apply(const LaunchCtx& lc, const float* y, const float* part, cons
                     float* stats, int B, int HW, int C, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int nparts) {
   IGM_TRY(check_gn_shape(lc, C));
   if (nparts <= 0) nparts = cdiv(HW, igm::kGnChunk);   // partials written by launch_gn_partial
+  const int L = C >> 2;
+  static const bool fast_off = [] { const char* e = getenv("IGM_GN_FAST"); return e && e[0] == '0'; }();
+  if (!fast_off && (L & (L - 1)) == 0 && L >= 8 && L <= 256) {
+    int lgL = 3;
+    while ((1 << lgL) < L) ++lgL;
+    const int chunk = (256 >> lgL) * kGnIter;
+    ProfScope ps_(lc, K_NORM, 30.0 * B * HW * C, 4.0 * B * HW * C * (res ? 3 : 2));
+    cudaError_t le = launch_pdl(gn_apply_fast_kernel, dim3(cdiv(HW, chunk), B), dim3(256), 0, lc.stream, y, part, gamma, beta, temb,
+                                temb_stride, res, out, stats, HW, C, lgL, out_hi, out_lo, nparts,
+                                1.0 / ((double)HW * (C / kGroups)));
+    if (le != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le));
+    IGM_POST_LAUNCH(lc);
+    return IGM_OK;
+  }
   const int kGnChunk = gn_chunk(B, HW, C);
   const int nchunks = cdiv(HW, kGnChunk);
   ProfScope ps_(lc, K_NORM, 30.0 * B * HW * C, 4.0 * B * HW * C * (res ? 3 : 2));
