@@ -332,32 +332,40 @@ int launch_nhwc_to_nchw(const LaunchCtx& lc, const float* src, float* dst, int B
 // With w = e^x:  tanh(log(1 + w)) = ((1+w)^2 - 1) / ((1+w)^2 + 1) = n / (n + 2),  n = w (w + 2),
 // so one exp and one division replace exp + log1p + tanh (the GroupNorm kernels were ALU-bound on
 // those three library calls).  Above the softplus threshold tanh(x) == 1 in fp32, so mish(x) = x.
+// Branch-free: ex2.approx / rcp.approx (~2 ulp, far inside the 1e-3 parity budget) and a select; for x <= 20 the
+// operands stay in the normal range (n + 2 in [2, 2.4e17]), so no range handling is needed.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mish_f(float x) {
-  if (x > 20.f) return x;
-  const float w = __expf(x);   // ex2.approx: ~2 ulp, far inside the 1e-3 parity budget
+  const float w = ex2_approx(x * 1.4426950408889634f);
   const float n = w * (w + 2.f);
-  return x * __fdividef(n, n + 2.f);
+  const float m = x * (n * rcp_approx(n + 2.f));
+  return x > 20.f ? x : m;
 }
 // d/dx mish = t + x * dt/dx,  t = n/(n+2),  dt/dx = 2 n' / (n+2)^2,  n' = 2 w (w + 1)
+// (kept with its early-out branch: the branch-free form lets ptxas interleave all 32 elements of the fused GroupNorm
+// backward and pushes it from 128 to 176 registers, one resident CTA per SM instead of two)
 __device__ __forceinline__ float mish_grad_f(float x) {
   if (x > 20.f) return 1.f;
-  const float w = __expf(x);
+  const float w = ex2_approx(x * 1.4426950408889634f);
   const float n = w * (w + 2.f);
-  const float r = __fdividef(1.f, n + 2.f);
+  const float r = rcp_approx(n + 2.f);
   return n * r + x * (4.f * w * (w + 1.f)) * (r * r);
 }
 // bf16 hi/lo staging of four consecutive fp32 values (operands of the tcgen05 bf16x3 engine)
+// (a, b) -> packed bf16 hi pair and packed bf16 lo pair (element a in the low half: lower address); two values per cvt
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - bh), "f"(a - ah));
+}
 __device__ __forceinline__ void store_split4(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                              int64_t off, const float4& o) {
-  __align__(8) __nv_bfloat16 h[4], l[4];
-  const float x[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    h[j] = __float2bfloat16_rn(x[j]);
-    l[j] = __float2bfloat16_rn(x[j] - __bfloat162float(h[j]));
-  }
-  *reinterpret_cast<uint2*>(hi + off) = *reinterpret_cast<const uint2*>(h);
-  *reinterpret_cast<uint2*>(lo + off) = *reinterpret_cast<const uint2*>(l);
+  uint2 h, l;
+  split_pair(o.x, o.y, h.x, l.x);
+  split_pair(o.z, o.w, h.y, l.y);
+  *reinterpret_cast<uint2*>(hi + off) = h;
+  *reinterpret_cast<uint2*>(lo + off) = l;
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

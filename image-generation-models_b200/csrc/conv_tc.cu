@@ -313,12 +313,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
           if (want_hi) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              __align__(16) __nv_bfloat16 h[8], l[8];
+              __align__(16) uint32_t h[4], l[4];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                h[e] = __float2bfloat16_rn(v[8 * j + e]);
-                l[e] = __float2bfloat16_rn(v[8 * j + e] - __bfloat162float(h[e]));
-              }
+              for (int e = 0; e < 4; ++e) split_pair(v[8 * j + 2 * e], v[8 * j + 2 * e + 1], h[e], l[e]);
               const int off = lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
               *reinterpret_cast<uint4*>(st_h + off) = *reinterpret_cast<const uint4*>(h);
               *reinterpret_cast<uint4*>(st_l + off) = *reinterpret_cast<const uint4*>(l);
@@ -364,12 +361,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
             __nv_bfloat16* ol = p.lo0 + opix * p.N0 + n;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              __align__(16) __nv_bfloat16 h[8], l[8];
+              __align__(16) uint32_t h[4], l[4];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                h[e] = __float2bfloat16_rn(v[j + e]);
-                l[e] = __float2bfloat16_rn(v[j + e] - __bfloat162float(h[e]));
-              }
+              for (int e = 0; e < 4; ++e) split_pair(v[j + 2 * e], v[j + 2 * e + 1], h[e], l[e]);
               *reinterpret_cast<uint4*>(oh + j) = *reinterpret_cast<const uint4*>(h);
               *reinterpret_cast<uint4*>(ol + j) = *reinterpret_cast<const uint4*>(l);
             }
@@ -401,16 +395,7 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, int64_t M, int 
     const int64_t m = i / c4n;
     const int c = (int)(i - m * c4n) * 4;
     const float4 v = __ldg(reinterpret_cast<const float4*>(src + m * C + c));
-    const float x[4] = {v.x, v.y, v.z, v.w};
-    __nv_bfloat16 h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      h[j] = __float2bfloat16_rn(x[j]);
-      l[j] = __float2bfloat16_rn(x[j] - __bfloat162float(h[j]));
-    }
-    const int64_t o = m * cdst + coff + c;
-    *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(h);
-    *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(l);
+    store_split4(hi, lo, m * cdst + coff + c, v);
   }
 }
 
@@ -438,15 +423,7 @@ __global__ void __launch_bounds__(256) split_colsum_kernel(const float* __restri
       if (m >= M) break;
       const int64_t o = m * C + c4 * 4;
       acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
-      const float x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-      __align__(8) __nv_bfloat16 h[4], l[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        h[j] = __float2bfloat16_rn(x[j]);
-        l[j] = __float2bfloat16_rn(x[j] - __bfloat162float(h[j]));
-      }
-      *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(h);
-      *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(l);
+      store_split4(hi, lo, o, v[u]);
     }
   }
   red[threadIdx.x] = acc;

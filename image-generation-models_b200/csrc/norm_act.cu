@@ -20,12 +20,20 @@ struct GnLayout {
   int L, PPI, c4, pslot, cpg, lpg, group;
   __device__ GnLayout(int C) {
     L = C >> 2;
-    PPI = 256 / L;
-    c4 = threadIdx.x % L;
-    pslot = threadIdx.x / L;
-    cpg = C / kGroups;
+    cpg = C >> 3;      // kGroups == 8
     lpg = cpg >> 2;
-    group = c4 / lpg;
+    if ((L & (L - 1)) == 0) {   // power of two (every width of the reference's configs): shifts, no integer division
+      const int lg = 31 - __clz(L);
+      PPI = 256 >> lg;
+      c4 = threadIdx.x & (L - 1);
+      pslot = threadIdx.x >> lg;
+      group = c4 >> (lg - 3);
+    } else {
+      PPI = 256 / L;
+      c4 = threadIdx.x % L;
+      pslot = threadIdx.x / L;
+      group = c4 / lpg;
+    }
   }
 };
 
@@ -138,21 +146,6 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
 // thread layout is shifts and masks, all four pixel loads of a thread are in flight before the statistics are touched,
 // warp g folds group g's slots with one load round and five shuffles (fp32 tree, fixed order; mean / variance arithmetic
 // in fp64 as before), Mish is ex2.approx + rcp.approx with a select, and the split packs two values per cvt.
-__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float mish_fast(float x) {
-  const float w = ex2_approx(x * 1.4426950408889634f);
-  const float n = w * (w + 2.f);
-  const float m = x * (n * rcp_approx(n + 2.f));
-  return x > 20.f ? x : m;        // softplus threshold (F.softplus, threshold = 20): tanh(x) == 1 in fp32 there
-}
-// (a, b) -> packed bf16 hi pair and packed bf16 lo pair (element a in the low half: lower address)
-__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
-  const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - bh), "f"(a - ah));
-}
-
 constexpr int kGnIter = 4;   // float4 per thread
 
 __global__ void __launch_bounds__(256) gn_apply_fast_kernel(const float* __restrict__ y, const float* __restrict__ part,
@@ -215,10 +208,10 @@ __global__ void __launch_bounds__(256) gn_apply_fast_kernel(const float* __restr
   for (int i = 0; i < kGnIter; ++i) {
     if (p0 + i * ppi >= HW) break;
     float4 o;
-    o.x = mish_fast(fmaf(v[i].x, sa.x, sd.x)) + te.x + r[i].x;
-    o.y = mish_fast(fmaf(v[i].y, sa.y, sd.y)) + te.y + r[i].y;
-    o.z = mish_fast(fmaf(v[i].z, sa.z, sd.z)) + te.z + r[i].z;
-    o.w = mish_fast(fmaf(v[i].w, sa.w, sd.w)) + te.w + r[i].w;
+    o.x = mish_f(fmaf(v[i].x, sa.x, sd.x)) + te.x + r[i].x;
+    o.y = mish_f(fmaf(v[i].y, sa.y, sd.y)) + te.y + r[i].y;
+    o.z = mish_f(fmaf(v[i].z, sa.z, sd.z)) + te.z + r[i].z;
+    o.w = mish_f(fmaf(v[i].w, sa.w, sd.w)) + te.w + r[i].w;
     const int64_t off = off0 + i * step;
     if (out) *reinterpret_cast<float4*>(out + off) = o;
     if (out_hi) {
