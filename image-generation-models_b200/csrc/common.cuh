@@ -244,7 +244,8 @@ int launch_ln_forward(const LaunchCtx& lc, const float* x, const float* g, const
                       int64_t M, int C, __nv_bfloat16* out_hi = nullptr, __nv_bfloat16* out_lo = nullptr);
 // dx = d_res + LN'(d_out)  (the Residual branch add is fused); dg/db accumulated via ws partials.
 int launch_ln_backward(const LaunchCtx& lc, const float* d_out, const float* x, const float* g,
-                       const float* d_res, float* dx, float* dg, float* db, float* ws, int64_t M, int C);
+                       const float* d_res, float* dx, float* dg, float* db, float* ws, int64_t M, int C, bool finalize = true);
+int launch_ln_param_finalize(const LaunchCtx& lc, const float* ws, int64_t M, int C, float* dg, float* db);
 int ln_backward_parts(int64_t M);   // CTAs (= partial rows of ws [parts][2][C]) the backward kernel uses
 
 // ---------------------------------------------------------------------------

@@ -1002,8 +1002,17 @@ int launch_ln_forward(const LaunchCtx& lc, const float* x, const float* g, const
 
 int ln_backward_parts(int64_t M) { return ln_grid(M); }
 
+// parameter gradients from the per-CTA partials of launch_ln_backward (split off so that it can leave the critical path)
+int launch_ln_param_finalize(const LaunchCtx& lc, const float* ws, int64_t M, int C, float* dg, float* db) {
+  const int grid = ln_grid(M);
+  ProfScope ps_(lc, K_NORM, 2.0 * grid * C, 8.0 * grid * C);
+  { cudaError_t le_ = launch_pdl(ln_param_finalize_kernel, dim3(cdiv(C, 32), cdiv(grid, 128)), dim3(32, 32), (size_t)0, lc.stream, ws, grid, C, dg, db); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
 int launch_ln_backward(const LaunchCtx& lc, const float* d_out, const float* x, const float* g,
-                       const float* d_res, float* dx, float* dg, float* db, float* ws, int64_t M, int C) {
+                       const float* d_res, float* dx, float* dg, float* db, float* ws, int64_t M, int C, bool finalize) {
   if (C % 4 != 0 || C > 1024) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "LayerNorm: C must be a multiple of 4, <= 1024");
   const int grid = ln_grid(M);
   ProfScope ps_(lc, K_NORM, 20.0 * M * C, 4.0 * M * C * (d_res ? 4 : 3));
@@ -1021,6 +1030,7 @@ int launch_ln_backward(const LaunchCtx& lc, const float* d_out, const float* x, 
     default:   { cudaError_t le_ = launch_pdl(ln_backward_kernel, dim3(grid), dim3(256), (size_t)(smem), lc.stream, d_out, x, g, d_res, dx, ws, M, C); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); } break;
   }
   IGM_POST_LAUNCH(lc);
+  if (!finalize) return IGM_OK;
   { cudaError_t le_ = launch_pdl(ln_param_finalize_kernel, dim3(cdiv(C, 32), cdiv(grid, 128)), dim3(32, 32), (size_t)0, lc.stream, ws, grid, C, dg, db); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
   return IGM_OK;

@@ -227,6 +227,8 @@ struct igm_ctx {
   cudaEvent_t ev_wr = nullptr, ev_join = nullptr, ev_rd[kDyBufs] = {nullptr, nullptr, nullptr};
   bool rd_pending[kDyBufs] = {false, false, false};
   bool side_dirty = false;
+  cudaEvent_t ev_ln = nullptr;   // side stream has folded the LayerNorm partials workspace (ws_ln may be overwritten)
+  bool ln_pending = false;
   bool tc_available = false;
   HaloFinJob* fin_dev = nullptr;      // device job table of the halo-wgrad finalize pass
   int* fin_cta_dev = nullptr;         // CTA -> job
@@ -613,7 +615,7 @@ struct Runner {
     return IGM_OK;
   }
   // launch context for a weight-gradient kernel of layer l (reads slot l.dyb, already staged on the main stream)
-  int wgrad_begin(const ConvL& l, LaunchCtx& out) {
+  int side_begin(LaunchCtx& out) {
     out = lc;
     if (!side_active()) return IGM_OK;
     IGM_CUDA(c.st, cudaEventRecord(c.ev_wr, lc.stream));
@@ -621,6 +623,7 @@ struct Runner {
     out.stream = c.side;
     return IGM_OK;
   }
+  int wgrad_begin(const ConvL& l, LaunchCtx& out) { (void)l; return side_begin(out); }
   int wgrad_end(const ConvL& l, const LaunchCtx& used) {
     if (used.stream == lc.stream) return IGM_OK;
     IGM_CUDA(c.st, cudaEventRecord(c.ev_rd[l.dyb], c.side));
@@ -634,6 +637,7 @@ struct Runner {
       IGM_CUDA(c.st, cudaEventRecord(c.ev_join, c.side));
       IGM_CUDA(c.st, cudaStreamWaitEvent(lc.stream, c.ev_join, 0));
       c.side_dirty = false;
+      c.ln_pending = false;
       for (bool& b : c.rd_pending) b = false;
     }
     return IGM_OK;
@@ -877,7 +881,21 @@ struct Runner {
     IGM_TRY(launch_linattn_backward(lc, a.qkv_t, a.ctx, a.kstat, c.scrB, direct ? nullptr : c.scrC, B, H * W, c.attn_ws,
                                     direct ? dyh(a.qkv) : nullptr, direct ? dyl(a.qkv) : nullptr));
     IGM_TRY(conv_bwd(a.qkv, H, W, c.scrC, c.scrA, nullptr, nullptr, nullptr, direct));
-    IGM_TRY(launch_ln_backward(lc, c.scrA, a.in->v, c.Pp(a.ln_g), d_out, dx, c.Gp(a.ln_g), c.Gp(a.ln_b), c.ws_ln, m, a.C));
+    if (!side_active())
+      return launch_ln_backward(lc, c.scrA, a.in->v, c.Pp(a.ln_g), d_out, dx, c.Gp(a.ln_g), c.Gp(a.ln_b), c.ws_ln, m, a.C);
+    // the fold of the per-CTA partials into d(gamma), d(beta) feeds nothing downstream: side stream; the next LayerNorm
+    // backward waits for it before it overwrites the partials workspace
+    if (c.ln_pending) {
+      IGM_CUDA(c.st, cudaStreamWaitEvent(lc.stream, c.ev_ln, 0));
+      c.ln_pending = false;
+    }
+    IGM_TRY(launch_ln_backward(lc, c.scrA, a.in->v, c.Pp(a.ln_g), d_out, dx, c.Gp(a.ln_g), c.Gp(a.ln_b), c.ws_ln, m, a.C, false));
+    LaunchCtx sl;
+    IGM_TRY(side_begin(sl));
+    IGM_TRY(launch_ln_param_finalize(sl, c.ws_ln, m, a.C, c.Gp(a.ln_g), c.Gp(a.ln_b)));
+    IGM_CUDA(c.st, cudaEventRecord(c.ev_ln, c.side));
+    c.ln_pending = true;
+    c.side_dirty = true;
     return IGM_OK;
   }
 
@@ -963,8 +981,11 @@ struct Runner {
       w.Q = c.final_act.v; w.QC = c.final_conv.Cin; w.QH = H0; w.QW = W0;
       w.B = B; w.grad = c.Gp(c.final_conv.pw);
       w.sq = 1; w.sp = c.final_conv.Cin;
-      IGM_TRY(launch_wgrad(lc, w));
-      IGM_TRY(launch_colsum(lc, d_pred, M(H0, W0), cfg.channels, c.Gp(c.final_conv.pb)));
+      LaunchCtx sl;                      // parameter gradients only: off the critical path
+      IGM_TRY(side_begin(sl));
+      IGM_TRY(launch_wgrad(sl, w));
+      IGM_TRY(launch_colsum(sl, d_pred, M(H0, W0), cfg.channels, c.Gp(c.final_conv.pb)));
+      if (sl.stream != lc.stream) c.side_dirty = true;
       ConvArgs a;
       a.in0 = d_pred; a.C0 = cfg.channels; a.B = B; a.IH = a.OH = H0; a.IW = a.OW = W0;
       a.N = a.N0 = c.final_conv.Cin; a.transposed = 1; a.kclass = K_CONV_DGRAD;
@@ -1276,6 +1297,7 @@ int igm_unet_create(igm_ctx** out, const igm_unet_cfg* cfg, int device) {
     cudaError_t se = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
     if (se == cudaSuccess) se = cudaEventCreateWithFlags(&c->ev_wr, cudaEventDisableTiming);
     if (se == cudaSuccess) se = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+    if (se == cudaSuccess) se = cudaEventCreateWithFlags(&c->ev_ln, cudaEventDisableTiming);
     for (int k = 0; k < igm_ctx::kDyBufs && se == cudaSuccess; ++k)
       se = cudaEventCreateWithFlags(&c->ev_rd[k], cudaEventDisableTiming);
     if (se != cudaSuccess) {
@@ -1295,6 +1317,7 @@ void igm_unet_destroy(igm_ctx* c) {
   if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
   if (c->ev_wr) cudaEventDestroy(c->ev_wr);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->ev_ln) cudaEventDestroy(c->ev_ln);
   for (cudaEvent_t e : c->ev_rd) if (e) cudaEventDestroy(e);
   c->prof.reset();
   for (cudaEvent_t e : c->prof.pool) cudaEventDestroy(e);
