@@ -30,12 +30,13 @@ __device__ __forceinline__ void outer4x4(const float (*Xs)[D], const float (*Ys)
     const float4 x = *reinterpret_cast<const float4*>(&Xs[nn][d0]);
     const float4 y = *reinterpret_cast<const float4*>(&Ys[nn][e0]);
     const float xv[4] = {x.x, x.y, x.z, x.w};
-    const float yv[4] = {y.x, y.y, y.z, y.w};
+    const float2 y01 = make_float2(y.x, y.y), y23 = make_float2(y.z, y.w);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       xsum[i] += xv[i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], yv[j], acc[i][j]);
+      const float2 xx = make_float2(xv[i], xv[i]);
+      ffma2(*reinterpret_cast<float2*>(&acc[i][0]), xx, y01);   // acc[i][0..1] += x_i * y_{0,1}
+      ffma2(*reinterpret_cast<float2*>(&acc[i][2]), xx, y23);
     }
   }
 }
@@ -203,21 +204,20 @@ __global__ void __launch_bounds__(256) linattn_out_kernel(const float* __restric
   load_tile(Xs, qkv + ((int64_t)b * N + n0) * QKV + h * D, QKV, rows, tid);
   // lane e keeps column e of the context in registers
   const int e = tid & 31, r = tid >> 5;
-  float col[D];
+  float2 col[D / 2];
 #pragma unroll
-  for (int dd = 0; dd < D; ++dd) col[dd] = __ldg(ctx + (int64_t)bh * D * D + dd * D + e);
+  for (int dd = 0; dd < D; dd += 2)
+    col[dd >> 1] = make_float2(__ldg(ctx + (int64_t)bh * D * D + dd * D + e), __ldg(ctx + (int64_t)bh * D * D + (dd + 1) * D + e));
   __syncthreads();
   for (int nn = r; nn < rows; nn += 8) {
-    float a0 = 0.f, a1 = 0.f;
+    float2 a2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int d4 = 0; d4 < D; d4 += 4) {
       const float4 x = *reinterpret_cast<const float4*>(&Xs[nn][d4]);
-      a0 = fmaf(col[d4], x.x, a0);
-      a1 = fmaf(col[d4 + 1], x.y, a1);
-      a0 = fmaf(col[d4 + 2], x.z, a0);
-      a1 = fmaf(col[d4 + 3], x.w, a1);
+      ffma2(a2, col[d4 >> 1], make_float2(x.x, x.y));
+      ffma2(a2, col[(d4 >> 1) + 1], make_float2(x.z, x.w));
     }
-    const float a = a0 + a1;
+    const float a = a2.x + a2.y;
     const int64_t o = ((int64_t)b * N + n0 + nn) * HD + h * D + e;
     if (out) out[o] = a;
     if (out_hi) {
@@ -327,46 +327,30 @@ __global__ void __launch_bounds__(256, 3) linattn_bwd_rows_kernel(const float* _
         d_lo[o] = __float2bfloat16_rn(val - __bfloat162float(hv));
       }
     };
-    float w[D];
+    float2 w[D / 2];
+    // 32-term dot product of the register-resident row/column w with one staged row (packed FMAs: two terms per issue)
+    auto dot = [&](const float* row) {
+      float2 a2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j4 = 0; j4 < D; j4 += 4) {
+        const float4 g4 = *reinterpret_cast<const float4*>(row + j4);
+        ffma2(a2, w[j4 >> 1], make_float2(g4.x, g4.y));
+        ffma2(a2, w[(j4 >> 1) + 1], make_float2(g4.z, g4.w));
+      }
+      return a2.x + a2.y;
+    };
     // dq = ctx[c][:] . dO[n][:]
 #pragma unroll
-    for (int j = 0; j < D; ++j) w[j] = ctxs[c][j];
-    for (int nn = r; nn < rows; nn += 8) {
-      float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-      for (int j4 = 0; j4 < D; j4 += 4) {
-        const float4 g4 = *reinterpret_cast<const float4*>(&Ys[nn][j4]);
-        a0 = fmaf(w[j4], g4.x, a0); a1 = fmaf(w[j4 + 1], g4.y, a1);
-        a0 = fmaf(w[j4 + 2], g4.z, a0); a1 = fmaf(w[j4 + 3], g4.w, a1);
-      }
-      emit(obase + (int64_t)nn * QKV + qcol + c, a0 + a1);
-    }
+    for (int j = 0; j < D; j += 2) w[j >> 1] = make_float2(ctxs[c][j], ctxs[c][j + 1]);
+    for (int nn = r; nn < rows; nn += 8) emit(obase + (int64_t)nn * QKV + qcol + c, dot(&Ys[nn][0]));
     // dk = p * (dctx[c][:] . v[n][:] - cdot)
 #pragma unroll
-    for (int j = 0; j < D; ++j) w[j] = dctxs[c][j];
-    for (int nn = r; nn < rows; nn += 8) {
-      float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-      for (int j4 = 0; j4 < D; j4 += 4) {
-        const float4 v4 = *reinterpret_cast<const float4*>(&Vs[nn][j4]);
-        a0 = fmaf(w[j4], v4.x, a0); a1 = fmaf(w[j4 + 1], v4.y, a1);
-        a0 = fmaf(w[j4 + 2], v4.z, a0); a1 = fmaf(w[j4 + 3], v4.w, a1);
-      }
-      emit(obase + (int64_t)nn * QKV + kcol + c, Xs[nn][c] * ((a0 + a1) - cdot));
-    }
+    for (int j = 0; j < D; j += 2) w[j >> 1] = make_float2(dctxs[c][j], dctxs[c][j + 1]);
+    for (int nn = r; nn < rows; nn += 8) emit(obase + (int64_t)nn * QKV + kcol + c, Xs[nn][c] * (dot(&Vs[nn][0]) - cdot));
     // dv = dctx[:][c] . p[n][:]
 #pragma unroll
-    for (int j = 0; j < D; ++j) w[j] = dctxs[j][c];
-    for (int nn = r; nn < rows; nn += 8) {
-      float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-      for (int j4 = 0; j4 < D; j4 += 4) {
-        const float4 p4 = *reinterpret_cast<const float4*>(&Xs[nn][j4]);
-        a0 = fmaf(w[j4], p4.x, a0); a1 = fmaf(w[j4 + 1], p4.y, a1);
-        a0 = fmaf(w[j4 + 2], p4.z, a0); a1 = fmaf(w[j4 + 3], p4.w, a1);
-      }
-      emit(obase + (int64_t)nn * QKV + vcol + c, a0 + a1);
-    }
+    for (int j = 0; j < D; j += 2) w[j >> 1] = make_float2(dctxs[j][c], dctxs[j + 1][c]);
+    for (int nn = r; nn < rows; nn += 8) emit(obase + (int64_t)nn * QKV + vcol + c, dot(&Xs[nn][0]));
     __syncthreads();
   }
 }

@@ -368,6 +368,15 @@ __device__ __forceinline__ void store_split4(__nv_bfloat16* __restrict__ hi, __n
   *reinterpret_cast<uint2*>(hi + off) = h;
   *reinterpret_cast<uint2*>(lo + off) = l;
 }
+// Packed fp32 FMA (Blackwell FFMA2): d.x += a.x * b.x, d.y += a.y * b.y in ONE issue slot.  A three-register FFMA issues
+// every other cycle per scheduler on sm_100; the packed form carries two FMAs per issue, so FMA-issue-bound loops
+// (linear attention) run up to twice as fast.  Each lane's rounding is that of a scalar fmaf.
+__device__ __forceinline__ void ffma2(float2& d, const float2& a, const float2& b) {
+  uint64_t dd = *reinterpret_cast<uint64_t*>(&d);
+  const uint64_t aa = *reinterpret_cast<const uint64_t*>(&a), bb = *reinterpret_cast<const uint64_t*>(&b);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+  d = *reinterpret_cast<float2*>(&dd);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
