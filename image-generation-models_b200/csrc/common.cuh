@@ -233,11 +233,15 @@ struct GnBwdArgs {
   float* dy; float* dgamma; float* dbeta; float* dtemb; int dtemb_stride;
   float* dbias;       // optional: += column sums of dy (gradient of the bias of the conv feeding this norm)
   __nv_bfloat16* dy_hi; __nv_bfloat16* dy_lo;   // optional bf16 hi/lo copy of dy (tensor-core wgrad / dgrad operand)
+  // optional by-products on d_out itself (fused kernel only, see gn_backward_is_fused): its bf16 hi/lo staging copy and
+  // its column sums -- the dY operand and the bias gradient of a ResnetBlock's res_conv, which shares d_out with block2
+  __nv_bfloat16* dout_hi = nullptr; __nv_bfloat16* dout_lo = nullptr; float* dout_colsum = nullptr;
   float* ws_group;    // [B][chunks][G][2]
   float* ws_chan;     // [B][chunks][C][3]
   int B, HW, C;
 };
 int launch_gn_backward(const LaunchCtx& lc, const GnBwdArgs& a);
+bool gn_backward_is_fused(const GnBwdArgs& a);   // will launch_gn_backward take the single-kernel path for this shape?
 
 // Channel LayerNorm of reference ddpm.py:85-95 (eps added to std).  x,out: [M, C]
 int launch_ln_forward(const LaunchCtx& lc, const float* x, const float* g, const float* b, float* out,

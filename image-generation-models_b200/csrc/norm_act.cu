@@ -387,6 +387,10 @@ __global__ void __launch_bounds__(256) gn_bwd_fused_kernel(const GnBwdArgs a, in
     nv[i] = __ldg(reinterpret_cast<const float4*>(a.y + base + i * step));
     dnv[i] = __ldg(reinterpret_cast<const float4*>(a.d_out + base + i * step));
   }
+  if (a.dout_hi) {
+#pragma unroll
+    for (int i = 0; i < GN_NV; ++i) store_split4(a.dout_hi, a.dout_lo, base + i * step, dnv[i]);
+  }
   float dgam[4] = {0.f, 0.f, 0.f, 0.f}, dbet[4] = {0.f, 0.f, 0.f, 0.f}, dte[4] = {0.f, 0.f, 0.f, 0.f};
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -475,6 +479,10 @@ __global__ void __launch_bounds__(256) gn_bwd_fused_kernel(const GnBwdArgs a, in
     atomicAdd(a.dbeta + c + 0, acc[1].x); atomicAdd(a.dbeta + c + 1, acc[1].y);
     atomicAdd(a.dbeta + c + 2, acc[1].z); atomicAdd(a.dbeta + c + 3, acc[1].w);
     if (a.dtemb) *reinterpret_cast<float4*>(a.dtemb + (int64_t)b * a.dtemb_stride + c) = acc[2];
+    if (a.dout_colsum) {
+      atomicAdd(a.dout_colsum + c + 0, acc[2].x); atomicAdd(a.dout_colsum + c + 1, acc[2].y);
+      atomicAdd(a.dout_colsum + c + 2, acc[2].z); atomicAdd(a.dout_colsum + c + 3, acc[2].w);
+    }
     if (a.dbias) {
       atomicAdd(a.dbias + c + 0, acc[3].x); atomicAdd(a.dbias + c + 1, acc[3].y);
       atomicAdd(a.dbias + c + 2, acc[3].z); atomicAdd(a.dbias + c + 3, acc[3].w);
@@ -932,11 +940,22 @@ static int gn_fused_cluster(const GnBwdArgs& a, int& nv) {
   return 0;
 }
 
+static bool gn_fused_disabled() {
+  static const bool off = [] { const char* e = getenv("IGM_GN_FUSED"); return e && e[0] == '0'; }();
+  return off;
+}
+
+bool gn_backward_is_fused(const GnBwdArgs& a) {
+  int nv = 0;
+  return !gn_fused_disabled() && a.C % 32 == 0 && a.C >= 32 && a.C <= 1024 && gn_fused_cluster(a, nv) > 0;
+}
+
 int launch_gn_backward(const LaunchCtx& lc, const GnBwdArgs& a) {
   IGM_TRY(check_gn_shape(lc, a.C));
-  static const bool fused_off = [] { const char* e = getenv("IGM_GN_FUSED"); return e && e[0] == '0'; }();
+  const bool fused_off = gn_fused_disabled();
   int nv = 0;
   const int cs = fused_off ? 0 : gn_fused_cluster(a, nv);
+  if (cs == 0 && (a.dout_hi || a.dout_colsum)) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "GroupNorm backward: d_out by-products need the fused kernel");
   if (cs > 0) {
     ProfScope ps_(lc, K_NORM, 80.0 * a.B * a.HW * a.C, 4.0 * a.B * a.HW * a.C * 3);
     cudaLaunchConfig_t cfg = {};

@@ -772,13 +772,16 @@ struct Runner {
     return launch_split_bf16(lc, dY, m, l.Cout, dyh(l), dyl(l), l.Cout, 0);
   }
 
+  // does conv_bwd(l, ..., d0) stage dY as bf16 hi/lo (tensor-core wgrad and/or dgrad)?
+  bool bwd_stages_dy(const ConvL& l, bool want_dgrad) const {
+    return tc_on() && (tcw_batch_ok(l.tc_w, B) || (want_dgrad && l.tc_b.valid && l.src0->C % 32 == 0));
+  }
   // Backward of a stride-1 conv: weight/bias gradients, then (if d0) the data gradient.  dY is staged
   // once as bf16 hi/lo (by the producer when `staged`, else here) and shared by wgrad and dgrad.
   int conv_bwd(const ConvL& l, int H, int W, const float* dY, float* d0, float* d1, const float* add0,
-               const float* add1, bool staged = false) {
+               const float* add1, bool staged = false, bool bias_done = false) {
     const int pad = (l.K - 1) / 2;
     const int C0 = l.src0->C, C1 = l.src1 ? l.src1->C : 0;
-    bool bias_done = false;
     if (!staged && tc_on() && (tcw_batch_ok(l.tc_w, B) || (d0 && l.tc_b.valid && C0 % 32 == 0))) {
       IGM_TRY(stage_dy(l, dY, M(H, W), bias_done));
       staged = true;
@@ -801,7 +804,11 @@ struct Runner {
     return IGM_OK;
   }
   // d_out: grad of block output; leaves dy (grad of conv output) in scrA (+ its bf16 staging copy)
-  int block_bwd_norm(BlockL& b, const float* d_out, int H, int W, float* dtemb) {
+  // also_stage (optional): a conv whose dY is this block's d_out (the ResnetBlock's res_conv).  When the fused kernel
+  // runs, it writes the bf16 hi/lo staging of d_out into that conv's ring slot and adds d_out's column sums to its bias
+  // gradient on the way, and *also_done is set: the separate split (+ column-sum) pass over d_out is not needed.
+  int block_bwd_norm(BlockL& b, const float* d_out, int H, int W, float* dtemb, const ConvL* also_stage = nullptr,
+                     bool* also_done = nullptr) {
     GnBwdArgs g;
     g.d_out = d_out; g.y = b.raw; g.stats = b.stats;
     g.gamma = c.Pp(b.gn_w); g.beta = c.Pp(b.gn_b);
@@ -814,6 +821,13 @@ struct Runner {
     g.dy_hi = tc_on() ? dyh(b.conv) : nullptr; g.dy_lo = tc_on() ? dyl(b.conv) : nullptr;
     g.ws_group = c.ws_group; g.ws_chan = c.ws_chan;
     g.B = B; g.HW = H * W; g.C = b.conv.Cout;
+    if (also_done) *also_done = false;
+    if (also_stage && also_done && tc_on() && also_stage->Cout == g.C && gn_backward_is_fused(g)) {
+      IGM_TRY(before_dy_write(*also_stage));
+      g.dout_hi = dyh(*also_stage); g.dout_lo = dyl(*also_stage);
+      if (also_stage->pb >= 0 && !also_stage->bias_in_norm) g.dout_colsum = c.Gp(also_stage->pb);
+      *also_done = true;
+    }
     return launch_gn_backward(lc, g);
   }
   bool dy_is_staged() const { return tc_on() && c.dy_hi[0] != nullptr; }
@@ -833,13 +847,15 @@ struct Runner {
   int resnet_bwd(ResnetL& r, float* d0, float* d1) {
     const int H = r.H, W = r.W;
     const float* d_out = r.out.g;
-    // block2
-    IGM_TRY(block_bwd_norm(r.b2, d_out, H, W, nullptr));
+    // block2 (its fused GroupNorm backward also stages d_out for res_conv, which shares it)
+    bool res_staged = false;
+    const bool res_wants = r.has_res && bwd_stages_dy(r.res, d0 != nullptr);
+    IGM_TRY(block_bwd_norm(r.b2, d_out, H, W, nullptr, res_wants ? &r.res : nullptr, &res_staged));
     IGM_TRY(conv_bwd(r.b2.conv, H, W, c.scrA, r.h1.g, nullptr, nullptr, nullptr, dy_is_staged()));
     // block1 (+ time-embedding add)
     if (r.has_res) {
       // res_conv first (its dY is d_out), then block1 accumulates on top of its data gradient
-      IGM_TRY(conv_bwd(r.res, H, W, d_out, d0, d1, nullptr, nullptr));
+      IGM_TRY(conv_bwd(r.res, H, W, d_out, d0, d1, nullptr, nullptr, res_staged, res_staged));
       IGM_TRY(block_bwd_norm(r.b1, r.h1.g, H, W, c.t_dproj + r.temb_off));
       IGM_TRY(conv_bwd(r.b1.conv, H, W, c.scrA, d0, d1, d0, d1, dy_is_staged()));
     } else {
