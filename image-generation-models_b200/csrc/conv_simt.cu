@@ -425,8 +425,79 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(const float* __restrict_
   }
 }
 
+// Same contract, row-band form.  The kernel above is bound by shared-memory weight traffic (one 128-bit weight load per
+// four FMAs, nothing reused across pixels).  Here a lane owns TWO output channels and keeps all KS*KS*C_in weight pairs
+// in registers; a CTA stages the zero-padded input rows of a band of R image rows in shared memory, and every input
+// value is then one broadcast shared-memory load feeding one packed FMA (FFMA2) per lane.  Out-of-image taps multiply
+// zeros, in the same tap order as above, so results are bit-identical.  grid (B * ceil(H / R), C_out / 64), 8 warps.
+template <int CI, int KS>
+__global__ void __launch_bounds__(256) conv_stem_rows_kernel(const float* __restrict__ X, const float* __restrict__ Wp,
+                                                             const float* __restrict__ bias, float* __restrict__ out,
+                                                             int B, int H, int W, int Cout, int R) {
+  constexpr int T = KS * KS, PAD = (KS - 1) / 2;
+  extern __shared__ float sx[];                  // [R + 2 PAD][(W + 2 PAD) * CI]
+  const int bands = (H + R - 1) / R;
+  const int b = blockIdx.x / bands, y0 = (blockIdx.x - b * bands) * R;
+  const int rows = min(R, H - y0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int co = blockIdx.y * 64 + lane * 2;
+  const bool cok = co < Cout;
+  float2 w[T * CI];
+#pragma unroll
+  for (int k = 0; k < T * CI; ++k)
+    w[k] = cok ? __ldg(reinterpret_cast<const float2*>(Wp + (int64_t)k * Cout + co)) : make_float2(0.f, 0.f);
+  float2 bv = make_float2(0.f, 0.f);
+  if (bias && cok) bv = __ldg(reinterpret_cast<const float2*>(bias + co));
+  const int PW = (W + 2 * PAD) * CI;
+  const int nrow = rows + 2 * PAD;
+  for (int i = threadIdx.x; i < nrow * PW; i += 256) {
+    const int rr = i / PW, cc = i - rr * PW;
+    const int px = cc / CI, ci = cc - px * CI;
+    const int iy = y0 - PAD + rr, ix = px - PAD;
+    sx[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(X + (((int64_t)b * H + iy) * W + ix) * CI + ci) : 0.f;
+  }
+  __syncthreads();
+  if (!cok) return;
+  // two pixels per iteration: two independent FMA chains per lane (each pixel keeps the tap order of the kernel above)
+  const int npx = rows * W;
+  for (int p = warp; p < npx; p += 16) {
+    const int pb = (p + 8 < npx) ? p + 8 : p;
+    const int ya = p / W, xa = p - ya * W;
+    const int yb = pb / W, xb = pb - yb * W;
+    const float* sa = sx + ya * PW + xa * CI;
+    const float* sb = sx + yb * PW + xb * CI;
+    float2 acca = bv, accb = bv;
+#pragma unroll
+    for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci) {
+          const float va = sa[ky * PW + kx * CI + ci], vb = sb[ky * PW + kx * CI + ci];
+          ffma2(acca, make_float2(va, va), w[(ky * KS + kx) * CI + ci]);
+          ffma2(accb, make_float2(vb, vb), w[(ky * KS + kx) * CI + ci]);
+        }
+    *reinterpret_cast<float2*>(out + (((int64_t)b * H + y0 + ya) * W + xa) * Cout + co) = acca;
+    if (pb != p) *reinterpret_cast<float2*>(out + (((int64_t)b * H + y0 + yb) * W + xb) * Cout + co) = accb;
+  }
+}
+
 template <int CI>
 static void launch_stem(const ConvArgs& a, dim3 grid, int per, cudaStream_t st) {
+  static const bool rows_off = [] { const char* e = getenv("IGM_STEM_ROWS"); return e && e[0] == '0'; }();
+  if (!rows_off && a.N % 2 == 0) {
+    const int R = a.IH < 4 ? a.IH : 4;
+    const int PADk = (a.KH - 1) / 2;
+    const size_t smem = (size_t)(R + 2 * PADk) * (a.IW + 2 * PADk) * CI * sizeof(float);
+    if (smem <= 40 * 1024) {
+      dim3 g2((unsigned)(a.B * cdiv(a.IH, R)), (unsigned)cdiv(a.N, 64));
+      if (a.KH == 3)
+        conv_stem_rows_kernel<CI, 3><<<g2, 256, smem, st>>>(a.in0, a.w, a.bias, a.out0, a.B, a.IH, a.IW, a.N, R);
+      else
+        conv_stem_rows_kernel<CI, 1><<<g2, 256, smem, st>>>(a.in0, a.w, a.bias, a.out0, a.B, a.IH, a.IW, a.N, R);
+      return;
+    }
+  }
   if (a.KH == 3)
     conv_stem_kernel<CI, 3><<<grid, 256, 0, st>>>(a.in0, a.w, a.bias, a.out0, a.B, a.IH, a.IW, a.N, per);
   else
