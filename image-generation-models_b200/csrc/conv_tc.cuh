@@ -144,7 +144,9 @@ int tcwh_plan(Status& st, TcWgradHalo& t, int Cin, int Cout, int H, int W, int B
               __nv_bfloat16* x1_lo, float* ws);
 int launch_wgrad_halo(const LaunchCtx& lc, const TcWgradHalo& t, int B);
 // tile_begin = first CTA of the layer; d_cta_job[cta] = layer index (a layer spans (Cin/32)*(Cout/32) CTAs)
-int launch_wgrad_halo_finalize(const LaunchCtx& lc, const HaloFinJob* d_jobs, const int* d_cta_job, int n_ctas, double elems);
+// (n_ctas, cta_base) select the CTA range: all layers (0 .. total) or one layer (its tile_begin, its CTA count)
+int launch_wgrad_halo_finalize(const LaunchCtx& lc, const HaloFinJob* d_jobs, const int* d_cta_job, int n_ctas, double elems,
+                               int cta_base = 0);
 
 // fp32 [M, C] -> bf16 hi / lo written at channel offset `coff` of rows with `cdst` channels
 int launch_split_bf16(const LaunchCtx& lc, const float* src, int64_t M, int C, __nv_bfloat16* hi,

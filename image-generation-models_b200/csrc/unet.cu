@@ -82,6 +82,7 @@ struct Act {
 
 struct ConvL {
   int dyb = 0;   // slot of the dY staging ring this layer's gradient is staged in
+  int fin_begin = 0, fin_ctas = 0;   // CTA range of this layer in the halo-wgrad finalize table (set at bind time)
   int pw = -1, pb = -1;   // parameter indices
   int Cin = 0, Cout = 0, K = 1;
   bool convT = false;
@@ -229,6 +230,7 @@ struct igm_ctx {
   bool side_dirty = false;
   cudaEvent_t ev_ln = nullptr;   // side stream has folded the LayerNorm partials workspace (ws_ln may be overwritten)
   bool ln_pending = false;
+  bool fin_per_layer = false;    // this backward folded the halo workspaces layer by layer (no finalize pass at the end)
   bool tc_available = false;
   HaloFinJob* fin_dev = nullptr;      // device job table of the halo-wgrad finalize pass
   int* fin_cta_dev = nullptr;         // CTA -> job
@@ -730,8 +732,13 @@ struct Runner {
       }
       LaunchCtx wl;
       IGM_TRY(wgrad_begin(l, wl));
-      if (c.halo_on && l.tc_wh.valid) IGM_TRY(launch_wgrad_halo(wl, l.tc_wh, B));   // folded into gw by wgrad_finalize()
-      else IGM_TRY(launch_wgrad_tc(wl, l.tc_w, B, gw));
+      if (c.halo_on && l.tc_wh.valid) {
+        IGM_TRY(launch_wgrad_halo(wl, l.tc_wh, B));   // workspace -> OIHW gradient by the finalize pass:
+        if (wl.stream != lc.stream) {                   // per layer, right behind it, when the side stream carries it
+          IGM_TRY(launch_wgrad_halo_finalize(wl, c.fin_dev, c.fin_cta_dev, l.fin_ctas, 9.0 * l.Cin * l.Cout, l.fin_begin));
+          c.fin_per_layer = true;
+        }
+      } else IGM_TRY(launch_wgrad_tc(wl, l.tc_w, B, gw));
       IGM_TRY(wgrad_end(l, wl));
     } else if (!l.convT) {
       // Conv2d: P = d_out (pc = co), Q = input (qc = ci) gathered at oy*s - p + ky;  W[co][ci][tap]
@@ -843,6 +850,15 @@ struct Runner {
     IGM_TRY(block_fwd(r.b2, H, W, nullptr, res, r.out));
     return IGM_OK;
   }
+  int maybe_time_backward(const ResnetL& r) {
+    if (time_after != &r || time_done) return IGM_OK;
+    LaunchCtx sl;
+    IGM_TRY(side_begin(sl));
+    IGM_TRY(time_backward(sl));
+    if (sl.stream != lc.stream) c.side_dirty = true;
+    time_done = true;
+    return IGM_OK;
+  }
   // d_out = r.out.g ; writes d_in0 / d_in1 unless null
   int resnet_bwd(ResnetL& r, float* d0, float* d1) {
     const int H = r.H, W = r.W;
@@ -857,9 +873,11 @@ struct Runner {
       // res_conv first (its dY is d_out), then block1 accumulates on top of its data gradient
       IGM_TRY(conv_bwd(r.res, H, W, d_out, d0, d1, nullptr, nullptr, res_staged, res_staged));
       IGM_TRY(block_bwd_norm(r.b1, r.h1.g, H, W, c.t_dproj + r.temb_off));
+      IGM_TRY(maybe_time_backward(r));
       IGM_TRY(conv_bwd(r.b1.conv, H, W, c.scrA, d0, d1, d0, d1, dy_is_staged()));
     } else {
       IGM_TRY(block_bwd_norm(r.b1, r.h1.g, H, W, c.t_dproj + r.temb_off));
+      IGM_TRY(maybe_time_backward(r));
       IGM_TRY(conv_bwd(r.b1.conv, H, W, c.scrA, d0, nullptr, d_out, nullptr, dy_is_staged()));
     }
     return IGM_OK;
@@ -986,9 +1004,22 @@ struct Runner {
   }
 
   // d_pred: NHWC [M, channels]; d_x_nhwc may be null
+  // time-embedding MLP backward: needs every block's d(temb), i.e. may start once block1 of the first ResnetBlock has run
+  // its GroupNorm backward; it then overlaps that block's (SIMT, few-channel) stem weight gradients on the side stream
+  const ResnetL* time_after = nullptr;
+  bool time_done = false;
+  int time_backward(const LaunchCtx& l) {
+    TimeMlpParams tp;
+    time_params(tp);
+    return launch_time_backward(l, tp, c.proj_dev, c.n_proj, c.proj_total, B, c.t_emb, c.t_h1, c.t_temb, c.t_act,
+                                c.t_dproj, c.t_ws);
+  }
+
   int backward(const float* d_pred, float* d_x_nhwc) {
     const igm_unet_cfg& cfg = c.cfg;
     const int nres = cfg.n_mults;
+    time_after = side_active() ? &c.downs[0].r1 : nullptr;
+    time_done = false;
     const int H0 = cfg.height, W0 = cfg.width;
     // final 1x1: W[c][k]
     {
@@ -1033,12 +1064,13 @@ struct Runner {
       IGM_TRY(resnet_bwd(s.r2, s.r1.out.g, nullptr));
       IGM_TRY(resnet_bwd(s.r1, i > 0 ? s.r1.in0->g : d_x_nhwc, nullptr));
     }
-    TimeMlpParams tp;
-    time_params(tp);
-    IGM_TRY(launch_time_backward(lc, tp, c.proj_dev, c.n_proj, c.proj_total, B, c.t_emb, c.t_h1, c.t_temb, c.t_act,
-                                 c.t_dproj, c.t_ws));
+    if (!time_done) IGM_TRY(time_backward(lc));
+    time_done = false;
+    time_after = nullptr;
     IGM_TRY(side_join());
-    if (tc_on() && c.halo_on) IGM_TRY(launch_wgrad_halo_finalize(lc, c.fin_dev, c.fin_cta_dev, c.fin_n > 0 ? c.fin_tiles : 0, c.fin_elems));
+    const bool fin_done = c.fin_per_layer;   // every halo layer was folded right behind its wgrad on the side stream
+    c.fin_per_layer = false;
+    if (tc_on() && c.halo_on && !fin_done) IGM_TRY(launch_wgrad_halo_finalize(lc, c.fin_dev, c.fin_cta_dev, c.fin_n > 0 ? c.fin_tiles : 0, c.fin_elems));
     return IGM_OK;
   }
 };
@@ -1387,6 +1419,7 @@ int igm_unet_bind_params(igm_ctx* c, float* params, float* grads) {
       if (!l.tc_wh.valid) return IGM_OK;
       HaloFinJob j{l.wg_ws, c->Gp(l.pw), l.Cin, l.Cout, c->fin_tiles};
       const int n_ctas = (l.Cin / 32) * (l.Cout / 32);   // one CTA per 32 x 32 (ci, co) tile
+      l.fin_begin = c->fin_tiles; l.fin_ctas = n_ctas;
       c->fin_tiles += n_ctas;
       c->fin_elems += 9.0 * l.Cin * l.Cout;
       cta_job.insert(cta_job.end(), n_ctas, (int)jobs.size());

@@ -268,10 +268,11 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap ts_hi, const __grid_consta
 // grad[co][ci][tap] += ws[tap][ci][co]; ws = 0.   One CTA per 32(ci) x 32(co) tile of one layer (transposed
 // through shared memory so that both sides move whole 128-byte lines); CTA -> layer through a per-CTA table.
 __global__ void __launch_bounds__(1024) wgrad_halo_finalize_kernel(const HaloFinJob* __restrict__ jobs,
-                                                                   const int* __restrict__ cta_job) {
+                                                                   const int* __restrict__ cta_job, int cta_base) {
   __shared__ float tile[9][32][33];
-  const HaloFinJob j = jobs[cta_job[blockIdx.x]];
-  const int t = blockIdx.x - j.tile_begin;
+  const int cta = blockIdx.x + cta_base;   // a launch may cover the CTA range of a single layer
+  const HaloFinJob j = jobs[cta_job[cta]];
+  const int t = cta - j.tile_begin;
   const int tco = j.Cout / 32;
   const int ci0 = (t / tco) * 32, co0 = (t % tco) * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -435,10 +436,11 @@ int launch_wgrad_halo(const LaunchCtx& lc, const TcWgradHalo& t, int B) {
   return IGM_OK;
 }
 
-int launch_wgrad_halo_finalize(const LaunchCtx& lc, const HaloFinJob* d_jobs, const int* d_cta_job, int n_ctas, double elems) {
+int launch_wgrad_halo_finalize(const LaunchCtx& lc, const HaloFinJob* d_jobs, const int* d_cta_job, int n_ctas, double elems,
+                               int cta_base) {
   if (n_ctas <= 0) return IGM_OK;
   ProfScope ps_(lc, K_CONV_WGRAD, elems, 16.0 * elems);
-  wgrad_halo_finalize_kernel<<<n_ctas, 1024, 0, lc.stream>>>(d_jobs, d_cta_job);
+  wgrad_halo_finalize_kernel<<<n_ctas, 1024, 0, lc.stream>>>(d_jobs, d_cta_job, cta_base);
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }
