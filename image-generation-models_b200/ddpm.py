@@ -421,6 +421,30 @@ def _cosine_betas(timesteps: int, s: float = 0.008) -> np.ndarray:
     return np.clip(1 - f[1:] / f[:-1], a_min=0, a_max=0.999)
 
 
+def cosine_beta_schedule(timesteps, s=0.008):
+    """reference ddpm.py:281-291 (numpy float64)."""
+    return _cosine_betas(timesteps, s)
+
+
+def linear_beta_schedule(timesteps):
+    """reference ddpm.py:275-279 (torch float64); pass it as ``GaussianDiffusion(betas=...)``."""
+    scale = 1000 / timesteps
+    return torch.linspace(scale * 0.0001, scale * 0.02, timesteps, dtype=torch.float64)
+
+
+def extract(a, t, x_shape):
+    """reference ddpm.py:263-266."""
+    b, *_ = t.shape
+    return a.gather(-1, t).reshape(b, *((1,) * (len(x_shape) - 1)))
+
+
+def noise_like(shape, device, repeat=False):
+    """reference ddpm.py:268-273."""
+    if repeat:
+        return torch.randn((1, *shape[1:]), device=device).repeat(shape[0], *((1,) * (len(shape) - 1)))
+    return torch.randn(shape, device=device)
+
+
 _SCHED_FIELDS = ("sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod",
                  "sqrt_recipm1_alphas_cumprod", "posterior_log_variance_clipped", "posterior_mean_coef1",
                  "posterior_mean_coef2")

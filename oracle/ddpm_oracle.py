@@ -297,9 +297,16 @@ SCHEDULE_KEYS = (
 )
 
 
-def diffusion_buffers(timesteps: int = 1000) -> Dict[str, torch.Tensor]:
-    """The 12 fp32 schedule buffers of GaussianDiffusion.__init__ (ddpm.py:317-350)."""
-    betas = cosine_beta_schedule(timesteps)
+def linear_beta_schedule(timesteps: int) -> np.ndarray:
+    """ddpm.py:275-279 — torch.linspace(scale * 1e-4, scale * 0.02, T, dtype=float64), scale = 1000 / T."""
+    scale = 1000 / timesteps
+    return torch.linspace(scale * 0.0001, scale * 0.02, timesteps, dtype=torch.float64).numpy()
+
+
+def diffusion_buffers(timesteps: int = 1000, betas=None) -> Dict[str, torch.Tensor]:
+    """The 12 fp32 schedule buffers of GaussianDiffusion.__init__ (ddpm.py:317-350); ``betas`` overrides the
+    cosine default like the constructor's ``betas=`` argument (:303-310)."""
+    betas = cosine_beta_schedule(timesteps) if betas is None else np.asarray(betas, dtype=np.float64)
     alphas = 1.0 - betas
     ac = np.cumprod(alphas, axis=0)
     ac_prev = np.append(1.0, ac[:-1])

@@ -302,3 +302,49 @@ def test_eager_training_step_equals_lazy_backward():
     d.training_step((imgs, None), 1)
     with pytest.raises(RuntimeError, match="overwritten"):
         stale.backward()
+
+
+def test_linear_schedule_repeat_noise_and_interpolate():
+    """GaussianDiffusion(betas=linear_beta_schedule(T)), p_sample(repeat_noise=True) and interpolate (reference
+    ddpm.py:275-279, :268-273 with :390-397, :417-431) against the oracle; torch's CUDA generator is re-seeded to
+    reproduce the draws the mirror makes exactly where the reference makes them."""
+    case = "tiny"
+    dim, ch, mults, H, W, B, _ = CASES[case]
+    T = 100
+    spec = O.UnetSpec(dim, ch, mults)
+    params = O.init_params(spec, seed=7)
+    unet = igm_b200.Unet(dim=dim, channels=ch, dim_mults=mults)
+    unet.load_state_dict(params)
+    gd = igm_b200.GaussianDiffusion(unet, image_size=(H, W), channels=ch, timesteps=T, loss_type="l2",
+                                    betas=igm_b200.linear_beta_schedule(T)).cuda()
+    buf = O.diffusion_buffers(T, betas=O.linear_beta_schedule(T))
+    g = torch.Generator().manual_seed(99)
+    x1 = (torch.randn(B, ch, H, W, generator=g) * 0.5).clamp(-1, 1)
+    x2 = (torch.randn(B, ch, H, W, generator=g) * 0.5).clamp(-1, 1)
+    t = torch.randint(0, T, (B,), generator=g)
+    noise = torch.randn(B, ch, H, W, generator=g)
+    with torch.no_grad():
+        ref_loss = O.p_losses(params, spec, buf, x1, t, noise, "l2")
+        loss = gd.p_losses(x1.cuda(), t.cuda(), noise.cuda())
+    assert abs(loss.item() - ref_loss.item()) <= REL_TOL * abs(ref_loss.item())
+    # p_sample(repeat_noise=True): ONE [1, C, H, W] draw repeated over the batch
+    tt = torch.full((B,), 40, dtype=torch.long)
+    torch.manual_seed(77)
+    out = gd.p_sample(x1.cuda(), tt.cuda(), repeat_noise=True)
+    torch.manual_seed(77)
+    z = torch.randn((1, ch, H, W), device="cuda").cpu().repeat(B, 1, 1, 1)
+    with torch.no_grad():
+        ref = O.p_sample(params, spec, buf, x1, tt, z)
+    assert_close(out.cpu(), ref, "p_sample(repeat_noise=True)")
+    # interpolate at t = 1: q_sample both images at t = 1, mix, one reverse step at t = 0 (which adds no noise)
+    torch.manual_seed(78)
+    got = gd.interpolate(x1.cuda(), x2.cuda(), t=1, weight=0.3)
+    torch.manual_seed(78)
+    n1 = torch.randn_like(x1.cuda()).cpu()
+    n2 = torch.randn_like(x2.cuda()).cpu()
+    t1 = torch.full((B,), 1, dtype=torch.long)
+    mix = (1 - 0.3) * O.q_sample(buf, x1, t1, n1) + 0.3 * O.q_sample(buf, x2, t1, n2)
+    with torch.no_grad():
+        ref = O.p_sample(params, spec, buf, mix, torch.zeros(B, dtype=torch.long), torch.zeros_like(mix))
+    assert_close(got.cpu(), ref, "interpolate(t=1)")
+    assert got.shape == x1.shape and torch.isfinite(gd.interpolate(x1.cuda(), x2.cuda(), t=5)).all()

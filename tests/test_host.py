@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 import torch
 
@@ -86,3 +87,35 @@ def test_no_cpu_fallback():
     u = igm_b200.Unet(dim=32, channels=3, dim_mults=(1, 2))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         u(torch.zeros(1, 3, 16, 16), torch.zeros(1, dtype=torch.long))
+
+
+def test_schedule_helpers_and_betas_argument():
+    """linear_beta_schedule / cosine_beta_schedule / extract / noise_like (reference ddpm.py:263-291) and the
+    ``betas=`` constructor argument (:303-310): mirror == oracle everywhere, == live reference where it is mounted."""
+    T = 200
+    lin = igm_b200.linear_beta_schedule(T)
+    assert lin.dtype == torch.float64 and np.array_equal(lin.numpy(), O.linear_beta_schedule(T))
+    assert np.array_equal(igm_b200.cosine_beta_schedule(T), O.cosine_beta_schedule(T))
+    u = igm_b200.Unet(dim=32, channels=3, dim_mults=(1, 2))
+    gd = igm_b200.GaussianDiffusion(u, image_size=(16, 16), channels=3, timesteps=T, betas=lin)
+    buf = O.diffusion_buffers(T, betas=O.linear_beta_schedule(T))
+    assert gd.num_timesteps == T
+    for k in O.SCHEDULE_KEYS:
+        assert torch.equal(getattr(gd, k), buf[k]), k
+    a = torch.arange(10.0)
+    t = torch.tensor([3, 7])
+    assert torch.equal(igm_b200.extract(a, t, (2, 3, 4, 4)), torch.tensor([3.0, 7.0]).reshape(2, 1, 1, 1))
+    torch.manual_seed(3)
+    z = igm_b200.noise_like((4, 3, 8, 8), "cpu", repeat=True)
+    assert z.shape == (4, 3, 8, 8) and torch.equal(z[0], z[3])
+    if ref_loader.available():
+        ref = ref_loader.load("ddpm")
+        assert torch.equal(ref.linear_beta_schedule(T), lin)
+        assert np.array_equal(ref.cosine_beta_schedule(T), igm_b200.cosine_beta_schedule(T))
+        assert torch.equal(ref.extract(a, t, (2, 3, 4, 4)), igm_b200.extract(a, t, (2, 3, 4, 4)))
+        torch.manual_seed(3)
+        assert torch.equal(ref.noise_like((4, 3, 8, 8), "cpu", repeat=True), z)
+        rgd = ref.GaussianDiffusion(ref.Unet(dim=32, channels=3, dim_mults=(1, 2)), image_size=(16, 16), channels=3,
+                                    timesteps=T, betas=lin)
+        for k in O.SCHEDULE_KEYS:
+            assert torch.equal(getattr(rgd, k), getattr(gd, k)), k
