@@ -1,0 +1,29 @@
+"""CPU: the padded-linear tile -> pixel map planned for the halo-reuse forward conv (tools/halo_fprop_model.py) against
+torch's conv2d, including ragged bands (H not a multiple of BH) and the 28x28 / 8x8 geometries."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+_p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "halo_fprop_model.py")
+_s = importlib.util.spec_from_file_location("halo_fprop_model", _p)
+M = importlib.util.module_from_spec(_s)
+_s.loader.exec_module(M)
+
+
+@pytest.mark.parametrize("H,W,BH", [(8, 8, 3), (8, 8, 8), (16, 16, 7), (28, 28, 5), (32, 32, 7)])
+def test_padded_linear_conv_equals_conv2d(H, W, BH):
+    g = torch.Generator().manual_seed(H * 100 + BH)
+    x = torch.randn(2, 5, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(6, 5, 3, 3, generator=g, dtype=torch.float64)
+    ref = F.conv2d(x, w, padding=1).permute(0, 2, 3, 1).numpy()
+    got = M.conv3x3_halo(x.permute(0, 2, 3, 1).numpy(), w.numpy(), BH)
+    np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-12)
+
+
+def test_band_plan_numbers():
+    m, n, f, px = M.band_plan(32, 32, 7)
+    assert (m, n) == (238, 2) and abs(f - 0.875) < 1e-9 and px == 9 * 34 + 2 * 34
