@@ -1,5 +1,6 @@
 // Test-only entry point: one stride-1 convolution (or its data gradient) on either engine,
 // so the tcgen05 kernel can be parity-checked in isolation over many shapes.
+// engine 0 = fp32 SIMT, 1 = tcgen05 per-tap (conv_tc.cu), 2 = tcgen05 halo-reuse (conv_halo.cu, bring-up).
 #include "common.cuh"
 #include "conv_tc.cuh"
 
@@ -47,13 +48,23 @@ extern "C" int igm_debug_conv(int engine, int mode, const float* x, const float*
   IGM_CUDA(st, cudaMalloc(&ah, M * Kc * 2));
   IGM_CUDA(st, cudaMalloc(&al, M * Kc * 2));
   TcConv t;
-  rc = tc_plan(st, t, Kc, N, H, W, B, K, pad, ah, al, wh, wl);
+  TcConvHalo th;
+  if (engine == 2) {   // halo-reuse engine (conv_halo.cu), 3x3 only
+    if (K != 3 || !tch_eligible(Kc, N, H, W)) {
+      set_error(st, IGM_ERR_INVALID, __FILE__, __LINE__, "shape not eligible for the halo-reuse tcgen05 conv");
+      rc = IGM_ERR_INVALID;
+    } else {
+      rc = tch_plan(st, th, Kc, N, H, W, B, ah, al, wh, wl);
+    }
+  } else {
+    rc = tc_plan(st, t, Kc, N, H, W, B, K, pad, ah, al, wh, wl);
+  }
   if (rc == IGM_OK) rc = launch_pack_weight_tc(lc, w_oihw, wh, wl, KK, Kc, N, sk, sn, mode);
   if (rc == IGM_OK) rc = launch_split_bf16(lc, x, M, Kc, ah, al, Kc, 0);
   if (rc == IGM_OK) {
     TcRun r;
     r.B = B; r.bias = bias; r.out0 = out; r.N0 = N; r.add0 = add;
-    rc = launch_conv_tc(lc, t, r);
+    rc = engine == 2 ? launch_conv_halo(lc, th, r) : launch_conv_tc(lc, t, r);
   }
   cudaError_t e = cudaStreamSynchronize(lc.stream);
   if (rc == IGM_OK && e != cudaSuccess) {

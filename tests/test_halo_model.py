@@ -27,3 +27,19 @@ def test_padded_linear_conv_equals_conv2d(H, W, BH):
 def test_band_plan_numbers():
     m, n, f, px = M.band_plan(32, 32, 7)
     assert (m, n) == (238, 2) and abs(f - 0.875) < 1e-9 and px == 9 * 34 + 2 * 34
+
+
+@pytest.mark.parametrize("H,W", [(32, 32), (28, 28), (64, 64), (5, 32), (7, 40)])
+def test_kernel_decomposition_and_row_stores(H, W):
+    """csrc/conv_halo.cu's band / tile / warp decomposition and its clipped per-image-row stores: every output pixel
+    is stored exactly once, from the right accumulator row, junk rows (NaN in the model) never reach the output, and
+    the per-warp GroupNorm slots partition the valid pixels."""
+    g = torch.Generator().manual_seed(H * 1000 + W)
+    x = torch.randn(2, 4, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(3, 4, 3, 3, generator=g, dtype=torch.float64)
+    bias = torch.randn(3, generator=g, dtype=torch.float64)
+    ref = F.conv2d(x, w, bias, padding=1).permute(0, 2, 3, 1).numpy()
+    out, writes, slots = M.conv3x3_halo_kernel_model(x.permute(0, 2, 3, 1).numpy(), w.numpy(), bias.numpy())
+    assert (writes == 1).all()
+    np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(slots.sum(axis=1), ref.sum(axis=(1, 2, 3)), rtol=1e-10, atol=1e-10)

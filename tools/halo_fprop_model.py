@@ -62,6 +62,69 @@ def conv3x3_halo(x_nhwc, w_oihw, BH):
     return out
 
 
+def kernel_plan(W):
+    """BH of csrc/conv_halo.cu: two M = 128 tiles per band."""
+    return 256 // (W + 2)
+
+
+def conv3x3_halo_kernel_model(x_nhwc, w_oihw, bias=None):
+    """The work decomposition and the epilogue of csrc/conv_halo.cu, step by step: bands of BH = 256 // (W+2) image rows,
+    two 128-row MMA tiles (the second skipped when the band's live rows fit the first), per epilogue warp (32 accumulator
+    rows) one clipped row store per image row it touches, one GroupNorm slot per (band, tile, warp).
+    Returns (out [B,H,W,Cout], writes [B,H,W] = how often each pixel was stored, slot_sums [B, slots] = sum over the
+    output channels of each slot's valid rows)."""
+    B, H, W, C = x_nhwc.shape
+    Cout = w_oihw.shape[0]
+    PW = W + 2
+    BH = kernel_plan(W)
+    bands = -(-H // BH)
+    out = np.full((B, H, W, Cout), np.nan)
+    writes = np.zeros((B, H, W), dtype=np.int64)
+    slots = np.zeros((B, bands * 8))
+    wt = w_oihw.astype(np.float64).transpose(2, 3, 1, 0)
+    for b in range(B):
+        for band_i in range(bands):
+            y0 = band_i * BH
+            bh = min(BH, H - y0)
+            n_t = 2 if bh * PW > 128 else 1
+            # the TMA box: BH+2 rows from y0-1, W+2 columns from -1, zeros outside the image; reads past the box hit
+            # whatever follows in shared memory (modelled as NaN: junk rows must never reach the output)
+            S = np.full(((256 + 2 * PW + 2), C), np.nan)
+            S[:(BH + 2) * PW] = 0.0
+            for r in range(BH + 2):
+                y = y0 - 1 + r
+                if 0 <= y < H:
+                    S[r * PW + 1:r * PW + 1 + W] = x_nhwc[b, y]
+            acc = np.zeros((256, Cout))
+            for t in range(n_t):
+                for ky in range(3):
+                    for kx in range(3):
+                        rows = np.arange(t * 128, (t + 1) * 128) + ky * PW + kx      # descriptor start shifted by whole rows
+                        acc[t * 128:(t + 1) * 128] += S[rows] @ wt[ky, kx]
+            if bias is not None:
+                acc = acc + bias
+            for t in range(2):
+                for q in range(4):
+                    m0w = t * 128 + q * 32
+                    m = m0w + np.arange(32)
+                    yy, xx = m // PW, m % PW
+                    valid = (t < n_t) & (xx < W) & (yy < bh)
+                    slots[b, (band_i * 2 + t) * 4 + q] = acc[m][valid].sum() if valid.any() else 0.0
+                    if t >= n_t:
+                        continue
+                    yr0, yr1 = m0w // PW, min((m0w + 31) // PW, bh - 1)
+                    for yr in range(yr0, yr1 + 1):
+                        xs = m0w - yr * PW
+                        if xs >= W:
+                            continue
+                        for r in range(32):                 # one TMA store: box row r lands at column xs + r, clipped to [0, W)
+                            xcol = xs + r
+                            if 0 <= xcol < W:
+                                out[b, y0 + yr, xcol] = acc[m0w + r]
+                                writes[b, y0 + yr, xcol] += 1
+    return out, writes, slots
+
+
 if __name__ == "__main__":
     for (H, W) in ((32, 32), (16, 16), (8, 8), (28, 28), (64, 64)):
         for BH in (3, 7, 15):
