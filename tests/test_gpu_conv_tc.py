@@ -228,3 +228,17 @@ def test_conv_halo_dgrad(shape):
     got = _run(2, 1, dy.cuda(), w.cuda(), None, None, B, H, W, Cin, Cout, 3).cpu()
     l2, mx = rel_err(got, ref)
     assert l2 < 1e-4 and mx < 1e-4, f"halo engine dgrad: rel-L2 {l2:.2e} max-rel {mx:.2e}"
+
+
+@_halo
+def test_unet_parity_with_halo_engine():
+    """The whole parity suite with IGM_CONV_HALO=1 (the switch is read once per process, hence the subprocess): the
+    32x32 / 28x28 / 64x64 3x3 convs then run forward and data gradient on conv_halo.cu, GroupNorm statistics included."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, IGM_CONV_HALO="1")
+    env.pop("IGM_TEST_CONV_HALO", None)
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-x", "-q", "-m", "gpu"], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=1800)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
