@@ -74,6 +74,7 @@ SYMBOLS = {
                                      C.c_int, C.c_int, _P]),
     "igm_debug_conv": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, _P]),
+    "igm_debug_conv_bench": (C.c_int, [C.c_int] * 11 + [C.POINTER(C.c_float), _P]),
     "igm_set_conv_engine": (C.c_int, [_P, C.c_int]),
     "igm_get_conv_engine": (C.c_int, [_P]),
 }

@@ -75,6 +75,73 @@ extern "C" int igm_debug_conv(int engine, int mode, const float* x, const float*
   return rc;
 }
 
+// Kernel-level timing of one stride-1 convolution on the tcgen05 engines: operands are staged and the plan is built
+// once, then `iters` launches are timed with CUDA events on `stream` (after `warm` untimed ones).  engine 1 = per-tap
+// (conv_tc.cu), 2 = halo-reuse (conv_halo.cu); gn != 0 also produces the fused GroupNorm partial statistics, as the
+// Block convs of the U-Net do.  Inputs are synthetic (a fixed pattern); *ms_per_launch receives the average.
+extern "C" int igm_debug_conv_bench(int engine, int mode, int B, int H, int W, int Cin, int Cout, int K, int gn, int warm,
+                                    int iters, float* ms_per_launch, void* stream) {
+  Status& st = global_status();
+  st = Status();
+  int64_t launches = 0;
+  LaunchCtx lc;
+  lc.stream = (cudaStream_t)stream;
+  lc.st = &st;
+  lc.counter = &launches;
+  if (K != 1 && K != 3) IGM_FAIL(st, IGM_ERR_INVALID, "K must be 1 or 3");
+  if (engine != 1 && engine != 2) IGM_FAIL(st, IGM_ERR_INVALID, "engine must be 1 (per-tap) or 2 (halo-reuse)");
+  if (iters < 1 || warm < 0 || !ms_per_launch) IGM_FAIL(st, IGM_ERR_INVALID, "bad iteration counts");
+  const int KK = K * K, pad = (K - 1) / 2;
+  const int Kc = mode == 0 ? Cin : Cout, N = mode == 0 ? Cout : Cin;
+  const int64_t M = (int64_t)B * H * W;
+  const int64_t nw = (int64_t)KK * Cin * Cout;
+  if (!tc_eligible(Kc, N, H, W, K) || (engine == 2 && (K != 3 || !tch_eligible(Kc, N, H, W))))
+    IGM_FAIL(st, IGM_ERR_INVALID, "shape not eligible for the requested tcgen05 engine");
+  __nv_bfloat16 *wh = nullptr, *wl = nullptr, *ah = nullptr, *al = nullptr;
+  float *out = nullptr, *part = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = IGM_OK;
+  auto fail = [&](cudaError_t e) {
+    if (e != cudaSuccess && rc == IGM_OK) { set_error(st, IGM_ERR_CUDA, __FILE__, __LINE__, cudaGetErrorString(e)); rc = IGM_ERR_CUDA; }
+  };
+  fail(cudaMalloc(&wh, nw * 2)); fail(cudaMalloc(&wl, nw * 2));
+  fail(cudaMalloc(&ah, M * Kc * 2)); fail(cudaMalloc(&al, M * Kc * 2));
+  fail(cudaMalloc(&out, M * N * 4));
+  fail(cudaMalloc(&part, (size_t)B * (H * W / 16 + 64) * kGroups * 2 * 4));
+  fail(cudaEventCreate(&e0)); fail(cudaEventCreate(&e1));
+  if (rc == IGM_OK) {
+    // bf16 1.0 / small values: the timing does not depend on the data, only finite operands are needed
+    fail(cudaMemsetAsync(wh, 0x3c, nw * 2, lc.stream)); fail(cudaMemsetAsync(wl, 0x30, nw * 2, lc.stream));
+    fail(cudaMemsetAsync(ah, 0x3c, M * Kc * 2, lc.stream)); fail(cudaMemsetAsync(al, 0x30, M * Kc * 2, lc.stream));
+  }
+  TcConv t;
+  TcConvHalo th;
+  if (rc == IGM_OK) rc = engine == 2 ? tch_plan(st, th, Kc, N, H, W, B, ah, al, wh, wl) : tc_plan(st, t, Kc, N, H, W, B, K, pad, ah, al, wh, wl);
+  TcRun r;
+  r.B = B; r.out0 = out; r.N0 = N; r.kclass = mode == 0 ? K_CONV_FPROP : K_CONV_DGRAD;
+  if (rc == IGM_OK && gn) {
+    const bool ok = engine == 2 ? tch_gn_fusable(th) : tc_gn_fusable(t, B);
+    if (ok) r.gn_part = part;
+  }
+  for (int i = 0; i < warm + iters && rc == IGM_OK; ++i) {
+    if (i == warm) fail(cudaEventRecord(e0, lc.stream));
+    if (rc == IGM_OK) rc = engine == 2 ? launch_conv_halo(lc, th, r) : launch_conv_tc(lc, t, r);
+  }
+  if (rc == IGM_OK) {
+    fail(cudaEventRecord(e1, lc.stream));
+    fail(cudaStreamSynchronize(lc.stream));
+    float ms = 0.f;
+    if (rc == IGM_OK) fail(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_per_launch = ms / (float)iters;
+  } else {
+    cudaStreamSynchronize(lc.stream);
+  }
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  cudaFree(wh); cudaFree(wl); cudaFree(ah); cudaFree(al); cudaFree(out); cudaFree(part);
+  return rc;
+}
+
 // Weight gradient of a stride-1 KxK conv: gw[Cout,Cin,K,K] += sum dY * X.  engine 0 = SIMT split-K,
 // engine 1 = tcgen05 (variant selects the MN-major descriptor convention during bring-up).
 extern "C" int igm_debug_wgrad(int engine, int variant, const float* x, const float* dy, float* gw, int B, int H,
