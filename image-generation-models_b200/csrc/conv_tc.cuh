@@ -113,6 +113,19 @@ int tch_gn_slots(const TcConvHalo& t);
 bool tch_gn_fusable(const TcConvHalo& t);
 int launch_conv_halo(const LaunchCtx& lc, const TcConvHalo& t, const TcRun& r);
 
+// CTA-pair (`cta_group::2`, M = 256) variant of the per-tap engine (conv_tc2.cu): same activation boxes and packed weights
+// as `base`, each CTA of a pair stages its own M tile and half of the weight tile.  Bring-up state: reachable through
+// igm_debug_conv / igm_debug_conv_bench (engine = 3) only.  `base` must outlive the pair plan.
+struct TcConvPair {
+  bool valid = false;
+  const TcConv* base = nullptr;
+  alignas(64) CUtensorMap b_hi, b_lo;   // weight boxes of 64 channels x 64 rows
+  mutable TcConv::OutMaps om;
+};
+bool tc2_eligible(const TcConv& base);
+int tc2_plan(Status& st, TcConvPair& t, const TcConv& base);
+int launch_conv_tc2(const LaunchCtx& lc, const TcConvPair& t, const TcRun& r);
+
 // Weight gradients on the tensor cores (wgrad_tc.cu).  Pixels are the reduction axis:
 //   G[tap][cs][cp] = sum_pixels S[pixel shifted by tap][cs] * P[pixel][cp]
 // S ("shifted") is fetched with the per-tap offsets / stride-2 sub-lattices of TcTap, P ("plain") is

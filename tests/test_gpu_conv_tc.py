@@ -242,3 +242,48 @@ def test_unet_parity_with_halo_engine():
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-x", "-q", "-m", "gpu"], cwd=root, env=env,
                        capture_output=True, text=True, timeout=1800)
     assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
+
+
+# ---- CTA-pair (cta_group::2) engine (csrc/conv_tc2.cu), bring-up state: never run on hardware yet ----
+_pair = pytest.mark.skipif(os.environ.get("IGM_TEST_CONV_PAIR") != "1",
+                           reason="conv_tc2.cu is in bring-up (never run on a GPU yet); set IGM_TEST_CONV_PAIR=1")
+
+PAIR_SHAPES = [
+    # B, H, W, Cin, Cout, K   (Cout % 128 == 0 for fprop; dgrad needs Cin % 128 == 0)
+    (1, 8, 32, 64, 128, 1),      # one pair tile, one tap, one K chunk
+    (2, 16, 16, 128, 128, 3),    # 4 M tiles = 2 pairs
+    (4, 8, 8, 256, 256, 3),      # two images per M tile, two N tiles
+    (5, 8, 8, 128, 128, 3),      # 3 M tiles (two images each): the last pair's second tile does not exist
+    (2, 32, 32, 128, 128, 3),
+    (160, 16, 16, 128, 128, 3),  # more pair tiles than CTA pairs: persistent loop, both accumulator stages
+]
+
+
+@_pair
+@pytest.mark.parametrize("shape", PAIR_SHAPES)
+def test_conv_pair_forward(shape):
+    B, H, W, Cin, Cout, K = shape
+    g = torch.Generator().manual_seed(13 + hash(shape) % 1000)
+    x = torch.randn(B, H, W, Cin, generator=g)
+    w = torch.randn(Cout, Cin, K, K, generator=g) / (Cin * K * K) ** 0.5
+    bias = torch.randn(Cout, generator=g)
+    add = torch.randn(B, H, W, Cout, generator=g)
+    xs, ws, bs, ads = x.cuda(), w.cuda(), bias.cuda(), add.cuda()
+    ref = _run(1, 0, xs, ws, bs, ads, B, H, W, Cin, Cout, K).cpu()
+    got = _run(3, 0, xs, ws, bs, ads, B, H, W, Cin, Cout, K).cpu()
+    assert torch.isfinite(got).all()
+    l2, mx = rel_err(got, ref.double())
+    assert l2 < 1e-5 and mx < 1e-5, f"pair engine vs per-tap engine: rel-L2 {l2:.2e} max-rel {mx:.2e}"
+
+
+@_pair
+@pytest.mark.parametrize("shape", PAIR_SHAPES[1:5])
+def test_conv_pair_dgrad(shape):
+    B, H, W, Cin, Cout, K = shape
+    g = torch.Generator().manual_seed(17 + hash(shape) % 1000)
+    dy = torch.randn(B, H, W, Cout, generator=g)
+    w = torch.randn(Cout, Cin, K, K, generator=g) / (Cout * K * K) ** 0.5
+    ref = F.conv_transpose2d(dy.permute(0, 3, 1, 2).double(), w.double(), padding=(K - 1) // 2).permute(0, 2, 3, 1)
+    got = _run(3, 1, dy.cuda(), w.cuda(), None, None, B, H, W, Cin, Cout, K).cpu()
+    l2, mx = rel_err(got, ref)
+    assert l2 < 1e-4 and mx < 1e-4, f"pair engine dgrad: rel-L2 {l2:.2e} max-rel {mx:.2e}"
