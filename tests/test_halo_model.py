@@ -43,3 +43,17 @@ def test_kernel_decomposition_and_row_stores(H, W):
     assert (writes == 1).all()
     np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(slots.sum(axis=1), ref.sum(axis=(1, 2, 3)), rtol=1e-10, atol=1e-10)
+
+
+def test_pair_kernel_column_algebra():
+    """csrc/conv_tc2.cu: per-CTA weight staging [w_hi half ; w_lo half], the 64-column offset of the a_lo x w_hi MMA and
+    the epilogue's column map reproduce a_hi*w_hi + a_hi*w_lo + a_lo*w_hi for every output channel."""
+    _q = os.path.join(os.path.dirname(_p), "pair_columns_model.py")
+    _t = importlib.util.spec_from_file_location("pair_columns_model", _q)
+    PM = importlib.util.module_from_spec(_t)
+    _t.loader.exec_module(PM)
+    rng = np.random.default_rng(0)
+    a_hi, a_lo = rng.standard_normal((256, 64)), 1e-3 * rng.standard_normal((256, 64))
+    w_hi, w_lo = rng.standard_normal((128, 64)), 1e-3 * rng.standard_normal((128, 64))
+    want = a_hi @ w_hi.T + a_hi @ w_lo.T + a_lo @ w_hi.T
+    np.testing.assert_allclose(PM.pair_tile(a_hi, a_lo, w_hi, w_lo), want, rtol=1e-12, atol=1e-12)
