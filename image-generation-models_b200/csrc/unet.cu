@@ -70,6 +70,13 @@ bool conv_halo_on() {
   return on;
 }
 
+// IGM_CONV_PAIR=1: eligible stride-1 convs (N % 128 == 0) run forward and data gradient on the cta_group::2 engine
+// (conv_tc2.cu).  Bring-up switch, default off: the kernel has not run on hardware yet.
+bool conv_pair_on() {
+  static const bool on = [] { const char* e = getenv("IGM_CONV_PAIR"); return e && e[0] == '1'; }();
+  return on;
+}
+
 struct ParamInfo {
   std::string name;
   int64_t offset = 0;
@@ -101,6 +108,7 @@ struct ConvL {
   __nv_bfloat16 *wf_hi = nullptr, *wf_lo = nullptr, *wb_hi = nullptr, *wb_lo = nullptr;
   TcConv tc_f, tc_b;
   TcConvHalo tch_f, tch_b;   // halo-reuse fprop / dgrad plans (conv_halo.cu), only when IGM_CONV_HALO=1 (bring-up, default off)
+  TcConvPair tcp_f, tcp_b;   // CTA-pair plans on top of tc_f / tc_b (conv_tc2.cu), only when IGM_CONV_PAIR=1 (bring-up, default off)
   TcWgrad tc_w;
   bool tc_wh_ok = false;       // 3x3 stride-1: halo-reuse weight-gradient engine (wgrad_halo.cu)
   TcWgradHalo tc_wh;
@@ -658,6 +666,7 @@ struct Runner {
   bool tc_on() const { return c.conv_engine == 1; }
   bool use_tc(const TcConv& t) const { return tc_on() && t.valid; }
   bool use_halo(const TcConvHalo& t) const { return tc_on() && conv_halo_on() && t.valid; }
+  bool use_pair(const TcConvPair& t) const { return tc_on() && conv_pair_on() && t.valid; }
   // bf16 staging pointers of an activation: only handed to producers while the tcgen05 engine is on
   __nv_bfloat16* hi(const Act& a) const { return tc_on() ? a.hi : nullptr; }
   __nv_bfloat16* lo(const Act& a) const { return tc_on() ? a.lo : nullptr; }
@@ -685,6 +694,7 @@ struct Runner {
       r.gn_part = gn_part;
       if (out_act) { r.hi0 = hi(*out_act); r.lo0 = lo(*out_act); }
       if (use_halo(l.tch_f)) return launch_conv_halo(lc, l.tch_f, r);
+      if (use_pair(l.tcp_f)) return launch_conv_tc2(lc, l.tcp_f, r);
       return launch_conv_tc(lc, l.tc_f, r);
     }
     ConvArgs a;
@@ -715,6 +725,7 @@ struct Runner {
       r.B = B; r.bias = nullptr; r.out0 = d0; r.out1 = d1; r.N0 = C0; r.add0 = add0; r.add1 = add1;
       r.kclass = K_CONV_DGRAD;
       if (use_halo(l.tch_b) && !d1 && C0 == l.Cin) return launch_conv_halo(lc, l.tch_b, r);   // single output tensor only
+      if (use_pair(l.tcp_b)) return launch_conv_tc2(lc, l.tcp_b, r);
       return launch_conv_tc(lc, l.tc_b, r);
     }
     ConvArgs a;
@@ -1187,6 +1198,10 @@ static int plan_tc(igm_ctx* c) {
     if (l.tc_b_ok)
       IGM_TRY(tc_plan(c->st, l.tc_b, l.Cout, l.Cin, l.H, l.W, c->cfg.max_batch, l.K, pad, c->dy_hi[l.dyb], c->dy_lo[l.dyb], l.wb_hi,
                       l.wb_lo));
+    if (conv_pair_on()) {   // CTA-pair plans reference tc_f / tc_b (ConvL objects do not move after planning)
+      if (l.tc_f.valid && tc2_eligible(l.tc_f)) IGM_TRY(tc2_plan(c->st, l.tcp_f, l.tc_f));
+      if (l.tc_b.valid && tc2_eligible(l.tc_b)) IGM_TRY(tc2_plan(c->st, l.tcp_b, l.tc_b));
+    }
     if (conv_halo_on() && l.K == 3) {   // same operands and packed weights, halo-reuse tiling (bring-up switch)
       if (l.tc_f.valid && tch_eligible(l.Cin, l.Cout, l.H, l.W))
         IGM_TRY(tch_plan(c->st, l.tch_f, l.Cin, l.Cout, l.H, l.W, c->cfg.max_batch, s0->hi, s0->lo, l.wf_hi, l.wf_lo, s0->C,

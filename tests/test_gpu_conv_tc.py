@@ -287,3 +287,17 @@ def test_conv_pair_dgrad(shape):
     got = _run(3, 1, dy.cuda(), w.cuda(), None, None, B, H, W, Cin, Cout, K).cpu()
     l2, mx = rel_err(got, ref)
     assert l2 < 1e-4 and mx < 1e-4, f"pair engine dgrad: rel-L2 {l2:.2e} max-rel {mx:.2e}"
+
+
+@_pair
+def test_unet_parity_with_pair_engine():
+    """The whole parity suite with IGM_CONV_PAIR=1 (read once per process, hence the subprocess): every stride-1 conv
+    with N % 128 == 0 then runs forward and data gradient on conv_tc2.cu, fused GroupNorm statistics included."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, IGM_CONV_PAIR="1")
+    env.pop("IGM_TEST_CONV_PAIR", None)
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-x", "-q", "-m", "gpu"], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=1800)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
