@@ -31,6 +31,13 @@ METRIC = "ddpm_unet_train_steps_per_sec"
 UNIT = "steps/s (128 images per GPU-step)"
 
 
+def workload_name(B):
+    """config.workload, shared verbatim by our arm and the reference arm (BASELINE.json configs[1])."""
+    return (f"DDPM CIFAR-10 32x32 U-Net dims 3-64-128-256 T=1000 batch={B}/GPU "
+            "(BASELINE.json configs[1]); train step = noise+q_sample+fwd+L1+bwd+allreduce+Adam")
+
+
+
 def synth_batch(B, seed):
     g = torch.Generator().manual_seed(seed)
     return (torch.randn(B, CH, H, W, generator=g) * 0.5).clamp(-1, 1)
@@ -169,7 +176,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"DDPM CIFAR-10 32x32 U-Net dims 3-64-128-256 T=1000 batch={B}, train step on host CPU"},
+        "config": {"workload": workload_name(B), "where": "host CPU (torch fp32, all cores), one rank",
+                   "parallelism": f"dp{args.gpus}", "global_batch": B * args.gpus},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{args.steps} full train steps at B={B} (oracle port of the reference algorithm; "
                                    "the reference itself is torch-on-CPU and needs Lightning, absent here)"},
@@ -324,8 +332,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"DDPM CIFAR-10 32x32 U-Net dims 3-64-128-256 T=1000 batch={B}/GPU "
-                                   "(BASELINE.json configs[1]); train step = noise+q_sample+fwd+L1+bwd+allreduce+Adam",
+            "config": {"workload": workload_name(B),
                        "l2": "per-step working set ~3.5 GB of activations >> 126 MB L2; 8 rotating input batches",
                        "parallelism": f"dp{world}", "global_batch": B * world},
             "images_per_sec": value * B,
