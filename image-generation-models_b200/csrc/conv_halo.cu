@@ -55,6 +55,8 @@ struct HFArgs {
   const float* bias;
   const float* add0;
   int want_split;           // also emit the output as bf16 hi/lo
+  int tma_rows;             // 1: clipped per-image-row TMA stores; 0 (IGM_HALO_TMA_STORE=0): thread-per-row stores of the valid rows
+  float* out0; __nv_bfloat16* hi0; __nv_bfloat16* lo0;
   float* gn_part; int gn_cpg, gn_slots;
 };
 
@@ -316,6 +318,27 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constan
               v[jj] += av.x; v[jj + 1] += av.y; v[jj + 2] += av.z; v[jj + 3] += av.w;
             }
           }
+          if (!p.tma_rows) {
+            // fallback that does not rely on TMA stores clipping a box with a negative start: each valid thread writes
+            // its own row segment (64 contiguous bytes of its output pixel)
+            if (valid) {
+              float* o = p.out0 + opix * p.N + n;
+#pragma unroll
+              for (int jj = 0; jj < CW; jj += 4)
+                *reinterpret_cast<float4*>(o + jj) = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
+              if (p.want_split) {
+#pragma unroll
+                for (int jj = 0; jj < CW; jj += 8) {
+                  __align__(16) uint32_t h[4], l[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) split_pair(v[jj + 2 * e], v[jj + 2 * e + 1], h[e], l[e]);
+                  *reinterpret_cast<uint4*>(p.hi0 + opix * p.N + n + jj) = *reinterpret_cast<const uint4*>(h);
+                  *reinterpret_cast<uint4*>(p.lo0 + opix * p.N + n + jj) = *reinterpret_cast<const uint4*>(l);
+                }
+              }
+            }
+            continue;
+          }
           // registers -> staging tile (row = lane) -> one TMA store per image row the warp touches
           if (lane == 0) tma_store_wait_read<0>();   // the previous chunk's stores have drained the staging tiles
           __syncwarp();
@@ -495,6 +518,9 @@ int launch_conv_halo(const LaunchCtx& lc, const TcConvHalo& t, const TcRun& r) {
   a.a_tx_bytes = (uint32_t)(2 * (t.BH + 2) * (t.W + 2) * 128);
   a.bias = r.bias; a.add0 = r.add0;
   a.want_split = r.hi0 ? 1 : 0;
+  static const bool tma_rows_off = [] { const char* e = getenv("IGM_HALO_TMA_STORE"); return e && e[0] == '0'; }();
+  a.tma_rows = tma_rows_off ? 0 : 1;
+  a.out0 = r.out0; a.hi0 = r.hi0; a.lo0 = r.lo0;
   a.gn_part = r.gn_part; a.gn_cpg = r.gn_part ? t.N / kGroups : 0; a.gn_slots = tch_gn_slots(t);
   TcConv::OutMaps& om = t.om;
   if (om.p0 != r.out0) {

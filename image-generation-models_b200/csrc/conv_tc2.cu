@@ -55,6 +55,7 @@ struct PArgs {
   const float* add0; const float* add1;
   int want_split;
   float* gn_part; int gn_cpg, gn_slots;
+  int dbg;   // IGM_PAIR_DEBUG bring-up bits: 1 = skip the a_lo x w_hi MMA (result = a_hi x (w_hi + w_lo): isolates the N split)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -236,7 +237,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant
           for (int k = 0; k < KC / UMMA_K; ++k) {
             const uint32_t off = soff + (uint32_t)(k * UMMA_K * 2 >> 4);
             umma2_bf16(d_tmem, dA_hi0 + off, dB0 + off, idesc_2n, accum);      // [hh(0..63) | hl(0..63) | hh(64..127) | hl(64..127)]
-            umma2_bf16(d_tmem + 64u, dA_lo0 + off, dB0 + off, idesc_n, 1u);    // lh(0..63) onto hl(0..63), lh(64..127) onto hh(64..127)
+            if (!(p.dbg & 1))
+              umma2_bf16(d_tmem + 64u, dA_lo0 + off, dB0 + off, idesc_n, 1u);  // lh(0..63) onto hl(0..63), lh(64..127) onto hh(64..127)
             accum = 1u;
           }
           umma2_commit_both(&empty[stage]);
@@ -464,6 +466,11 @@ int launch_conv_tc2(const LaunchCtx& lc, const TcConvPair& tp, const TcRun& r) {
   a.stage_tx_bytes = 2 * A_TILE_BYTES + B_TILE_BYTES;
   a.bias = r.bias; a.add0 = r.add0; a.add1 = r.add1;
   a.want_split = r.hi0 ? 1 : 0;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("IGM_PAIR_DEBUG"); dbg = e ? atoi(e) : 0; }
+    a.dbg = dbg;
+  }
   a.gn_part = nullptr; a.gn_cpg = 0; a.gn_slots = 0;
   if (r.gn_part) {
     if (!tc_gn_fusable(t, r.B) || r.N0 != t.N) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "conv_tc2: GroupNorm statistics cannot be fused for this plan");
