@@ -1,12 +1,12 @@
-"""GPU: BASELINE.json configs[1] at its FULL size (CIFAR-10 U-Net, batch 128 on one GPU), where the CPU oracle cannot
-process the whole batch in seconds.  Every operator of the path is per-sample (GroupNorm / LayerNorm statistics, the
+"""GPU: BASELINE.json configs[1] (CIFAR-10 U-Net, batch 128 on one GPU) and configs[2] (CelebA-64 U-Net, 256 / 8 = 32
+images per GPU) at their FULL per-GPU sizes, where the CPU oracle cannot process the whole batch in seconds.  Every operator of the path is per-sample (GroupNorm / LayerNorm statistics, the
 linear-attention softmax and context are all computed inside one image; there is no BatchNorm: SURVEY.md section 8(e)),
 which gives size-independent properties:
 
   * the rows of a batch-128 result equal the oracle run on those samples alone (parity proper, on a subset);
   * the rows equal the CUDA path run on a small batch of the same samples (batch independence), and a repeat run of the
     inference forward reproduces the result;
-  * the gradient of the batch-mean loss over 128 samples is the mean of the gradients over its four 32-sample quarters,
+  * the gradient of the batch-mean loss over 128 samples is the mean of the gradients over its four quarters,
     and the loss the mean of their losses ("a checksum of checksums").
 
 (The file name sorts last on purpose: these are the heaviest tests of the suite.)"""
@@ -19,20 +19,30 @@ from tests._util import REL_TOL, assert_close
 
 pytestmark = pytest.mark.gpu
 
-DIM, CH, MULTS, H, W, B, T = 64, 3, (1, 2, 4), 32, 32, 128, 1000
-SUBSET = [0, 63, 127]
+DIM, CH, T = 64, 3, 1000
+CONFIGS = {
+    # name: (dim_mults, H, W, batch per GPU)
+    "cifar10_b128": ((1, 2, 4), 32, 32, 128),
+    "celeba64_b32": ((1, 2, 4, 8), 64, 64, 32),
+}
 
 
-def _build(loss_type="l1"):
-    spec = O.UnetSpec(DIM, CH, MULTS)
+def _subset(B):
+    return [0, B // 2 - 1, B - 1]
+
+
+def _build(cfg, loss_type="l1"):
+    mults, H, W, B = CONFIGS[cfg]
+    spec = O.UnetSpec(DIM, CH, mults)
     params = O.init_params(spec, seed=7)
-    unet = igm_b200.Unet(dim=DIM, channels=CH, dim_mults=MULTS)
+    unet = igm_b200.Unet(dim=DIM, channels=CH, dim_mults=mults)
     unet.load_state_dict(params)
     gd = igm_b200.GaussianDiffusion(unet, image_size=(H, W), channels=CH, timesteps=T, loss_type=loss_type).cuda()
     return spec, params, gd.denoise_fn, gd
 
 
-def _inputs(seed=2024):
+def _inputs(cfg, seed=2024):
+    mults, H, W, B = CONFIGS[cfg]
     g = torch.Generator().manual_seed(seed)
     x = (torch.randn(B, CH, H, W, generator=g) * 0.5).clamp(-1, 1)
     t = torch.randint(0, T, (B,), generator=g)
@@ -40,9 +50,11 @@ def _inputs(seed=2024):
     return x, t, noise
 
 
-def test_full_batch_forward_rows_match_oracle_and_small_batches():
-    spec, params, unet, gd = _build()
-    x, t, _ = _inputs()
+@pytest.mark.parametrize("cfg", list(CONFIGS))
+def test_full_batch_forward_rows_match_oracle_and_small_batches(cfg):
+    spec, params, unet, gd = _build(cfg)
+    x, t, _ = _inputs(cfg)
+    SUBSET = _subset(x.shape[0])
     with torch.no_grad():
         full = unet(x.cuda(), t.cuda())
         again = unet(x.cuda(), t.cuda())
@@ -50,12 +62,15 @@ def test_full_batch_forward_rows_match_oracle_and_small_batches():
         assert torch.isfinite(full).all()
         ref = O.unet_forward(params, spec, x[SUBSET], t[SUBSET])             # three samples on the CPU oracle
         small = unet(x[SUBSET].cuda(), t[SUBSET].cuda())                     # the same three as a batch of their own
-    assert_close(full[SUBSET].cpu(), ref, "rows of the batch-128 forward vs the oracle")
+    assert_close(full[SUBSET].cpu(), ref, f"{cfg}: rows of the full-batch forward vs the oracle")
     assert_close(small.cpu(), full[SUBSET].cpu(), "batch independence of the forward", 1e-4)
 
 
-def test_full_batch_sampler_rows_match_oracle():
-    spec, params, unet, gd = _build()
+@pytest.mark.parametrize("cfg", list(CONFIGS))
+def test_full_batch_sampler_rows_match_oracle(cfg):
+    spec, params, unet, gd = _build(cfg)
+    mults, H, W, B = CONFIGS[cfg]
+    SUBSET = _subset(B)
     g = torch.Generator().manual_seed(7)
     img = torch.randn(B, CH, H, W, generator=g)
     step_noise = torch.randn(2, B, CH, H, W, generator=g)
@@ -63,13 +78,16 @@ def test_full_batch_sampler_rows_match_oracle():
     out = gd._run_sampler(img.clone().cuda(), T - 1, 2, noise=step_noise.cuda())
     with torch.no_grad():
         ref = O.p_sample_loop(params, spec, buf, img[SUBSET].clone(), step_noise[:, SUBSET].contiguous(), t_start=T - 1, n_steps=2)
-    assert_close(out[SUBSET].cpu(), ref, "rows of two batch-128 denoise steps vs the oracle")
+    assert_close(out[SUBSET].cpu(), ref, f"{cfg}: rows of two full-batch denoise steps vs the oracle")
 
 
-def test_full_batch_gradient_is_the_mean_of_its_quarters():
+@pytest.mark.parametrize("cfg", list(CONFIGS))
+def test_full_batch_gradient_is_the_mean_of_its_quarters(cfg):
     # L2 loss: the L1 sign gradient is discontinuous, the property is about summation, not about the kink
-    spec, params, unet, gd = _build("l2")
-    x, t, noise = _inputs(seed=99)
+    spec, params, unet, gd = _build(cfg, "l2")
+    x, t, noise = _inputs(cfg, seed=99)
+    B = x.shape[0]
+    SUBSET = _subset(B)
     xc, tc, nc = x.cuda(), t.cuda(), noise.cuda()
     unet._flat_grad.zero_()
     loss_full = gd.p_losses(xc, tc, nc)
