@@ -17,6 +17,8 @@
 //     MMA 2:  a_lo x w_hi    M = 256, N = 128, the same B descriptor (the first 64 rows of each CTA's tile are its half
 //             of w_hi), accumulator address + 64 columns  ->  lands on [hl(0..63) | hh(64..127)]: columns of the right
 //             output channels; the epilogue adds a channel's hh and hl columns anyway.
+// (Operand partitioning of cta_group::2 as CUTLASS encodes it for SM100_MMA_F16BF16_2x1SM_SS, cute/atom/mma_traits_sm100.hpp:
+// CTA r supplies A rows r*M/2.., B rows r*N/2.. from the same descriptor offset, and holds D rows r*M/2.. x all N columns.)
 // Barrier protocol (DeepGEMM-style): both CTAs run a TMA producer whose loads complete on the LEADER's `full` barrier
 // (count 2: the leader's arrive.expect_tx for both CTAs' bytes + the peer's plain arrive); the leader's
 // tcgen05.commit multicasts to both CTAs' `empty` / `acc_full` barriers; all eight epilogue warps arrive on the leader's

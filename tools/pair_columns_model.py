@@ -2,7 +2,9 @@
 
 Assumed instruction semantics (PTX tcgen05.mma.cta_group::2, M = 256): A rows 0..127 come from CTA 0's shared memory and
 128..255 from CTA 1's; B's N rows are split - CTA r supplies rows r*N/2 .. (r+1)*N/2 - 1 FROM THE SAME DESCRIPTOR OFFSET of
-its own shared memory; each CTA's TMEM receives its 128 rows of D with all N columns.  Under that assumption the model
+its own shared memory; each CTA's TMEM receives its 128 rows of D with all N columns (this is the operand partitioning
+CUTLASS encodes for SM100_MMA_F16BF16_2x1SM_SS: cute/atom/mma_traits_sm100.hpp, ALayout / BLayout / CLayout with a CTA
+stride of M/2, N/2, M/2).  Under that assumption the model
 checks the kernel's operand staging and epilogue: CTA r stages B'_r = [w_hi[64r:64r+64] ; w_lo[64r:64r+64]],
 MMA 1 = a_hi x B' (N = 256), MMA 2 = a_lo x (first 64 rows of each B'_r) (N = 128) accumulated 64 columns to the right,
 epilogue channel c -> columns (c, c + 64) for c < 64 and (128 + c - 64, 192 + c - 64) otherwise.
