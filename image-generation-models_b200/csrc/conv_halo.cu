@@ -56,6 +56,8 @@ struct HFArgs {
   const float* add0;
   int want_split;           // also emit the output as bf16 hi/lo
   int tma_rows;             // 1: clipped per-image-row TMA stores; 0 (IGM_HALO_TMA_STORE=0): thread-per-row stores of the valid rows
+  int base_offset;          // IGM_HALO_BASE_OFFSET=1: fill the descriptor's matrix-base-offset field ((start >> 7) & 7) for the
+                            // shifted activation descriptors (tools/desc_probe.cu found 0 correct; bring-up alternative)
   float* out0; __nv_bfloat16* hi0; __nv_bfloat16* lo0;
   float* gn_part; int gn_cpg, gn_slots;
 };
@@ -219,6 +221,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constan
               mbar_wait(&w_full[ws], wphase);
               tc_fence_after();
               const uint64_t db = dB0 + (uint32_t)ws * (uint32_t)(W_STAGE_BYTES >> 4);
+              // start row of the shifted tile modulo the 8-row swizzle atom (stage and tile offsets are multiples of 8 rows)
+              const uint64_t bo = p.base_offset ? ((uint64_t)((shift >> 3) & 7u) << 49) : 0ull;
               const uint32_t first = (kc | ky | kx) ? 1u : 0u;
               for (int t = 0; t < n_t; ++t) {
                 const uint32_t off = a_off + shift + (uint32_t)t * (128u * 128u >> 4);
@@ -226,8 +230,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constan
 #pragma unroll
                 for (int k = 0; k < KC / UMMA_K; ++k) {
                   const uint32_t ko = (uint32_t)(k * UMMA_K * 2 >> 4);   // 32 bytes inside the 128-byte swizzle row
-                  umma_bf16(d, dA_hi0 + off + ko, db + ko, idesc_2n, (k == 0) ? first : 1u);   // [a_hi*w_hi | a_hi*w_lo]
-                  umma_bf16(d, dA_lo0 + off + ko, db + ko, idesc_n, 1u);                       //  a_lo*w_hi into the first half
+                  umma_bf16(d, (dA_hi0 + off + ko) | bo, db + ko, idesc_2n, (k == 0) ? first : 1u);   // [a_hi*w_hi | a_hi*w_lo]
+                  umma_bf16(d, (dA_lo0 + off + ko) | bo, db + ko, idesc_n, 1u);                       //  a_lo*w_hi into the first half
                 }
               }
               umma_commit(&w_empty[ws]);
@@ -520,6 +524,8 @@ int launch_conv_halo(const LaunchCtx& lc, const TcConvHalo& t, const TcRun& r) {
   a.want_split = r.hi0 ? 1 : 0;
   static const bool tma_rows_off = [] { const char* e = getenv("IGM_HALO_TMA_STORE"); return e && e[0] == '0'; }();
   a.tma_rows = tma_rows_off ? 0 : 1;
+  static const bool base_off = [] { const char* e = getenv("IGM_HALO_BASE_OFFSET"); return e && e[0] == '1'; }();
+  a.base_offset = base_off ? 1 : 0;
   a.out0 = r.out0; a.hi0 = r.hi0; a.lo0 = r.lo0;
   a.gn_part = r.gn_part; a.gn_cpg = r.gn_part ? t.N / kGroups : 0; a.gn_slots = tch_gn_slots(t);
   TcConv::OutMaps& om = t.om;
