@@ -1671,7 +1671,7 @@ int igm_ddpm_sample_loop(igm_ctx* c, float* img, const float* noise, uint64_t se
   const int64_t before = c->launches;
   IGM_TRY(sampler_step(c, r, img, noise, seed, clip_denoised));
   const int64_t per_step = c->launches - before;
-  if (n_steps == 1) { c->fwd_valid = false; return IGM_OK; }
+  if (n_steps == 1) { c->fwd_valid = false; c->loss_valid = false; return IGM_OK; }
   igm_ctx::GraphKey key;
   key.img = img; key.noise = noise; key.seed = seed; key.B = B; key.clip = clip_denoised;
   if (!c->graph_exec || !(c->graph_key == key)) {

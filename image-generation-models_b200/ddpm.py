@@ -248,6 +248,8 @@ class Unet(nn.Module):
                 mod._parameters[key] = q
         self._flat, self._flat_grad, self._layout = flat, grad, layout
         self._pend, self._pend_gen = None, 0
+        self._fwd_gen = getattr(self, "_fwd_gen", 0) + 1
+        self._synced = False
         self._anchor = torch.zeros(1, device=dev, requires_grad=True)
         if self._engine is not None:
             self._engine.close()
@@ -286,6 +288,14 @@ class Unet(nn.Module):
         e.check(e.lib.igm_unet_bind_params(e.ctx, _ptr(self._flat), _ptr(arena)))
         e.grad_target = which
 
+    def sync_parameters(self, force: bool = False):
+        """Data parallel: every replica starts from rank 0's parameters (what DistributedDataParallel does at wrap time;
+        the mirror is never wrapped).  One broadcast of the flat arena, once per arena."""
+        if _world() > 1 and getattr(self, "ddp_sync", True) and (force or not self._synced):
+            import torch.distributed as dist
+            dist.broadcast(self._flat, src=0)     # in place: bumps the arena's version counter -> weights are re-packed
+            self._synced = True
+
     def mark_dirty(self):
         """Call after editing parameters through ``.data`` (which bypasses the version counter)."""
         if self._engine is not None:
@@ -321,6 +331,7 @@ class Unet(nn.Module):
             e.check(e.lib.igm_unet_bind_params(e.ctx, _ptr(self._flat), _ptr(self._flat_grad)))
             e.grad_target = "grad"
             self._engine = e
+            self.sync_parameters()
         if e.packed_version != self._flat._version:
             e.check(e.lib.igm_unet_pack_weights(e.ctx, _stream()))
             e.packed_version = self._flat._version
@@ -372,7 +383,35 @@ def _unet_forward(unet: Unet, x, time, training):
     e = unet._get_engine(B, H, W, x.device, training)
     out = torch.empty_like(x)
     e.check(e.lib.igm_unet_forward(e.ctx, _ptr(x), _ptr(t), _ptr(out), B, _stream()))
+    unet._fwd_gen += 1     # the engine keeps the activations of its LAST forward only (see _check_gen)
     return out
+
+
+def _check_gen(unet: Unet, gen: int):
+    """The engine stores one forward's activations.  A backward whose forward is no longer the engine's last one
+    (two losses summed before one backward, a sampler / inference call in between) would silently differentiate the
+    wrong activations: refuse instead."""
+    if gen != unet._fwd_gen:
+        raise RuntimeError("libigm_b200 keeps the activations of the most recent forward only: call backward() on a loss "
+                           "before running another forward / sampler step through the same Unet")
+
+
+def _reduce_into_grad(unet: Unet, e: "_Engine", run_backward, d_scale: float = 1.0):
+    """Backward into ``.grad`` with torch's accumulate semantics.  One rank: the kernels add straight into the ``.grad``
+    arena.  Data parallel: this backward's gradients go to the pending arena, ONLY that delta is all-reduced (reducing the
+    accumulated ``.grad`` arena would re-reduce earlier micro-batches), and ``.grad += delta / world``."""
+    sync = _world() > 1 and getattr(unet, "ddp_sync", True)
+    if not sync:
+        unet._bind_grad_target("grad")
+        run_backward()
+        return
+    unet._bind_grad_target("pend")
+    unet._pend.zero_()
+    run_backward()
+    _allreduce(unet, unet._pend)
+    e.check(e.lib.igm_grad_axpy(e.ctx, _ptr(unet._flat_grad), _ptr(unet._pend), None, C.c_float(d_scale / _world()),
+                                unet._flat_grad.numel(), _stream()))
+    unet._pend_gen += 1    # the pending arena no longer holds an eager training_step's gradients
 
 
 class _UnetFn(torch.autograd.Function):
@@ -380,18 +419,20 @@ class _UnetFn(torch.autograd.Function):
     def forward(ctx, anchor, unet, x, time):
         ctx.unet = unet
         ctx.need_dx = x.requires_grad
-        return _unet_forward(unet, x, time, training=True)
+        out = _unet_forward(unet, x, time, training=True)
+        ctx.gen = unet._fwd_gen
+        return out
 
     @staticmethod
     def backward(ctx, d_out):
         unet = ctx.unet
         e = unet._engine
+        _check_gen(unet, ctx.gen)
         unet.attach_grads()
-        unet._bind_grad_target("grad")
         d_out = _f32c(d_out)
         dx = torch.empty_like(d_out) if ctx.need_dx else None
-        e.check(e.lib.igm_unet_backward(e.ctx, _ptr(d_out), _ptr(dx), _stream()))
-        _allreduce_grads(unet)
+        # parameter gradients are the MEAN over ranks (like DistributedDataParallel); dx stays this rank's own
+        _reduce_into_grad(unet, e, lambda: e.check(e.lib.igm_unet_backward(e.ctx, _ptr(d_out), _ptr(dx), _stream())))
         return None, None, dx, None
 
 
@@ -402,11 +443,19 @@ def _world():
     return 1
 
 
-def _allreduce_grads(unet: Unet):
-    """Data-parallel exchange: ONE NCCL all-reduce (SUM) over the flat fp32 gradient arena."""
-    if _world() > 1 and getattr(unet, "ddp_sync", True):
-        import torch.distributed as dist
-        dist.all_reduce(unet._flat_grad, op=dist.ReduceOp.SUM)
+def _allreduce(unet: Unet, arena: torch.Tensor):
+    """Data-parallel exchange of ONE backward's gradients (SUM over ranks) over the flat fp32 arena, in
+    ``unet.ddp_buckets`` contiguous pieces (NCCL pipelines them; one piece = one ncclAllReduce)."""
+    import torch.distributed as dist
+    nb = max(1, int(getattr(unet, "ddp_buckets", 1)))
+    if nb == 1:
+        dist.all_reduce(arena, op=dist.ReduceOp.SUM)
+        return
+    n = arena.numel()
+    step = (n + nb - 1) // nb
+    step = (step + 1023) // 1024 * 1024
+    for off in range(0, n, step):
+        dist.all_reduce(arena[off:off + step], op=dist.ReduceOp.SUM)
 
 
 # ---------------------------------------------------------------------------
@@ -580,6 +629,7 @@ class GaussianDiffusion(nn.Module):
                 raise ValueError("injected noise must be [n_steps, B, C, H, W]")
         e.check(e.lib.igm_ddpm_sample_loop(e.ctx, _ptr(img), _ptr(noise), C.c_uint64(seed), B, int(t_start),
                                            int(n_steps), int(bool(clip_denoised)), _stream()))
+        self.denoise_fn._fwd_gen += 1   # the sampler's forwards overwrote the activations of any earlier forward
         return img
 
     @torch.no_grad()
@@ -650,6 +700,7 @@ def _p_losses_forward(gd: GaussianDiffusion, x_start, t, noise, training):
     loss = torch.empty((), dtype=torch.float32, device=x_start.device)
     e.check(e.lib.igm_ddpm_p_losses(e.ctx, _ptr(x_start), _ptr(t.to(torch.int64).contiguous()), _ptr(noise),
                                     _ptr(loss), B, _stream()))
+    gd.denoise_fn._fwd_gen += 1
     return loss
 
 
@@ -664,9 +715,11 @@ class _PLossesFn(torch.autograd.Function):
     def forward(ctx, anchor, gd, x_start, t, noise, eager):
         ctx.gd = gd
         ctx.eager = eager
-        if not eager:
-            return _p_losses_forward(gd, x_start, t, noise, training=True)
         unet = gd.denoise_fn
+        if not eager:
+            loss = _p_losses_forward(gd, x_start, t, noise, training=True)
+            ctx.fgen = unet._fwd_gen
+            return loss
         x_start, noise = _f32c(x_start), _f32c(noise)
         B, _, H, W = x_start.shape
         e = gd._engine(B, H, W, x_start.device, True)
@@ -674,13 +727,13 @@ class _PLossesFn(torch.autograd.Function):
         loss = torch.empty((), dtype=torch.float32, device=x_start.device)
         e.check(e.lib.igm_ddpm_p_losses(e.ctx, _ptr(x_start), _ptr(t.to(torch.int64).contiguous()), _ptr(noise),
                                         _ptr(loss), B, _stream()))
+        unet._fwd_gen += 1
         gd._start_loss_readback(loss)   # D2H of the scalar on a copy stream, ahead of the backward kernels
         unet._pend.zero_()
         sync = _world() > 1 and getattr(unet, "ddp_sync", True)
         e.check(e.lib.igm_ddpm_p_losses_backward(e.ctx, None, C.c_float(1.0 / _world() if sync else 1.0), _stream()))
         if sync:
-            import torch.distributed as dist
-            dist.all_reduce(unet._pend, op=dist.ReduceOp.SUM)
+            _allreduce(unet, unet._pend)
         unet._pend_gen += 1
         ctx.gen = unet._pend_gen
         return loss
@@ -698,10 +751,9 @@ class _PLossesFn(torch.autograd.Function):
             e.check(e.lib.igm_grad_axpy(e.ctx, _ptr(unet._flat_grad), _ptr(unet._pend), _ptr(d_loss), C.c_float(1.0),
                                         unet._flat_grad.numel(), _stream()))
             return None, None, None, None, None, None
-        unet._bind_grad_target("grad")
-        scale = 1.0 / _world() if getattr(unet, "ddp_sync", True) else 1.0
-        e.check(e.lib.igm_ddpm_p_losses_backward(e.ctx, _ptr(d_loss), C.c_float(scale), _stream()))
-        _allreduce_grads(unet)
+        _check_gen(unet, ctx.fgen)
+        _reduce_into_grad(unet, e, lambda: e.check(e.lib.igm_ddpm_p_losses_backward(e.ctx, _ptr(d_loss), C.c_float(1.0),
+                                                                                    _stream())))
         return None, None, None, None, None, None
 
 
@@ -714,7 +766,10 @@ class FusedAdam(torch.optim.Optimizer):
 
     def __init__(self, unet: Unet, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
         self.unet = unet
-        super().__init__(list(unet.parameters()), dict(lr=lr, betas=betas, eps=eps))
+        # the full torch.optim.Adam group (its other options at their defaults) so that state_dict()s interchange
+        super().__init__(list(unet.parameters()), dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False,
+                                                       maximize=False, foreach=None, capturable=False,
+                                                       differentiable=False, fused=None, decoupled_weight_decay=False))
         self._step = 0
         self._m = None
         self._v = None
@@ -745,17 +800,48 @@ class FusedAdam(torch.optim.Optimizer):
         return loss
 
     def state_dict(self):
+        """torch.optim.Adam's format: per-parameter ``exp_avg`` / ``exp_avg_sq`` / ``step`` entries (views of the flat
+        moment arenas), so a checkpoint written here resumes under the reference's ``torch.optim.Adam`` and vice versa."""
         sd = super().state_dict()
-        sd["igm"] = {"step": self._step, "exp_avg": self._m, "exp_avg_sq": self._v}
+        if self._m is not None:
+            step = torch.tensor(float(self._step))
+            state = {}
+            for i, ((name, off, shape), p) in enumerate(zip(self.unet._layout, self.unet.parameters())):
+                n = p.numel()
+                state[i] = {"step": step.clone(), "exp_avg": self._m[off:off + n].view(shape),
+                            "exp_avg_sq": self._v[off:off + n].view(shape)}
+            sd["state"] = state
         return sd
 
     def load_state_dict(self, sd):
-        extra = sd.get("igm")
-        super().load_state_dict({k: v for k, v in sd.items() if k != "igm"})
-        if extra:
-            self._step = extra["step"]
-            self._m = None if extra["exp_avg"] is None else extra["exp_avg"].to(self.unet._flat.device)
-            self._v = None if extra["exp_avg_sq"] is None else extra["exp_avg_sq"].to(self.unet._flat.device)
+        sd = dict(sd)
+        legacy = sd.pop("igm", None)    # round-1 checkpoints kept the flat arenas under a private key
+        state = sd.get("state") or {}
+        super().load_state_dict({**sd, "state": {}})
+        u = self.unet
+        if legacy and legacy.get("exp_avg") is not None:
+            self._step = int(legacy["step"])
+            self._m = legacy["exp_avg"].to(u._flat.device, torch.float32).clone()
+            self._v = legacy["exp_avg_sq"].to(u._flat.device, torch.float32).clone()
+            return
+        if not state:
+            self._step, self._m, self._v = 0, None, None
+            return
+        self._m = torch.zeros_like(u._flat)
+        self._v = torch.zeros_like(u._flat)
+        steps = set()
+        with torch.no_grad():
+            for i, (name, off, shape) in enumerate(u._layout):
+                st = state.get(i, state.get(str(i)))
+                if st is None:
+                    continue
+                n = st["exp_avg"].numel()
+                self._m[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                self._v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"FusedAdam steps every parameter together; the checkpoint holds different step counts {sorted(steps)}")
+        self._step = steps.pop() if steps else 0
 
 
 # ---------------------------------------------------------------------------

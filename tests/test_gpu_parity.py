@@ -348,3 +348,58 @@ def test_linear_schedule_repeat_noise_and_interpolate():
         ref = O.p_sample(params, spec, buf, mix, torch.zeros(B, dtype=torch.long), torch.zeros_like(mix))
     assert_close(got.cpu(), ref, "interpolate(t=1)")
     assert got.shape == x1.shape and torch.isfinite(gd.interpolate(x1.cuda(), x2.cuda(), t=5)).all()
+
+
+def test_full_1000_step_chain_matches_reference_fixture(conv_engine):
+    """The M2 product itself: the captured T = 1000 reverse chain with injected noise, checked after 1, 10, 100 and 1000
+    steps against the snapshots of the UNMODIFIED reference (tests/golden/make_golden_chain.py) and the oracle.
+    Tolerance 1e-3 (rel-L2 and max-abs / max-ref), the north_star bound -- also after 1000 chained U-Net calls."""
+    import importlib.util
+    spec_ = importlib.util.spec_from_file_location("make_golden_chain", os.path.join(os.path.dirname(__file__), "golden",
+                                                                                     "make_golden_chain.py"))
+    mc = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(mc)
+    dim, ch, mults, H, W, B, T = mc.CASE
+    spec = O.UnetSpec(dim, ch, mults)
+    params = O.init_params(spec, seed=7)
+    unet = igm_b200.Unet(dim=dim, channels=ch, dim_mults=mults)
+    unet.load_state_dict(params)
+    gd = igm_b200.GaussianDiffusion(unet, image_size=(H, W), channels=ch, timesteps=T).cuda()
+    img, noise = mc.chain_inputs()
+    fix = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "ddpm_chain_tiny.npz")))
+    noise_dev = noise.cuda()
+    for n in mc.SNAPSHOTS:
+        out = gd._run_sampler(img.clone().cuda(), T - 1, n, noise=noise_dev[:n].contiguous())
+        l2, mx = assert_close(out.cpu(), fix[f"after_{n}"], f"chain after {n} steps vs the reference fixture")
+        _report(f"chain tiny  after {n:4d} steps rel-L2 {l2:.2e} max-rel {mx:.2e} (engine {conv_engine})")
+    # the public call: p_sample_loop draws x_T itself; same chain when the draw and the noise are injected
+    torch.manual_seed(11)
+    a = gd.p_sample_loop((B, ch, H, W), noise=noise_dev)
+    torch.manual_seed(11)
+    x_T = torch.randn((B, ch, H, W), device="cuda")
+    b = gd._run_sampler(x_T, T - 1, T, noise=noise_dev)
+    assert torch.equal(a, b)
+
+
+def test_backward_of_an_overwritten_forward_raises():
+    """The engine keeps ONE forward's activations: summing two losses before one backward, or sampling between a loss and
+    its backward, must raise instead of differentiating the wrong activations."""
+    spec, params, unet, gd = _build("tiny")
+    x, t, noise, step_noise = make_golden.inputs("tiny")
+    xc, tc, nc = x.cuda(), t.cuda(), noise.cuda()
+    la = gd.p_losses(xc, tc, nc)
+    lb = gd.p_losses(xc, tc, nc)
+    with pytest.raises(RuntimeError, match="most recent forward"):
+        (la + lb).backward()
+    lc = gd.p_losses(xc, tc, nc)
+    gd.p_sample(xc, torch.full((xc.shape[0],), 5, device="cuda", dtype=torch.long))
+    with pytest.raises(RuntimeError, match="most recent forward"):
+        lc.backward()
+    ua = unet(xc.clone().requires_grad_(True), tc)
+    unet(xc, tc)                                   # inference forward in between (no grad needed: same engine buffers)
+    ub = unet(xc.clone().requires_grad_(True), tc)
+    with pytest.raises(RuntimeError, match="most recent forward"):
+        ua.sum().backward()
+    ub.sum().backward()                            # the latest one is fine
+    ld = gd.p_losses(xc, tc, nc)
+    ld.backward()

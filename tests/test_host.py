@@ -119,3 +119,38 @@ def test_schedule_helpers_and_betas_argument():
                                     timesteps=T, betas=lin)
         for k in O.SCHEDULE_KEYS:
             assert torch.equal(getattr(rgd, k), getattr(gd, k)), k
+
+
+def test_fused_adam_checkpoint_interchanges_with_torch_adam():
+    """FusedAdam.state_dict() is torch.optim.Adam's format (per-parameter exp_avg / exp_avg_sq / step), in the order of
+    ``denoising_model.parameters()`` the reference hands to Adam (ddpm.py:507): a checkpoint resumes under either."""
+    u = igm_b200.Unet(dim=32, channels=3, dim_mults=(1, 2))
+    opt = igm_b200.FusedAdam(u, lr=1e-4, betas=(0.9, 0.999))
+    g = torch.Generator().manual_seed(0)
+    opt._m = torch.randn(u._flat.numel(), generator=g)
+    opt._v = torch.rand(u._flat.numel(), generator=g)
+    opt._step = 17
+    sd = opt.state_dict()
+    # -> the reference's optimizer
+    ref_params = [torch.nn.Parameter(p.detach().clone()) for p in u.parameters()]
+    adam = torch.optim.Adam(ref_params, lr=1e-4, betas=(0.9, 0.999))
+    adam.load_state_dict(sd)
+    for (name, off, shape), p in zip(u._layout, ref_params):
+        st = adam.state[p]
+        assert float(st["step"]) == 17
+        assert torch.equal(st["exp_avg"].reshape(-1), opt._m[off:off + p.numel()]), name
+        assert torch.equal(st["exp_avg_sq"].reshape(-1), opt._v[off:off + p.numel()]), name
+    # <- a state the reference's optimizer produced
+    for p in ref_params:
+        p.grad = torch.randn(p.shape, generator=g)
+    adam.step()
+    opt2 = igm_b200.FusedAdam(u, lr=1e-4, betas=(0.9, 0.999))
+    opt2.load_state_dict(adam.state_dict())
+    assert opt2._step == 18
+    for (name, off, shape), p in zip(u._layout, ref_params):
+        assert torch.equal(opt2._m[off:off + p.numel()], adam.state[p]["exp_avg"].reshape(-1)), name
+        assert torch.equal(opt2._v[off:off + p.numel()], adam.state[p]["exp_avg_sq"].reshape(-1)), name
+    # a fresh optimizer's (empty) state loads as "no moments yet"
+    opt3 = igm_b200.FusedAdam(u)
+    opt3.load_state_dict(igm_b200.FusedAdam(u).state_dict())
+    assert opt3._m is None and opt3._step == 0

@@ -73,3 +73,30 @@ def test_oracle_adam_matches_torch():
         O.adam_step(p, g, m, v, step, 1e-2, 0.9, 0.999)
     for k in p:
         assert torch.allclose(p[k], q[k].detach(), rtol=1e-6, atol=1e-7)
+
+
+def test_oracle_full_chain_matches_reference_fixture():
+    """The full T = 1000 reverse chain of the oracle against the snapshots the unmodified reference produced
+    (tests/golden/make_golden_chain.py): after 1, 10, 100 and 1000 steps."""
+    import importlib.util
+    import os
+
+    import numpy as np
+
+    from tests._util import GOLDEN
+    spec_ = importlib.util.spec_from_file_location("make_golden_chain", os.path.join(GOLDEN, "make_golden_chain.py"))
+    mc = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(mc)
+    dim, ch, mults, H, W, B, T = mc.CASE
+    spec = O.UnetSpec(dim, ch, mults)
+    params = O.init_params(spec, seed=7)
+    buf = O.diffusion_buffers(T)
+    img, noise = mc.chain_inputs()
+    fix = dict(np.load(os.path.join(GOLDEN, "ddpm_chain_tiny.npz")))
+    done = 0
+    for n in mc.SNAPSHOTS:
+        img = O.p_sample_loop(params, spec, buf, img, noise[done:n], t_start=T - 1 - done, n_steps=n - done)
+        done = n
+        ref = torch.from_numpy(fix[f"after_{n}"])
+        err = (img - ref).abs().max().item()
+        assert err <= 1e-5 * max(ref.abs().max().item(), 1.0), f"after {n} steps: max abs diff {err:.3e}"

@@ -7,7 +7,11 @@ which gives size-independent properties:
   * the rows equal the CUDA path run on a small batch of the same samples (batch independence), and a repeat run of the
     inference forward reproduces the result;
   * the gradient of the batch-mean loss over 128 samples is the mean of the gradients over its four quarters,
-    and the loss the mean of their losses ("a checksum of checksums").
+    and the loss the mean of their losses ("a checksum of checksums");
+  * and, because the oracle is plain torch, parity proper at the FULL size with the oracle evaluated in fp64 ON THE
+    GPU (cuDNN / cuBLAS fp64, seconds instead of minutes): loss and every one of the 178 / 236 parameter gradients of the
+    batch-128 / batch-32 backward within 1e-3, plus the epoch-tail case (a batch smaller than the engine was planned for:
+    the reference loaders have no drop_last, src/datamodules/base.py:14-21; 50000 % 128 = 80).
 
 (The file name sorts last on purpose: these are the heaviest tests of the suite.)"""
 import pytest
@@ -15,11 +19,17 @@ import torch
 
 import igm_b200
 from oracle import ddpm_oracle as O
-from tests._util import REL_TOL, assert_close
+from tests._util import REL_TOL, assert_close, rel_err
 
 pytestmark = pytest.mark.gpu
 
 DIM, CH, T = 64, 3, 1000
+# Two correct fp32 evaluations of the same weight gradient that differ only in the ORDER of the fp32 additions over the
+# B*H*W <= 131072 pixel terms (split-K over a different number of CTAs, red.global.add arrival order, TMEM accumulation
+# chunks) agree to ~1e-4 of the tensor norm, not to fp32 epsilon: the terms cancel heavily, and the tensor core's fp32
+# accumulator truncates.  Measured on B200 (tools/diag_full_grad.py, profiles/r2_full_grad_diag.md) and far inside the
+# 1e-3 parity bound, which the fp64-arbiter tests below hold both sides to.
+GRAD_SUM_TOL = 5e-4
 CONFIGS = {
     # name: (dim_mults, H, W, batch per GPU)
     "cifar10_b128": ((1, 2, 4), 32, 32, 128),
@@ -48,6 +58,80 @@ def _inputs(cfg, seed=2024):
     t = torch.randint(0, T, (B,), generator=g)
     noise = torch.randn(B, CH, H, W, generator=g)
     return x, t, noise
+
+
+def _device_oracle_grads(params, spec, x, t, noise, loss_type="l2", dtype=torch.float64):
+    """loss and parameter gradients of the oracle evaluated on the GPU in `dtype` (the checker, not the product)."""
+    dev = torch.device("cuda")
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        p = {k: v.to(dev, dtype).requires_grad_(True) for k, v in params.items()}
+        buf = {k: v.to(dev) for k, v in O.diffusion_buffers(T).items()}
+        loss = O.p_losses(p, spec, buf, x.to(dev, dtype), t.to(dev), noise.to(dev, dtype), loss_type)
+        grads = torch.autograd.grad(loss, list(p.values()))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    return loss.item(), grads
+
+
+def _check_grads(unet, ref_grads, what):
+    bad, worst = [], 0.0
+    for (name, prm), rg in zip(unet.named_parameters(), ref_grads):
+        l2, mx = rel_err(prm.grad, rg)
+        worst = max(worst, l2, mx)
+        if l2 > REL_TOL or mx > REL_TOL:
+            bad.append((name, f"{l2:.2e}", f"{mx:.2e}"))
+    _report(f"{what}: worst per-tensor gradient error {worst:.2e} over {len(ref_grads)} tensors")
+    assert not bad, f"{what}: gradients outside 1e-3: {bad[:6]} ({len(bad)} tensors)"
+
+
+def _report(line):
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_report.txt"), "a") as f:
+            f.write(line + "\n")
+
+
+@pytest.mark.parametrize("cfg", list(CONFIGS))
+def test_full_batch_loss_and_gradients_match_fp64_oracle_on_device(cfg):
+    """Parity proper at BASELINE.json's full per-GPU size: one backward at B = 128 (CIFAR-10) / 32 (CelebA-64) against the
+    oracle in fp64 on the same GPU -- every parameter gradient within 1e-3 (rel-L2 and max-abs / max-ref)."""
+    spec, params, unet, gd = _build(cfg, "l2")
+    x, t, noise = _inputs(cfg, seed=99)
+    unet._flat_grad.zero_()
+    loss = gd.p_losses(x.cuda(), t.cuda(), noise.cuda())
+    loss.backward()
+    ref_loss, ref_grads = _device_oracle_grads(params, spec, x, t, noise)
+    assert abs(loss.item() - ref_loss) <= REL_TOL * abs(ref_loss)
+    _check_grads(unet, ref_grads, f"{cfg} full batch vs fp64")
+
+
+@pytest.mark.parametrize("b", [32, 80])
+def test_tail_batch_inside_an_engine_planned_for_128(b):
+    """The last batch of an epoch is smaller than the one the engine was planned for (50000 % 128 = 80): gradients of a
+    B < max_batch backward inside the batch-128 training engine against the fp64 oracle and against a fresh engine."""
+    cfg = "cifar10_b128"
+    spec, params, unet, gd = _build(cfg, "l2")
+    x, t, noise = _inputs(cfg, seed=99)
+    xc, tc, nc = x.cuda(), t.cuda(), noise.cuda()
+    gd.p_losses(xc, tc, nc).backward()                        # plans the engine for max_batch = 128
+    assert unet._engine.cfg.max_batch == 128
+    unet._flat_grad.zero_()
+    loss = gd.p_losses(xc[:b].contiguous(), tc[:b].contiguous(), nc[:b].contiguous())
+    loss.backward()
+    assert unet._engine.cfg.max_batch == 128
+    ref_loss, ref_grads = _device_oracle_grads(params, spec, x[:b], t[:b], noise[:b])
+    assert abs(loss.item() - ref_loss) <= REL_TOL * abs(ref_loss)
+    _check_grads(unet, ref_grads, f"B={b} inside the batch-128 engine vs fp64")
+    spec2, params2, unet2, gd2 = _build(cfg, "l2")
+    loss2 = gd2.p_losses(xc[:b].contiguous(), tc[:b].contiguous(), nc[:b].contiguous())
+    loss2.backward()
+    assert unet2._engine.cfg.max_batch == b
+    assert abs(loss2.item() - loss.item()) <= 1e-6 * abs(loss.item())
+    assert_close(unet._flat_grad, unet2._flat_grad, f"B={b}: batch-128 engine vs an engine planned for {b}", GRAD_SUM_TOL)
 
 
 @pytest.mark.parametrize("cfg", list(CONFIGS))
@@ -104,7 +188,14 @@ def test_full_batch_gradient_is_the_mean_of_its_quarters(cfg):
         losses.append(loss.item())
     g_quarters = unet._flat_grad.clone() / 4
     assert abs(sum(losses) / 4 - loss_full.item()) <= 1e-4 * abs(loss_full.item())
-    assert_close(g_quarters, g_full, "gradient of the batch mean vs mean of the quarter gradients", 1e-4)
+    assert_close(g_quarters, g_full, "gradient of the batch mean vs mean of the quarter gradients", GRAD_SUM_TOL)
+    # both sides against the fp64 oracle on the device: neither may sit outside the parity bound
+    _, ref_grads = _device_oracle_grads(params, spec, x, t, noise)
+    ref = torch.zeros_like(g_full, dtype=torch.float64)
+    for (name, off, shape), rg in zip(unet._layout, ref_grads):
+        ref[off:off + rg.numel()] = rg.reshape(-1)
+    assert_close(g_full, ref, "full-batch gradient arena vs fp64")
+    assert_close(g_quarters, ref, "mean of the quarter gradients vs fp64")
     # anchor to the oracle: the loss of the three subset samples, same engine, against the CPU restatement
     with torch.no_grad():
         buf = O.diffusion_buffers(T)
