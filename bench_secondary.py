@@ -275,6 +275,7 @@ def run_vqvae(args, dev, rank, world):
     B, S = args.batch, 128
     torch.manual_seed(0)
     model = build_vqvae(dev, S)
+    model.sync_parameters()
     opt = model.configure_optimizers()
     host = [(torch.rand(B, 3, S, S, generator=torch.Generator().manual_seed(100 * rank + i)) * 2 - 1).pin_memory() for i in range(8)]
     dev_b = [h.to(dev) for h in host]

@@ -42,6 +42,8 @@ SYMBOLS = {
     "igm_unet_pack_weights": (C.c_int, [_P, _P]),
     "igm_unet_forward": (C.c_int, [_P, _P, _P, _P, C.c_int, _P]),
     "igm_unet_backward": (C.c_int, [_P, _P, _P, _P]),
+    "igm_unet_grad_buckets": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]),
+    "igm_unet_bucket_wait": (C.c_int, [_P, C.c_int, _P]),
     "igm_ddpm_set_schedule": (C.c_int, [_P, C.POINTER(Schedule)]),
     "igm_ddpm_q_sample": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P]),
     "igm_ddpm_p_losses": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P]),

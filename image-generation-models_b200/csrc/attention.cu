@@ -424,16 +424,20 @@ __global__ void __launch_bounds__(256) linattn_mb_kernel(const float* __restrict
 
 }  // namespace
 
-// scratch layout: [B*heads] chunk counters (zero on entry, self re-arming) | [B*heads][32*32] dctx | chunk partials
-int linattn_ws_floats(int B, int n) { return B * kHeads * (64 + D * D + cdiv(n, CH) * PART); }
+// scratch layout: kCtrCap chunk counters (zero on entry, self re-arming) | [B*heads][32*32] dctx | chunk partials.
+// The counter block has a FIXED size: were it sized by the batch of the call, the dctx / partial regions of a small batch
+// would land on counters a later, larger batch of the same context expects to find zero.
+constexpr int kCtrCap = 8192;   // (batch, head) pairs: B <= 2048
+int linattn_ws_floats(int B, int n) { return kCtrCap + B * kHeads * (D * D + cdiv(n, CH) * PART); }
 
 int launch_linattn_forward(const LaunchCtx& lc, const float* qkv, float* out, float* ctx, float* kstat,
                            int B, int n, float* ws, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo) {
   const int nsplit = cdiv(n, CH);
   if (nsplit > kMaxSplit) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linear attention: more than 8192 pixels per image");
   ProfScope ps_(lc, K_ATTN, 4.0 * B * kHeads * (double)n * D * D, 4.0 * B * (double)n * (QKV + HD));
+  if (B * kHeads > kCtrCap) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linear attention: batch too large");
   unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
-  float* parts = ws + (int64_t)B * kHeads * (64 + D * D);
+  float* parts = ws + kCtrCap + (int64_t)B * kHeads * (D * D);
   { cudaError_t le_ = launch_pdl(linattn_ctx_kernel, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, parts, counters, ctx, kstat, n); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
   { cudaError_t le_ = launch_pdl(linattn_out_kernel, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, ctx, out, n, out_hi, out_lo); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
@@ -446,8 +450,9 @@ int launch_linattn_ctx(const LaunchCtx& lc, const float* qkv, float* ctx, float*
   const int nsplit = cdiv(n, CH);
   if (nsplit > kMaxSplit) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linear attention: more than 8192 pixels per image");
   ProfScope ps_(lc, K_ATTN, 2.0 * B * kHeads * (double)n * D * D, 4.0 * B * (double)n * 2 * HD);
+  if (B * kHeads > kCtrCap) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linear attention: batch too large");
   unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
-  float* parts = ws + (int64_t)B * kHeads * (64 + D * D);
+  float* parts = ws + kCtrCap + (int64_t)B * kHeads * (D * D);
   { cudaError_t le_ = launch_pdl(linattn_ctx_kernel, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, parts, counters, ctx, kstat, n); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
@@ -475,9 +480,10 @@ int launch_linattn_backward(const LaunchCtx& lc, const float* qkv, const float* 
   const int nsplit = cdiv(n, CH);
   if (nsplit > kMaxSplit) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linear attention: more than 8192 pixels per image");
   ProfScope ps_(lc, K_ATTN, 8.0 * B * kHeads * (double)n * D * D, 4.0 * B * (double)n * (2 * QKV + HD));
+  if (B * kHeads > kCtrCap) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linear attention: batch too large");
   unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
-  float* dctx = ws + (int64_t)B * kHeads * 64;
-  float* parts = ws + (int64_t)B * kHeads * (64 + D * D);
+  float* dctx = ws + kCtrCap;
+  float* parts = ws + kCtrCap + (int64_t)B * kHeads * (D * D);
   { cudaError_t le_ = launch_pdl(linattn_bwd_dctx_kernel, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, d_out, parts, counters, dctx, n); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
   { cudaError_t le_ = launch_pdl(linattn_bwd_rows_kernel, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, ctx, kstat, d_out, dctx, d_qkv, n, d_hi, d_lo); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }

@@ -287,9 +287,11 @@ int launch_time_mlp_forward(const LaunchCtx& lc, const TimeMlpParams& p, const i
                             float* emb, float* h1, float* temb, float* act);
 int launch_time_proj_forward(const LaunchCtx& lc, const TimeProj* d_table, int n_proj, const float* act,
                              int dim, int B, int total, float* proj);
-int launch_time_backward(const LaunchCtx& lc, const TimeMlpParams& p, const TimeProj* d_table, int n_proj,
-                         int total, int B, const float* emb, const float* h1, const float* temb,
-                         const float* act, const float* d_proj, float* ws /* [B, 10d]: d_temb, d_h1, d_act accumulator (zero), mish(h1) */);
+// ws: [Bcap, 10 d] floats, layout fixed by the PLANNED batch Bcap (see time_mlp.cu); d_act accumulator zero between passes
+int launch_time_proj_backward(const LaunchCtx& lc, const TimeMlpParams& p, const TimeProj* d_table, int n_proj, int total,
+                              int B, int Bcap, const float* act, const float* d_proj, float* ws, int slab_lo, int slab_hi);
+int launch_time_mlp_backward(const LaunchCtx& lc, const TimeMlpParams& p, int B, int Bcap, const float* emb, const float* h1,
+                             const float* temb, float* ws);
 
 // ---------------------------------------------------------------------------
 // boundary + diffusion elementwise (diffusion.cu)

@@ -7,6 +7,7 @@
 // LayerNorm (:85-95) and their autograd.
 #include "common.cuh"
 
+#include <algorithm>
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
@@ -442,6 +443,179 @@ __global__ void __launch_bounds__(256) gn_bwd_fused_kernel(const GnBwdArgs a, in
   }
   // per-channel sums: fold the pixel slots of the CTA, then the CTAs of the cluster (rank 0), then one atomic per
   // (sample, channel) -- dtemb is per sample and written directly
+  sc[threadIdx.x][0] = make_float4(dgam[0], dgam[1], dgam[2], dgam[3]);
+  sc[threadIdx.x][1] = make_float4(dbet[0], dbet[1], dbet[2], dbet[3]);
+  sc[threadIdx.x][2] = make_float4(dte[0], dte[1], dte[2], dte[3]);
+  sc[threadIdx.x][3] = make_float4(dbs[0], dbs[1], dbs[2], dbs[3]);
+  __syncthreads();
+  float4 acc[4];
+  if (threadIdx.x < ly.L) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = sc[threadIdx.x][k];
+    for (int sl = 1; sl < ly.PPI; ++sl) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 v = sc[sl * ly.L + threadIdx.x][k];
+        acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < ly.L) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sc[threadIdx.x][k] = acc[k];
+  }
+  cluster.sync();
+  if (rank == 0 && threadIdx.x < ly.L) {
+    for (int r = 1; r < cs; ++r) {
+      const float4* rs = cluster.map_shared_rank(&sc[0][0], r) + threadIdx.x * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 v = rs[k];
+        acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+      }
+    }
+    atomicAdd(a.dgamma + c + 0, acc[0].x); atomicAdd(a.dgamma + c + 1, acc[0].y);
+    atomicAdd(a.dgamma + c + 2, acc[0].z); atomicAdd(a.dgamma + c + 3, acc[0].w);
+    atomicAdd(a.dbeta + c + 0, acc[1].x); atomicAdd(a.dbeta + c + 1, acc[1].y);
+    atomicAdd(a.dbeta + c + 2, acc[1].z); atomicAdd(a.dbeta + c + 3, acc[1].w);
+    if (a.dtemb) *reinterpret_cast<float4*>(a.dtemb + (int64_t)b * a.dtemb_stride + c) = acc[2];
+    if (a.dout_colsum) {
+      atomicAdd(a.dout_colsum + c + 0, acc[2].x); atomicAdd(a.dout_colsum + c + 1, acc[2].y);
+      atomicAdd(a.dout_colsum + c + 2, acc[2].z); atomicAdd(a.dout_colsum + c + 3, acc[2].w);
+    }
+    if (a.dbias) {
+      atomicAdd(a.dbias + c + 0, acc[3].x); atomicAdd(a.dbias + c + 1, acc[3].y);
+      atomicAdd(a.dbias + c + 2, acc[3].z); atomicAdd(a.dbias + c + 3, acc[3].w);
+    }
+  }
+  cluster.sync();   // remote shared memory stays valid until rank 0 has read it
+}
+
+// ---- backward, fused, bulk-staged variant (default) -------------------------------------------------------------
+// Same decomposition as gn_bwd_fused_kernel (one cluster per sample, group sums through distributed shared memory), but a
+// CTA's slice of y and d_out -- E = nv * 1024 consecutive floats each, NHWC pixels are contiguous -- is brought in by TWO
+// 1-D bulk async copies (cp.async.bulk, one elected thread, completion on an mbarrier) into shared memory instead of 2 * nv
+// float4 registers per thread.  The register version needed 128 registers (two CTAs per SM) and ran its load / reduce /
+// cluster-barrier / store phases in lock step: ncu showed it barrier-stalled at 22 % occupancy and 31 % of the HBM rate.
+// Here a thread keeps ~50 registers, three CTAs fit an SM (64 KB tiles), and the copies of one CTA overlap the compute
+// and barrier phases of its neighbours.  n and dn are written back to the thread's own tile slots after pass 1, so pass 2
+// does not recompute the Mish derivative.
+__device__ __forceinline__ void bulk_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(dst_smem)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(256) gn_bwd_bulk_kernel(const GnBwdArgs a, int cs, int nv) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(128) float tile[];   // y slice [E] | d_out slice [E]; later the per-thread channel partials
+  __shared__ float sm[256][2];
+  __shared__ float cl_grp[kGroups][2];    // this CTA's (sum dn, sum dn*n) per group, read by the whole cluster
+  __shared__ float s_m[kGroups][2];
+  __shared__ __align__(8) uint64_t bar;
+  const int E = nv * 1024;
+  float* ty = tile;
+  float* td = tile + E;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  pdl_wait();
+  const GnLayout ly(a.C);
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.x / cs;
+  const int npix = a.HW / cs;             // pixels of this CTA: nv * PPI
+  const int p0 = rank * npix;
+  const int64_t cta_base = ((int64_t)b * a.HW + p0) * a.C;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&bar)),
+                 "r"((uint32_t)(2 * E * sizeof(float)))
+                 : "memory");
+    bulk_load_1d(ty, a.y + cta_base, (uint32_t)(E * sizeof(float)), &bar);
+    bulk_load_1d(td, a.d_out + cta_base, (uint32_t)(E * sizeof(float)), &bar);
+  }
+  const float mean = __ldg(a.stats + ((int64_t)b * kGroups + ly.group) * 2 + 0);
+  const float rstd = __ldg(a.stats + ((int64_t)b * kGroups + ly.group) * 2 + 1);
+  const int c = ly.c4 * 4;
+  const float4 ga4 = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
+  const float4 be4 = __ldg(reinterpret_cast<const float4*>(a.beta + c));
+  const float ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w};
+  const float be[4] = {be4.x, be4.y, be4.z, be4.w};
+  const int loc0 = ly.pslot * a.C + c;    // this thread's first float inside the tile
+  const int lstep = ly.PPI * a.C;
+  const int64_t base = cta_base + loc0;
+  {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(done)
+          : "r"((uint32_t)__cvta_generic_to_shared(&bar))
+          : "memory");
+    }
+  }
+  float dgam[4] = {0.f, 0.f, 0.f, 0.f}, dbet[4] = {0.f, 0.f, 0.f, 0.f}, dte[4] = {0.f, 0.f, 0.f, 0.f};
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll 2
+  for (int i = 0; i < nv; ++i) {
+    float4 y4 = *reinterpret_cast<const float4*>(ty + loc0 + i * lstep);
+    float4 d4 = *reinterpret_cast<const float4*>(td + loc0 + i * lstep);
+    if (a.dout_hi) store_split4(a.dout_hi, a.dout_lo, base + (int64_t)i * lstep, d4);
+    float* yv = reinterpret_cast<float*>(&y4);
+    float* dv = reinterpret_cast<float*>(&d4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float n = (yv[j] - mean) * rstd;
+      const float g = n * ga[j] + be[j];
+      const float dg = dv[j] * mish_grad_f(g);
+      dgam[j] += dg * n;
+      dbet[j] += dg;
+      dte[j] += dv[j];
+      const float dn = dg * ga[j];
+      s1 += dn;
+      s2 += dn * n;
+      yv[j] = n;
+      dv[j] = dn;
+    }
+    *reinterpret_cast<float4*>(ty + loc0 + i * lstep) = y4;   // own slots only: no barrier needed before pass 2
+    *reinterpret_cast<float4*>(td + loc0 + i * lstep) = d4;
+  }
+  float r1, r2;
+  group_reduce2(ly, s1, s2, sm, r1, r2);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { cl_grp[w][0] = r1; cl_grp[w][1] = r2; }
+  cluster.sync();
+  if (threadIdx.x < kGroups * 2) {
+    const int g = threadIdx.x >> 1, k = threadIdx.x & 1;
+    float t = 0.f;
+    for (int r = 0; r < cs; ++r) t += cluster.map_shared_rank(&cl_grp[0][0], r)[g * 2 + k];   // fixed order
+    s_m[g][k] = t / ((float)a.HW * ly.cpg);
+  }
+  __syncthreads();
+  const float m1 = s_m[ly.group][0], m2 = s_m[ly.group][1];
+  float dbs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+  for (int i = 0; i < nv; ++i) {
+    const float4 n = *reinterpret_cast<const float4*>(ty + loc0 + i * lstep);
+    const float4 dn = *reinterpret_cast<const float4*>(td + loc0 + i * lstep);
+    float4 o;
+    o.x = rstd * (dn.x - m1 - n.x * m2);
+    o.y = rstd * (dn.y - m1 - n.y * m2);
+    o.z = rstd * (dn.z - m1 - n.z * m2);
+    o.w = rstd * (dn.w - m1 - n.w * m2);
+    dbs[0] += o.x; dbs[1] += o.y; dbs[2] += o.z; dbs[3] += o.w;
+    const int64_t off = base + (int64_t)i * lstep;
+    if (a.dy) *reinterpret_cast<float4*>(a.dy + off) = o;
+    if (a.dy_hi) store_split4(a.dy_hi, a.dy_lo, off, o);
+  }
+  // per-channel sums: fold the pixel slots of the CTA, then the CTAs of the cluster (rank 0), then one atomic per
+  // (sample, channel) -- dtemb is per sample and written directly.  The tile is dead now: it holds the partials.
+  __syncthreads();
+  float4 (*sc)[4] = reinterpret_cast<float4 (*)[4]>(tile);
   sc[threadIdx.x][0] = make_float4(dgam[0], dgam[1], dgam[2], dgam[3]);
   sc[threadIdx.x][1] = make_float4(dbet[0], dbet[1], dbet[2], dbet[3]);
   sc[threadIdx.x][2] = make_float4(dte[0], dte[1], dte[2], dte[3]);
@@ -973,6 +1147,22 @@ int launch_gn_backward(const LaunchCtx& lc, const GnBwdArgs& a) {
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e;
+    static const bool bulk = [] { const char* v = getenv("IGM_GN_BULK"); return !(v && v[0] == '0'); }();
+    // bulk copies need 16-byte aligned sources: every tensor comes from the 256-byte aligned arena, slices are 4 KB multiples
+    if (bulk && ((reinterpret_cast<uintptr_t>(a.y) | reinterpret_cast<uintptr_t>(a.d_out)) & 15) == 0) {
+      const int smem = std::max(2 * nv * 1024 * (int)sizeof(float), 256 * 4 * (int)sizeof(float4));
+      static bool attr_set = false;
+      if (!attr_set) {
+        e = cudaFuncSetAttribute(gn_bwd_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(e));
+        attr_set = true;
+      }
+      cfg.dynamicSmemBytes = (size_t)smem;
+      e = cudaLaunchKernelEx(&cfg, gn_bwd_bulk_kernel, a, cs, nv);
+      if (e != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(e));
+      IGM_POST_LAUNCH(lc);
+      return IGM_OK;
+    }
     switch (nv) {
       case 1: e = cudaLaunchKernelEx(&cfg, gn_bwd_fused_kernel<1>, a, cs); break;
       case 2: e = cudaLaunchKernelEx(&cfg, gn_bwd_fused_kernel<2>, a, cs); break;

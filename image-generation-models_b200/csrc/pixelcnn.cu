@@ -61,30 +61,60 @@ struct PcnnArgs {
   int normalize;             // pixel value k/255 (0) or 2k/255 - 1 (1)
 };
 
-// y[n] = bias[n] + extra[n] + sum_k Wt[k][n] * x[k]   for n < N (N <= 256 per call), all 256 threads
+// y[n] = bias[n] + extra[n] + sum_k Wt[k][n] * x[k]   for n < N (N = 64, 128 or 256 per call), all 256 threads.
+// The per-pixel chain of 22 dependent GEMVs is bound by the latency of the weight loads (the matrices stream from L2:
+// 901 KB per pixel step do not fit shared memory), so the loads are made wide and independent: a thread owns FOUR
+// adjacent outputs and one K slice (N/4 threads per slice, 256 / (N/4) slices), i.e. K * N / 1024 <= 16 128-bit loads,
+// all in flight before the first FMA.  Slice partials are summed in a fixed order (deterministic).
 __device__ __forceinline__ void cta_gemv(const float* __restrict__ Wt, const float* __restrict__ bias,
                                          const float* __restrict__ extra, const float* x_s, int K, int N,
-                                         float* red_s /*[256]*/, float* y_s) {
+                                         float* red_s /*[1024]*/, float* y_s) {
   const int tid = threadIdx.x;
-  int parts = 256 / N;
-  if (parts < 1) parts = 1;
-  const int n = tid % N, part = tid / N;
-  float acc = 0.f;
-  if (part < parts && tid < parts * N) {
-    const int kb = (K * part) / parts, ke = (K * (part + 1)) / parts;
-    const float* wp = Wt + (int64_t)kb * N + n;
-#pragma unroll 8
-    for (int k = kb; k < ke; ++k) {
-      acc = fmaf(__ldg(wp), x_s[k], acc);
-      wp += N;
+  const int n4 = N >> 2;                 // threads per K slice
+  const int parts = 256 / n4;            // K slices
+  const int part = tid / n4, q = tid - part * n4;
+  const int klen = K / parts;            // K, N are powers of two >= 64: divides exactly
+  const int kb = part * klen;
+  const float4* wp = reinterpret_cast<const float4*>(Wt + (int64_t)kb * N) + q;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (klen >= 16) {
+    for (int k0 = 0; k0 < klen; k0 += 16) {
+      float4 wv[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) wv[k] = __ldg(wp + (int64_t)(k0 + k) * n4);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float x = x_s[kb + k0 + k];
+        acc.x = fmaf(wv[k].x, x, acc.x); acc.y = fmaf(wv[k].y, x, acc.y);
+        acc.z = fmaf(wv[k].z, x, acc.z); acc.w = fmaf(wv[k].w, x, acc.w);
+      }
+    }
+  } else if (klen >= 4) {
+    for (int k0 = 0; k0 < klen; k0 += 4) {
+      float4 wv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) wv[k] = __ldg(wp + (int64_t)(k0 + k) * n4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float x = x_s[kb + k0 + k];
+        acc.x = fmaf(wv[k].x, x, acc.x); acc.y = fmaf(wv[k].y, x, acc.y);
+        acc.z = fmaf(wv[k].z, x, acc.z); acc.w = fmaf(wv[k].w, x, acc.w);
+      }
+    }
+  } else {
+    for (int k = 0; k < klen; ++k) {
+      const float4 wv = __ldg(wp + (int64_t)k * n4);
+      const float x = x_s[kb + k];
+      acc.x = fmaf(wv.x, x, acc.x); acc.y = fmaf(wv.y, x, acc.y);
+      acc.z = fmaf(wv.z, x, acc.z); acc.w = fmaf(wv.w, x, acc.w);
     }
   }
-  red_s[tid] = acc;
+  *reinterpret_cast<float4*>(red_s + part * N + q * 4) = acc;
   __syncthreads();
   if (tid < N) {
     float s = bias ? __ldg(bias + tid) : 0.f;
     if (extra) s += extra[tid];
-    for (int q = 0; q < parts; ++q) s += red_s[q * N + tid];
+    for (int p = 0; p < parts; ++p) s += red_s[p * N + tid];
     y_s[tid] = s;
   }
   __syncthreads();
@@ -109,6 +139,7 @@ __device__ __forceinline__ void cta_row_gemm(const float* __restrict__ Wt, const
       if (!row) continue;
       const int sh = shift[t];
       const float* wp = Wt + ((int64_t)t * Kc) * N + n;
+#pragma unroll 4
       for (int c4 = 0; c4 < Kc; c4 += 4) {
         const float w0v = __ldg(wp + (int64_t)(c4 + 0) * N), w1v = __ldg(wp + (int64_t)(c4 + 1) * N);
         const float w2v = __ldg(wp + (int64_t)(c4 + 2) * N), w3v = __ldg(wp + (int64_t)(c4 + 3) * N);
@@ -157,8 +188,8 @@ __global__ void __launch_bounds__(256) pixelcnn_kernel(const PcnnArgs a) {
   float* t_s = vc_s + W * N2;               // [W][2Hd]     scratch row (v2h result / gated row)
   float* x_s = t_s + W * N2;                // [2Hd]        gemv input
   float* y_s = x_s + N2;                    // [256]        gemv output
-  float* red_s = y_s + 256;                 // [256]
-  float* cur_s = red_s + 256;               // [Hd]         running h-stack column
+  float* red_s = y_s + 256;                 // [1024]       K-slice partials of a gemv
+  float* cur_s = red_s + 1024;              // [Hd]         running h-stack column
   float* lg_s = cur_s + Hd;                 // [256]        logits of one channel
   __shared__ int s_pick;
 
@@ -284,6 +315,7 @@ __global__ void __launch_bounds__(256) pixelcnn_kernel(const PcnnArgs a) {
         {
           float s = __ldg(Wt + a.off.out_b + (int64_t)tid * C + ch);
           const float* wp = Wt + a.off.out_w + (int64_t)tid * C + ch;
+#pragma unroll 16
           for (int k = 0; k < Hd; ++k) s = fmaf(__ldg(wp + (int64_t)k * 256 * C), x_s[k], s);
           lg_s[tid] = s;
           if (a.logits) a.logits[((((int64_t)n_img * 256 + tid) * C + ch) * H + h) * W + w] = s;
@@ -376,7 +408,7 @@ extern "C" int igm_pixelcnn_run(const float* weights, float* img, const float* u
   a.img = img; a.uniforms = uniforms; a.skip = skip; a.cond = cond; a.logits = logits; a.ws = ws;
   a.ws_per_img = igm_pixelcnn_workspace_floats(1, C, H, W, Hd);
   a.seed = seed; a.N = N; a.C = C; a.H = H; a.W = W; a.Hd = Hd; a.mode = mode; a.normalize = normalize;
-  const size_t smem = sizeof(float) * ((size_t)2 * W * Hd + (size_t)2 * W * 2 * Hd + 2 * Hd + 256 + 256 + Hd + 256);
+  const size_t smem = sizeof(float) * ((size_t)2 * W * Hd + (size_t)2 * W * 2 * Hd + 2 * Hd + 256 + 1024 + Hd + 256);
   cudaError_t e = cudaFuncSetAttribute(pixelcnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) IGM_FAIL(st, IGM_ERR_CUDA, cudaGetErrorString(e));
   pixelcnn_kernel<<<N, 256, smem, (cudaStream_t)stream>>>(a);

@@ -119,13 +119,14 @@ __global__ void __launch_bounds__(256) time_proj_fwd_kernel(const TimeProj* __re
 //     * its share of d_act[b][k] += sum_c dproj[b][c] * W[c][k]  (fp32 atomics into a zeroed accumulator)
 __global__ void __launch_bounds__(256) time_proj_bwd_kernel(const TimeProj* __restrict__ table, int n_proj,
                                                             const float* __restrict__ act, int dim, int B, int total,
-                                                            const float* __restrict__ d_proj, float* __restrict__ d_act) {
+                                                            const float* __restrict__ d_proj, float* __restrict__ d_act,
+                                                            int slab0) {
   extern __shared__ __align__(16) float ws[];   // W[32][dim+1] | act[32][dim+1] | dp[32 samples][33]
   float* s_act = ws + 32 * (dim + 1);
   float* s_dp = s_act + 32 * (dim + 1);
   TimeProj tp;
   int c0;
-  if (!find_slab(table, n_proj, blockIdx.x, tp, c0)) return;
+  if (!find_slab(table, n_proj, blockIdx.x + slab0, tp, c0)) return;
   const int b0 = blockIdx.y * kProjSamples;
   for (int i = threadIdx.x; i < 32 * dim; i += blockDim.x) {
     const int c = i / dim, k = i - c * dim;
@@ -253,21 +254,39 @@ int launch_time_proj_forward(const LaunchCtx& lc, const TimeProj* d_table, int n
   return IGM_OK;
 }
 
-int launch_time_backward(const LaunchCtx& lc, const TimeMlpParams& p, const TimeProj* d_table, int n_proj,
-                         int total, int B, const float* emb, const float* h1, const float* temb,
-                         const float* act, const float* d_proj, float* ws) {
-  const int d = p.dim, d4 = 4 * p.dim;
+// Backward of the per-block time projections for the 32-channel slabs [slab_lo, slab_hi) of the projection table (all of
+// them when slab_hi < 0): parameter gradients of those blocks + their share of d_act (accumulated; the accumulator is
+// zero on entry of a backward pass and re-zeroed by launch_time_mlp_backward).  Split by slab range so that the
+// gradients of a block group are final as soon as the backward pass has left that group (gradient buckets, unet.cu).
+// Workspace layout ([Bcap, 10 d] floats, Bcap = the batch the context was planned for, NOT the batch of this call: the
+// accumulator must sit at the same address whatever batch runs, or a smaller batch's d_temb / d_h1 would land on
+// accumulator rows a later, larger batch expects to find zero -- the epoch-tail batch of a loader without drop_last):
+//   d_act [Bcap, d] (accumulator, zero between backward passes) | d_temb [Bcap, d] | d_h1 [Bcap, 4d] | mish(h1) [Bcap, 4d]
+int launch_time_proj_backward(const LaunchCtx& lc, const TimeMlpParams& p, const TimeProj* d_table, int n_proj, int total,
+                              int B, int Bcap, const float* act, const float* d_proj, float* ws, int slab_lo, int slab_hi) {
+  const int d = p.dim;
   if (d % 32 != 0) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "time_mlp: dim must be a multiple of 32");
-  float* d_temb = ws;
-  float* d_h1 = d_temb + (int64_t)B * d;
-  float* d_act = d_h1 + (int64_t)B * d4;   // accumulator: zero on entry, re-zeroed by time_bwd_sample_kernel
-  float* a1 = d_act + (int64_t)B * d;
-  const int slabs = total / 32;
-  ProfScope ps_(lc, K_TIME, 6.0 * B * d * total, 0.0);
+  if (B > Bcap) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "time_mlp: batch exceeds the planned batch");
+  float* d_act = ws;
+  if (slab_hi < 0) { slab_lo = 0; slab_hi = total / 32; }
+  if (slab_hi <= slab_lo) return IGM_OK;
+  ProfScope ps_(lc, K_TIME, 6.0 * B * d * 32.0 * (slab_hi - slab_lo), 0.0);
   const size_t smem = (size_t)(2 * 32 * (d + 1) + 32 * 33) * sizeof(float);
-  time_proj_bwd_kernel<<<dim3(slabs, cdiv(B, kProjSamples)), 256, smem, lc.stream>>>(d_table, n_proj, act, d, B, total,
-                                                                                       d_proj, d_act);
+  time_proj_bwd_kernel<<<dim3(slab_hi - slab_lo, cdiv(B, kProjSamples)), 256, smem, lc.stream>>>(d_table, n_proj, act, d, B, total,
+                                                                                                 d_proj, d_act, slab_lo);
   IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+// The time MLP itself (Linear -> Mish -> Linear, ddpm.py:188-193), after EVERY projection slab has added its d_act share.
+int launch_time_mlp_backward(const LaunchCtx& lc, const TimeMlpParams& p, int B, int Bcap, const float* emb, const float* h1,
+                             const float* temb, float* ws) {
+  const int d = p.dim, d4 = 4 * p.dim;
+  float* d_act = ws;                           // accumulator: zero on entry, re-zeroed by time_bwd_sample_kernel
+  float* d_temb = d_act + (int64_t)Bcap * d;
+  float* d_h1 = d_temb + (int64_t)Bcap * d;
+  float* a1 = d_h1 + (int64_t)Bcap * d4;
+  ProfScope ps_(lc, K_TIME, 4.0 * B * d * d4 * 2, 0.0);
   time_bwd_sample_kernel<<<B, 256, d * sizeof(float), lc.stream>>>(p, h1, temb, d_act, d_temb, d_h1, a1);
   IGM_POST_LAUNCH(lc);
   const int tiles = 2 * (d / 32) * (d4 / 32);

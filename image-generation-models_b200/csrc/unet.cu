@@ -244,6 +244,16 @@ struct igm_ctx {
   cudaEvent_t ev_wr = nullptr, ev_join = nullptr, ev_rd[kDyBufs] = {nullptr, nullptr, nullptr};
   bool rd_pending[kDyBufs] = {false, false, false};
   bool side_dirty = false;
+  // gradient buckets (igm_unet_grad_buckets): contiguous ranges of the gradient arena in the order the backward pass
+  // completes them; ev_bk_main / ev_bk_side mark "every kernel that writes bucket k has been enqueued" on the caller's /
+  // the side stream, so an all-reduce of bucket k can start while the backward pass continues (igm_unet_bucket_wait)
+  static constexpr int kMaxBuckets = IGM_MAX_MULTS + 2;
+  int n_buckets = 0;
+  int64_t bucket_lo[kMaxBuckets] = {}, bucket_hi[kMaxBuckets] = {};
+  int bucket_slab_lo[kMaxBuckets] = {}, bucket_slab_hi[kMaxBuckets] = {};
+  cudaEvent_t ev_bk_main[kMaxBuckets] = {}, ev_bk_side[kMaxBuckets] = {};
+  bool bk_side_rec[kMaxBuckets] = {};
+  bool bk_valid = false;
   cudaEvent_t ev_ln = nullptr;   // side stream has folded the LayerNorm partials workspace (ws_ln may be overwritten)
   bool ln_pending = false;
   bool fin_per_layer = false;    // this backward folded the halo workspaces layer by layer (no finalize pass at the end)
@@ -883,6 +893,27 @@ struct Runner {
     time_done = true;
     return IGM_OK;
   }
+  // The backward pass has left parameter group k (igm_unet_grad_buckets): run the group's time-projection parameter
+  // gradients (their d(temb) are complete now) and mark the bucket's gradients as final on both streams.
+  int bucket_done(int k) {
+    if (k < 0 || k >= c.n_buckets) return IGM_OK;
+    if (k + 1 < c.n_buckets) {   // the last group's slabs run with the time MLP itself (time_backward)
+      TimeMlpParams tp;
+      time_params(tp);
+      LaunchCtx sl;
+      IGM_TRY(side_begin(sl));
+      IGM_TRY(launch_time_proj_backward(sl, tp, c.proj_dev, c.n_proj, c.proj_total, B, c.cfg.max_batch, c.t_act, c.t_dproj, c.t_ws,
+                                        c.bucket_slab_lo[k], c.bucket_slab_hi[k]));
+      if (sl.stream != lc.stream) c.side_dirty = true;
+    }
+    IGM_CUDA(c.st, cudaEventRecord(c.ev_bk_main[k], lc.stream));
+    c.bk_side_rec[k] = false;
+    if (side_active() && c.side_dirty) {
+      IGM_CUDA(c.st, cudaEventRecord(c.ev_bk_side[k], c.side));
+      c.bk_side_rec[k] = true;
+    }
+    return IGM_OK;
+  }
   // d_out = r.out.g ; writes d_in0 / d_in1 unless null
   int resnet_bwd(ResnetL& r, float* d0, float* d1) {
     const int H = r.H, W = r.W;
@@ -1035,15 +1066,20 @@ struct Runner {
   int time_backward(const LaunchCtx& l) {
     TimeMlpParams tp;
     time_params(tp);
-    return launch_time_backward(l, tp, c.proj_dev, c.n_proj, c.proj_total, B, c.t_emb, c.t_h1, c.t_temb, c.t_act,
-                                c.t_dproj, c.t_ws);
+    // the earlier groups' projection slabs ran in bucket_done(); the last group's (time_mlp + downs.0) and the MLP here
+    const int last = c.n_buckets - 1;
+    IGM_TRY(launch_time_proj_backward(l, tp, c.proj_dev, c.n_proj, c.proj_total, B, c.cfg.max_batch, c.t_act, c.t_dproj, c.t_ws,
+                                      c.bucket_slab_lo[last], c.bucket_slab_hi[last]));
+    return launch_time_mlp_backward(l, tp, B, c.cfg.max_batch, c.t_emb, c.t_h1, c.t_temb, c.t_ws);
   }
 
   int backward(const float* d_pred, float* d_x_nhwc) {
     const igm_unet_cfg& cfg = c.cfg;
     const int nres = cfg.n_mults;
-    time_after = side_active() ? &c.downs[0].r1 : nullptr;
+    const bool side_was_active = side_active();
+    time_after = side_was_active ? &c.downs[0].r1 : nullptr;
     time_done = false;
+    c.bk_valid = false;
     const int H0 = cfg.height, W0 = cfg.width;
     // final 1x1: W[c][k]
     {
@@ -1080,6 +1116,7 @@ struct Runner {
       IGM_TRY(resnet_bwd(c.mid1, last.attn.out.g, nullptr));
       if (nres > 1) IGM_TRY(launch_add(lc, last.attn.out.g, c.skip_g[nres - 1], M(last.attn.H, last.attn.W) * last.attn.C));
     }
+    IGM_TRY(bucket_done(0));                                     // ups.*, mid_*, final_conv.*
     for (int i = nres - 1; i >= 0; --i) {
       Stage& s = c.downs[i];
       // h[0] is never consumed by the up path (ddpm.py:254-259): no skip gradient for stage 0
@@ -1087,6 +1124,7 @@ struct Runner {
       IGM_TRY(attn_bwd(s.attn, s.r2.out.g));
       IGM_TRY(resnet_bwd(s.r2, s.r1.out.g, nullptr));
       IGM_TRY(resnet_bwd(s.r1, i > 0 ? s.r1.in0->g : d_x_nhwc, nullptr));
+      if (i > 0) IGM_TRY(bucket_done(nres - i));                 // downs.i
     }
     if (!time_done) IGM_TRY(time_backward(lc));
     time_done = false;
@@ -1095,6 +1133,13 @@ struct Runner {
     const bool fin_done = c.fin_per_layer;   // every halo layer was folded right behind its wgrad on the side stream
     c.fin_per_layer = false;
     if (tc_on() && c.halo_on && !fin_done) IGM_TRY(launch_wgrad_halo_finalize(lc, c.fin_dev, c.fin_cta_dev, c.fin_n > 0 ? c.fin_tiles : 0, c.fin_elems));
+    // the last bucket (time_mlp.*, downs.0.*) is final here; so is every bucket when the side stream was off (the halo
+    // workspaces were folded by the pass above, not layer by layer)
+    for (int k = side_was_active ? c.n_buckets - 1 : 0; k < c.n_buckets; ++k) {
+      IGM_CUDA(c.st, cudaEventRecord(c.ev_bk_main[k], lc.stream));
+      c.bk_side_rec[k] = false;
+    }
+    c.bk_valid = true;
     return IGM_OK;
   }
 };
@@ -1167,6 +1212,28 @@ static void wire_plan(igm_ctx* c) {
   }
   c->final_in = cur;
   c->final_block.conv.src0 = cur;
+}
+
+// Gradient buckets in the order Runner::backward completes them.  The arena is laid out in state_dict order
+// (time_mlp | downs.0 .. downs.n-1 | ups.* | mid_* | final_conv.*), the backward pass walks final_conv, ups, mid, then
+// downs.n-1 .. downs.0 and the time MLP: bucket 0 = [ups.0 (or mid_block1) .. end), bucket k = downs.(n-k), last =
+// [0 .. downs.1) = time_mlp + downs.0.
+static void plan_buckets(igm_ctx* c) {
+  const int nres = c->cfg.n_mults;
+  auto poff = [&](int idx) { return c->params[idx].offset; };
+  const ResnetL& head0 = c->ups.empty() ? c->mid1 : c->ups[0].r1;
+  int k = 0;
+  c->bucket_lo[k] = poff(head0.mlp_w); c->bucket_hi[k] = c->param_elems;
+  c->bucket_slab_lo[k] = head0.temb_off / 32; c->bucket_slab_hi[k] = c->proj_total / 32;
+  ++k;
+  for (int i = nres - 1; i >= 1; --i, ++k) {
+    c->bucket_lo[k] = poff(c->downs[i].r1.mlp_w); c->bucket_hi[k] = c->bucket_lo[k - 1];
+    c->bucket_slab_lo[k] = c->downs[i].r1.temb_off / 32;
+    c->bucket_slab_hi[k] = (c->downs[i].r2.temb_off + c->downs[i].r2.Cout) / 32;
+  }
+  c->bucket_lo[k] = 0; c->bucket_hi[k] = c->bucket_lo[k - 1];
+  c->bucket_slab_lo[k] = 0; c->bucket_slab_hi[k] = (c->downs[0].r2.temb_off + c->downs[0].r2.Cout) / 32;
+  c->n_buckets = k + 1;
 }
 
 // Slots of the dY staging ring, handed out round-robin in the order Runner::backward visits the convs, so that
@@ -1359,6 +1426,7 @@ int igm_unet_create(igm_ctx** out, const igm_unet_cfg* cfg, int device) {
   build_plan(c, c->arena, &floats2);
   wire_plan(c);
   assign_dy_slots(c);
+  plan_buckets(c);
   // tensor-core engine: on by default when the shapes allow it (IGM_CONV_ENGINE=0 forces the SIMT engine)
   if (const char* ps = getenv("IGM_PREFER_SHARED")) {
     if (ps[0] == '1') cudaDeviceSetCacheConfig(cudaFuncCachePreferShared);
@@ -1384,6 +1452,19 @@ int igm_unet_create(igm_ctx** out, const igm_unet_cfg* cfg, int device) {
     if (se == cudaSuccess) se = cudaEventCreateWithFlags(&c->ev_ln, cudaEventDisableTiming);
     for (int k = 0; k < igm_ctx::kDyBufs && se == cudaSuccess; ++k)
       se = cudaEventCreateWithFlags(&c->ev_rd[k], cudaEventDisableTiming);
+
+    if (se != cudaSuccess) {
+      set_error(st, IGM_ERR_CUDA, __FILE__, __LINE__, cudaGetErrorString(se));
+      igm_unet_destroy(c);
+      return st.code;
+    }
+  }
+  if (c->cfg.training) {
+    cudaError_t se = cudaSuccess;
+    for (int k = 0; k < c->n_buckets && se == cudaSuccess; ++k) {
+      se = cudaEventCreateWithFlags(&c->ev_bk_main[k], cudaEventDisableTiming);
+      if (se == cudaSuccess) se = cudaEventCreateWithFlags(&c->ev_bk_side[k], cudaEventDisableTiming);
+    }
     if (se != cudaSuccess) {
       set_error(st, IGM_ERR_CUDA, __FILE__, __LINE__, cudaGetErrorString(se));
       igm_unet_destroy(c);
@@ -1403,6 +1484,8 @@ void igm_unet_destroy(igm_ctx* c) {
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->ev_ln) cudaEventDestroy(c->ev_ln);
   for (cudaEvent_t e : c->ev_rd) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_bk_main) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_bk_side) if (e) cudaEventDestroy(e);
   c->prof.reset();
   for (cudaEvent_t e : c->prof.pool) cudaEventDestroy(e);
   if (c->arena) cudaFree(c->arena);
@@ -1581,6 +1664,25 @@ int igm_unet_backward(igm_ctx* c, const float* d_out, float* d_x, void* stream) 
   float* dx_nhwc = d_x ? c->noise_copy : nullptr;
   IGM_TRY(r.backward(c->d_pred, dx_nhwc));
   if (d_x) IGM_TRY(launch_nhwc_to_nchw(r.lc, dx_nhwc, d_x, B, HW, c->cfg.channels));
+  return IGM_OK;
+}
+
+int igm_unet_grad_buckets(const igm_ctx* c, int64_t* lo, int64_t* hi, int cap) {
+  if (!c) return IGM_ERR_INVALID;
+  for (int k = 0; k < c->n_buckets && k < cap; ++k) {
+    if (lo) lo[k] = c->bucket_lo[k];
+    if (hi) hi[k] = c->bucket_hi[k];
+  }
+  return c->n_buckets;
+}
+
+int igm_unet_bucket_wait(igm_ctx* c, int k, void* stream) {
+  if (!c) return IGM_ERR_INVALID;
+  if (k < 0 || k >= c->n_buckets) IGM_FAIL(c->st, IGM_ERR_INVALID, "bad bucket index");
+  if (!c->bk_valid || !c->ev_bk_main[k]) IGM_FAIL(c->st, IGM_ERR_STATE, "bucket_wait without a backward pass of a training context");
+  IGM_CUDA(c->st, cudaSetDevice(c->device));
+  IGM_CUDA(c->st, cudaStreamWaitEvent((cudaStream_t)stream, c->ev_bk_main[k], 0));
+  if (c->bk_side_rec[k]) IGM_CUDA(c->st, cudaStreamWaitEvent((cudaStream_t)stream, c->ev_bk_side[k], 0));
   return IGM_OK;
 }
 

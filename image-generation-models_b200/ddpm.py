@@ -28,6 +28,7 @@ import os
 from . import _lib
 
 _EAGER_BWD = os.environ.get("IGM_EAGER_BWD", "1") != "0"
+_DDP_OVERLAP = os.environ.get("IGM_DDP_OVERLAP", "1") != "0"   # bucketed gradient all-reduce overlapped with backward
 
 try:  # the real Lightning base class when it is installed, a minimal stand-in otherwise
     from pytorch_lightning import LightningModule as _LightningModule  # type: ignore
@@ -136,6 +137,7 @@ class _Engine:
         self.cfg = cfg
         self.sched_key = None
         self.packed_version = None
+        self.bucket_ranges = None
 
     def check(self, rc):
         _lib.check(self.ctx, rc)
@@ -250,6 +252,7 @@ class Unet(nn.Module):
         self._pend, self._pend_gen = None, 0
         self._fwd_gen = getattr(self, "_fwd_gen", 0) + 1
         self._synced = False
+        self._comm = None
         self._anchor = torch.zeros(1, device=dev, requires_grad=True)
         if self._engine is not None:
             self._engine.close()
@@ -408,7 +411,10 @@ def _reduce_into_grad(unet: Unet, e: "_Engine", run_backward, d_scale: float = 1
     unet._bind_grad_target("pend")
     unet._pend.zero_()
     run_backward()
-    _allreduce(unet, unet._pend)
+    if unet._pend.is_cuda and getattr(unet, "ddp_overlap", _DDP_OVERLAP):
+        _allreduce_overlapped(unet, e, unet._pend)
+    else:
+        _allreduce(unet, unet._pend)
     e.check(e.lib.igm_grad_axpy(e.ctx, _ptr(unet._flat_grad), _ptr(unet._pend), None, C.c_float(d_scale / _world()),
                                 unet._flat_grad.numel(), _stream()))
     unet._pend_gen += 1    # the pending arena no longer holds an eager training_step's gradients
@@ -441,6 +447,30 @@ def _world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_world_size()
     return 1
+
+
+def _allreduce_overlapped(unet: Unet, e: "_Engine", arena: torch.Tensor):
+    """The exchange of the backward pass that was JUST enqueued, overlapped with it: the engine completes the gradient
+    arena bucket by bucket (igm_unet_grad_buckets: ups/mid/final first, downs.(n-1) .. downs.1, time_mlp + downs.0 last);
+    a communication stream waits for bucket k's events (igm_unet_bucket_wait, device-side) and all-reduces that range
+    while the compute stream is still running the rest of the backward pass.  The compute stream then waits for the
+    communication stream, so whatever follows (axpy into .grad, Adam) sees the reduced arena."""
+    import torch.distributed as dist
+    if e.bucket_ranges is None:
+        lo, hi = (C.c_int64 * 16)(), (C.c_int64 * 16)()
+        n = e.lib.igm_unet_grad_buckets(e.ctx, lo, hi, 16)
+        if n < 1:
+            e.check(n if n < 0 else -1)
+        e.bucket_ranges = [(int(lo[k]), int(hi[k])) for k in range(n)]
+    dev = arena.device
+    if unet._comm is None or unet._comm.device != dev:
+        unet._comm = torch.cuda.Stream(device=dev)
+    comm, main = unet._comm, torch.cuda.current_stream(dev)
+    with torch.cuda.stream(comm):
+        for k, (lo_k, hi_k) in enumerate(e.bucket_ranges):
+            e.check(e.lib.igm_unet_bucket_wait(e.ctx, k, C.c_void_p(comm.cuda_stream)))
+            dist.all_reduce(arena[lo_k:hi_k], op=dist.ReduceOp.SUM)
+    main.wait_stream(comm)
 
 
 def _allreduce(unet: Unet, arena: torch.Tensor):
@@ -733,7 +763,10 @@ class _PLossesFn(torch.autograd.Function):
         sync = _world() > 1 and getattr(unet, "ddp_sync", True)
         e.check(e.lib.igm_ddpm_p_losses_backward(e.ctx, None, C.c_float(1.0 / _world() if sync else 1.0), _stream()))
         if sync:
-            _allreduce(unet, unet._pend)
+            if getattr(unet, "ddp_overlap", _DDP_OVERLAP):
+                _allreduce_overlapped(unet, e, unet._pend)
+            else:
+                _allreduce(unet, unet._pend)
         unet._pend_gen += 1
         ctx.gen = unet._pend_gen
         return loss

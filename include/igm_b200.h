@@ -102,6 +102,16 @@ int igm_unet_forward(igm_ctx* ctx, const float* x, const int64_t* t, float* out,
  * d_x is not NULL, writes dL/dx. */
 int igm_unet_backward(igm_ctx* ctx, const float* d_out, float* d_x, void* stream);
 
+/* Data-parallel gradient exchange ("one ncclAllReduce over the flat fp32 gradient arena per
+ * step, chunked and overlapped with backward"; the reference itself delegates this to Lightning's DDP wrapper around
+ * DDPM, src/train.py:27 + trainer strategy).  igm_unet_grad_buckets returns the number of buckets and fills up to `cap`
+ * element ranges [lo, hi) of the gradient arena, in the order the backward pass completes them: bucket 0 = ups.*,
+ * mid_*, final_conv.*; then downs.(n-1) ... downs.1; last = time_mlp.* + downs.0.*.  igm_unet_bucket_wait makes `stream`
+ * wait (cudaStreamWaitEvent, no host sync) until every kernel of the MOST RECENT backward pass that writes bucket k has
+ * finished, so the caller can start that bucket's all-reduce on `stream` while the backward pass is still running. */
+int igm_unet_grad_buckets(const igm_ctx* ctx, int64_t* lo, int64_t* hi, int cap);
+int igm_unet_bucket_wait(igm_ctx* ctx, int k, void* stream);
+
 /* ---- diffusion ------------------------------------------------------------ */
 int igm_ddpm_set_schedule(igm_ctx* ctx, const igm_schedule* sched);
 /* GaussianDiffusion.q_sample — ddpm.py:433-444. */
