@@ -92,30 +92,10 @@ bool tc_gn_fusable(const TcConv& t, int B);
 inline int tc_gn_slots(const TcConv& t) { return t.H * t.W / 32; }
 int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r);
 
-// Halo-reuse forward / data-gradient engine for the stride-1 3x3 convs on wide images (conv_halo.cu): one zero-padded
-// activation tile per (band of image rows, 64-channel chunk) feeds all nine taps through shifted shared-memory
-// descriptors.  Same packed weights Wt[N][tap*K + k] and the same TcRun as the per-tap engine (N0 = N, no second
-// output).  Bring-up state: reachable through igm_debug_conv(engine = 2) only.
-struct TcConvHalo {
-  bool valid = false;
-  alignas(64) CUtensorMap a_hi, a_lo, a1_hi, a1_lo, b_hi, b_lo;
-  int K = 0, K0 = 0, N = 0, H = 0, W = 0, Bmax = 0;
-  int BH = 0;                 // image rows per band: two M = 128 tiles over BH * (W + 2) padded-linear rows
-  int a_tile_bytes = 0;       // one hi (or lo) activation tile in shared memory
-  mutable TcConv::OutMaps om; // row-store output maps, (re-)encoded when a launch passes a new output pointer
-};
-bool tch_eligible(int K, int N, int H, int W);
-int tch_plan(Status& st, TcConvHalo& t, int K, int N, int H, int W, int Bmax, __nv_bfloat16* a_hi, __nv_bfloat16* a_lo,
-             __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, int K0 = 0, __nv_bfloat16* a1_hi = nullptr,
-             __nv_bfloat16* a1_lo = nullptr);
-// GroupNorm partials of this engine: part[b][slot][8][2] with one slot per (band, tile, epilogue warp)
-int tch_gn_slots(const TcConvHalo& t);
-bool tch_gn_fusable(const TcConvHalo& t);
-int launch_conv_halo(const LaunchCtx& lc, const TcConvHalo& t, const TcRun& r);
-
 // CTA-pair (`cta_group::2`, M = 256) variant of the per-tap engine (conv_tc2.cu): same activation boxes and packed weights
-// as `base`, each CTA of a pair stages its own M tile and half of the weight tile.  Bring-up state: reachable through
-// igm_debug_conv / igm_debug_conv_bench (engine = 3) only.  `base` must outlive the pair plan.
+// as `base`, each CTA of a pair stages its own M tile and half of the weight tile.  Parity-green on B200 but slower than
+// the per-tap engine (profiles/r2_conv_engines.md): reachable through igm_debug_conv / igm_debug_conv_bench (engine = 3)
+// and IGM_CONV_PAIR=1 only.  `base` must outlive the pair plan.
 struct TcConvPair {
   bool valid = false;
   const TcConv* base = nullptr;

@@ -1,7 +1,7 @@
 // Test-only entry point: one stride-1 convolution (or its data gradient) on either engine,
 // so the tcgen05 kernel can be parity-checked in isolation over many shapes.
-// engine 0 = fp32 SIMT, 1 = tcgen05 per-tap (conv_tc.cu), 2 = tcgen05 halo-reuse (conv_halo.cu, bring-up),
-// 3 = tcgen05 CTA pair (conv_tc2.cu, bring-up).
+// engine 0 = fp32 SIMT, 1 = tcgen05 per-tap (conv_tc.cu), 3 = tcgen05 CTA pair (conv_tc2.cu, comparison only).
+// (engine 2 was the halo-reuse forward kernel: removed in round 2, it faulted on hardware and only covered W >= 28.)
 #include "common.cuh"
 #include "conv_tc.cuh"
 
@@ -49,14 +49,9 @@ extern "C" int igm_debug_conv(int engine, int mode, const float* x, const float*
   IGM_CUDA(st, cudaMalloc(&ah, M * Kc * 2));
   IGM_CUDA(st, cudaMalloc(&al, M * Kc * 2));
   TcConv t;
-  TcConvHalo th;
-  if (engine == 2) {   // halo-reuse engine (conv_halo.cu), 3x3 only
-    if (K != 3 || !tch_eligible(Kc, N, H, W)) {
-      set_error(st, IGM_ERR_INVALID, __FILE__, __LINE__, "shape not eligible for the halo-reuse tcgen05 conv");
-      rc = IGM_ERR_INVALID;
-    } else {
-      rc = tch_plan(st, th, Kc, N, H, W, B, ah, al, wh, wl);
-    }
+  if (engine != 1 && engine != 3) {
+    set_error(st, IGM_ERR_INVALID, __FILE__, __LINE__, "engine must be 0 (SIMT), 1 (per-tap tcgen05) or 3 (CTA pair)");
+    rc = IGM_ERR_INVALID;
   } else {
     rc = tc_plan(st, t, Kc, N, H, W, B, K, pad, ah, al, wh, wl);
   }
@@ -67,7 +62,7 @@ extern "C" int igm_debug_conv(int engine, int mode, const float* x, const float*
   if (rc == IGM_OK) {
     TcRun r;
     r.B = B; r.bias = bias; r.out0 = out; r.N0 = N; r.add0 = add;
-    rc = engine == 2 ? launch_conv_halo(lc, th, r) : engine == 3 ? launch_conv_tc2(lc, tp, r) : launch_conv_tc(lc, t, r);
+    rc = engine == 3 ? launch_conv_tc2(lc, tp, r) : launch_conv_tc(lc, t, r);
   }
   cudaError_t e = cudaStreamSynchronize(lc.stream);
   if (rc == IGM_OK && e != cudaSuccess) {
@@ -80,7 +75,7 @@ extern "C" int igm_debug_conv(int engine, int mode, const float* x, const float*
 
 // Kernel-level timing of one stride-1 convolution on the tcgen05 engines: operands are staged and the plan is built
 // once, then `iters` launches are timed with CUDA events on `stream` (after `warm` untimed ones).  engine 1 = per-tap
-// (conv_tc.cu), 2 = halo-reuse (conv_halo.cu), 3 = CTA pair (conv_tc2.cu); gn != 0 also produces the fused GroupNorm partial statistics, as the
+// (conv_tc.cu), 3 = CTA pair (conv_tc2.cu); gn != 0 also produces the fused GroupNorm partial statistics, as the
 // Block convs of the U-Net do.  Inputs are synthetic (a fixed pattern); *ms_per_launch receives the average.
 extern "C" int igm_debug_conv_bench(int engine, int mode, int B, int H, int W, int Cin, int Cout, int K, int gn, int warm,
                                     int iters, float* ms_per_launch, void* stream) {
@@ -92,13 +87,13 @@ extern "C" int igm_debug_conv_bench(int engine, int mode, int B, int H, int W, i
   lc.st = &st;
   lc.counter = &launches;
   if (K != 1 && K != 3) IGM_FAIL(st, IGM_ERR_INVALID, "K must be 1 or 3");
-  if (engine < 1 || engine > 3) IGM_FAIL(st, IGM_ERR_INVALID, "engine must be 1 (per-tap), 2 (halo-reuse) or 3 (CTA pair)");
+  if (engine != 1 && engine != 3) IGM_FAIL(st, IGM_ERR_INVALID, "engine must be 1 (per-tap) or 3 (CTA pair)");
   if (iters < 1 || warm < 0 || !ms_per_launch) IGM_FAIL(st, IGM_ERR_INVALID, "bad iteration counts");
   const int KK = K * K, pad = (K - 1) / 2;
   const int Kc = mode == 0 ? Cin : Cout, N = mode == 0 ? Cout : Cin;
   const int64_t M = (int64_t)B * H * W;
   const int64_t nw = (int64_t)KK * Cin * Cout;
-  if (!tc_eligible(Kc, N, H, W, K) || (engine == 2 && (K != 3 || !tch_eligible(Kc, N, H, W))))
+  if (!tc_eligible(Kc, N, H, W, K))
     IGM_FAIL(st, IGM_ERR_INVALID, "shape not eligible for the requested tcgen05 engine");
   __nv_bfloat16 *wh = nullptr, *wl = nullptr, *ah = nullptr, *al = nullptr;
   float *out = nullptr, *part = nullptr;
@@ -118,19 +113,17 @@ extern "C" int igm_debug_conv_bench(int engine, int mode, int B, int H, int W, i
     fail(cudaMemsetAsync(ah, 0x3c, M * Kc * 2, lc.stream)); fail(cudaMemsetAsync(al, 0x30, M * Kc * 2, lc.stream));
   }
   TcConv t;
-  TcConvHalo th;
-  if (rc == IGM_OK) rc = engine == 2 ? tch_plan(st, th, Kc, N, H, W, B, ah, al, wh, wl) : tc_plan(st, t, Kc, N, H, W, B, K, pad, ah, al, wh, wl);
+  if (rc == IGM_OK) rc = tc_plan(st, t, Kc, N, H, W, B, K, pad, ah, al, wh, wl);
   TcConvPair tp;
   if (rc == IGM_OK && engine == 3) rc = tc2_plan(st, tp, t);
   TcRun r;
   r.B = B; r.out0 = out; r.N0 = N; r.kclass = mode == 0 ? K_CONV_FPROP : K_CONV_DGRAD;
   if (rc == IGM_OK && gn) {
-    const bool ok = engine == 2 ? tch_gn_fusable(th) : tc_gn_fusable(t, B);
-    if (ok) r.gn_part = part;
+    if (tc_gn_fusable(t, B)) r.gn_part = part;
   }
   for (int i = 0; i < warm + iters && rc == IGM_OK; ++i) {
     if (i == warm) fail(cudaEventRecord(e0, lc.stream));
-    if (rc == IGM_OK) rc = engine == 2 ? launch_conv_halo(lc, th, r) : engine == 3 ? launch_conv_tc2(lc, tp, r) : launch_conv_tc(lc, t, r);
+    if (rc == IGM_OK) rc = engine == 3 ? launch_conv_tc2(lc, tp, r) : launch_conv_tc(lc, t, r);
   }
   if (rc == IGM_OK) {
     fail(cudaEventRecord(e1, lc.stream));

@@ -63,15 +63,9 @@ Status& global_status() {
 
 namespace {
 
-// IGM_CONV_HALO=1: eligible 3x3 stride-1 convs (W >= 28) run their forward and data gradient on the halo-reuse engine
-// (conv_halo.cu).  Bring-up switch, default off: the kernel has not run on hardware yet.
-bool conv_halo_on() {
-  static const bool on = [] { const char* e = getenv("IGM_CONV_HALO"); return e && e[0] == '1'; }();
-  return on;
-}
-
 // IGM_CONV_PAIR=1: eligible stride-1 convs (N % 128 == 0) run forward and data gradient on the cta_group::2 engine
-// (conv_tc2.cu).  Bring-up switch, default off: the kernel has not run on hardware yet.
+// (conv_tc2.cu).  Parity-green on B200 but 1.7-1.9x SLOWER than the per-tap engine on every layer shape
+// (profiles/r2_conv_engines.md), so it stays an off-by-default comparison switch.
 bool conv_pair_on() {
   static const bool on = [] { const char* e = getenv("IGM_CONV_PAIR"); return e && e[0] == '1'; }();
   return on;
@@ -107,7 +101,6 @@ struct ConvL {
   bool tc_f_ok = false, tc_b_ok = false, tc_w_ok = false;
   __nv_bfloat16 *wf_hi = nullptr, *wf_lo = nullptr, *wb_hi = nullptr, *wb_lo = nullptr;
   TcConv tc_f, tc_b;
-  TcConvHalo tch_f, tch_b;   // halo-reuse fprop / dgrad plans (conv_halo.cu), only when IGM_CONV_HALO=1 (bring-up, default off)
   TcConvPair tcp_f, tcp_b;   // CTA-pair plans on top of tc_f / tc_b (conv_tc2.cu), only when IGM_CONV_PAIR=1 (bring-up, default off)
   TcWgrad tc_w;
   bool tc_wh_ok = false;       // 3x3 stride-1: halo-reuse weight-gradient engine (wgrad_halo.cu)
@@ -581,8 +574,8 @@ struct PlanBuilder {
     c.t_proj = ar.alloc((int64_t)B * c.proj_total);
     tap("time_mlp", c.t_temb, d, 1, 1);
     const int64_t HW0 = (int64_t)cfg.height * cfg.width;
-    // 32-pixel slots (fused) or 64-pixel chunks; the halo-reuse conv engine writes 8 slots per band of 256 / (W+2) rows
-    c.gn_part = ar.alloc((int64_t)B * cdiv((int)HW0, 32) * kGroups * 2 * (conv_halo_on() ? 2 : 1));
+    // 32-pixel slots (statistics fused into the conv epilogue) or 64-pixel chunks
+    c.gn_part = ar.alloc((int64_t)B * cdiv((int)HW0, 32) * kGroups * 2);
     c.attn_ws = ar.alloc(linattn_ws_floats(B, (int)HW0));
     c.pred = ar.alloc((int64_t)B * cfg.channels * HW0);
     c.loss_ws = ar.alloc(1024);
@@ -675,7 +668,6 @@ struct Runner {
   int64_t M(int H, int W) const { return (int64_t)B * H * W; }
   bool tc_on() const { return c.conv_engine == 1; }
   bool use_tc(const TcConv& t) const { return tc_on() && t.valid; }
-  bool use_halo(const TcConvHalo& t) const { return tc_on() && conv_halo_on() && t.valid; }
   bool use_pair(const TcConvPair& t) const { return tc_on() && conv_pair_on() && t.valid; }
   // bf16 staging pointers of an activation: only handed to producers while the tcgen05 engine is on
   __nv_bfloat16* hi(const Act& a) const { return tc_on() ? a.hi : nullptr; }
@@ -703,7 +695,6 @@ struct Runner {
       r.B = B; r.bias = c.Pp(l.pb); r.out0 = out; r.N0 = l.Cout; r.add0 = add; r.kclass = K_CONV_FPROP;
       r.gn_part = gn_part;
       if (out_act) { r.hi0 = hi(*out_act); r.lo0 = lo(*out_act); }
-      if (use_halo(l.tch_f)) return launch_conv_halo(lc, l.tch_f, r);
       if (use_pair(l.tcp_f)) return launch_conv_tc2(lc, l.tcp_f, r);
       return launch_conv_tc(lc, l.tc_f, r);
     }
@@ -734,7 +725,6 @@ struct Runner {
       TcRun r;
       r.B = B; r.bias = nullptr; r.out0 = d0; r.out1 = d1; r.N0 = C0; r.add0 = add0; r.add1 = add1;
       r.kclass = K_CONV_DGRAD;
-      if (use_halo(l.tch_b) && !d1 && C0 == l.Cin) return launch_conv_halo(lc, l.tch_b, r);   // single output tensor only
       if (use_pair(l.tcp_b)) return launch_conv_tc2(lc, l.tcp_b, r);
       return launch_conv_tc(lc, l.tc_b, r);
     }
@@ -834,11 +824,10 @@ struct Runner {
   // ---- Block: conv3x3 -> GN -> Mish (+temb) (+res) ----
   int block_fwd(BlockL& b, int H, int W, const float* temb, const float* res, const Act& out, bool lean = false) {
     // GroupNorm partial statistics come out of the conv epilogue when the tensor-core plan allows it
-    const bool halo = use_tc(b.conv.tc_f) && use_halo(b.conv.tch_f);
-    const bool fused = use_tc(b.conv.tc_f) && (halo ? tch_gn_fusable(b.conv.tch_f) : tc_gn_fusable(b.conv.tc_f, B));
+    const bool fused = use_tc(b.conv.tc_f) && tc_gn_fusable(b.conv.tc_f, B);
     IGM_TRY(conv_fwd(b.conv, H, W, H, W, 1, 1, b.raw, nullptr, nullptr, fused ? c.gn_part : nullptr));
     int nparts = 0;
-    if (fused) nparts = halo ? tch_gn_slots(b.conv.tch_f) : tc_gn_slots(b.conv.tc_f);
+    if (fused) nparts = tc_gn_slots(b.conv.tc_f);
     else IGM_TRY(launch_gn_partial(lc, b.raw, B, H * W, b.conv.Cout, c.gn_part));
     IGM_TRY(launch_gn_apply(lc, b.raw, c.gn_part, c.Pp(b.gn_w), c.Pp(b.gn_b), temb, c.proj_total, res, lean ? nullptr : out.v,
                             b.stats, B, H * W, b.conv.Cout, hi(out), lo(out), nparts));
@@ -1268,14 +1257,6 @@ static int plan_tc(igm_ctx* c) {
     if (conv_pair_on()) {   // CTA-pair plans reference tc_f / tc_b (ConvL objects do not move after planning)
       if (l.tc_f.valid && tc2_eligible(l.tc_f)) IGM_TRY(tc2_plan(c->st, l.tcp_f, l.tc_f));
       if (l.tc_b.valid && tc2_eligible(l.tc_b)) IGM_TRY(tc2_plan(c->st, l.tcp_b, l.tc_b));
-    }
-    if (conv_halo_on() && l.K == 3) {   // same operands and packed weights, halo-reuse tiling (bring-up switch)
-      if (l.tc_f.valid && tch_eligible(l.Cin, l.Cout, l.H, l.W))
-        IGM_TRY(tch_plan(c->st, l.tch_f, l.Cin, l.Cout, l.H, l.W, c->cfg.max_batch, s0->hi, s0->lo, l.wf_hi, l.wf_lo, s0->C,
-                         s1 ? s1->hi : nullptr, s1 ? s1->lo : nullptr));
-      if (l.tc_b.valid && tch_eligible(l.Cout, l.Cin, l.H, l.W))
-        IGM_TRY(tch_plan(c->st, l.tch_b, l.Cout, l.Cin, l.H, l.W, c->cfg.max_batch, c->dy_hi[l.dyb], c->dy_lo[l.dyb], l.wb_hi,
-                         l.wb_lo));
     }
     if (l.tc_w_ok && staged)
       IGM_TRY(tcw_plan(c->st, l.tc_w, l.Cin, l.Cout, l.H, l.W, c->cfg.max_batch, l.K, pad, c->dy_hi[l.dyb], c->dy_lo[l.dyb], s0->hi,

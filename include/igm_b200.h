@@ -237,13 +237,13 @@ int64_t igm_launch_count(const igm_ctx* ctx);
 /* One stride-1 KxK (K = 1 or 3, pad (K-1)/2) convolution on NHWC fp32 tensors, for kernel-level
  * parity tests: mode 0 = forward  x[B,H,W,Cin] -> out[B,H,W,Cout] (+bias, +add);
  *               mode 1 = data gradient  x = d_out[B,H,W,Cout] -> out = d_in[B,H,W,Cin].
- * w is the PyTorch OIHW weight.  engine as in igm_set_conv_engine; engine 2 = the halo-reuse tcgen05 kernel
- * (conv_halo.cu; K = 3, W >= 28; bring-up).  Synchronous. */
+ * w is the PyTorch OIHW weight.  engine as in igm_set_conv_engine; engine 3 = the CTA-pair (cta_group::2) tcgen05
+ * kernel (conv_tc2.cu; N % 128 == 0; comparison only: parity-green but slower than engine 1).  Synchronous. */
 int igm_debug_conv(int engine, int mode, const float* x, const float* w_oihw, const float* bias,
                    const float* add, float* out, int B, int H, int W, int Cin, int Cout, int K,
                    void* stream);
-/* Kernel-level timing of the same convolution on the tcgen05 engines (1 = per-tap conv_tc.cu, 2 = halo-reuse
- * conv_halo.cu, bring-up): synthetic operands staged once, `warm` untimed then `iters` timed launches between CUDA
+/* Kernel-level timing of the same convolution on the tcgen05 engines (1 = per-tap conv_tc.cu, 3 = CTA pair
+ * conv_tc2.cu): synthetic operands staged once, `warm` untimed then `iters` timed launches between CUDA
  * events on `stream`; gn != 0 adds the fused GroupNorm partial statistics.  Synchronous. */
 int igm_debug_conv_bench(int engine, int mode, int B, int H, int W, int Cin, int Cout, int K, int gn, int warm,
                          int iters, float* ms_per_launch, void* stream);

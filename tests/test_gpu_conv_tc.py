@@ -180,73 +180,13 @@ def test_resample_tc(shape):
         assert l2 < 1e-4 and mx < 1e-4, f"tcgen05 kind {kind} mode {mode}: rel-L2 {l2:.2e} max-rel {mx:.2e}"
 
 
-# ---- halo-reuse forward / data-gradient engine (csrc/conv_halo.cu), bring-up state ----
-# The kernel was written after the round's GPU budget was spent and has never run on hardware; no network path
-# selects it.  These tests are the first thing to run on it: IGM_TEST_CONV_HALO=1 python -m pytest -m gpu -k conv_halo
 import os
 
-_halo = pytest.mark.skipif(os.environ.get("IGM_TEST_CONV_HALO") != "1",
-                           reason="conv_halo.cu is in bring-up (never run on a GPU yet); set IGM_TEST_CONV_HALO=1")
-
-HALO_SHAPES = [
-    # B, H, W, Cin, Cout
-    (1, 7, 32, 64, 64),          # exactly one band, both tiles live
-    (2, 32, 32, 64, 64),         # 4 full bands + a 4-row band per image
-    (2, 32, 32, 128, 64),        # two K chunks: the activation ring turns over inside a band
-    (2, 32, 32, 64, 128),        # two N tiles share each band
-    (3, 28, 28, 128, 128),       # MNIST width: BH = 8, last band 4 rows
-    (1, 64, 64, 64, 64),         # CelebA width: BH = 3, last band 1 row (second tile idle)
-    (160, 32, 32, 64, 64),       # more work items than CTAs: persistent loop, both accumulator stages
-]
-
-
-@_halo
-@pytest.mark.parametrize("shape", HALO_SHAPES)
-def test_conv_halo_forward(shape):
-    B, H, W, Cin, Cout = shape
-    g = torch.Generator().manual_seed(7 + hash(shape) % 1000)
-    x = torch.randn(B, H, W, Cin, generator=g)
-    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
-    bias = torch.randn(Cout, generator=g)
-    add = torch.randn(B, H, W, Cout, generator=g)
-    xs, ws, bs, ads = x.cuda(), w.cuda(), bias.cuda(), add.cuda()
-    ref = _run(1, 0, xs, ws, bs, ads, B, H, W, Cin, Cout, 3).cpu()     # the per-tap tcgen05 engine (itself checked above)
-    got = _run(2, 0, xs, ws, bs, ads, B, H, W, Cin, Cout, 3).cpu()
-    assert torch.isfinite(got).all()
-    l2, mx = rel_err(got, ref.double())
-    assert l2 < 1e-5 and mx < 1e-5, f"halo engine vs per-tap engine: rel-L2 {l2:.2e} max-rel {mx:.2e}"
-
-
-@_halo
-@pytest.mark.parametrize("shape", HALO_SHAPES[:5])
-def test_conv_halo_dgrad(shape):
-    B, H, W, Cin, Cout = shape
-    g = torch.Generator().manual_seed(11 + hash(shape) % 1000)
-    dy = torch.randn(B, H, W, Cout, generator=g)
-    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cout * 9) ** 0.5
-    ref = F.conv_transpose2d(dy.permute(0, 3, 1, 2).double(), w.double(), padding=1).permute(0, 2, 3, 1)
-    got = _run(2, 1, dy.cuda(), w.cuda(), None, None, B, H, W, Cin, Cout, 3).cpu()
-    l2, mx = rel_err(got, ref)
-    assert l2 < 1e-4 and mx < 1e-4, f"halo engine dgrad: rel-L2 {l2:.2e} max-rel {mx:.2e}"
-
-
-@_halo
-def test_unet_parity_with_halo_engine():
-    """The whole parity suite with IGM_CONV_HALO=1 (the switch is read once per process, hence the subprocess): the
-    32x32 / 28x28 / 64x64 3x3 convs then run forward and data gradient on conv_halo.cu, GroupNorm statistics included."""
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, IGM_CONV_HALO="1")
-    env.pop("IGM_TEST_CONV_HALO", None)
-    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-x", "-q", "-m", "gpu"], cwd=root, env=env,
-                       capture_output=True, text=True, timeout=1800)
-    assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
-
-
-# ---- CTA-pair (cta_group::2) engine (csrc/conv_tc2.cu), bring-up state: never run on hardware yet ----
-_pair = pytest.mark.skipif(os.environ.get("IGM_TEST_CONV_PAIR") != "1",
-                           reason="conv_tc2.cu is in bring-up (never run on a GPU yet); set IGM_TEST_CONV_PAIR=1")
+# ---- CTA-pair (cta_group::2) engine (csrc/conv_tc2.cu): parity-green on B200 (round 2) but slower than the per-tap
+# engine, so it is not on the product path; the kernel-level tests run by default, the whole-net one on request ----
+_pair = pytest.mark.skipif(False, reason="")
+_pair_net = pytest.mark.skipif(os.environ.get("IGM_TEST_CONV_PAIR") != "1",
+                               reason="whole-net parity with the (slower) CTA-pair engine: set IGM_TEST_CONV_PAIR=1")
 
 PAIR_SHAPES = [
     # B, H, W, Cin, Cout, K   (Cout % 128 == 0 for fprop; dgrad needs Cin % 128 == 0)
@@ -289,7 +229,7 @@ def test_conv_pair_dgrad(shape):
     assert l2 < 1e-4 and mx < 1e-4, f"pair engine dgrad: rel-L2 {l2:.2e} max-rel {mx:.2e}"
 
 
-@_pair
+@_pair_net
 def test_unet_parity_with_pair_engine():
     """The whole parity suite with IGM_CONV_PAIR=1 (read once per process, hence the subprocess): every stride-1 conv
     with N % 128 == 0 then runs forward and data gradient on conv_tc2.cu, fused GroupNorm statistics included."""

@@ -1,8 +1,8 @@
 """Per-layer timing of the 3x3 / 1x1 convolutions of the DDPM U-Nets on the two tcgen05 engines (GPU tool, not a test):
-engine 1 = per-tap conv_tc.cu, engine 2 = halo-reuse conv_halo.cu (bring-up), engine 3 = CTA pair conv_tc2.cu (bring-up).  Uses the C-ABI timing entry
+engine 1 = per-tap conv_tc.cu, engine 3 = CTA pair conv_tc2.cu (comparison only).  Uses the C-ABI timing entry
 igm_debug_conv_bench (operands staged once, CUDA events around `iters` back-to-back launches, warm L2).
 
-    python tools/conv_layer_bench.py [--halo] [--pair] [--batch 128] [--iters 50]
+    python tools/conv_layer_bench.py [--pair] [--batch 128] [--iters 50]
 
 Prints one line per (layer shape, mode, engine): microseconds per launch and fp32-equivalent TFLOP/s, next to the
 bf16x3 ceiling (measured bf16 dense peak / 3)."""
@@ -25,7 +25,6 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--iters", type=int, default=50)
-    ap.add_argument("--halo", action="store_true", help="also time engine 2 where the shape is eligible")
     ap.add_argument("--pair", action="store_true", help="also time engine 3 where the shape is eligible")
     ap.add_argument("--celeba", action="store_true")
     args = ap.parse_args()
@@ -44,7 +43,7 @@ def main():
     ms = C.c_float(0)
     for (H, W, Cin, Cout, K, n) in shapes:
         for mode in (0, 1):
-            for engine in [1] + ([2] if args.halo else []) + ([3] if args.pair else []):
+            for engine in [1] + ([3] if args.pair else []):
                 rc = lib.igm_debug_conv_bench(engine, mode, B, H, W, Cin, Cout, K, 1 if (mode == 0 and K == 3) else 0, 5,
                                               args.iters, C.byref(ms), None)
                 if rc != 0:
