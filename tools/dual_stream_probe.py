@@ -8,7 +8,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 import igm_b200  # noqa: E402
-from bench import CH, DIM, H, MULTS, T, W  # noqa: E402
+from bench import CH, CONFIGS, DIM, T  # noqa: E402
+
+H, W, MULTS = CONFIGS["cifar10"]["H"], CONFIGS["cifar10"]["W"], CONFIGS["cifar10"]["mults"]
 
 dev = torch.device("cuda", 0)
 dm = SimpleNamespace(width=W, height=H, channels=CH, transforms=SimpleNamespace(normalize=True))

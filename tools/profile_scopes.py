@@ -12,7 +12,14 @@ os.environ["IGM_PROFILE_DUMP"] = out
 import torch  # noqa: E402
 
 import igm_b200  # noqa: E402
-from bench import CH, DIM, H, MULTS, T, W, synth_batch  # noqa: E402
+from bench import CH, CONFIGS, DIM, T, synth_batch as _synth  # noqa: E402
+
+H, W, MULTS = CONFIGS["cifar10"]["H"], CONFIGS["cifar10"]["W"], CONFIGS["cifar10"]["mults"]
+
+
+def synth_batch(B, seed):
+    return _synth(B, seed, H, W)
+
 
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)

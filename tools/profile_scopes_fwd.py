@@ -11,7 +11,9 @@ os.environ["IGM_PROFILE_DUMP"] = out
 import torch  # noqa: E402
 
 import igm_b200  # noqa: E402
-from bench import CH, DIM, H, MULTS, T, W  # noqa: E402
+from bench import CH, CONFIGS, DIM, T  # noqa: E402
+
+H, W, MULTS = CONFIGS["cifar10"]["H"], CONFIGS["cifar10"]["W"], CONFIGS["cifar10"]["mults"]
 
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
