@@ -74,3 +74,43 @@ def test_checkpoint_interchange_with_reference():
     for p, q in zip(rm.denoising_model.parameters(), mine.denoising_model.parameters()):
         assert torch.equal(p, q.cpu())
     assert torch.equal(rm.diffusion_model.betas, mine.diffusion_model.betas.cpu())
+
+
+@pytest.mark.gpu
+def test_validation_step_output_feeds_the_callback_from_the_device(tmp_path, monkeypatch):
+    """The step after the hot path, on hardware: DDPM.validation_step (reference ddpm.py:514-521 -- q_sample of the batch at
+    t = T-1 and a 64-image reverse chain on batch 0) hands DEVICE tensors to SampleImagesCallback, which must produce the
+    same grids as from host copies, write results/<epoch>.jpg, and the checkpoint written afterwards must reload."""
+    monkeypatch.chdir(tmp_path)
+    torch.manual_seed(0)
+    T = 20
+    d = igm_b200.DDPM(ref_loader.datamodule_cfg(3, 16, 16), hidden_dim=32, dim_mults=(1, 2), timesteps=T, lr=1e-4, b1=0.9,
+                      b2=0.999).cuda()
+    imgs = (torch.randn(8, 3, 16, 16) * 0.5).clamp(-1, 1).cuda()
+    out = d.validation_step((imgs, None), 0)
+    assert out.fake_image.is_cuda and out.fake_image.shape == (64, 3, 16, 16) and torch.isfinite(out.fake_image).all()
+    assert out.others["diffusion"].is_cuda
+    # q_sample at t = T-1 against the oracle's schedule
+    buf = O.diffusion_buffers(T)
+    exp = _Exp()
+    trainer = SimpleNamespace(current_epoch=2, logger=SimpleNamespace(experiment=exp))
+    cb = igm_b200.SampleImagesCallback()
+    cb.on_validation_batch_end(trainer, d, out, (imgs, None), 0)
+    assert set(exp.images) == {"images/real", "images/sample", "images/diffusion"}
+    grid = exp.images["images/sample"][0]
+    host_grid = igm_b200.get_grid_images(out.fake_image.cpu(), d)
+    assert grid.is_cuda and torch.allclose(grid.cpu(), host_grid, atol=1e-6)
+    assert os.path.exists(tmp_path / "results" / "2.jpg")
+    # checkpoint round trip after validation (what ModelCheckpoint does next)
+    b = io.BytesIO()
+    torch.save({"state_dict": d.state_dict()}, b)
+    b.seek(0)
+    d2 = igm_b200.DDPM(ref_loader.datamodule_cfg(3, 16, 16), hidden_dim=32, dim_mults=(1, 2), timesteps=T).cuda()
+    d2.load_state_dict(torch.load(b)["state_dict"])
+    x_t = d2.diffusion_model.q_sample(imgs, torch.full((8,), T - 1, device="cuda", dtype=torch.long), noise=torch.zeros_like(imgs))
+    want = buf["sqrt_alphas_cumprod"][T - 1] * imgs.cpu()
+    assert torch.allclose(x_t.cpu(), want, atol=1e-6)
+    with torch.no_grad():
+        a = d.denoising_model(imgs, torch.full((8,), 3, device="cuda", dtype=torch.long))
+        c = d2.denoising_model(imgs, torch.full((8,), 3, device="cuda", dtype=torch.long))
+    assert torch.equal(a, c)
