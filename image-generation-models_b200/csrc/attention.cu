@@ -84,6 +84,25 @@ __device__ __forceinline__ void load_tile(float (*dst)[D], const float* __restri
   }
 }
 
+// the same tile from a bf16 hi / lo staging pair (value = hi + lo, 16 significant bits): `ld` in elements
+template <int R = CH>
+__device__ __forceinline__ void load_tile_hl(float (*dst)[D], const __nv_bfloat16* __restrict__ hi,
+                                             const __nv_bfloat16* __restrict__ lo, int ld, int rows, int tid) {
+  for (int i = tid; i < R * (D / 4); i += 256) {
+    const int nn = i >> 3, c4 = (i & 7) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nn < rows) {
+      const uint2 h = __ldg(reinterpret_cast<const uint2*>(hi + (int64_t)nn * ld + c4));
+      const uint2 l = __ldg(reinterpret_cast<const uint2*>(lo + (int64_t)nn * ld + c4));
+      v.x = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+      v.y = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
+      v.z = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+      v.w = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
+    }
+    *reinterpret_cast<float4*>(&dst[nn][c4]) = v;
+  }
+}
+
 constexpr int PART = 2 * D + D * D;   // per-chunk partial: max[32] | sum[32] | S[32][32]
 
 // "last CTA of the group finishes the job": returns true in exactly one CTA of the gridDim.y CTAs that
@@ -105,7 +124,10 @@ __device__ __forceinline__ bool last_chunk_done(unsigned int* counter, int tid) 
 // Pass 1, grid (B*heads, nsplit): chunk-local softmax statistics of k and the unnormalised context
 //   m[d] = max_n k[n][d],  l[d] = sum_n exp(k - m),  S[d][e] = sum_n exp(k[n][d] - m[d]) v[n][e];
 // the last CTA of each (batch, head) merges the chunk partials into ctx / kstat.
-__global__ void __launch_bounds__(256) linattn_ctx_kernel(const float* __restrict__ qkv, float* __restrict__ part_ws,
+// HL: q / k / v come from the bf16 hi / lo staging pair of the to_qkv output (tensor-core attention path, no fp32 qkv)
+template <bool HL>
+__global__ void __launch_bounds__(256) linattn_ctx_kernel(const float* __restrict__ qkv, const __nv_bfloat16* __restrict__ q_hi,
+                                                          const __nv_bfloat16* __restrict__ q_lo, float* __restrict__ part_ws,
                                                           unsigned int* __restrict__ counters, float* __restrict__ ctx,
                                                           float* __restrict__ kstat, int N) {
   __shared__ __align__(16) float buf[2 * CH * D];   // k | v tiles, later the reduction scratch
@@ -120,9 +142,14 @@ __global__ void __launch_bounds__(256) linattn_ctx_kernel(const float* __restric
   const int nsplit = gridDim.y;
   const int n0 = blockIdx.y * CH, rows = min(CH, N - n0);
   const int tid = threadIdx.x;
-  const float* base = qkv + ((int64_t)b * N + n0) * QKV;
-  load_tile(Xs, base + HD + h * D, QKV, rows, tid);
-  load_tile(Ys, base + 2 * HD + h * D, QKV, rows, tid);
+  const int64_t boff = ((int64_t)b * N + n0) * QKV;
+  if (HL) {
+    load_tile_hl(Xs, q_hi + boff + HD + h * D, q_lo + boff + HD + h * D, QKV, rows, tid);
+    load_tile_hl(Ys, q_hi + boff + 2 * HD + h * D, q_lo + boff + 2 * HD + h * D, QKV, rows, tid);
+  } else {
+    load_tile(Xs, qkv + boff + HD + h * D, QKV, rows, tid);
+    load_tile(Ys, qkv + boff + 2 * HD + h * D, QKV, rows, tid);
+  }
   __syncthreads();
   {
     const int d = tid & 31, r = tid >> 5;
@@ -230,8 +257,13 @@ __global__ void __launch_bounds__(256) linattn_out_kernel(const float* __restric
 
 // Backward pass 1, grid (B*heads, nsplit): dctx[d][e] = sum_n q[n][d] * dO[n][e]; the last CTA of each
 // (batch, head) sums the chunk partials into dctx_full.
+template <bool HL>
 __global__ void __launch_bounds__(256) linattn_bwd_dctx_kernel(const float* __restrict__ qkv,
                                                                const float* __restrict__ d_out,
+                                                               const __nv_bfloat16* __restrict__ q_hi,
+                                                               const __nv_bfloat16* __restrict__ q_lo,
+                                                               const __nv_bfloat16* __restrict__ d_hi,
+                                                               const __nv_bfloat16* __restrict__ d_lo,
                                                                float* __restrict__ part_ws,
                                                                unsigned int* __restrict__ counters,
                                                                float* __restrict__ dctx_full, int N) {
@@ -245,8 +277,14 @@ __global__ void __launch_bounds__(256) linattn_bwd_dctx_kernel(const float* __re
   const int nsplit = gridDim.y;
   const int n0 = blockIdx.y * CH, rows = min(CH, N - n0);
   const int tid = threadIdx.x;
-  load_tile(Xs, qkv + ((int64_t)b * N + n0) * QKV + h * D, QKV, rows, tid);
-  load_tile(Ys, d_out + ((int64_t)b * N + n0) * HD + h * D, HD, rows, tid);
+  if (HL) {
+    const int64_t qo = ((int64_t)b * N + n0) * QKV + h * D, dof = ((int64_t)b * N + n0) * HD + h * D;
+    load_tile_hl(Xs, q_hi + qo, q_lo + qo, QKV, rows, tid);
+    load_tile_hl(Ys, d_hi + dof, d_lo + dof, HD, rows, tid);
+  } else {
+    load_tile(Xs, qkv + ((int64_t)b * N + n0) * QKV + h * D, QKV, rows, tid);
+    load_tile(Ys, d_out + ((int64_t)b * N + n0) * HD + h * D, HD, rows, tid);
+  }
   __syncthreads();
   const int grp = tid >> 6, t64 = tid & 63;
   const int d0 = (t64 >> 3) * 4, e0 = (t64 & 7) * 4;
@@ -422,6 +460,103 @@ __global__ void __launch_bounds__(256) linattn_mb_kernel(const float* __restrict
   }
 }
 
+
+// ---- tensor-core attention path (training, n >= 1024 pixels): every per-pixel contraction of the block is a 1x1
+// convolution whose 128 x 128 weight matrix differs per image and is block-diagonal over the four heads, i.e. exactly what
+// conv_tc_kernel runs with a tc_plan_img plan:
+//     out = conv(q; ctx)   dq = conv(dO; ctx^T)   dv = conv(p; dctx)   T = conv(v; dctx^T)   dk = p * (T - c)
+// (reference ddpm.py:161-162 and their autograd).  The kernels below are the glue that stays on CUDA cores.
+
+// Per-image block-diagonal weight matrix Wt[b][row][col] (row = output channel, col = input channel, K-major rows, what
+// the conv engine's weight descriptor reads) from m[b][h][d][e]:
+//   transpose = 0:  Wt[(h,e)][(h,d)] = m[d][e]      (out = conv(q; ctx), dv = conv(p; dctx))
+//   transpose = 1:  Wt[(h,d)][(h,e)] = m[d][e]      (dq = conv(dO; ctx^T), T = conv(v; dctx^T))
+// grid (B), 256 threads; cc (nullable): cc[b][(h,d)] = sum_e m[d][e] * m2[d][e]  (the softmax-normaliser term of dk)
+__global__ void __launch_bounds__(256) linattn_wt_kernel(const float* __restrict__ m, int transpose,
+                                                         __nv_bfloat16* __restrict__ w_hi, __nv_bfloat16* __restrict__ w_lo,
+                                                         const float* __restrict__ m2, float* __restrict__ cc) {
+  __shared__ float sm[kHeads][D][D + 1];
+  pdl_wait();
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < kHeads * D * D; i += 256) sm[i >> 10][(i >> 5) & 31][i & 31] = __ldg(m + (int64_t)b * kHeads * D * D + i);
+  __syncthreads();
+  for (int i = tid; i < HD * HD / 2; i += 256) {          // two adjacent columns per thread
+    const int row = i / (HD / 2), col = (i - row * (HD / 2)) * 2;
+    const int hr = row >> 5, hc = col >> 5;
+    float v0 = 0.f, v1 = 0.f;
+    if (hr == hc) {
+      if (transpose) { v0 = sm[hr][row & 31][col & 31]; v1 = sm[hr][row & 31][(col + 1) & 31]; }
+      else { v0 = sm[hr][col & 31][row & 31]; v1 = sm[hr][(col + 1) & 31][row & 31]; }
+    }
+    uint32_t h, l;
+    split_pair(v0, v1, h, l);
+    const int64_t o = ((int64_t)b * HD + row) * HD + col;
+    *reinterpret_cast<uint32_t*>(w_hi + o) = h;
+    *reinterpret_cast<uint32_t*>(w_lo + o) = l;
+  }
+  if (cc && tid < HD) {
+    const int h = tid >> 5, d = tid & 31;
+    const float* r2 = m2 + ((int64_t)b * kHeads + h) * D * D + d * D;
+    float a = 0.f;
+#pragma unroll
+    for (int e = 0; e < D; ++e) a = fmaf(sm[h][d][e], __ldg(r2 + e), a);
+    cc[(int64_t)b * HD + tid] = a;
+  }
+}
+
+// p = softmax_n(k) as a bf16 hi / lo pair [M, 128] (operand of dv = conv(p; dctx) and factor of dk), from the k third
+// of the to_qkv staging pair and the (max, sum) statistics the forward kept.  One thread per 4 channels of a pixel.
+__global__ void __launch_bounds__(256) linattn_p_kernel(const __nv_bfloat16* __restrict__ q_hi, const __nv_bfloat16* __restrict__ q_lo,
+                                                        const float* __restrict__ kstat, __nv_bfloat16* __restrict__ p_hi,
+                                                        __nv_bfloat16* __restrict__ p_lo, int64_t M, int N) {
+  pdl_wait();
+  const int64_t total = M * (HD / 4);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i >> 5;
+    const int c = (int)(i & 31) * 4;
+    const int64_t b = pix / N;
+    const int64_t src = pix * QKV + HD + c;
+    const uint2 h = __ldg(reinterpret_cast<const uint2*>(q_hi + src));
+    const uint2 l = __ldg(reinterpret_cast<const uint2*>(q_lo + src));
+    const float k0 = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+    const float k1 = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
+    const float k2 = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+    const float k3 = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
+    const float4 s01 = __ldg(reinterpret_cast<const float4*>(kstat + (b * HD + c) * 2));       // (max, sum) x 2 channels
+    const float4 s23 = __ldg(reinterpret_cast<const float4*>(kstat + (b * HD + c + 2) * 2));
+    float4 o;
+    o.x = expf(k0 - s01.x) / s01.y;
+    o.y = expf(k1 - s01.z) / s01.w;
+    o.z = expf(k2 - s23.x) / s23.y;
+    o.w = expf(k3 - s23.z) / s23.w;
+    store_split4(p_hi, p_lo, pix * HD + c, o);
+  }
+}
+
+// dk = p * (T - c) into the k third of the d(qkv) staging pair (pitch 384): T = conv(v; dctx^T) fp32 [M, 128]
+__global__ void __launch_bounds__(256) linattn_dk_kernel(const __nv_bfloat16* __restrict__ p_hi, const __nv_bfloat16* __restrict__ p_lo,
+                                                         const float* __restrict__ T, const float* __restrict__ cc,
+                                                         __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo,
+                                                         int64_t M, int N) {
+  pdl_wait();
+  const int64_t total = M * (HD / 4);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i >> 5;
+    const int c = (int)(i & 31) * 4;
+    const int64_t b = pix / N;
+    const uint2 h = __ldg(reinterpret_cast<const uint2*>(p_hi + pix * HD + c));
+    const uint2 l = __ldg(reinterpret_cast<const uint2*>(p_lo + pix * HD + c));
+    const float4 t = __ldg(reinterpret_cast<const float4*>(T + pix * HD + c));
+    const float4 cv = __ldg(reinterpret_cast<const float4*>(cc + b * HD + c));
+    float4 o;
+    o.x = (__uint_as_float(h.x << 16) + __uint_as_float(l.x << 16)) * (t.x - cv.x);
+    o.y = (__uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u)) * (t.y - cv.y);
+    o.z = (__uint_as_float(h.y << 16) + __uint_as_float(l.y << 16)) * (t.z - cv.z);
+    o.w = (__uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u)) * (t.w - cv.w);
+    store_split4(d_hi, d_lo, pix * QKV + HD + c, o);
+  }
+}
+
 }  // namespace
 
 // scratch layout: kCtrCap chunk counters (zero on entry, self re-arming) | [B*heads][32*32] dctx | chunk partials.
@@ -438,7 +573,7 @@ int launch_linattn_forward(const LaunchCtx& lc, const float* qkv, float* out, fl
   if (B * kHeads > kCtrCap) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linear attention: batch too large");
   unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
   float* parts = ws + kCtrCap + (int64_t)B * kHeads * (D * D);
-  { cudaError_t le_ = launch_pdl(linattn_ctx_kernel, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, parts, counters, ctx, kstat, n); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
+  { cudaError_t le_ = launch_pdl(linattn_ctx_kernel<false>, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)nullptr, parts, counters, ctx, kstat, n); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
   { cudaError_t le_ = launch_pdl(linattn_out_kernel, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, ctx, out, n, out_hi, out_lo); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
@@ -453,7 +588,7 @@ int launch_linattn_ctx(const LaunchCtx& lc, const float* qkv, float* ctx, float*
   if (B * kHeads > kCtrCap) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linear attention: batch too large");
   unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
   float* parts = ws + kCtrCap + (int64_t)B * kHeads * (D * D);
-  { cudaError_t le_ = launch_pdl(linattn_ctx_kernel, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, parts, counters, ctx, kstat, n); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
+  { cudaError_t le_ = launch_pdl(linattn_ctx_kernel<false>, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)nullptr, parts, counters, ctx, kstat, n); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }
@@ -484,10 +619,70 @@ int launch_linattn_backward(const LaunchCtx& lc, const float* qkv, const float* 
   unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
   float* dctx = ws + kCtrCap;
   float* parts = ws + kCtrCap + (int64_t)B * kHeads * (D * D);
-  { cudaError_t le_ = launch_pdl(linattn_bwd_dctx_kernel, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, d_out, parts, counters, dctx, n); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
+  { cudaError_t le_ = launch_pdl(linattn_bwd_dctx_kernel<false>, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, d_out, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)nullptr, parts, counters, dctx, n); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
   { cudaError_t le_ = launch_pdl(linattn_bwd_rows_kernel, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, ctx, kstat, d_out, dctx, d_qkv, n, d_hi, d_lo); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+// ---- tensor-core attention path: launches of the CUDA-core glue kernels ------------------------------------------------
+#define IGM_LAUNCH_PDL(...) do { cudaError_t le_ = launch_pdl(__VA_ARGS__); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); IGM_POST_LAUNCH(lc); } while (0)
+
+// statistics + context from the k / v thirds of the bf16 hi / lo staging pair of the to_qkv output ([M, 384])
+int launch_linattn_ctx_hl(const LaunchCtx& lc, const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo, float* ctx, float* kstat,
+                          int B, int n, float* ws) {
+  const int nsplit = cdiv(n, CH);
+  if (nsplit > kMaxSplit) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linear attention: more than 8192 pixels per image");
+  if (B * kHeads > kCtrCap) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linear attention: batch too large");
+  ProfScope ps_(lc, K_ATTN, 2.0 * B * kHeads * (double)n * D * D, 2.0 * B * (double)n * 2 * HD * 2);
+  unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
+  float* parts = ws + kCtrCap + (int64_t)B * kHeads * (D * D);
+  IGM_LAUNCH_PDL(linattn_ctx_kernel<true>, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, (const float*)nullptr, q_hi, q_lo,
+                 parts, counters, ctx, kstat, n);
+  return IGM_OK;
+}
+
+// dctx[b][h][d][e] = sum_n q[n][d] dO[n][e] from the staging pairs; result at linattn_dctx_ptr(ws)
+float* linattn_dctx_ptr(float* ws) { return ws + kCtrCap; }
+int launch_linattn_dctx_hl(const LaunchCtx& lc, const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo, const __nv_bfloat16* d_hi,
+                           const __nv_bfloat16* d_lo, int B, int n, float* ws) {
+  const int nsplit = cdiv(n, CH);
+  if (nsplit > kMaxSplit) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linear attention: more than 8192 pixels per image");
+  if (B * kHeads > kCtrCap) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linear attention: batch too large");
+  ProfScope ps_(lc, K_ATTN, 2.0 * B * kHeads * (double)n * D * D, 2.0 * B * (double)n * 2 * HD * 2);
+  unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
+  float* dctx = ws + kCtrCap;
+  float* parts = ws + kCtrCap + (int64_t)B * kHeads * (D * D);
+  IGM_LAUNCH_PDL(linattn_bwd_dctx_kernel<true>, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, (const float*)nullptr,
+                 (const float*)nullptr, q_hi, q_lo, d_hi, d_lo, parts, counters, dctx, n);
+  return IGM_OK;
+}
+
+int launch_linattn_wt(const LaunchCtx& lc, const float* m, int transpose, int B, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo,
+                      const float* m2, float* cc) {
+  ProfScope ps_(lc, K_ATTN, 0.0, 4.0 * B * (4096.0 + HD * HD));
+  IGM_LAUNCH_PDL(linattn_wt_kernel, dim3(B), dim3(256), (size_t)0, lc.stream, m, transpose, w_hi, w_lo, m2, cc);
+  return IGM_OK;
+}
+
+int launch_linattn_p(const LaunchCtx& lc, const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo, const float* kstat,
+                     __nv_bfloat16* p_hi, __nv_bfloat16* p_lo, int B, int n) {
+  const int64_t M = (int64_t)B * n;
+  int blocks = (int)cdiv64(M * (HD / 4), 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  ProfScope ps_(lc, K_ATTN, 4.0 * M * HD, 8.0 * M * HD);
+  IGM_LAUNCH_PDL(linattn_p_kernel, dim3(blocks), dim3(256), (size_t)0, lc.stream, q_hi, q_lo, kstat, p_hi, p_lo, M, n);
+  return IGM_OK;
+}
+
+int launch_linattn_dk(const LaunchCtx& lc, const __nv_bfloat16* p_hi, const __nv_bfloat16* p_lo, const float* T, const float* cc,
+                      __nv_bfloat16* d_hi, __nv_bfloat16* d_lo, int B, int n) {
+  const int64_t M = (int64_t)B * n;
+  int blocks = (int)cdiv64(M * (HD / 4), 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  ProfScope ps_(lc, K_ATTN, 2.0 * M * HD, 12.0 * M * HD);
+  IGM_LAUNCH_PDL(linattn_dk_kernel, dim3(blocks), dim3(256), (size_t)0, lc.stream, p_hi, p_lo, T, cc, d_hi, d_lo, M, n);
   return IGM_OK;
 }
 

@@ -263,6 +263,21 @@ int launch_linattn_forward(const LaunchCtx& lc, const float* qkv, float* out, fl
                            int B, int n, float* ws, __nv_bfloat16* out_hi = nullptr, __nv_bfloat16* out_lo = nullptr);
 // inference shortcut (attention.cu: linattn_mb_kernel): context only, then the per-image matrix M_b = W_out ctx^T W_q
 int launch_linattn_ctx(const LaunchCtx& lc, const float* qkv, float* ctx, float* kstat, int B, int n, float* ws);
+// tensor-core attention path (training, n >= 1024): glue kernels around the per-image 1x1 convs of conv_tc.cu; q / k / v
+// and dO come as bf16 hi / lo staging pairs ([M, 384] resp. [M, 128]), d(qkv) leaves as thirds of a [M, 384] pair
+int launch_linattn_ctx_hl(const LaunchCtx& lc, const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo, float* ctx, float* kstat,
+                          int B, int n, float* ws);
+float* linattn_dctx_ptr(float* ws);
+int launch_linattn_dctx_hl(const LaunchCtx& lc, const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo, const __nv_bfloat16* d_hi,
+                           const __nv_bfloat16* d_lo, int B, int n, float* ws);
+// per-image block-diagonal 128 x 128 weight matrices (bf16 hi / lo, [B * 128 rows][128]) from m [B, 4, 32, 32];
+// cc (nullable) [B, 128] = sum_e m[d][e] * m2[d][e]
+int launch_linattn_wt(const LaunchCtx& lc, const float* m, int transpose, int B, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo,
+                      const float* m2 = nullptr, float* cc = nullptr);
+int launch_linattn_p(const LaunchCtx& lc, const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo, const float* kstat,
+                     __nv_bfloat16* p_hi, __nv_bfloat16* p_lo, int B, int n);
+int launch_linattn_dk(const LaunchCtx& lc, const __nv_bfloat16* p_hi, const __nv_bfloat16* p_lo, const float* T, const float* cc,
+                      __nv_bfloat16* d_hi, __nv_bfloat16* d_lo, int B, int n);
 int launch_linattn_mb(const LaunchCtx& lc, const float* ctx, const float* w_out, const float* w_q, int B, int C,
                       __nv_bfloat16* mb_hi, __nv_bfloat16* mb_lo);
 int launch_linattn_backward(const LaunchCtx& lc, const float* qkv, const float* ctx, const float* kstat,

@@ -44,6 +44,7 @@ struct TcArgs {
   float* out0; float* out1;
   const float* add0; const float* add1;
   __nv_bfloat16* hi0; __nv_bfloat16* lo0;
+  int ldh;              // row pitch (elements) of hi0 / lo0: N0, or larger when the output is a channel slice of a wider tensor
   float* gn_part; int gn_cpg, gn_slots;
   // TMA-store epilogue: each epilogue warp stages its 32 rows x 32 channels in swizzled shared memory and one
   // lane issues cp.async.bulk.tensor stores (a warp = box wb x hb x ib pixels of the [B, H, W, C] output)
@@ -307,10 +308,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
           uint8_t* st_l = st_f + 6144;
           if (lane == 0) tma_store_wait_read<0>();         // the previous chunk's stores have drained this staging tile
           __syncwarp();
+          const bool want_f = !first_half || p.out0 != nullptr;   // "lean" output: only the bf16 hi/lo staging copy is kept
+          if (want_f) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(st_f + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(st_f + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
           const bool want_hi = p.hi0 && first_half;
           if (want_hi) {
 #pragma unroll
@@ -331,8 +335,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
             const int x0 = r0 % p.BW;
             const int r2 = r0 / p.BW;
             const int yy = y0 + r2 % p.BH, bb0 = b0 + r2 / p.BH;
-            if (first_half) tma_store_4d(&to0, st_f, n, x0, yy, bb0);
-            else tma_store_4d(&to1, st_f, n - p.N0, x0, yy, bb0);
+            if (!first_half) tma_store_4d(&to1, st_f, n - p.N0, x0, yy, bb0);
+            else if (want_f) tma_store_4d(&to0, st_f, n, x0, yy, bb0);
             if (want_hi) {
               tma_store_4d(&to_hi, st_h, n, x0, yy, bb0);
               tma_store_4d(&to_lo, st_l, n, x0, yy, bb0);
@@ -345,7 +349,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
           // memory transpose to 8-lanes-per-row stores was measured 15-20 % SLOWER on every layer, r1h.)
           float* o;
           const float* ad;
-          if (n < p.N0) { o = p.out0 + opix * p.N0 + n; ad = p.add0 ? p.add0 + opix * p.N0 + n : nullptr; }
+          if (n < p.N0) { o = p.out0 ? p.out0 + opix * p.N0 + n : nullptr; ad = p.add0 ? p.add0 + opix * p.N0 + n : nullptr; }
           else { o = p.out1 + opix * N1 + (n - p.N0); ad = p.add1 ? p.add1 + opix * N1 + (n - p.N0) : nullptr; }
           if (ad) {
 #pragma unroll
@@ -354,13 +358,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
               v[j] += av.x; v[j + 1] += av.y; v[j + 2] += av.z; v[j + 3] += av.w;
             }
           }
+          if (o) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
           if (p.hi0 && n < p.N0) {
             // bf16 hi/lo copy of the output row segment: the next tensor-core conv reads it directly
-            __nv_bfloat16* oh = p.hi0 + opix * p.N0 + n;
-            __nv_bfloat16* ol = p.lo0 + opix * p.N0 + n;
+            __nv_bfloat16* oh = p.hi0 + opix * p.ldh + n;
+            __nv_bfloat16* ol = p.lo0 + opix * p.ldh + n;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               __align__(16) uint32_t h[4], l[4];
@@ -613,13 +619,16 @@ int plan_common(Status& st, TcConv& t, int K, int K0, int N, int GH, int GW, int
 // Rank-5 activation descriptor (channel, x, sub-lattice row, y, image) of a [Bmax, SH, SW, C] bf16 tensor.
 // s2d = false: plain view (C, SW, 1, SH, B).  s2d = true: stride-2 view (2C, SW/2, 2, SH/2, B), where
 // channel index px*C + c addresses pixel column 2x + px and the third coordinate py row 2y + py.
-int encode_act(Status& st, CUtensorMap* m, void* ptr, int C, int SH, int SW, int Bmax, bool s2d, const TcConv& t) {
+// `pitch` (elements, plain view only): distance between consecutive pixels when the C channels are a slice of a wider
+// tensor (the q / k / v thirds of the [M, 384] to_qkv output); 0 = dense.
+int encode_act(Status& st, CUtensorMap* m, void* ptr, int C, int SH, int SW, int Bmax, bool s2d, const TcConv& t, int pitch = 0) {
   auto enc = get_encode_fn();
-  const cuuint64_t rowB = (cuuint64_t)SW * C * 2;
+  if (pitch <= 0) pitch = C;
+  const cuuint64_t rowB = (cuuint64_t)SW * (s2d ? C : pitch) * 2;
   cuuint64_t dims[5], strides[4];
   if (!s2d) {
     dims[0] = C; dims[1] = SW; dims[2] = 1; dims[3] = SH; dims[4] = Bmax;
-    strides[0] = (cuuint64_t)C * 2; strides[1] = rowB; strides[2] = rowB; strides[3] = rowB * SH;
+    strides[0] = (cuuint64_t)pitch * 2; strides[1] = rowB; strides[2] = rowB; strides[3] = rowB * SH;
   } else {
     dims[0] = 2 * (cuuint64_t)C; dims[1] = SW / 2; dims[2] = 2; dims[3] = SH / 2; dims[4] = Bmax;
     strides[0] = (cuuint64_t)C * 4; strides[1] = rowB; strides[2] = 2 * rowB; strides[3] = rowB * SH;
@@ -658,7 +667,7 @@ int tc_plan(Status& st, TcConv& t, int K, int N, int H, int W, int Bmax, int KH,
 }
 
 int tc_plan_img(Status& st, TcConv& t, int K, int N, int H, int W, int Bmax, __nv_bfloat16* a_hi, __nv_bfloat16* a_lo,
-                __nv_bfloat16* w_hi, __nv_bfloat16* w_lo) {
+                __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, int a_pitch) {
   t.valid = false;
   if (!tc_eligible(K, N, H, W, 1)) IGM_FAIL(st, IGM_ERR_INVALID, "shape not eligible for the tcgen05 engine");
   IGM_TRY(plan_common(st, t, K, K, N, H, W, Bmax, 1, w_hi, w_lo, /*per_image=*/true));
@@ -667,8 +676,8 @@ int tc_plan_img(Status& st, TcConv& t, int K, int N, int H, int W, int Bmax, __n
   t.taps[0] = TcTap{0, 0, 0, 0, 0};
   t.Csrc = K;
   t.out_H = H; t.out_W = W; t.sy = t.sx = 1; t.oy_off = t.ox_off = 0;
-  IGM_TRY(encode_act(st, &t.a_hi, a_hi, K, H, W, Bmax, false, t));
-  IGM_TRY(encode_act(st, &t.a_lo, a_lo, K, H, W, Bmax, false, t));
+  IGM_TRY(encode_act(st, &t.a_hi, a_hi, K, H, W, Bmax, false, t, a_pitch));
+  IGM_TRY(encode_act(st, &t.a_lo, a_lo, K, H, W, Bmax, false, t, a_pitch));
   t.a1_hi = t.a_hi; t.a1_lo = t.a_lo;
   t.valid = true;
   return IGM_OK;
@@ -732,12 +741,13 @@ int tc_plan_phase(Status& st, TcConv& t, int K, int N, int GH, int GW, int Bmax,
 
 // [Bmax, H, W, C] output tensor as a rank-4 map (C, W, H, B) whose box is one epilogue warp's 32 pixels x 32 channels
 static int encode_out(Status& st, CUtensorMap* m, const void* ptr, int C, int H, int W, int Bmax, int wb, int hb, int ib,
-                      bool bf16) {
+                      bool bf16, int pitch = 0) {
   auto enc = get_encode_fn();
   if (!enc) IGM_FAIL(st, IGM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t es_b = bf16 ? 2 : 4;
+  if (pitch <= 0) pitch = C;   // > C: the output is a channel slice of a wider [.., pitch] tensor
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Bmax};
-  cuuint64_t strides[3] = {(cuuint64_t)C * es_b, (cuuint64_t)W * C * es_b, (cuuint64_t)H * W * C * es_b};
+  cuuint64_t strides[3] = {(cuuint64_t)pitch * es_b, (cuuint64_t)W * pitch * es_b, (cuuint64_t)H * W * pitch * es_b};
   cuuint32_t box[4] = {32u, (cuuint32_t)wb, (cuuint32_t)hb, (cuuint32_t)ib};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims,
@@ -846,6 +856,9 @@ int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r) {
   a.stage_tx_bytes = 2 * (t.BB * t.BH * t.BW * KC * 2) + 2 * (t.BN * KC * 2);
   a.bias = r.bias; a.out0 = r.out0; a.out1 = r.out1; a.add0 = r.add0; a.add1 = r.add1;
   a.hi0 = r.hi0; a.lo0 = r.lo0;
+  a.ldh = r.ld_hi > 0 ? r.ld_hi : r.N0;
+  if (!r.out0 && !r.hi0) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "conv_tc: no output tensor");
+  if (r.ld_hi > 0 && (r.ld_hi < r.N0 || r.ld_hi % 8 != 0)) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "conv_tc: bad hi/lo output pitch");
   a.gn_part = nullptr; a.gn_cpg = 0; a.gn_slots = 0;
   if (r.gn_part) {
     if (!tc_gn_fusable(t, r.B) || r.N0 != t.N) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "conv_tc: GroupNorm statistics cannot be fused for this plan");
@@ -858,7 +871,7 @@ int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r) {
   if (!tma_store_off && tma_out_geometry(t, wb, hb, ib)) {
     TcConv::OutMaps& om = t.om;
     const int N1 = t.N - r.N0;
-    if (om.p0 != r.out0 || om.n0 != r.N0) {
+    if (r.out0 && (om.p0 != r.out0 || om.n0 != r.N0)) {
       IGM_TRY(encode_out(*lc.st, &om.m0, r.out0, r.N0, t.out_H, t.out_W, t.Bmax, wb, hb, ib, false));
       om.p0 = r.out0; om.n0 = r.N0;
       if (!om.p1) om.m1 = om.m0;
@@ -868,10 +881,11 @@ int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r) {
       IGM_TRY(encode_out(*lc.st, &om.m1, r.out1, N1, t.out_H, t.out_W, t.Bmax, wb, hb, ib, false));
       om.p1 = r.out1; om.n1 = N1;
     }
-    if (r.hi0 && (om.ph != r.hi0 || om.pl != r.lo0)) {
-      IGM_TRY(encode_out(*lc.st, &om.mh, r.hi0, r.N0, t.out_H, t.out_W, t.Bmax, wb, hb, ib, true));
-      IGM_TRY(encode_out(*lc.st, &om.ml, r.lo0, r.N0, t.out_H, t.out_W, t.Bmax, wb, hb, ib, true));
-      om.ph = r.hi0; om.pl = r.lo0;
+    if (r.hi0 && (om.ph != r.hi0 || om.pl != r.lo0 || om.nh != r.N0 || om.ldh != a.ldh)) {
+      IGM_TRY(encode_out(*lc.st, &om.mh, r.hi0, r.N0, t.out_H, t.out_W, t.Bmax, wb, hb, ib, true, a.ldh));
+      IGM_TRY(encode_out(*lc.st, &om.ml, r.lo0, r.N0, t.out_H, t.out_W, t.Bmax, wb, hb, ib, true, a.ldh));
+      om.ph = r.hi0; om.pl = r.lo0; om.nh = r.N0; om.ldh = a.ldh;
+      if (!om.p0) { om.m0 = om.mh; if (!om.p1) om.m1 = om.mh; }   // lean output: the fp32 maps are never dereferenced
     }
     a.tma_out = 1; a.wb = wb; a.hb = hb; a.ib = ib;
   }

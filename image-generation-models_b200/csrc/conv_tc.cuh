@@ -41,7 +41,7 @@ struct TcConv {
   // TMA-store epilogue: output tensor maps, (re-)encoded when a launch passes a new output pointer
   struct OutMaps {
     const void* p0 = nullptr; const void* p1 = nullptr; const void* ph = nullptr; const void* pl = nullptr;
-    int n0 = 0, n1 = 0;
+    int n0 = 0, n1 = 0, nh = 0, ldh = 0;
     alignas(64) CUtensorMap m0, m1, mh, ml;
   };
   mutable OutMaps om;
@@ -63,8 +63,9 @@ int tc_plan_phases4(Status& st, TcConv& t, int K, int N, int GH, int GW, int Bma
                     __nv_bfloat16* a_lo, __nv_bfloat16* w_hi, __nv_bfloat16* w_lo);
 
 // 1x1 convolution whose weights differ per image: weight tensor [Bmax * N rows][K] (image b owns rows b*N .. b*N+N-1)
+// a_pitch > K: the K input channels are a slice of a wider tensor (a_hi / a_lo already point at the slice's first channel)
 int tc_plan_img(Status& st, TcConv& t, int K, int N, int H, int W, int Bmax, __nv_bfloat16* a_hi, __nv_bfloat16* a_lo,
-                __nv_bfloat16* w_hi, __nv_bfloat16* w_lo);
+                __nv_bfloat16* w_hi, __nv_bfloat16* w_lo, int a_pitch = 0);
 
 // Can this (stride-1, non-dilated) conv run on the tensor-core engine?
 bool tc_eligible(int K, int N, int H, int W, int KH);
@@ -81,7 +82,8 @@ struct TcRun {
   float* out0 = nullptr; float* out1 = nullptr; int N0 = 0;
   const float* add0 = nullptr; const float* add1 = nullptr;
   __nv_bfloat16* hi0 = nullptr;   // optional: also emit out0 as bf16 hi/lo (operand staging for the
-  __nv_bfloat16* lo0 = nullptr;   // next tensor-core conv), same [M, N0] layout
+  __nv_bfloat16* lo0 = nullptr;   // next tensor-core conv), same [M, N0] layout; out0 may then be null ("lean")
+  int ld_hi = 0;                  // > N0: hi0 / lo0 are a channel slice of a wider [M, ld_hi] tensor (pointers at the slice)
   // optional fused GroupNorm(8) partial statistics of the output (sum, sum of squares per image,
   // 32-pixel slot and group), layout part[b][slot][8][2]; see tc_gn_fusable()
   float* gn_part = nullptr;

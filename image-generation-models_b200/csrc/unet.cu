@@ -147,6 +147,12 @@ struct AttnL {
   float* ctx = nullptr;    // [B, 4, 32, 32]
   float* kstat = nullptr;  // [B, 4, 32, 2]
   Act out;
+  // tensor-core attention path (training, n >= 1024): q / k / v only exist as the bf16 hi / lo staging pair of the
+  // to_qkv output, every per-pixel contraction is a per-image 1x1 conv on the tcgen05 engine (attention.cu, bottom)
+  bool tcp_ok = false;
+  __nv_bfloat16 *qkv_hi = nullptr, *qkv_lo = nullptr;   // [M, 384]
+  __nv_bfloat16 *w1_hi = nullptr, *w1_lo = nullptr;     // [B][128][128] block-diagonal ctx (forward out = conv(q; ctx))
+  TcConv tc_att_out, tc_att_dq, tc_att_dv, tc_att_t;
   // inference shortcut (n >= 2C): to_out runs with the per-image matrix M_b on LN(x); no attention output tensor
   bool mb_ok = false;
   __nv_bfloat16 *mb_hi = nullptr, *mb_lo = nullptr;   // [B][C][C]
@@ -224,6 +230,12 @@ struct igm_ctx {
   float *t_dproj = nullptr, *t_ws = nullptr;
   float* gn_part = nullptr;
   float* attn_ws = nullptr;   // per-chunk partials of the linear-attention kernels
+  // shared scratch of the tensor-core attention path (one attention block runs at a time): dO and softmax(k) staging
+  // pairs [maxM, 128], the three backward weight matrices [B][128][128] and the normaliser term [B][128]
+  __nv_bfloat16 *att_d_hi = nullptr, *att_d_lo = nullptr, *att_p_hi = nullptr, *att_p_lo = nullptr;
+  __nv_bfloat16 *att_w_hi[3] = {nullptr, nullptr, nullptr}, *att_w_lo[3] = {nullptr, nullptr, nullptr};
+  float* att_cc = nullptr;
+  bool attn_tc = true;        // IGM_ATTN_TC=0: CUDA-core attention kernels everywhere
   float *ws_group = nullptr, *ws_chan = nullptr, *ws_ln = nullptr;
   float *scrA = nullptr, *scrB = nullptr, *scrC = nullptr;
   // bf16x2 staging of an output gradient: a small ring, each conv layer owns one slot (ConvL::dyb, assigned in backward
@@ -333,7 +345,7 @@ struct PlanBuilder {
   Arena ar;
   bool training;
   int B;
-  int64_t maxMC = 0, maxM = 0, maxGnWs = 0, maxDy = 0, halo_w_elems = 0;
+  int64_t maxMC = 0, maxM = 0, maxGnWs = 0, maxDy = 0, halo_w_elems = 0, maxAttTc = 0;
 
   PlanBuilder(igm_ctx& ctx, float* base) : c(ctx), pb{ctx.params} {
     ar.base = base;
@@ -471,6 +483,14 @@ struct PlanBuilder {
     a.kstat = ar.alloc((int64_t)B * kHeads * kDimHead * 2);
     a.out = act(C, H, W, true);
     a.mb_ok = H * W >= 8 * C   /* measured: only pays off when the image has many more pixels than channels */ && H * W >= 128 && C % 64 == 0 && tc_eligible(C, C, H, W, 1);
+    a.tcp_ok = training && H * W >= 1024 && tc_eligible(hd, hd, H, W, 1) && tc_eligible(C, 3 * hd, H, W, 1);
+    if (a.tcp_ok) {
+      a.qkv_hi = reinterpret_cast<__nv_bfloat16*>(ar.alloc((M(H, W) * 3 * hd + 1) / 2));
+      a.qkv_lo = reinterpret_cast<__nv_bfloat16*>(ar.alloc((M(H, W) * 3 * hd + 1) / 2));
+      a.w1_hi = reinterpret_cast<__nv_bfloat16*>(ar.alloc(((int64_t)B * hd * hd + 1) / 2));
+      a.w1_lo = reinterpret_cast<__nv_bfloat16*>(ar.alloc(((int64_t)B * hd * hd + 1) / 2));
+      maxAttTc = std::max(maxAttTc, M(H, W));
+    }
     if (a.mb_ok) {
       a.mb_hi = reinterpret_cast<__nv_bfloat16*>(ar.alloc(((int64_t)B * C * C + 1) / 2));
       a.mb_lo = reinterpret_cast<__nv_bfloat16*>(ar.alloc(((int64_t)B * C * C + 1) / 2));
@@ -602,6 +622,14 @@ struct PlanBuilder {
       c.noise_copy = ar.alloc((int64_t)B * cfg.channels * HW0);
       c.d_pred = ar.alloc((int64_t)B * cfg.channels * HW0);
     }
+    if (maxAttTc > 0) {
+      const int64_t hd = kHeads * kDimHead;
+      auto bf = [&](int64_t n) { return reinterpret_cast<__nv_bfloat16*>(ar.alloc((n + 1) / 2)); };
+      c.att_d_hi = bf(maxAttTc * hd); c.att_d_lo = bf(maxAttTc * hd);
+      c.att_p_hi = bf(maxAttTc * hd); c.att_p_lo = bf(maxAttTc * hd);
+      for (int k = 0; k < 3; ++k) { c.att_w_hi[k] = bf((int64_t)B * hd * hd); c.att_w_lo[k] = bf((int64_t)B * hd * hd); }
+      c.att_cc = ar.alloc((int64_t)B * hd);
+    }
     if (maxDy > 0) {
       for (int k = 0; k < igm_ctx::kDyBufs; ++k) {
         c.dy_hi[k] = reinterpret_cast<__nv_bfloat16*>(ar.alloc((maxDy + 1) / 2));
@@ -665,8 +693,16 @@ struct Runner {
     return IGM_OK;
   }
 
+  // optional by-product of the NEXT conv_dgrad on the tensor-core engine: its output also (lean: only) as a bf16 hi / lo pair
+  __nv_bfloat16 *dg_hi = nullptr, *dg_lo = nullptr;
+  bool dg_lean = false;
   int64_t M(int H, int W) const { return (int64_t)B * H * W; }
   bool tc_on() const { return c.conv_engine == 1; }
+  // tensor-core attention path for this block?  (training forward / backward only; the sampler keeps the M_b shortcut)
+  bool attn_tcp(const AttnL& a) const {
+    return c.attn_tc && a.tcp_ok && tc_on() && !infer && c.cfg.training && a.tc_att_out.valid && a.qkv.tc_f.valid &&
+           a.qkv.tc_b.valid && tcw_batch_ok(a.qkv.tc_w, B) && a.outc.tc_b.valid;
+  }
   bool use_tc(const TcConv& t) const { return tc_on() && t.valid; }
   bool use_pair(const TcConvPair& t) const { return tc_on() && conv_pair_on() && t.valid; }
   // bf16 staging pointers of an activation: only handed to producers while the tcgen05 engine is on
@@ -725,6 +761,11 @@ struct Runner {
       TcRun r;
       r.B = B; r.bias = nullptr; r.out0 = d0; r.out1 = d1; r.N0 = C0; r.add0 = add0; r.add1 = add1;
       r.kclass = K_CONV_DGRAD;
+      if (dg_hi && !d1) {
+        r.hi0 = dg_hi; r.lo0 = dg_lo;
+        if (dg_lean) r.out0 = nullptr;
+        return launch_conv_tc(lc, l.tc_b, r);
+      }
       if (use_pair(l.tcp_b)) return launch_conv_tc2(lc, l.tcp_b, r);
       return launch_conv_tc(lc, l.tc_b, r);
     }
@@ -932,6 +973,24 @@ struct Runner {
     const int64_t m = M(H, W);
     const float* x = a.in->v;
     IGM_TRY(launch_ln_forward(lc, x, c.Pp(a.ln_g), c.Pp(a.ln_b), lean_ok(a.qkv) ? nullptr : a.ln.v, m, a.C, hi(a.ln), lo(a.ln)));
+    if (attn_tcp(a)) {
+      const int hd = kHeads * kDimHead;
+      {   // to_qkv (no bias): only the bf16 hi / lo staging pair of q | k | v is written
+        TcRun r;
+        r.B = B; r.N0 = 3 * hd; r.hi0 = a.qkv_hi; r.lo0 = a.qkv_lo; r.kclass = K_CONV_FPROP;
+        IGM_TRY(launch_conv_tc(lc, a.qkv.tc_f, r));
+      }
+      IGM_TRY(launch_linattn_ctx_hl(lc, a.qkv_hi, a.qkv_lo, a.ctx, a.kstat, B, H * W, c.attn_ws));
+      IGM_TRY(launch_linattn_wt(lc, a.ctx, 0, B, a.w1_hi, a.w1_lo));
+      {   // out = conv(q; ctx): [M, 128] x per-image block-diagonal 128 x 128 on the tensor cores
+        TcRun r;
+        r.B = B; r.N0 = hd; r.out0 = lean_ok(a.outc) ? nullptr : a.att.v; r.hi0 = hi(a.att); r.lo0 = lo(a.att);
+        r.kclass = K_ATTN;
+        IGM_TRY(launch_conv_tc(lc, a.tc_att_out, r));
+      }
+      IGM_TRY(conv_fwd(a.outc, H, W, H, W, 1, 0, a.out.v, x, &a.out));
+      return IGM_OK;
+    }
     IGM_TRY(conv_fwd(a.qkv, H, W, H, W, 1, 0, a.qkv_t, nullptr));
     if (c.attn_mb && (infer || !c.cfg.training) && tc_on() && a.tc_mb.valid && use_tc(a.qkv.tc_f)) {
       // inference, n >= 2C: y = (W_out ctx^T W_q) LN(x) + b + x with one C x C matrix per image
@@ -951,6 +1010,33 @@ struct Runner {
     const int H = a.H, W = a.W;
     const int64_t m = M(H, W);
     const float* d_out = a.out.g;
+    if (attn_tcp(a)) {
+      const int hd = kHeads * kDimHead, n = H * W;
+      // to_out backward: its data gradient dO leaves only as a staging pair
+      dg_hi = c.att_d_hi; dg_lo = c.att_d_lo; dg_lean = true;
+      const int rc0 = conv_bwd(a.outc, H, W, d_out, c.scrB, nullptr, nullptr, nullptr);
+      dg_hi = dg_lo = nullptr; dg_lean = false;
+      IGM_TRY(rc0);
+      IGM_TRY(launch_linattn_dctx_hl(lc, a.qkv_hi, a.qkv_lo, c.att_d_hi, c.att_d_lo, B, n, c.attn_ws));
+      const float* dctx = linattn_dctx_ptr(c.attn_ws);
+      IGM_TRY(launch_linattn_wt(lc, a.ctx, 1, B, c.att_w_hi[0], c.att_w_lo[0]));                       // dq = conv(dO; ctx^T)
+      IGM_TRY(launch_linattn_wt(lc, dctx, 0, B, c.att_w_hi[1], c.att_w_lo[1], a.ctx, c.att_cc));       // dv = conv(p; dctx), c
+      IGM_TRY(launch_linattn_wt(lc, dctx, 1, B, c.att_w_hi[2], c.att_w_lo[2]));                        // T = conv(v; dctx^T)
+      IGM_TRY(launch_linattn_p(lc, a.qkv_hi, a.qkv_lo, a.kstat, c.att_p_hi, c.att_p_lo, B, n));
+      IGM_TRY(before_dy_write(a.qkv));
+      __nv_bfloat16 *dh = dyh(a.qkv), *dl = dyl(a.qkv);
+      TcRun r;
+      r.B = B; r.N0 = hd; r.ld_hi = 3 * hd; r.kclass = K_ATTN;
+      r.hi0 = dh; r.lo0 = dl;
+      IGM_TRY(launch_conv_tc(lc, a.tc_att_dq, r));
+      r.hi0 = dh + 2 * hd; r.lo0 = dl + 2 * hd;
+      IGM_TRY(launch_conv_tc(lc, a.tc_att_dv, r));
+      TcRun rt;
+      rt.B = B; rt.N0 = hd; rt.out0 = c.scrB; rt.kclass = K_ATTN;
+      IGM_TRY(launch_conv_tc(lc, a.tc_att_t, rt));
+      IGM_TRY(launch_linattn_dk(lc, c.att_p_hi, c.att_p_lo, c.scrB, c.att_cc, dh, dl, B, n));
+      IGM_TRY(conv_bwd(a.qkv, H, W, c.scrC, c.scrA, nullptr, nullptr, nullptr, /*staged=*/true));
+    } else {
     IGM_TRY(conv_bwd(a.outc, H, W, d_out, c.scrB, nullptr, nullptr, nullptr));
     // to_qkv has no bias: when both of its backward convs run on the tensor cores they only read the bf16 hi/lo
     // staging copy of d(qkv), which the attention backward then writes directly (no fp32 tensor, no split pass)
@@ -959,6 +1045,7 @@ struct Runner {
     IGM_TRY(launch_linattn_backward(lc, a.qkv_t, a.ctx, a.kstat, c.scrB, direct ? nullptr : c.scrC, B, H * W, c.attn_ws,
                                     direct ? dyh(a.qkv) : nullptr, direct ? dyl(a.qkv) : nullptr));
     IGM_TRY(conv_bwd(a.qkv, H, W, c.scrC, c.scrA, nullptr, nullptr, nullptr, direct));
+    }
     if (!side_active())
       return launch_ln_backward(lc, c.scrA, a.in->v, c.Pp(a.ln_g), d_out, dx, c.Gp(a.ln_g), c.Gp(a.ln_b), c.ws_ln, m, a.C);
     // the fold of the per-CTA partials into d(gamma), d(beta) feeds nothing downstream: side stream; the next LayerNorm
@@ -1267,8 +1354,17 @@ static int plan_tc(igm_ctx* c) {
     n_valid += (l.tc_f.valid ? 1 : 0) + (l.tc_b.valid ? 1 : 0) + (l.tc_w.valid ? 1 : 0);
     return IGM_OK;
   });
-  // per-image to_out convs of the inference attention shortcut
+  // per-image to_out convs of the inference attention shortcut, and the per-image 1x1 convs of the tensor-core
+  // attention path (operands: thirds of the [M, 384] qkv staging pair, pitch 384)
   auto plan_mb = [&](AttnL& a) -> int {
+    if (a.tcp_ok && a.qkv_hi && c->att_d_hi) {
+      const int hd = kHeads * kDimHead, Bm = c->cfg.max_batch;
+      IGM_TRY(tc_plan_img(c->st, a.tc_att_out, hd, hd, a.H, a.W, Bm, a.qkv_hi, a.qkv_lo, a.w1_hi, a.w1_lo, 3 * hd));
+      IGM_TRY(tc_plan_img(c->st, a.tc_att_dq, hd, hd, a.H, a.W, Bm, c->att_d_hi, c->att_d_lo, c->att_w_hi[0], c->att_w_lo[0]));
+      IGM_TRY(tc_plan_img(c->st, a.tc_att_dv, hd, hd, a.H, a.W, Bm, c->att_p_hi, c->att_p_lo, c->att_w_hi[1], c->att_w_lo[1]));
+      IGM_TRY(tc_plan_img(c->st, a.tc_att_t, hd, hd, a.H, a.W, Bm, a.qkv_hi + 2 * hd, a.qkv_lo + 2 * hd, c->att_w_hi[2],
+                          c->att_w_lo[2], 3 * hd));
+    }
     if (!a.mb_ok || !a.ln.hi) return IGM_OK;
     return tc_plan_img(c->st, a.tc_mb, a.C, a.C, a.H, a.W, c->cfg.max_batch, a.ln.hi, a.ln.lo, a.mb_hi, a.mb_lo);
   };
@@ -1413,6 +1509,7 @@ int igm_unet_create(igm_ctx** out, const igm_unet_cfg* cfg, int device) {
     if (ps[0] == '1') cudaDeviceSetCacheConfig(cudaFuncCachePreferShared);
   }
   if (const char* mbe = getenv("IGM_ATTN_MB")) c->attn_mb = !(mbe[0] == '0');
+  if (const char* ate = getenv("IGM_ATTN_TC")) c->attn_tc = !(ate[0] == '0');
   const char* halo = getenv("IGM_WGRAD_HALO");
   c->halo_on = !(halo && halo[0] == '0');
   const char* eng = getenv("IGM_CONV_ENGINE");
