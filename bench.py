@@ -274,7 +274,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        opts = None
+        if os.environ.get("IGM_NCCL_PRIO") == "1":   # experiment: NCCL kernels on a high-priority stream
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     if args.config == "vqvae":
         import bench_secondary
         line = bench_secondary.run_vqvae(args, dev, rank, world)

@@ -601,6 +601,10 @@ int plan_common(Status& st, TcConv& t, int K, int K0, int N, int GH, int GW, int
     const int64_t t128 = tiles_m * (N / 128), t64 = tiles_m * (N / 64);
     const int64_t cost128 = cdiv64(t128, 148) * 2, cost64 = cdiv64(t64, 148);
     if (cost64 < cost128) t.BN = 64;
+    // experiment switch IGM_TC_BN=64: 64-wide tiles also where the 128-wide plan leaves a CTA with at most two tiles
+    // (its fill and its 128-column epilogue are then not hidden behind MMAs of a following tile)
+    static const int bn_mode = [] { const char* e = getenv("IGM_TC_BN"); return e ? atoi(e) : 0; }();
+    if (bn_mode == 64 && t128 <= 2 * 148 && !per_image) t.BN = 64;
   }
   // weights: [N rows][wtaps*K cols], K-major
   for (int which = 0; which < 2; ++which) {

@@ -236,6 +236,7 @@ struct igm_ctx {
   __nv_bfloat16 *att_w_hi[3] = {nullptr, nullptr, nullptr}, *att_w_lo[3] = {nullptr, nullptr, nullptr};
   float* att_cc = nullptr;
   bool attn_tc = true;        // IGM_ATTN_TC=0: CUDA-core attention kernels everywhere
+  int64_t attn_tc_min_pix = 65536;   // IGM_ATTN_TC_MIN=<pixels per launch> from which the tensor-core path is taken
   float *ws_group = nullptr, *ws_chan = nullptr, *ws_ln = nullptr;
   float *scrA = nullptr, *scrB = nullptr, *scrC = nullptr;
   // bf16x2 staging of an output gradient: a small ring, each conv layer owns one slot (ConvL::dyb, assigned in backward
@@ -700,8 +701,10 @@ struct Runner {
   bool tc_on() const { return c.conv_engine == 1; }
   // tensor-core attention path for this block?  (training forward / backward only; the sampler keeps the M_b shortcut)
   bool attn_tcp(const AttnL& a) const {
-    return c.attn_tc && a.tcp_ok && tc_on() && !infer && c.cfg.training && a.tc_att_out.valid && a.qkv.tc_f.valid &&
-           a.qkv.tc_b.valid && tcw_batch_ok(a.qkv.tc_w, B) && a.outc.tc_b.valid;
+    // measured (profiles/r2_attention.md): the path pays for itself from ~64 K pixels per launch on; below that its
+    // twelve launches per block lose against the four of the CUDA-core kernels
+    return c.attn_tc && a.tcp_ok && tc_on() && !infer && c.cfg.training && (int64_t)B * a.H * a.W >= c.attn_tc_min_pix &&
+           a.tc_att_out.valid && a.qkv.tc_f.valid && a.qkv.tc_b.valid && tcw_batch_ok(a.qkv.tc_w, B) && a.outc.tc_b.valid;
   }
   bool use_tc(const TcConv& t) const { return tc_on() && t.valid; }
   bool use_pair(const TcConvPair& t) const { return tc_on() && conv_pair_on() && t.valid; }
@@ -1510,6 +1513,7 @@ int igm_unet_create(igm_ctx** out, const igm_unet_cfg* cfg, int device) {
   }
   if (const char* mbe = getenv("IGM_ATTN_MB")) c->attn_mb = !(mbe[0] == '0');
   if (const char* ate = getenv("IGM_ATTN_TC")) c->attn_tc = !(ate[0] == '0');
+  if (const char* atm = getenv("IGM_ATTN_TC_MIN")) c->attn_tc_min_pix = atoll(atm);
   const char* halo = getenv("IGM_WGRAD_HALO");
   c->halo_on = !(halo && halo[0] == '0');
   const char* eng = getenv("IGM_CONV_ENGINE");

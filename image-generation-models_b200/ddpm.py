@@ -250,6 +250,7 @@ class Unet(nn.Module):
                 mod._parameters[key] = q
         self._flat, self._flat_grad, self._layout = flat, grad, layout
         self._pend, self._pend_gen = None, 0
+        self._zero_version = None
         self._fwd_gen = getattr(self, "_fwd_gen", 0) + 1
         self._synced = False
         self._comm = None
@@ -276,6 +277,9 @@ class Unet(nn.Module):
                 p.grad = self._flat_grad[off:off + p.numel()].view(shape)
         if zero:
             self._flat_grad.zero_()
+            # torch bumps the version counter on every in-place edit: while it stays at this value the arena is known to
+            # be all zeros (the kernels' own writes do not bump it; _reduce_into_grad clears the mark after a backward)
+            self._zero_version = self._flat_grad._version
 
     def _bind_grad_target(self, which: str):
         """Point the engine's weight-gradient kernels at ``.grad``'s arena ("grad") or at the pending arena of an eager
@@ -399,25 +403,41 @@ def _check_gen(unet: Unet, gen: int):
                            "before running another forward / sampler step through the same Unet")
 
 
-def _reduce_into_grad(unet: Unet, e: "_Engine", run_backward, d_scale: float = 1.0):
-    """Backward into ``.grad`` with torch's accumulate semantics.  One rank: the kernels add straight into the ``.grad``
-    arena.  Data parallel: this backward's gradients go to the pending arena, ONLY that delta is all-reduced (reducing the
-    accumulated ``.grad`` arena would re-reduce earlier micro-batches), and ``.grad += delta / world``."""
+def _reduce_into_grad(unet: Unet, e: "_Engine", run_backward, d_scale: float = 1.0, scalable: bool = False):
+    """Backward into ``.grad`` with torch's accumulate semantics.  ``run_backward(scale)`` enqueues the kernels with the
+    seed gradient multiplied by ``scale``.  One rank: the kernels add straight into the ``.grad`` arena.  Data parallel:
+    this backward's gradients go to the pending arena, ONLY that delta is all-reduced (reducing the accumulated ``.grad``
+    arena would re-reduce earlier micro-batches), and ``.grad += delta / world``.  When ``.grad`` is known to be all zeros
+    (``zero_grad()`` just ran, the common loop) the delta IS the arena: the kernels write into it directly with the seed
+    scaled by 1 / world and the arena is all-reduced in place -- no memset of the pending arena, no axpy pass."""
     sync = _world() > 1 and getattr(unet, "ddp_sync", True)
+    overlap = getattr(unet, "ddp_overlap", _DDP_OVERLAP)
     if not sync:
         unet._bind_grad_target("grad")
-        run_backward()
+        run_backward(1.0)
+        unet._zero_version = None
+        return
+    zv = unet._zero_version
+    if scalable and zv is not None and zv == unet._flat_grad._version and unet._flat_grad.is_cuda:
+        unet._bind_grad_target("grad")
+        run_backward(d_scale / _world())
+        if overlap:
+            _allreduce_overlapped(unet, e, unet._flat_grad)
+        else:
+            _allreduce(unet, unet._flat_grad)
+        unet._zero_version = None
         return
     unet._bind_grad_target("pend")
     unet._pend.zero_()
-    run_backward()
-    if unet._pend.is_cuda and getattr(unet, "ddp_overlap", _DDP_OVERLAP):
+    run_backward(1.0)
+    if unet._pend.is_cuda and overlap:
         _allreduce_overlapped(unet, e, unet._pend)
     else:
         _allreduce(unet, unet._pend)
     e.check(e.lib.igm_grad_axpy(e.ctx, _ptr(unet._flat_grad), _ptr(unet._pend), None, C.c_float(d_scale / _world()),
                                 unet._flat_grad.numel(), _stream()))
     unet._pend_gen += 1    # the pending arena no longer holds an eager training_step's gradients
+    unet._zero_version = None
 
 
 class _UnetFn(torch.autograd.Function):
@@ -438,7 +458,7 @@ class _UnetFn(torch.autograd.Function):
         d_out = _f32c(d_out)
         dx = torch.empty_like(d_out) if ctx.need_dx else None
         # parameter gradients are the MEAN over ranks (like DistributedDataParallel); dx stays this rank's own
-        _reduce_into_grad(unet, e, lambda: e.check(e.lib.igm_unet_backward(e.ctx, _ptr(d_out), _ptr(dx), _stream())))
+        _reduce_into_grad(unet, e, lambda scale: e.check(e.lib.igm_unet_backward(e.ctx, _ptr(d_out), _ptr(dx), _stream())))
         return None, None, dx, None
 
 
@@ -783,10 +803,11 @@ class _PLossesFn(torch.autograd.Function):
                                    "training_step; call backward() before the next one")
             e.check(e.lib.igm_grad_axpy(e.ctx, _ptr(unet._flat_grad), _ptr(unet._pend), _ptr(d_loss), C.c_float(1.0),
                                         unet._flat_grad.numel(), _stream()))
+            unet._zero_version = None
             return None, None, None, None, None, None
         _check_gen(unet, ctx.fgen)
-        _reduce_into_grad(unet, e, lambda: e.check(e.lib.igm_ddpm_p_losses_backward(e.ctx, _ptr(d_loss), C.c_float(1.0),
-                                                                                    _stream())))
+        _reduce_into_grad(unet, e, lambda scale: e.check(e.lib.igm_ddpm_p_losses_backward(e.ctx, _ptr(d_loss), C.c_float(scale),
+                                                                                          _stream())), scalable=True)
         return None, None, None, None, None, None
 
 

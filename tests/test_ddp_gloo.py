@@ -135,10 +135,10 @@ def _accum_worker(rank, world, port, out_path):
     for k in range(2):                                    # two micro-batches, no zero_grad in between
         fake = torch.randn(n, generator=_micro(rank, k))  # this rank's gradient of micro-batch k
 
-        def run_backward():
+        def run_backward(scale):
             target = unet._pend if eng.grad_target == "pend" else unet._flat_grad
-            target += fake                                # the kernels ACCUMULATE into the bound arena
-        D._reduce_into_grad(unet, eng, run_backward)
+            target.data += scale * fake                   # the kernels ACCUMULATE into the bound arena (no version bump)
+        D._reduce_into_grad(unet, eng, run_backward, scalable=True)
     if rank == 0:
         torch.save(unet._flat_grad.clone(), out_path)
     dist.barrier()
