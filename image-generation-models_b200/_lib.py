@@ -60,7 +60,7 @@ SYMBOLS = {
     "igm_pixelcnn_workspace_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "igm_pixelcnn_run": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_int, _P]),
-    "igm_conv2d_workspace_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "igm_conv2d_workspace_floats": (C.c_int64, [C.c_int] * 13),
     "igm_conv2d_forward": (C.c_int, [_P, _P, _P, _P, _P] + [C.c_int] * 14 + [_P, _P]),
     "igm_conv2d_backward": (C.c_int, [_P, _P, _P, _P, _P, _P] + [C.c_int] * 14 + [_P, _P]),
     "igm_act_forward": (C.c_int, [C.c_int, _P, _P, C.c_int64, _P, C.c_int64, C.c_int, _P]),

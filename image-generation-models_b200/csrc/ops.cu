@@ -159,12 +159,26 @@ int check_geo(Status& st, const Geo& g) {
 }
 
 }  // namespace
+
+// tensor-core route (ops_tc.cu)
+bool ops_tc_geo_ok(int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_h, int pad_w, int dil, int OH, int OW);
+int64_t ops_tc_ws_floats(int B, int H, int W, int Cin, int Cout, int KH);
+int ops_tc_conv_forward(const LaunchCtx& lc, const float* x, const float* w, const float* bias, const float* residual, float* y,
+                        int B, int H, int W, int Cin, int Cout, int KH, int transposed, float* ws);
+int ops_tc_conv_backward(const LaunchCtx& lc, const float* x, const float* w, const float* dy, float* dx, float* dw, int B, int H,
+                         int W, int Cin, int Cout, int KH, int transposed, float* ws, int* did_dw);
 }  // namespace igm
 
 using namespace igm;
 
-// workspace floats a conv forward / backward call needs (packed weights)
-extern "C" int64_t igm_conv2d_workspace_floats(int Cin, int Cout, int KH, int KW) { return (int64_t)KH * KW * Cin * Cout + 64; }
+// workspace floats a conv forward / backward call needs: the fp32 packed weights of the CUDA-core engine, followed (when the
+// geometry qualifies for the tensor-core route) by the bf16 weight / activation / gradient staging pairs
+extern "C" int64_t igm_conv2d_workspace_floats(int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_h,
+                                               int pad_w, int dil, int OH, int OW) {
+  int64_t n = (int64_t)KH * KW * Cin * Cout + 64;
+  if (ops_tc_geo_ok(H, W, Cin, Cout, KH, KW, stride, pad_h, pad_w, dil, OH, OW)) n += ops_tc_ws_floats(B, H, W, Cin, Cout, KH);
+  return n;
+}
 
 // y[B,OH,OW,Cout] = conv(x[B,H,W,Cin]) (+bias).  transposed = 0: Conv2d, weight OIHW [Cout,Cin,KH,KW];
 // transposed = 1: ConvTranspose2d, weight IOHW [Cin,Cout,KH,KW].  Dilation applies to Conv2d only.
@@ -180,6 +194,8 @@ extern "C" int igm_conv2d_forward(const float* x, const float* w, const float* b
   int64_t n = 0;
   LaunchCtx lc = make_lc(st, n, stream);
   const int KK = KH * KW;
+  if (ops_tc_geo_ok(H, W, Cin, Cout, KH, KW, stride, pad_h, pad_w, dil, OH, OW))
+    return ops_tc_conv_forward(lc, x, w, bias, residual, y, B, H, W, Cin, Cout, KH, transposed, ws + (int64_t)KK * Cin * Cout + 64);
   // packed [tap][ci][co]
   if (!transposed) IGM_TRY(launch_pack_weight(lc, w, ws, KK, Cin, Cout, KK, (int64_t)Cin * KK));
   else IGM_TRY(launch_pack_weight(lc, w, ws, KK, Cin, Cout, (int64_t)Cout * KK, KK));
@@ -202,6 +218,12 @@ extern "C" int igm_conv2d_backward(const float* x, const float* w, const float* 
   int64_t n = 0;
   LaunchCtx lc = make_lc(st, n, stream);
   const int KK = KH * KW;
+  if (ops_tc_geo_ok(H, W, Cin, Cout, KH, KW, stride, pad_h, pad_w, dil, OH, OW)) {
+    int did_dw = 0;
+    IGM_TRY(ops_tc_conv_backward(lc, x, w, dy, dx, dw, B, H, W, Cin, Cout, KH, transposed, ws + (int64_t)KK * Cin * Cout + 64, &did_dw));
+    dx = nullptr;                 // done on the tensor cores
+    if (did_dw) dw = nullptr;
+  }
   if (dx) {
     // packed [tap][co][ci]; the data gradient of a Conv2d is a transposed gather and vice versa
     if (!transposed) IGM_TRY(launch_pack_weight(lc, w, ws, KK, Cout, Cin, (int64_t)Cin * KK, KK));

@@ -28,7 +28,20 @@ import os
 from . import _lib
 
 _EAGER_BWD = os.environ.get("IGM_EAGER_BWD", "1") != "0"
-_DDP_OVERLAP = os.environ.get("IGM_DDP_OVERLAP", "1") != "0"   # bucketed gradient all-reduce overlapped with backward
+# Bucketed gradient all-reduce overlapped with backward: IGM_DDP_OVERLAP=1 / 0 forces it on / off; by default it is used
+# from 64 MB of gradients on.  Measured on B200 (profiles/r2_scaling.md): NCCL's CTAs cannot co-reside with the persistent
+# one-CTA-per-SM conv kernels, so the overlap is worth +0.4 ... +0.9 % on the 119 MB CelebA-64 arena and -0.3 ... 0 % on
+# the 30.5 MB CIFAR-10 arena, where one all-reduce after the backward pass is as good.
+_DDP_OVERLAP_ENV = os.environ.get("IGM_DDP_OVERLAP", "auto")
+
+
+def _ddp_overlap(unet) -> bool:
+    v = getattr(unet, "ddp_overlap", None)
+    if v is not None:
+        return bool(v)
+    if _DDP_OVERLAP_ENV in ("0", "1"):
+        return _DDP_OVERLAP_ENV == "1"
+    return unet._flat.numel() * 4 >= (64 << 20)
 
 try:  # the real Lightning base class when it is installed, a minimal stand-in otherwise
     from pytorch_lightning import LightningModule as _LightningModule  # type: ignore
@@ -411,7 +424,7 @@ def _reduce_into_grad(unet: Unet, e: "_Engine", run_backward, d_scale: float = 1
     (``zero_grad()`` just ran, the common loop) the delta IS the arena: the kernels write into it directly with the seed
     scaled by 1 / world and the arena is all-reduced in place -- no memset of the pending arena, no axpy pass."""
     sync = _world() > 1 and getattr(unet, "ddp_sync", True)
-    overlap = getattr(unet, "ddp_overlap", _DDP_OVERLAP)
+    overlap = _ddp_overlap(unet)
     if not sync:
         unet._bind_grad_target("grad")
         run_backward(1.0)
@@ -783,7 +796,7 @@ class _PLossesFn(torch.autograd.Function):
         sync = _world() > 1 and getattr(unet, "ddp_sync", True)
         e.check(e.lib.igm_ddpm_p_losses_backward(e.ctx, None, C.c_float(1.0 / _world() if sync else 1.0), _stream()))
         if sync:
-            if getattr(unet, "ddp_overlap", _DDP_OVERLAP):
+            if _ddp_overlap(unet):
                 _allreduce_overlapped(unet, e, unet._pend)
             else:
                 _allreduce(unet, unet._pend)

@@ -28,9 +28,12 @@ def _cl(x):
     return x.contiguous(memory_format=CL)
 
 
-def _ws(weight):
+def _ws(weight, geo):
+    """Scratch of one conv call: packed weights, plus the bf16 operand staging of the tensor-core route when the geometry
+    (B, H, W, Cin, Cout, KH, KW, stride, pad_h, pad_w, dil, transposed, OH, OW) qualifies for it."""
     lib = _lib.load()
-    n = lib.igm_conv2d_workspace_floats(weight.shape[0], weight.shape[1], weight.shape[2], weight.shape[3])
+    B, H, W, Cin, Cout, KH, KW, stride, pad_h, pad_w, dil, _transposed, OH, OW = geo
+    n = lib.igm_conv2d_workspace_floats(B, H, W, Cin, Cout, KH, KW, stride, pad_h, pad_w, dil, OH, OW)
     return torch.empty(int(n), dtype=torch.float32, device=weight.device)
 
 
@@ -59,7 +62,7 @@ class _ConvFn(torch.autograd.Function):
             r = _cl(residual)
             if r.shape != y.shape:
                 raise ValueError(f"residual shape {tuple(r.shape)} != conv output {tuple(y.shape)}")
-        rc = lib.igm_conv2d_forward(_ptr(x), _ptr(w), _ptr(b), _ptr(r), _ptr(y), *geo, _ptr(_ws(w)), _stream())
+        rc = lib.igm_conv2d_forward(_ptr(x), _ptr(w), _ptr(b), _ptr(r), _ptr(y), *geo, _ptr(_ws(w, geo)), _stream())
         _lib.check(None, rc)
         ctx.save_for_backward(x, w)
         ctx.geo = geo
@@ -75,7 +78,7 @@ class _ConvFn(torch.autograd.Function):
         dx = torch.empty_like(x, memory_format=CL) if ctx.needs_input_grad[0] else None
         dw = torch.zeros_like(w) if ctx.needs_input_grad[1] else None
         db = torch.zeros(ctx.geo[4], device=x.device) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
-        rc = lib.igm_conv2d_backward(_ptr(x), _ptr(w), _ptr(dy), _ptr(dx), _ptr(dw), _ptr(db), *ctx.geo, _ptr(_ws(w)),
+        rc = lib.igm_conv2d_backward(_ptr(x), _ptr(w), _ptr(dy), _ptr(dx), _ptr(dw), _ptr(db), *ctx.geo, _ptr(_ws(w, ctx.geo)),
                                      _stream())
         _lib.check(None, rc)
         dres = dy if (ctx.has_res and ctx.needs_input_grad[3]) else None

@@ -185,11 +185,14 @@ int igm_pixelcnn_run(const float* weights, float* img, const float* uniforms, co
                      int mode, int normalize, void* stream);
 
 /* ---- generic operators (secondary models: VQ-VAE encoder/decoder, PixelCNN training) --------- */
-/* NHWC fp32 tensors (= torch channels_last); fp32 CUDA-core engine; context-free, errors via
- * igm_last_error(NULL).  ws: igm_conv2d_workspace_floats(...) floats of scratch (packed weights).
+/* NHWC fp32 tensors (= torch channels_last); context-free, errors via igm_last_error(NULL).  Stride-1 1x1 / 3x3 "same"
+ * convolutions with 64-multiple channel counts run on the tcgen05 bf16x3 engine (operands split and weights re-packed
+ * per call into ws; IGM_OPS_TC=0 disables), everything else on the fp32 CUDA-core engine.
+ * ws: igm_conv2d_workspace_floats(<the call's geometry>) floats of scratch.
  * transposed = 0: nn.Conv2d (weight OIHW, dilation allowed); 1: nn.ConvTranspose2d (weight IOHW).
  * Used behind src/networks/vqvae.py:5-136 and src/models/pixelcnn.py:12-82,:128-165. */
-int64_t igm_conv2d_workspace_floats(int Cin, int Cout, int KH, int KW);
+int64_t igm_conv2d_workspace_floats(int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_h,
+                                    int pad_w, int dil, int OH, int OW);
 int igm_conv2d_forward(const float* x, const float* w, const float* bias, const float* residual, float* y,
                        int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_h,
                        int pad_w, int dil, int transposed, int OH, int OW, float* ws, void* stream);

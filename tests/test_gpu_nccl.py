@@ -61,11 +61,11 @@ def _worker(rank, world, port, out_path):
     res["lazy2"] = unet._flat_grad.clone().cpu()
     res["params"] = unet._flat.clone().cpu()
     # bucketed exchange
-    unet.ddp_buckets = 3
+    unet.ddp_buckets = 3; unet.ddp_overlap = False
     unet.attach_grads(zero=True)
     gd.p_losses(xs, ts, ns).backward()
     res["lazy_b3"] = unet._flat_grad.clone().cpu()
-    unet.ddp_buckets = 1
+    unet.ddp_buckets = 1; unet.ddp_overlap = True
     # eager path (what DDPM.training_step uses)
     unet.attach_grads(zero=True)
     gd.eager_backward = True
