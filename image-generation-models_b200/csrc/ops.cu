@@ -162,7 +162,13 @@ int check_geo(Status& st, const Geo& g) {
 
 // tensor-core route (ops_tc.cu)
 bool ops_tc_geo_ok(int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_h, int pad_w, int dil, int OH, int OW);
-int64_t ops_tc_ws_floats(int B, int H, int W, int Cin, int Cout, int KH);
+bool ops_tc_convT2_ok(int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_h, int pad_w, int dil, int transposed,
+                      int OH, int OW);
+int64_t ops_tc_ws_floats(int B, int H, int W, int Cin, int Cout, int KH, int OH, int OW);
+int ops_tc_convT2_forward(const LaunchCtx& lc, const float* x, const float* w, const float* bias, float* y, int B, int H, int W,
+                          int Cin, int Cout, float* ws);
+int ops_tc_convT2_backward(const LaunchCtx& lc, const float* x, const float* w, const float* dy, float* dx, float* dw, int B, int H,
+                           int W, int Cin, int Cout, float* ws, int* did_dw);
 int ops_tc_conv_forward(const LaunchCtx& lc, const float* x, const float* w, const float* bias, const float* residual, float* y,
                         int B, int H, int W, int Cin, int Cout, int KH, int transposed, float* ws);
 int ops_tc_conv_backward(const LaunchCtx& lc, const float* x, const float* w, const float* dy, float* dx, float* dw, int B, int H,
@@ -176,7 +182,10 @@ using namespace igm;
 extern "C" int64_t igm_conv2d_workspace_floats(int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_h,
                                                int pad_w, int dil, int OH, int OW) {
   int64_t n = (int64_t)KH * KW * Cin * Cout + 64;
-  if (ops_tc_geo_ok(H, W, Cin, Cout, KH, KW, stride, pad_h, pad_w, dil, OH, OW)) n += ops_tc_ws_floats(B, H, W, Cin, Cout, KH);
+  // sized for either tensor-core route (the transposed flag is not part of this query: both are "64-multiple channels")
+  if (ops_tc_geo_ok(H, W, Cin, Cout, KH, KW, stride, pad_h, pad_w, dil, OH, OW) ||
+      ops_tc_convT2_ok(H, W, Cin, Cout, KH, KW, stride, pad_h, pad_w, dil, 1, OH, OW))
+    n += ops_tc_ws_floats(B, H, W, Cin, Cout, KH, OH, OW);
   return n;
 }
 
@@ -196,6 +205,8 @@ extern "C" int igm_conv2d_forward(const float* x, const float* w, const float* b
   const int KK = KH * KW;
   if (ops_tc_geo_ok(H, W, Cin, Cout, KH, KW, stride, pad_h, pad_w, dil, OH, OW))
     return ops_tc_conv_forward(lc, x, w, bias, residual, y, B, H, W, Cin, Cout, KH, transposed, ws + (int64_t)KK * Cin * Cout + 64);
+  if (!residual && ops_tc_convT2_ok(H, W, Cin, Cout, KH, KW, stride, pad_h, pad_w, dil, transposed, OH, OW))
+    return ops_tc_convT2_forward(lc, x, w, bias, y, B, H, W, Cin, Cout, ws + (int64_t)KK * Cin * Cout + 64);
   // packed [tap][ci][co]
   if (!transposed) IGM_TRY(launch_pack_weight(lc, w, ws, KK, Cin, Cout, KK, (int64_t)Cin * KK));
   else IGM_TRY(launch_pack_weight(lc, w, ws, KK, Cin, Cout, (int64_t)Cout * KK, KK));
@@ -222,6 +233,11 @@ extern "C" int igm_conv2d_backward(const float* x, const float* w, const float* 
     int did_dw = 0;
     IGM_TRY(ops_tc_conv_backward(lc, x, w, dy, dx, dw, B, H, W, Cin, Cout, KH, transposed, ws + (int64_t)KK * Cin * Cout + 64, &did_dw));
     dx = nullptr;                 // done on the tensor cores
+    if (did_dw) dw = nullptr;
+  } else if (ops_tc_convT2_ok(H, W, Cin, Cout, KH, KW, stride, pad_h, pad_w, dil, transposed, OH, OW)) {
+    int did_dw = 0;
+    IGM_TRY(ops_tc_convT2_backward(lc, x, w, dy, dx, dw, B, H, W, Cin, Cout, ws + (int64_t)KK * Cin * Cout + 64, &did_dw));
+    dx = nullptr;
     if (did_dw) dw = nullptr;
   }
   if (dx) {

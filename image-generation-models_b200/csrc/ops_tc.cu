@@ -28,12 +28,23 @@ bool ops_tc_geo_ok(int H, int W, int Cin, int Cout, int KH, int KW, int stride, 
   return tc_eligible(Cin, Cout, H, W, KH) && tc_eligible(Cout, Cin, H, W, KH);
 }
 
+// ConvTranspose2d(k = 4, s = 2, p = 1) with 64-multiple channels (the VQ-VAE decoder's first upsampling layer, 128 -> 64 at
+// 32x32 -> 64x64: 13 % of the network's FLOPs): forward = four output-parity phases, data gradient = stride-2 gather over
+// dY, weight gradient = stride-2 wgrad -- the plans the DDPM Upsample layer uses (conv_tc.cu / wgrad_tc.cu)
+bool ops_tc_convT2_ok(int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad_h, int pad_w, int dil, int transposed,
+                      int OH, int OW) {
+  if (!ops_tc_enabled() || !transposed) return false;
+  if (stride != 2 || dil != 1 || KH != 4 || KW != 4 || pad_h != 1 || pad_w != 1 || OH != 2 * H || OW != 2 * W) return false;
+  if (Cin % 64 != 0 || Cout % 64 != 0 || W > 128) return false;
+  return tc_strided_eligible(Cout, Cin, OH, OW, 4) && tcw_strided_eligible(Cout, Cin, H, W, 4);
+}
+
 static int64_t r64(int64_t n) { return (n + 63) & ~int64_t(63); }
 
-// extra workspace floats of the tensor-core route (0: not eligible): packed bf16 weights | x pair | dy pair
-int64_t ops_tc_ws_floats(int B, int H, int W, int Cin, int Cout, int KH) {
-  const int64_t M = (int64_t)B * H * W, nw = (int64_t)KH * KH * Cin * Cout;
-  return r64(nw) + r64(M * Cin) + r64(M * Cout) + 64;
+// extra workspace floats of the tensor-core routes: packed bf16 weights | x pair | dy pair
+int64_t ops_tc_ws_floats(int B, int H, int W, int Cin, int Cout, int KH, int OH, int OW) {
+  const int64_t nw = (int64_t)KH * KH * Cin * Cout;
+  return r64(nw) + r64((int64_t)B * H * W * Cin) + r64((int64_t)B * OH * OW * Cout) + 64;
 }
 
 namespace {
@@ -134,6 +145,61 @@ int ops_tc_conv_backward(const LaunchCtx& lc, const float* x, const float* w, co
       if (!transposed) IGM_TRY(tcw_plan(*lc.st, *t, Cin, Cout, H, W, B, KH, (KH - 1) / 2, dh, dl, xh, xl));
       else IGM_TRY(tcw_plan(*lc.st, *t, Cout, Cin, H, W, B, KH, (KH - 1) / 2, xh, xl, dh, dl));
     }
+    if (tcw_batch_ok(*t, B)) {
+      IGM_TRY(launch_wgrad_tc(lc, *t, B, dw));
+      *did_dw = 1;
+    }
+  }
+  return IGM_OK;
+}
+
+// ---- ConvTranspose2d k4 s2 p1 ---------------------------------------------------------------------------------------
+int ops_tc_convT2_forward(const LaunchCtx& lc, const float* x, const float* w, const float* bias, float* y, int B, int H, int W,
+                          int Cin, int Cout, float* ws) {
+  const int KK = 16;
+  const int64_t M = (int64_t)B * H * W, nw = (int64_t)KK * Cin * Cout;
+  __nv_bfloat16* wh = reinterpret_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* wl = wh + nw;
+  __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(ws + r64(nw));
+  __nv_bfloat16* xl = xh + M * Cin;
+  IGM_TRY(launch_pack_weight_tc(lc, w, wh, wl, KK, Cin, Cout, (int64_t)Cout * KK, KK, 0));   // IOHW, taps as they are
+  IGM_TRY(launch_split_bf16(lc, x, M, Cin, xh, xl, Cin, 0));
+  bool fresh;
+  TcConv* t = conv_plans().get(make_key(2, B, H, W, Cin, Cout, 4, xh, xl, wh, wl), fresh);
+  if (fresh || !t->valid) IGM_TRY(tc_plan_phases4(*lc.st, *t, Cin, Cout, H, W, B, 4, 1, xh, xl, wh, wl));
+  TcRun r;
+  r.B = B; r.bias = bias; r.out0 = y; r.N0 = Cout; r.kclass = K_CONV_FPROP;
+  return launch_conv_tc(lc, *t, r);
+}
+
+int ops_tc_convT2_backward(const LaunchCtx& lc, const float* x, const float* w, const float* dy, float* dx, float* dw, int B, int H,
+                           int W, int Cin, int Cout, float* ws, int* did_dw) {
+  const int KK = 16;
+  const int64_t M = (int64_t)B * H * W, Mo = 4 * M, nw = (int64_t)KK * Cin * Cout;
+  __nv_bfloat16* wh = reinterpret_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* wl = wh + nw;
+  __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(ws + r64(nw));
+  __nv_bfloat16* xl = xh + M * Cin;
+  __nv_bfloat16* dh = reinterpret_cast<__nv_bfloat16*>(ws + r64(nw) + r64(M * Cin));
+  __nv_bfloat16* dl = dh + Mo * Cout;
+  *did_dw = 0;
+  IGM_TRY(launch_split_bf16(lc, dy, Mo, Cout, dh, dl, Cout, 0));
+  if (dx) {
+    // dx[i] = sum_k dy[2 i - 1 + k] w[ci][co][k]: a stride-2 gather over dY, contraction over co (IOHW: co stride KK)
+    IGM_TRY(launch_pack_weight_tc(lc, w, wh, wl, KK, Cout, Cin, KK, (int64_t)Cout * KK, 0));
+    bool fresh;
+    TcConv* t = conv_plans().get(make_key(3, B, H, W, Cout, Cin, 4, dh, dl, wh, wl), fresh);
+    if (fresh || !t->valid) IGM_TRY(tc_plan_strided(*lc.st, *t, Cout, Cin, 2 * H, 2 * W, B, 4, 1, dh, dl, wh, wl));
+    TcRun r;
+    r.B = B; r.out0 = dx; r.N0 = Cin; r.kclass = K_CONV_DGRAD;
+    IGM_TRY(launch_conv_tc(lc, *t, r));
+  }
+  if (dw) {
+    IGM_TRY(launch_split_bf16(lc, x, M, Cin, xh, xl, Cin, 0));
+    bool fresh;
+    // S = dY (fine grid, co), P = X (coarse grid, ci); IOHW: co stride KK, ci stride Cout * KK
+    TcWgrad* t = wgrad_plans().get(make_key(4, B, H, W, Cout, Cin, 4, dh, dl, xh, xl), fresh);
+    if (fresh || !t->valid) IGM_TRY(tcw_plan_strided(*lc.st, *t, Cout, Cin, H, W, B, 4, 1, dh, dl, xh, xl, KK, (int64_t)Cout * KK));
     if (tcw_batch_ok(*t, B)) {
       IGM_TRY(launch_wgrad_tc(lc, *t, B, dw));
       *did_dw = 1;

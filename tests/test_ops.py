@@ -21,6 +21,13 @@ CONVS = [
     (2, 32, 9, 11, 64, 1, 3, 1, (0, 4), 4, False, True),     # dilated horizontal (rectangular)
     (3, 4, 1, 1, 32, 1, 1, 1, (0, 0), 1, False, False),      # cond_proj on [N, n_classes, 1, 1]
     (1, 5, 7, 5, 6, 3, 3, 2, (1, 1), 1, False, True),        # odd sizes, stride 2
+    # 64-multiple channels: the tensor-core route of the operator (csrc/ops_tc.cu, tcgen05 bf16x3)
+    (2, 64, 8, 8, 128, 3, 3, 1, (1, 1), 1, False, True),     # VQ-VAE residual 3x3 (two 8x8 images per MMA tile)
+    (2, 128, 8, 8, 64, 1, 1, 1, (0, 0), 1, False, False),    # VQ-VAE residual 1x1
+    (3, 64, 32, 32, 64, 3, 3, 1, (1, 1), 1, False, True),    # encoder 3x3 at the C5 latent size, odd batch
+    (2, 64, 8, 8, 128, 3, 3, 1, (1, 1), 1, True, True),      # decoder ConvTranspose k3 s1 p1 64 -> 128
+    (2, 128, 8, 8, 64, 4, 4, 2, (1, 1), 1, True, True),      # decoder ConvTranspose k4 s2 p1 128 -> 64 (phases / strided plans)
+    (3, 128, 16, 16, 64, 4, 4, 2, (1, 1), 1, True, False),
 ]
 
 
