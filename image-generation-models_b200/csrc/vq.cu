@@ -164,8 +164,10 @@ extern "C" int igm_vq_forward(const float* z, const float* codebook, int64_t* id
   lc.counter = &launches;
   const int64_t nvec = (int64_t)N * HW;
   const int parts = (int)cdiv64(nvec, 256);
+  // 256 codes per shared-memory chunk (66 KB at D = 64): three 128-thread CTAs per SM (168 registers per thread), i.e. six
+  // independent FMA chains per scheduler
   int k_tile = K;
-  const int max_codes = (160 * 1024) / ((D + 1) * 4);
+  const int max_codes = (64 * 1024) / (D * 4);
   if (k_tile > max_codes) k_tile = max_codes;
   const size_t smem = (size_t)k_tile * (D + 1) * sizeof(float);
   cudaError_t e = cudaSuccess;
