@@ -1,4 +1,4 @@
-"""profiles/r1final_conv_tc_dram.json out of an ncu CSV with dram__bytes_read.sum / dram__bytes_write.sum /
+"""profiles/r<N>_conv_tc_dram.json (bench.py's roofline.traffic) out of an ncu CSV with dram__bytes_read.sum / dram__bytes_write.sum /
 gpu__time_duration.sum for every conv_tc_kernel launch of ONE training step (tools/profile_step.py --what train)."""
 import csv
 import json
@@ -22,7 +22,8 @@ out = {"launches": n, "avg_dram_bytes_per_launch": (rd + wr) / n, "dram_read_byt
        "ncu_time_us_total": us,
        "note": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none over all {n} "
                f"conv_tc_kernel launches of one training step (B=128, cold cache per launch): {rd / 1e6:.0f} MB read + {wr / 1e6:.0f} MB written; "
-               "ncu --set full captures of individual layers: profiles/r1_conv_tc_ncu_full.md (8x8 256->256: 10.8 MB read, tensor pipe 59 % active)"
+               "launches include the 8 per-image attention convs of the two 32x32 blocks; ncu --set full captures of individual layers: "
+               "profiles/r2_ncu_full.md (8x8 256->256: 17.4 MB read, tensor pipe 56 % of active / 42 % of elapsed cycles)"
                }
 json.dump(out, open(sys.argv[2], "w"), indent=1)
 print(json.dumps(out))
