@@ -73,14 +73,47 @@ __device__ __forceinline__ void reduce_groups(float (&acc)[4][4], float (&xsum)[
   }
 }
 
-// rows [n0, n0+rows) of one 32-wide column block of an [n, ld] tensor -> smem tile (128-bit loads, zero fill)
+// rows [n0, n0+rows) of one 32-wide column block of an [n, ld] tensor -> smem tile (128-bit loads, zero fill).
+// All R / 32 loads of a thread are issued before the first store: with a load -> store pair per iteration the compiler
+// kept ONE load in flight per thread (ncu, round 2: 35 % of the ctx kernel's stall samples sat on the two STS.128).
 template <int R = CH>
 __device__ __forceinline__ void load_tile(float (*dst)[D], const float* __restrict__ src, int ld, int rows, int tid) {
-  for (int i = tid; i < R * (D / 4); i += 256) {
+  constexpr int IT = R * (D / 4) / 256;
+  float4 v[IT];
+#pragma unroll
+  for (int k = 0; k < IT; ++k) {
+    const int i = tid + k * 256;
     const int nn = i >> 3, c4 = (i & 7) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (nn < rows) v = __ldg(reinterpret_cast<const float4*>(src + (int64_t)nn * ld + c4));
-    *reinterpret_cast<float4*>(&dst[nn][c4]) = v;
+    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nn < rows) v[k] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)nn * ld + c4));
+  }
+#pragma unroll
+  for (int k = 0; k < IT; ++k) {
+    const int i = tid + k * 256;
+    *reinterpret_cast<float4*>(&dst[i >> 3][(i & 7) * 4]) = v[k];
+  }
+}
+// two tiles at once (both tiles' loads in flight together)
+template <int R = CH>
+__device__ __forceinline__ void load_tile2(float (*d0)[D], const float* __restrict__ s0, int ld0, float (*d1)[D],
+                                           const float* __restrict__ s1, int ld1, int rows, int tid) {
+  constexpr int IT = R * (D / 4) / 256;
+  float4 a[IT], b[IT];
+#pragma unroll
+  for (int k = 0; k < IT; ++k) {
+    const int i = tid + k * 256;
+    const int nn = i >> 3, c4 = (i & 7) * 4;
+    a[k] = b[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nn < rows) {
+      a[k] = __ldg(reinterpret_cast<const float4*>(s0 + (int64_t)nn * ld0 + c4));
+      b[k] = __ldg(reinterpret_cast<const float4*>(s1 + (int64_t)nn * ld1 + c4));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < IT; ++k) {
+    const int i = tid + k * 256;
+    *reinterpret_cast<float4*>(&d0[i >> 3][(i & 7) * 4]) = a[k];
+    *reinterpret_cast<float4*>(&d1[i >> 3][(i & 7) * 4]) = b[k];
   }
 }
 
@@ -88,18 +121,27 @@ __device__ __forceinline__ void load_tile(float (*dst)[D], const float* __restri
 template <int R = CH>
 __device__ __forceinline__ void load_tile_hl(float (*dst)[D], const __nv_bfloat16* __restrict__ hi,
                                              const __nv_bfloat16* __restrict__ lo, int ld, int rows, int tid) {
-  for (int i = tid; i < R * (D / 4); i += 256) {
+  constexpr int IT = R * (D / 4) / 256;
+  uint2 h[IT], l[IT];
+#pragma unroll
+  for (int k = 0; k < IT; ++k) {
+    const int i = tid + k * 256;
     const int nn = i >> 3, c4 = (i & 7) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    h[k] = l[k] = make_uint2(0u, 0u);
     if (nn < rows) {
-      const uint2 h = __ldg(reinterpret_cast<const uint2*>(hi + (int64_t)nn * ld + c4));
-      const uint2 l = __ldg(reinterpret_cast<const uint2*>(lo + (int64_t)nn * ld + c4));
-      v.x = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
-      v.y = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
-      v.z = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
-      v.w = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
+      h[k] = __ldg(reinterpret_cast<const uint2*>(hi + (int64_t)nn * ld + c4));
+      l[k] = __ldg(reinterpret_cast<const uint2*>(lo + (int64_t)nn * ld + c4));
     }
-    *reinterpret_cast<float4*>(&dst[nn][c4]) = v;
+  }
+#pragma unroll
+  for (int k = 0; k < IT; ++k) {
+    const int i = tid + k * 256;
+    float4 v;
+    v.x = __uint_as_float(h[k].x << 16) + __uint_as_float(l[k].x << 16);
+    v.y = __uint_as_float(h[k].x & 0xffff0000u) + __uint_as_float(l[k].x & 0xffff0000u);
+    v.z = __uint_as_float(h[k].y << 16) + __uint_as_float(l[k].y << 16);
+    v.w = __uint_as_float(h[k].y & 0xffff0000u) + __uint_as_float(l[k].y & 0xffff0000u);
+    *reinterpret_cast<float4*>(&dst[i >> 3][(i & 7) * 4]) = v;
   }
 }
 
@@ -147,8 +189,7 @@ __global__ void __launch_bounds__(256) linattn_ctx_kernel(const float* __restric
     load_tile_hl(Xs, q_hi + boff + HD + h * D, q_lo + boff + HD + h * D, QKV, rows, tid);
     load_tile_hl(Ys, q_hi + boff + 2 * HD + h * D, q_lo + boff + 2 * HD + h * D, QKV, rows, tid);
   } else {
-    load_tile(Xs, qkv + boff + HD + h * D, QKV, rows, tid);
-    load_tile(Ys, qkv + boff + 2 * HD + h * D, QKV, rows, tid);
+    load_tile2(Xs, qkv + boff + HD + h * D, QKV, Ys, qkv + boff + 2 * HD + h * D, QKV, rows, tid);
   }
   __syncthreads();
   {
@@ -282,8 +323,7 @@ __global__ void __launch_bounds__(256) linattn_bwd_dctx_kernel(const float* __re
     load_tile_hl(Xs, q_hi + qo, q_lo + qo, QKV, rows, tid);
     load_tile_hl(Ys, d_hi + dof, d_lo + dof, HD, rows, tid);
   } else {
-    load_tile(Xs, qkv + ((int64_t)b * N + n0) * QKV + h * D, QKV, rows, tid);
-    load_tile(Ys, d_out + ((int64_t)b * N + n0) * HD + h * D, HD, rows, tid);
+    load_tile2(Xs, qkv + ((int64_t)b * N + n0) * QKV + h * D, QKV, Ys, d_out + ((int64_t)b * N + n0) * HD + h * D, HD, rows, tid);
   }
   __syncthreads();
   const int grp = tid >> 6, t64 = tid & 63;

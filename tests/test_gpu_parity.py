@@ -403,3 +403,43 @@ def test_backward_of_an_overwritten_forward_raises():
     ub.sum().backward()                            # the latest one is fine
     ld = gd.p_losses(xc, tc, nc)
     ld.backward()
+
+
+def test_gradient_buckets_partition_the_arena_and_their_events_order_the_streams(conv_engine):
+    """igm_unet_grad_buckets / igm_unet_bucket_wait (the data-parallel exchange's device-side interface): the buckets are
+    disjoint ranges that cover the gradient arena, start at parameter-group boundaries in backward-completion order
+    (ups | mid | final first, downs.(n-1) .. downs.1, time_mlp + downs.0 last), and a stream that waits for bucket k
+    reads that bucket's final gradients while the rest of the backward pass may still be running."""
+    import ctypes as C
+    spec, params, unet, gd = _build("cifar10")
+    x, t, noise, _ = make_golden.inputs("cifar10")
+    xc, tc, nc = x.cuda(), t.cuda(), noise.cuda()
+    gd.p_losses(xc, tc, nc).backward()
+    torch.cuda.synchronize()
+    ref = unet._flat_grad.clone()
+    e = unet._engine
+    lo, hi = (C.c_int64 * 16)(), (C.c_int64 * 16)()
+    n = e.lib.igm_unet_grad_buckets(e.ctx, lo, hi, 16)
+    assert n == len(unet.dim_mults) + 1
+    ranges = [(int(lo[k]), int(hi[k])) for k in range(n)]
+    assert ranges[-1][0] == 0 and ranges[0][1] == unet._flat_grad.numel()
+    for k in range(1, n):
+        assert ranges[k][1] == ranges[k - 1][0]                      # contiguous, walking down the arena
+    offs = {name: off for name, off, _ in unet._layout}
+    assert ranges[0][0] == offs["ups.0.0.mlp.1.weight"]
+    assert ranges[1][0] == offs[f"downs.{len(unet.dim_mults) - 1}.0.mlp.1.weight"]
+    assert ranges[-1][1] == offs["downs.1.0.mlp.1.weight"]
+    # a second backward: copy every bucket out on a side stream that only waits for that bucket's events
+    unet._flat_grad.zero_()
+    side = torch.cuda.Stream()
+    outs = []
+    loss = gd.p_losses(xc, tc, nc)
+    loss.backward()
+    with torch.cuda.stream(side):
+        for k, (a, b) in enumerate(ranges):
+            e.check(e.lib.igm_unet_bucket_wait(e.ctx, k, C.c_void_p(side.cuda_stream)))
+            outs.append(unet._flat_grad[a:b].clone())
+    side.synchronize()
+    torch.cuda.synchronize()
+    for (a, b), o in zip(ranges, outs):
+        assert_close(o, ref[a:b], f"bucket [{a}, {b}) read behind its events", 1e-5)
