@@ -120,6 +120,47 @@ __device__ __forceinline__ void cta_gemv(const float* __restrict__ Wt, const flo
   __syncthreads();
 }
 
+// The same GEMV in two halves, so that the weight loads of the NEXT matrix of the per-pixel chain are in flight while the
+// current one is computed (the weights do not depend on the data): gemv_prefetch issues the K * N / 1024 <= NW 128-bit loads
+// of this thread's slice, gemv_finish consumes them.  Same slicing and summation order as cta_gemv: bit-identical results.
+template <int NW>
+__device__ __forceinline__ void gemv_prefetch(const float* __restrict__ Wt, int K, int N, float4 (&w)[NW]) {
+  const int tid = threadIdx.x;
+  const int n4 = N >> 2, parts = 256 / n4;
+  const int part = tid / n4, q = tid - part * n4;
+  const int klen = K / parts;
+  const float4* wp = reinterpret_cast<const float4*>(Wt + (int64_t)(part * klen) * N) + q;
+#pragma unroll
+  for (int k = 0; k < NW; ++k)
+    if (k < klen) w[k] = __ldg(wp + (int64_t)k * n4);
+}
+template <int NW>
+__device__ __forceinline__ void gemv_finish(const float4 (&w)[NW], const float* __restrict__ bias, const float* __restrict__ extra,
+                                            const float* x_s, int K, int N, float* red_s /*[1024]*/, float* y_s) {
+  const int tid = threadIdx.x;
+  const int n4 = N >> 2, parts = 256 / n4;
+  const int part = tid / n4, q = tid - part * n4;
+  const int klen = K / parts, kb = part * klen;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < NW; ++k) {
+    if (k < klen) {
+      const float x = x_s[kb + k];
+      acc.x = fmaf(w[k].x, x, acc.x); acc.y = fmaf(w[k].y, x, acc.y);
+      acc.z = fmaf(w[k].z, x, acc.z); acc.w = fmaf(w[k].w, x, acc.w);
+    }
+  }
+  *reinterpret_cast<float4*>(red_s + part * N + q * 4) = acc;
+  __syncthreads();
+  if (tid < N) {
+    float s = bias ? __ldg(bias + tid) : 0.f;
+    if (extra) s += extra[tid];
+    for (int p = 0; p < parts; ++p) s += red_s[p * N + tid];
+    y_s[tid] = s;
+  }
+  __syncthreads();
+}
+
 // out[w][n] = bias[n] + sum_{taps} sum_ci Wt[(tap*Kc + ci)][n] * in(tap, w)[ci]  for all w < W, n < N.
 // `rows[t]` points at the smem row (W x Kc, ci contiguous) tap t reads, or null (zero); `shift[t]`
 // is the column offset of tap t.  N divides 256.
@@ -177,7 +218,7 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t a, uint3
   return (float)(c0 >> 8) * (1.0f / 16777216.0f);
 }
 
-__global__ void __launch_bounds__(256) pixelcnn_kernel(const PcnnArgs a) {
+__global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
   extern __shared__ __align__(16) float sm[];
   const int n_img = blockIdx.x;
   const int tid = threadIdx.x;
@@ -275,6 +316,10 @@ __global__ void __launch_bounds__(256) pixelcnn_kernel(const PcnnArgs a) {
         Hs[((int64_t)0 * W + w) * Hd + tid] = s;
       }
       __syncthreads();
+      // weights of the chain one matrix ahead (registers): possible while a slice is <= 16 / <= 4 float4 (hidden_dim <= 64)
+      const bool pipe = (N2 * N2 / 1024 <= 16) && (Hd * Hd / 1024 <= 4);
+      float4 wA[16], wB[4];
+      if (pipe) gemv_prefetch<16>(Wt + a.off.horiz_w[0], N2, N2, wA);
       for (int l = 0; l < NLAYERS; ++l) {
         const int d = c_dil[l];
         // horiz_conv 1x3 dilated, cols kx = 0 (w-d), 1 (w)                        (pixelcnn.py:48-50)
@@ -283,7 +328,12 @@ __global__ void __launch_bounds__(256) pixelcnn_kernel(const PcnnArgs a) {
           x_s[tid] = (w - d >= 0) ? Hs[((int64_t)l * W + (w - d)) * Hd + tid] : 0.f;
         }
         __syncthreads();
-        cta_gemv(Wt + a.off.horiz_w[l], Wt + a.off.horiz_b[l], V2H + ((int64_t)l * W + w) * N2, x_s, N2, N2, red_s, y_s);
+        if (pipe) {
+          gemv_prefetch<4>(Wt + a.off.h2_w[l], Hd, Hd, wB);
+          gemv_finish<16>(wA, Wt + a.off.horiz_b[l], V2H + ((int64_t)l * W + w) * N2, x_s, N2, N2, red_s, y_s);
+        } else {
+          cta_gemv(Wt + a.off.horiz_w[l], Wt + a.off.horiz_b[l], V2H + ((int64_t)l * W + w) * N2, x_s, N2, N2, red_s, y_s);
+        }
         // gated horizontal output: tanh(a) * tanh(b)  (sic)                      (pixelcnn.py:77)
         if (tid < Hd) {
           float ah = y_s[tid], bh = y_s[Hd + tid];
@@ -296,7 +346,12 @@ __global__ void __launch_bounds__(256) pixelcnn_kernel(const PcnnArgs a) {
         }
         __syncthreads();
         // conv1x1_2 + residual                                                    (pixelcnn.py:80)
-        cta_gemv(Wt + a.off.h2_w[l], Wt + a.off.h2_b[l], cur_s, x_s, Hd, Hd, red_s, y_s);
+        if (pipe) {
+          if (l + 1 < NLAYERS) gemv_prefetch<16>(Wt + a.off.horiz_w[l + 1], N2, N2, wA);
+          gemv_finish<4>(wB, Wt + a.off.h2_b[l], cur_s, x_s, Hd, Hd, red_s, y_s);
+        } else {
+          cta_gemv(Wt + a.off.h2_w[l], Wt + a.off.h2_b[l], cur_s, x_s, Hd, Hd, red_s, y_s);
+        }
         if (tid < Hd) {
           cur_s[tid] = y_s[tid];
           Hs[((int64_t)(l + 1) * W + w) * Hd + tid] = y_s[tid];
