@@ -10,112 +10,69 @@ namespace {
 
 constexpr int VQ_MAX_D = 64;
 
-// Work split of the lookup.  The per-GPU problem is small (32768 vectors x 512 codes): one vector per thread is 7 warps per
-// SM, each a 64-long dependent FMA chain fed by one broadcast LDS.128 per four FMAs -- latency- and LSU-bound at 14.8 TFLOP/s
-// (20 % of the fp32 peak).  Here a thread owns V = 2 vectors (each code load feeds two chains) and ONE of S = 4 interleaved
-// code slices (k = slice mod 4), so a 128-thread CTA covers 64 vectors and the grid is four times larger; the slices' winners
-// are merged with "smaller distance, then smaller index", which is the first index over all codes because every slice scans
-// its codes in increasing order with a strict '<'.  Per-(vector, code) arithmetic (order of the 64 FMAs, the distance formula)
-// is unchanged, so the chosen codes are bit-identical to the one-vector kernel.  Codebook rows are padded to D + 4 floats:
-// the four codes a warp reads at once then sit in different banks.
-constexpr int VQ_V = 2;
-constexpr int VQ_S = 4;
-constexpr int VQ_THREADS = 128;
-constexpr int VQ_VEC_PER_CTA = VQ_THREADS / VQ_S * VQ_V;   // 64
-
+// one thread per latent vector; the codebook (chunk) is broadcast from shared memory.
+// (Round 2 tried two vectors per thread, and two vectors x four interleaved code slices per thread group with padded codebook
+// rows: 0.174 / 0.169 ms against 0.145 ms for this kernel on the C5 per-GPU problem, 32768 vectors x 512 codes -- the problem
+// is one wave of 128 CTAs either way, and the finer split only added a partial second wave.  Reverted.)
 template <int D>
-__global__ void __launch_bounds__(VQ_THREADS, 3) vq_forward_kernel(const float* __restrict__ z, const float* __restrict__ cb,
-                                                                int64_t* __restrict__ idx_out, float* __restrict__ quant,
-                                                                float* __restrict__ ws, int N, int HW, int K, int k_tile) {
-  constexpr int LD = D + 4;
-  extern __shared__ __align__(16) float sm[];   // [k_tile][D + 4] codes | [k_tile] squared norms
+__global__ void __launch_bounds__(256) vq_forward_kernel(const float* __restrict__ z, const float* __restrict__ cb,
+                                                         int64_t* __restrict__ idx_out, float* __restrict__ quant,
+                                                         float* __restrict__ ws, int N, int HW, int K, int k_tile) {
+  extern __shared__ __align__(16) float sm[];   // [k_tile][D] codes | [k_tile] squared norms
   float* s_cb = sm;
-  float* s_e2 = sm + (size_t)k_tile * LD;
-  __shared__ float red[VQ_THREADS / 32];
-  const int slice = threadIdx.x & (VQ_S - 1), grp = threadIdx.x >> 2;   // VQ_S == 4
+  float* s_e2 = sm + (size_t)k_tile * D;
+  __shared__ float red[8];
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nvec = (int64_t)N * HW;
-  int64_t v[VQ_V];
-  bool ok[VQ_V];
-  int n[VQ_V], p[VQ_V];
-  float x[VQ_V][D], x2[VQ_V], best[VQ_V];
-  int best_k[VQ_V];
+  const bool ok = v < nvec;
+  const int n = ok ? (int)(v / HW) : 0;
+  const int p = ok ? (int)(v - (int64_t)n * HW) : 0;
+  float x[D];
+  float x2 = 0.f;
 #pragma unroll
-  for (int u = 0; u < VQ_V; ++u) {
-    v[u] = (int64_t)blockIdx.x * VQ_VEC_PER_CTA + u * (VQ_THREADS / VQ_S) + grp;
-    ok[u] = v[u] < nvec;
-    n[u] = ok[u] ? (int)(v[u] / HW) : 0;
-    p[u] = ok[u] ? (int)(v[u] - (int64_t)n[u] * HW) : 0;
-    x2[u] = 0.f;
-    best[u] = INFINITY;
-    best_k[u] = 0x7fffffff;
-#pragma unroll
-    for (int c = 0; c < D; ++c) {
-      x[u][c] = ok[u] ? __ldg(z + ((int64_t)n[u] * D + c) * HW + p[u]) : 0.f;
-      x2[u] = fmaf(x[u][c], x[u][c], x2[u]);
-    }
+  for (int c = 0; c < D; ++c) {
+    x[c] = ok ? __ldg(z + ((int64_t)n * D + c) * HW + p) : 0.f;
+    x2 = fmaf(x[c], x[c], x2);
   }
+  float best = INFINITY;
+  int best_k = 0;
   for (int k0 = 0; k0 < K; k0 += k_tile) {
     const int kt = min(k_tile, K - k0);
     __syncthreads();
-    for (int i = threadIdx.x; i < kt * (D / 4); i += blockDim.x) {
-      const int k = i / (D / 4), c4 = i - k * (D / 4);
-      *reinterpret_cast<float4*>(s_cb + k * LD + c4 * 4) = __ldg(reinterpret_cast<const float4*>(cb + (size_t)(k0 + k) * D) + c4);
-    }
+    for (int i = threadIdx.x; i < kt * D / 4; i += blockDim.x)
+      reinterpret_cast<float4*>(s_cb)[i] = __ldg(reinterpret_cast<const float4*>(cb + (size_t)k0 * D) + i);
     __syncthreads();
     for (int k = threadIdx.x; k < kt; k += blockDim.x) {
       float e2 = 0.f;
-      for (int c = 0; c < D; ++c) e2 = fmaf(s_cb[k * LD + c], s_cb[k * LD + c], e2);
+      for (int c = 0; c < D; ++c) e2 = fmaf(s_cb[k * D + c], s_cb[k * D + c], e2);
       s_e2[k] = e2;
     }
     __syncthreads();
-    for (int k = slice; k < kt; k += VQ_S) {
-      const float4* e = reinterpret_cast<const float4*>(s_cb + k * LD);
-      float dot[VQ_V];
-#pragma unroll
-      for (int u = 0; u < VQ_V; ++u) dot[u] = 0.f;
+    for (int k = 0; k < kt; ++k) {
+      const float4* e = reinterpret_cast<const float4*>(s_cb + k * D);
+      float dot = 0.f;
 #pragma unroll
       for (int c4 = 0; c4 < D / 4; ++c4) {
         const float4 ev = e[c4];
-#pragma unroll
-        for (int u = 0; u < VQ_V; ++u) {
-          dot[u] = fmaf(x[u][c4 * 4 + 0], ev.x, dot[u]);
-          dot[u] = fmaf(x[u][c4 * 4 + 1], ev.y, dot[u]);
-          dot[u] = fmaf(x[u][c4 * 4 + 2], ev.z, dot[u]);
-          dot[u] = fmaf(x[u][c4 * 4 + 3], ev.w, dot[u]);
-        }
+        dot = fmaf(x[c4 * 4 + 0], ev.x, dot);
+        dot = fmaf(x[c4 * 4 + 1], ev.y, dot);
+        dot = fmaf(x[c4 * 4 + 2], ev.z, dot);
+        dot = fmaf(x[c4 * 4 + 3], ev.w, dot);
       }
-      // torch.cdist (mm path): sqrt(clamp(|x|^2 + |e|^2 - 2 x.e, 0)); strict '<' keeps the first index of the slice on ties
-      const float e2 = s_e2[k];
-#pragma unroll
-      for (int u = 0; u < VQ_V; ++u) {
-        const float d = sqrtf(fmaxf(x2[u] + e2 - 2.f * dot[u], 0.f));
-        if (d < best[u]) { best[u] = d; best_k[u] = k0 + k; }
-      }
-    }
-  }
-  // merge the four slices of a vector (adjacent lanes): smaller distance, then smaller index = first index overall
-#pragma unroll
-  for (int u = 0; u < VQ_V; ++u) {
-#pragma unroll
-    for (int o = 1; o < VQ_S; o <<= 1) {
-      const float od = __shfl_xor_sync(0xffffffffu, best[u], o);
-      const int ok_ = __shfl_xor_sync(0xffffffffu, best_k[u], o);
-      if (od < best[u] || (od == best[u] && ok_ < best_k[u])) { best[u] = od; best_k[u] = ok_; }
+      // torch.cdist (mm path): sqrt(clamp(|x|^2 + |e|^2 - 2 x.e, 0)); strict '<' keeps the first index on ties
+      const float d = sqrtf(fmaxf(x2 + s_e2[k] - 2.f * dot, 0.f));
+      if (d < best) { best = d; best_k = k0 + k; }
     }
   }
   float err = 0.f;
-#pragma unroll
-  for (int u = 0; u < VQ_V; ++u) {
-    if (!ok[u]) continue;
-    if (slice == 0) idx_out[v[u]] = best_k[u];
-    const float* q = cb + (size_t)best_k[u] * D;
-    // the four lanes of a vector share the gather: lane `slice` writes channels slice, slice + 4, ...
+  if (ok) {
+    idx_out[v] = best_k;
+    const float* q = cb + (size_t)best_k * D;
 #pragma unroll
     for (int c = 0; c < D; ++c) {
-      if ((c & (VQ_S - 1)) != slice) continue;
       const float qc = __ldg(q + c);
-      quant[((int64_t)n[u] * D + c) * HW + p[u]] = qc;
-      const float df = x[u][c] - qc;
+      quant[((int64_t)n * D + c) * HW + p] = qc;
+      const float df = x[c] - qc;
       err = fmaf(df, df, err);
     }
   }
@@ -125,19 +82,16 @@ __global__ void __launch_bounds__(VQ_THREADS, 3) vq_forward_kernel(const float* 
   if (threadIdx.x == 0) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < VQ_THREADS / 32; ++i) t += red[i];
+    for (int i = 0; i < 8; ++i) t += red[i];
     ws[blockIdx.x] = t;
   }
 }
 
 __global__ void vq_loss_final_kernel(const float* __restrict__ ws, int parts, double n_el, float beta,
                                      float* __restrict__ losses) {
-  // one warp, fixed order (lane-strided partial sums, then a shuffle tree): deterministic
-  double t = 0.0;
-  for (int i = threadIdx.x; i < parts; i += 32) t += (double)ws[i];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < parts; ++i) t += (double)ws[i];
     const float mse = (float)(t / n_el);
     losses[0] = mse;          // vq_loss     = mse(z.detach(), q)        (vqvae.py:38)
     losses[1] = beta * mse;   // commit_loss = beta * mse(z, q.detach()) (vqvae.py:39)
@@ -173,7 +127,7 @@ __global__ void vq_backward_kernel(const float* __restrict__ z, const float* __r
 
 using namespace igm;
 
-extern "C" int igm_vq_workspace_floats(int N, int HW) { return (int)cdiv64((int64_t)N * HW, VQ_VEC_PER_CTA) + 8; }
+extern "C" int igm_vq_workspace_floats(int N, int HW) { return (int)cdiv64((int64_t)N * HW, 256) + 8; }
 
 extern "C" int igm_vq_forward(const float* z, const float* codebook, int64_t* idx, float* quant, float* losses, int N,
                               int D, int HW, int K, float beta, float* ws, void* stream) {
@@ -188,23 +142,21 @@ extern "C" int igm_vq_forward(const float* z, const float* codebook, int64_t* id
   lc.st = &st;
   lc.counter = &launches;
   const int64_t nvec = (int64_t)N * HW;
-  const int parts = (int)cdiv64(nvec, VQ_VEC_PER_CTA);
-  // 256 codes per shared-memory chunk (66 KB at D = 64): three 128-thread CTAs per SM (168 registers per thread), i.e. six
-  // independent FMA chains per scheduler
+  const int parts = (int)cdiv64(nvec, 256);
   int k_tile = K;
-  const int max_codes = (64 * 1024) / (D * 4);
+  const int max_codes = (160 * 1024) / ((D + 1) * 4);
   if (k_tile > max_codes) k_tile = max_codes;
-  const size_t smem = (size_t)k_tile * (D + 4 + 1) * sizeof(float);
+  const size_t smem = (size_t)k_tile * (D + 1) * sizeof(float);
   cudaError_t e = cudaSuccess;
   if (D == 64) {
     e = cudaFuncSetAttribute(vq_forward_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) vq_forward_kernel<64><<<parts, VQ_THREADS, smem, lc.stream>>>(z, codebook, idx, quant, ws, N, HW, K, k_tile);
+    if (e == cudaSuccess) vq_forward_kernel<64><<<parts, 256, smem, lc.stream>>>(z, codebook, idx, quant, ws, N, HW, K, k_tile);
   } else if (D == 32) {
     e = cudaFuncSetAttribute(vq_forward_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) vq_forward_kernel<32><<<parts, VQ_THREADS, smem, lc.stream>>>(z, codebook, idx, quant, ws, N, HW, K, k_tile);
+    if (e == cudaSuccess) vq_forward_kernel<32><<<parts, 256, smem, lc.stream>>>(z, codebook, idx, quant, ws, N, HW, K, k_tile);
   } else {
     e = cudaFuncSetAttribute(vq_forward_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) vq_forward_kernel<16><<<parts, VQ_THREADS, smem, lc.stream>>>(z, codebook, idx, quant, ws, N, HW, K, k_tile);
+    if (e == cudaSuccess) vq_forward_kernel<16><<<parts, 256, smem, lc.stream>>>(z, codebook, idx, quant, ws, N, HW, K, k_tile);
   }
   if (e != cudaSuccess) IGM_FAIL(st, IGM_ERR_CUDA, cudaGetErrorString(e));
   IGM_POST_LAUNCH(lc);
