@@ -117,6 +117,33 @@ __device__ __forceinline__ void load_tile2(float (*d0)[D], const float* __restri
   }
 }
 
+// three tiles at once
+template <int R = CH>
+__device__ __forceinline__ void load_tile3(float (*d0)[D], const float* __restrict__ s0, int ld0, float (*d1)[D],
+                                           const float* __restrict__ s1, int ld1, float (*d2)[D], const float* __restrict__ s2,
+                                           int ld2, int rows, int tid) {
+  constexpr int IT = R * (D / 4) / 256;
+  float4 a[IT], b[IT], c[IT];
+#pragma unroll
+  for (int k = 0; k < IT; ++k) {
+    const int i = tid + k * 256;
+    const int nn = i >> 3, c4 = (i & 7) * 4;
+    a[k] = b[k] = c[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nn < rows) {
+      a[k] = __ldg(reinterpret_cast<const float4*>(s0 + (int64_t)nn * ld0 + c4));
+      b[k] = __ldg(reinterpret_cast<const float4*>(s1 + (int64_t)nn * ld1 + c4));
+      c[k] = __ldg(reinterpret_cast<const float4*>(s2 + (int64_t)nn * ld2 + c4));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < IT; ++k) {
+    const int i = tid + k * 256;
+    *reinterpret_cast<float4*>(&d0[i >> 3][(i & 7) * 4]) = a[k];
+    *reinterpret_cast<float4*>(&d1[i >> 3][(i & 7) * 4]) = b[k];
+    *reinterpret_cast<float4*>(&d2[i >> 3][(i & 7) * 4]) = c[k];
+  }
+}
+
 // the same tile from a bf16 hi / lo staging pair (value = hi + lo, 16 significant bits): `ld` in elements
 template <int R = CH>
 __device__ __forceinline__ void load_tile_hl(float (*dst)[D], const __nv_bfloat16* __restrict__ hi,
@@ -389,9 +416,7 @@ __global__ void __launch_bounds__(256, 3) linattn_bwd_rows_kernel(const float* _
   for (int n0 = blockIdx.y * CH; n0 < n_end; n0 += SUB) {
     const int rows = min(SUB, n_end - n0);
     const float* base = qkv + ((int64_t)b * N + n0) * QKV;
-    load_tile<SUB>(Xs, base + kcol, QKV, rows, tid);
-    load_tile<SUB>(Vs, base + vcol, QKV, rows, tid);
-    load_tile<SUB>(Ys, d_out + ((int64_t)b * N + n0) * HD + h * D, HD, rows, tid);
+    load_tile3<SUB>(Xs, base + kcol, QKV, Vs, base + vcol, QKV, Ys, d_out + ((int64_t)b * N + n0) * HD + h * D, HD, rows, tid);
     __syncthreads();
     for (int nn = r; nn < rows; nn += 8) Xs[nn][c] = expf(Xs[nn][c] - kmax) * kinv;
     __syncthreads();
