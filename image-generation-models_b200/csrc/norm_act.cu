@@ -596,10 +596,6 @@ __global__ void __launch_bounds__(256) gn_bwd_bulk_kernel(const GnBwdArgs a, int
     s_m[g][k] = t / ((float)a.HW * ly.cpg);
   }
   __syncthreads();
-  // this CTA is done with the other CTAs' shared memory: arrive now, wait only right before exit (a CTA must not retire
-  // while a sibling may still read its cl_grp); nothing else crosses the cluster -- the per-channel sums below go out as one
-  // atomic per (CTA, channel) instead of being folded by rank 0 behind two more cluster-wide barriers
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   const float m1 = s_m[ly.group][0], m2 = s_m[ly.group][1];
   float dbs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 2
@@ -616,8 +612,8 @@ __global__ void __launch_bounds__(256) gn_bwd_bulk_kernel(const GnBwdArgs a, int
     if (a.dy) *reinterpret_cast<float4*>(a.dy + off) = o;
     if (a.dy_hi) store_split4(a.dy_hi, a.dy_lo, off, o);
   }
-  // per-channel sums: fold the pixel slots of the CTA (the tile is dead now: it holds the partials), then one atomic per
-  // (CTA, channel); dtemb [B, stride] is accumulated too (the caller zeroes it once per backward pass)
+  // per-channel sums: fold the pixel slots of the CTA, then the CTAs of the cluster (rank 0), then one atomic per
+  // (sample, channel) -- dtemb is per sample and written directly.  The tile is dead now: it holds the partials.
   __syncthreads();
   float4 (*sc)[4] = reinterpret_cast<float4 (*)[4]>(tile);
   sc[threadIdx.x][0] = make_float4(dgam[0], dgam[1], dgam[2], dgam[3]);
@@ -625,8 +621,8 @@ __global__ void __launch_bounds__(256) gn_bwd_bulk_kernel(const GnBwdArgs a, int
   sc[threadIdx.x][2] = make_float4(dte[0], dte[1], dte[2], dte[3]);
   sc[threadIdx.x][3] = make_float4(dbs[0], dbs[1], dbs[2], dbs[3]);
   __syncthreads();
+  float4 acc[4];
   if (threadIdx.x < ly.L) {
-    float4 acc[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) acc[k] = sc[threadIdx.x][k];
     for (int sl = 1; sl < ly.PPI; ++sl) {
@@ -636,14 +632,27 @@ __global__ void __launch_bounds__(256) gn_bwd_bulk_kernel(const GnBwdArgs a, int
         acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
       }
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < ly.L) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sc[threadIdx.x][k] = acc[k];
+  }
+  cluster.sync();
+  if (rank == 0 && threadIdx.x < ly.L) {
+    for (int r = 1; r < cs; ++r) {
+      const float4* rs = cluster.map_shared_rank(&sc[0][0], r) + threadIdx.x * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 v = rs[k];
+        acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+      }
+    }
     atomicAdd(a.dgamma + c + 0, acc[0].x); atomicAdd(a.dgamma + c + 1, acc[0].y);
     atomicAdd(a.dgamma + c + 2, acc[0].z); atomicAdd(a.dgamma + c + 3, acc[0].w);
     atomicAdd(a.dbeta + c + 0, acc[1].x); atomicAdd(a.dbeta + c + 1, acc[1].y);
     atomicAdd(a.dbeta + c + 2, acc[1].z); atomicAdd(a.dbeta + c + 3, acc[1].w);
-    if (a.dtemb) {
-      float* dt = a.dtemb + (int64_t)b * a.dtemb_stride + c;
-      atomicAdd(dt + 0, acc[2].x); atomicAdd(dt + 1, acc[2].y); atomicAdd(dt + 2, acc[2].z); atomicAdd(dt + 3, acc[2].w);
-    }
+    if (a.dtemb) *reinterpret_cast<float4*>(a.dtemb + (int64_t)b * a.dtemb_stride + c) = acc[2];
     if (a.dout_colsum) {
       atomicAdd(a.dout_colsum + c + 0, acc[2].x); atomicAdd(a.dout_colsum + c + 1, acc[2].y);
       atomicAdd(a.dout_colsum + c + 2, acc[2].z); atomicAdd(a.dout_colsum + c + 3, acc[2].w);
@@ -653,7 +662,7 @@ __global__ void __launch_bounds__(256) gn_bwd_bulk_kernel(const GnBwdArgs a, int
       atomicAdd(a.dbias + c + 2, acc[3].z); atomicAdd(a.dbias + c + 3, acc[3].w);
     }
   }
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  cluster.sync();   // remote shared memory stays valid until rank 0 has read it
 }
 
 // ---- backward, pass 3: parameter / time-embedding gradients -------------------

@@ -1160,8 +1160,6 @@ struct Runner {
     time_done = false;
     c.bk_valid = false;
     const int H0 = cfg.height, W0 = cfg.width;
-    // d(temb) of every ResnetBlock is ACCUMULATED by the GroupNorm backward (one atomic per CTA and channel)
-    IGM_CUDA(c.st, cudaMemsetAsync(c.t_dproj, 0, (size_t)B * c.proj_total * sizeof(float), lc.stream));
     // final 1x1: W[c][k]
     {
       WgradArgs w;
