@@ -46,10 +46,6 @@ struct TcArgs {
   __nv_bfloat16* hi0; __nv_bfloat16* lo0;
   int ldh;              // row pitch (elements) of hi0 / lo0: N0, or larger when the output is a channel slice of a wider tensor
   float* gn_part; int gn_cpg, gn_slots;
-  // GroupNorm + Mish (+ time-embedding add) (+ residual = add0) applied INSIDE the epilogue (sampler steps, tiles that hold
-  // whole images: 8x8 layers): gn_epi = warps per image (HW / 32), 0 = off; group = gn_cpg <= 32 consecutive channels
-  int gn_epi; float gn_inv_count;
-  const float* gn_gamma; const float* gn_beta; const float* gn_temb; int gn_temb_stride;
   // TMA-store epilogue: each epilogue warp stages its 32 rows x 32 channels in swizzled shared memory and one
   // lane issues cp.async.bulk.tensor stores (a warp = box wb x hb x ib pixels of the [B, H, W, C] output)
   int tma_out, wb, hb, ib;
@@ -80,54 +76,6 @@ __device__ __forceinline__ void gn_chunk_stats(const float (&v)[32], bool valid,
   }
 }
 
-// GroupNorm + Mish (+ time-embedding add) of one 32-column chunk INSIDE the epilogue (sampler steps): the tile holds whole
-// images (`wpi` warps of 32 pixels each per image), the chunk holds 32 / SEG complete groups.  Per-warp (sum, sum of squares) of
-// every group segment go through shared memory; the four epilogue warps meet on named barrier 1 (twice per chunk: publish,
-// then release the exchange buffer).  Same arithmetic as gn_apply_fast_kernel: fp32 sums, mean / variance in fp64,
-// x * (rstd * gamma) + (beta - mean * rstd * gamma), branch-free Mish.
-template <int SEG>
-__device__ __forceinline__ void gn_epi_chunk(float (&v)[32], bool valid, int lane, int q, int wpi, float inv_count,
-                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                             const float* __restrict__ te, float* gn_st) {
-  constexpr int NSEG = 32 / SEG;
-#pragma unroll
-  for (int sg = 0; sg < NSEG; ++sg) {
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < SEG; ++j) { const float x = v[sg * SEG + j]; s1 += x; s2 = fmaf(x, x, s2); }
-    if (!valid) { s1 = 0.f; s2 = 0.f; }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    if (lane == 0) { gn_st[(q * 4 + sg) * 2 + 0] = s1; gn_st[(q * 4 + sg) * 2 + 1] = s2; }
-  }
-  asm volatile("bar.sync 1, 128;" ::: "memory");
-  const int w0 = (q / wpi) * wpi;            // first warp of this warp's image
-#pragma unroll
-  for (int sg = 0; sg < NSEG; ++sg) {
-    float s1 = 0.f, s2 = 0.f;
-    for (int w = 0; w < wpi; ++w) { s1 += gn_st[((w0 + w) * 4 + sg) * 2 + 0]; s2 += gn_st[((w0 + w) * 4 + sg) * 2 + 1]; }
-    const double m = (double)s1 * (double)inv_count;
-    double var = (double)s2 * (double)inv_count - m * m;
-    if (var < 0.0) var = 0.0;
-    const float mean = (float)m, rstd = rsqrtf((float)var + kGnEps);
-#pragma unroll
-    for (int j = 0; j < SEG; j += 4) {
-      const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + sg * SEG + j));
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + sg * SEG + j));
-      float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (te) t4 = __ldg(reinterpret_cast<const float4*>(te + sg * SEG + j));
-      const float ga[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w}, tt[4] = {t4.x, t4.y, t4.z, t4.w};
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float sa = rstd * ga[u];
-        const float sd = be[u] - mean * sa;
-        v[sg * SEG + j + u] = mish_f(fmaf(v[sg * SEG + j + u], sa, sd)) + tt[u];
-      }
-    }
-  }
-  asm volatile("bar.sync 1, 128;" ::: "memory");       // the next chunk overwrites the exchange buffer
-}
-
 template <int BN>
 struct Cfg {
   static constexpr int B_TILE_BYTES = BN * KC * 2;
@@ -145,8 +93,7 @@ struct Cfg {
   static constexpr int ACC_COLS = 2 * BN;
   static constexpr int TMEM_COLS = 2 * ACC_COLS;   // two accumulator stages (power of two >= 32)
   static constexpr int STORE_STAGE_BYTES = 4 * (4096 + 2048 + 2048);   // per epilogue warp: fp32 | bf16 hi | bf16 lo tiles
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                    256 /*GroupNorm statistics exchange of the fused epilogue: [4 warps][4 segments][2]*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN>
@@ -166,7 +113,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
   uint64_t* acc_full = bars + 2 * C::STAGES;   // [2]       MMA -> epilogue
   uint64_t* acc_empty = acc_full + 2;          // [2]       epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* gn_st = reinterpret_cast<float*>(store_stage + C::STORE_STAGE_BYTES + 256);   // [4][4][2] per 32-column chunk
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -319,12 +265,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
             v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
           }
         }
-        if (p.gn_epi) {
-          const float* te = (p.gn_temb && valid) ? p.gn_temb + (int64_t)b * p.gn_temb_stride + n : nullptr;
-          if (p.gn_cpg == 32) gn_epi_chunk<32>(v, valid, lane, q, p.gn_epi, p.gn_inv_count, p.gn_gamma + n, p.gn_beta + n, te, gn_st);
-          else if (p.gn_cpg == 16) gn_epi_chunk<16>(v, valid, lane, q, p.gn_epi, p.gn_inv_count, p.gn_gamma + n, p.gn_beta + n, te, gn_st);
-          else gn_epi_chunk<8>(v, valid, lane, q, p.gn_epi, p.gn_inv_count, p.gn_gamma + n, p.gn_beta + n, te, gn_st);
-        } else
         if (p.gn_part) {
           // GroupNorm partials of (conv + bias): this warp's 32 pixels lie in one image and one 32-pixel slot
           const int slot = (oy * p.W + bx) >> 5;     // uniform across the warp (taken from lane 0 below)
@@ -887,17 +827,6 @@ static int launch_tc_impl(const LaunchCtx& lc, const TcConv& t, const TcArgs& a,
   return IGM_OK;
 }
 
-// GroupNorm + Mish applied in the epilogue: every M tile holds whole images (H*W*BB = 128, H*W a multiple of 32), a group is
-// at most one 32-column chunk wide and never straddles two chunks
-bool tc_gn_epi_ok(const TcConv& t) {
-  if (!t.valid || t.sy != 1 || t.sx != 1 || t.out_H != t.H || t.out_W != t.W || t.nph != 1 || t.w_img_rows) return false;
-  const int hw = t.H * t.W;
-  if (hw % 32 != 0 || hw > BM || BM % hw != 0 || t.BB * hw != BM) return false;
-  if (t.N % kGroups != 0) return false;
-  const int cpg = t.N / kGroups;
-  return cpg == 8 || cpg == 16 || cpg == 32;
-}
-
 bool tc_gn_fusable(const TcConv& t, int B) {
   (void)B;
   if (!t.valid || t.sy != 1 || t.sx != 1 || t.out_H != t.H || t.out_W != t.W) return false;
@@ -935,14 +864,6 @@ int launch_conv_tc(const LaunchCtx& lc, const TcConv& t, const TcRun& r) {
   if (!r.out0 && !r.hi0) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "conv_tc: no output tensor");
   if (r.ld_hi > 0 && (r.ld_hi < r.N0 || r.ld_hi % 8 != 0)) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "conv_tc: bad hi/lo output pitch");
   a.gn_part = nullptr; a.gn_cpg = 0; a.gn_slots = 0;
-  a.gn_epi = 0; a.gn_inv_count = 0.f; a.gn_gamma = a.gn_beta = a.gn_temb = nullptr; a.gn_temb_stride = 0;
-  if (r.gn_gamma) {
-    if (!tc_gn_epi_ok(t) || r.N0 != t.N || r.gn_part || !r.gn_beta)
-      IGM_FAIL(*lc.st, IGM_ERR_INVALID, "conv_tc: GroupNorm cannot be applied in the epilogue of this plan");
-    a.gn_epi = t.H * t.W / 32; a.gn_cpg = t.N / kGroups;
-    a.gn_inv_count = 1.0f / ((float)(t.H * t.W) * (float)a.gn_cpg);
-    a.gn_gamma = r.gn_gamma; a.gn_beta = r.gn_beta; a.gn_temb = r.gn_temb; a.gn_temb_stride = r.gn_temb_stride;
-  }
   if (r.gn_part) {
     if (!tc_gn_fusable(t, r.B) || r.N0 != t.N) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "conv_tc: GroupNorm statistics cannot be fused for this plan");
     a.gn_part = r.gn_part; a.gn_cpg = t.N / kGroups; a.gn_slots = tc_gn_slots(t);

@@ -87,12 +87,8 @@ struct TcRun {
   // optional fused GroupNorm(8) partial statistics of the output (sum, sum of squares per image,
   // 32-pixel slot and group), layout part[b][slot][8][2]; see tc_gn_fusable()
   float* gn_part = nullptr;
-  // optional (sampler steps, see tc_gn_epi_ok): GroupNorm(8) + Mish (+ per-image time-embedding add) applied to conv + bias INSIDE
-  // the epilogue, add0 (the residual) added afterwards: the outputs are the Block's final activation, no raw conv output exists
-  const float* gn_gamma = nullptr; const float* gn_beta = nullptr; const float* gn_temb = nullptr; int gn_temb_stride = 0;
   int kclass = K_CONV_FPROP;
 };
-bool tc_gn_epi_ok(const TcConv& t);
 // Can the epilogue of plan `t` produce the GroupNorm partials (full 128-pixel tiles, warps inside one image)?
 bool tc_gn_fusable(const TcConv& t, int B);
 inline int tc_gn_slots(const TcConv& t) { return t.H * t.W / 32; }

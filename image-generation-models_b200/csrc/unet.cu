@@ -235,7 +235,6 @@ struct igm_ctx {
   __nv_bfloat16 *att_d_hi = nullptr, *att_d_lo = nullptr, *att_p_hi = nullptr, *att_p_lo = nullptr;
   __nv_bfloat16 *att_w_hi[3] = {nullptr, nullptr, nullptr}, *att_w_lo[3] = {nullptr, nullptr, nullptr};
   float* att_cc = nullptr;
-  bool gn_epi = true;         // IGM_GN_EPI=0: sampler steps keep conv and GroupNorm-apply as two launches everywhere
   bool attn_tc = true;        // IGM_ATTN_TC=0: CUDA-core attention kernels everywhere
   int64_t attn_tc_min_pix = 65536;   // IGM_ATTN_TC_MIN=<pixels per launch> from which the tensor-core path is taken
   float *ws_group = nullptr, *ws_chan = nullptr, *ws_ln = nullptr;
@@ -868,15 +867,6 @@ struct Runner {
 
   // ---- Block: conv3x3 -> GN -> Mish (+temb) (+res) ----
   int block_fwd(BlockL& b, int H, int W, const float* temb, const float* res, const Act& out, bool lean = false) {
-    // sampler steps, tiles that hold whole images (8x8 layers): GroupNorm + Mish + temb + residual inside the conv epilogue --
-    // one launch instead of two, no raw conv output (nothing will differentiate this forward)
-    if (infer && c.gn_epi && use_tc(b.conv.tc_f) && !use_pair(b.conv.tcp_f) && tc_gn_epi_ok(b.conv.tc_f) && hi(out)) {
-      TcRun r;
-      r.B = B; r.bias = c.Pp(b.conv.pb); r.N0 = b.conv.Cout; r.kclass = K_CONV_FPROP;
-      r.out0 = lean ? nullptr : out.v; r.hi0 = hi(out); r.lo0 = lo(out); r.add0 = res;
-      r.gn_gamma = c.Pp(b.gn_w); r.gn_beta = c.Pp(b.gn_b); r.gn_temb = temb; r.gn_temb_stride = c.proj_total;
-      return launch_conv_tc(lc, b.conv.tc_f, r);
-    }
     // GroupNorm partial statistics come out of the conv epilogue when the tensor-core plan allows it
     const bool fused = use_tc(b.conv.tc_f) && tc_gn_fusable(b.conv.tc_f, B);
     IGM_TRY(conv_fwd(b.conv, H, W, H, W, 1, 1, b.raw, nullptr, nullptr, fused ? c.gn_part : nullptr));
@@ -1523,7 +1513,6 @@ int igm_unet_create(igm_ctx** out, const igm_unet_cfg* cfg, int device) {
   }
   if (const char* mbe = getenv("IGM_ATTN_MB")) c->attn_mb = !(mbe[0] == '0');
   if (const char* ate = getenv("IGM_ATTN_TC")) c->attn_tc = !(ate[0] == '0');
-  if (const char* gne = getenv("IGM_GN_EPI")) c->gn_epi = !(gne[0] == '0');
   if (const char* atm = getenv("IGM_ATTN_TC_MIN")) c->attn_tc_min_pix = atoll(atm);
   const char* halo = getenv("IGM_WGRAD_HALO");
   c->halo_on = !(halo && halo[0] == '0');
