@@ -443,3 +443,36 @@ def test_gradient_buckets_partition_the_arena_and_their_events_order_the_streams
     torch.cuda.synchronize()
     for (a, b), o in zip(ranges, outs):
         assert_close(o, ref[a:b], f"bucket [{a}, {b}) read behind its events", 1e-5)
+
+
+@pytest.mark.parametrize("case", ["cifar10", "celeba64"])
+def test_tensor_core_attention_path_at_small_batch(case, monkeypatch):
+    """The tensor-core attention path (out / dq / dv / T as per-image 1x1 convs on the tcgen05 engine, csrc/attention.cu bottom)
+    is only taken from 64 K pixels per launch on, i.e. never at the batch sizes of the other parity tests; force it with
+    IGM_ATTN_TC_MIN=0 (read at engine creation) and check loss, every gradient and the attention taps against the oracle."""
+    monkeypatch.setenv("IGM_CONV_ENGINE", "1")
+    monkeypatch.setenv("IGM_ATTN_TC_MIN", "0")
+    dim, ch, mults, H, W, B, T = CASES[case]
+    spec = O.UnetSpec(dim, ch, mults)
+    params = O.init_params(spec, seed=7)
+    unet = igm_b200.Unet(dim=dim, channels=ch, dim_mults=mults)
+    unet.load_state_dict(params)
+    gd = igm_b200.GaussianDiffusion(unet, image_size=(H, W), channels=ch, timesteps=T, loss_type="l2").cuda()
+    x, t, noise, _ = make_golden.inputs(case)
+    buf = O.diffusion_buffers(T)
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    taps = {}
+    ref_loss = O.p_losses(p, spec, buf, x, t, noise, "l2")
+    ref_grads = torch.autograd.grad(ref_loss, list(p.values()))
+    with torch.no_grad():
+        O.unet_forward(params, spec, O.q_sample(buf, x, t, noise), t, taps=taps)
+    loss = gd.p_losses(x.cuda(), t.cuda(), noise.cuda())
+    got_attn = gd.denoise_fn.read_tap("downs.0.2.out").reshape(taps["downs.0.2.out"].shape).cpu()   # training forward: TC path
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= REL_TOL * abs(ref_loss.item())
+    assert_close(got_attn, taps["downs.0.2.out"], f"{case}: attention block output through the tensor-core path")
+    worst = 0.0
+    for (name, prm), rg in zip(gd.denoise_fn.named_parameters(), ref_grads):
+        l2, mx = assert_close(prm.grad, rg, f"{case} tensor-core attention: grad {name}")
+        worst = max(worst, l2, mx)
+    _report(f"{case:12s} tensor-core attention path at B={B}: worst gradient error {worst:.2e}")
