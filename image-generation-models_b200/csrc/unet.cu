@@ -262,9 +262,7 @@ struct igm_ctx {
   bool bk_valid = false;
   cudaEvent_t ev_ln = nullptr;   // side stream has folded the LayerNorm partials workspace (ws_ln may be overwritten)
   bool ln_pending = false;
-  bool fin_per_layer = false;    // this backward folded the halo workspaces bucket by bucket (no finalize pass at the end)
-  int bucket_fin_begin[IGM_MAX_MULTS + 2] = {}, bucket_fin_ctas[IGM_MAX_MULTS + 2] = {};   // CTA range of the finalize table per bucket
-  double bucket_fin_elems[IGM_MAX_MULTS + 2] = {};
+  bool fin_per_layer = false;    // this backward folded the halo workspaces layer by layer (no finalize pass at the end)
   bool tc_available = false;
   HaloFinJob* fin_dev = nullptr;      // device job table of the halo-wgrad finalize pass
   int* fin_cta_dev = nullptr;         // CTA -> job
@@ -802,8 +800,11 @@ struct Runner {
       LaunchCtx wl;
       IGM_TRY(wgrad_begin(l, wl));
       if (c.halo_on && l.tc_wh.valid) {
-        IGM_TRY(launch_wgrad_halo(wl, l.tc_wh, B));   // workspace -> OIHW gradient by the finalize pass: one launch per
-        if (wl.stream != lc.stream) c.fin_per_layer = true;   // gradient bucket on the side stream (bucket_done), else at the end
+        IGM_TRY(launch_wgrad_halo(wl, l.tc_wh, B));   // workspace -> OIHW gradient by the finalize pass:
+        if (wl.stream != lc.stream) {                   // per layer, right behind it, when the side stream carries it
+          IGM_TRY(launch_wgrad_halo_finalize(wl, c.fin_dev, c.fin_cta_dev, l.fin_ctas, 9.0 * l.Cin * l.Cout, l.fin_begin));
+          c.fin_per_layer = true;
+        }
       } else IGM_TRY(launch_wgrad_tc(wl, l.tc_w, B, gw));
       IGM_TRY(wgrad_end(l, wl));
     } else if (!l.convT) {
@@ -937,14 +938,6 @@ struct Runner {
       IGM_TRY(launch_time_proj_backward(sl, tp, c.proj_dev, c.n_proj, c.proj_total, B, c.cfg.max_batch, c.t_act, c.t_dproj, c.t_ws,
                                         c.bucket_slab_lo[k], c.bucket_slab_hi[k]));
       if (sl.stream != lc.stream) c.side_dirty = true;
-    }
-    if (side_active() && c.fin_per_layer && tc_on() && c.halo_on && c.bucket_fin_ctas[k] > 0) {
-      // fold the halo weight-gradient workspaces of the group's layers into their OIHW gradients: ONE launch per bucket behind
-      // the group's last wgrad on the side stream (a launch per layer cost 24 x 8.7 us of launch floor per step)
-      LaunchCtx sl;
-      IGM_TRY(side_begin(sl));
-      IGM_TRY(launch_wgrad_halo_finalize(sl, c.fin_dev, c.fin_cta_dev, c.bucket_fin_ctas[k], c.bucket_fin_elems[k], c.bucket_fin_begin[k]));
-      c.side_dirty = true;
     }
     IGM_CUDA(c.st, cudaEventRecord(c.ev_bk_main[k], lc.stream));
     c.bk_side_rec[k] = false;
@@ -1215,13 +1208,6 @@ struct Runner {
     if (!time_done) IGM_TRY(time_backward(lc));
     time_done = false;
     time_after = nullptr;
-    if (side_was_active && c.fin_per_layer && tc_on() && c.halo_on && c.bucket_fin_ctas[c.n_buckets - 1] > 0) {
-      const int k = c.n_buckets - 1;   // downs.0: its layers' wgrads are all enqueued now
-      LaunchCtx sl;
-      IGM_TRY(side_begin(sl));
-      IGM_TRY(launch_wgrad_halo_finalize(sl, c.fin_dev, c.fin_cta_dev, c.bucket_fin_ctas[k], c.bucket_fin_elems[k], c.bucket_fin_begin[k]));
-      c.side_dirty = true;
-    }
     IGM_TRY(side_join());
     const bool fin_done = c.fin_per_layer;   // every halo layer was folded right behind its wgrad on the side stream
     c.fin_per_layer = false;
@@ -1641,38 +1627,6 @@ int igm_unet_bind_params(igm_ctx* c, float* params, float* grads) {
       jobs.push_back(j);
       return IGM_OK;
     });
-    // CTA ranges per gradient bucket (plan_buckets): the table is in for_each_conv order -- downs.0 .. downs.(n-1), then ups, mid,
-    // final -- so bucket 0 (ups | mid | final) is the tail and bucket k = downs.(n-k) a contiguous slice
-    {
-      const int nres = c->cfg.n_mults;
-      auto stage_first = [&](const Stage& s) { return s.r1.b1.conv.tc_wh.valid ? s.r1.b1.conv.fin_begin : -1; };
-      std::vector<int> start(nres + 1, c->fin_tiles);   // start[i] = first CTA of downs.i (or of the tail for i = nres)
-      {
-        // walk the stages in table order and take the first valid layer of each as its start
-        auto first_of = [&](Stage& s) -> int {
-          int f = -1;
-          auto look = [&](const ConvL& l) { if (f < 0 && l.tc_wh.valid) f = l.fin_begin; };
-          look(s.r1.b1.conv); look(s.r1.b2.conv); look(s.r1.res); look(s.r2.b1.conv); look(s.r2.b2.conv); look(s.r2.res);
-          look(s.attn.qkv); look(s.attn.outc); if (s.rs.present) look(s.rs.conv);
-          return f;
-        };
-        int tail = -1;
-        for (auto& s : c->ups) { const int f = first_of(s); if (tail < 0 && f >= 0) tail = f; }
-        if (tail < 0) {
-          auto look = [&](const ConvL& l) { if (tail < 0 && l.tc_wh.valid) tail = l.fin_begin; };
-          look(c->mid1.b1.conv); look(c->mid1.b2.conv); look(c->mid2.b1.conv); look(c->mid2.b2.conv); look(c->final_block.conv);
-        }
-        start[nres] = tail >= 0 ? tail : c->fin_tiles;
-        for (int i = nres - 1; i >= 0; --i) { const int f = first_of(c->downs[i]); start[i] = f >= 0 ? f : start[i + 1]; }
-      }
-      (void)stage_first;
-      auto set = [&](int k, int lo, int hi) {
-        c->bucket_fin_begin[k] = lo; c->bucket_fin_ctas[k] = hi - lo;
-        c->bucket_fin_elems[k] = (double)(hi - lo) * 32 * 32 * 9;
-      };
-      set(0, start[nres], c->fin_tiles);
-      for (int k = 1; k < c->n_buckets; ++k) { const int i = nres - k; set(k, start[i], start[i + 1]); }   // k = n_buckets-1 -> downs.0
-    }
     if (jobs.size() > 256 || (int)cta_job.size() > c->fin_cta_cap) IGM_FAIL(c->st, IGM_ERR_INVALID, "too many halo-wgrad layers");
     if (!jobs.empty()) {
       IGM_CUDA(c->st, cudaMemcpy(c->fin_dev, jobs.data(), jobs.size() * sizeof(HaloFinJob), cudaMemcpyHostToDevice));
