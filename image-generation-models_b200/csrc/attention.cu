@@ -198,7 +198,7 @@ template <bool HL>
 __global__ void __launch_bounds__(256) linattn_ctx_kernel(const float* __restrict__ qkv, const __nv_bfloat16* __restrict__ q_hi,
                                                           const __nv_bfloat16* __restrict__ q_lo, float* __restrict__ part_ws,
                                                           unsigned int* __restrict__ counters, float* __restrict__ ctx,
-                                                          float* __restrict__ kstat, int N) {
+                                                          float* __restrict__ kstat, int N, int ld, int koff) {
   __shared__ __align__(16) float buf[2 * CH * D];   // k | v tiles, later the reduction scratch
   float (*Xs)[D] = reinterpret_cast<float (*)[D]>(buf);
   float (*Ys)[D] = reinterpret_cast<float (*)[D]>(buf + CH * D);
@@ -211,12 +211,13 @@ __global__ void __launch_bounds__(256) linattn_ctx_kernel(const float* __restric
   const int nsplit = gridDim.y;
   const int n0 = blockIdx.y * CH, rows = min(CH, N - n0);
   const int tid = threadIdx.x;
-  const int64_t boff = ((int64_t)b * N + n0) * QKV;
+  // rows of `ld` floats, k at column koff, v right behind it: [M, 384] q | k | v (koff = 128) or a compact [M, 256] k | v
+  const int64_t boff = ((int64_t)b * N + n0) * ld + koff + h * D;
   if (HL) {
-    load_tile_hl(Xs, q_hi + boff + HD + h * D, q_lo + boff + HD + h * D, QKV, rows, tid);
-    load_tile_hl(Ys, q_hi + boff + 2 * HD + h * D, q_lo + boff + 2 * HD + h * D, QKV, rows, tid);
+    load_tile_hl(Xs, q_hi + boff, q_lo + boff, ld, rows, tid);
+    load_tile_hl(Ys, q_hi + boff + HD, q_lo + boff + HD, ld, rows, tid);
   } else {
-    load_tile2(Xs, qkv + boff + HD + h * D, QKV, Ys, qkv + boff + 2 * HD + h * D, QKV, rows, tid);
+    load_tile2(Xs, qkv + boff, ld, Ys, qkv + boff + HD, ld, rows, tid);
   }
   __syncthreads();
   {
@@ -638,7 +639,7 @@ int launch_linattn_forward(const LaunchCtx& lc, const float* qkv, float* out, fl
   if (B * kHeads > kCtrCap) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linear attention: batch too large");
   unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
   float* parts = ws + kCtrCap + (int64_t)B * kHeads * (D * D);
-  { cudaError_t le_ = launch_pdl(linattn_ctx_kernel<false>, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)nullptr, parts, counters, ctx, kstat, n); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
+  { cudaError_t le_ = launch_pdl(linattn_ctx_kernel<false>, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)nullptr, parts, counters, ctx, kstat, n, QKV, HD); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
   { cudaError_t le_ = launch_pdl(linattn_out_kernel, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, ctx, out, n, out_hi, out_lo); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
@@ -646,14 +647,14 @@ int launch_linattn_forward(const LaunchCtx& lc, const float* qkv, float* out, fl
 }
 
 // statistics + context only (the first half of launch_linattn_forward)
-int launch_linattn_ctx(const LaunchCtx& lc, const float* qkv, float* ctx, float* kstat, int B, int n, float* ws) {
+int launch_linattn_ctx(const LaunchCtx& lc, const float* qkv, float* ctx, float* kstat, int B, int n, float* ws, bool kv_only) {
   const int nsplit = cdiv(n, CH);
   if (nsplit > kMaxSplit) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linear attention: more than 8192 pixels per image");
   ProfScope ps_(lc, K_ATTN, 2.0 * B * kHeads * (double)n * D * D, 4.0 * B * (double)n * 2 * HD);
   if (B * kHeads > kCtrCap) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linear attention: batch too large");
   unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
   float* parts = ws + kCtrCap + (int64_t)B * kHeads * (D * D);
-  { cudaError_t le_ = launch_pdl(linattn_ctx_kernel<false>, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)nullptr, parts, counters, ctx, kstat, n); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
+  { cudaError_t le_ = launch_pdl(linattn_ctx_kernel<false>, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)nullptr, parts, counters, ctx, kstat, n, kv_only ? 2 * HD : QKV, kv_only ? 0 : HD); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }
@@ -704,7 +705,7 @@ int launch_linattn_ctx_hl(const LaunchCtx& lc, const __nv_bfloat16* q_hi, const 
   unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
   float* parts = ws + kCtrCap + (int64_t)B * kHeads * (D * D);
   IGM_LAUNCH_PDL(linattn_ctx_kernel<true>, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, (const float*)nullptr, q_hi, q_lo,
-                 parts, counters, ctx, kstat, n);
+                 parts, counters, ctx, kstat, n, QKV, HD);
   return IGM_OK;
 }
 

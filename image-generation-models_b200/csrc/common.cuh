@@ -262,7 +262,9 @@ int linattn_ws_floats(int B, int n);
 int launch_linattn_forward(const LaunchCtx& lc, const float* qkv, float* out, float* ctx, float* kstat,
                            int B, int n, float* ws, __nv_bfloat16* out_hi = nullptr, __nv_bfloat16* out_lo = nullptr);
 // inference shortcut (attention.cu: linattn_mb_kernel): context only, then the per-image matrix M_b = W_out ctx^T W_q
-int launch_linattn_ctx(const LaunchCtx& lc, const float* qkv, float* ctx, float* kstat, int B, int n, float* ws);
+// kv_only: `qkv` is a compact [M, 256] k | v tensor (the sampler's per-image-matrix path never forms q)
+int launch_linattn_ctx(const LaunchCtx& lc, const float* qkv, float* ctx, float* kstat, int B, int n, float* ws,
+                       bool kv_only = false);
 // tensor-core attention path (training, n >= 1024): glue kernels around the per-image 1x1 convs of conv_tc.cu; q / k / v
 // and dO come as bf16 hi / lo staging pairs ([M, 384] resp. [M, 128]), d(qkv) leaves as thirds of a [M, 384] pair
 int launch_linattn_ctx_hl(const LaunchCtx& lc, const __nv_bfloat16* q_hi, const __nv_bfloat16* q_lo, float* ctx, float* kstat,

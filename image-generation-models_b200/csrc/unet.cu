@@ -157,6 +157,7 @@ struct AttnL {
   bool mb_ok = false;
   __nv_bfloat16 *mb_hi = nullptr, *mb_lo = nullptr;   // [B][C][C]
   TcConv tc_mb;
+  TcConv tc_kv;   // to_qkv restricted to its k | v rows (the per-image-matrix path of sampler steps never forms q)
 };
 
 struct ResampleL {
@@ -271,6 +272,7 @@ struct igm_ctx {
   double fin_elems = 0;
   bool halo_on = true;
   bool attn_mb = true;                // IGM_ATTN_MB=0: always materialise the attention output
+  bool attn_kv_only = true;           // IGM_ATTN_KV=0: the per-image-matrix path still computes all of q | k | v
   PackJob* pack_dev = nullptr;        // device job table of igm_unet_pack_weights
   int pack_n = 0, pack_engine = -1;
   int64_t pack_total = 0;
@@ -994,16 +996,25 @@ struct Runner {
       IGM_TRY(conv_fwd(a.outc, H, W, H, W, 1, 0, a.out.v, x, &a.out));
       return IGM_OK;
     }
-    IGM_TRY(conv_fwd(a.qkv, H, W, H, W, 1, 0, a.qkv_t, nullptr));
     if (c.attn_mb && (infer || !c.cfg.training) && tc_on() && a.tc_mb.valid && use_tc(a.qkv.tc_f)) {
-      // inference, n >= 2C: y = (W_out ctx^T W_q) LN(x) + b + x with one C x C matrix per image
-      IGM_TRY(launch_linattn_ctx(lc, a.qkv_t, a.ctx, a.kstat, B, H * W, c.attn_ws));
+      // inference, n >= 8C: y = (W_out ctx^T W_q) LN(x) + b + x with one C x C matrix per image; q itself is never
+      // needed, so to_qkv only produces its k | v rows ([M, 256], two thirds of the output traffic that bounds this conv)
+      const bool kv_only = c.attn_kv_only && use_tc(a.tc_kv);
+      if (kv_only) {
+        TcRun r;
+        r.B = B; r.out0 = a.qkv_t; r.N0 = 2 * kHeads * kDimHead; r.kclass = K_CONV_FPROP;
+        IGM_TRY(launch_conv_tc(lc, a.tc_kv, r));
+      } else {
+        IGM_TRY(conv_fwd(a.qkv, H, W, H, W, 1, 0, a.qkv_t, nullptr));
+      }
+      IGM_TRY(launch_linattn_ctx(lc, a.qkv_t, a.ctx, a.kstat, B, H * W, c.attn_ws, kv_only));
       IGM_TRY(launch_linattn_mb(lc, a.ctx, c.Pp(a.outc.pw), c.Pp(a.qkv.pw), B, a.C, a.mb_hi, a.mb_lo));
       TcRun r;
       r.B = B; r.bias = c.Pp(a.outc.pb); r.out0 = a.out.v; r.N0 = a.C; r.add0 = x; r.kclass = K_CONV_FPROP;
       r.hi0 = hi(a.out); r.lo0 = lo(a.out);
       return launch_conv_tc(lc, a.tc_mb, r);
     }
+    IGM_TRY(conv_fwd(a.qkv, H, W, H, W, 1, 0, a.qkv_t, nullptr));
     IGM_TRY(launch_linattn_forward(lc, a.qkv_t, lean_ok(a.outc) ? nullptr : a.att.v, a.ctx, a.kstat, B, H * W, c.attn_ws,
                                    hi(a.att), lo(a.att)));
     IGM_TRY(conv_fwd(a.outc, H, W, H, W, 1, 0, a.out.v, x, &a.out));
@@ -1369,6 +1380,11 @@ static int plan_tc(igm_ctx* c) {
                           c->att_w_lo[2], 3 * hd));
     }
     if (!a.mb_ok || !a.ln.hi) return IGM_OK;
+    if (a.qkv.tc_f.valid && a.qkv.wf_hi) {
+      const int hd = kHeads * kDimHead;   // packed weights are [Cout rows][Cin]: rows hd .. 3 hd - 1 are k | v
+      IGM_TRY(tc_plan(c->st, a.tc_kv, a.C, 2 * hd, a.H, a.W, c->cfg.max_batch, 1, 0, a.ln.hi, a.ln.lo,
+                      a.qkv.wf_hi + (int64_t)hd * a.C, a.qkv.wf_lo + (int64_t)hd * a.C));
+    }
     return tc_plan_img(c->st, a.tc_mb, a.C, a.C, a.H, a.W, c->cfg.max_batch, a.ln.hi, a.ln.lo, a.mb_hi, a.mb_lo);
   };
   if (rc == IGM_OK) for (auto& s : c->downs) { rc = plan_mb(s.attn); if (rc != IGM_OK) break; }
@@ -1512,6 +1528,7 @@ int igm_unet_create(igm_ctx** out, const igm_unet_cfg* cfg, int device) {
     if (ps[0] == '1') cudaDeviceSetCacheConfig(cudaFuncCachePreferShared);
   }
   if (const char* mbe = getenv("IGM_ATTN_MB")) c->attn_mb = !(mbe[0] == '0');
+  if (const char* kve = getenv("IGM_ATTN_KV")) c->attn_kv_only = !(kve[0] == '0');
   if (const char* ate = getenv("IGM_ATTN_TC")) c->attn_tc = !(ate[0] == '0');
   if (const char* atm = getenv("IGM_ATTN_TC_MIN")) c->attn_tc_min_pix = atoll(atm);
   const char* halo = getenv("IGM_WGRAD_HALO");
