@@ -376,6 +376,15 @@ __device__ __forceinline__ float mish_grad_f(float x) {
   const float r = rcp_approx(n + 2.f);
   return n * r + x * (4.f * w * (w + 1.f)) * (r * r);
 }
+// branch-free form for the kernels whose tiles live in shared memory (registers are not the constraint there): the
+// exponent argument is clamped at 20, where t = 1 - 2/n is already 1.0f and the x * dt/dx term is < 1e-15, so the value
+// equals the early-out's 1.0f; without the per-element branch the four chains of a float4 interleave.
+__device__ __forceinline__ float mish_grad_nb_f(float x) {
+  const float w = ex2_approx(fminf(x, 20.f) * 1.4426950408889634f);
+  const float n = w * (w + 2.f);
+  const float r = rcp_approx(n + 2.f);
+  return n * r + x * (4.f * w * (w + 1.f)) * (r * r);
+}
 // bf16 hi/lo staging of four consecutive fp32 values (operands of the tcgen05 bf16x3 engine)
 // (a, b) -> packed bf16 hi pair and packed bf16 lo pair (element a in the low half: lower address); two values per cvt
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {

@@ -540,6 +540,7 @@ __global__ void __launch_bounds__(256) gn_bwd_bulk_kernel(const GnBwdArgs a, int
   }
   const float mean = __ldg(a.stats + ((int64_t)b * kGroups + ly.group) * 2 + 0);
   const float rstd = __ldg(a.stats + ((int64_t)b * kGroups + ly.group) * 2 + 1);
+  const float nmr = -mean * rstd;
   const int c = ly.c4 * 4;
   const float4 ga4 = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
   const float4 be4 = __ldg(reinterpret_cast<const float4*>(a.beta + c));
@@ -569,9 +570,9 @@ __global__ void __launch_bounds__(256) gn_bwd_bulk_kernel(const GnBwdArgs a, int
     float* dv = reinterpret_cast<float*>(&d4);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float n = (yv[j] - mean) * rstd;
-      const float g = n * ga[j] + be[j];
-      const float dg = dv[j] * mish_grad_f(g);
+      const float n = fmaf(yv[j], rstd, nmr);   // (y - mean) * rstd
+      const float g = fmaf(n, ga[j], be[j]);
+      const float dg = dv[j] * mish_grad_nb_f(g);
       dgam[j] += dg * n;
       dbet[j] += dg;
       dte[j] += dv[j];
@@ -597,16 +598,17 @@ __global__ void __launch_bounds__(256) gn_bwd_bulk_kernel(const GnBwdArgs a, int
   }
   __syncthreads();
   const float m1 = s_m[ly.group][0], m2 = s_m[ly.group][1];
+  const float q1 = -m1 * rstd, q2 = -m2 * rstd;
   float dbs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 2
   for (int i = 0; i < nv; ++i) {
     const float4 n = *reinterpret_cast<const float4*>(ty + loc0 + i * lstep);
     const float4 dn = *reinterpret_cast<const float4*>(td + loc0 + i * lstep);
     float4 o;
-    o.x = rstd * (dn.x - m1 - n.x * m2);
-    o.y = rstd * (dn.y - m1 - n.y * m2);
-    o.z = rstd * (dn.z - m1 - n.z * m2);
-    o.w = rstd * (dn.w - m1 - n.w * m2);
+    o.x = fmaf(n.x, q2, fmaf(dn.x, rstd, q1));   // rstd * (dn - m1 - n * m2)
+    o.y = fmaf(n.y, q2, fmaf(dn.y, rstd, q1));
+    o.z = fmaf(n.z, q2, fmaf(dn.z, rstd, q1));
+    o.w = fmaf(n.w, q2, fmaf(dn.w, rstd, q1));
     dbs[0] += o.x; dbs[1] += o.y; dbs[2] += o.z; dbs[3] += o.w;
     const int64_t off = base + (int64_t)i * lstep;
     if (a.dy) *reinterpret_cast<float4*>(a.dy + off) = o;
@@ -1149,7 +1151,8 @@ int launch_gn_backward(const LaunchCtx& lc, const GnBwdArgs& a) {
     cudaError_t e;
     static const bool bulk = [] { const char* v = getenv("IGM_GN_BULK"); return !(v && v[0] == '0'); }();
     // bulk copies need 16-byte aligned sources: every tensor comes from the 256-byte aligned arena, slices are 4 KB multiples
-    if (bulk && ((reinterpret_cast<uintptr_t>(a.y) | reinterpret_cast<uintptr_t>(a.d_out)) & 15) == 0) {
+    const bool aligned = ((reinterpret_cast<uintptr_t>(a.y) | reinterpret_cast<uintptr_t>(a.d_out)) & 15) == 0;
+    if (bulk && aligned) {
       const int smem = std::max(2 * nv * 1024 * (int)sizeof(float), 256 * 4 * (int)sizeof(float4));
       static bool attr_set = false;
       if (!attr_set) {
