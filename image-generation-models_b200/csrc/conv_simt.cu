@@ -435,7 +435,9 @@ __global__ void __launch_bounds__(256) conv_stem_rows_kernel(const float* __rest
                                                              const float* __restrict__ bias, float* __restrict__ out,
                                                              int B, int H, int W, int Cout, int R) {
   constexpr int T = KS * KS, PAD = (KS - 1) / 2;
-  extern __shared__ float sx[];                  // [R + 2 PAD][(W + 2 PAD) * CI]
+  // [R + 2 PAD][W + 2 PAD] pixels of FOUR floats (channels CI .. 3 are padding): one aligned 128-bit broadcast load brings
+  // all input channels of a tap (the scalar form issued CI loads per tap and was bound by the shared-memory pipe)
+  extern __shared__ __align__(16) float sx[];
   const int bands = (H + R - 1) / R;
   const int b = blockIdx.x / bands, y0 = (blockIdx.x - b * bands) * R;
   const int rows = min(R, H - y0);
@@ -448,13 +450,19 @@ __global__ void __launch_bounds__(256) conv_stem_rows_kernel(const float* __rest
     w[k] = cok ? __ldg(reinterpret_cast<const float2*>(Wp + (int64_t)k * Cout + co)) : make_float2(0.f, 0.f);
   float2 bv = make_float2(0.f, 0.f);
   if (bias && cok) bv = __ldg(reinterpret_cast<const float2*>(bias + co));
-  const int PW = (W + 2 * PAD) * CI;
+  const int PWp = W + 2 * PAD;               // padded pixels per row
   const int nrow = rows + 2 * PAD;
-  for (int i = threadIdx.x; i < nrow * PW; i += 256) {
-    const int rr = i / PW, cc = i - rr * PW;
-    const int px = cc / CI, ci = cc - px * CI;
+  for (int i = threadIdx.x; i < nrow * PWp; i += 256) {
+    const int rr = i / PWp, px = i - rr * PWp;
     const int iy = y0 - PAD + rr, ix = px - PAD;
-    sx[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(X + (((int64_t)b * H + iy) * W + ix) * CI + ci) : 0.f;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      const float* xp = X + (((int64_t)b * H + iy) * W + ix) * CI;
+      float* ve = reinterpret_cast<float*>(&v);
+#pragma unroll
+      for (int ci = 0; ci < CI; ++ci) ve[ci] = __ldg(xp + ci);
+    }
+    *reinterpret_cast<float4*>(sx + (size_t)i * 4) = v;
   }
   __syncthreads();
   if (!cok) return;
@@ -464,19 +472,22 @@ __global__ void __launch_bounds__(256) conv_stem_rows_kernel(const float* __rest
     const int pb = (p + 8 < npx) ? p + 8 : p;
     const int ya = p / W, xa = p - ya * W;
     const int yb = pb / W, xb = pb - yb * W;
-    const float* sa = sx + ya * PW + xa * CI;
-    const float* sb = sx + yb * PW + xb * CI;
+    const float* sa = sx + ((size_t)ya * PWp + xa) * 4;
+    const float* sb = sx + ((size_t)yb * PWp + xb) * 4;
     float2 acca = bv, accb = bv;
 #pragma unroll
     for (int ky = 0; ky < KS; ++ky)
 #pragma unroll
-      for (int kx = 0; kx < KS; ++kx)
+      for (int kx = 0; kx < KS; ++kx) {
+        const float4 va4 = *reinterpret_cast<const float4*>(sa + ((size_t)ky * PWp + kx) * 4);
+        const float4 vb4 = *reinterpret_cast<const float4*>(sb + ((size_t)ky * PWp + kx) * 4);
+        const float va[4] = {va4.x, va4.y, va4.z, va4.w}, vb[4] = {vb4.x, vb4.y, vb4.z, vb4.w};
 #pragma unroll
         for (int ci = 0; ci < CI; ++ci) {
-          const float va = sa[ky * PW + kx * CI + ci], vb = sb[ky * PW + kx * CI + ci];
-          ffma2(acca, make_float2(va, va), w[(ky * KS + kx) * CI + ci]);
-          ffma2(accb, make_float2(vb, vb), w[(ky * KS + kx) * CI + ci]);
+          ffma2(acca, make_float2(va[ci], va[ci]), w[(ky * KS + kx) * CI + ci]);
+          ffma2(accb, make_float2(vb[ci], vb[ci]), w[(ky * KS + kx) * CI + ci]);
         }
+      }
     *reinterpret_cast<float2*>(out + (((int64_t)b * H + y0 + ya) * W + xa) * Cout + co) = acca;
     if (pb != p) *reinterpret_cast<float2*>(out + (((int64_t)b * H + y0 + yb) * W + xb) * Cout + co) = accb;
   }
@@ -486,9 +497,11 @@ template <int CI>
 static void launch_stem(const ConvArgs& a, dim3 grid, int per, cudaStream_t st) {
   static const bool rows_off = [] { const char* e = getenv("IGM_STEM_ROWS"); return e && e[0] == '0'; }();
   if (!rows_off && a.N % 2 == 0) {
-    const int R = a.IH < 4 ? a.IH : 4;
+    // bands of 8 rows while that still leaves two CTAs per SM (fewer prologues, one wave); else 4
+    int R = ((int64_t)a.B * cdiv(a.IH, 8) * cdiv(a.N, 64) >= 296) ? 8 : 4;
+    if (a.IH < R) R = a.IH;
     const int PADk = (a.KH - 1) / 2;
-    const size_t smem = (size_t)(R + 2 * PADk) * (a.IW + 2 * PADk) * CI * sizeof(float);
+    const size_t smem = (size_t)(R + 2 * PADk) * (a.IW + 2 * PADk) * 4 * sizeof(float);
     if (smem <= 40 * 1024) {
       dim3 g2((unsigned)(a.B * cdiv(a.IH, R)), (unsigned)cdiv(a.N, 64));
       if (a.KH == 3)
