@@ -13,6 +13,9 @@
 // broadcast load per 4..16 FMAs.
 #include "common.cuh"
 
+#include <algorithm>
+#include <stdlib.h>
+
 namespace igm {
 namespace {
 
@@ -172,6 +175,51 @@ __device__ __forceinline__ void load_tile_hl(float (*dst)[D], const __nv_bfloat1
   }
 }
 
+// The same tiles in two halves -- global loads into registers, registers to shared memory -- so that a kernel walking
+// several chunks can have the NEXT chunk's loads in flight while it computes on the current one.
+constexpr int kTileIt = CH * (D / 4) / 256;
+__device__ __forceinline__ void tile_fetch(float4 (&v)[kTileIt], const float* __restrict__ src, int ld, int rows, int tid) {
+#pragma unroll
+  for (int k = 0; k < kTileIt; ++k) {
+    const int i = tid + k * 256;
+    const int nn = i >> 3, c4 = (i & 7) * 4;
+    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nn < rows) v[k] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)nn * ld + c4));
+  }
+}
+__device__ __forceinline__ void tile_fetch_hl(uint2 (&h)[kTileIt], uint2 (&l)[kTileIt], const __nv_bfloat16* __restrict__ hi,
+                                              const __nv_bfloat16* __restrict__ lo, int ld, int rows, int tid) {
+#pragma unroll
+  for (int k = 0; k < kTileIt; ++k) {
+    const int i = tid + k * 256;
+    const int nn = i >> 3, c4 = (i & 7) * 4;
+    h[k] = l[k] = make_uint2(0u, 0u);
+    if (nn < rows) {
+      h[k] = __ldg(reinterpret_cast<const uint2*>(hi + (int64_t)nn * ld + c4));
+      l[k] = __ldg(reinterpret_cast<const uint2*>(lo + (int64_t)nn * ld + c4));
+    }
+  }
+}
+__device__ __forceinline__ void tile_store(float (*dst)[D], const float4 (&v)[kTileIt], int tid) {
+#pragma unroll
+  for (int k = 0; k < kTileIt; ++k) {
+    const int i = tid + k * 256;
+    *reinterpret_cast<float4*>(&dst[i >> 3][(i & 7) * 4]) = v[k];
+  }
+}
+__device__ __forceinline__ void tile_store_hl(float (*dst)[D], const uint2 (&h)[kTileIt], const uint2 (&l)[kTileIt], int tid) {
+#pragma unroll
+  for (int k = 0; k < kTileIt; ++k) {
+    const int i = tid + k * 256;
+    float4 v;
+    v.x = __uint_as_float(h[k].x << 16) + __uint_as_float(l[k].x << 16);
+    v.y = __uint_as_float(h[k].x & 0xffff0000u) + __uint_as_float(l[k].x & 0xffff0000u);
+    v.z = __uint_as_float(h[k].y << 16) + __uint_as_float(l[k].y << 16);
+    v.w = __uint_as_float(h[k].y & 0xffff0000u) + __uint_as_float(l[k].y & 0xffff0000u);
+    *reinterpret_cast<float4*>(&dst[i >> 3][(i & 7) * 4]) = v;
+  }
+}
+
 constexpr int PART = 2 * D + D * D;   // per-chunk partial: max[32] | sum[32] | S[32][32]
 
 // "last CTA of the group finishes the job": returns true in exactly one CTA of the gridDim.y CTAs that
@@ -190,74 +238,111 @@ __device__ __forceinline__ bool last_chunk_done(unsigned int* counter, int tid) 
   return s_last != 0;
 }
 
-// Pass 1, grid (B*heads, nsplit): chunk-local softmax statistics of k and the unnormalised context
-//   m[d] = max_n k[n][d],  l[d] = sum_n exp(k - m),  S[d][e] = sum_n exp(k[n][d] - m[d]) v[n][e];
-// the last CTA of each (batch, head) merges the chunk partials into ctx / kstat.
+// Pass 1, grid (B*heads, nsplit): softmax statistics of k over the pixels and the context
+//   m[d] = max_n k[n][d],  l[d] = sum_n exp(k - m),  S[d][e] = sum_n exp(k[n][d] - m[d]) v[n][e],  ctx = S / l.
+// A CTA walks `cpc` consecutive 128-pixel chunks: chunk-local statistics as before, merged into running (m, l, S) with the
+// usual rescaling (fixed order -> deterministic): the one-chunk-per-CTA form paid a partial write, a gpu-scope fence and a
+// share of the last-CTA merge per chunk.  (Prefetching the next chunk into registers was measured as well: 122 registers,
+// two CTAs per SM, slower than letting five resident CTAs hide the load latency.)  With more than one CTA per
+// (batch, head) the last one merges the CTAs' running statistics into ctx / kstat.
 // HL: q / k / v come from the bf16 hi / lo staging pair of the to_qkv output (tensor-core attention path, no fp32 qkv)
 template <bool HL>
-__global__ void __launch_bounds__(256) linattn_ctx_kernel(const float* __restrict__ qkv, const __nv_bfloat16* __restrict__ q_hi,
-                                                          const __nv_bfloat16* __restrict__ q_lo, float* __restrict__ part_ws,
-                                                          unsigned int* __restrict__ counters, float* __restrict__ ctx,
-                                                          float* __restrict__ kstat, int N, int ld, int koff) {
+__global__ void __launch_bounds__(256, 4) linattn_ctx_kernel(const float* __restrict__ qkv, const __nv_bfloat16* __restrict__ q_hi,
+                                                             const __nv_bfloat16* __restrict__ q_lo, float* __restrict__ part_ws,
+                                                             unsigned int* __restrict__ counters, float* __restrict__ ctx,
+                                                             float* __restrict__ kstat, int N, int ld, int koff, int cpc) {
   __shared__ __align__(16) float buf[2 * CH * D];   // k | v tiles, later the reduction scratch
   float (*Xs)[D] = reinterpret_cast<float (*)[D]>(buf);
   float (*Ys)[D] = reinterpret_cast<float (*)[D]>(buf + CH * D);
   float (*part)[64][17] = reinterpret_cast<float (*)[64][17]>(buf);
   __shared__ float ctxs[D][D + 1];
+  __shared__ float r_ctx[D][D + 1];                 // running S
   __shared__ float red[8][D];
-  __shared__ float s_kmax[D], s_ksum[D];
+  __shared__ float s_kmax[D], s_ksum[D], r_max[D], r_sum[D];
   pdl_wait();
   const int bh = blockIdx.x, b = bh / kHeads, h = bh % kHeads;
   const int nsplit = gridDim.y;
-  const int n0 = blockIdx.y * CH, rows = min(CH, N - n0);
+  const int nchunks = (N + CH - 1) / CH;
+  const int c_begin = blockIdx.y * cpc, c_end = min(nchunks, c_begin + cpc);
   const int tid = threadIdx.x;
   // rows of `ld` floats, k at column koff, v right behind it: [M, 384] q | k | v (koff = 128) or a compact [M, 256] k | v
-  const int64_t boff = ((int64_t)b * N + n0) * ld + koff + h * D;
-  if (HL) {
-    load_tile_hl(Xs, q_hi + boff, q_lo + boff, ld, rows, tid);
-    load_tile_hl(Ys, q_hi + boff + HD, q_lo + boff + HD, ld, rows, tid);
-  } else {
-    load_tile2(Xs, qkv + boff, ld, Ys, qkv + boff + HD, ld, rows, tid);
-  }
-  __syncthreads();
-  {
-    const int d = tid & 31, r = tid >> 5;
-    float m = -INFINITY;
-    for (int nn = r; nn < rows; nn += 8) m = fmaxf(m, Xs[nn][d]);
-    red[r][d] = m;
-    __syncthreads();
-    if (tid < D) {
-      float t = red[0][tid];
-#pragma unroll
-      for (int i = 1; i < 8; ++i) t = fmaxf(t, red[i][tid]);
-      s_kmax[tid] = t;
+  const int64_t boff0 = (int64_t)b * N * ld + koff + h * D;
+  auto load = [&](int c) {
+    const int64_t boff = boff0 + (int64_t)c * CH * ld;
+    const int rows = min(CH, N - c * CH);
+    if (HL) {
+      load_tile_hl(Xs, q_hi + boff, q_lo + boff, ld, rows, tid);
+      load_tile_hl(Ys, q_hi + boff + HD, q_lo + boff + HD, ld, rows, tid);
+    } else {
+      load_tile2(Xs, qkv + boff, ld, Ys, qkv + boff + HD, ld, rows, tid);
     }
-    __syncthreads();
-    for (int nn = r; nn < rows; nn += 8) Xs[nn][d] = expf(Xs[nn][d] - s_kmax[d]);
-    __syncthreads();
-  }
+  };
+  load(c_begin);
+  __syncthreads();
   const int grp = tid >> 6, t64 = tid & 63;
   const int d0 = (t64 >> 3) * 4, e0 = (t64 & 7) * 4;
-  float acc[4][4], xsum[4];
+  for (int c = c_begin; c < c_end; ++c) {
+    const int rows = min(CH, N - c * CH);
+    const bool more = c + 1 < c_end;
+    {
+      const int d = tid & 31, r = tid >> 5;
+      float m = -INFINITY;
+      for (int nn = r; nn < rows; nn += 8) m = fmaxf(m, Xs[nn][d]);
+      red[r][d] = m;
+      __syncthreads();
+      if (tid < D) {
+        float t = red[0][tid];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    xsum[i] = 0.f;
+        for (int i = 1; i < 8; ++i) t = fmaxf(t, red[i][tid]);
+        s_kmax[tid] = t;
+      }
+      __syncthreads();
+      for (int nn = r; nn < rows; nn += 8) Xs[nn][d] = expf(Xs[nn][d] - s_kmax[d]);
+      __syncthreads();
+    }
+    float acc[4][4], xsum[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int i = 0; i < 4; ++i) {
+      xsum[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    }
+    outer4x4(Xs, Ys, rows, grp, d0, e0, acc, xsum);
+    __syncthreads();   // `part` aliases the tiles
+    reduce_groups(acc, xsum, grp, t64, d0, e0, part, ctxs, s_ksum);
+    // running (m, l, S) <- merge with this chunk's
+    if (c == c_begin) {
+      for (int i = tid; i < D * D; i += 256) r_ctx[i >> 5][i & 31] = ctxs[i >> 5][i & 31];
+      if (tid < D) { r_max[tid] = s_kmax[tid]; r_sum[tid] = s_ksum[tid]; }
+    } else {
+      for (int i = tid; i < D * D; i += 256) {
+        const int d = i >> 5, e = i & 31;
+        const float mo = r_max[d], mc = s_kmax[d], mn = fmaxf(mo, mc);
+        r_ctx[d][e] = fmaf(r_ctx[d][e], expf(mo - mn), ctxs[d][e] * expf(mc - mn));
+      }
+      __syncthreads();   // every reader of r_max is done
+      if (tid < D) {
+        const float mo = r_max[tid], mc = s_kmax[tid], mn = fmaxf(mo, mc);
+        r_sum[tid] = fmaf(r_sum[tid], expf(mo - mn), s_ksum[tid] * expf(mc - mn));
+        r_max[tid] = mn;
+      }
+    }
+    __syncthreads();
+    if (more) {
+      load(c + 1);
+      __syncthreads();
+    }
   }
-  outer4x4(Xs, Ys, rows, grp, d0, e0, acc, xsum);
-  __syncthreads();   // `part` aliases the tiles
-  reduce_groups(acc, xsum, grp, t64, d0, e0, part, ctxs, s_ksum);
   float* cdst = ctx + (int64_t)bh * D * D;
   float* kdst = kstat + (int64_t)bh * D * 2;
   if (nsplit == 1) {
-    for (int i = tid; i < D * D; i += 256) cdst[i] = ctxs[i >> 5][i & 31] / s_ksum[i >> 5];
-    if (tid < D) { kdst[tid * 2] = s_kmax[tid]; kdst[tid * 2 + 1] = s_ksum[tid]; }
+    for (int i = tid; i < D * D; i += 256) cdst[i] = r_ctx[i >> 5][i & 31] / r_sum[i >> 5];
+    if (tid < D) { kdst[tid * 2] = r_max[tid]; kdst[tid * 2 + 1] = r_sum[tid]; }
     return;
   }
   float* dst = part_ws + ((int64_t)bh * nsplit + blockIdx.y) * PART;
-  if (tid < D) { dst[tid] = s_kmax[tid]; dst[D + tid] = s_ksum[tid]; }
-  for (int i = tid; i < D * D; i += 256) dst[2 * D + i] = ctxs[i >> 5][i & 31];
+  if (tid < D) { dst[tid] = r_max[tid]; dst[D + tid] = r_sum[tid]; }
+  for (int i = tid; i < D * D; i += 256) dst[2 * D + i] = r_ctx[i >> 5][i & 31];
   if (!last_chunk_done(counters + bh, tid)) return;
   // merge: global max / denominator, rescaled sum of the partial contexts (fixed order -> deterministic)
   const float* src = part_ws + (int64_t)bh * nsplit * PART;
@@ -478,20 +563,28 @@ __global__ void __launch_bounds__(256) linattn_mb_kernel(const float* __restrict
   }
   __syncthreads();
   // A[c][(h,d)]: warp -> 4 rows, lane -> d; W_out values are warp-wide broadcasts, ctx rows are 33 floats apart
+  // (the lane's ctx row is read once per head and kept in registers for the warp's four rows, W_out arrives as 128-bit
+  // broadcasts: 64 shared-memory loads per head and warp instead of 256; same summation order as the scalar form)
   {
     const int w = tid >> 5, lane = tid & 31;
 #pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-      const int r = w * 4 + rr;
+    for (int h = 0; h < kHeads; ++h) {
+      float cx[D];
+      const float* cxp = s_ctx + (h * D + lane) * 33;
 #pragma unroll
-      for (int h = 0; h < kHeads; ++h) {
-        const float* wo = s_wo + r * HD + h * D;
-        const float* cx = s_ctx + (h * D + lane) * 33;
+      for (int e = 0; e < D; ++e) cx[e] = cxp[e];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int r = w * 4 + rr;
+        const float4* wo = reinterpret_cast<const float4*>(s_wo + r * HD + h * D);
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-        for (int e = 0; e < D; e += 2) {
-          a0 = fmaf(wo[e], cx[e], a0);
-          a1 = fmaf(wo[e + 1], cx[e + 1], a1);
+        for (int e4 = 0; e4 < D / 4; ++e4) {
+          const float4 wv = wo[e4];
+          a0 = fmaf(wv.x, cx[4 * e4 + 0], a0);
+          a1 = fmaf(wv.y, cx[4 * e4 + 1], a1);
+          a0 = fmaf(wv.z, cx[4 * e4 + 2], a0);
+          a1 = fmaf(wv.w, cx[4 * e4 + 3], a1);
         }
         s_a[r * HD + h * D + lane] = a0 + a1;
       }
@@ -628,6 +721,18 @@ __global__ void __launch_bounds__(256) linattn_dk_kernel(const __nv_bfloat16* __
 // scratch layout: kCtrCap chunk counters (zero on entry, self re-arming) | [B*heads][32*32] dctx | chunk partials.
 // The counter block has a FIXED size: were it sized by the batch of the call, the dctx / partial regions of a small batch
 // would land on counters a later, larger batch of the same context expects to find zero.
+// chunks per CTA of the statistics / context kernel: up to 4 (a whole image where it has no more: no cross-CTA merge at
+// all), halved while the launch would leave fewer than three CTAs per SM.  Measured: 4 chunks per CTA +0.7 % on the CIFAR-10
+// sampler; unconditionally it cost CelebA-64 at 32 images 0.4 % (its 32x32 / 16x16 blocks were left with 256 / 128 CTAs).
+// IGM_ATTN_CPC overrides (1 = one chunk per CTA as in round 1).
+static int ctx_cpc(int nchunks, int B) {
+  static const int env = [] { const char* e = getenv("IGM_ATTN_CPC"); return e ? atoi(e) : 0; }();
+  int cpc = env > 0 ? env : 4;
+  if (cpc > nchunks) cpc = nchunks;
+  if (env <= 0)
+    while (cpc > 1 && B * kHeads * cdiv(nchunks, cpc) < 148 * 3) cpc >>= 1;
+  return cpc;
+}
 constexpr int kCtrCap = 8192;   // (batch, head) pairs: B <= 2048
 int linattn_ws_floats(int B, int n) { return kCtrCap + B * kHeads * (D * D + cdiv(n, CH) * PART); }
 
@@ -639,7 +744,7 @@ int launch_linattn_forward(const LaunchCtx& lc, const float* qkv, float* out, fl
   if (B * kHeads > kCtrCap) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linear attention: batch too large");
   unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
   float* parts = ws + kCtrCap + (int64_t)B * kHeads * (D * D);
-  { cudaError_t le_ = launch_pdl(linattn_ctx_kernel<false>, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)nullptr, parts, counters, ctx, kstat, n, QKV, HD); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
+  { cudaError_t le_ = launch_pdl(linattn_ctx_kernel<false>, dim3(B * kHeads, cdiv(nsplit, ctx_cpc(nsplit, B))), dim3(256), (size_t)0, lc.stream, qkv, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)nullptr, parts, counters, ctx, kstat, n, QKV, HD, ctx_cpc(nsplit, B)); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
   { cudaError_t le_ = launch_pdl(linattn_out_kernel, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, ctx, out, n, out_hi, out_lo); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
@@ -654,7 +759,7 @@ int launch_linattn_ctx(const LaunchCtx& lc, const float* qkv, float* ctx, float*
   if (B * kHeads > kCtrCap) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "linear attention: batch too large");
   unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
   float* parts = ws + kCtrCap + (int64_t)B * kHeads * (D * D);
-  { cudaError_t le_ = launch_pdl(linattn_ctx_kernel<false>, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)nullptr, parts, counters, ctx, kstat, n, kv_only ? 2 * HD : QKV, kv_only ? 0 : HD); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
+  { cudaError_t le_ = launch_pdl(linattn_ctx_kernel<false>, dim3(B * kHeads, cdiv(nsplit, ctx_cpc(nsplit, B))), dim3(256), (size_t)0, lc.stream, qkv, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)nullptr, parts, counters, ctx, kstat, n, kv_only ? 2 * HD : QKV, kv_only ? 0 : HD, ctx_cpc(nsplit, B)); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
   return IGM_OK;
 }
@@ -704,8 +809,8 @@ int launch_linattn_ctx_hl(const LaunchCtx& lc, const __nv_bfloat16* q_hi, const 
   ProfScope ps_(lc, K_ATTN, 2.0 * B * kHeads * (double)n * D * D, 2.0 * B * (double)n * 2 * HD * 2);
   unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
   float* parts = ws + kCtrCap + (int64_t)B * kHeads * (D * D);
-  IGM_LAUNCH_PDL(linattn_ctx_kernel<true>, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, (const float*)nullptr, q_hi, q_lo,
-                 parts, counters, ctx, kstat, n, QKV, HD);
+  IGM_LAUNCH_PDL(linattn_ctx_kernel<true>, dim3(B * kHeads, cdiv(nsplit, ctx_cpc(nsplit, B))), dim3(256), (size_t)0, lc.stream, (const float*)nullptr, q_hi, q_lo,
+                 parts, counters, ctx, kstat, n, QKV, HD, ctx_cpc(nsplit, B));
   return IGM_OK;
 }
 
