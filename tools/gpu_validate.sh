@@ -2,7 +2,7 @@
 # suite + short benches (both DDPM configs), two runs each
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-T=${TAG:-r2c14}
+T=${TAG:-r2v}
 run() { name=$1; t=$2; shift 2; echo "== $name"; timeout $t "$@" > gpurun_out/${T}_$name.log 2>&1; rc=$?; echo "$name rc=$rc"; tail -${TAILN:-4} gpurun_out/${T}_$name.log | cut -c1-400; return $rc; }
 TAILN=12 run pytest_gpu 1500 python -m pytest tests -m gpu -q -x
 short="--steps 30 --warmup 8 --no-cpu --no-eager --no-secondary --sample-steps 100 --sustain-s 0"
