@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(256) linattn_bwd_dctx_kernel(const float* __re
                                                                const __nv_bfloat16* __restrict__ d_lo,
                                                                float* __restrict__ part_ws,
                                                                unsigned int* __restrict__ counters,
-                                                               float* __restrict__ dctx_full, int N) {
+                                                               float* __restrict__ dctx_full, int N, int cpc) {
   __shared__ __align__(16) float buf[2 * CH * D];   // q | dO tiles, later the reduction scratch
   float (*Xs)[D] = reinterpret_cast<float (*)[D]>(buf);
   float (*Ys)[D] = reinterpret_cast<float (*)[D]>(buf + CH * D);
@@ -429,16 +429,9 @@ __global__ void __launch_bounds__(256) linattn_bwd_dctx_kernel(const float* __re
   pdl_wait();
   const int bh = blockIdx.x, b = bh / kHeads, h = bh % kHeads;
   const int nsplit = gridDim.y;
-  const int n0 = blockIdx.y * CH, rows = min(CH, N - n0);
+  const int nchunks = (N + CH - 1) / CH;
+  const int c_begin = blockIdx.y * cpc, c_end = min(nchunks, c_begin + cpc);
   const int tid = threadIdx.x;
-  if (HL) {
-    const int64_t qo = ((int64_t)b * N + n0) * QKV + h * D, dof = ((int64_t)b * N + n0) * HD + h * D;
-    load_tile_hl(Xs, q_hi + qo, q_lo + qo, QKV, rows, tid);
-    load_tile_hl(Ys, d_hi + dof, d_lo + dof, HD, rows, tid);
-  } else {
-    load_tile2(Xs, qkv + ((int64_t)b * N + n0) * QKV + h * D, QKV, Ys, d_out + ((int64_t)b * N + n0) * HD + h * D, HD, rows, tid);
-  }
-  __syncthreads();
   const int grp = tid >> 6, t64 = tid & 63;
   const int d0 = (t64 >> 3) * 4, e0 = (t64 & 7) * 4;
   float acc[4][4], xsum[4];
@@ -448,8 +441,20 @@ __global__ void __launch_bounds__(256) linattn_bwd_dctx_kernel(const float* __re
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   }
-  outer4x4(Xs, Ys, rows, grp, d0, e0, acc, xsum);
-  __syncthreads();   // `part` aliases the tiles
+  // a CTA walks `cpc` consecutive chunks and keeps accumulating its 4x4 register tiles (see linattn_ctx_kernel)
+  for (int c = c_begin; c < c_end; ++c) {
+    const int n0 = c * CH, rows = min(CH, N - n0);
+    if (HL) {
+      const int64_t qo = ((int64_t)b * N + n0) * QKV + h * D, dof = ((int64_t)b * N + n0) * HD + h * D;
+      load_tile_hl(Xs, q_hi + qo, q_lo + qo, QKV, rows, tid);
+      load_tile_hl(Ys, d_hi + dof, d_lo + dof, HD, rows, tid);
+    } else {
+      load_tile2(Xs, qkv + ((int64_t)b * N + n0) * QKV + h * D, QKV, Ys, d_out + ((int64_t)b * N + n0) * HD + h * D, HD, rows, tid);
+    }
+    __syncthreads();
+    outer4x4(Xs, Ys, rows, grp, d0, e0, acc, xsum);
+    __syncthreads();   // the tiles are overwritten by the next chunk / aliased by `part`
+  }
   reduce_groups(acc, xsum, grp, t64, d0, e0, part, full, nullptr);
   float* fdst = dctx_full + (int64_t)bh * D * D;
   if (nsplit == 1) {
@@ -790,7 +795,7 @@ int launch_linattn_backward(const LaunchCtx& lc, const float* qkv, const float* 
   unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
   float* dctx = ws + kCtrCap;
   float* parts = ws + kCtrCap + (int64_t)B * kHeads * (D * D);
-  { cudaError_t le_ = launch_pdl(linattn_bwd_dctx_kernel<false>, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, d_out, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)nullptr, parts, counters, dctx, n); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
+  { cudaError_t le_ = launch_pdl(linattn_bwd_dctx_kernel<false>, dim3(B * kHeads, cdiv(nsplit, ctx_cpc(nsplit, B))), dim3(256), (size_t)0, lc.stream, qkv, d_out, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)nullptr, parts, counters, dctx, n, ctx_cpc(nsplit, B)); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
   { cudaError_t le_ = launch_pdl(linattn_bwd_rows_kernel, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, qkv, ctx, kstat, d_out, dctx, d_qkv, n, d_hi, d_lo); if (le_ != cudaSuccess) IGM_FAIL(*lc.st, IGM_ERR_CUDA, cudaGetErrorString(le_)); }
   IGM_POST_LAUNCH(lc);
@@ -825,8 +830,8 @@ int launch_linattn_dctx_hl(const LaunchCtx& lc, const __nv_bfloat16* q_hi, const
   unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
   float* dctx = ws + kCtrCap;
   float* parts = ws + kCtrCap + (int64_t)B * kHeads * (D * D);
-  IGM_LAUNCH_PDL(linattn_bwd_dctx_kernel<true>, dim3(B * kHeads, nsplit), dim3(256), (size_t)0, lc.stream, (const float*)nullptr,
-                 (const float*)nullptr, q_hi, q_lo, d_hi, d_lo, parts, counters, dctx, n);
+  IGM_LAUNCH_PDL(linattn_bwd_dctx_kernel<true>, dim3(B * kHeads, cdiv(nsplit, ctx_cpc(nsplit, B))), dim3(256), (size_t)0, lc.stream, (const float*)nullptr,
+                 (const float*)nullptr, q_hi, q_lo, d_hi, d_lo, parts, counters, dctx, n, ctx_cpc(nsplit, B));
   return IGM_OK;
 }
 
