@@ -319,25 +319,53 @@ def run_vqvae(args, dev, rank, world):
             loss.item()
         return loss
 
+    from igm_b200 import _lib
+    lib = _lib.load()
+    counted = {}
+
     def timed(steps, warmup, e2e):
         for i in range(warmup):
             step(i, e2e)
         barrier()
+        n0 = int(lib.igm_ops_launch_count())
         e0, e1 = _events()
         e0.record()
         for i in range(steps):
             step(i, e2e)
         e1.record()
         barrier()
+        counted["launches"] = int(lib.igm_ops_launch_count()) - n0   # this rank's kernels inside the timed region
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    ms = timed(args.steps, args.warmup, False)
+    from bench import ClockSampler, peaks
+    clk = ClockSampler(dev.index or 0)
+    with clk:
+        ms = timed(args.steps, args.warmup, False)
+    launches = counted["launches"]
     ms_e = timed(args.steps, 3, True)
     unit = f"steps/s ({B} images per GPU-step)"
+    P = peaks()
+    tf = 3 * B * VQVAE_FWD_GFLOP / (ms / args.steps)          # fwd + data-gradient + weight-gradient passes, TFLOP/s
+    extra = {}
+    if world == 1 and not getattr(args, "no_cpu", False):      # bounded CPU sample: 2 steps of the oracle on the host cores
+        torch.set_num_threads(os.cpu_count() or 1)
+        cst = _vqvae_torch_step("cpu", B, S)
+        cst()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            cst().item()
+        dt = (time.perf_counter() - t0) / 2
+        extra["cpu_baseline"] = {"value": 1.0 / dt, "unit": unit, "cores": torch.get_num_threads(), "kind": "port",
+                                 "sample": f"2 train steps (+1 warm-up) at B={B}, oracle/vqvae_oracle.py (torch CPU fp32)"}
     return {
+        **extra,
+        "clocks": clk.summary(),
+        "roofline": {"bound": "tensor", "kernel": "whole step (tcgen05 bf16x3 convs via igm_conv2d_*; 3- and 32-channel layers on CUDA cores)",
+                     "achieved": tf, "peak": P["tf_burst"], "unit": "TFLOP/s", "frac": tf / P["tf_burst"], "traffic": None,
+                     "peak_source": f"{P['src']} bf16 dense burst; algorithmic 3 x {VQVAE_FWD_GFLOP} GFLOP per sample and step"},
         "metric": VQ_METRIC, "value": world * args.steps / (ms / 1e3), "unit": unit, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -345,7 +373,7 @@ def run_vqvae(args, dev, rank, world):
                    "l2": "activations of one step (~2 GB) >> L2; 8 rotating input batches"},
         "e2e": {"value": world * args.steps / (ms_e / 1e3), "unit": unit, "h2d_bytes_per_step": B * 3 * S * S * 4,
                 "d2h_bytes_per_step": 4, "api": "H2D of the pinned batch + VQVAE.training_step + backward + on_after_backward + Adam + loss.item()"},
-        "gpu_launches": None,
+        "gpu_launches": launches * world,
     }
 
 

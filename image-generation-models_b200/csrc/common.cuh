@@ -22,6 +22,7 @@ struct Status {
 
 void set_error(Status& st, int code, const char* file, int line, const char* what);
 Status& global_status();   // errors raised without a context (igm_unet_create, igm_debug_*)
+int64_t& ops_launch_counter();   // kernels launched by the context-free entry points (igm_conv2d_*, igm_vq_*, igm_pixelcnn_run, ...)
 
 #define IGM_CUDA(st, expr)                                                      \
   do {                                                                          \

@@ -467,6 +467,7 @@ extern "C" int igm_pixelcnn_run(const float* weights, float* img, const float* u
   cudaError_t e = cudaFuncSetAttribute(pixelcnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) IGM_FAIL(st, IGM_ERR_CUDA, cudaGetErrorString(e));
   pixelcnn_kernel<<<N, 256, smem, (cudaStream_t)stream>>>(a);
+  ++ops_launch_counter();
   e = cudaPeekAtLastError();
   if (e != cudaSuccess) { cudaGetLastError(); IGM_FAIL(st, IGM_ERR_CUDA, cudaGetErrorString(e)); }
   return IGM_OK;

@@ -61,6 +61,11 @@ Status& global_status() {
   return s;
 }
 
+int64_t& ops_launch_counter() {
+  static int64_t n = 0;
+  return n;
+}
+
 namespace {
 
 // IGM_CONV_PAIR=1: eligible stride-1 convs (N % 128 == 0) run forward and data gradient on the cta_group::2 engine

@@ -136,11 +136,10 @@ extern "C" int igm_vq_forward(const float* z, const float* codebook, int64_t* id
   if (!z || !codebook || !idx || !quant || !losses || !ws) IGM_FAIL(st, IGM_ERR_INVALID, "null tensor");
   if (N < 1 || HW < 1 || K < 1) IGM_FAIL(st, IGM_ERR_INVALID, "bad sizes");
   if (D != 16 && D != 32 && D != 64) IGM_FAIL(st, IGM_ERR_INVALID, "latent_dim must be 16, 32 or 64");
-  int64_t launches = 0;
   LaunchCtx lc;
   lc.stream = (cudaStream_t)stream;
   lc.st = &st;
-  lc.counter = &launches;
+  lc.counter = &ops_launch_counter();
   const int64_t nvec = (int64_t)N * HW;
   const int parts = (int)cdiv64(nvec, 256);
   int k_tile = K;
@@ -172,11 +171,10 @@ extern "C" int igm_vq_backward(const float* z, const float* codebook, const int6
   st = Status();
   (void)K;
   if (!z || !codebook || !idx) IGM_FAIL(st, IGM_ERR_INVALID, "null tensor");
-  int64_t launches = 0;
   LaunchCtx lc;
   lc.stream = (cudaStream_t)stream;
   lc.st = &st;
-  lc.counter = &launches;
+  lc.counter = &ops_launch_counter();
   const int64_t total = (int64_t)N * D * HW;
   vq_backward_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, lc.stream>>>(z, codebook, idx, d_quant, d_vq, d_commit, beta,
                                                                          dz, d_codebook, N, D, HW);

@@ -237,6 +237,9 @@ int igm_profile_start(igm_ctx* ctx);
 int igm_profile_stop(igm_ctx* ctx, igm_profile_entry* out, int cap);
 /* Number of kernels the library launched on behalf of this context so far. */
 int64_t igm_launch_count(const igm_ctx* ctx);
+/* Number of kernels launched so far by the context-free entry points (igm_conv2d_*, igm_act_*, igm_ce256, igm_ewise,
+ * igm_mse, igm_vq_*, igm_pixelcnn_run) of this process. */
+int64_t igm_ops_launch_count(void);
 /* One stride-1 KxK (K = 1 or 3, pad (K-1)/2) convolution on NHWC fp32 tensors, for kernel-level
  * parity tests: mode 0 = forward  x[B,H,W,Cin] -> out[B,H,W,Cout] (+bias, +add);
  *               mode 1 = data gradient  x = d_out[B,H,W,Cout] -> out = d_in[B,H,W,Cin].
