@@ -698,6 +698,313 @@ static int launch_thin(const LaunchCtx& lc, int TC, const float* wide, const flo
   }
 }
 
+// ---- thin 4x4 stride-2 layers (first Conv2d / last ConvTranspose2d of the VQ-VAE: 3 image channels on one side) ----------
+// The generic 64 x 64-tile kernels above spend > 90 % of a tile on padding when one side has 3 channels (ncu, round 2: 159 us
+// for Conv2d(3, 32, 4, 2, 1) on 32 x 128 x 128 images, 715 us for ConvTranspose2d(32, 3, 4, 2, 1), 557 us for each of their
+// weight gradients -- 40 % of the VQ-VAE step for 0.3 % of its FLOPs).  Same ideas as the stem kernels of the U-Net: the thin
+// operand lives zero-padded in shared memory as 4-float pixels, a lane owns wide channels, thin values are broadcasts.
+
+// Conv2d(CI <= 4 -> N, 4, 2, 1), also the data gradient of ConvTranspose2d(N -> CI, 4, 2, 1).  Wp packed [16][CI][N].
+// grid (B * ceil(OH / R), N / (32 * CPL)); a lane owns CPL output channels and keeps their 16 * CI weights in registers.
+template <int CI, int CPL>
+__global__ void __launch_bounds__(256) conv_thin_in_s2_kernel(const float* __restrict__ X, const float* __restrict__ Wp,
+                                                              const float* __restrict__ bias, float* __restrict__ out,
+                                                              int H, int W, int OH, int OW, int Cout, int R) {
+  constexpr int KS = 4, T = 16;
+  extern __shared__ __align__(16) float sx[];   // [(R - 1) * 2 + 4][2 OW + 2] pixels of four floats
+  const int bands = (OH + R - 1) / R;
+  const int b = blockIdx.x / bands, y0 = (blockIdx.x - b * bands) * R;
+  const int rows = min(R, OH - y0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int co = (blockIdx.y * 32 + lane) * CPL;
+  float w[T * CI][CPL];
+#pragma unroll
+  for (int k = 0; k < T * CI; ++k)
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) w[k][j] = __ldg(Wp + (int64_t)k * Cout + co + j);
+  float bv[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) bv[j] = bias ? __ldg(bias + co + j) : 0.f;
+  const int PWp = 2 * OW + 2;
+  const int nrow = (rows - 1) * 2 + KS;
+  for (int i = threadIdx.x; i < nrow * PWp; i += 256) {
+    const int rr = i / PWp, px = i - rr * PWp;
+    const int iy = 2 * y0 - 1 + rr, ix = px - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      const float* xp = X + (((int64_t)b * H + iy) * W + ix) * CI;
+      float* ve = reinterpret_cast<float*>(&v);
+#pragma unroll
+      for (int ci = 0; ci < CI; ++ci) ve[ci] = __ldg(xp + ci);
+    }
+    *reinterpret_cast<float4*>(sx + (size_t)i * 4) = v;
+  }
+  __syncthreads();
+  const int npx = rows * OW;
+  for (int p = warp; p < npx; p += 16) {   // two pixels per iteration: independent FMA chains
+    const int pb = (p + 8 < npx) ? p + 8 : p;
+    const int ya = p / OW, xa = p - ya * OW;
+    const int yb = pb / OW, xb = pb - yb * OW;
+    const float* sa = sx + ((size_t)(2 * ya) * PWp + 2 * xa) * 4;
+    const float* sb = sx + ((size_t)(2 * yb) * PWp + 2 * xb) * 4;
+    float acca[CPL], accb[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) { acca[j] = bv[j]; accb[j] = bv[j]; }
+#pragma unroll
+    for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < KS; ++kx) {
+        const float4 va4 = *reinterpret_cast<const float4*>(sa + ((size_t)ky * PWp + kx) * 4);
+        const float4 vb4 = *reinterpret_cast<const float4*>(sb + ((size_t)ky * PWp + kx) * 4);
+        const float va[4] = {va4.x, va4.y, va4.z, va4.w}, vb[4] = {vb4.x, vb4.y, vb4.z, vb4.w};
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci)
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) {
+            acca[j] = fmaf(va[ci], w[(ky * KS + kx) * CI + ci][j], acca[j]);
+            accb[j] = fmaf(vb[ci], w[(ky * KS + kx) * CI + ci][j], accb[j]);
+          }
+      }
+    float* oa = out + (((int64_t)b * OH + y0 + ya) * OW + xa) * Cout + co;
+    float* ob = out + (((int64_t)b * OH + y0 + yb) * OW + xb) * Cout + co;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) oa[j] = acca[j];
+    if (pb != p) {
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) ob[j] = accb[j];
+    }
+  }
+}
+
+// ConvTranspose2d(Cin -> CO <= 4, 4, 2, 1) forward.  Wp packed [16][Cin][CO] (staged in shared memory, read as broadcasts).
+// A thread produces the 2 x 2 output block (2j + a, 2i + b) from the 3 x 3 input pixels around (j, i): every tap is used
+// exactly once per block (oy = 2 iy - 1 + ky), 16 * Cin * CO FMAs per thread.  grid: ceil(B * IH * IW / 256).
+template <int CO>
+__global__ void __launch_bounds__(256) convT_thin_out_s2_kernel(const float* __restrict__ X, const float* __restrict__ Wp,
+                                                                const float* __restrict__ bias, float* __restrict__ out,
+                                                                int B, int IH, int IW, int Cin) {
+  extern __shared__ __align__(16) float swt[];   // [16][Cin][CO]
+  for (int i = threadIdx.x; i < 16 * Cin * CO; i += 256) swt[i] = __ldg(Wp + i);
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= (int64_t)B * IH * IW) return;
+  const int i = (int)(t % IW);
+  const int j = (int)((t / IW) % IH);
+  const int b = (int)(t / ((int64_t)IW * IH));
+  float acc[2][2][CO];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int o = 0; o < CO; ++o) acc[a][c][o] = bias ? __ldg(bias + o) : 0.f;
+  // output row parity a uses (ky, window row): a = 0 -> (1, 1), (3, 0);  a = 1 -> (0, 2), (2, 1)   (window row r <-> iy = j - 1 + r)
+  constexpr int kk[2][2] = {{1, 3}, {0, 2}};
+  constexpr int rr[2][2] = {{1, 0}, {2, 1}};
+  for (int c4 = 0; c4 < Cin; c4 += 4) {
+    float4 xin[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int iy = j - 1 + r, ix = i - 1 + c;
+        xin[r][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (iy >= 0 && iy < IH && ix >= 0 && ix < IW)
+          xin[r][c] = __ldg(reinterpret_cast<const float4*>(X + (((int64_t)b * IH + iy) * IW + ix) * Cin + c4));
+      }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int ty = 0; ty < 2; ++ty)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int tx = 0; tx < 2; ++tx) {
+            const int tap = kk[a][ty] * 4 + kk[c][tx];
+            const float4 xv4 = xin[rr[a][ty]][rr[c][tx]];
+            const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
+            const float* wp = swt + ((size_t)tap * Cin + c4) * CO;   // 4 * CO consecutive floats, 16-byte aligned
+            float wv[4 * CO];
+#pragma unroll
+            for (int q = 0; q < CO; ++q) *reinterpret_cast<float4*>(&wv[4 * q]) = *reinterpret_cast<const float4*>(wp + 4 * q);
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+              for (int o = 0; o < CO; ++o) acc[a][c][o] = fmaf(xv[ci], wv[ci * CO + o], acc[a][c][o]);
+          }
+  }
+  const int OH = 2 * IH, OW = 2 * IW;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float* o = out + (((int64_t)b * OH + 2 * j + a) * OW + 2 * i + c) * CO;
+#pragma unroll
+      for (int q = 0; q < CO; ++q) o[q] = acc[a][c][q];
+    }
+}
+
+// Weight gradient of both thin 4x4 stride-2 layers:
+//   grad[w * s_wide + t * s_thin + tap] += sum_{b, y, x} Wide[b, y, x][w] * Thin[b, 2y - 1 + ky, 2x - 1 + kx][t]
+// (Conv2d: Wide = dY, Thin = X; ConvTranspose2d: Wide = X, Thin = dY).  wgrad_thin_kernel with a stride-2 window: a CTA owns RB
+// coarse rows of one image and CW wide channels, 256 / CW pixel lanes walk contiguous runs of coarse pixels, the window of
+// 4 x 4 thin pixels slides by two columns per step (two new columns = 8 broadcast 128-bit loads per 16 * TC FMAs).
+template <int TC, int CW>
+__global__ void __launch_bounds__(256) wgrad_thin_s2_kernel(const float* __restrict__ Wide, const float* __restrict__ Thin,
+                                                            float* __restrict__ grad, int H, int W, int WC, int RB,
+                                                            int64_t s_wide, int64_t s_thin) {
+  constexpr int KS = 4, T = 16, NA = T * TC, LG = 256 / CW;
+  extern __shared__ __align__(16) float smem_thin[];   // tile [(RB - 1) * 2 + 4][2 W + 2] of float4, then red[LG][CW][NA + 1]
+  const int TW = 2 * W + 2, TH = (RB - 1) * 2 + KS;
+  const int HF = 2 * H, WF = 2 * W;
+  float4* tile = reinterpret_cast<float4*>(smem_thin);
+  float (*red)[CW][NA + 1] = reinterpret_cast<float (*)[CW][NA + 1]>(smem_thin + (size_t)TH * TW * 4);
+  const int tiles_per_img = (H + RB - 1) / RB;
+  const int b = blockIdx.x / tiles_per_img, y0 = (blockIdx.x % tiles_per_img) * RB;
+  for (int i = threadIdx.x; i < TH * TW; i += 256) {
+    const int tx = i % TW, ty = i / TW;
+    const int y = 2 * y0 - 1 + ty, x = tx - 1;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (y >= 0 && y < HF && x >= 0 && x < WF) {
+      const float* src = Thin + (((int64_t)b * HF + y) * WF + x) * TC;
+#pragma unroll
+      for (int ci = 0; ci < TC; ++ci) v[ci] = __ldg(src + ci);
+    }
+    tile[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  __syncthreads();
+  const int cl = threadIdx.x % CW, lg = threadIdx.x / CW;
+  const int c = blockIdx.y * CW + cl;
+  float acc[NA];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) acc[i] = 0.f;
+  if (c < WC) {
+    const int npix = min(RB, H - y0) * W;
+    const int per = (npix + LG - 1) / LG;
+    const int i0 = lg * per, i1 = min(i0 + per, npix);
+    int yy = i0 / W, xx = i0 - yy * W;
+    float4 win[KS][KS];
+    bool fresh = true;
+    const float* wp = Wide + (((int64_t)b * H + y0) * W + i0) * WC + c;
+    constexpr int UB = 8;
+    for (int ib = i0; ib < i1; ib += UB, wp += (int64_t)UB * WC) {
+      float gb[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) gb[u] = (ib + u < i1) ? __ldg(wp + (int64_t)u * WC) : 0.f;
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        if (ib + u >= i1) break;
+        const float g = gb[u];
+        const float4* t0 = tile + (size_t)(2 * yy) * TW + 2 * xx;
+        if (fresh) {
+#pragma unroll
+          for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < KS; ++kx) win[ky][kx] = t0[ky * TW + kx];
+          fresh = false;
+        } else {
+#pragma unroll
+          for (int ky = 0; ky < KS; ++ky) {
+            win[ky][0] = win[ky][2];
+            win[ky][1] = win[ky][3];
+            win[ky][2] = t0[ky * TW + 2];
+            win[ky][3] = t0[ky * TW + 3];
+          }
+        }
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < KS; ++kx) {
+            const float tv[4] = {win[ky][kx].x, win[ky][kx].y, win[ky][kx].z, win[ky][kx].w};
+#pragma unroll
+            for (int ci = 0; ci < TC; ++ci) acc[(ky * KS + kx) * TC + ci] = fmaf(g, tv[ci], acc[(ky * KS + kx) * TC + ci]);
+          }
+        if (++xx == W) { xx = 0; ++yy; fresh = true; }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NA; ++i) red[lg][cl][i] = acc[i];
+  __syncthreads();
+  if (lg == 0 && c < WC) {
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+#pragma unroll
+      for (int ci = 0; ci < TC; ++ci) {
+        const int i = t * TC + ci;
+        float v = 0.f;
+#pragma unroll
+        for (int l = 0; l < LG; ++l) v += red[l][cl][i];
+        atomicAdd(grad + (int64_t)c * s_wide + (int64_t)ci * s_thin + t, v);
+      }
+  }
+}
+
+template <int TC, int CW>
+static int launch_thin_s2_impl(const LaunchCtx& lc, const float* wide, const float* thin, float* grad, int B, int H, int W, int WC,
+                               int64_t s_wide, int64_t s_thin) {
+  constexpr int NA = 16 * TC, LG = 256 / CW;
+  const int red_f = LG * CW * (NA + 1);
+  int RB = (int)cdiv64((int64_t)B * H, 296);   // ~2 CTAs per SM and channel slab
+  if (RB < 1) RB = 1;
+  if (RB > H) RB = H;
+  auto tile_f = [&](int rb) { return ((rb - 1) * 2 + 4) * (2 * W + 2) * 4; };
+  while (RB > 1 && (size_t)(tile_f(RB) + red_f) * sizeof(float) > 96 * 1024) --RB;
+  const size_t smem = (size_t)(tile_f(RB) + red_f) * sizeof(float);
+  if (smem > 96 * 1024) IGM_FAIL(*lc.st, IGM_ERR_INVALID, "thin stride-2 wgrad: image row too wide");
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(wgrad_thin_s2_kernel<TC, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr = true;
+  }
+  dim3 grid((unsigned)(B * cdiv(H, RB)), (unsigned)cdiv(WC, CW));
+  wgrad_thin_s2_kernel<TC, CW><<<grid, 256, smem, lc.stream>>>(wide, thin, grad, H, W, WC, RB, s_wide, s_thin);
+  IGM_POST_LAUNCH(lc);
+  return IGM_OK;
+}
+
+static int launch_thin_s2(const LaunchCtx& lc, int TC, const float* wide, const float* thin, float* grad, int B, int H, int W,
+                          int WC, int64_t s_wide, int64_t s_thin) {
+  const bool narrow = WC <= 32;
+  switch (TC) {
+    case 1: return narrow ? launch_thin_s2_impl<1, 32>(lc, wide, thin, grad, B, H, W, WC, s_wide, s_thin)
+                          : launch_thin_s2_impl<1, 64>(lc, wide, thin, grad, B, H, W, WC, s_wide, s_thin);
+    case 2: return narrow ? launch_thin_s2_impl<2, 32>(lc, wide, thin, grad, B, H, W, WC, s_wide, s_thin)
+                          : launch_thin_s2_impl<2, 64>(lc, wide, thin, grad, B, H, W, WC, s_wide, s_thin);
+    case 3: return narrow ? launch_thin_s2_impl<3, 32>(lc, wide, thin, grad, B, H, W, WC, s_wide, s_thin)
+                          : launch_thin_s2_impl<3, 64>(lc, wide, thin, grad, B, H, W, WC, s_wide, s_thin);
+    default: return narrow ? launch_thin_s2_impl<4, 32>(lc, wide, thin, grad, B, H, W, WC, s_wide, s_thin)
+                           : launch_thin_s2_impl<4, 64>(lc, wide, thin, grad, B, H, W, WC, s_wide, s_thin);
+  }
+}
+
+template <int CI>
+static int launch_thin_in_s2(const LaunchCtx& lc, const ConvArgs& a) {
+  const int cpl = (a.N % 64 == 0) ? 2 : 1;
+  int R = ((int64_t)a.B * cdiv(a.OH, 8) * (a.N / (32 * cpl)) >= 296) ? 8 : 4;
+  if (a.OH < R) R = a.OH;
+  const size_t smem = (size_t)((R - 1) * 2 + 4) * (2 * a.OW + 2) * 4 * sizeof(float);
+  if (smem > 96 * 1024) return -1;
+  dim3 grid((unsigned)(a.B * cdiv(a.OH, R)), (unsigned)(a.N / (32 * cpl)));
+  if (cpl == 2) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(conv_thin_in_s2_kernel<CI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+    conv_thin_in_s2_kernel<CI, 2><<<grid, 256, smem, lc.stream>>>(a.in0, a.w, a.bias, a.out0, a.IH, a.IW, a.OH, a.OW, a.N, R);
+  } else {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(conv_thin_in_s2_kernel<CI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+    conv_thin_in_s2_kernel<CI, 1><<<grid, 256, smem, lc.stream>>>(a.in0, a.w, a.bias, a.out0, a.IH, a.IW, a.OH, a.OW, a.N, R);
+  }
+  return 0;
+}
+
+template <int CO>
+static void launch_thin_out_s2(const LaunchCtx& lc, const ConvArgs& a) {
+  const size_t smem = (size_t)16 * a.C0 * CO * sizeof(float);
+  const int64_t nthr = (int64_t)a.B * a.IH * a.IW;
+  convT_thin_out_s2_kernel<CO><<<(unsigned)cdiv64(nthr, 256), 256, smem, lc.stream>>>(a.in0, a.w, a.bias, a.out0, a.B, a.IH, a.IW, a.C0);
+}
+
 // out[n] += sum_m x[m, n]; grid.x = row splits; block (32 x 8): 32 columns x 8 row lanes
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int64_t M, int N,
                                                      float* __restrict__ out, int rows_per_cta) {
@@ -757,6 +1064,37 @@ int launch_conv(const LaunchCtx& lc, const ConvArgs& a) {
     IGM_POST_LAUNCH(lc);
     return IGM_OK;
   }
+  static const bool thin_s2 = [] { const char* e = getenv("IGM_THIN_S2"); return !(e && e[0] == '0'); }();
+  const bool s2_geo = thin_s2 && !a.in1 && a.C1 == 0 && a.stride == 2 && a.dil == 1 && a.KH == 4 && a.KW == 4 && a.pad == 1 &&
+                      (a.pad_w < 0 || a.pad_w == 1) && !a.add0 && a.N0 == a.N;
+  if (s2_geo && !a.transposed && a.C0 >= 1 && a.C0 <= 4 && a.N % 32 == 0 && a.IH == 2 * a.OH && a.IW == 2 * a.OW) {
+    // Conv2d(<= 4 -> N, 4, 2, 1) (and the data gradient of the matching ConvTranspose2d)
+    ProfScope ps_(lc, a.kclass, 2.0 * a.B * a.OH * a.OW * (double)a.N * a.C0 * 16, 4.0 * a.B * ((double)a.OH * a.OW * a.N + (double)a.IH * a.IW * a.C0));
+    int rc = -1;
+    switch (a.C0) {
+      case 1: rc = launch_thin_in_s2<1>(lc, a); break;
+      case 2: rc = launch_thin_in_s2<2>(lc, a); break;
+      case 3: rc = launch_thin_in_s2<3>(lc, a); break;
+      default: rc = launch_thin_in_s2<4>(lc, a); break;
+    }
+    if (rc == 0) {
+      IGM_POST_LAUNCH(lc);
+      return IGM_OK;
+    }
+  }
+  if (s2_geo && a.transposed && a.N >= 1 && a.N <= 4 && a.C0 % 4 == 0 && 16 * a.C0 * a.N <= 12288 && a.OH == 2 * a.IH &&
+      a.OW == 2 * a.IW) {
+    // ConvTranspose2d(C -> <= 4, 4, 2, 1)
+    ProfScope ps_(lc, a.kclass, 2.0 * a.B * a.IH * a.IW * (double)a.N * a.C0 * 16, 4.0 * a.B * ((double)a.OH * a.OW * a.N + (double)a.IH * a.IW * a.C0));
+    switch (a.N) {
+      case 1: launch_thin_out_s2<1>(lc, a); break;
+      case 2: launch_thin_out_s2<2>(lc, a); break;
+      case 3: launch_thin_out_s2<3>(lc, a); break;
+      default: launch_thin_out_s2<4>(lc, a); break;
+    }
+    IGM_POST_LAUNCH(lc);
+    return IGM_OK;
+  }
   const int ps = (a.transposed && a.stride > 1) ? a.stride : 1;
   const int OHp = cdiv(a.OH, ps), OWp = cdiv(a.OW, ps);
   const int64_t Mp = (int64_t)a.B * OHp * OWp;
@@ -787,6 +1125,14 @@ int launch_wgrad(const LaunchCtx& lc, const WgradArgs& a) {
     // few output channels (P = d_pred), wide input (Q): the final 1x1 conv
     ProfScope ps_(lc, K_CONV_WGRAD, 2.0 * npix * (double)a.PC * a.QC, 4.0 * npix * (a.PC + a.QC));
     return launch_thin<1>(lc, a.PC, a.Q, a.P, a.grad, a.B, a.PH, a.PW, a.QC, a.sq, a.sp);
+  }
+  static const bool thin_s2 = [] { const char* e = getenv("IGM_THIN_S2"); return !(e && e[0] == '0'); }();
+  if (thin_s2 && a.stride == 2 && a.dil == 1 && (a.pad_w < 0 || a.pad_w == 1) && a.KH == 4 && a.KW == 4 && a.pad == 1 && a.QC >= 1 &&
+      a.QC <= 4 &&
+      a.PC >= 32 && a.QH == 2 * a.PH && a.QW == 2 * a.PW) {
+    // thin operand gathered on the fine grid (Q), wide operand enumerated on the coarse grid (P): 4x4 stride-2 layers
+    ProfScope ps_(lc, K_CONV_WGRAD, 2.0 * npix * (double)a.PC * a.QC * 16, 4.0 * npix * (a.PC + 4.0 * a.QC));
+    return launch_thin_s2(lc, a.QC, a.P, a.Q, a.grad, a.B, a.PH, a.PW, a.PC, a.sp, a.sq);
   }
   const int q_tiles = cdiv(a.QC, WB), p_tiles = cdiv(a.PC, WB);
   const int taps = a.KH * a.KW;

@@ -57,6 +57,40 @@ def test_conv2d_forward_backward(cfg):
         assert_close(bc.grad, b.grad, "db")
 
 
+THIN_S2 = [
+    # (B, Cin, H, W, Cout, transposed): 4x4 stride-2 pad-1 layers with <= 4 channels on one side, no residual -- the first conv
+    # and the last transposed conv of the VQ-VAE (csrc/conv_simt.cu conv_thin_in_s2 / convT_thin_out_s2 / wgrad_thin_s2 kernels)
+    (2, 3, 16, 16, 32, False),     # encoder stem at hidden 32 (one output channel per lane)
+    (3, 3, 32, 24, 64, False),     # two output channels per lane, odd batch, non-square
+    (2, 1, 8, 8, 32, False),
+    (2, 32, 8, 8, 3, True),        # decoder head
+    (3, 64, 12, 16, 3, True),
+    (2, 32, 4, 4, 1, True),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", THIN_S2, ids=lambda c: "x".join(str(v) for v in c[:5]) + ("T" if c[5] else ""))
+def test_thin_stride2_layers(cfg):
+    from igm_b200 import ops
+    B, Ci, H, W, Co, tr = cfg
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, Ci, H, W, generator=g, requires_grad=True)
+    w = (torch.randn((Ci, Co, 4, 4) if tr else (Co, Ci, 4, 4), generator=g) * 0.2).requires_grad_(True)
+    b = torch.randn(Co, generator=g).requires_grad_(True)
+    ref = F.conv_transpose2d(x, w, b, 2, 1) if tr else F.conv2d(x, w, b, 2, 1)
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy)
+    xc, wc, bc = (t.detach().cuda().requires_grad_(True) for t in (x, w, b))
+    got = ops.conv_transpose2d(xc, wc, bc, 2, (1, 1)) if tr else ops.conv2d(xc, wc, bc, 2, (1, 1), 1)
+    assert got.shape == ref.shape
+    got.backward(dy.cuda())
+    assert_close(got, ref, "y")
+    assert_close(xc.grad, x.grad, "dx")
+    assert_close(wc.grad, w.grad, "dw")
+    assert_close(bc.grad, b.grad, "db")
+
+
 @pytest.mark.gpu
 def test_activations_and_losses():
     from igm_b200 import ops
