@@ -1129,7 +1129,7 @@ int launch_wgrad(const LaunchCtx& lc, const WgradArgs& a) {
   static const bool thin_s2 = [] { const char* e = getenv("IGM_THIN_S2"); return !(e && e[0] == '0'); }();
   if (thin_s2 && a.stride == 2 && a.dil == 1 && (a.pad_w < 0 || a.pad_w == 1) && a.KH == 4 && a.KW == 4 && a.pad == 1 && a.QC >= 1 &&
       a.QC <= 4 &&
-      a.PC >= 32 && a.QH == 2 * a.PH && a.QW == 2 * a.PW) {
+      a.PC >= 32 && a.QH == 2 * a.PH && a.QW == 2 * a.PW && a.PW <= 320 /* one band of thin rows must fit shared memory */) {
     // thin operand gathered on the fine grid (Q), wide operand enumerated on the coarse grid (P): 4x4 stride-2 layers
     ProfScope ps_(lc, K_CONV_WGRAD, 2.0 * npix * (double)a.PC * a.QC * 16, 4.0 * npix * (a.PC + 4.0 * a.QC));
     return launch_thin_s2(lc, a.QC, a.P, a.Q, a.grad, a.B, a.PH, a.PW, a.PC, a.sp, a.sq);
