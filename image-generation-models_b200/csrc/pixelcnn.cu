@@ -112,7 +112,7 @@ __device__ __forceinline__ void cta_gemv(const float* __restrict__ Wt, const flo
   *reinterpret_cast<float4*>(red_s + part * N + q * 4) = acc;
   __syncthreads();
   if (tid < N) {
-    float s = bias ? __ldg(bias + tid) : 0.f;
+    float s = bias ? bias[tid] : 0.f;   // generic load: the per-pixel chain passes shared-memory copies
     if (extra) s += extra[tid];
     for (int p = 0; p < parts; ++p) s += red_s[p * N + tid];
     y_s[tid] = s;
@@ -153,7 +153,7 @@ __device__ __forceinline__ void gemv_finish(const float4 (&w)[NW], const float* 
   *reinterpret_cast<float4*>(red_s + part * N + q * 4) = acc;
   __syncthreads();
   if (tid < N) {
-    float s = bias ? __ldg(bias + tid) : 0.f;
+    float s = bias ? bias[tid] : 0.f;
     if (extra) s += extra[tid];
     for (int p = 0; p < parts; ++p) s += red_s[p * N + tid];
     y_s[tid] = s;
@@ -232,6 +232,13 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
   float* red_s = y_s + 256;                 // [1024]       K-slice partials of a gemv
   float* cur_s = red_s + 1024;              // [Hd]         running h-stack column
   float* lg_s = cur_s + Hd;                 // [256]        logits of one channel
+  // Small operands of the per-pixel chain, staged so that no global load sits on its critical path (each one was an
+  // exposed L2 round trip between two barriers: ~3 per layer, 33 per pixel): constants once per kernel, the rest per pixel
+  float* hb_s = lg_s + 256;                 // [11][2Hd]    horiz_conv biases
+  float* h2b_s = hb_s + NLAYERS * N2;       // [11][Hd]     conv1x1_2 biases
+  float* cond_s = h2b_s + NLAYERS * Hd;     // [11][2Hd]    class-conditioning addends of the horizontal gates (zeros without)
+  float* v2h_s = cond_s + NLAYERS * N2;     // [11][2Hd]    conv1x1_1(vert_conv) at (h, w) of every layer
+  float* hsp_s = v2h_s + NLAYERS * N2;      // [11][Hd]     horizontal features at (h, w - dilation) of every layer
   __shared__ int s_pick;
 
   float* ws = a.ws + (int64_t)n_img * a.ws_per_img;
@@ -240,6 +247,17 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
   float* Hs = V2H + (int64_t)NLAYERS * W * N2;           // [12][W][Hd]      horizontal-stack features of row h
   float* img = a.img + (int64_t)n_img * C * H * W;
   const float* Wt = a.Wt;
+
+  for (int i = tid; i < NLAYERS * N2; i += 256) {
+    const int l = i / N2, j = i - l * N2;
+    hb_s[i] = __ldg(Wt + a.off.horiz_b[l] + j);
+    cond_s[i] = a.cond ? __ldg(a.cond + ((int64_t)(l * 2 + 1) * a.N + blockIdx.x) * N2 + j) : 0.f;
+  }
+  for (int i = tid; i < NLAYERS * Hd; i += 256) {
+    const int l = i / Hd;
+    h2b_s[i] = __ldg(Wt + a.off.h2_b[l] + (i - l * Hd));
+  }
+  __syncthreads();
 
   for (int h = 0; h < H; ++h) {
     // ================= row pass: vertical stack =================
@@ -315,6 +333,19 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
         cur_s[tid] = s;
         Hs[((int64_t)0 * W + w) * Hd + tid] = s;
       }
+      // this pixel's v->h link rows and the features one dilation to the left, for all layers at once (plain loads: both were
+      // written by this CTA, V2H in the row pass, Hs at earlier pixels of this row -- dilations are >= 1)
+      for (int i = tid; i < NLAYERS * N2 / 4; i += 256) {
+        const int l = i / (N2 / 4), j4 = i - l * (N2 / 4);
+        reinterpret_cast<float4*>(v2h_s)[i] = reinterpret_cast<const float4*>(V2H + ((int64_t)l * W + w) * N2)[j4];
+      }
+      for (int i = tid; i < NLAYERS * Hd / 4; i += 256) {
+        const int l = i / (Hd / 4), j4 = i - l * (Hd / 4);
+        const int col = w - c_dil[l];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col >= 0) v = reinterpret_cast<const float4*>(Hs + ((int64_t)l * W + col) * Hd)[j4];
+        reinterpret_cast<float4*>(hsp_s)[i] = v;
+      }
       __syncthreads();
       // weights of the chain one matrix ahead (registers): possible while a slice is <= 16 / <= 4 float4 (hidden_dim <= 64)
       const bool pipe = (N2 * N2 / 1024 <= 16) && (Hd * Hd / 1024 <= 4);
@@ -325,22 +356,21 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
         // horiz_conv 1x3 dilated, cols kx = 0 (w-d), 1 (w)                        (pixelcnn.py:48-50)
         if (tid < Hd) {
           x_s[Hd + tid] = cur_s[tid];
-          x_s[tid] = (w - d >= 0) ? Hs[((int64_t)l * W + (w - d)) * Hd + tid] : 0.f;
+          x_s[tid] = hsp_s[l * Hd + tid];
         }
         __syncthreads();
         if (pipe) {
           gemv_prefetch<4>(Wt + a.off.h2_w[l], Hd, Hd, wB);
-          gemv_finish<16>(wA, Wt + a.off.horiz_b[l], V2H + ((int64_t)l * W + w) * N2, x_s, N2, N2, red_s, y_s);
+          gemv_finish<16>(wA, hb_s + l * N2, v2h_s + l * N2, x_s, N2, N2, red_s, y_s);
         } else {
-          cta_gemv(Wt + a.off.horiz_w[l], Wt + a.off.horiz_b[l], V2H + ((int64_t)l * W + w) * N2, x_s, N2, N2, red_s, y_s);
+          cta_gemv(Wt + a.off.horiz_w[l], hb_s + l * N2, v2h_s + l * N2, x_s, N2, N2, red_s, y_s);
         }
         // gated horizontal output: tanh(a) * tanh(b)  (sic)                      (pixelcnn.py:77)
         if (tid < Hd) {
           float ah = y_s[tid], bh = y_s[Hd + tid];
           if (a.cond) {
-            const float* cp = a.cond + ((int64_t)(l * 2 + 1) * a.N + blockIdx.x) * N2;
-            ah = __fadd_rn(ah, __ldg(cp + tid));
-            bh = __fadd_rn(bh, __ldg(cp + Hd + tid));
+            ah = __fadd_rn(ah, cond_s[l * N2 + tid]);
+            bh = __fadd_rn(bh, cond_s[l * N2 + Hd + tid]);
           }
           x_s[tid] = tanhf(ah) * tanhf(bh);
         }
@@ -348,9 +378,9 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
         // conv1x1_2 + residual                                                    (pixelcnn.py:80)
         if (pipe) {
           if (l + 1 < NLAYERS) gemv_prefetch<16>(Wt + a.off.horiz_w[l + 1], N2, N2, wA);
-          gemv_finish<4>(wB, Wt + a.off.h2_b[l], cur_s, x_s, Hd, Hd, red_s, y_s);
+          gemv_finish<4>(wB, h2b_s + l * Hd, cur_s, x_s, Hd, Hd, red_s, y_s);
         } else {
-          cta_gemv(Wt + a.off.h2_w[l], Wt + a.off.h2_b[l], cur_s, x_s, Hd, Hd, red_s, y_s);
+          cta_gemv(Wt + a.off.h2_w[l], h2b_s + l * Hd, cur_s, x_s, Hd, Hd, red_s, y_s);
         }
         if (tid < Hd) {
           cur_s[tid] = y_s[tid];
@@ -463,7 +493,8 @@ extern "C" int igm_pixelcnn_run(const float* weights, float* img, const float* u
   a.img = img; a.uniforms = uniforms; a.skip = skip; a.cond = cond; a.logits = logits; a.ws = ws;
   a.ws_per_img = igm_pixelcnn_workspace_floats(1, C, H, W, Hd);
   a.seed = seed; a.N = N; a.C = C; a.H = H; a.W = W; a.Hd = Hd; a.mode = mode; a.normalize = normalize;
-  const size_t smem = sizeof(float) * ((size_t)2 * W * Hd + (size_t)2 * W * 2 * Hd + 2 * Hd + 256 + 1024 + Hd + 256);
+  const size_t smem = sizeof(float) * ((size_t)2 * W * Hd + (size_t)2 * W * 2 * Hd + 2 * Hd + 256 + 1024 + Hd + 256 +
+                                       (size_t)NLAYERS * (3 * 2 * Hd + 2 * Hd));
   cudaError_t e = cudaFuncSetAttribute(pixelcnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) IGM_FAIL(st, IGM_ERR_CUDA, cudaGetErrorString(e));
   pixelcnn_kernel<<<N, 256, smem, (cudaStream_t)stream>>>(a);
