@@ -72,6 +72,7 @@ SYMBOLS = {
     "igm_profile_stop": (C.c_int, [_P, C.POINTER(ProfileEntry), C.c_int]),
     "igm_launch_count": (C.c_int64, [_P]),
     "igm_ops_launch_count": (C.c_int64, []),
+    "igm_debug_pixelcnn_prof": (C.c_int, [_P]),
     "igm_debug_wgrad": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "igm_debug_resample": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_int, _P]),

@@ -59,13 +59,19 @@ struct PcnnArgs {
   int N, C, H, W, Hd;
   int mode;                  // 0 inverse-CDF draw, 1 greedy argmax, 2 teacher forced (no draw)
   int normalize;             // pixel value k/255 (0) or 2k/255 - 1 (1)
+  int prof;                  // IGM_PCNN_PROF=1: thread 0 of every CTA adds its row-pass / pixel-chain / head cycles to g_pcnn_prof
 };
 
 // y[n] = bias[n] + extra[n] + sum_k Wt[k][n] * x[k]   for n < N (N = 64, 128 or 256 per call), all 256 threads.
 // The per-pixel chain of 22 dependent GEMVs is bound by the latency of the weight loads (the matrices stream from L2:
 // 901 KB per pixel step do not fit shared memory), so the loads are made wide and independent: a thread owns FOUR
 // adjacent outputs and one K slice (N/4 threads per slice, 256 / (N/4) slices), i.e. K * N / 1024 <= 16 128-bit loads,
-// all in flight before the first FMA.  Slice partials are summed in a fixed order (deterministic).
+// all in flight before the first FMA.  Slice partials are summed in a fixed order (deterministic).  Measured and dropped:
+// fetching the NEXT matrix of the chain ahead of time, into registers (+1 % while the chain still had global loads of small
+// operands between its barriers, see the staging arrays of the kernel) or with cp.async into thread-private shared-memory
+// slots a whole layer ahead -- once those small loads were staged, both pipelines LOST 6 % against this plain form
+// (1602 vs 1708 samples/s).  Keeping nine of the eleven conv1x1_2 matrices resident in the SM's spare shared memory changed
+// nothing either (1753 vs 1755): the weight fetches are not what the chain waits for.
 __device__ __forceinline__ void cta_gemv(const float* __restrict__ Wt, const float* __restrict__ bias,
                                          const float* __restrict__ extra, const float* x_s, int K, int N,
                                          float* red_s /*[1024]*/, float* y_s) {
@@ -113,47 +119,6 @@ __device__ __forceinline__ void cta_gemv(const float* __restrict__ Wt, const flo
   __syncthreads();
   if (tid < N) {
     float s = bias ? bias[tid] : 0.f;   // generic load: the per-pixel chain passes shared-memory copies
-    if (extra) s += extra[tid];
-    for (int p = 0; p < parts; ++p) s += red_s[p * N + tid];
-    y_s[tid] = s;
-  }
-  __syncthreads();
-}
-
-// The same GEMV in two halves, so that the weight loads of the NEXT matrix of the per-pixel chain are in flight while the
-// current one is computed (the weights do not depend on the data): gemv_prefetch issues the K * N / 1024 <= NW 128-bit loads
-// of this thread's slice, gemv_finish consumes them.  Same slicing and summation order as cta_gemv: bit-identical results.
-template <int NW>
-__device__ __forceinline__ void gemv_prefetch(const float* __restrict__ Wt, int K, int N, float4 (&w)[NW]) {
-  const int tid = threadIdx.x;
-  const int n4 = N >> 2, parts = 256 / n4;
-  const int part = tid / n4, q = tid - part * n4;
-  const int klen = K / parts;
-  const float4* wp = reinterpret_cast<const float4*>(Wt + (int64_t)(part * klen) * N) + q;
-#pragma unroll
-  for (int k = 0; k < NW; ++k)
-    if (k < klen) w[k] = __ldg(wp + (int64_t)k * n4);
-}
-template <int NW>
-__device__ __forceinline__ void gemv_finish(const float4 (&w)[NW], const float* __restrict__ bias, const float* __restrict__ extra,
-                                            const float* x_s, int K, int N, float* red_s /*[1024]*/, float* y_s) {
-  const int tid = threadIdx.x;
-  const int n4 = N >> 2, parts = 256 / n4;
-  const int part = tid / n4, q = tid - part * n4;
-  const int klen = K / parts, kb = part * klen;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int k = 0; k < NW; ++k) {
-    if (k < klen) {
-      const float x = x_s[kb + k];
-      acc.x = fmaf(w[k].x, x, acc.x); acc.y = fmaf(w[k].y, x, acc.y);
-      acc.z = fmaf(w[k].z, x, acc.z); acc.w = fmaf(w[k].w, x, acc.w);
-    }
-  }
-  *reinterpret_cast<float4*>(red_s + part * N + q * 4) = acc;
-  __syncthreads();
-  if (tid < N) {
-    float s = bias ? bias[tid] : 0.f;
     if (extra) s += extra[tid];
     for (int p = 0; p < parts; ++p) s += red_s[p * N + tid];
     y_s[tid] = s;
@@ -218,6 +183,8 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t a, uint3
   return (float)(c0 >> 8) * (1.0f / 16777216.0f);
 }
 
+__device__ unsigned long long g_pcnn_prof[4];   // row pass | per-pixel chain | head + draw | pixels   (IGM_PCNN_PROF=1)
+
 __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
   extern __shared__ __align__(16) float sm[];
   const int n_img = blockIdx.x;
@@ -260,6 +227,8 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
   __syncthreads();
 
   for (int h = 0; h < H; ++h) {
+    long long t_row = 0;
+    if (a.prof && tid == 0) t_row = clock64();
     // ================= row pass: vertical stack =================
     // layer 0: conv_vstack 5x5, rows ky = 0,1 live (image rows h-2, h-1), pad 2   (pixelcnn.py:98-100)
     for (int i = tid; i < W * Hd; i += 256) {
@@ -319,8 +288,11 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
       __syncthreads();
     }
 
+    if (a.prof && tid == 0) atomicAdd(&g_pcnn_prof[0], (unsigned long long)(clock64() - t_row));
     // ================= pixel pass: horizontal stack, one column at a time =================
     for (int w = 0; w < W; ++w) {
+      long long t_px = 0;
+      if (a.prof && tid == 0) t_px = clock64();
       // layer 0: conv_hstack 1x5, cols kx = 0,1 live (w-2, w-1), pad 2           (pixelcnn.py:101-103)
       if (tid < Hd) {
         float s = __ldg(Wt + a.off.hs0_b + tid);
@@ -348,9 +320,6 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
       }
       __syncthreads();
       // weights of the chain one matrix ahead (registers): possible while a slice is <= 16 / <= 4 float4 (hidden_dim <= 64)
-      const bool pipe = (N2 * N2 / 1024 <= 16) && (Hd * Hd / 1024 <= 4);
-      float4 wA[16], wB[4];
-      if (pipe) gemv_prefetch<16>(Wt + a.off.horiz_w[0], N2, N2, wA);
       for (int l = 0; l < NLAYERS; ++l) {
         const int d = c_dil[l];
         // horiz_conv 1x3 dilated, cols kx = 0 (w-d), 1 (w)                        (pixelcnn.py:48-50)
@@ -359,12 +328,7 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
           x_s[tid] = hsp_s[l * Hd + tid];
         }
         __syncthreads();
-        if (pipe) {
-          gemv_prefetch<4>(Wt + a.off.h2_w[l], Hd, Hd, wB);
-          gemv_finish<16>(wA, hb_s + l * N2, v2h_s + l * N2, x_s, N2, N2, red_s, y_s);
-        } else {
-          cta_gemv(Wt + a.off.horiz_w[l], hb_s + l * N2, v2h_s + l * N2, x_s, N2, N2, red_s, y_s);
-        }
+        cta_gemv(Wt + a.off.horiz_w[l], hb_s + l * N2, v2h_s + l * N2, x_s, N2, N2, red_s, y_s);
         // gated horizontal output: tanh(a) * tanh(b)  (sic)                      (pixelcnn.py:77)
         if (tid < Hd) {
           float ah = y_s[tid], bh = y_s[Hd + tid];
@@ -376,17 +340,18 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
         }
         __syncthreads();
         // conv1x1_2 + residual                                                    (pixelcnn.py:80)
-        if (pipe) {
-          if (l + 1 < NLAYERS) gemv_prefetch<16>(Wt + a.off.horiz_w[l + 1], N2, N2, wA);
-          gemv_finish<4>(wB, h2b_s + l * Hd, cur_s, x_s, Hd, Hd, red_s, y_s);
-        } else {
-          cta_gemv(Wt + a.off.h2_w[l], h2b_s + l * Hd, cur_s, x_s, Hd, Hd, red_s, y_s);
-        }
+        cta_gemv(Wt + a.off.h2_w[l], h2b_s + l * Hd, cur_s, x_s, Hd, Hd, red_s, y_s);
         if (tid < Hd) {
           cur_s[tid] = y_s[tid];
           Hs[((int64_t)(l + 1) * W + w) * Hd + tid] = y_s[tid];
         }
         __syncthreads();
+      }
+      if (a.prof && tid == 0) {
+        const long long t = clock64();
+        atomicAdd(&g_pcnn_prof[1], (unsigned long long)(t - t_px));
+        atomicAdd(&g_pcnn_prof[3], 1ull);
+        t_px = t;
       }
       // head: conv_out(elu(h_stack))                                              (pixelcnn.py:148)
       if (tid < Hd) {
@@ -460,6 +425,7 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
         }
         __syncthreads();
       }
+      if (a.prof && tid == 0) atomicAdd(&g_pcnn_prof[2], (unsigned long long)(clock64() - t_px));
     }
   }
 }
@@ -495,11 +461,23 @@ extern "C" int igm_pixelcnn_run(const float* weights, float* img, const float* u
   a.seed = seed; a.N = N; a.C = C; a.H = H; a.W = W; a.Hd = Hd; a.mode = mode; a.normalize = normalize;
   const size_t smem = sizeof(float) * ((size_t)2 * W * Hd + (size_t)2 * W * 2 * Hd + 2 * Hd + 256 + 1024 + Hd + 256 +
                                        (size_t)NLAYERS * (3 * 2 * Hd + 2 * Hd));
+  static const bool prof_on = [] { const char* e = getenv("IGM_PCNN_PROF"); return e && e[0] == '1'; }();
+  a.prof = prof_on ? 1 : 0;
+  if (smem > 227 * 1024) IGM_FAIL(st, IGM_ERR_INVALID, "PixelCNN: image row too wide for this hidden_dim (shared memory)");
   cudaError_t e = cudaFuncSetAttribute(pixelcnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) IGM_FAIL(st, IGM_ERR_CUDA, cudaGetErrorString(e));
   pixelcnn_kernel<<<N, 256, smem, (cudaStream_t)stream>>>(a);
   ++ops_launch_counter();
   e = cudaPeekAtLastError();
   if (e != cudaSuccess) { cudaGetLastError(); IGM_FAIL(st, IGM_ERR_CUDA, cudaGetErrorString(e)); }
+  return IGM_OK;
+}
+
+// IGM_PCNN_PROF=1: cycles summed over all CTAs since the last call -- out[0] row pass, out[1] per-pixel chain, out[2] head +
+// draw, out[3] pixels -- and reset.  Diagnosis only (tools/pixelcnn_phases.py).
+extern "C" int igm_debug_pixelcnn_prof(unsigned long long* out) {
+  unsigned long long z[4] = {0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(out, g_pcnn_prof, sizeof(z)) != cudaSuccess) return IGM_ERR_CUDA;
+  if (cudaMemcpyToSymbol(g_pcnn_prof, z, sizeof(z)) != cudaSuccess) return IGM_ERR_CUDA;
   return IGM_OK;
 }

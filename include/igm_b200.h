@@ -240,6 +240,9 @@ int64_t igm_launch_count(const igm_ctx* ctx);
 /* Number of kernels launched so far by the context-free entry points (igm_conv2d_*, igm_act_*, igm_ce256, igm_ewise,
  * igm_mse, igm_vq_*, igm_pixelcnn_run) of this process. */
 int64_t igm_ops_launch_count(void);
+/* Diagnosis of the PixelCNN engine (IGM_PCNN_PROF=1 in the environment): SM cycles summed over all CTAs since the last call,
+ * out[0] = row pass (vertical stack), out[1] = per-pixel chain, out[2] = head + draw, out[3] = pixels; resets the counters. */
+int igm_debug_pixelcnn_prof(unsigned long long* out);
 /* One stride-1 KxK (K = 1 or 3, pad (K-1)/2) convolution on NHWC fp32 tensors, for kernel-level
  * parity tests: mode 0 = forward  x[B,H,W,Cin] -> out[B,H,W,Cout] (+bias, +add);
  *               mode 1 = data gradient  x = d_out[B,H,W,Cout] -> out = d_in[B,H,W,Cin].
