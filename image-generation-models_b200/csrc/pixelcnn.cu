@@ -17,7 +17,9 @@ namespace {
 
 constexpr int NLAYERS = 11;
 __constant__ int c_dil[NLAYERS] = {1, 2, 1, 4, 1, 2, 1, 4, 1, 2, 1};   // pixelcnn.py:108-122
-constexpr int PPT = 14;       // output positions per thread in the row GEMMs
+constexpr int PB = 7;         // output positions per thread and pass in the row GEMMs (28 = 4 x 7, 32 = 2 x 2 x 7 + ...)
+constexpr int PADW = 4;       // zero columns on either side of a staged input row (largest dilation)
+constexpr int ROWX = 2 * PADW + PB;   // extra columns of a staged row: both paddings + slack for positions past W
 constexpr int MAX_W = 64;
 constexpr int MAX_HD = 128;
 
@@ -127,44 +129,50 @@ __device__ __forceinline__ void cta_gemv(const float* __restrict__ Wt, const flo
 }
 
 // out[w][n] = bias[n] + sum_{taps} sum_ci Wt[(tap*Kc + ci)][n] * in(tap, w)[ci]  for all w < W, n < N.
-// `rows[t]` points at the smem row (W x Kc, ci contiguous) tap t reads, or null (zero); `shift[t]`
-// is the column offset of tap t.  N divides 256.
+// `rows[t]` points at column 0 of the smem row (ci contiguous, Kc floats per column) tap t reads, or null (zero); `shift[t]` is
+// the column offset of tap t (|shift| <= PADW: the staged rows carry PADW zero columns on either side, so the inner loop has
+// no bounds test).  Register tile: a thread owns TWO adjacent output channels and PB = 7 positions (N / 2 thread columns x
+// 512 / N position groups); per 4 input channels that is 4 64-bit weight loads + 7 128-bit broadcast loads for 56 FMAs.
+// (The first version -- one channel x 14 positions, three bounds tests and a 64-bit address product per load -- ran the row
+// pass at 12 % of the SM's FMA rate and was 51 % of the sampler; tools/pixelcnn_phases.py.)  Every output is still ONE
+// accumulator walking (tap, ci) in ascending order: bit-identical to the scalar form.
 __device__ __forceinline__ void cta_row_gemm(const float* __restrict__ Wt, const float* __restrict__ bias,
                                              const float* const* rows, const int* shift, int ntaps, int Kc,
                                              int N, int W, float* out_s /*[W][N]*/) {
   const int tid = threadIdx.x;
-  const int groups = 256 / N;
-  const int n = tid % N, grp = tid / N;
-  const float b = bias ? __ldg(bias + n) : 0.f;
-  for (int w0 = grp * PPT; w0 < W; w0 += groups * PPT) {
-    float acc[PPT];
+  const int ncol = N >> 1;                 // thread columns
+  const int groups = 256 / ncol;
+  const int tc = tid % ncol, grp = tid / ncol;
+  const int n0 = tc * 2;
+  const float2 b2 = bias ? __ldg(reinterpret_cast<const float2*>(bias + n0)) : make_float2(0.f, 0.f);
+  for (int w0 = grp * PB; w0 < W; w0 += groups * PB) {
+    float2 acc[PB];
 #pragma unroll
-    for (int p = 0; p < PPT; ++p) acc[p] = b;
+    for (int p = 0; p < PB; ++p) acc[p] = b2;
     for (int t = 0; t < ntaps; ++t) {
       const float* row = rows[t];
       if (!row) continue;
-      const int sh = shift[t];
-      const float* wp = Wt + ((int64_t)t * Kc) * N + n;
-#pragma unroll 4
+      const float* xp = row + (w0 + shift[t]) * Kc;
+      const float* wp = Wt + ((int64_t)t * Kc) * N + n0;
+#pragma unroll 2
       for (int c4 = 0; c4 < Kc; c4 += 4) {
-        const float w0v = __ldg(wp + (int64_t)(c4 + 0) * N), w1v = __ldg(wp + (int64_t)(c4 + 1) * N);
-        const float w2v = __ldg(wp + (int64_t)(c4 + 2) * N), w3v = __ldg(wp + (int64_t)(c4 + 3) * N);
+        const float2 wa = __ldg(reinterpret_cast<const float2*>(wp + (int64_t)(c4 + 0) * N));
+        const float2 wb = __ldg(reinterpret_cast<const float2*>(wp + (int64_t)(c4 + 1) * N));
+        const float2 wc = __ldg(reinterpret_cast<const float2*>(wp + (int64_t)(c4 + 2) * N));
+        const float2 wd = __ldg(reinterpret_cast<const float2*>(wp + (int64_t)(c4 + 3) * N));
 #pragma unroll
-        for (int p = 0; p < PPT; ++p) {
-          const int col = w0 + p + sh;
-          if (w0 + p < W && col >= 0 && col < W) {
-            const float4 x = *reinterpret_cast<const float4*>(row + (int64_t)col * Kc + c4);
-            acc[p] = fmaf(w0v, x.x, acc[p]);
-            acc[p] = fmaf(w1v, x.y, acc[p]);
-            acc[p] = fmaf(w2v, x.z, acc[p]);
-            acc[p] = fmaf(w3v, x.w, acc[p]);
-          }
+        for (int p = 0; p < PB; ++p) {
+          const float4 x = *reinterpret_cast<const float4*>(xp + p * Kc + c4);
+          acc[p].x = fmaf(wa.x, x.x, acc[p].x); acc[p].y = fmaf(wa.y, x.x, acc[p].y);
+          acc[p].x = fmaf(wb.x, x.y, acc[p].x); acc[p].y = fmaf(wb.y, x.y, acc[p].y);
+          acc[p].x = fmaf(wc.x, x.z, acc[p].x); acc[p].y = fmaf(wc.y, x.z, acc[p].y);
+          acc[p].x = fmaf(wd.x, x.w, acc[p].x); acc[p].y = fmaf(wd.y, x.w, acc[p].y);
         }
       }
     }
 #pragma unroll
-    for (int p = 0; p < PPT; ++p)
-      if (w0 + p < W) out_s[(w0 + p) * N + n] = acc[p];
+    for (int p = 0; p < PB; ++p)
+      if (w0 + p < W) *reinterpret_cast<float2*>(out_s + (w0 + p) * N + n0) = acc[p];
   }
   __syncthreads();
 }
@@ -191,8 +199,8 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
   const int tid = threadIdx.x;
   const int C = a.C, H = a.H, W = a.W, Hd = a.Hd, N2 = 2 * a.Hd;
   // shared memory carve-up
-  float* in_s = sm;                         // [2][W][Hd]   two input rows of the vertical conv
-  float* vc_s = in_s + 2 * W * Hd;          // [W][2Hd]     vert_conv output of the current layer
+  float* in_s = sm;                         // [2][W + ROWX][Hd]  two input rows of the vertical conv, PADW zero columns either side
+  float* vc_s = in_s + 2 * (W + ROWX) * Hd; // [W][2Hd]     vert_conv output of the current layer (+ PB rows of slack via t_s)
   float* t_s = vc_s + W * N2;               // [W][2Hd]     scratch row (v2h result / gated row)
   float* x_s = t_s + W * N2;                // [2Hd]        gemv input
   float* y_s = x_s + N2;                    // [256]        gemv output
@@ -215,6 +223,7 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
   float* img = a.img + (int64_t)n_img * C * H * W;
   const float* Wt = a.Wt;
 
+  for (int i = tid; i < 2 * (W + ROWX) * Hd; i += 256) in_s[i] = 0.f;   // the padding columns stay zero for the whole kernel
   for (int i = tid; i < NLAYERS * N2; i += 256) {
     const int l = i / N2, j = i - l * N2;
     hb_s[i] = __ldg(Wt + a.off.horiz_b[l] + j);
@@ -253,9 +262,11 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
       // stage rows h-d and h of the previous layer's vertical features
       const float* prev = Vc + ((int64_t)l * H) * W * Hd;
       const bool top_ok = (h - d) >= 0;
+      float* row0 = in_s + PADW * Hd;                        // column 0 of the staged row h - d
+      float* row1 = in_s + (W + ROWX) * Hd + PADW * Hd;      // column 0 of the staged row h
       for (int i = tid; i < W * Hd / 4; i += 256) {
-        reinterpret_cast<float4*>(in_s + W * Hd)[i] = reinterpret_cast<const float4*>(prev + (int64_t)h * W * Hd)[i];
-        if (top_ok) reinterpret_cast<float4*>(in_s)[i] = reinterpret_cast<const float4*>(prev + (int64_t)(h - d) * W * Hd)[i];
+        reinterpret_cast<float4*>(row1)[i] = reinterpret_cast<const float4*>(prev + (int64_t)h * W * Hd)[i];
+        if (top_ok) reinterpret_cast<float4*>(row0)[i] = reinterpret_cast<const float4*>(prev + (int64_t)(h - d) * W * Hd)[i];
       }
       __syncthreads();
       // vert_conv 3x3 dilated, rows ky = 0 (h-d), 1 (h); cols w-d, w, w+d      (pixelcnn.py:51-53)
@@ -263,7 +274,7 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
       int shift[6];
       for (int ky = 0; ky < 2; ++ky)
         for (int kx = 0; kx < 3; ++kx) {
-          rows[ky * 3 + kx] = (ky == 0) ? (top_ok ? in_s : nullptr) : (in_s + W * Hd);
+          rows[ky * 3 + kx] = (ky == 0) ? (top_ok ? row0 : nullptr) : row1;
           shift[ky * 3 + kx] = (kx - 1) * d;
         }
       cta_row_gemm(Wt + a.off.vert_w[l], Wt + a.off.vert_b[l], rows, shift, 6, Hd, N2, W, vc_s);
@@ -459,7 +470,7 @@ extern "C" int igm_pixelcnn_run(const float* weights, float* img, const float* u
   a.img = img; a.uniforms = uniforms; a.skip = skip; a.cond = cond; a.logits = logits; a.ws = ws;
   a.ws_per_img = igm_pixelcnn_workspace_floats(1, C, H, W, Hd);
   a.seed = seed; a.N = N; a.C = C; a.H = H; a.W = W; a.Hd = Hd; a.mode = mode; a.normalize = normalize;
-  const size_t smem = sizeof(float) * ((size_t)2 * W * Hd + (size_t)2 * W * 2 * Hd + 2 * Hd + 256 + 1024 + Hd + 256 +
+  const size_t smem = sizeof(float) * ((size_t)2 * (W + ROWX) * Hd + (size_t)2 * W * 2 * Hd + 2 * Hd + 256 + 1024 + Hd + 256 +
                                        (size_t)NLAYERS * (3 * 2 * Hd + 2 * Hd));
   static const bool prof_on = [] { const char* e = getenv("IGM_PCNN_PROF"); return e && e[0] == '1'; }();
   a.prof = prof_on ? 1 : 0;
