@@ -136,12 +136,16 @@ __device__ __forceinline__ void cta_gemv(const float* __restrict__ Wt, const flo
 // (The first version -- one channel x 14 positions, three bounds tests and a 64-bit address product per load -- ran the row
 // pass at 12 % of the SM's FMA rate and was 51 % of the sampler; tools/pixelcnn_phases.py.)  Every output is still ONE
 // accumulator walking (tap, ci) in ascending order: bit-identical to the scalar form.
-__device__ __forceinline__ void cta_row_gemm(const float* __restrict__ Wt, const float* __restrict__ bias,
-                                             const float* const* rows, const int* shift, int ntaps, int Kc,
-                                             int N, int W, float* out_s /*[W][N]*/) {
+// N and Kc are compile-time (N = 2 * hidden_dim; Kc = hidden_dim for vert_conv, 2 * hidden_dim for the v -> h link): with
+// run-time strides ptxas spent ~60 integer instructions per 112 FMAs on 64-bit address products (SASS of the first tiled
+// version), and the weight loads of only two k-chunks were in flight.
+template <int N, int KC>
+__device__ __forceinline__ void cta_row_gemm_t(const float* __restrict__ Wt, const float* __restrict__ bias,
+                                               const float* const* rows, const int* shift, int ntaps, int W,
+                                               float* out_s /*[W][N]*/) {
   const int tid = threadIdx.x;
-  const int ncol = N >> 1;                 // thread columns
-  const int groups = 256 / ncol;
+  constexpr int ncol = N >> 1;             // thread columns
+  constexpr int groups = 256 / ncol;
   const int tc = tid % ncol, grp = tid / ncol;
   const int n0 = tc * 2;
   const float2 b2 = bias ? __ldg(reinterpret_cast<const float2*>(bias + n0)) : make_float2(0.f, 0.f);
@@ -152,21 +156,23 @@ __device__ __forceinline__ void cta_row_gemm(const float* __restrict__ Wt, const
     for (int t = 0; t < ntaps; ++t) {
       const float* row = rows[t];
       if (!row) continue;
-      const float* xp = row + (w0 + shift[t]) * Kc;
-      const float* wp = Wt + ((int64_t)t * Kc) * N + n0;
-#pragma unroll 2
-      for (int c4 = 0; c4 < Kc; c4 += 4) {
-        const float2 wa = __ldg(reinterpret_cast<const float2*>(wp + (int64_t)(c4 + 0) * N));
-        const float2 wb = __ldg(reinterpret_cast<const float2*>(wp + (int64_t)(c4 + 1) * N));
-        const float2 wc = __ldg(reinterpret_cast<const float2*>(wp + (int64_t)(c4 + 2) * N));
-        const float2 wd = __ldg(reinterpret_cast<const float2*>(wp + (int64_t)(c4 + 3) * N));
+      const float* xp = row + (w0 + shift[t]) * KC;
+      const float2* wp = reinterpret_cast<const float2*>(Wt + (size_t)t * KC * N + n0);
+#pragma unroll 1
+      for (int c16 = 0; c16 < KC; c16 += 16, wp += 16 * (N / 2), xp += 16) {
+        float2 wv[16];
 #pragma unroll
-        for (int p = 0; p < PB; ++p) {
-          const float4 x = *reinterpret_cast<const float4*>(xp + p * Kc + c4);
-          acc[p].x = fmaf(wa.x, x.x, acc[p].x); acc[p].y = fmaf(wa.y, x.x, acc[p].y);
-          acc[p].x = fmaf(wb.x, x.y, acc[p].x); acc[p].y = fmaf(wb.y, x.y, acc[p].y);
-          acc[p].x = fmaf(wc.x, x.z, acc[p].x); acc[p].y = fmaf(wc.y, x.z, acc[p].y);
-          acc[p].x = fmaf(wd.x, x.w, acc[p].x); acc[p].y = fmaf(wd.y, x.w, acc[p].y);
+        for (int k = 0; k < 16; ++k) wv[k] = __ldg(wp + k * (N / 2));
+#pragma unroll
+        for (int c4 = 0; c4 < 16; c4 += 4) {
+#pragma unroll
+          for (int p = 0; p < PB; ++p) {
+            const float4 x = *reinterpret_cast<const float4*>(xp + p * KC + c4);
+            acc[p].x = fmaf(wv[c4 + 0].x, x.x, acc[p].x); acc[p].y = fmaf(wv[c4 + 0].y, x.x, acc[p].y);
+            acc[p].x = fmaf(wv[c4 + 1].x, x.y, acc[p].x); acc[p].y = fmaf(wv[c4 + 1].y, x.y, acc[p].y);
+            acc[p].x = fmaf(wv[c4 + 2].x, x.z, acc[p].x); acc[p].y = fmaf(wv[c4 + 2].y, x.z, acc[p].y);
+            acc[p].x = fmaf(wv[c4 + 3].x, x.w, acc[p].x); acc[p].y = fmaf(wv[c4 + 3].y, x.w, acc[p].y);
+          }
         }
       }
     }
@@ -175,6 +181,16 @@ __device__ __forceinline__ void cta_row_gemm(const float* __restrict__ Wt, const
       if (w0 + p < W) *reinterpret_cast<float2*>(out_s + (w0 + p) * N + n0) = acc[p];
   }
   __syncthreads();
+}
+
+// run-time dispatch over the hidden sizes the engine accepts (32, 64, 128); V2H: the 1x1 v -> h link (Kc = 2 * hidden_dim)
+template <bool V2H>
+__device__ __forceinline__ void cta_row_gemm(const float* __restrict__ Wt, const float* __restrict__ bias,
+                                             const float* const* rows, const int* shift, int ntaps, int Hd, int W,
+                                             float* out_s) {
+  if (Hd == 64) cta_row_gemm_t<128, V2H ? 128 : 64>(Wt, bias, rows, shift, ntaps, W, out_s);
+  else if (Hd == 32) cta_row_gemm_t<64, V2H ? 64 : 32>(Wt, bias, rows, shift, ntaps, W, out_s);
+  else cta_row_gemm_t<256, V2H ? 256 : 128>(Wt, bias, rows, shift, ntaps, W, out_s);
 }
 
 __device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t a, uint32_t b) {
@@ -277,7 +293,7 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
           rows[ky * 3 + kx] = (ky == 0) ? (top_ok ? row0 : nullptr) : row1;
           shift[ky * 3 + kx] = (kx - 1) * d;
         }
-      cta_row_gemm(Wt + a.off.vert_w[l], Wt + a.off.vert_b[l], rows, shift, 6, Hd, N2, W, vc_s);
+      cta_row_gemm<false>(Wt + a.off.vert_w[l], Wt + a.off.vert_b[l], rows, shift, 6, Hd, W, vc_s);
       // gated vertical output: tanh(a) * sigmoid(b)                            (pixelcnn.py:69)
       float* vout = Vc + (((int64_t)(l + 1) * H + h) * W) * Hd;
       for (int i = tid; i < W * Hd; i += 256) {
@@ -293,7 +309,7 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
       // v -> h link: conv1x1_1 on the PRE-gate features                         (pixelcnn.py:74)
       const float* rows1[1] = {vc_s};
       const int shift1[1] = {0};
-      cta_row_gemm(Wt + a.off.v2h_w[l], Wt + a.off.v2h_b[l], rows1, shift1, 1, N2, N2, W, t_s);
+      cta_row_gemm<true>(Wt + a.off.v2h_w[l], Wt + a.off.v2h_b[l], rows1, shift1, 1, Hd, W, t_s);
       float* v2h = V2H + (int64_t)l * W * N2;
       for (int i = tid; i < W * N2 / 4; i += 256) reinterpret_cast<float4*>(v2h)[i] = reinterpret_cast<const float4*>(t_s)[i];
       __syncthreads();
