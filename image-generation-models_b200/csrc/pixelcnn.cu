@@ -207,7 +207,7 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t a, uint3
   return (float)(c0 >> 8) * (1.0f / 16777216.0f);
 }
 
-__device__ unsigned long long g_pcnn_prof[4];   // row pass | per-pixel chain | head + draw | pixels   (IGM_PCNN_PROF=1)
+__device__ unsigned long long g_pcnn_prof[8];   // + [4..7]: chain split (fill, horiz gemv, gate, conv1x1_2 + tail)   // row pass | per-pixel chain | head + draw | pixels   (IGM_PCNN_PROF=1)
 
 __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
   extern __shared__ __align__(16) float sm[];
@@ -350,12 +350,16 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
       for (int l = 0; l < NLAYERS; ++l) {
         const int d = c_dil[l];
         // horiz_conv 1x3 dilated, cols kx = 0 (w-d), 1 (w)                        (pixelcnn.py:48-50)
+        long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        if (a.prof && tid == 0) c0 = clock64();
         if (tid < Hd) {
           x_s[Hd + tid] = cur_s[tid];
           x_s[tid] = hsp_s[l * Hd + tid];
         }
         __syncthreads();
+        if (a.prof && tid == 0) c1 = clock64();
         cta_gemv(Wt + a.off.horiz_w[l], hb_s + l * N2, v2h_s + l * N2, x_s, N2, N2, red_s, y_s);
+        if (a.prof && tid == 0) c2 = clock64();
         // gated horizontal output: tanh(a) * tanh(b)  (sic)                      (pixelcnn.py:77)
         if (tid < Hd) {
           float ah = y_s[tid], bh = y_s[Hd + tid];
@@ -366,6 +370,7 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
           x_s[tid] = tanhf(ah) * tanhf(bh);
         }
         __syncthreads();
+        if (a.prof && tid == 0) c3 = clock64();
         // conv1x1_2 + residual                                                    (pixelcnn.py:80)
         cta_gemv(Wt + a.off.h2_w[l], h2b_s + l * Hd, cur_s, x_s, Hd, Hd, red_s, y_s);
         if (tid < Hd) {
@@ -373,6 +378,13 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
           Hs[((int64_t)(l + 1) * W + w) * Hd + tid] = y_s[tid];
         }
         __syncthreads();
+        if (a.prof && tid == 0) {
+          const long long c4 = clock64();
+          atomicAdd(&g_pcnn_prof[4], (unsigned long long)(c1 - c0));
+          atomicAdd(&g_pcnn_prof[5], (unsigned long long)(c2 - c1));
+          atomicAdd(&g_pcnn_prof[6], (unsigned long long)(c3 - c2));
+          atomicAdd(&g_pcnn_prof[7], (unsigned long long)(c4 - c3));
+        }
       }
       if (a.prof && tid == 0) {
         const long long t = clock64();
@@ -501,9 +513,9 @@ extern "C" int igm_pixelcnn_run(const float* weights, float* img, const float* u
 }
 
 // IGM_PCNN_PROF=1: cycles summed over all CTAs since the last call -- out[0] row pass, out[1] per-pixel chain, out[2] head +
-// draw, out[3] pixels -- and reset.  Diagnosis only (tools/pixelcnn_phases.py).
+// draw, out[3] pixels, out[4..7] the chain split into x fill / horiz GEMV / gate / conv1x1_2 + tail -- and reset.  Diagnosis only (tools/pixelcnn_phases.py).
 extern "C" int igm_debug_pixelcnn_prof(unsigned long long* out) {
-  unsigned long long z[4] = {0, 0, 0, 0};
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (cudaMemcpyFromSymbol(out, g_pcnn_prof, sizeof(z)) != cudaSuccess) return IGM_ERR_CUDA;
   if (cudaMemcpyToSymbol(g_pcnn_prof, z, sizeof(z)) != cudaSuccess) return IGM_ERR_CUDA;
   return IGM_OK;

@@ -241,7 +241,8 @@ int64_t igm_launch_count(const igm_ctx* ctx);
  * igm_mse, igm_vq_*, igm_pixelcnn_run) of this process. */
 int64_t igm_ops_launch_count(void);
 /* Diagnosis of the PixelCNN engine (IGM_PCNN_PROF=1 in the environment): SM cycles summed over all CTAs since the last call,
- * out[0] = row pass (vertical stack), out[1] = per-pixel chain, out[2] = head + draw, out[3] = pixels; resets the counters. */
+ * out[0] = row pass (vertical stack), out[1] = per-pixel chain, out[2] = head + draw, out[3] = pixels, out[4..7] = the chain
+ * split into input fill / horiz_conv GEMV / gate / conv1x1_2 GEMV + tail (eight values); resets the counters. */
 int igm_debug_pixelcnn_prof(unsigned long long* out);
 /* One stride-1 KxK (K = 1 or 3, pad (K-1)/2) convolution on NHWC fp32 tensors, for kernel-level
  * parity tests: mode 0 = forward  x[B,H,W,Cin] -> out[B,H,W,Cout] (+bias, +add);

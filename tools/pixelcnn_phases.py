@@ -17,13 +17,14 @@ torch.manual_seed(0)
 from bench_secondary import _dm  # noqa: E402
 
 model = igm_b200.PixelCNN(_dm(1, 28, 28, False), hidden_dim=64).to(dev)   # default init: timing does not depend on the weights
-out = (C.c_ulonglong * 4)()
+out = (C.c_ulonglong * 8)()
 model.sample((64, 1, 28, 28), seed=1)
 torch.cuda.synchronize()
 lib.igm_debug_pixelcnn_prof(out)
 model.sample((64, 1, 28, 28), seed=1)
 torch.cuda.synchronize()
 lib.igm_debug_pixelcnn_prof(out)
-row, chain, head, px = (int(v) for v in out)
+row, chain, head, px, f0, f1, f2, f3 = (int(v) for v in out)
 print(f"pixels {px}: row pass {row / px:.0f} cycles/pixel, chain {chain / px:.0f}, head + draw {head / px:.0f}  "
       f"(total {(row + chain + head) / px:.0f} cycles = {(row + chain + head) / px / 1965:.1f} us per pixel at 1965 MHz)")
+print(f"chain per pixel: input fill {f0 / px:.0f}, horiz_conv GEMV {f1 / px:.0f}, gate {f2 / px:.0f}, conv1x1_2 GEMV + tail {f3 / px:.0f} cycles")
