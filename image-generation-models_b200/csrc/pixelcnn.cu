@@ -74,47 +74,32 @@ struct PcnnArgs {
 // slots a whole layer ahead -- once those small loads were staged, both pipelines LOST 6 % against this plain form
 // (1602 vs 1708 samples/s).  Keeping nine of the eleven conv1x1_2 matrices resident in the SM's spare shared memory changed
 // nothing either (1753 vs 1755): the weight fetches are not what the chain waits for.
-__device__ __forceinline__ void cta_gemv(const float* __restrict__ Wt, const float* __restrict__ bias,
-                                         const float* __restrict__ extra, const float* x_s, int K, int N,
-                                         float* red_s /*[1024]*/, float* y_s) {
+template <int N, int K>
+__device__ __forceinline__ void cta_gemv_t(const float* __restrict__ Wt, const float* __restrict__ bias,
+                                           const float* __restrict__ extra, const float* x_s, float* red_s /*[1024]*/,
+                                           float* y_s) {
+  // compile-time shape: the slice arithmetic (three integer divisions in the run-time form) folds away and the loads of a
+  // slice are addressed with immediates
+  constexpr int n4 = N >> 2;             // threads per K slice
+  constexpr int parts = 256 / n4;        // K slices
+  constexpr int klen = K / parts;        // K, N are powers of two >= 64: divides exactly
+  constexpr int CH = klen < 16 ? klen : 16;   // rows per batch of loads (all in flight before the first FMA)
+  static_assert(klen >= 1 && klen % CH == 0, "a thread's K slice is a multiple of its load batch");
   const int tid = threadIdx.x;
-  const int n4 = N >> 2;                 // threads per K slice
-  const int parts = 256 / n4;            // K slices
-  const int part = tid / n4, q = tid - part * n4;
-  const int klen = K / parts;            // K, N are powers of two >= 64: divides exactly
+  const int part = tid / n4, q = tid % n4;
   const int kb = part * klen;
-  const float4* wp = reinterpret_cast<const float4*>(Wt + (int64_t)kb * N) + q;
+  const float4* wp = reinterpret_cast<const float4*>(Wt + (size_t)kb * N) + q;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (klen >= 16) {
-    for (int k0 = 0; k0 < klen; k0 += 16) {
-      float4 wv[16];
+#pragma unroll 1
+  for (int k0 = 0; k0 < klen; k0 += CH) {
+    float4 wv[CH];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) wv[k] = __ldg(wp + (int64_t)(k0 + k) * n4);
+    for (int k = 0; k < CH; ++k) wv[k] = __ldg(wp + (k0 + k) * n4);
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const float x = x_s[kb + k0 + k];
-        acc.x = fmaf(wv[k].x, x, acc.x); acc.y = fmaf(wv[k].y, x, acc.y);
-        acc.z = fmaf(wv[k].z, x, acc.z); acc.w = fmaf(wv[k].w, x, acc.w);
-      }
-    }
-  } else if (klen >= 4) {
-    for (int k0 = 0; k0 < klen; k0 += 4) {
-      float4 wv[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) wv[k] = __ldg(wp + (int64_t)(k0 + k) * n4);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float x = x_s[kb + k0 + k];
-        acc.x = fmaf(wv[k].x, x, acc.x); acc.y = fmaf(wv[k].y, x, acc.y);
-        acc.z = fmaf(wv[k].z, x, acc.z); acc.w = fmaf(wv[k].w, x, acc.w);
-      }
-    }
-  } else {
-    for (int k = 0; k < klen; ++k) {
-      const float4 wv = __ldg(wp + (int64_t)k * n4);
-      const float x = x_s[kb + k];
-      acc.x = fmaf(wv.x, x, acc.x); acc.y = fmaf(wv.y, x, acc.y);
-      acc.z = fmaf(wv.z, x, acc.z); acc.w = fmaf(wv.w, x, acc.w);
+    for (int k = 0; k < CH; ++k) {
+      const float x = x_s[kb + k0 + k];
+      acc.x = fmaf(wv[k].x, x, acc.x); acc.y = fmaf(wv[k].y, x, acc.y);
+      acc.z = fmaf(wv[k].z, x, acc.z); acc.w = fmaf(wv[k].w, x, acc.w);
     }
   }
   *reinterpret_cast<float4*>(red_s + part * N + q * 4) = acc;
@@ -122,10 +107,19 @@ __device__ __forceinline__ void cta_gemv(const float* __restrict__ Wt, const flo
   if (tid < N) {
     float s = bias ? bias[tid] : 0.f;   // generic load: the per-pixel chain passes shared-memory copies
     if (extra) s += extra[tid];
+#pragma unroll
     for (int p = 0; p < parts; ++p) s += red_s[p * N + tid];
     y_s[tid] = s;
   }
   __syncthreads();
+}
+// SQ = false: the 2 Hd x 2 Hd horiz_conv matrix; true: the Hd x Hd conv1x1_2 matrix
+template <bool SQ>
+__device__ __forceinline__ void cta_gemv(const float* __restrict__ Wt, const float* __restrict__ bias,
+                                         const float* __restrict__ extra, const float* x_s, int Hd, float* red_s, float* y_s) {
+  if (Hd == 64) cta_gemv_t<SQ ? 64 : 128, SQ ? 64 : 128>(Wt, bias, extra, x_s, red_s, y_s);
+  else if (Hd == 32) cta_gemv_t<SQ ? 32 : 64, SQ ? 32 : 64>(Wt, bias, extra, x_s, red_s, y_s);
+  else cta_gemv_t<SQ ? 128 : 256, SQ ? 128 : 256>(Wt, bias, extra, x_s, red_s, y_s);
 }
 
 // out[w][n] = bias[n] + sum_{taps} sum_ci Wt[(tap*Kc + ci)][n] * in(tap, w)[ci]  for all w < W, n < N.
@@ -358,7 +352,7 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
         }
         __syncthreads();
         if (a.prof && tid == 0) c1 = clock64();
-        cta_gemv(Wt + a.off.horiz_w[l], hb_s + l * N2, v2h_s + l * N2, x_s, N2, N2, red_s, y_s);
+        cta_gemv<false>(Wt + a.off.horiz_w[l], hb_s + l * N2, v2h_s + l * N2, x_s, Hd, red_s, y_s);
         if (a.prof && tid == 0) c2 = clock64();
         // gated horizontal output: tanh(a) * tanh(b)  (sic)                      (pixelcnn.py:77)
         if (tid < Hd) {
@@ -372,7 +366,7 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
         __syncthreads();
         if (a.prof && tid == 0) c3 = clock64();
         // conv1x1_2 + residual                                                    (pixelcnn.py:80)
-        cta_gemv(Wt + a.off.h2_w[l], h2b_s + l * Hd, cur_s, x_s, Hd, Hd, red_s, y_s);
+        cta_gemv<true>(Wt + a.off.h2_w[l], h2b_s + l * Hd, cur_s, x_s, Hd, red_s, y_s);
         if (tid < Hd) {
           cur_s[tid] = y_s[tid];
           Hs[((int64_t)(l + 1) * W + w) * Hd + tid] = y_s[tid];
