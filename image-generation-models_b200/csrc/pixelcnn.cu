@@ -113,15 +113,6 @@ __device__ __forceinline__ void cta_gemv_t(const float* __restrict__ Wt, const f
   }
   __syncthreads();
 }
-// SQ = false: the 2 Hd x 2 Hd horiz_conv matrix; true: the Hd x Hd conv1x1_2 matrix
-template <bool SQ>
-__device__ __forceinline__ void cta_gemv(const float* __restrict__ Wt, const float* __restrict__ bias,
-                                         const float* __restrict__ extra, const float* x_s, int Hd, float* red_s, float* y_s) {
-  if (Hd == 64) cta_gemv_t<SQ ? 64 : 128, SQ ? 64 : 128>(Wt, bias, extra, x_s, red_s, y_s);
-  else if (Hd == 32) cta_gemv_t<SQ ? 32 : 64, SQ ? 32 : 64>(Wt, bias, extra, x_s, red_s, y_s);
-  else cta_gemv_t<SQ ? 128 : 256, SQ ? 128 : 256>(Wt, bias, extra, x_s, red_s, y_s);
-}
-
 // out[w][n] = bias[n] + sum_{taps} sum_ci Wt[(tap*Kc + ci)][n] * in(tap, w)[ci]  for all w < W, n < N.
 // `rows[t]` points at column 0 of the smem row (ci contiguous, Kc floats per column) tap t reads, or null (zero); `shift[t]` is
 // the column offset of tap t (|shift| <= PADW: the staged rows carry PADW zero columns on either side, so the inner loop has
@@ -177,16 +168,6 @@ __device__ __forceinline__ void cta_row_gemm_t(const float* __restrict__ Wt, con
   __syncthreads();
 }
 
-// run-time dispatch over the hidden sizes the engine accepts (32, 64, 128); V2H: the 1x1 v -> h link (Kc = 2 * hidden_dim)
-template <bool V2H>
-__device__ __forceinline__ void cta_row_gemm(const float* __restrict__ Wt, const float* __restrict__ bias,
-                                             const float* const* rows, const int* shift, int ntaps, int Hd, int W,
-                                             float* out_s) {
-  if (Hd == 64) cta_row_gemm_t<128, V2H ? 128 : 64>(Wt, bias, rows, shift, ntaps, W, out_s);
-  else if (Hd == 32) cta_row_gemm_t<64, V2H ? 64 : 32>(Wt, bias, rows, shift, ntaps, W, out_s);
-  else cta_row_gemm_t<256, V2H ? 256 : 128>(Wt, bias, rows, shift, ntaps, W, out_s);
-}
-
 __device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t a, uint32_t b) {
   // Philox4x32-10 keyed by seed, counter (a, b, 0, 0) -> one uniform in [0, 1)
   uint32_t c0 = a, c1 = b, c2 = 0, c3 = 0, k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
@@ -203,11 +184,15 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t a, uint3
 
 __device__ unsigned long long g_pcnn_prof[8];   // + [4..7]: chain split (fill, horiz gemv, gate, conv1x1_2 + tail)   // row pass | per-pixel chain | head + draw | pixels   (IGM_PCNN_PROF=1)
 
+// HD = hidden_dim as a template parameter: every index split of the kernel (staging loops, gates, slices) divides by a
+// power-of-two constant instead of a run-time value.
+template <int HD>
 __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
   extern __shared__ __align__(16) float sm[];
   const int n_img = blockIdx.x;
   const int tid = threadIdx.x;
-  const int C = a.C, H = a.H, W = a.W, Hd = a.Hd, N2 = 2 * a.Hd;
+  constexpr int Hd = HD, N2 = 2 * HD;
+  const int C = a.C, H = a.H, W = a.W;
   // shared memory carve-up
   float* in_s = sm;                         // [2][W + ROWX][Hd]  two input rows of the vertical conv, PADW zero columns either side
   float* vc_s = in_s + 2 * (W + ROWX) * Hd; // [W][2Hd]     vert_conv output of the current layer (+ PB rows of slack via t_s)
@@ -287,7 +272,7 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
           rows[ky * 3 + kx] = (ky == 0) ? (top_ok ? row0 : nullptr) : row1;
           shift[ky * 3 + kx] = (kx - 1) * d;
         }
-      cta_row_gemm<false>(Wt + a.off.vert_w[l], Wt + a.off.vert_b[l], rows, shift, 6, Hd, W, vc_s);
+      cta_row_gemm_t<N2, Hd>(Wt + a.off.vert_w[l], Wt + a.off.vert_b[l], rows, shift, 6, W, vc_s);
       // gated vertical output: tanh(a) * sigmoid(b)                            (pixelcnn.py:69)
       float* vout = Vc + (((int64_t)(l + 1) * H + h) * W) * Hd;
       for (int i = tid; i < W * Hd; i += 256) {
@@ -303,7 +288,7 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
       // v -> h link: conv1x1_1 on the PRE-gate features                         (pixelcnn.py:74)
       const float* rows1[1] = {vc_s};
       const int shift1[1] = {0};
-      cta_row_gemm<true>(Wt + a.off.v2h_w[l], Wt + a.off.v2h_b[l], rows1, shift1, 1, Hd, W, t_s);
+      cta_row_gemm_t<N2, N2>(Wt + a.off.v2h_w[l], Wt + a.off.v2h_b[l], rows1, shift1, 1, W, t_s);
       float* v2h = V2H + (int64_t)l * W * N2;
       for (int i = tid; i < W * N2 / 4; i += 256) reinterpret_cast<float4*>(v2h)[i] = reinterpret_cast<const float4*>(t_s)[i];
       __syncthreads();
@@ -352,7 +337,7 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
         }
         __syncthreads();
         if (a.prof && tid == 0) c1 = clock64();
-        cta_gemv<false>(Wt + a.off.horiz_w[l], hb_s + l * N2, v2h_s + l * N2, x_s, Hd, red_s, y_s);
+        cta_gemv_t<N2, N2>(Wt + a.off.horiz_w[l], hb_s + l * N2, v2h_s + l * N2, x_s, red_s, y_s);
         if (a.prof && tid == 0) c2 = clock64();
         // gated horizontal output: tanh(a) * tanh(b)  (sic)                      (pixelcnn.py:77)
         if (tid < Hd) {
@@ -366,7 +351,7 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
         __syncthreads();
         if (a.prof && tid == 0) c3 = clock64();
         // conv1x1_2 + residual                                                    (pixelcnn.py:80)
-        cta_gemv<true>(Wt + a.off.h2_w[l], h2b_s + l * Hd, cur_s, x_s, Hd, red_s, y_s);
+        cta_gemv_t<Hd, Hd>(Wt + a.off.h2_w[l], h2b_s + l * Hd, cur_s, x_s, red_s, y_s);
         if (tid < Hd) {
           cur_s[tid] = y_s[tid];
           Hs[((int64_t)(l + 1) * W + w) * Hd + tid] = y_s[tid];
@@ -497,9 +482,14 @@ extern "C" int igm_pixelcnn_run(const float* weights, float* img, const float* u
   static const bool prof_on = [] { const char* e = getenv("IGM_PCNN_PROF"); return e && e[0] == '1'; }();
   a.prof = prof_on ? 1 : 0;
   if (smem > 227 * 1024) IGM_FAIL(st, IGM_ERR_INVALID, "PixelCNN: image row too wide for this hidden_dim (shared memory)");
-  cudaError_t e = cudaFuncSetAttribute(pixelcnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto go = [&](auto kernel) -> cudaError_t {
+    cudaError_t er = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (er != cudaSuccess) return er;
+    kernel<<<N, 256, smem, (cudaStream_t)stream>>>(a);
+    return cudaSuccess;
+  };
+  cudaError_t e = Hd == 64 ? go(pixelcnn_kernel<64>) : Hd == 32 ? go(pixelcnn_kernel<32>) : go(pixelcnn_kernel<128>);
   if (e != cudaSuccess) IGM_FAIL(st, IGM_ERR_CUDA, cudaGetErrorString(e));
-  pixelcnn_kernel<<<N, 256, smem, (cudaStream_t)stream>>>(a);
   ++ops_launch_counter();
   e = cudaPeekAtLastError();
   if (e != cudaSuccess) { cudaGetLastError(); IGM_FAIL(st, IGM_ERR_CUDA, cudaGetErrorString(e)); }
