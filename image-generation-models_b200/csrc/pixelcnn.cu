@@ -143,22 +143,34 @@ __device__ __forceinline__ void cta_row_gemm_t(const float* __restrict__ Wt, con
       if (!row) continue;
       const float* xp = row + (w0 + shift[t]) * KC;
       const float2* wp = reinterpret_cast<const float2*>(Wt + (size_t)t * KC * N + n0);
-#pragma unroll 1
-      for (int c16 = 0; c16 < KC; c16 += 16, wp += 16 * (N / 2), xp += 16) {
-        float2 wv[16];
+      // 16-row weight blocks, double-buffered in registers: the next block's loads are issued before the current block's
+      // 448 FMAs (with the loads at the top of each block every block waited out an L2 round trip: 32 per layer)
+      auto load16 = [&](float2 (&wv)[16], const float2* src) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) wv[k] = __ldg(wp + k * (N / 2));
+        for (int k = 0; k < 16; ++k) wv[k] = __ldg(src + k * (N / 2));
+      };
+      auto fma16 = [&](const float2 (&wv)[16], const float* xq) {
 #pragma unroll
         for (int c4 = 0; c4 < 16; c4 += 4) {
 #pragma unroll
           for (int p = 0; p < PB; ++p) {
-            const float4 x = *reinterpret_cast<const float4*>(xp + p * KC + c4);
+            const float4 x = *reinterpret_cast<const float4*>(xq + p * KC + c4);
             acc[p].x = fmaf(wv[c4 + 0].x, x.x, acc[p].x); acc[p].y = fmaf(wv[c4 + 0].y, x.x, acc[p].y);
             acc[p].x = fmaf(wv[c4 + 1].x, x.y, acc[p].x); acc[p].y = fmaf(wv[c4 + 1].y, x.y, acc[p].y);
             acc[p].x = fmaf(wv[c4 + 2].x, x.z, acc[p].x); acc[p].y = fmaf(wv[c4 + 2].y, x.z, acc[p].y);
             acc[p].x = fmaf(wv[c4 + 3].x, x.w, acc[p].x); acc[p].y = fmaf(wv[c4 + 3].y, x.w, acc[p].y);
           }
         }
+      };
+      static_assert(KC % 32 == 0, "two 16-row blocks per iteration");
+      float2 wA[16], wB[16];
+      load16(wA, wp);
+#pragma unroll 1
+      for (int c32 = 0; c32 < KC; c32 += 32, wp += 32 * (N / 2), xp += 32) {
+        load16(wB, wp + 16 * (N / 2));
+        fma16(wA, xp);
+        if (c32 + 32 < KC) load16(wA, wp + 32 * (N / 2));
+        fma16(wB, xp + 16);
       }
     }
 #pragma unroll
