@@ -61,6 +61,7 @@ struct PcnnArgs {
   int N, C, H, W, Hd;
   int mode;                  // 0 inverse-CDF draw, 1 greedy argmax, 2 teacher forced (no draw)
   int normalize;             // pixel value k/255 (0) or 2k/255 - 1 (1)
+  int early;                 // conv1x1_2 weight slices loaded next to horiz_conv's (IGM_PCNN_EARLY=0: at their use)
   int prof;                  // IGM_PCNN_PROF=1: thread 0 of every CTA adds its row-pass / pixel-chain / head cycles to g_pcnn_prof
 };
 
@@ -113,6 +114,50 @@ __device__ __forceinline__ void cta_gemv_t(const float* __restrict__ Wt, const f
   }
   __syncthreads();
 }
+// The small GEMV of a layer (conv1x1_2) with its weight slice loaded EARLY: gemv_early_load is issued next to the loads of the
+// layer's large GEMV (the weights do not depend on the data), gemv_early_finish consumes the registers after the gate -- the
+// second L2 round trip of the layer overlaps the first.  Same slicing and summation order as cta_gemv_t.
+template <int N, int K>
+struct GemvSlice {
+  static constexpr int n4 = N >> 2, parts = 256 / n4, klen = K / parts;
+  static_assert(klen >= 1 && klen <= 16, "an early slice lives in registers");
+  float4 w[klen];
+};
+template <int N, int K>
+__device__ __forceinline__ void gemv_early_load(const float* __restrict__ Wt, GemvSlice<N, K>& sl) {
+  using S = GemvSlice<N, K>;
+  const int tid = threadIdx.x;
+  const int part = tid / S::n4, q = tid % S::n4;
+  const float4* wp = reinterpret_cast<const float4*>(Wt + (size_t)(part * S::klen) * N) + q;
+#pragma unroll
+  for (int k = 0; k < S::klen; ++k) sl.w[k] = __ldg(wp + k * S::n4);
+}
+template <int N, int K>
+__device__ __forceinline__ void gemv_early_finish(const GemvSlice<N, K>& sl, const float* __restrict__ bias,
+                                                  const float* __restrict__ extra, const float* x_s, float* red_s, float* y_s) {
+  using S = GemvSlice<N, K>;
+  const int tid = threadIdx.x;
+  const int part = tid / S::n4, q = tid % S::n4;
+  const int kb = part * S::klen;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < S::klen; ++k) {
+    const float x = x_s[kb + k];
+    acc.x = fmaf(sl.w[k].x, x, acc.x); acc.y = fmaf(sl.w[k].y, x, acc.y);
+    acc.z = fmaf(sl.w[k].z, x, acc.z); acc.w = fmaf(sl.w[k].w, x, acc.w);
+  }
+  *reinterpret_cast<float4*>(red_s + part * N + q * 4) = acc;
+  __syncthreads();
+  if (tid < N) {
+    float s = bias ? bias[tid] : 0.f;
+    if (extra) s += extra[tid];
+#pragma unroll
+    for (int p = 0; p < S::parts; ++p) s += red_s[p * N + tid];
+    y_s[tid] = s;
+  }
+  __syncthreads();
+}
+
 // out[w][n] = bias[n] + sum_{taps} sum_ci Wt[(tap*Kc + ci)][n] * in(tap, w)[ci]  for all w < W, n < N.
 // `rows[t]` points at column 0 of the smem row (ci contiguous, Kc floats per column) tap t reads, or null (zero); `shift[t]` is
 // the column offset of tap t (|shift| <= PADW: the staged rows carry PADW zero columns on either side, so the inner loop has
@@ -349,6 +394,8 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
         }
         __syncthreads();
         if (a.prof && tid == 0) c1 = clock64();
+        GemvSlice<Hd, Hd> h2sl;
+        if (a.early) gemv_early_load<Hd, Hd>(Wt + a.off.h2_w[l], h2sl);   // conv1x1_2's slice travels with horiz_conv's
         cta_gemv_t<N2, N2>(Wt + a.off.horiz_w[l], hb_s + l * N2, v2h_s + l * N2, x_s, red_s, y_s);
         if (a.prof && tid == 0) c2 = clock64();
         // gated horizontal output: tanh(a) * tanh(b)  (sic)                      (pixelcnn.py:77)
@@ -363,7 +410,8 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
         __syncthreads();
         if (a.prof && tid == 0) c3 = clock64();
         // conv1x1_2 + residual                                                    (pixelcnn.py:80)
-        cta_gemv_t<Hd, Hd>(Wt + a.off.h2_w[l], h2b_s + l * Hd, cur_s, x_s, red_s, y_s);
+        if (a.early) gemv_early_finish<Hd, Hd>(h2sl, h2b_s + l * Hd, cur_s, x_s, red_s, y_s);
+        else cta_gemv_t<Hd, Hd>(Wt + a.off.h2_w[l], h2b_s + l * Hd, cur_s, x_s, red_s, y_s);
         if (tid < Hd) {
           cur_s[tid] = y_s[tid];
           Hs[((int64_t)(l + 1) * W + w) * Hd + tid] = y_s[tid];
@@ -491,6 +539,8 @@ extern "C" int igm_pixelcnn_run(const float* weights, float* img, const float* u
   a.seed = seed; a.N = N; a.C = C; a.H = H; a.W = W; a.Hd = Hd; a.mode = mode; a.normalize = normalize;
   const size_t smem = sizeof(float) * ((size_t)2 * (W + ROWX) * Hd + (size_t)2 * W * 2 * Hd + 2 * Hd + 256 + 1024 + Hd + 256 +
                                        (size_t)NLAYERS * (3 * 2 * Hd + 2 * Hd));
+  static const bool early_on = [] { const char* e = getenv("IGM_PCNN_EARLY"); return !(e && e[0] == '0'); }();
+  a.early = (early_on && Hd <= 64) ? 1 : 0;   // hidden_dim 128: 16 float4 per thread would spill
   static const bool prof_on = [] { const char* e = getenv("IGM_PCNN_PROF"); return e && e[0] == '1'; }();
   a.prof = prof_on ? 1 : 0;
   if (smem > 227 * 1024) IGM_FAIL(st, IGM_ERR_INVALID, "PixelCNN: image row too wide for this hidden_dim (shared memory)");
