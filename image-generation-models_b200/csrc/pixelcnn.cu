@@ -443,8 +443,17 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
         {
           float s = __ldg(Wt + a.off.out_b + (int64_t)tid * C + ch);
           const float* wp = Wt + a.off.out_w + (int64_t)tid * C + ch;
-#pragma unroll 16
-          for (int k = 0; k < Hd; ++k) s = fmaf(__ldg(wp + (int64_t)k * 256 * C), x_s[k], s);
+          // all weights of a 64-row block in flight before the first FMA (the 16-way unrolled form made four dependent L2
+          // round trips per logit); same summation order
+          constexpr int HB = Hd < 64 ? Hd : 64;
+#pragma unroll 1
+          for (int k0 = 0; k0 < Hd; k0 += HB) {
+            float wv[HB];
+#pragma unroll
+            for (int k = 0; k < HB; ++k) wv[k] = __ldg(wp + (int64_t)(k0 + k) * 256 * C);
+#pragma unroll
+            for (int k = 0; k < HB; ++k) s = fmaf(wv[k], x_s[k0 + k], s);
+          }
           lg_s[tid] = s;
           if (a.logits) a.logits[((((int64_t)n_img * 256 + tid) * C + ch) * H + h) * W + w] = s;
         }
