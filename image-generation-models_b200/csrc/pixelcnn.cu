@@ -159,7 +159,7 @@ __device__ __forceinline__ void gemv_early_finish(const GemvSlice<N, K>& sl, con
 }
 
 // out[w][n] = bias[n] + sum_{taps} sum_ci Wt[(tap*Kc + ci)][n] * in(tap, w)[ci]  for all w < W, n < N.
-// `rows[t]` points at column 0 of the smem row (ci contiguous, Kc floats per column) tap t reads, or null (zero); `shift[t]` is
+// `sm_base + row_off[t]` is column 0 of the smem row (ci contiguous, Kc floats per column) tap t reads (row_off < 0: zero row); `shift[t]` is
 // the column offset of tap t (|shift| <= PADW: the staged rows carry PADW zero columns on either side, so the inner loop has
 // no bounds test).  Register tile: a thread owns TWO adjacent output channels and PB = 7 positions (N / 2 thread columns x
 // 512 / N position groups); per 4 input channels that is 4 64-bit weight loads + 7 128-bit broadcast loads for 56 FMAs.
@@ -171,7 +171,7 @@ __device__ __forceinline__ void gemv_early_finish(const GemvSlice<N, K>& sl, con
 // version), and the weight loads of only two k-chunks were in flight.
 template <int N, int KC>
 __device__ __forceinline__ void cta_row_gemm_t(const float* __restrict__ Wt, const float* __restrict__ bias,
-                                               const float* const* rows, const int* shift, int ntaps, int W,
+                                               const float* sm_base, const int* row_off, const int* shift, int ntaps, int W,
                                                float* out_s /*[W][N]*/) {
   const int tid = threadIdx.x;
   constexpr int ncol = N >> 1;             // thread columns
@@ -184,8 +184,10 @@ __device__ __forceinline__ void cta_row_gemm_t(const float* __restrict__ Wt, con
 #pragma unroll
     for (int p = 0; p < PB; ++p) acc[p] = b2;
     for (int t = 0; t < ntaps; ++t) {
-      const float* row = rows[t];
-      if (!row) continue;
+      if (row_off[t] < 0) continue;
+      // offset from the kernel's shared-memory array, not a pointer out of a local array: a pointer of unknown address space
+      // made ptxas emit generic LD for the operand rows (ncu source page of the previous version) instead of LDS
+      const float* row = sm_base + row_off[t];
       const float* xp = row + (w0 + shift[t]) * KC;
       const float2* wp = reinterpret_cast<const float2*>(Wt + (size_t)t * KC * N + n0);
       // 16-row weight blocks, double-buffered in registers: the next block's loads are issued before the current block's
@@ -322,14 +324,14 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
       }
       __syncthreads();
       // vert_conv 3x3 dilated, rows ky = 0 (h-d), 1 (h); cols w-d, w, w+d      (pixelcnn.py:51-53)
-      const float* rows[6];
+      int rows[6];
       int shift[6];
       for (int ky = 0; ky < 2; ++ky)
         for (int kx = 0; kx < 3; ++kx) {
-          rows[ky * 3 + kx] = (ky == 0) ? (top_ok ? row0 : nullptr) : row1;
+          rows[ky * 3 + kx] = (ky == 0) ? (top_ok ? (int)(row0 - sm) : -1) : (int)(row1 - sm);
           shift[ky * 3 + kx] = (kx - 1) * d;
         }
-      cta_row_gemm_t<N2, Hd>(Wt + a.off.vert_w[l], Wt + a.off.vert_b[l], rows, shift, 6, W, vc_s);
+      cta_row_gemm_t<N2, Hd>(Wt + a.off.vert_w[l], Wt + a.off.vert_b[l], sm, rows, shift, 6, W, vc_s);
       // gated vertical output: tanh(a) * sigmoid(b)                            (pixelcnn.py:69)
       float* vout = Vc + (((int64_t)(l + 1) * H + h) * W) * Hd;
       for (int i = tid; i < W * Hd; i += 256) {
@@ -343,9 +345,9 @@ __global__ void __launch_bounds__(256, 1) pixelcnn_kernel(const PcnnArgs a) {
         vout[i] = tanhf(av) * (1.f / (1.f + expf(-bv)));
       }
       // v -> h link: conv1x1_1 on the PRE-gate features                         (pixelcnn.py:74)
-      const float* rows1[1] = {vc_s};
+      const int rows1[1] = {(int)(vc_s - sm)};
       const int shift1[1] = {0};
-      cta_row_gemm_t<N2, N2>(Wt + a.off.v2h_w[l], Wt + a.off.v2h_b[l], rows1, shift1, 1, W, t_s);
+      cta_row_gemm_t<N2, N2>(Wt + a.off.v2h_w[l], Wt + a.off.v2h_b[l], sm, rows1, shift1, 1, W, t_s);
       float* v2h = V2H + (int64_t)l * W * N2;
       for (int i = tid; i < W * N2 / 4; i += 256) reinterpret_cast<float4*>(v2h)[i] = reinterpret_cast<const float4*>(t_s)[i];
       __syncthreads();
