@@ -105,7 +105,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
                const __grid_constant__ CUtensorMap to_hi, const __grid_constant__ CUtensorMap to_lo, const TcArgs p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an OFFSET from the shared array (not through an integer): the pointer keeps its address space, so
+  // the epilogue's staging accesses compile to LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* store_stage = smem + C::STAGES * C::STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(store_stage + C::STORE_STAGE_BYTES);
   uint64_t* full = bars;                       // [STAGES]  TMA -> MMA

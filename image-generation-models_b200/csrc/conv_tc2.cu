@@ -143,7 +143,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant
                 const __grid_constant__ CUtensorMap to0, const __grid_constant__ CUtensorMap to1,
                 const __grid_constant__ CUtensorMap to_hi, const __grid_constant__ CUtensorMap to_lo, const PArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an OFFSET from the shared array (not through an integer): the pointer keeps its address space, so
+  // the epilogue's staging accesses compile to LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* store_stage = smem + STAGES * STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(store_stage + STORE_STAGE_BYTES);
   uint64_t* full = bars;                    // [STAGES]  both producers -> leader's MMA   (the peer's copy is unused)

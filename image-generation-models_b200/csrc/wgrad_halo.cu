@@ -109,7 +109,9 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap ts_hi, const __grid_consta
                   const __grid_constant__ CUtensorMap tp_hi, const __grid_constant__ CUtensorMap tp_lo,
                   const __grid_constant__ CUtensorMap tp1_hi, const __grid_constant__ CUtensorMap tp1_lo, const HArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an OFFSET from the shared array (not through an integer): the pointer keeps its address space, so
+  // the epilogue's staging accesses compile to LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + 4;

@@ -61,7 +61,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tdy_hi, const __grid_constan
   // tdy_* = the SHIFTED operand S (A blocks), tx_* / tx1_* = the PLAIN operand P (B blocks)
   using C = WCfg<NB>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an OFFSET from the shared array (not through an integer): the pointer keeps its address space, so
+  // the epilogue's staging accesses compile to LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + C::STAGES;
